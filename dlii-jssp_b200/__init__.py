@@ -1,0 +1,18 @@
+"""dlii_jssp_b200 - B200 (sm_100a) implementation of the DLII-JSSP jerk-space sampling planner's per-cycle candidate
+evaluation, behind the reference's own planner interface.
+
+The package directory is ``dlii-jssp_b200/`` (not an importable name); ``import dlii_jssp_b200`` resolves to it through
+the one-line shim module ``dlii_jssp_b200.py`` at the repository root.  All compute goes through ``libjssp_b200.so``
+(include/jssp_b200.h); there is no CPU fallback - importing the engine without the library or a GPU raises.
+"""
+from . import _lib
+from ._lib import JsspError, TRAJ_COLUMNS, STATE_COLUMNS
+from .engine import JsspConfig, JsspEngine, CycleResult
+from .frenet import State, FrenetState, JerkSpaceSamplingFrenetTrajectory, Vehicle
+from .geometry import CubicSpline2D, QuinticPolynomial, spline_tables
+from .planner import (JerkSpaceSamplingPlanner, JerkSpaceSamplingPlannerSettings, IntersectionPlanner, PlannerSettings)
+from . import scenario
+
+__all__ = ["JsspConfig", "JsspEngine", "CycleResult", "JsspError", "State", "FrenetState", "JerkSpaceSamplingFrenetTrajectory", "Vehicle",
+           "CubicSpline2D", "QuinticPolynomial", "spline_tables", "JerkSpaceSamplingPlanner", "JerkSpaceSamplingPlannerSettings",
+           "IntersectionPlanner", "PlannerSettings", "scenario", "TRAJ_COLUMNS", "STATE_COLUMNS"]

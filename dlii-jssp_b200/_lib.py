@@ -1,0 +1,114 @@
+"""ctypes binding of include/jssp_b200.h.  Fails loudly when the library is missing: there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+JSSP_MAX_WIDTHS = 16
+JSSP_TRAJ_COLS = 16
+JSSP_STATE_COLS = 8
+FLAG_NO_SYNC = 1
+FLAG_NO_EXPORT = 2
+
+TRAJ_COLUMNS = ("t", "s", "s_d", "s_dd", "s_ddd", "d", "d_d", "d_dd", "d_ddd", "x", "y", "yaw", "ds", "c", "c_d", "c_dd")
+STATE_COLUMNS = ("s", "s_d", "s_dd", "d", "x", "y", "yaw", "c")
+
+
+class JsspConfigC(C.Structure):
+    _fields_ = [
+        ("delta_t", C.c_double), ("plan_horizon", C.c_double), ("max_road_width", C.c_double),
+        ("num_width", C.c_int32), ("num_jerk", C.c_int32), ("highest_jerk", C.c_double),
+        ("speed_max", C.c_double), ("lon_accel_max", C.c_double),
+        ("ego_length", C.c_double), ("ego_width", C.c_double),
+        ("max_curvature", C.c_double), ("obstacle_inflation", C.c_double),
+        ("check_res", C.c_int32), ("reserved0", C.c_int32),
+        ("cost_weights", C.c_double * 8), ("max_distance", C.c_double),
+        ("thr_lon_accel", C.c_double), ("thr_lon_jerk", C.c_double), ("thr_lat_accel", C.c_double), ("thr_lat_jerk", C.c_double),
+        ("p_min", C.c_double), ("w_risk", C.c_double),
+        ("max_seeds", C.c_int32), ("max_knots", C.c_int32), ("max_obstacle_modes", C.c_int32), ("max_total_steps", C.c_int32),
+    ]
+
+
+class JsspCycleIn(C.Structure):
+    _fields_ = [
+        ("s0", C.c_double), ("v0", C.c_double), ("a0", C.c_double),
+        ("d0", C.c_double), ("d_d0", C.c_double), ("d_dd0", C.c_double),
+        ("time_step_now", C.c_int32), ("final_time_step", C.c_int32), ("n_widths", C.c_int32), ("flags", C.c_int32),
+        ("targets", C.c_double * JSSP_MAX_WIDTHS),
+        ("seeds_dev", C.c_void_p), ("n_seeds", C.c_int32), ("reserved0", C.c_int32),
+    ]
+
+
+class JsspCycleOut(C.Structure):
+    _fields_ = [
+        ("feasible_dev", C.c_void_p), ("collision_dev", C.c_void_p), ("cost_dev", C.c_void_p), ("states_dev", C.c_void_p),
+        ("best_traj_host", C.c_void_p),
+        ("n_candidates", C.c_int32), ("best_idx", C.c_int32), ("best_n_pts", C.c_int32), ("n_seeds", C.c_int32),
+        ("best_cost", C.c_double),
+    ]
+
+
+class JsspImmParams(C.Structure):
+    _fields_ = [("dt", C.c_double), ("q_pos", C.c_double), ("q_vel", C.c_double), ("r_pos", C.c_double),
+                ("k_lat", C.c_double), ("p_stay", C.c_double), ("mu_floor", C.c_double)]
+
+
+# every symbol include/jssp_b200.h declares (tests check that the library exports exactly these)
+SYMBOLS = {
+    "jssp_abi_version": (C.c_int32, []),
+    "jssp_strerror": (C.c_char_p, [C.c_int32]),
+    "jssp_last_cuda_error": (C.c_char_p, [C.c_void_p]),
+    "jssp_default_config": (None, [C.POINTER(JsspConfigC)]),
+    "jssp_create": (C.c_int32, [C.POINTER(JsspConfigC), C.c_int32, C.POINTER(C.c_void_p)]),
+    "jssp_destroy": (C.c_int32, [C.c_void_p]),
+    "jssp_make_grids": (C.c_int32, [C.c_double, C.c_double, C.c_int32, C.c_int32] + [C.c_void_p] * 9 + [C.POINTER(C.c_int32 * 9)]),
+    "jssp_quintic_coeffs": (None, [C.c_double] * 7 + [C.POINTER(C.c_double * 6)]),
+    "jssp_set_refline": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "jssp_set_obstacles": (C.c_int32, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_void_p]),
+    "jssp_set_obstacles_dev": (C.c_int32, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_void_p]),
+    "jssp_enumerate_seeds": (C.c_int32, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "jssp_get_seeds": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_void_p]),
+    "jssp_evaluate": (C.c_int32, [C.c_void_p, C.POINTER(JsspCycleIn), C.c_void_p, C.POINTER(JsspCycleOut)]),
+    "jssp_fetch_best": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(JsspCycleOut)]),
+    "jssp_best_record_dev": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "jssp_launch_count": (C.c_int64, [C.c_void_p]),
+    "jssp_imm_update": (C.c_int32, [C.c_void_p, C.POINTER(JsspImmParams)] + [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_void_p]),
+    "jssp_predict_modes": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """Load libjssp_b200.so (building it in-tree with nvcc when absent).  Raises - never falls back to a CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise RuntimeError(f"{path} is missing: build it with `python -m dlii_jssp_b200.build` (no CPU fallback exists)")
+        _build.build_library()
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)      # AttributeError here = the library does not export what the header declares
+        fn.restype = res
+        fn.argtypes = args
+    if lib.jssp_abi_version() != 1:
+        raise RuntimeError("libjssp_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+class JsspError(RuntimeError):
+    def __init__(self, status: int, where: str, detail: str = ""):
+        self.status = status
+        msg = load().jssp_strerror(status).decode()
+        super().__init__(f"{where}: {msg} [{status}]" + (f" ({detail})" if detail else ""))

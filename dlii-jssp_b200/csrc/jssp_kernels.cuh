@@ -1,0 +1,767 @@
+// jssp_kernels.cuh - sm_100a kernels of the JSSP candidate evaluation (included by jssp_b200.cu only).
+//
+//   K1  seed_flag_main / seed_flag_stop / seed_sort_emit   polyvt_sampling.py:167-305
+//   K2  evaluate_kernel (unroll -> Frenet->Cartesian -> heading/curvature -> feasibility -> rectangle collision
+//       against every obstacle mode -> cost -> block argmin -> last-block global argmin)
+//                                                           polyvt_sampling.py:311-385, jerk_space_sampling_planner.py:131-294,326-327
+//   K3  export_best_kernel / dump_states_kernel            consumers listed in SURVEY.md section 8 a12
+//   K0  pack_obstacles_kernel                               obstacle dict -> device tables
+//   K4  imm_update_kernel / predict_modes_kernel            builder-specified (no reference code)
+#pragma once
+#include "jssp_device.cuh"
+#include "../../include/jssp_b200.h"
+
+namespace jssp {
+
+constexpr int EVAL_THREADS = 128;
+constexpr float SAT_EPS = 2e-3f;        // fp32 guard band [m]; inside it the pair is re-decided in float64
+constexpr float FAR_AWAY = 1e30f;       // x of an absent obstacle state: squared distance overflows to +inf -> culled
+
+struct BestRecord {
+  unsigned long long key;   // orderable_bits(cost)
+  long long idx;            // candidate index (+ offset for candidate-split runs), -1 = none
+  double cost;
+  int n_pts;
+  int n_candidates;
+  int n_seeds;
+  int pad;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk copy (TMA engine, SASS UBLKCP)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1: seed enumeration.  One thread per point of the flat grid; survivors append their flat index, a single block
+// sorts the (few) indices so that the emitted order is the reference's nested-loop order, then decodes them.
+// ------------------------------------------------------------------------------------------------------------------
+struct SeedGrids {
+  const double *j1, *t1, *t2, *j3, *t3, *t4;  // main grid axes (loop order j1, t1, t2, j3, t3, t4)
+  int n_j1, n_t1, n_t2, n_j3, n_t3, n_t4;
+  const double *jneg, *jpos, *ts;             // stop grid axes (j1 <= 0, t1, j2 >= 0, t2)
+  int n_jneg, n_jpos, n_ts;
+  double total_time, acc_max, vel_max, v_max, jmin5, jmax5;
+  double lim2, lim3, lim4;                    // total - 0.8*3, total - 1.0*2, total - 1.5 (host-computed, same ops)
+};
+
+struct SeedState { double s0, v0, a0; };
+
+__device__ __forceinline__ bool main_seed_ok(const SeedGrids& g, const SeedState& st, double j1, double t1, double t2,
+                                             double j3, double t3, double t4, double& j5, double& t5) {
+  const double T = g.total_time;
+  if (t1 < 0.55) return false;                                                           // polyvt_sampling.py:183
+  const double s1 = st_by_jt(st.s0, st.v0, st.a0, j1, t1), v1 = vt_by_jt(st.v0, st.a0, j1, t1), a1 = at_by_jt(st.a0, j1, t1);
+  if (!check_state(s1, v1, a1, st.s0, g.acc_max, g.vel_max)) return false;               // :190
+  if (t1 + t2 >= g.lim2) return false;                                                   // :195
+  const double s2 = st_by_jt(s1, v1, a1, 0.0, t2), v2 = vt_by_jt(v1, a1, 0.0, t2), a2 = at_by_jt(a1, 0.0, t2);
+  if (!check_state(s2, v2, a2, s1, g.acc_max, g.vel_max)) return false;                  // :202
+  if (t1 + t2 > T + 1e-9) return false;                                                  // :205
+  if (j3 * j1 > 0) return false;                                                         // :209
+  if (t1 + t2 + t3 > g.lim3) return false;                                               // :213
+  const double s3 = st_by_jt(s2, v2, a2, j3, t3), v3 = vt_by_jt(v2, a2, j3, t3), a3 = at_by_jt(a2, j3, t3);
+  if (!check_state(s3, v3, a3, s2, g.acc_max, g.vel_max)) return false;                  // :220
+  if (a3 * a1 > 0) return false;                                                         // :223
+  if (a3 * a2 < 0) {                                                                     // :226-230
+    const double t25 = (0.0 - a2) / j3;
+    const double v25 = vt_by_jt(v2, a2, j3, t25);
+    if (v25 > g.v_max || v25 < 0.0 + 1e-9) return false;
+  }
+  if (t1 + t2 + t3 + t4 > g.lim4) return false;                                          // :234
+  const double s4 = st_by_jt(s3, v3, a3, 0.0, t4), v4 = vt_by_jt(v3, a3, 0.0, t4), a4 = at_by_jt(a3, 0.0, t4);
+  if (!check_state(s4, v4, a4, s3, g.acc_max, g.vel_max)) return false;                  // :241
+  t5 = T - t1 - t2 - t3 - t4;
+  j5 = (0.0 - a4) / t5;
+  if (j5 > g.jmax5 || j5 < g.jmin5) return false;                                        // :246
+  const double s5 = st_by_jt(s4, v4, a4, j5, t5), v5 = vt_by_jt(v4, a4, j5, t5), a5 = at_by_jt(a4, j5, t5);
+  return check_state(s5, v5, a5, s4, g.acc_max, g.vel_max);                              // :252
+}
+
+__device__ __forceinline__ void decode_main(const SeedGrids& g, uint32_t f, double& j1, double& t1, double& t2, double& j3,
+                                            double& t3, double& t4) {
+  uint32_t r = f;
+  const uint32_t i4 = r % g.n_t4; r /= g.n_t4;
+  const uint32_t i3 = r % g.n_t3; r /= g.n_t3;
+  const uint32_t ij3 = r % g.n_j3; r /= g.n_j3;
+  const uint32_t i2 = r % g.n_t2; r /= g.n_t2;
+  const uint32_t i1 = r % g.n_t1; r /= g.n_t1;
+  j1 = g.j1[r]; t1 = g.t1[i1]; t2 = g.t2[i2]; j3 = g.j3[ij3]; t3 = g.t3[i3]; t4 = g.t4[i4];
+}
+
+__global__ void seed_flag_main(SeedGrids g, SeedState st, uint32_t total, uint32_t* __restrict__ list, int* __restrict__ counts,
+                               int cap) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= total) return;
+  double j1, t1, t2, j3, t3, t4, j5, t5;
+  decode_main(g, f, j1, t1, t2, j3, t3, t4);
+  if (main_seed_ok(g, st, j1, t1, t2, j3, t3, t4, j5, t5)) {
+    const int pos = atomicAdd(&counts[0], 1);
+    if (pos < cap) list[pos] = f; else counts[3] = 1;
+  }
+}
+
+__device__ __forceinline__ void decode_stop(const SeedGrids& g, uint32_t f, double& j1, double& t1, double& j2, double& t2) {
+  uint32_t r = f;
+  const uint32_t i2 = r % g.n_ts; r /= g.n_ts;
+  const uint32_t ij2 = r % g.n_jpos; r /= g.n_jpos;
+  const uint32_t i1 = r % g.n_ts; r /= g.n_ts;
+  j1 = g.jneg[r]; t1 = g.ts[i1]; j2 = g.jpos[ij2]; t2 = g.ts[i2];
+}
+
+__global__ void seed_flag_stop(SeedGrids g, SeedState st, uint32_t total, uint32_t* __restrict__ list, int* __restrict__ counts,
+                               int cap) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= total) return;
+  double j1, t1, j2, t2;
+  decode_stop(g, f, j1, t1, j2, t2);
+  const double s1 = st_by_jt(st.s0, st.v0, st.a0, j1, t1), v1 = vt_by_jt(st.v0, st.a0, j1, t1), a1 = at_by_jt(st.a0, j1, t1);
+  if (!check_state(s1, v1, a1, st.s0, g.acc_max, g.vel_max)) return;                     // :283
+  if (t1 + t2 >= g.total_time) return;                                                   // :291
+  const double a2 = at_by_jt(a1, j2, t2);
+  if (a2 > 0.0 || a2 < -0.3) return;                                                     // :293
+  const double v2 = vt_by_jt(v1, a1, j2, t2);
+  if (v2 > 0.0 || v2 < -0.3) return;                                                     // :296
+  const double s2 = st_by_jt(s1, v1, a1, j2, t2);
+  if (s2 < s1 - 0.1) return;                                                             // :299
+  const int pos = atomicAdd(&counts[1], 1);
+  if (pos < cap) list[pos] = f; else counts[3] = 1;
+}
+
+// bitonic sort of n <= SORT_CAP keys held in shared memory (padding = 0xffffffff)
+constexpr int SORT_CAP = 8192;
+__device__ void bitonic_sort_smem(uint32_t* key, int npow2) {
+  for (int k = 2; k <= npow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint32_t a = key[i], b = key[ixj];
+          const bool up = ((i & k) == 0);
+          if ((a > b) == up) { key[i] = b; key[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// counts: [0] main found, [1] stop found, [2] total emitted, [3] overflow flag
+__global__ void __launch_bounds__(1024) seed_sort_emit(SeedGrids g, SeedState st, const uint32_t* __restrict__ list_main,
+                                                       const uint32_t* __restrict__ list_stop, int* __restrict__ counts,
+                                                       double* __restrict__ seeds, int cap_list, int cap_seeds) {
+  __shared__ uint32_t key[SORT_CAP];
+  const int n_main = min(counts[0], cap_list), n_stop = min(counts[1], cap_list);
+  int emitted = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int n = pass == 0 ? n_main : n_stop;
+    const uint32_t* list = pass == 0 ? list_main : list_stop;
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) key[i] = i < n ? list[i] : 0xffffffffu;
+    __syncthreads();
+    bitonic_sort_smem(key, np2);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int row = emitted + i;
+      if (row >= cap_seeds) continue;
+      double* o = seeds + (size_t)row * 10;
+      if (pass == 0) {
+        double j1, t1, t2, j3, t3, t4, j5 = 0, t5 = 0;
+        decode_main(g, key[i], j1, t1, t2, j3, t3, t4);
+        main_seed_ok(g, st, j1, t1, t2, j3, t3, t4, j5, t5);   // recompute j5, t5 with identical arithmetic
+        o[0] = j1; o[1] = t1; o[2] = 0.0; o[3] = t2; o[4] = j3; o[5] = t3; o[6] = 0.0; o[7] = t4; o[8] = j5; o[9] = t5;
+      } else {
+        double j1, t1, j2, t2;
+        decode_stop(g, key[i], j1, t1, j2, t2);
+        o[0] = j1; o[1] = t1; o[2] = j2; o[3] = t2; o[4] = 0.0; o[5] = g.total_time - t1 - t2;   // :302
+        o[6] = 0.0; o[7] = 0.0; o[8] = 0.0; o[9] = 0.0;
+      }
+    }
+    __syncthreads();
+    emitted += n;
+  }
+  if (threadIdx.x == 0) {
+    if (emitted > cap_seeds) { counts[3] = 1; emitted = cap_seeds; }
+    counts[2] = emitted;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K0: obstacle tables.  raw state [OM][Tt][3] (x, y, yaw), valid [OM][Tt] ->
+//   broad  [Tt][OM] float4 = (x - ox, y - oy, (r_ego + r_obs + pad)^2, prob)      (FAR_AWAY when absent)
+//   narrow [Tt][OM] float4 = (cos yaw, sin yaw, half length + infl/2, half width + infl/2)
+//   obs64  [Tt][OM][4]     = x, y, cos yaw, sin yaw in float64 for the guard-band re-decision
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void pack_obstacles_kernel(const double* __restrict__ state, const uint8_t* __restrict__ valid,
+                                      const double* __restrict__ size, const double* __restrict__ prob, int OM, int M, int Tt,
+                                      double ox, double oy, double inflation, double r_ego, float4* __restrict__ broad,
+                                      float4* __restrict__ narrow, double* __restrict__ obs64, double* __restrict__ ext64) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // idx = t * OM + om
+  if (idx >= OM * Tt) return;
+  const int t = idx / OM, om = idx - t * OM, o = om / M;
+  const double a2 = (size[2 * o] + inflation) / 2.0, b2 = (size[2 * o + 1] + inflation) / 2.0;
+  if (t == 0) { ext64[2 * om] = a2; ext64[2 * om + 1] = b2; }
+  const double* s = state + ((size_t)om * Tt + t) * 3;
+  const bool ok = valid[(size_t)om * Tt + t] != 0;
+  double sn, cs;
+  sincos(s[2], &sn, &cs);
+  const float r = (float)(r_ego + sqrt(a2 * a2 + b2 * b2)) + 0.05f;
+  broad[idx] = make_float4(ok ? (float)(s[0] - ox) : FAR_AWAY, ok ? (float)(s[1] - oy) : FAR_AWAY, r * r * 1.0001f,
+                           (float)prob[om]);
+  narrow[idx] = make_float4((float)cs, (float)sn, (float)a2, (float)b2);
+  double* q = obs64 + (size_t)idx * 4;
+  q[0] = s[0]; q[1] = s[1]; q[2] = cs; q[3] = sn;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2: candidate evaluation
+// ------------------------------------------------------------------------------------------------------------------
+struct EvalParams {
+  // cycle
+  double s0, v0, a0;
+  double quintic[JSSP_MAX_WIDTHS][6];
+  int W, P, now, tcap;            // tcap = final_time_step - time_step_now
+  int n_dict, check_res;
+  // constants
+  double kmax, ea, eb, p_min, w_risk, vmax, max_distance, half_w, thr_lon_a, thr_lon_j, thr_lat_a, thr_lat_j;
+  double cw[8];
+  // tables
+  const double* time;
+  const double* knot;
+  const double* coef;
+  int K, kpad;
+  double ox, oy;
+  const double* seeds;
+  const int* n_seeds_ptr;         // device count (enumerated seeds) or NULL
+  int n_seeds_fixed, seed_cap;
+  // obstacles
+  const float4* broad;
+  const float4* narrow;
+  const double* obs64;
+  const double* ext64;
+  int OM, Tt, win_rows, smem_obs;
+  // outputs
+  uint8_t* feasible;
+  uint8_t* collision;
+  float* cost;
+  double* blk_cost;
+  int* blk_idx;
+  unsigned int* ticket;
+  BestRecord* best;
+};
+
+struct BlockTables {
+  const float4* broad;   // window rows [win_rows][OM] (shared) or the global table
+  int broad_row0;        // 0 for the shared window, time_step_now for the global table
+  int broad_stride;      // rows advance by check_res in the global table, 1 in the window
+  SplineView sp;
+  const double* time;
+  const double* lat;     // [W][P][4]
+};
+
+// Walks one candidate through the horizon and hands every derived quantity to `sink`, in the order the reference
+// derives them (get_one_frenet_trajectory -> calc_global_paths).  Used by the evaluation, export and dump kernels so
+// that all three see identical arithmetic.
+//   sink.sample(i, t, s, sd, sdd, sddd)                      every i in [0, P)
+//   sink.point(i, x, y)                                      i < n_pts
+//   sink.segment(i, x_i, y_i, dx, dy, yaw_i, ds_i)           i < n_pts - 1  (yaw_i = atan2(dy, dx), forward difference)
+//   sink.curvature(i, dyaw, ds_i)                            i < n_pts - 2  (c_i = dyaw / ds_i, no unwrapping)
+//   sink.finish(n_pts, x_L, y_L, yaw_{L-1}, cos, sin, ds_{L-1})   once; L = n_pts - 1
+template <class Sink>
+__device__ __forceinline__ void walk_candidate(const EvalParams& p, const BlockTables& tb, const LonProfile& lp, int w,
+                                               int seg, Sink& sink) {
+  const int P = p.P;
+  const double* lat = tb.lat + (size_t)w * P * 4;
+  bool live = true;
+  int n_pts = P;
+  double xp = 0, yp = 0, thp = 0, dsp = 0, cp = 1, sp_ = 0;
+  for (int i = 0; i < P; ++i) {
+    const double t = tb.time[i];
+    double s, sd, sdd, sddd;
+    lon_eval(lp, p.s0, p.v0, p.a0, t, s, sd, sdd, sddd);
+    sink.sample(i, t, s, sd, sdd, sddd);
+    if (!live) continue;
+    if (!spline_in_range(tb.sp, s)) {   // calc_position returned None -> break (jerk_space_sampling_planner.py:138-139)
+      live = false;
+      n_pts = i;
+      continue;
+    }
+    seg = spline_walk(tb.sp, s, seg);
+    double x, y;
+    frenet_point(tb.sp, seg, s, lat[i * 4], x, y);
+    sink.point(i, x, y);
+    if (i >= 1) {
+      const double dx = x - xp, dy = y - yp;
+      const double th = atan2(dy, dx);
+      const double ds = hypot_safe(dx, dy);
+      double c = 1.0, sn = 0.0;           // atan2(0, 0) = 0 -> axis-aligned box when the car does not move
+      if (ds > 0.0) { const double inv = 1.0 / ds; c = dx * inv; sn = dy * inv; }
+      if (i >= 2) sink.curvature(i - 2, th - thp, dsp);
+      sink.segment(i - 1, xp, yp, dx, dy, th, ds, c, sn);
+      thp = th; dsp = ds; cp = c; sp_ = sn;
+    }
+    xp = x; yp = y;
+  }
+  sink.finish(n_pts, xp, yp, thp, cp, sp_, dsp);
+}
+
+// -- the evaluation sink ---------------------------------------------------------------------------------------------
+struct EvalSink {
+  const EvalParams& p;
+  const BlockTables& tb;
+  double sum_a = 0, sum_j = 0, sum_v = 0, s_first = 0, s_last = 0, risk = 0;
+  bool curv_fail = false, collided = false;
+  __device__ __forceinline__ EvalSink(const EvalParams& p_, const BlockTables& tb_) : p(p_), tb(tb_) {}
+
+  __device__ __forceinline__ void sample(int i, double, double s, double sd, double sdd, double sddd) {
+    if (i == 0) s_first = s;
+    s_last = s;
+    const double ea = fmax(fabs(sdd) - p.thr_lon_a, 0.0);
+    const double ej = fmax(fabs(sddd) - p.thr_lon_j, 0.0);
+    const double ev = (p.vmax - sd) / p.vmax;
+    sum_a = sum_a + ea * ea;
+    sum_j = sum_j + ej * ej;
+    sum_v = sum_v + ev * ev;
+  }
+  __device__ __forceinline__ void point(int, double, double) {}
+  __device__ __forceinline__ void curvature(int, double dyaw, double ds) {
+    // |dyaw / ds| > kmax  (jerk_space_sampling_planner.py:175); ds == 0: inf fails, nan passes
+    if (fabs(dyaw) > p.kmax * ds) curv_fail = true;
+  }
+  __device__ __forceinline__ void collide(int i, double x, double y, double c, double sn) {
+    if (collided || p.n_dict <= 0 || i >= p.tcap || (i % p.check_res) != 0) return;
+    const int abs_step = p.now + i;
+    if (abs_step >= p.Tt) return;
+    const int r = i / p.check_res;
+    const float4* row = tb.broad + (size_t)(tb.broad_row0 + r * tb.broad_stride) * p.OM;
+    const float fx = (float)(x - p.ox), fy = (float)(y - p.oy), fc = (float)c, fs = (float)sn;
+    const float fea = (float)p.ea, feb = (float)p.eb;
+#pragma unroll 4
+    for (int om = 0; om < p.OM; ++om) {
+      const float4 b = row[om];
+      const float dx = b.x - fx, dy = b.y - fy;
+      const float d2 = fmaf(dx, dx, dy * dy);
+      if (d2 <= b.z) {
+        const size_t gi = (size_t)abs_step * p.OM + om;
+        const float4 nb = __ldg(p.narrow + gi);
+        const int cls = sat_classify_f32(dx, dy, fc, fs, fea, feb, nb.x, nb.y, nb.z, nb.w, SAT_EPS);
+        bool hit = cls < 0;
+        if (cls == 0) {
+          const double* q = p.obs64 + gi * 4;
+          hit = sat_intersects_f64(q[0] - x, q[1] - y, c, sn, p.ea, p.eb, q[2], q[3], p.ext64[2 * om], p.ext64[2 * om + 1]);
+        }
+        if (hit) {
+          if ((double)b.w >= p.p_min) { collided = true; break; }
+          risk = risk + (double)b.w;
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void segment(int i, double x, double y, double, double, double, double, double c, double sn) {
+    collide(i, x, y, c, sn);
+  }
+  __device__ __forceinline__ void finish(int n_pts, double x, double y, double, double c, double sn, double) {
+    if (n_pts >= 2) collide(n_pts - 1, x, y, c, sn);   // last point reuses the previous heading (:158-160)
+    else if (n_pts == 1 && p.n_dict > 0 && p.tcap >= 1) collided = true;   // bare except -> collision (:250-254)
+  }
+};
+
+__device__ __forceinline__ double candidate_cost(const EvalParams& p, const EvalSink& k, const double* latcost) {
+  const double P = (double)p.P;
+  double cost = p.cw[1] * (1.0 - (k.s_last - k.s_first) / p.max_distance);
+  cost = cost + p.cw[2] * (latcost[0] / P / (p.half_w * p.half_w));
+  cost = cost + p.cw[3] * (latcost[1] / P);
+  cost = cost + p.cw[4] * (latcost[2] / P);
+  cost = cost + p.cw[5] * (k.sum_a / P);
+  cost = cost + p.cw[6] * (k.sum_j / P);
+  cost = cost + p.cw[7] * (k.sum_v / P);
+  cost = cost + p.w_risk * k.risk;
+  return cost;
+}
+
+// dynamic shared memory carve-up (host mirrors this in eval_smem_bytes)
+struct SmemLayout {
+  size_t off_broad, off_knot, off_coef, off_time, off_lat, off_latcost, total;
+};
+__host__ __device__ inline SmemLayout eval_smem_layout(int win_rows, int OM, int smem_obs, int K, int kpad, int P, int W) {
+  SmemLayout L;
+  size_t o = 16;   // mbarrier
+  L.off_broad = o; o += smem_obs ? (size_t)win_rows * OM * 16 : 0;
+  L.off_knot = o; o += (size_t)((K + 1) & ~1) * 8;
+  L.off_coef = o; o += (size_t)8 * kpad * 8;
+  L.off_time = o; o += (size_t)((P + 1) & ~1) * 8;
+  L.off_lat = o; o += (size_t)W * P * 4 * 8;
+  L.off_latcost = o; o += (size_t)W * 4 * 8;
+  L.total = o;
+  return L;
+}
+
+// Stage the per-block tables: obstacle window by bulk copy (one row per issued copy, all on one mbarrier), spline,
+// time grid and the lateral quintic samples (jerk_space_sampling_planner.py:118-122) by ordinary loads.
+__device__ __forceinline__ void stage_tables(const EvalParams& p, unsigned char* smem, BlockTables& tb, const double*& latcost) {
+  const SmemLayout L = eval_smem_layout(p.win_rows, p.OM, p.smem_obs, p.K, p.kpad, p.P, p.W);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  float4* sm_broad = reinterpret_cast<float4*>(smem + L.off_broad);
+  double* sm_knot = reinterpret_cast<double*>(smem + L.off_knot);
+  double* sm_coef = reinterpret_cast<double*>(smem + L.off_coef);
+  double* sm_time = reinterpret_cast<double*>(smem + L.off_time);
+  double* sm_lat = reinterpret_cast<double*>(smem + L.off_lat);
+  double* sm_latcost = reinterpret_cast<double*>(smem + L.off_latcost);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const uint32_t row_bytes = (uint32_t)p.OM * 16u;
+  int rows_avail = 0;
+  if (p.smem_obs) {
+    // rows of the window that exist in the scenario table: absolute step now + r*check_res < Tt
+    for (int r = 0; r < p.win_rows; ++r) rows_avail += (p.now + r * p.check_res < p.Tt) ? 1 : 0;
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid < 32) {
+      if (tid == 0) mbar_arrive_expect_tx(bar, row_bytes * (uint32_t)rows_avail);
+      __syncwarp();
+      for (int r = tid; r < rows_avail; r += 32)
+        bulk_copy_g2s(sm_broad + (size_t)r * p.OM, p.broad + (size_t)(p.now + r * p.check_res) * p.OM, row_bytes, bar);
+    }
+    for (int e = rows_avail * p.OM + tid; e < p.win_rows * p.OM; e += nt) sm_broad[e] = make_float4(FAR_AWAY, FAR_AWAY, 0.f, 0.f);
+  }
+  for (int e = tid; e < p.K; e += nt) sm_knot[e] = p.knot[e];
+  for (int e = tid; e < 8 * p.kpad; e += nt) sm_coef[e] = p.coef[e];
+  for (int e = tid; e < p.P; e += nt) sm_time[e] = p.time[e];
+  __syncthreads();
+  for (int e = tid; e < p.W * p.P; e += nt) {
+    const int w = e / p.P, i = e - w * p.P;
+    double d, d1, d2, d3;
+    quintic_eval(p.quintic[w], sm_time[i], d, d1, d2, d3);
+    double* o = sm_lat + (size_t)e * 4;
+    o[0] = d; o[1] = d1; o[2] = d2; o[3] = d3;
+  }
+  __syncthreads();
+  if (tid < p.W) {   // per-width lateral cost sums, sequential in time like the oracle
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int i = 0; i < p.P; ++i) {
+      const double* o = sm_lat + ((size_t)tid * p.P + i) * 4;
+      const double e1 = fmax(fabs(o[2]) - p.thr_lat_a, 0.0), e2 = fmax(fabs(o[3]) - p.thr_lat_j, 0.0);
+      s0 = s0 + o[0] * o[0]; s1 = s1 + e1 * e1; s2 = s2 + e2 * e2;
+    }
+    sm_latcost[tid * 4] = s0; sm_latcost[tid * 4 + 1] = s1; sm_latcost[tid * 4 + 2] = s2;
+  }
+  __syncthreads();
+  if (p.smem_obs) {
+    if (rows_avail > 0) mbar_wait(bar, 0);
+    tb.broad = sm_broad; tb.broad_row0 = 0; tb.broad_stride = 1;
+  } else {
+    tb.broad = p.broad; tb.broad_row0 = p.now; tb.broad_stride = p.check_res;
+  }
+  tb.sp.knot = sm_knot; tb.sp.coef = sm_coef; tb.sp.K = p.K; tb.sp.kpad = p.kpad;
+  tb.time = sm_time; tb.lat = sm_lat;
+  latcost = sm_latcost;
+}
+
+__device__ __forceinline__ int resolve_n_seeds(const EvalParams& p) {
+  return p.n_seeds_ptr ? min(p.n_seeds_ptr[2], p.seed_cap) : p.n_seeds_fixed;
+}
+
+__device__ __forceinline__ bool lex_less(double ca, int ia, double cb, int ib) {
+  // (cost, index) lexicographic; index -1 = empty
+  if (ib < 0) return ia >= 0;
+  if (ia < 0) return false;
+  return ca < cb || (ca == cb && ia < ib);
+}
+
+__global__ void __launch_bounds__(EVAL_THREADS) evaluate_kernel(const __grid_constant__ EvalParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ double red_cost[EVAL_THREADS / 32];
+  __shared__ int red_idx[EVAL_THREADS / 32];
+  __shared__ bool is_last;
+  const int Ns = resolve_n_seeds(p);
+  const int N = Ns * p.W;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  double my_cost = INFINITY;
+  int my_idx = -1;
+  if (blockIdx.x * blockDim.x < N) {   // block-uniform
+    BlockTables tb;
+    const double* latcost;
+    stage_tables(p, smem, tb, latcost);
+    if (n < N) {
+      const int w = n / Ns, k = n - w * Ns;
+      LonProfile lp;
+      lon_profile_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
+      EvalSink sink(p, tb);
+      const int seg0 = spline_bisect(tb.sp, fmin(fmax(p.s0, tb.sp.knot[0]), tb.sp.knot[p.K - 1]));
+      walk_candidate(p, tb, lp, w, seg0, sink);
+      const double cost = candidate_cost(p, sink, latcost + w * 4);
+      if (p.feasible) p.feasible[n] = sink.curv_fail ? 0 : 1;
+      if (p.collision) p.collision[n] = sink.collided ? 1 : 0;
+      if (p.cost) p.cost[n] = (float)cost;
+      if (!sink.curv_fail && !sink.collided && isfinite(cost)) { my_cost = cost; my_idx = n; }
+    }
+  }
+  // block argmin (cost, index) - warp shuffles, then one value per warp through shared memory
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oc = __shfl_down_sync(0xffffffffu, my_cost, o);
+    const int oi = __shfl_down_sync(0xffffffffu, my_idx, o);
+    if (lex_less(oc, oi, my_cost, my_idx)) { my_cost = oc; my_idx = oi; }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { red_cost[wid] = my_cost; red_idx[wid] = my_idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < EVAL_THREADS / 32; ++q)
+      if (lex_less(red_cost[q], red_idx[q], my_cost, my_idx)) { my_cost = red_cost[q]; my_idx = red_idx[q]; }
+    p.blk_cost[blockIdx.x] = my_cost;
+    p.blk_idx[blockIdx.x] = my_idx;
+    __threadfence();
+    const unsigned int t = atomicAdd(p.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  // the last block to finish reduces the per-block winners: deterministic, no floating-point atomics
+  __threadfence();
+  my_cost = INFINITY; my_idx = -1;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+    const double c = __ldcg(p.blk_cost + b);
+    const int i = __ldcg(p.blk_idx + b);
+    if (lex_less(c, i, my_cost, my_idx)) { my_cost = c; my_idx = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oc = __shfl_down_sync(0xffffffffu, my_cost, o);
+    const int oi = __shfl_down_sync(0xffffffffu, my_idx, o);
+    if (lex_less(oc, oi, my_cost, my_idx)) { my_cost = oc; my_idx = oi; }
+  }
+  if (lane == 0) { red_cost[wid] = my_cost; red_idx[wid] = my_idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < EVAL_THREADS / 32; ++q)
+      if (lex_less(red_cost[q], red_idx[q], my_cost, my_idx)) { my_cost = red_cost[q]; my_idx = red_idx[q]; }
+    BestRecord r;
+    r.key = orderable_bits(my_idx >= 0 ? my_cost : INFINITY);
+    r.idx = my_idx;
+    r.cost = my_cost;
+    r.n_pts = 0;
+    r.n_candidates = N;
+    r.n_seeds = Ns;
+    r.pad = 0;
+    *p.best = r;
+    *p.ticket = 0u;   // re-arm for the next launch (stream-ordered)
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K3: export of the selected trajectory (float64 rows) and optional fp32 state dump of every candidate
+// ------------------------------------------------------------------------------------------------------------------
+struct ExportSink {
+  double* out;   // [P][16]
+  const double* lat;
+  int P;
+  int n_pts;
+  __device__ __forceinline__ void sample(int i, double t, double s, double sd, double sdd, double sddd) {
+    double* r = out + (size_t)i * JSSP_TRAJ_COLS;
+    r[0] = t; r[1] = s; r[2] = sd; r[3] = sdd; r[4] = sddd;
+    r[5] = lat[i * 4]; r[6] = lat[i * 4 + 1]; r[7] = lat[i * 4 + 2]; r[8] = lat[i * 4 + 3];
+    for (int c = 9; c < JSSP_TRAJ_COLS; ++c) r[c] = nan("");
+  }
+  __device__ __forceinline__ void point(int i, double x, double y) {
+    out[(size_t)i * JSSP_TRAJ_COLS + 9] = x; out[(size_t)i * JSSP_TRAJ_COLS + 10] = y;
+  }
+  __device__ __forceinline__ void curvature(int i, double dyaw, double ds) { out[(size_t)i * JSSP_TRAJ_COLS + 13] = dyaw / ds; }
+  __device__ __forceinline__ void segment(int i, double, double, double, double, double yaw, double ds, double, double) {
+    out[(size_t)i * JSSP_TRAJ_COLS + 11] = yaw; out[(size_t)i * JSSP_TRAJ_COLS + 12] = ds;
+  }
+  __device__ __forceinline__ void finish(int n_pts_, double, double, double yaw, double, double, double ds) {
+    n_pts = n_pts_;
+    if (n_pts >= 2) {
+      out[(size_t)(n_pts - 1) * JSSP_TRAJ_COLS + 11] = yaw;           // yaw = append(yaw, yaw[-1])
+      out[(size_t)(n_pts - 2) * JSSP_TRAJ_COLS + 13] = (yaw - yaw) / ds;   // c[n-2] = diff(yaw)[-1] / ds[-1]
+    }
+  }
+};
+
+__global__ void export_best_kernel(const __grid_constant__ EvalParams p, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  EvalParams q = p;
+  q.smem_obs = 0;   // no obstacle window needed
+  BlockTables tb;
+  const double* latcost;
+  // layout without the obstacle window
+  {
+    EvalParams& r = q;
+    r.win_rows = 0;
+  }
+  stage_tables(q, smem, tb, latcost);
+  const long long best = p.best->idx;
+  if (threadIdx.x != 0) return;
+  if (best < 0) { p.best->n_pts = 0; return; }
+  const int Ns = resolve_n_seeds(p);
+  const int n = (int)best, w = n / Ns, k = n - w * Ns;
+  LonProfile lp;
+  lon_profile_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
+  ExportSink sink{out, tb.lat + (size_t)w * p.P * 4, p.P, 0};
+  const int seg0 = spline_bisect(tb.sp, fmin(fmax(p.s0, tb.sp.knot[0]), tb.sp.knot[p.K - 1]));
+  walk_candidate(p, tb, lp, w, seg0, sink);
+  // c_d = diff(c)/dt, c_dd = diff(c_d)/dt (jerk_space_sampling_planner.py:164-165)
+  const double dt = tb.time[1] - tb.time[0];
+  const int np = sink.n_pts;
+  for (int i = 0; i + 2 < np; ++i) out[(size_t)i * JSSP_TRAJ_COLS + 14] = (out[(size_t)(i + 1) * JSSP_TRAJ_COLS + 13] - out[(size_t)i * JSSP_TRAJ_COLS + 13]) / dt;
+  for (int i = 0; i + 3 < np; ++i) out[(size_t)i * JSSP_TRAJ_COLS + 15] = (out[(size_t)(i + 1) * JSSP_TRAJ_COLS + 14] - out[(size_t)i * JSSP_TRAJ_COLS + 14]) / dt;
+  p.best->n_pts = np;
+}
+
+struct DumpSink {
+  float* out;   // [P][8] of this candidate: s, s_d, s_dd, d, x, y, yaw, c
+  const double* lat;
+  __device__ __forceinline__ void sample(int i, double, double s, double sd, double sdd, double) {
+    float4* r = reinterpret_cast<float4*>(out + (size_t)i * JSSP_STATE_COLS);
+    const float nanv = __int_as_float(0x7fc00000);
+    r[0] = make_float4((float)s, (float)sd, (float)sdd, (float)lat[i * 4]);
+    r[1] = make_float4(nanv, nanv, nanv, nanv);
+  }
+  __device__ __forceinline__ void point(int i, double x, double y) {
+    out[(size_t)i * JSSP_STATE_COLS + 4] = (float)x; out[(size_t)i * JSSP_STATE_COLS + 5] = (float)y;
+  }
+  __device__ __forceinline__ void curvature(int i, double dyaw, double ds) { out[(size_t)i * JSSP_STATE_COLS + 7] = (float)(dyaw / ds); }
+  __device__ __forceinline__ void segment(int i, double, double, double, double, double yaw, double, double, double) {
+    out[(size_t)i * JSSP_STATE_COLS + 6] = (float)yaw;
+  }
+  __device__ __forceinline__ void finish(int n_pts, double, double, double yaw, double, double, double ds) {
+    if (n_pts >= 2) {
+      out[(size_t)(n_pts - 1) * JSSP_STATE_COLS + 6] = (float)yaw;
+      out[(size_t)(n_pts - 2) * JSSP_STATE_COLS + 7] = (float)((yaw - yaw) / ds);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(EVAL_THREADS) dump_states_kernel(const __grid_constant__ EvalParams p, float* __restrict__ states) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int Ns = resolve_n_seeds(p);
+  const int N = Ns * p.W;
+  if (blockIdx.x * blockDim.x >= N) return;
+  BlockTables tb;
+  const double* latcost;
+  stage_tables(p, smem, tb, latcost);   // p.smem_obs == 0 for this launch
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int w = n / Ns, k = n - w * Ns;
+  LonProfile lp;
+  lon_profile_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
+  DumpSink sink{states + (size_t)n * p.P * JSSP_STATE_COLS, tb.lat + (size_t)w * p.P * 4};
+  const int seg0 = spline_bisect(tb.sp, fmin(fmax(p.s0, tb.sp.knot[0]), tb.sp.knot[p.K - 1]));
+  walk_candidate(p, tb, lp, w, seg0, sink);
+}
+
+__global__ void best_record_kernel(const BestRecord* __restrict__ best, long long offset, unsigned long long* __restrict__ rec) {
+  rec[0] = best->key;
+  rec[1] = best->idx >= 0 ? (unsigned long long)(best->idx + offset) : 0xffffffffffffffffull;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K4: batched IMM lane-intention update (builder-specified; no reference code exists)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int IMM_MAX_MODES = 8;
+__global__ void imm_update_kernel(jssp_imm_params prm, double* __restrict__ mean, double* __restrict__ cov, double* __restrict__ mu,
+                                  const double* __restrict__ z, int O, int M) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= O) return;
+  double e[IMM_MAX_MODES], ed[IMM_MAX_MODES], p00[IMM_MAX_MODES], p01[IMM_MAX_MODES], p11[IMM_MAX_MODES], m[IMM_MAX_MODES],
+      zz[IMM_MAX_MODES], cbar[IMM_MAX_MODES], lik[IMM_MAX_MODES];
+  for (int i = 0; i < M; ++i) {
+    e[i] = mean[((size_t)o * M + i) * 2]; ed[i] = mean[((size_t)o * M + i) * 2 + 1];
+    p00[i] = cov[((size_t)o * M + i) * 3]; p01[i] = cov[((size_t)o * M + i) * 3 + 1]; p11[i] = cov[((size_t)o * M + i) * 3 + 2];
+    m[i] = mu[(size_t)o * M + i]; zz[i] = z[(size_t)o * M + i];
+  }
+  const double p_off = M > 1 ? (1.0 - prm.p_stay) / (double)(M - 1) : 0.0;
+  double ne[IMM_MAX_MODES], ned[IMM_MAX_MODES], n00[IMM_MAX_MODES], n01[IMM_MAX_MODES], n11[IMM_MAX_MODES];
+  for (int j = 0; j < M; ++j) {
+    // 1) interaction / mixing, expressed in mode j's lane frame: e_i + (z_j - z_i)
+    double cb = 0.0;
+    for (int i = 0; i < M; ++i) cb = cb + (i == j ? prm.p_stay : p_off) * m[i];
+    cbar[j] = cb;
+    double x0 = 0.0, x1 = 0.0;
+    for (int i = 0; i < M; ++i) {
+      const double wgt = cb > 0.0 ? (i == j ? prm.p_stay : p_off) * m[i] / cb : (i == j ? 1.0 : 0.0);
+      x0 = x0 + wgt * (e[i] + (zz[j] - zz[i]));
+      x1 = x1 + wgt * ed[i];
+    }
+    double q00 = 0.0, q01 = 0.0, q11 = 0.0;
+    for (int i = 0; i < M; ++i) {
+      const double wgt = cb > 0.0 ? (i == j ? prm.p_stay : p_off) * m[i] / cb : (i == j ? 1.0 : 0.0);
+      const double d0 = e[i] + (zz[j] - zz[i]) - x0, d1 = ed[i] - x1;
+      q00 = q00 + wgt * (p00[i] + d0 * d0); q01 = q01 + wgt * (p01[i] + d0 * d1); q11 = q11 + wgt * (p11[i] + d1 * d1);
+    }
+    // 2) mode-matched prediction, F = [[1, dt], [-k dt, 1]] (lane keeping towards this mode's centre line)
+    const double dt = prm.dt, kd = -prm.k_lat * dt;
+    const double xp0 = x0 + dt * x1, xp1 = kd * x0 + x1;
+    const double f00 = q00 + dt * q01, f01 = q01 + dt * q11;      // (F P) rows
+    const double f10 = kd * q00 + q01, f11 = kd * q01 + q11;
+    const double pp00 = f00 + f01 * dt + prm.q_pos;
+    const double pp01 = f00 * kd + f01;
+    const double pp11 = f10 * kd + f11 + prm.q_vel;
+    // 3) update with z_j (H = [1 0])
+    const double nu = zz[j] - xp0, S = pp00 + prm.r_pos;
+    const double k0 = pp00 / S, k1 = pp01 / S;
+    ne[j] = xp0 + k0 * nu; ned[j] = xp1 + k1 * nu;
+    n00[j] = pp00 - k0 * pp00; n01[j] = pp01 - k0 * pp01; n11[j] = pp11 - k1 * pp01;
+    lik[j] = exp(-0.5 * nu * nu / S) / sqrt(2.0 * 3.14159265358979323846 * S);
+  }
+  // 4) mode probabilities
+  double tot = 0.0;
+  for (int j = 0; j < M; ++j) { m[j] = fmax(lik[j] * cbar[j], prm.mu_floor); tot = tot + m[j]; }
+  for (int j = 0; j < M; ++j) {
+    mean[((size_t)o * M + j) * 2] = ne[j]; mean[((size_t)o * M + j) * 2 + 1] = ned[j];
+    cov[((size_t)o * M + j) * 3] = n00[j]; cov[((size_t)o * M + j) * 3 + 1] = n01[j]; cov[((size_t)o * M + j) * 3 + 2] = n11[j];
+    mu[(size_t)o * M + j] = m[j] / tot;
+  }
+}
+
+// one thread per (obstacle, mode): walk the mode's lane polyline at constant speed
+__global__ void predict_modes_kernel(const double* __restrict__ lanes, int L, int Pn, const int* __restrict__ lane_of,
+                                     const double* __restrict__ s_start, const double* __restrict__ speed, double dt, int O,
+                                     int M, int Tt, double* __restrict__ state, uint8_t* __restrict__ valid) {
+  const int om = blockIdx.x * blockDim.x + threadIdx.x;
+  if (om >= O * M) return;
+  const int lane = lane_of[om];
+  double* st = state + (size_t)om * Tt * 3;
+  uint8_t* va = valid + (size_t)om * Tt;
+  if (lane < 0 || lane >= L) { for (int t = 0; t < Tt; ++t) { va[t] = 0; st[t * 3] = st[t * 3 + 1] = st[t * 3 + 2] = 0.0; } return; }
+  const double* pl = lanes + (size_t)lane * Pn * 2;
+  const double v = speed[om / M];
+  int seg = 0;
+  double acc = 0.0;   // arc length at the start of segment `seg`
+  double seg_len = hypot(pl[2] - pl[0], pl[3] - pl[1]);
+  for (int t = 0; t < Tt; ++t) {
+    const double s = s_start[om] + v * ((double)t * dt);
+    while (seg < Pn - 2 && s > acc + seg_len) {
+      acc = acc + seg_len; ++seg;
+      seg_len = hypot(pl[(seg + 1) * 2] - pl[seg * 2], pl[(seg + 1) * 2 + 1] - pl[seg * 2 + 1]);
+    }
+    const bool ok = s >= 0.0 && s <= acc + seg_len && seg_len > 0.0;
+    const double dx = pl[(seg + 1) * 2] - pl[seg * 2], dy = pl[(seg + 1) * 2 + 1] - pl[seg * 2 + 1];
+    const double u = seg_len > 0.0 ? (s - acc) / seg_len : 0.0;
+    st[t * 3] = pl[seg * 2] + u * dx; st[t * 3 + 1] = pl[seg * 2 + 1] + u * dy; st[t * 3 + 2] = atan2(dy, dx);
+    va[t] = ok ? 1 : 0;
+  }
+}
+
+}  // namespace jssp

@@ -1,0 +1,189 @@
+/*
+ * jssp_b200.h - C ABI of libjssp_b200.so: the B200 (sm_100a) implementation of the DLII-JSSP
+ * jerk-space sampling planner's per-cycle candidate evaluation.
+ *
+ * Reference = byChenZhifa/DLII-JSSP; every entry point names the reference interface it replaces
+ * (paths relative to the reference root, `jssp.py` = code/intersection_local_planner/jerk_space_sampling_planner.py,
+ * `polyvt.py` = code/intersection_local_planner/polyvt_sampling.py).  The reference is pure Python, so there is no
+ * existing FFI; INTEGRATION.md shows the ctypes stub a maintainer adds.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every function returns an int32 status (0 = JSSP_OK, < 0 = error, see
+ *     jssp_strerror) and never throws.
+ *   - "dev" pointers are CUDA device pointers owned by the CALLER (e.g. torch tensors, pass tensor.data_ptr());
+ *     "host" pointers are ordinary host memory.  The library allocates only its private workspace in jssp_create
+ *     (sized from the capacities in jssp_config) and frees it in jssp_destroy; nothing is allocated per cycle.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls are stream-ordered; only the calls
+ *     documented as synchronising block the host.
+ *   - a handle is bound to one device and is not thread-safe.
+ */
+#ifndef JSSP_B200_H_
+#define JSSP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JSSP_ABI_VERSION 1
+#define JSSP_MAX_WIDTHS 16     /* lateral targets per cycle */
+#define JSSP_TRAJ_COLS 16      /* columns of an exported trajectory row, see jssp_cycle_out.best_traj */
+#define JSSP_STATE_COLS 8      /* columns of the optional per-candidate state dump */
+
+enum jssp_status {
+  JSSP_OK = 0,
+  JSSP_ERR_INVALID_ARG = -1,
+  JSSP_ERR_CUDA = -2,
+  JSSP_ERR_CAPACITY = -3,      /* more seeds / knots / obstacles / steps than the handle was created for */
+  JSSP_ERR_NOT_READY = -4,     /* reference line, obstacles or seeds missing */
+  JSSP_ERR_SEED_OVERFLOW = -5, /* seed enumeration produced more than max_seeds seeds */
+  JSSP_ERR_NO_DEVICE = -6
+};
+
+/* Planner constants.  Defaults (jssp_default_config) are the reference's values:
+ *   JerkSpaceSamplingPlannerSettings  jssp.py:35-64 with configuration_parameters.py:52-61
+ *   parameters["vehicle_para"], ["para_threshold"]  configuration_parameters.py:7-22
+ *   PlannerSettings.max_road_width  intersection_planner.py:60 */
+typedef struct jssp_config {
+  double delta_t;            /* 0.1 */
+  double plan_horizon;       /* 5.0  -> n_steps = int(plan_horizon / 0.1), polyvt.py:44 */
+  double max_road_width;     /* 3.5 */
+  int32_t num_width;         /* 3 */
+  int32_t num_jerk;          /* 25 (PolyVTSampling num_samples) */
+  double highest_jerk;       /* 10.0 */
+  double speed_max;          /* 18.0 */
+  double lon_accel_max;      /* 8.0 */
+  double ego_length;         /* ego footprint, centred rectangle */
+  double ego_width;
+  double max_curvature;      /* Vehicle.max_curvature, builder-specified 0.2 1/m */
+  double obstacle_inflation; /* 0.1, jssp.py:263-265 */
+  int32_t check_res;         /* 2, jssp.py:280 */
+  int32_t reserved0;
+  double cost_weights[8];    /* w_time, w_distance, w_laneoffset, w_lat_a, w_lat_j, w_lon_a, w_lon_j, w_lon_v */
+  double max_distance;       /* 140.0 */
+  double thr_lon_accel, thr_lon_jerk, thr_lat_accel, thr_lat_jerk; /* 3.0 6.0 0.5 1.0 */
+  double p_min;              /* multi-modal extension: modes with prob >= p_min veto (0 = every mode) */
+  double w_risk;             /* weight of the summed probability of the non-vetoing modes hit */
+  /* capacities of the private workspace */
+  int32_t max_seeds;         /* longitudinal seeds per cycle (enumerated or external) */
+  int32_t max_knots;         /* reference-line knots */
+  int32_t max_obstacle_modes;/* O * M */
+  int32_t max_total_steps;   /* scenario length in steps (Tt) */
+} jssp_config;
+
+typedef struct jssp_handle jssp_handle;
+
+/* One plan cycle's inputs = the arguments of JerkSpaceSamplingPlanner.plan_traj (jssp.py:296-300):
+ * frenet_state (s, s_d, s_dd, d, d_d, d_dd), time_step_now = int(t / dt), final_time_step = int(max_t / dt)
+ * (jssp.py:244). */
+typedef struct jssp_cycle_in {
+  double s0, v0, a0;           /* frenet_state.s, s_d, s_dd */
+  double d0, d_d0, d_dd0;      /* frenet_state.d, d_d, d_dd */
+  int32_t time_step_now;
+  int32_t final_time_step;
+  int32_t n_widths;            /* 0 -> cfg.num_width targets from jssp.py:100-104; else use targets[] */
+  int32_t flags;               /* JSSP_FLAG_* */
+  double targets[JSSP_MAX_WIDTHS];
+  const double* seeds_dev;     /* NULL -> the seeds of the last jssp_enumerate_seeds; else dev [n_seeds,10] */
+  int32_t n_seeds;             /* rows of seeds_dev (ignored when seeds_dev == NULL) */
+  int32_t reserved0;
+} jssp_cycle_in;
+
+#define JSSP_FLAG_NO_SYNC 1      /* do not wait / do not fill the host fields of jssp_cycle_out */
+#define JSSP_FLAG_NO_EXPORT 2    /* skip the best-trajectory export kernel */
+
+/* Outputs.  Candidate n = w * n_seeds + k (width-major, jssp.py:106,124-125).  All dev pointers may be NULL. */
+typedef struct jssp_cycle_out {
+  uint8_t* feasible_dev;       /* [N] 1 = passes check_constraints_curvature (jssp.py:171-180) */
+  uint8_t* collision_dev;      /* [N] 1 = has_collision (jssp.py:233-272), evaluated for every candidate */
+  float* cost_dev;             /* [N] cost_total (jssp.py:288-294) rounded to fp32; +inf is never written */
+  float* states_dev;           /* [N, n_steps+1, 8] = s, s_d, s_dd, d, x, y, yaw, c (NaN beyond n_pts); optional */
+  double* best_traj_host;      /* host [n_steps+1, 16] = t, s, s_d, s_dd, s_ddd, d, d_d, d_dd, d_ddd, x, y, yaw,
+                                  ds, c, c_d, c_dd of the selected candidate; filled unless NO_SYNC/NO_EXPORT */
+  /* host results (valid after a synchronising call) */
+  int32_t n_candidates;
+  int32_t best_idx;            /* -1 = no candidate survived ("No solution", jssp.py:359-360) */
+  int32_t best_n_pts;          /* Cartesian points of the best trajectory (< n_steps+1 when s leaves the spline) */
+  int32_t n_seeds;
+  double best_cost;
+} jssp_cycle_out;
+
+/* -- lifecycle ------------------------------------------------------------------------------------------ */
+int32_t jssp_abi_version(void);
+const char* jssp_strerror(int32_t status);
+/* last CUDA error string seen by this handle (for JSSP_ERR_CUDA) */
+const char* jssp_last_cuda_error(const jssp_handle* h);
+void jssp_default_config(jssp_config* cfg);
+/* replaces JerkSpaceSamplingPlanner.__init__ (jssp.py:67-78) */
+int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out);
+int32_t jssp_destroy(jssp_handle* h);
+
+/* -- host-only helpers (no GPU needed) --------------------------------------------------------------------- */
+/* The sampling grids of PolyVTSampling.__init__ (polyvt.py:33-58) and of the two samplers (:181, :274-279),
+ * bit-identical to numpy's linspace / arange.  Each out array must hold `cap` doubles; n_* receive the lengths in
+ * the order time_array, j1, t1, t2, j3, t3, t4, js, ts. */
+int32_t jssp_make_grids(double total_time, double jerk, int32_t num_samples, int32_t cap, double* time_array, double* j1,
+                        double* t1, double* t2, double* j3, double* t3, double* t4, double* js, double* ts,
+                        int32_t n_out[9]);
+/* Lateral quintic coefficients a0..a5 (QuinticPolynomial, jssp.py:109-117), closed form. */
+void jssp_quintic_coeffs(double xs, double vxs, double axs, double xe, double vxe, double axe, double T, double out[6]);
+
+/* -- per-scenario state ---------------------------------------------------------------------------------- */
+/* replaces the assignment `planner.fplanner.cubic_spline = CubicSpline2D(...)` (code/__main__.py:100, jssp.py:365):
+ * host knot_s[K] (cumulative chord length, knot_s[0] = 0) and host coef[K-1][8] = ax,bx,cx,dx,ay,by,cy,dy per segment. */
+int32_t jssp_set_refline(jssp_handle* h, const double* knot_s, const double* coef, int32_t K, void* stream);
+/* replaces the `obstacles` dict argument of plan_traj / has_collision (jssp.py:233-272; format controller.py:92-107):
+ * host state[O][M][Tt][3] = x, y, yaw; host valid[O][M][Tt]; host size[O][2] = length, width (not inflated);
+ * host prob[O][M]; n_dict = len(obstacles) for the `len(obstacles) <= 0` early-out (jssp.py:241).  M = 1, prob = 1
+ * is the reference's ground-truth replay case. */
+int32_t jssp_set_obstacles(jssp_handle* h, const double* state, const uint8_t* valid, const double* size,
+                           const double* prob, int32_t O, int32_t M, int32_t Tt, int32_t n_dict, void* stream);
+/* same, from caller-owned DEVICE buffers (e.g. the output of jssp_imm_update / jssp_predict_modes) */
+int32_t jssp_set_obstacles_dev(jssp_handle* h, const double* state_dev, const uint8_t* valid_dev, const double* size_dev,
+                               const double* prob_dev, int32_t O, int32_t M, int32_t Tt, int32_t n_dict, void* stream);
+
+/* -- per-cycle ------------------------------------------------------------------------------------------- */
+/* replaces PolyVTSampling.sampling + sampling_stop_seeds_supplement (polyvt.py:167-305; jssp.py:95-97).
+ * Seeds stay on the device.  n_main / n_stop may be NULL (then the call does not synchronise). */
+int32_t jssp_enumerate_seeds(jssp_handle* h, double s0, double v0, double a0, void* stream, int32_t* n_main,
+                             int32_t* n_stop);
+/* copy the enumerated seeds to host [cap,10]; synchronises; returns the count in *n */
+int32_t jssp_get_seeds(jssp_handle* h, double* seeds_host, int32_t cap, int32_t* n, void* stream);
+/* replaces the body of JerkSpaceSamplingPlanner.plan_traj after sampling (jssp.py:303-327):
+ * get_all_frenet_trajectory (polyvt.py:307-385), calc_global_paths, check_constraints_curvature, check_collisions,
+ * calc_all_trajs_cost and the PriorityQueue argmin, fused. */
+int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jssp_cycle_out* out);
+/* fetch the results of a JSSP_FLAG_NO_SYNC evaluate (synchronises the stream) */
+int32_t jssp_fetch_best(jssp_handle* h, void* stream, jssp_cycle_out* out);
+/* write the selection record of the last evaluate into caller-owned device memory: record_dev[0] = orderable bits of
+ * the float64 cost (unsigned order == numeric order), record_dev[1] = candidate index + index_offset (UINT64_MAX when
+ * no candidate survived) - what a candidate-split run feeds to its NCCL reduction. */
+int32_t jssp_best_record_dev(jssp_handle* h, int64_t index_offset, void* stream, uint64_t* record_dev);
+/* number of kernels the library has launched through this handle so far */
+int64_t jssp_launch_count(const jssp_handle* h);
+
+/* -- secondary kernel: batched IMM lane-intention update (no reference code, README.md:19,23,98-110) ------- */
+typedef struct jssp_imm_params {
+  double dt;
+  double q_pos, q_vel;         /* process noise of the per-mode lateral KF */
+  double r_pos;                /* measurement noise of the lateral offset */
+  double k_lat;                /* lane-keeping gain of a mode towards its own lane centre */
+  double p_stay;               /* diagonal of the Markov transition matrix; off-diagonals share 1 - p_stay */
+  double mu_floor;             /* lower clamp on the mode probabilities before normalisation */
+} jssp_imm_params;
+/* All pointers are device pointers.  Per obstacle o and mode m: mean[o][m][2], cov[o][m][3] (p00,p01,p11),
+ * mu[o][m]; z[o][m] = measured lateral offset of the obstacle from mode m's lane centre.  Updates in place. */
+int32_t jssp_imm_update(jssp_handle* h, const jssp_imm_params* p, double* mean_dev, double* cov_dev, double* mu_dev,
+                        const double* z_dev, int32_t O, int32_t M, void* stream);
+/* Roll out one constant-speed trajectory per (obstacle, mode) along the mode's lane polyline:
+ * lanes_dev[L][P][2] polylines, lane_of[o][m] lane index, s_start[o][m] arc length at t0, speed[o], ->
+ * state_dev[O][M][Tt][3] (x, y, yaw), valid_dev[O][M][Tt]. */
+int32_t jssp_predict_modes(jssp_handle* h, const double* lanes_dev, int32_t L, int32_t P, const int32_t* lane_of_dev,
+                           const double* s_start_dev, const double* speed_dev, double dt, int32_t O, int32_t M,
+                           int32_t Tt, double* state_dev, uint8_t* valid_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JSSP_B200_H_ */
