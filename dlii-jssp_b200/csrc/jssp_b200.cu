@@ -215,6 +215,7 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   } while (0)
   CKC(cudaSetDevice(device));
   CKC(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  h->max_smem_optin -= 1024;   // static shared memory of the kernels + slack
   HostGrids g = make_grids(cfg->plan_horizon, cfg->highest_jerk, cfg->num_jerk, cfg->delta_t);
   std::vector<double> jneg, jpos;
   for (double j : g.js) { if (!(j > 0)) jneg.push_back(j); if (!(j < 0)) jpos.push_back(j); }   // polyvt_sampling.py:275,287

@@ -7,7 +7,7 @@ import torch
 
 import dlii_jssp_b200 as J
 from oracle import jssp_oracle as O
-from tests import helpers as H
+import jssp_test_helpers as H
 
 pytestmark = pytest.mark.gpu
 
