@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py - candidate-timesteps/s of the JSSP per-cycle candidate evaluation on B200 (contract: see DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3|C5]
+
+A "step" is one plan cycle over one synthetic batch of candidates: the fused evaluation kernel (unroll -> Frenet->Cartesian
+-> curvature feasibility -> rectangle collision against every obstacle mode -> cost -> argmin) plus the export of the
+selected trajectory.  Workload at N = 1: BASELINE.json configs[2] ("C3": 65,536 candidates x 50 steps x 32 obstacles x 3
+modes; configs[1] has no reference data - SURVEY.md section 0.5).  For N > 1 every rank evaluates an independent scenario
+of the same shape (rank-specific seed): the path shards over scenarios with no data-path collective ("weak").  With
+--workload C5 the 1M-candidate cycle is split over the ranks and reduced with one NCCL all-gather of 16 B per rank.
+
+Prints ONE JSON line.  Timing: CUDA events on torch's current stream (the stream handed to the library), one event pair
+per step, L2 flushed (256 MiB write) between steps outside the event pairs, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic work per candidate-timestep: F_base + F_sat * O * M / check_res
+F_BASE, F_SAT = 128.0, 48.0
+METRIC, UNIT = "candidate_timesteps_per_s", "candidate-timesteps/s"
+
+
+_WORKLOADS = {}
+
+
+def workload(name: str, rank: int = 0):
+    """Seeded synthetic cycle (cached per process)."""
+    from dlii_jssp_b200 import scenario as S
+    key = (name, rank)
+    if key not in _WORKLOADS:
+        if name == "C3":
+            _WORKLOADS[key] = S.dense_cycle(n_seeds=16384, n_widths=4, O=32, M=3, plan_horizon=5.0, seed=20251019 + rank, name="C3")
+        elif name == "C5":
+            _WORKLOADS[key] = S.dense_cycle(n_seeds=131072, n_widths=8, O=64, M=3, plan_horizon=8.0, seed=20251020, name="C5")
+        else:
+            raise SystemExit(f"unknown workload {name}")
+    return _WORKLOADS[key]
+
+
+def workload_config(name, cyc, n_gpus):
+    O, M, Tt = cyc.obstacles.shape
+    desc = {"C3": "synthetic dense plan cycle: 65,536 candidates x 50 steps x 32 obstacles x 3 intention modes (BASELINE configs[2])",
+            "C5": "synthetic 1M-candidate x 80-step x 64-obstacle x 3-mode cycle split across the ranks (BASELINE configs[4])"}[name]
+    return {"workload": desc, "candidates": cyc.n_candidates, "steps_per_candidate": int(cyc.plan_horizon / 0.1), "obstacles": O, "modes": M,
+            "parallelism": (f"{n_gpus} independent scenarios, no collective" if name == "C3" else f"candidate split x{n_gpus}, one 16 B/rank NCCL all-gather"),
+            "l2": "flushed between steps (256 MiB write outside the event pairs)", "seed": 20251019 if name == "C3" else 20251020}
+
+
+def algorithmic_flops(cyc, n_candidates=None):
+    O, M, _ = cyc.obstacles.shape
+    P = int(cyc.plan_horizon / 0.1) + 1
+    n = cyc.n_candidates if n_candidates is None else n_candidates
+    return (F_BASE + F_SAT * O * M / 2.0) * n * P
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons via NVML while the timed regions run."""
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+               0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.ok = index, [], set(), False, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self.stop_flag:
+            try:
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                util = self.nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                bits = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((mhz, util))
+                for b, name in self.REASONS.items():
+                    if bits & b and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        busy = [m for m, u in self.samples if u > 0] or [m for m, _ in self.samples]
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def oracle_inputs(cyc):
+    from oracle import jssp_oracle as O
+    cfg = O.OracleConfig(ego_length=cyc.ego_length, ego_width=cyc.ego_width, plan_horizon=cyc.plan_horizon)
+    spline = O.CubicSpline2D(cyc.route_xy[:, 0], cyc.route_xy[:, 1])
+    o = cyc.obstacles
+    return cfg, spline, (o.state, o.valid.astype(bool), o.size, o.prob)
+
+
+def _loop_chunk(args):
+    name, idx = args
+    from oracle import jssp_loop as L
+    cyc = workload(name)
+    cfg, spline, obs = oracle_inputs(cyc)
+    t0 = time.perf_counter()
+    L.plan_cycle_loop(cfg, spline, cyc.frenet0, obs, cyc.time_step_now, cyc.final_time_step, seeds=cyc.seeds, targets=cyc.targets,
+                      candidate_subset=idx)
+    return time.perf_counter() - t0
+
+
+def cpu_port_rate(name, cyc, n_sample, cores=1, pool=None):
+    """candidate-timesteps/s of the loop-form port on ``n_sample`` candidates spread evenly over the workload."""
+    N = cyc.n_candidates
+    P = int(cyc.plan_horizon / 0.1) + 1
+    idx = np.unique(np.linspace(0, N - 1, n_sample).astype(np.int64)).tolist()
+    t0 = time.perf_counter()
+    if cores <= 1:
+        _loop_chunk((name, idx))
+    else:
+        chunks = [idx[c::cores] for c in range(cores)]
+        list(pool.map(_loop_chunk, [(name, c) for c in chunks]))
+    dt = time.perf_counter() - t0
+    return len(idx) * P / dt, len(idx), dt
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """Reference arm: the reference's CPU evaluation path.  The reference itself cannot run (its `common` package is
+    unpublished, shapely is absent), so this is the loop-form port (oracle/jssp_loop.py) on all host cores, each step a
+    bounded, evenly spread sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    cyc = workload(args.workload)
+    P = int(cyc.plan_horizon / 0.1) + 1
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        rate0, n0, _ = cpu_port_rate(args.workload, cyc, 16 * cores, cores, pool)        # calibration (+ worker warm-up)
+        budget = 150.0 / max(args.steps + args.warmup, 1)
+        n_sample = int(max(8 * cores, min(cyc.n_candidates, rate0 / P * budget)))
+        for _ in range(args.warmup):
+            cpu_port_rate(args.workload, cyc, n_sample, cores, pool)
+        rates, times, used = [], [], 0
+        for _ in range(args.steps):
+            r, used, dt = cpu_port_rate(args.workload, cyc, n_sample, cores, pool)
+            rates.append(r); times.append(dt)
+    value = used * P * len(times) / sum(times)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args.workload, cyc, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{used} of {cyc.n_candidates} candidates per step (evenly spread), loop-form float64 port of the reference stages, "
+                                       f"SAT in place of shapely, {cores} processes"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import dlii_jssp_b200 as J
+    from dlii_jssp_b200 import distributed as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    split = args.workload == "C5"
+    cyc = workload(args.workload, rank=0 if split else rank)
+    P = int(cyc.plan_horizon / 0.1) + 1
+    O, M, Tt = cyc.obstacles.shape
+    W = len(cyc.targets)
+    seeds_all = cyc.seeds
+    if split:   # contiguous candidate ranges per rank = contiguous seed ranges for every width
+        per = len(seeds_all) // world
+        seeds_host = np.ascontiguousarray(seeds_all[rank * per:(rank + 1) * per])
+    else:
+        seeds_host = seeds_all
+    n_local = len(seeds_host) * W
+    cfg = J.JsspConfig(plan_horizon=cyc.plan_horizon, ego_length=cyc.ego_length, ego_width=cyc.ego_width, max_seeds=len(seeds_host),
+                       max_obstacle_modes=O * M, max_total_steps=Tt, max_knots=max(1024, len(cyc.route_xy)))
+    eng = J.JsspEngine(cfg, device=local)
+    spline = J.CubicSpline2D(cyc.route_xy[:, 0], cyc.route_xy[:, 1])
+    eng.set_refline(spline.s_list, spline.coefficient_table())
+    o = cyc.obstacles
+    eng.set_obstacles(o.state, o.valid, o.size, o.prob, o.n_dict)
+    seeds_pinned = torch.from_numpy(seeds_host).pin_memory()
+    seeds_dev = seeds_pinned.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    seed_lo = rank * (len(seeds_all) // world) if split else 0
+
+    def reduce_best():
+        """candidate-split exchange: per-rank winner (float64 cost bits, global index) -> one 16 B/rank NCCL all-gather"""
+        if not split:
+            return None
+        rec = D.localize_record(eng.best_record(), seed_lo, len(seeds_host), len(seeds_all))
+        return D.allgather_argmin(rec)
+
+    def timed(steps, warmup, export, with_reduce=False):
+        for _ in range(warmup):
+            eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=seeds_dev, targets=cyc.targets, sync=False, export=export)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        l0 = eng.launch_count
+        for e0, e1 in evs:
+            flush.fill_(1)
+            e0.record()
+            eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=seeds_dev, targets=cyc.targets, sync=False, export=export)
+            if with_reduce:
+                reduce_best()
+            e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = [a.elapsed_time(b) for a, b in evs]
+        return ms, eng.launch_count - l0
+
+    # (1) whole step, inputs resident in HBM
+    step_ms, launches = timed(args.steps, args.warmup, export=True, with_reduce=split)
+    total_ms = sum(step_ms)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    units_all = (cyc.n_candidates if split else n_local * world) * P * args.steps
+    value = units_all / (total_ms * 1e-3)
+    res = eng.fetch()
+
+    # (2) dominant kernel alone (no export) for the roofline
+    k_ms, _ = timed(args.steps, 3, export=False)
+    k_avg_s = 1e-3 * sum(k_ms) / len(k_ms)
+    flops = algorithmic_flops(cyc, n_local)
+    peak32, peak64 = __import__("ctypes").c_double(0), __import__("ctypes").c_double(0)
+    eng.lib.jssp_measure_fma_peak(local, 32, peak32)
+    eng.lib.jssp_measure_fma_peak(local, 64, peak64)
+    achieved = flops / k_avg_s / 1e12
+    alg_bytes = n_local * 6 + len(seeds_host) * 80 + O * M * P * 16 + len(cyc.route_xy) * 72 + P * 48
+
+    # (3) end to end through the public API with host buffers: H2D of this cycle's seeds and obstacle predictions, evaluate,
+    #     D2H of the selected trajectory
+    h2d = seeds_host.nbytes + o.state.nbytes + o.valid.nbytes + o.size.nbytes + o.prob.nbytes
+    d2h = P * 16 * 8 + 40
+    def e2e_step():
+        sd = seeds_pinned.to(dev, non_blocking=True)
+        eng.set_obstacles(o.state, o.valid, o.size, o.prob, o.n_dict)
+        r = eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=sd, targets=cyc.targets, sync=not split)
+        if split:
+            reduce_best()
+            r = eng.fetch()
+        return r
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    lat = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        e2e_step()
+        lat.append(time.perf_counter() - t0)
+    e2e_total = sum(lat)
+    if world > 1:
+        t = torch.tensor([e2e_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_total = float(t.item())
+    e2e_value = units_all / e2e_total
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if split else "weak", "vs_baseline": None,
+                "dtype": "f64 geometry + f32 collision", "data": "synthetic", "config": workload_config(args.workload, cyc, world),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "p50_cycle_ms": 1e3 * statistics.median(lat)},
+                "gpu_launches": int(launches), "clocks": sampler.summary(),
+                "roofline": {"bound": "fp32", "kernel": "evaluate_kernel", "achieved": achieved, "peak": peak32.value, "unit": "TFLOP/s",
+                             "frac": achieved / peak32.value if peak32.value else None, "traffic": None,
+                             "peak_source": "measured live: FFMA micro-benchmark in libjssp_b200 (MEASURED_PEAKS.json has no CUDA-core figure); "
+                                            "fp64 FMA peak %.1f TFLOP/s" % peak64.value,
+                             "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes,
+                             "kernel_ms": 1e3 * k_avg_s, "hbm_frac_of_measured": (alg_bytes / k_avg_s / 1e9) / 6544.3,
+                             "note": "algorithmic flops = (128 + 48*O*M/2) per candidate-timestep (SURVEY 8d); broad-phase culling skips most of "
+                                     "the 48-flop rectangle tests, so achieved can exceed the executed-flop rate - see profiles/ for pipe utilisation"},
+                "selected": {"best_idx": res.best_idx, "best_cost": res.best_cost}}
+        if world == 1 and not args.no_cpu:
+            n_s = max(64, cyc.n_candidates // args.cpu_sample_div)
+            rate, used, dt = cpu_port_rate(args.workload, cyc, n_s, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"{used} of {cyc.n_candidates} candidates (evenly spread) in {dt:.1f} s; loop-form float64 port of the "
+                                              "reference stages (oracle/jssp_loop.py), SAT in place of shapely, 1 process like the reference"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3", choices=["C3", "C5"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--cpu-sample-div", type=int, default=32, help="cpu_baseline sample = candidates / this")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

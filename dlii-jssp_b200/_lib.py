@@ -74,6 +74,7 @@ SYMBOLS = {
     "jssp_fetch_best": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(JsspCycleOut)]),
     "jssp_best_record_dev": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "jssp_launch_count": (C.c_int64, [C.c_void_p]),
+    "jssp_measure_fma_peak": (C.c_int32, [C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "jssp_imm_update": (C.c_int32, [C.c_void_p, C.POINTER(JsspImmParams)] + [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_void_p]),
     "jssp_predict_modes": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

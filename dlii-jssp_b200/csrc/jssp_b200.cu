@@ -8,6 +8,7 @@
 #include <cmath>
 #include <new>
 #include <vector>
+#include <algorithm>
 
 #include "jssp_kernels.cuh"
 
@@ -132,6 +133,33 @@ int pack_if_dirty(jssp_handle* h, cudaStream_t st) {
     CK(cudaGetLastError());
   }
   h->obs_dirty = false;
+  return JSSP_OK;
+}
+
+template <typename T>
+static int32_t measure_fma(int device, double* tflops) {
+  jssp_handle* h = nullptr;
+  if (cudaSetDevice(device) != cudaSuccess) return JSSP_ERR_NO_DEVICE;
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int blocks = sms * 8, threads = 256, iters = 8192;
+  T* out = nullptr;
+  CK(cudaMalloc(&out, (size_t)blocks * threads * sizeof(T)));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    CK(cudaEventRecord(e0, 0));
+    fma_peak_kernel<T><<<blocks, threads>>>(out, iters, (T)1.0000001, (T)1e-7);
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    if (rep > 0 && ms > 0.f) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  *tflops = best;
   return JSSP_OK;
 }
 
@@ -492,6 +520,13 @@ int32_t jssp_best_record_dev(jssp_handle* h, int64_t index_offset, void* stream,
 }
 
 int64_t jssp_launch_count(const jssp_handle* h) { return h ? h->launches : 0; }
+
+int32_t jssp_measure_fma_peak(int32_t device, int32_t bits, double* tflops) {
+  if (!tflops || (bits != 32 && bits != 64)) return JSSP_ERR_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return JSSP_ERR_NO_DEVICE; }
+  return bits == 32 ? measure_fma<float>(device, tflops) : measure_fma<double>(device, tflops);
+}
 
 int32_t jssp_imm_update(jssp_handle* h, const jssp_imm_params* prm, double* mean_dev, double* cov_dev, double* mu_dev,
                         const double* z_dev, int32_t O, int32_t M, void* stream) {

@@ -764,4 +764,18 @@ __global__ void predict_modes_kernel(const double* __restrict__ lanes, int L, in
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// bench utility: dense FMA throughput of the CUDA cores (the roofline denominator of the evaluation kernel)
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* __restrict__ out, int iters, T a, T b) {
+  T x0 = (T)threadIdx.x, x1 = x0 + (T)1, x2 = x0 + (T)2, x3 = x0 + (T)3, x4 = x0 + (T)4, x5 = x0 + (T)5, x6 = x0 + (T)6, x7 = x0 + (T)7;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 }  // namespace jssp

@@ -162,6 +162,9 @@ int32_t jssp_fetch_best(jssp_handle* h, void* stream, jssp_cycle_out* out);
 int32_t jssp_best_record_dev(jssp_handle* h, int64_t index_offset, void* stream, uint64_t* record_dev);
 /* number of kernels the library has launched through this handle so far */
 int64_t jssp_launch_count(const jssp_handle* h);
+/* bench utility: measured dense FMA throughput of the CUDA cores in TFLOP/s (bits = 32 or 64): the roofline
+ * denominator bench.py reports the evaluation kernel against (MEASURED_PEAKS.json has no CUDA-core figure). */
+int32_t jssp_measure_fma_peak(int32_t device, int32_t bits, double* tflops);
 
 /* -- secondary kernel: batched IMM lane-intention update (no reference code, README.md:19,23,98-110) ------- */
 typedef struct jssp_imm_params {
