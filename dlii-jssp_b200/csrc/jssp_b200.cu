@@ -123,10 +123,11 @@ cudaError_t upload(T** dst, const std::vector<T>& v) {
 int pack_if_dirty(jssp_handle* h, cudaStream_t st) {
   if (!h->obs_dirty) return JSSP_OK;
   const int OM = h->O * h->M;
-  const int total = OM * h->Tt;
+  const int OMpad = (OM + 31) & ~31;
+  const int total = OMpad * h->Tt;
   if (total > 0) {
     const double r_ego = std::sqrt(h->cfg.ego_length * h->cfg.ego_length + h->cfg.ego_width * h->cfg.ego_width) / 2.0;
-    pack_obstacles_kernel<<<(total + 255) / 256, 256, 0, st>>>(h->src_state, h->src_valid, h->src_size, h->src_prob, OM, h->M, h->Tt,
+    pack_obstacles_kernel<<<(total + 255) / 256, 256, 0, st>>>(h->src_state, h->src_valid, h->src_size, h->src_prob, OM, OMpad, h->M, h->Tt,
                                                                h->ox, h->oy, h->cfg.obstacle_inflation, r_ego, h->d_broad, h->d_narrow,
                                                                h->d_obs64, h->d_ext64);
     h->launches++;
@@ -270,7 +271,7 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(cudaMalloc(&h->d_counts, 4 * sizeof(int)));
   CKC(cudaMemset(h->d_counts, 0, 4 * sizeof(int)));
   CKC(cudaMallocHost(&h->h_counts, 4 * sizeof(int)));
-  h->kpad = (cfg->max_knots + 1) & ~1;
+  h->kpad = (cfg->max_knots + 1) & ~1;   // capacity; the per-scenario stride is set in jssp_set_refline
   CKC(cudaMalloc(&h->d_knot, (size_t)cfg->max_knots * sizeof(double)));
   CKC(cudaMalloc(&h->d_coef, (size_t)8 * h->kpad * sizeof(double)));
   const size_t om = (size_t)(cfg->max_obstacle_modes > 0 ? cfg->max_obstacle_modes : 1), tt = (size_t)cfg->max_total_steps;
@@ -278,7 +279,7 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(cudaMalloc(&h->d_raw_valid, om * tt));
   CKC(cudaMalloc(&h->d_raw_size, om * 2 * sizeof(double)));
   CKC(cudaMalloc(&h->d_raw_prob, om * sizeof(double)));
-  CKC(cudaMalloc(&h->d_broad, om * tt * sizeof(float4)));
+  CKC(cudaMalloc(&h->d_broad, ((om + 31) & ~(size_t)31) * tt * sizeof(float4)));
   CKC(cudaMalloc(&h->d_narrow, om * tt * sizeof(float4)));
   CKC(cudaMalloc(&h->d_obs64, om * tt * 4 * sizeof(double)));
   CKC(cudaMalloc(&h->d_ext64, om * 2 * sizeof(double)));
@@ -292,8 +293,8 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(cudaMallocHost(&h->h_best, sizeof(BestRecord)));
   CKC(cudaMalloc(&h->d_best_traj, (size_t)h->P * JSSP_TRAJ_COLS * sizeof(double)));
   CKC(cudaMallocHost(&h->h_best_traj, (size_t)h->P * JSSP_TRAJ_COLS * sizeof(double)));
-  CKC(cudaFuncSetAttribute(evaluate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  CKC(cudaFuncSetAttribute(export_best_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CKC(cudaFuncSetAttribute(evaluate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CKC(cudaFuncSetAttribute(evaluate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CKC(cudaFuncSetAttribute(dump_states_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CKC(cudaDeviceSynchronize());
 #undef CKC
@@ -323,6 +324,7 @@ int32_t jssp_set_refline(jssp_handle* h, const double* knot_s, const double* coe
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
   // structure-of-arrays [8][kpad] so that lanes on neighbouring segments hit different shared-memory banks
+  h->kpad = (K + 1) & ~1;
   std::vector<double> soa((size_t)8 * h->kpad, 0.0);
   for (int i = 0; i < K - 1; ++i)
     for (int c = 0; c < 8; ++c) soa[(size_t)c * h->kpad + i] = coef[(size_t)i * 8 + c];
@@ -460,7 +462,7 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   p.W = W; p.P = h->P; p.now = in->time_step_now; p.tcap = in->final_time_step - in->time_step_now;
   p.n_dict = h->n_dict; p.check_res = c.check_res;
   p.kmax = c.max_curvature; p.ea = c.ego_length / 2.0; p.eb = c.ego_width / 2.0; p.p_min = c.p_min; p.w_risk = c.w_risk;
-  p.vmax = c.speed_max; p.max_distance = c.max_distance; p.half_w = c.max_road_width / 2.0;
+  p.vmax = c.speed_max; p.inv_vmax = 1.0 / c.speed_max; p.max_distance = c.max_distance; p.half_w = c.max_road_width / 2.0;
   p.thr_lon_a = c.thr_lon_accel; p.thr_lon_j = c.thr_lon_jerk; p.thr_lat_a = c.thr_lat_accel; p.thr_lat_j = c.thr_lat_jerk;
   memcpy(p.cw, c.cost_weights, sizeof(p.cw));
   p.time = h->d_time; p.knot = h->d_knot; p.coef = h->d_coef; p.K = h->K; p.kpad = h->kpad; p.ox = h->ox; p.oy = h->oy;
@@ -469,38 +471,35 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   p.n_seeds_fixed = ext ? in->n_seeds : 0;
   p.seed_cap = c.max_seeds;
   p.broad = h->d_broad; p.narrow = h->d_narrow; p.obs64 = h->d_obs64; p.ext64 = h->d_ext64;
-  p.OM = h->O * h->M; p.Tt = h->Tt;
+  p.OM = h->O * h->M; p.OMpad = (p.OM + 31) & ~31; p.Tt = h->Tt;
   int rows = 0;   // collision rows of the window: i = 0, check_res, ... < min(P, tcap)
   if (p.tcap > 0 && p.now >= 0) rows = (std::min(p.P, p.tcap) + c.check_res - 1) / c.check_res;
   if (p.now < 0) return JSSP_ERR_INVALID_ARG;
   p.win_rows = p.OM > 0 ? rows : 0;
   p.smem_obs = 1;
-  SmemLayout L = eval_smem_layout(p.win_rows, p.OM, 1, p.K, p.kpad, p.P, p.W);
+  SmemLayout L = eval_smem_layout(p.win_rows, p.OMpad, 1, p.K, p.kpad, p.P, p.W);
   if (p.win_rows == 0 || L.total > (size_t)h->max_smem_optin) {
     p.smem_obs = 0;
-    L = eval_smem_layout(p.win_rows, p.OM, 0, p.K, p.kpad, p.P, p.W);
+    L = eval_smem_layout(p.win_rows, p.OMpad, 0, p.K, p.kpad, p.P, p.W);
     if (L.total > (size_t)h->max_smem_optin) return JSSP_ERR_CAPACITY;
   }
   p.feasible = out->feasible_dev; p.collision = out->collision_dev; p.cost = out->cost_dev;
   p.blk_cost = h->d_blk_cost; p.blk_idx = h->d_blk_idx; p.ticket = h->d_ticket; p.best = h->d_best;
+  p.best_traj = (in->flags & JSSP_FLAG_NO_EXPORT) ? nullptr : h->d_best_traj;
 
   const long long n_max = (long long)W * (ext ? in->n_seeds : c.max_seeds);
   int blocks = (int)((n_max + EVAL_THREADS - 1) / EVAL_THREADS);
   if (blocks < 1) blocks = 1;
   if (blocks > h->max_blocks) return JSSP_ERR_CAPACITY;
-  evaluate_kernel<<<blocks, EVAL_THREADS, L.total, st>>>(p);
+  if (p.smem_obs) evaluate_kernel<true><<<blocks, EVAL_THREADS, L.total, st>>>(p);
+  else evaluate_kernel<false><<<blocks, EVAL_THREADS, L.total, st>>>(p);
   h->launches++;
   CK(cudaGetLastError());
   EvalParams q = p;
   q.smem_obs = 0; q.win_rows = 0;
-  const SmemLayout L2 = eval_smem_layout(0, q.OM, 0, q.K, q.kpad, q.P, q.W);
+  const SmemLayout L2 = eval_smem_layout(0, q.OMpad, 0, q.K, q.kpad, q.P, q.W);
   if (out->states_dev) {
     dump_states_kernel<<<blocks, EVAL_THREADS, L2.total, st>>>(q, out->states_dev);
-    h->launches++;
-    CK(cudaGetLastError());
-  }
-  if (!(in->flags & JSSP_FLAG_NO_EXPORT)) {
-    export_best_kernel<<<1, EVAL_THREADS, L2.total, st>>>(q, h->d_best_traj);
     h->launches++;
     CK(cudaGetLastError());
   }

@@ -13,7 +13,8 @@
 
 namespace jssp {
 
-constexpr int EVAL_THREADS = 128;
+constexpr int EVAL_THREADS = 256;
+constexpr int EVAL_MIN_BLOCKS = 2;
 constexpr float SAT_EPS = 2e-3f;        // fp32 guard band [m]; inside it the pair is re-decided in float64
 constexpr float FAR_AWAY = 1e30f;       // x of an absent obstacle state: squared distance overflows to +inf -> culled
 
@@ -209,29 +210,37 @@ __global__ void __launch_bounds__(1024) seed_sort_emit(SeedGrids g, SeedState st
 
 // ------------------------------------------------------------------------------------------------------------------
 // K0: obstacle tables.  raw state [OM][Tt][3] (x, y, yaw), valid [OM][Tt] ->
-//   broad  [Tt][OM] float4 = (x - ox, y - oy, (r_ego + r_obs + pad)^2, prob)      (FAR_AWAY when absent)
+//   broad  [Tt][OMpad] float4 = (x', y', |o'|^2 - R^2, prob) with o' = o - origin, R = r_ego + r_obs + pad; the
+//          squared-distance test |o' - e'|^2 <= R^2 becomes  x'*(-2ex) + y'*(-2ey) + (|o'|^2 - R^2) <= -|e'|^2
+//          (2 FFMA + 1 compare per pair).  Absent states and the padding up to a multiple of 32 hold +FAR.
 //   narrow [Tt][OM] float4 = (cos yaw, sin yaw, half length + infl/2, half width + infl/2)
 //   obs64  [Tt][OM][4]     = x, y, cos yaw, sin yaw in float64 for the guard-band re-decision
 // ------------------------------------------------------------------------------------------------------------------
+constexpr float BROAD_PAD = 0.05f;        // [m] added to the bounding-circle radius sum
+constexpr float BROAD_CANCEL = 0.5f;      // [m^2] covers fp32 cancellation of the expanded form for |coord| <= 1000 m
 __global__ void pack_obstacles_kernel(const double* __restrict__ state, const uint8_t* __restrict__ valid,
-                                      const double* __restrict__ size, const double* __restrict__ prob, int OM, int M, int Tt,
-                                      double ox, double oy, double inflation, double r_ego, float4* __restrict__ broad,
+                                      const double* __restrict__ size, const double* __restrict__ prob, int OM, int OMpad, int M,
+                                      int Tt, double ox, double oy, double inflation, double r_ego, float4* __restrict__ broad,
                                       float4* __restrict__ narrow, double* __restrict__ obs64, double* __restrict__ ext64) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // idx = t * OM + om
-  if (idx >= OM * Tt) return;
-  const int t = idx / OM, om = idx - t * OM, o = om / M;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // idx = t * OMpad + om
+  if (idx >= OMpad * Tt) return;
+  const int t = idx / OMpad, om = idx - t * OMpad;
+  if (om >= OM) { broad[idx] = make_float4(0.f, 0.f, FAR_AWAY, 0.f); return; }
+  const int o = om / M;
   const double a2 = (size[2 * o] + inflation) / 2.0, b2 = (size[2 * o + 1] + inflation) / 2.0;
   if (t == 0) { ext64[2 * om] = a2; ext64[2 * om + 1] = b2; }
   const double* s = state + ((size_t)om * Tt + t) * 3;
   const bool ok = valid[(size_t)om * Tt + t] != 0;
   double sn, cs;
   sincos(s[2], &sn, &cs);
-  const float r = (float)(r_ego + sqrt(a2 * a2 + b2 * b2)) + 0.05f;
-  broad[idx] = make_float4(ok ? (float)(s[0] - ox) : FAR_AWAY, ok ? (float)(s[1] - oy) : FAR_AWAY, r * r * 1.0001f,
-                           (float)prob[om]);
-  narrow[idx] = make_float4((float)cs, (float)sn, (float)a2, (float)b2);
-  double* q = obs64 + (size_t)idx * 4;
-  q[0] = s[0]; q[1] = s[1]; q[2] = cs; q[3] = sn;
+  const float r = (float)(r_ego + sqrt(a2 * a2 + b2 * b2)) + BROAD_PAD;
+  const float fx = (float)(s[0] - ox), fy = (float)(s[1] - oy);
+  const float q = fmaf(fx, fx, fy * fy) - (r * r * 1.0001f + BROAD_CANCEL);
+  broad[idx] = ok ? make_float4(fx, fy, q, (float)prob[om]) : make_float4(0.f, 0.f, FAR_AWAY, 0.f);
+  const size_t gi = (size_t)t * OM + om;
+  narrow[gi] = make_float4((float)cs, (float)sn, (float)a2, (float)b2);
+  double* q64 = obs64 + gi * 4;
+  q64[0] = s[0]; q64[1] = s[1]; q64[2] = cs; q64[3] = sn;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -244,7 +253,7 @@ struct EvalParams {
   int W, P, now, tcap;            // tcap = final_time_step - time_step_now
   int n_dict, check_res;
   // constants
-  double kmax, ea, eb, p_min, w_risk, vmax, max_distance, half_w, thr_lon_a, thr_lon_j, thr_lat_a, thr_lat_j;
+  double kmax, ea, eb, p_min, w_risk, vmax, inv_vmax, max_distance, half_w, thr_lon_a, thr_lon_j, thr_lat_a, thr_lat_j;
   double cw[8];
   // tables
   const double* time;
@@ -260,7 +269,7 @@ struct EvalParams {
   const float4* narrow;
   const double* obs64;
   const double* ext64;
-  int OM, Tt, win_rows, smem_obs;
+  int OM, OMpad, Tt, win_rows, smem_obs;
   // outputs
   uint8_t* feasible;
   uint8_t* collision;
@@ -269,10 +278,11 @@ struct EvalParams {
   int* blk_idx;
   unsigned int* ticket;
   BestRecord* best;
+  double* best_traj;              // [P][16] export of the selected trajectory (NULL = skip)
 };
 
 struct BlockTables {
-  const float4* broad;   // window rows [win_rows][OM] (shared) or the global table
+  const float4* broad;   // window rows [win_rows][OMpad] (shared) or the global table [Tt][OMpad]
   int broad_row0;        // 0 for the shared window, time_step_now for the global table
   int broad_stride;      // rows advance by check_res in the global table, 1 in the window
   SplineView sp;
@@ -282,12 +292,12 @@ struct BlockTables {
 
 // Walks one candidate through the horizon and hands every derived quantity to `sink`, in the order the reference
 // derives them (get_one_frenet_trajectory -> calc_global_paths).  Used by the evaluation, export and dump kernels so
-// that all three see identical arithmetic.
+// that all three see the same positions.
 //   sink.sample(i, t, s, sd, sdd, sddd)                      every i in [0, P)
 //   sink.point(i, x, y)                                      i < n_pts
-//   sink.segment(i, x_i, y_i, dx, dy, yaw_i, ds_i)           i < n_pts - 1  (yaw_i = atan2(dy, dx), forward difference)
-//   sink.curvature(i, dyaw, ds_i)                            i < n_pts - 2  (c_i = dyaw / ds_i, no unwrapping)
-//   sink.finish(n_pts, x_L, y_L, yaw_{L-1}, cos, sin, ds_{L-1})   once; L = n_pts - 1
+//   sink.segment(i, x_i, y_i, dx, dy, ds_i, cos, sin)        i < n_pts - 1: forward difference p_{i+1} - p_i, its length
+//                                                            and unit vector ((1, 0) when the length is 0: atan2(0,0) = 0)
+//   sink.finish(n_pts, x_L, y_L)                             once; L = n_pts - 1
 template <class Sink>
 __device__ __forceinline__ void walk_candidate(const EvalParams& p, const BlockTables& tb, const LonProfile& lp, int w,
                                                int seg, Sink& sink) {
@@ -295,7 +305,7 @@ __device__ __forceinline__ void walk_candidate(const EvalParams& p, const BlockT
   const double* lat = tb.lat + (size_t)w * P * 4;
   bool live = true;
   int n_pts = P;
-  double xp = 0, yp = 0, thp = 0, dsp = 0, cp = 1, sp_ = 0;
+  double xp = 0, yp = 0;
   for (int i = 0; i < P; ++i) {
     const double t = tb.time[i];
     double s, sd, sdd, sddd;
@@ -313,24 +323,25 @@ __device__ __forceinline__ void walk_candidate(const EvalParams& p, const BlockT
     sink.point(i, x, y);
     if (i >= 1) {
       const double dx = x - xp, dy = y - yp;
-      const double th = atan2(dy, dx);
-      const double ds = hypot_safe(dx, dy);
-      double c = 1.0, sn = 0.0;           // atan2(0, 0) = 0 -> axis-aligned box when the car does not move
-      if (ds > 0.0) { const double inv = 1.0 / ds; c = dx * inv; sn = dy * inv; }
-      if (i >= 2) sink.curvature(i - 2, th - thp, dsp);
-      sink.segment(i - 1, xp, yp, dx, dy, th, ds, c, sn);
-      thp = th; dsp = ds; cp = c; sp_ = sn;
+      const double q = dx * dx + dy * dy;
+      double ds, c = 1.0, sn = 0.0;
+      if (q > 1e-200 && q < 1e200) { const double inv = rsqrt(q); ds = q * inv; c = dx * inv; sn = dy * inv; }
+      else { ds = hypot(dx, dy); if (ds > 0.0) { c = dx / ds; sn = dy / ds; } }
+      sink.segment(i - 1, xp, yp, dx, dy, ds, c, sn);
     }
     xp = x; yp = y;
   }
-  sink.finish(n_pts, xp, yp, thp, cp, sp_, dsp);
+  sink.finish(n_pts, xp, yp);
 }
+
+__device__ __forceinline__ double heading_of(double dx, double dy) { return atan2(dy, dx); }   // np.arctan2(y_d, x_d)
 
 // -- the evaluation sink ---------------------------------------------------------------------------------------------
 struct EvalSink {
   const EvalParams& p;
   const BlockTables& tb;
   double sum_a = 0, sum_j = 0, sum_v = 0, s_first = 0, s_last = 0, risk = 0;
+  double pdx = 0, pdy = 0, pds = 0, pc = 1, psn = 0;   // previous segment (difference, length, unit vector)
   bool curv_fail = false, collided = false;
   __device__ __forceinline__ EvalSink(const EvalParams& p_, const BlockTables& tb_) : p(p_), tb(tb_) {}
 
@@ -339,51 +350,79 @@ struct EvalSink {
     s_last = s;
     const double ea = fmax(fabs(sdd) - p.thr_lon_a, 0.0);
     const double ej = fmax(fabs(sddd) - p.thr_lon_j, 0.0);
-    const double ev = (p.vmax - sd) / p.vmax;
+    const double ev = (p.vmax - sd) * p.inv_vmax;
     sum_a = sum_a + ea * ea;
     sum_j = sum_j + ej * ej;
     sum_v = sum_v + ev * ev;
   }
   __device__ __forceinline__ void point(int, double, double) {}
-  __device__ __forceinline__ void curvature(int, double dyaw, double ds) {
-    // |dyaw / ds| > kmax  (jerk_space_sampling_planner.py:175); ds == 0: inf fails, nan passes
-    if (fabs(dyaw) > p.kmax * ds) curv_fail = true;
+
+  // c_{i-1} = (yaw_i - yaw_{i-1}) / ds_{i-1} with yaw = arctan2 of the forward differences and NO unwrapping
+  // (jerk_space_sampling_planner.py:155-163); the candidate fails when |c| > kmax (:175).  Fast path: the wrapped angle
+  // between the two difference vectors from fp32 atan2f of their float64 cross / dot products, the +-2*pi jump of the
+  // un-unwrapped difference from the exact signs, and a relative guard band inside which the float64 atan2 decides.
+  __device__ __forceinline__ void curvature_step(double dx, double dy, double ds, double c, double sn) {
+    const double phi = p.kmax * pds;
+    bool exact = !(pds > 0.0) || !(ds > 0.0);
+    if (!exact) {
+      const double cr = pc * sn - psn * c, dt = pc * c + psn * sn;      // unit vectors: |cr|, |dt| <= 1
+      const float w = fabsf(atan2f((float)cr, (float)dt));
+      const bool na = signbit(pdy), nb = signbit(dy);
+      const bool wrap = (na != nb) && (nb ? (cr > 0.0) : (cr < 0.0));
+      const float dabs = wrap ? 6.2831853071795864769f - w : w;
+      const float pf = (float)phi;
+      if (fabsf(dabs - pf) > 4e-6f * fmaxf(dabs, pf) && pf > 1e-30f) { if (dabs > pf) curv_fail = true; }
+      else exact = true;
+    }
+    if (exact) {
+      const double dyaw = heading_of(dx, dy) - heading_of(pdx, pdy);
+      if (fabs(dyaw) > phi) curv_fail = true;      // pds == 0: inf fails (dyaw != 0), nan passes (dyaw == 0)
+    }
   }
+
   __device__ __forceinline__ void collide(int i, double x, double y, double c, double sn) {
     if (collided || p.n_dict <= 0 || i >= p.tcap || (i % p.check_res) != 0) return;
     const int abs_step = p.now + i;
     if (abs_step >= p.Tt) return;
     const int r = i / p.check_res;
-    const float4* row = tb.broad + (size_t)(tb.broad_row0 + r * tb.broad_stride) * p.OM;
-    const float fx = (float)(x - p.ox), fy = (float)(y - p.oy), fc = (float)c, fs = (float)sn;
-    const float fea = (float)p.ea, feb = (float)p.eb;
-#pragma unroll 4
-    for (int om = 0; om < p.OM; ++om) {
-      const float4 b = row[om];
-      const float dx = b.x - fx, dy = b.y - fy;
-      const float d2 = fmaf(dx, dx, dy * dy);
-      if (d2 <= b.z) {
+    const float4* row = tb.broad + (size_t)(tb.broad_row0 + r * tb.broad_stride) * p.OMpad;
+    const float fx = (float)(x - p.ox), fy = (float)(y - p.oy);
+    const float m2x = -2.0f * fx, m2y = -2.0f * fy, ne2 = -fmaf(fx, fx, fy * fy);
+    for (int base = 0; base < p.OMpad; base += 32) {
+      unsigned int mask = 0u;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float4 b = row[base + j];
+        const float t = fmaf(b.x, m2x, fmaf(b.y, m2y, b.z));
+        mask |= (t <= ne2) ? (1u << j) : 0u;
+      }
+      while (mask) {      // rare: bounding circles overlap -> separating-axis test
+        const int om = base + __ffs(mask) - 1;
+        mask &= mask - 1u;
+        const float4 b = row[om];
         const size_t gi = (size_t)abs_step * p.OM + om;
         const float4 nb = __ldg(p.narrow + gi);
-        const int cls = sat_classify_f32(dx, dy, fc, fs, fea, feb, nb.x, nb.y, nb.z, nb.w, SAT_EPS);
+        const int cls = sat_classify_f32(b.x - fx, b.y - fy, (float)c, (float)sn, (float)p.ea, (float)p.eb, nb.x, nb.y, nb.z, nb.w, SAT_EPS);
         bool hit = cls < 0;
         if (cls == 0) {
           const double* q = p.obs64 + gi * 4;
           hit = sat_intersects_f64(q[0] - x, q[1] - y, c, sn, p.ea, p.eb, q[2], q[3], p.ext64[2 * om], p.ext64[2 * om + 1]);
         }
         if (hit) {
-          if ((double)b.w >= p.p_min) { collided = true; break; }
+          if ((double)b.w >= p.p_min) { collided = true; return; }
           risk = risk + (double)b.w;
         }
       }
     }
   }
-  __device__ __forceinline__ void segment(int i, double x, double y, double, double, double, double, double c, double sn) {
+  __device__ __forceinline__ void segment(int i, double x, double y, double dx, double dy, double ds, double c, double sn) {
+    if (i >= 1) curvature_step(dx, dy, ds, c, sn);
     collide(i, x, y, c, sn);
+    pdx = dx; pdy = dy; pds = ds; pc = c; psn = sn;
   }
-  __device__ __forceinline__ void finish(int n_pts, double x, double y, double, double c, double sn, double) {
-    if (n_pts >= 2) collide(n_pts - 1, x, y, c, sn);   // last point reuses the previous heading (:158-160)
-    else if (n_pts == 1 && p.n_dict > 0 && p.tcap >= 1) collided = true;   // bare except -> collision (:250-254)
+  __device__ __forceinline__ void finish(int n_pts, double x, double y) {
+    if (n_pts >= 2) collide(n_pts - 1, x, y, pc, psn);                      // last point reuses the previous heading (:158-160)
+    else if (n_pts == 1 && p.n_dict > 0 && p.tcap >= 1) collided = true;    // bare except -> collision (:250-254)
   }
 };
 
@@ -400,14 +439,14 @@ __device__ __forceinline__ double candidate_cost(const EvalParams& p, const Eval
   return cost;
 }
 
-// dynamic shared memory carve-up (host mirrors this in eval_smem_bytes)
+// dynamic shared memory carve-up (the host uses the same function to size the launch)
 struct SmemLayout {
   size_t off_broad, off_knot, off_coef, off_time, off_lat, off_latcost, total;
 };
-__host__ __device__ inline SmemLayout eval_smem_layout(int win_rows, int OM, int smem_obs, int K, int kpad, int P, int W) {
+__host__ __device__ inline SmemLayout eval_smem_layout(int win_rows, int OMpad, int smem_obs, int K, int kpad, int P, int W) {
   SmemLayout L;
   size_t o = 16;   // mbarrier
-  L.off_broad = o; o += smem_obs ? (size_t)win_rows * OM * 16 : 0;
+  L.off_broad = o; o += smem_obs ? (size_t)win_rows * OMpad * 16 : 0;
   L.off_knot = o; o += (size_t)((K + 1) & ~1) * 8;
   L.off_coef = o; o += (size_t)8 * kpad * 8;
   L.off_time = o; o += (size_t)((P + 1) & ~1) * 8;
@@ -417,10 +456,11 @@ __host__ __device__ inline SmemLayout eval_smem_layout(int win_rows, int OM, int
   return L;
 }
 
-// Stage the per-block tables: obstacle window by bulk copy (one row per issued copy, all on one mbarrier), spline,
-// time grid and the lateral quintic samples (jerk_space_sampling_planner.py:118-122) by ordinary loads.
+// Stage the per-block tables: obstacle window by bulk copy (TMA engine; one row per issued copy, all completing on one
+// mbarrier), spline, time grid and the lateral quintic samples (jerk_space_sampling_planner.py:118-122) by ordinary loads.
+template <bool kSmem>
 __device__ __forceinline__ void stage_tables(const EvalParams& p, unsigned char* smem, BlockTables& tb, const double*& latcost) {
-  const SmemLayout L = eval_smem_layout(p.win_rows, p.OM, p.smem_obs, p.K, p.kpad, p.P, p.W);
+  const SmemLayout L = eval_smem_layout(p.win_rows, p.OMpad, kSmem ? 1 : 0, p.K, p.kpad, p.P, p.W);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   float4* sm_broad = reinterpret_cast<float4*>(smem + L.off_broad);
   double* sm_knot = reinterpret_cast<double*>(smem + L.off_knot);
@@ -429,9 +469,9 @@ __device__ __forceinline__ void stage_tables(const EvalParams& p, unsigned char*
   double* sm_lat = reinterpret_cast<double*>(smem + L.off_lat);
   double* sm_latcost = reinterpret_cast<double*>(smem + L.off_latcost);
   const int tid = threadIdx.x, nt = blockDim.x;
-  const uint32_t row_bytes = (uint32_t)p.OM * 16u;
+  const uint32_t row_bytes = (uint32_t)p.OMpad * 16u;
   int rows_avail = 0;
-  if (p.smem_obs) {
+  if (kSmem) {
     // rows of the window that exist in the scenario table: absolute step now + r*check_res < Tt
     for (int r = 0; r < p.win_rows; ++r) rows_avail += (p.now + r * p.check_res < p.Tt) ? 1 : 0;
     if (tid == 0) mbar_init(bar, 1);
@@ -440,9 +480,9 @@ __device__ __forceinline__ void stage_tables(const EvalParams& p, unsigned char*
       if (tid == 0) mbar_arrive_expect_tx(bar, row_bytes * (uint32_t)rows_avail);
       __syncwarp();
       for (int r = tid; r < rows_avail; r += 32)
-        bulk_copy_g2s(sm_broad + (size_t)r * p.OM, p.broad + (size_t)(p.now + r * p.check_res) * p.OM, row_bytes, bar);
+        bulk_copy_g2s(sm_broad + (size_t)r * p.OMpad, p.broad + (size_t)(p.now + r * p.check_res) * p.OMpad, row_bytes, bar);
     }
-    for (int e = rows_avail * p.OM + tid; e < p.win_rows * p.OM; e += nt) sm_broad[e] = make_float4(FAR_AWAY, FAR_AWAY, 0.f, 0.f);
+    for (int e = rows_avail * p.OMpad + tid; e < p.win_rows * p.OMpad; e += nt) sm_broad[e] = make_float4(0.f, 0.f, FAR_AWAY, 0.f);
   }
   for (int e = tid; e < p.K; e += nt) sm_knot[e] = p.knot[e];
   for (int e = tid; e < 8 * p.kpad; e += nt) sm_coef[e] = p.coef[e];
@@ -466,7 +506,7 @@ __device__ __forceinline__ void stage_tables(const EvalParams& p, unsigned char*
     sm_latcost[tid * 4] = s0; sm_latcost[tid * 4 + 1] = s1; sm_latcost[tid * 4 + 2] = s2;
   }
   __syncthreads();
-  if (p.smem_obs) {
+  if (kSmem) {
     if (rows_avail > 0) mbar_wait(bar, 0);
     tb.broad = sm_broad; tb.broad_row0 = 0; tb.broad_stride = 1;
   } else {
@@ -488,20 +528,80 @@ __device__ __forceinline__ bool lex_less(double ca, int ia, double cb, int ib) {
   return ca < cb || (ca == cb && ia < ib);
 }
 
-__global__ void __launch_bounds__(EVAL_THREADS) evaluate_kernel(const __grid_constant__ EvalParams p) {
+// Export of the selected trajectory by one thread block: thread i owns sample i.  Positions come from the same
+// lon_eval / frenet_point arithmetic as the evaluation walk (bisect and walk select the same spline segment), headings are
+// the float64 arctan2 of the forward differences exactly as jerk_space_sampling_planner.py:155-165 derives them.
+// `out` (global, [P][16]) doubles as the exchange buffer between the phases.
+__device__ __forceinline__ void export_block(const EvalParams& p, const BlockTables& tb, int best, double* __restrict__ out,
+                                             int* sm_npts) {
+  const int P = p.P, i = threadIdx.x;
+  const int Ns = resolve_n_seeds(p);
+  const int w = best / Ns, k = best - w * Ns;
+  const double* lat = tb.lat + (size_t)w * P * 4;
+  if (i == 0) *sm_npts = P;
+  __syncthreads();
+  double s = 0.0;
+  bool inr = false;
+  for (int j = i; j < P; j += blockDim.x) {      // blockDim >= P in practice; the loop keeps small blocks correct
+    LonProfile lp;
+    lon_profile_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
+    double sd, sdd, sddd;
+    lon_eval(lp, p.s0, p.v0, p.a0, tb.time[j], s, sd, sdd, sddd);
+    double* r = out + (size_t)j * JSSP_TRAJ_COLS;
+    r[0] = tb.time[j]; r[1] = s; r[2] = sd; r[3] = sdd; r[4] = sddd;
+    r[5] = lat[j * 4]; r[6] = lat[j * 4 + 1]; r[7] = lat[j * 4 + 2]; r[8] = lat[j * 4 + 3];
+    for (int c = 9; c < JSSP_TRAJ_COLS; ++c) r[c] = nan("");
+    inr = spline_in_range(tb.sp, s);
+    if (!inr) atomicMin(sm_npts, j);             // first sample off the reference line ends the Cartesian path (:138-139)
+  }
+  __syncthreads();
+  const int np = *sm_npts;
+  for (int j = i; j < np; j += blockDim.x) {
+    const double sj = out[(size_t)j * JSSP_TRAJ_COLS + 1];
+    double x, y;
+    frenet_point(tb.sp, spline_bisect(tb.sp, sj), sj, lat[j * 4], x, y);
+    out[(size_t)j * JSSP_TRAJ_COLS + 9] = x; out[(size_t)j * JSSP_TRAJ_COLS + 10] = y;
+  }
+  __syncthreads();
+  for (int j = i; j + 1 < np; j += blockDim.x) {
+    const double dx = out[(size_t)(j + 1) * JSSP_TRAJ_COLS + 9] - out[(size_t)j * JSSP_TRAJ_COLS + 9];
+    const double dy = out[(size_t)(j + 1) * JSSP_TRAJ_COLS + 10] - out[(size_t)j * JSSP_TRAJ_COLS + 10];
+    const double q = dx * dx + dy * dy;
+    out[(size_t)j * JSSP_TRAJ_COLS + 11] = heading_of(dx, dy);
+    out[(size_t)j * JSSP_TRAJ_COLS + 12] = (q > 1e-200 && q < 1e200) ? q * rsqrt(q) : hypot(dx, dy);
+  }
+  __syncthreads();
+  if (i == 0 && np >= 2) out[(size_t)(np - 1) * JSSP_TRAJ_COLS + 11] = out[(size_t)(np - 2) * JSSP_TRAJ_COLS + 11];   // yaw[-1] repeated
+  __syncthreads();
+  for (int j = i; j + 1 < np; j += blockDim.x)
+    out[(size_t)j * JSSP_TRAJ_COLS + 13] = (out[(size_t)(j + 1) * JSSP_TRAJ_COLS + 11] - out[(size_t)j * JSSP_TRAJ_COLS + 11]) / out[(size_t)j * JSSP_TRAJ_COLS + 12];
+  __syncthreads();
+  const double dt = tb.time[1] - tb.time[0];
+  for (int j = i; j + 2 < np; j += blockDim.x)
+    out[(size_t)j * JSSP_TRAJ_COLS + 14] = (out[(size_t)(j + 1) * JSSP_TRAJ_COLS + 13] - out[(size_t)j * JSSP_TRAJ_COLS + 13]) / dt;
+  __syncthreads();
+  for (int j = i; j + 3 < np; j += blockDim.x)
+    out[(size_t)j * JSSP_TRAJ_COLS + 15] = (out[(size_t)(j + 1) * JSSP_TRAJ_COLS + 14] - out[(size_t)j * JSSP_TRAJ_COLS + 14]) / dt;
+  if (i == 0) p.best->n_pts = np;
+}
+
+template <bool kSmem>
+__global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_kernel(const __grid_constant__ EvalParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ double red_cost[EVAL_THREADS / 32];
   __shared__ int red_idx[EVAL_THREADS / 32];
   __shared__ bool is_last;
+  __shared__ int sm_npts;
   const int Ns = resolve_n_seeds(p);
   const int N = Ns * p.W;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   double my_cost = INFINITY;
   int my_idx = -1;
-  if (blockIdx.x * blockDim.x < N) {   // block-uniform
-    BlockTables tb;
-    const double* latcost;
-    stage_tables(p, smem, tb, latcost);
+  BlockTables tb;
+  const double* latcost;
+  const bool staged = blockIdx.x * blockDim.x < N;   // block-uniform
+  if (staged) {
+    stage_tables<kSmem>(p, smem, tb, latcost);
     if (n < N) {
       const int w = n / Ns, k = n - w * Ns;
       LonProfile lp;
@@ -566,72 +666,24 @@ __global__ void __launch_bounds__(EVAL_THREADS) evaluate_kernel(const __grid_con
     r.pad = 0;
     *p.best = r;
     *p.ticket = 0u;   // re-arm for the next launch (stream-ordered)
+    red_idx[0] = my_idx;
   }
+  // the same block exports the winner: no second launch, no host round trip in between
+  if (p.best_traj == nullptr) return;
+  __syncthreads();
+  const int best = red_idx[0];
+  if (best < 0) return;
+  if (!staged) stage_tables<kSmem>(p, smem, tb, latcost);
+  export_block(p, tb, best, p.best_traj, &sm_npts);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // K3: export of the selected trajectory (float64 rows) and optional fp32 state dump of every candidate
 // ------------------------------------------------------------------------------------------------------------------
-struct ExportSink {
-  double* out;   // [P][16]
-  const double* lat;
-  int P;
-  int n_pts;
-  __device__ __forceinline__ void sample(int i, double t, double s, double sd, double sdd, double sddd) {
-    double* r = out + (size_t)i * JSSP_TRAJ_COLS;
-    r[0] = t; r[1] = s; r[2] = sd; r[3] = sdd; r[4] = sddd;
-    r[5] = lat[i * 4]; r[6] = lat[i * 4 + 1]; r[7] = lat[i * 4 + 2]; r[8] = lat[i * 4 + 3];
-    for (int c = 9; c < JSSP_TRAJ_COLS; ++c) r[c] = nan("");
-  }
-  __device__ __forceinline__ void point(int i, double x, double y) {
-    out[(size_t)i * JSSP_TRAJ_COLS + 9] = x; out[(size_t)i * JSSP_TRAJ_COLS + 10] = y;
-  }
-  __device__ __forceinline__ void curvature(int i, double dyaw, double ds) { out[(size_t)i * JSSP_TRAJ_COLS + 13] = dyaw / ds; }
-  __device__ __forceinline__ void segment(int i, double, double, double, double, double yaw, double ds, double, double) {
-    out[(size_t)i * JSSP_TRAJ_COLS + 11] = yaw; out[(size_t)i * JSSP_TRAJ_COLS + 12] = ds;
-  }
-  __device__ __forceinline__ void finish(int n_pts_, double, double, double yaw, double, double, double ds) {
-    n_pts = n_pts_;
-    if (n_pts >= 2) {
-      out[(size_t)(n_pts - 1) * JSSP_TRAJ_COLS + 11] = yaw;           // yaw = append(yaw, yaw[-1])
-      out[(size_t)(n_pts - 2) * JSSP_TRAJ_COLS + 13] = (yaw - yaw) / ds;   // c[n-2] = diff(yaw)[-1] / ds[-1]
-    }
-  }
-};
-
-__global__ void export_best_kernel(const __grid_constant__ EvalParams p, double* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  EvalParams q = p;
-  q.smem_obs = 0;   // no obstacle window needed
-  BlockTables tb;
-  const double* latcost;
-  // layout without the obstacle window
-  {
-    EvalParams& r = q;
-    r.win_rows = 0;
-  }
-  stage_tables(q, smem, tb, latcost);
-  const long long best = p.best->idx;
-  if (threadIdx.x != 0) return;
-  if (best < 0) { p.best->n_pts = 0; return; }
-  const int Ns = resolve_n_seeds(p);
-  const int n = (int)best, w = n / Ns, k = n - w * Ns;
-  LonProfile lp;
-  lon_profile_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
-  ExportSink sink{out, tb.lat + (size_t)w * p.P * 4, p.P, 0};
-  const int seg0 = spline_bisect(tb.sp, fmin(fmax(p.s0, tb.sp.knot[0]), tb.sp.knot[p.K - 1]));
-  walk_candidate(p, tb, lp, w, seg0, sink);
-  // c_d = diff(c)/dt, c_dd = diff(c_d)/dt (jerk_space_sampling_planner.py:164-165)
-  const double dt = tb.time[1] - tb.time[0];
-  const int np = sink.n_pts;
-  for (int i = 0; i + 2 < np; ++i) out[(size_t)i * JSSP_TRAJ_COLS + 14] = (out[(size_t)(i + 1) * JSSP_TRAJ_COLS + 13] - out[(size_t)i * JSSP_TRAJ_COLS + 13]) / dt;
-  for (int i = 0; i + 3 < np; ++i) out[(size_t)i * JSSP_TRAJ_COLS + 15] = (out[(size_t)(i + 1) * JSSP_TRAJ_COLS + 14] - out[(size_t)i * JSSP_TRAJ_COLS + 14]) / dt;
-  p.best->n_pts = np;
-}
-
 struct DumpSink {
   float* out;   // [P][8] of this candidate: s, s_d, s_dd, d, x, y, yaw, c
   const double* lat;
+  double pyaw, pds;
   __device__ __forceinline__ void sample(int i, double, double s, double sd, double sdd, double) {
     float4* r = reinterpret_cast<float4*>(out + (size_t)i * JSSP_STATE_COLS);
     const float nanv = __int_as_float(0x7fc00000);
@@ -641,14 +693,16 @@ struct DumpSink {
   __device__ __forceinline__ void point(int i, double x, double y) {
     out[(size_t)i * JSSP_STATE_COLS + 4] = (float)x; out[(size_t)i * JSSP_STATE_COLS + 5] = (float)y;
   }
-  __device__ __forceinline__ void curvature(int i, double dyaw, double ds) { out[(size_t)i * JSSP_STATE_COLS + 7] = (float)(dyaw / ds); }
-  __device__ __forceinline__ void segment(int i, double, double, double, double, double yaw, double, double, double) {
+  __device__ __forceinline__ void segment(int i, double, double, double dx, double dy, double ds, double, double) {
+    const double yaw = heading_of(dx, dy);
     out[(size_t)i * JSSP_STATE_COLS + 6] = (float)yaw;
+    if (i >= 1) out[(size_t)(i - 1) * JSSP_STATE_COLS + 7] = (float)((yaw - pyaw) / pds);
+    pyaw = yaw; pds = ds;
   }
-  __device__ __forceinline__ void finish(int n_pts, double, double, double yaw, double, double, double ds) {
+  __device__ __forceinline__ void finish(int n_pts, double, double) {
     if (n_pts >= 2) {
-      out[(size_t)(n_pts - 1) * JSSP_STATE_COLS + 6] = (float)yaw;
-      out[(size_t)(n_pts - 2) * JSSP_STATE_COLS + 7] = (float)((yaw - yaw) / ds);
+      out[(size_t)(n_pts - 1) * JSSP_STATE_COLS + 6] = (float)pyaw;
+      out[(size_t)(n_pts - 2) * JSSP_STATE_COLS + 7] = (float)((pyaw - pyaw) / pds);
     }
   }
 };
@@ -660,13 +714,13 @@ __global__ void __launch_bounds__(EVAL_THREADS) dump_states_kernel(const __grid_
   if (blockIdx.x * blockDim.x >= N) return;
   BlockTables tb;
   const double* latcost;
-  stage_tables(p, smem, tb, latcost);   // p.smem_obs == 0 for this launch
+  stage_tables<false>(p, smem, tb, latcost);
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int w = n / Ns, k = n - w * Ns;
   LonProfile lp;
   lon_profile_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
-  DumpSink sink{states + (size_t)n * p.P * JSSP_STATE_COLS, tb.lat + (size_t)w * p.P * 4};
+  DumpSink sink{states + (size_t)n * p.P * JSSP_STATE_COLS, tb.lat + (size_t)w * p.P * 4, 0.0, 0.0};
   const int seg0 = spline_bisect(tb.sp, fmin(fmax(p.s0, tb.sp.knot[0]), tb.sp.knot[p.K - 1]));
   walk_candidate(p, tb, lp, w, seg0, sink);
 }
