@@ -101,10 +101,10 @@ def parse_openscenario(path: str, name: Optional[str] = None) -> ReplayScenario:
     doc = xml.dom.minidom.parse(path).documentElement
     dims = [(float(n.getAttribute("length")), float(n.getAttribute("width"))) for n in doc.getElementsByTagName("Dimensions")]
     private = doc.getElementsByTagName("Private")[0]
-    comments = [n.data for n in private.childNodes if n.nodeType == n.COMMENT_NODE]
-    ev, ex, ey, eh = [float(tok.split("=")[1]) for tok in comments[0].split(",")]
+    ego_init, goal_init = private.childNodes[3].data, private.childNodes[5].data        # positional, like controller.py:177-178,215
+    ev, ex, ey, eh = [float(tok.split("=")[1]) for tok in ego_init.split(",")]
     ego = {"length": dims[0][0], "width": dims[0][1], "x": ex, "y": ey, "v": abs(ev), "a": 0, "yaw": _wrap_pi(eh)}
-    gl = [float(v) for v in re.findall(r"-*\d+\.\d+", comments[1])]
+    gl = [float(v) for v in re.findall(r"-*\d+\.\d+", goal_init)]
     goal = {"x": gl[:2], "y": gl[2:]}
     traj: Dict[int, dict] = {}
     last_keys = None

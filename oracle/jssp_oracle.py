@@ -129,6 +129,7 @@ def sample_main_seeds(s0, v0, a0, g, a_max=8.0, v_max=18.0) -> np.ndarray:
     """PolyVTSampling.sampling (polyvt_sampling.py:167-263) as one flat predicate over the
     (j1, t1, t2, j3, t3, t4) grid; survivors are emitted in the reference's loop (= C) order."""
     T = g["total_time"]
+    _err = np.seterr(all="ignore")      # inf * 0 etc. inside rejected grid points, as in the reference's scalar code
     J1, T1, T2, J3, T3, T4 = np.meshgrid(g["j1"], g["t1"], g["t2"], g["j3"], g["t3"], g["t4"], indexing="ij")
     ok = ~(T1 < 0.55)                                                    # :183-184
     s1, v1, a1 = _st(s0, v0, a0, J1, T1), _vt(v0, a0, J1, T1), _at(a0, J1, T1)
@@ -155,6 +156,7 @@ def sample_main_seeds(s0, v0, a0, g, a_max=8.0, v_max=18.0) -> np.ndarray:
     ok &= ~((J5 > g["jmax5"]) | (J5 < g["jmin5"]))                        # :246-247
     s5, v5, a5 = _st(s4, v4, a4, J5, T5), _vt(v4, a4, J5, T5), _at(a4, J5, T5)
     ok &= _check_state(s5, v5, a5, s4, a_max, v_max)                      # :252
+    np.seterr(**_err)
     idx = np.nonzero(ok.ravel())[0]                                       # C order == loop order
     z = np.zeros(len(idx))
     cols = [J1.ravel()[idx], T1.ravel()[idx], z, T2.ravel()[idx], J3.ravel()[idx], T3.ravel()[idx],

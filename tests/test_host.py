@@ -1,0 +1,143 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header declares, host-only entry
+points agree with NumPy / the oracle, the reference-shaped containers behave, and nothing falls back to the CPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import dlii_jssp_b200 as J
+from dlii_jssp_b200 import _lib, scenario as S
+from oracle import jssp_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "jssp_b200.h")).read()
+    declared = set(re.findall(r"\b(jssp_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no prototypes found in the header"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/jssp_b200.h but not exported"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert lib.jssp_abi_version() == 1
+    assert b"no CPU fallback" in lib.jssp_strerror(-6)
+
+
+def test_struct_layouts_match_header():
+    lib = _lib.load()
+    cfg = _lib.JsspConfigC()
+    lib.jssp_default_config(C.byref(cfg))
+    d = J.JsspConfig()
+    for f, _ in _lib.JsspConfigC._fields_:
+        if f in ("reserved0",):
+            continue
+        v = getattr(cfg, f)
+        if f == "cost_weights":
+            assert list(v) == list(d.cost_weights)
+        else:
+            assert v == getattr(d, f), f          # ctypes layout == C layout, field by field
+    assert C.sizeof(_lib.JsspCycleIn) == 6 * 8 + 4 * 4 + 16 * 8 + 8 + 8
+    assert C.sizeof(_lib.JsspCycleOut) == 5 * 8 + 4 * 4 + 8
+
+
+@pytest.mark.parametrize("T,jerk,ns", [(5.0, 10.0, 25), (5.0, 13.4112, 25), (8.0, 10.0, 13), (3.0, 7.5, 9)])
+def test_host_grids_bit_identical_to_numpy(T, jerk, ns):
+    lib = _lib.load()
+    n = (C.c_int32 * 9)()
+    arr = [np.zeros(512) for _ in range(9)]
+    assert lib.jssp_make_grids(T, jerk, ns, 512, *[a.ctypes.data for a in arr], C.byref(n)) == 0
+    g = O.make_grids(T, jerk, ns)
+    for k, name in enumerate(["time_array", "j1", "t1", "t2", "j3", "t3", "t4", "js", "ts"]):
+        assert np.array_equal(arr[k][: n[k]], g[name]), name
+
+
+def test_quintic_closed_form_matches_linear_solve():
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        xs, vs, a_s, xe = rng.normal(0, 1, 4)
+        T = rng.uniform(2, 9)
+        out = (C.c_double * 6)()
+        lib.jssp_quintic_coeffs(xs, vs, a_s, xe, 0.0, 0.0, T, C.byref(out))
+        q = O.QuinticPolynomial(xs, vs, a_s, xe, 0.0, 0.0, T)
+        np.testing.assert_allclose(list(out), [q.a0, q.a1, q.a2, q.a3, q.a4, q.a5], rtol=1e-9, atol=1e-12)
+        p = J.QuinticPolynomial(xs, vs, a_s, xe, 0.0, 0.0, T)
+        assert np.allclose([p.a3, p.a4, p.a5], list(out)[3:], rtol=1e-13, atol=0)
+
+
+def test_product_spline_matches_oracle_spline(scenario_fixture):
+    xy = scenario_fixture.route_xy
+    a, b = J.CubicSpline2D(xy[:, 0], xy[:, 1]), O.CubicSpline2D(xy[:, 0], xy[:, 1])
+    assert np.array_equal(a.s_list, b.s_list)
+    np.testing.assert_allclose(a.coefficient_table(), b.coefficient_table(), rtol=1e-9, atol=1e-11)   # Thomas vs dense solve
+    knot, coef = J.spline_tables(b)                     # any PythonRobotics-shaped object can be uploaded
+    assert np.array_equal(coef, b.coefficient_table()) and np.array_equal(knot, b.s_list)
+    for s in (0.0, 3.3, a.s_list[-1]):
+        pa, pb = a.calc_position(s), b.calc_position(s)
+        assert np.allclose(pa, pb, atol=1e-9) and np.isclose(a.calc_yaw(s), float(b.calc_yaw(s)), atol=1e-9)
+    assert a.calc_position(a.s_list[-1] + 1e-6) == (None, None)
+
+
+def test_openscenario_parser_matches_reference_parser(scenario_fixture):
+    """Only where the reference tree is mounted (the build container): our parser against the fixture that the
+    reference's own ReplayParser produced."""
+    path = "/root/reference/inputs/8_3_4_565/8_3_4_565_exam.xosc"
+    if not os.path.exists(path):
+        pytest.skip("reference data not mounted")
+    sc, fx = S.parse_openscenario(path, "8_3_4_565"), scenario_fixture
+    assert sc.dt == fx.dt and sc.max_t == fx.max_t and sc.goal == fx.goal
+    for k in ("x", "y", "v", "yaw", "length", "width"):
+        assert sc.ego[k] == fx.ego[k], k
+    assert set(sc.vehicle_traj) == set(fx.vehicle_traj)
+    for vid, tr in fx.vehicle_traj.items():
+        assert tr == sc.vehicle_traj[vid], vid
+
+
+def test_trajectory_container_contract():
+    rows = np.full((51, 16), np.nan)
+    rows[:, :9] = np.arange(51 * 9).reshape(51, 9)
+    rows[:40, 9:12] = 1.0; rows[:39, 12:14] = 2.0; rows[:38, 14] = 3.0; rows[:37, 15] = 4.0
+    tr = J.JerkSpaceSamplingFrenetTrajectory.from_rows(rows, 40, idx=7, path_id=1, cost=3.5)
+    assert len(tr.s) == 51 and len(tr.x) == 40 and len(tr.yaw) == 40 and len(tr.c) == 39 and len(tr.c_d) == 38 and len(tr.c_dd) == 37
+    fs = tr.frenet_state_at_time_step(t=1)
+    assert (fs.s, fs.s_d, fs.s_dd, fs.d, fs.d_d, fs.d_dd) == tuple(rows[1, [1, 2, 3, 5, 6, 7]])
+    other = J.JerkSpaceSamplingFrenetTrajectory.from_rows(rows, 40, idx=3, path_id=0, cost=3.5)
+    assert other < tr                                    # equal cost -> lowest candidate index first (PriorityQueue tie)
+    s = J.JerkSpaceSamplingPlannerSettings()
+    assert (s.num_width, s.num_jerk, s.highest_jerk, s.plan_horizon) == (5, 5, 13.4112, 5.0)     # reference class defaults
+    i = J.JerkSpaceSamplingPlannerSettings.intended()
+    assert (i.num_width, i.num_jerk, i.highest_jerk) == (3, 25, 10.0)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        J.JsspEngine()
+    h = C.c_void_p()
+    cfg = J.JsspConfig().to_c()
+    assert _lib.load().jssp_create(C.byref(cfg), 0, C.byref(h)) == -6      # JSSP_ERR_NO_DEVICE
+    # nothing under the product package imports the oracle
+    pkg = os.path.join(ROOT, "dlii-jssp_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            assert not re.search(r"^\s*(from|import)\s+oracle", open(os.path.join(pkg, fn)).read(), re.M), fn
+
+
+def test_synthetic_generators_are_seeded_and_valid():
+    a, b = S.dense_cycle(n_seeds=64, n_widths=2, O=4, M=2, seed=7), S.dense_cycle(n_seeds=64, n_widths=2, O=4, M=2, seed=7)
+    assert np.array_equal(a.seeds, b.seeds) and np.array_equal(a.obstacles.state, b.obstacles.state)
+    s, sd, sdd, _ = O.unroll_seeds(a.seeds, 0.0, 6.0, 0.0, np.linspace(0, 5, 51))
+    assert (sd > -1e-6).all() and (sd < 18.0).all() and (np.abs(sdd) < 8.0 + 1e-9).all()      # the grammar's limits hold
+    sc = S.synthetic_intersection(5)
+    assert 3 <= len(sc.vehicle_traj) <= 12 and sc.route_xy.shape[1] == 2
+    assert np.all(np.hypot(*np.diff(sc.route_xy, axis=0).T) > 1e-6)
+    t = S.pack_obstacle_dict(sc.vehicle_traj, sc.dt, 130)
+    assert t.valid.any()
+    d = S.tensors_to_dict(t, sc.dt)
+    t2 = S.pack_obstacle_dict(d, sc.dt, 130)
+    assert np.array_equal(t.valid, t2.valid) and np.allclose(t.state, t2.state)

@@ -1,0 +1,142 @@
+"""CPU tests of the oracle itself: pinned against golden vectors produced by RUNNING the reference's own
+polyvt_sampling.py (oracle/make_golden_polyvt.py), plus known-answer and property tests for the builder-specified pieces."""
+import math
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import jssp_oracle as O
+from oracle import jssp_loop as L
+
+warnings.filterwarnings("ignore", category=RuntimeWarning)
+
+# seed counts measured on the reference file: (v0, a0, J) -> (main, stop)
+REFERENCE_COUNTS = {(5.686, 0.0, 10.0): (175, 142), (0.0, 0.0, 10.0): (103, 625), (10.0, 1.0, 10.0): (112, 60), (17.0, 0.0, 10.0): (115, 13),
+                    (3.0, -2.0, 10.0): (42, 307), (0.0, 0.0, 13.4112): (97, 625), (10.0, 1.0, 13.4112): (95, 41), (3.0, -2.0, 13.4112): (37, 138)}
+
+
+def test_seeds_and_unroll_bit_identical_to_reference(polyvt_golden):
+    g = polyvt_golden
+    for k, (s0, v0, a0, J, T, ns) in enumerate(g["meta"]):
+        gr = O.make_grids(T, J, int(ns))
+        assert np.array_equal(gr["time_array"], g[f"c{k}_time"])
+        main, stop = O.sample_main_seeds(s0, v0, a0, gr), O.sample_stop_seeds(s0, v0, a0, gr)
+        assert np.array_equal(main, g[f"c{k}_main"]), k
+        assert np.array_equal(stop, g[f"c{k}_stop"]), k
+        seeds = np.concatenate([main, stop], 0)
+        s, sd, sdd, sddd = O.unroll_seeds(seeds[g[f"c{k}_pick"]], s0, v0, a0, gr["time_array"])
+        for a, b in zip((s, sd, sdd, sddd), g[f"c{k}_unroll"].transpose(1, 0, 2)):
+            assert np.array_equal(a, b), k
+        key = (round(float(v0), 3), float(a0), float(J))
+        if T == 5.0 and key in REFERENCE_COUNTS:
+            assert (len(main), len(stop)) == REFERENCE_COUNTS[key]
+
+
+def test_obb_known_answers():
+    hit = lambda *a: bool(O.obb_intersects(*[np.float64(v) for v in a]))
+    # unit squares (half extents 0.5): overlapping, exactly touching edge (closed sets -> intersect), separated
+    assert hit(0, 0, 1, 0, .5, .5, 0.9, 0, 1, 0, .5, .5)
+    assert hit(0, 0, 1, 0, .5, .5, 1.0, 0, 1, 0, .5, .5)
+    assert not hit(0, 0, 1, 0, .5, .5, 1.0 + 1e-12, 0, 1, 0, .5, .5)
+    # touching corner to corner
+    assert hit(0, 0, 1, 0, .5, .5, 1.0, 1.0, 1, 0, .5, .5)
+    # 45 degree square: corner reaches sqrt(0.5) along x
+    c = math.sqrt(0.5)
+    assert hit(0, 0, 1, 0, .5, .5, 0.5 + c - 1e-9, 0, c, c, .5, .5)
+    assert not hit(0, 0, 1, 0, .5, .5, 0.5 + c + 1e-9, 0, c, c, .5, .5)
+    # a long box crossing another without any corner inside (needs the second box's axes)
+    assert hit(0, 0, 1, 0, 5, .2, 0, 0, 0, 1, 5, .2)
+    # parallel offset boxes separated only along the ego's lateral axis
+    assert not hit(0, 0, 1, 0, 2.5, 1.0, 0, 2.2, 1, 0, 2.5, 1.0)
+
+
+def test_spline_and_quintic_known_answers():
+    th = np.linspace(0, np.pi / 2, 60)
+    sp = O.CubicSpline2D(20 * np.cos(th), 20 * np.sin(th))            # circle arc, R = 20
+    s = np.linspace(2.0, sp.s_list[-1] - 2.0, 50)
+    assert np.allclose(sp.calc_curvature(s), 1 / 20, rtol=2e-3)
+    x, y = sp.calc_position(sp.s_list)
+    assert np.allclose(x, 20 * np.cos(th), atol=1e-12) and np.allclose(y, 20 * np.sin(th), atol=1e-12)   # interpolates the knots
+    assert sp.calc_position(-1e-9) == (None, None) and sp.calc_position(sp.s_list[-1] + 1e-9) == (None, None)
+    assert sp.calc_position(sp.s_list[-1])[0] is not None                                           # end point is on the line
+    q = O.QuinticPolynomial(0.2, -0.1, 0.05, 0.75, 0.0, 0.0, 5.0)
+    assert np.isclose(q.calc_point(0), 0.2) and np.isclose(q.calc_first_derivative(0), -0.1) and np.isclose(q.calc_second_derivative(0), 0.05)
+    assert np.isclose(q.calc_point(5.0), 0.75) and abs(q.calc_first_derivative(5.0)) < 1e-12 and abs(q.calc_second_derivative(5.0)) < 1e-12
+
+
+def _cycle(n_seeds=96, n_widths=3, O_=8, M=2, seed=5, **cfg_kw):
+    from dlii_jssp_b200 import scenario as S
+    cyc = S.dense_cycle(n_seeds=n_seeds, n_widths=n_widths, O=O_, M=M, seed=seed)
+    cfg = O.OracleConfig(ego_length=cyc.ego_length, ego_width=cyc.ego_width, **cfg_kw)
+    spline = O.CubicSpline2D(cyc.route_xy[:, 0], cyc.route_xy[:, 1])
+    o = cyc.obstacles
+    return cyc, cfg, spline, (o.state, o.valid.astype(bool), o.size, o.prob)
+
+
+def test_loop_form_agrees_with_vectorised_oracle():
+    cyc, cfg, spline, obs = _cycle(p_min=0.25, w_risk=1.5)
+    a = O.plan_cycle(cfg, spline, cyc.frenet0, obs, 0, cyc.final_time_step, seeds=cyc.seeds, targets=cyc.targets)
+    b = L.plan_cycle_loop(cfg, spline, cyc.frenet0, obs, 0, cyc.final_time_step, seeds=cyc.seeds, targets=cyc.targets)
+    assert np.array_equal(a["feasible"], b["feasible"]) and np.array_equal(a["collision"], b["collision"])
+    np.testing.assert_allclose(a["cost"], b["cost"], rtol=1e-12)
+    assert a["best"] == b["best"]
+
+
+def test_reference_edge_semantics():
+    """Truncation, 1-point / 0-point trajectories, stopped car (ds == 0 -> nan passes), reversing car (|c| = pi/ds fails)."""
+    cyc, cfg, spline, obs = _cycle()
+    s_end = spline.s_list[-1]
+    stop = np.array([[0.0, 0.0, 0.0, 0.0, 0.0, 5.0, 0.0, 0.0, 0.0, 0.0]])       # all-zero jerk seed
+    # stopped on the line with d(t) = const: every forward difference is exactly zero -> c = 0/0 = nan -> feasible
+    r = O.plan_cycle(cfg, spline, (10.0, 0.0, 0.0, 0.0, 0.0, 0.0), obs, 0, 100, seeds=stop, targets=np.array([0.0]))
+    assert r["n_pts"][0] == 51 and np.all(r["ds"][0] == 0) and np.all(np.isnan(r["c"][0])) and r["feasible"][0]
+    assert np.all(r["yaw"][0] == 0.0)                                              # arctan2(0, 0) = 0
+    # slowly reversing: heading flips by pi between the first forward and the first backward step
+    rev = np.array([[-1.0, 1.0, 0.0, 0.0, 0.0, 4.0, 0.0, 0.0, 0.0, 0.0]])
+    r = O.plan_cycle(cfg, spline, (10.0, 0.2, 0.0, 0.0, 0.0, 0.0), obs, 0, 100, seeds=rev, targets=np.array([0.0]))
+    assert not r["feasible"][0] and np.nanmax(np.abs(r["c"][0])) > 10
+    # start beyond the end of the line: 0 Cartesian points -> passes both checks vacuously
+    r = O.plan_cycle(cfg, spline, (s_end + 1.0, 3.0, 0.0, 0.0, 0.0, 0.0), obs, 0, 100, seeds=stop, targets=np.array([0.0]))
+    assert r["n_pts"][0] == 0 and r["feasible"][0] and not r["collision"][0]
+    # exactly one point on the line -> the reference's bare except reports a collision
+    one = np.array([[0.0, 1.0, 0.0, 1.0, 0.0, 3.0, 0.0, 0.0, 0.0, 0.0]])
+    r = O.plan_cycle(cfg, spline, (s_end - 1e-3, 5.0, 0.0, 0.0, 0.0, 0.0), obs, 0, 100, seeds=one, targets=np.array([0.0]))
+    assert r["n_pts"][0] == 1 and r["collision"][0]
+    # ... unless there are no obstacles at all (len(obstacles) <= 0 early-out)
+    empty = (np.zeros((0, 1, 60, 3)), np.zeros((0, 1, 60), bool), np.zeros((0, 2)), np.zeros((0, 1)))
+    r = O.plan_cycle(cfg, spline, (s_end - 1e-3, 5.0, 0.0, 0.0, 0.0, 0.0), empty, 0, 100, seeds=one, targets=np.array([0.0]))
+    assert not r["collision"][0]
+
+
+def test_collision_properties():
+    cyc, cfg, spline, obs = _cycle(n_seeds=128, O_=12, M=3, seed=9)
+    state, valid, size, prob = obs
+    base = O.plan_cycle(cfg, spline, cyc.frenet0, obs, 0, cyc.final_time_step, seeds=cyc.seeds, targets=cyc.targets)
+    # monotone under obstacle removal
+    fewer = O.plan_cycle(cfg, spline, cyc.frenet0, (state[:6], valid[:6], size[:6], prob[:6]), 0, cyc.final_time_step, seeds=cyc.seeds, targets=cyc.targets)
+    assert not (fewer["collision"] & ~base["collision"]).any()
+    # any-mode semantics: union of the per-mode single-trajectory checks
+    per = [O.plan_cycle(cfg, spline, cyc.frenet0, (state[:, m:m + 1], valid[:, m:m + 1], size, np.ones((len(size), 1))), 0, cyc.final_time_step,
+                        seeds=cyc.seeds, targets=cyc.targets)["collision"] for m in range(3)]
+    assert np.array_equal(base["collision"], per[0] | per[1] | per[2])
+    # argmin invariant under a permutation of the seeds (as a seed/width pair)
+    perm = np.random.default_rng(0).permutation(len(cyc.seeds))
+    shuf = O.plan_cycle(cfg, spline, cyc.frenet0, obs, 0, cyc.final_time_step, seeds=cyc.seeds[perm], targets=cyc.targets)
+    if base["best"] >= 0:
+        w0, k0 = divmod(base["best"], len(cyc.seeds)); w1, k1 = divmod(shuf["best"], len(cyc.seeds))
+        assert w0 == w1 and np.array_equal(cyc.seeds[k0], cyc.seeds[perm][k1])
+    # the end of the scenario cuts the collision window
+    cut = O.plan_cycle(cfg, spline, cyc.frenet0, obs, 0, 4, seeds=cyc.seeds, targets=cyc.targets)
+    assert not (cut["collision"] & ~base["collision"]).any()
+
+
+def test_time_key_lookup_matches_reference_rounding(scenario_fixture):
+    from dlii_jssp_b200 import scenario as S
+    sc = scenario_fixture
+    n_total = int(sc.max_t / sc.dt) + 60
+    a = S.pack_obstacle_dict(sc.vehicle_traj, sc.dt, n_total)
+    st, va, sz, pr = O.pack_obstacles(sc.vehicle_traj, sc.dt, n_total)
+    assert np.array_equal(a.state, st) and np.array_equal(a.valid.astype(bool), va) and np.array_equal(a.size, sz)
+    assert a.valid.sum() == sum(len([k for k in tr if k != "shape"]) for tr in sc.vehicle_traj.values()) == 271
+    assert int(sc.max_t / sc.dt) == 121                       # float truncation of 12.2 / 0.1 (jerk_space_sampling_planner.py:244)
