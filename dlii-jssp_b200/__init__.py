@@ -13,7 +13,8 @@ from .geometry import CubicSpline2D, QuinticPolynomial, spline_tables
 from .planner import (JerkSpaceSamplingPlanner, JerkSpaceSamplingPlannerSettings, IntersectionPlanner, PlannerSettings)
 from . import scenario
 from . import distributed
+from . import replay
 
 __all__ = ["JsspConfig", "JsspEngine", "CycleResult", "JsspError", "State", "FrenetState", "JerkSpaceSamplingFrenetTrajectory", "Vehicle",
            "CubicSpline2D", "QuinticPolynomial", "spline_tables", "JerkSpaceSamplingPlanner", "JerkSpaceSamplingPlannerSettings",
-           "IntersectionPlanner", "PlannerSettings", "scenario", "distributed", "TRAJ_COLUMNS", "STATE_COLUMNS"]
+           "IntersectionPlanner", "PlannerSettings", "scenario", "distributed", "replay", "TRAJ_COLUMNS", "STATE_COLUMNS"]

@@ -168,6 +168,14 @@ class JerkSpaceSamplingPlanner(object):
             print(f"###log### plan_traj time:{dt_s}\n")
         return self.best_traj
 
+    def reset(self):
+        """Forget the previous scenario (reference line, obstacles, best trajectory); the device workspace is kept."""
+        self.best_traj = None
+        self.all_trajs, self.all_path_sampling_trajs = [], []
+        self._cubic_spline = None
+        self._obstacle_key = None
+        self.last_result = None
+
     def count_passed(self) -> int:
         """Number of candidates that passed both checks in the last cycle (the reference prints it, :324)."""
         r = self.last_result
@@ -219,6 +227,14 @@ class IntersectionPlanner:
         e = observation["vehicle_info"]["ego"]
         self.ego_state = State(t=observation["test_setting"]["t"], x=e["x"], y=e["y"], yaw=e["yaw"], v=e["v"], a=e["a"])
         return self.ego_state
+
+    def reset(self, observation):
+        """Start a new scenario with the same ego footprint."""
+        self.dt = observation["test_setting"]["dt"]
+        self.ego_states, self.ego_frenet_states, self.time_list = [], [], []
+        self.ego_frenet_state = FrenetState()
+        self.ego_state = self._get_ego_states(observation)
+        self.fplanner.reset()
 
     def generate_frenet_frame(self, centerline_pts: np.ndarray):
         self.cubic_spline, self.ref_ego_lane_pts = self.fplanner.generate_frenet_frame(centerline_pts)

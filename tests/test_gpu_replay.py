@@ -1,0 +1,61 @@
+"""GPU replay tests through the reference-shaped planner interface (IntersectionPlanner.plan -> JerkSpaceSamplingPlanner.plan_traj):
+the CUDA planner's replay against the oracle's, cycle by cycle."""
+import numpy as np
+import pytest
+
+import dlii_jssp_b200 as J
+from dlii_jssp_b200 import replay as R, scenario as S
+from oracle import replay_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(sc, max_cycles=None):
+    gpu = R.run_replay(sc, max_cycles=max_cycles)
+    # initial Frenet state exactly as the product façade computes it (host logic, FrenetState.from_state)
+    obs = sc.observation()
+    sp = J.CubicSpline2D(sc.route_xy[:, 0], sc.route_xy[:, 1])
+    s = np.arange(0, sp.s_list[-1], 0.1)
+    ref = np.column_stack(([sp.calc_position(v) for v in s], [sp.calc_yaw(v) for v in s], [sp.calc_curvature(v) for v in s]))
+    e = obs["vehicle_info"]["ego"]
+    fr0 = J.FrenetState().from_state(J.State(0.0, e["x"], e["y"], e["yaw"], e["v"], e["a"]), ref).as_tuple()
+    cpu = replay_oracle.replay(sc, fr0, S.pack_obstacle_dict, R.end_status, R.goal_pose_of(sc), max_cycles=max_cycles)
+    return gpu, cpu
+
+
+def _assert_same(gpu, cpu):
+    assert gpu.best_idx == cpu["best_idx"], (gpu.best_idx[:20], cpu["best_idx"][:20])
+    assert gpu.n_candidates == cpu["n"]
+    assert gpu.end == cpu["end"]
+    if cpu["rows"]:
+        np.testing.assert_allclose(np.array(gpu.ego_rows), np.array(cpu["rows"]), rtol=1e-9, atol=1e-9)
+
+
+def test_c1_bundled_scenario_replay_matches_oracle(scenario_fixture):
+    """BASELINE config 1: inputs/8_3_4_565, default sampling grid, full replay."""
+    gpu, cpu = _both(scenario_fixture)
+    assert gpu.cycles >= 1
+    _assert_same(gpu, cpu)
+
+
+@pytest.mark.parametrize("seed", [1, 4])
+def test_c2_perturbed_scene_replay_matches_oracle(scenario_fixture, seed):
+    """BASELINE config 2 (the reference's 8 demo scenes are 0-byte placeholders): seeded variants of 8_3_4_565."""
+    gpu, cpu = _both(S.perturbed_scenario(scenario_fixture, seed), max_cycles=25)
+    _assert_same(gpu, cpu)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_c4_synthetic_intersection_replay_matches_oracle(seed):
+    """BASELINE config 4 (scenes_all(800) is absent): seeded synthetic intersections - left turn, straight, right turn."""
+    gpu, cpu = _both(S.synthetic_intersection(seed), max_cycles=30)
+    assert gpu.cycles >= 5
+    _assert_same(gpu, cpu)
+
+
+def test_sweep_reuses_planner_and_matches_individual_replays():
+    scs = [S.synthetic_intersection(s) for s in (3, 4, 5)]
+    sweep = R.run_sweep(scs, max_cycles=8)
+    solo = [R.run_replay(sc, max_cycles=8) for sc in scs]
+    for a, b in zip(sweep, solo):
+        assert a.best_idx == b.best_idx and a.ego_rows == b.ego_rows and a.end == b.end
