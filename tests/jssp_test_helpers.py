@@ -34,7 +34,10 @@ def compare_cycle(res, ref, rtol=1e-4, check_traj=True):
     bad_c = np.nonzero(coll != ref["collision"])[0]
     assert bad_f.size == 0, f"feasible mask differs at {bad_f[:10]} ({bad_f.size} of {n})"
     assert bad_c.size == 0, f"collision mask differs at {bad_c[:10]} ({bad_c.size} of {n})"
-    np.testing.assert_allclose(cost, ref["cost"], rtol=rtol, atol=0)
+    # the cost is defined for every candidate, except that the soft-risk term of a vetoed candidate stops accumulating at
+    # the veto (the reference only ever costs survivors, jerk_space_sampling_planner.py:313-320)
+    sel = ~ref["collision"] if np.any(ref.get("risk", 0) != 0) else np.ones(n, dtype=bool)
+    np.testing.assert_allclose(cost[sel], ref["cost"][sel], rtol=rtol, atol=0)
     assert res.best_idx == ref["best"], (res.best_idx, ref["best"], res.best_cost, ref["cost"][ref["best"]] if ref["best"] >= 0 else None)
     if ref["best"] >= 0 and check_traj and res.best_traj is not None:
         b = ref["best"]
