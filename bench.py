@@ -223,12 +223,14 @@ def run_ours(args):
         """candidate-split exchange: per-rank winner (float64 cost bits, global index) -> one 16 B/rank NCCL all-gather"""
         if not split:
             return None
-        rec = D.localize_record(eng.best_record(), seed_lo, len(seeds_host), len(seeds_all))
-        return D.allgather_argmin(rec)
+        per = len(seeds_all) // world
+        return D.allgather_argmin(eng.best_record(), index_map=lambda r, i: D.global_candidate_index(i, r * per, per, len(seeds_all)))
 
     def timed(steps, warmup, export, with_reduce=False):
         for _ in range(warmup):
             eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=seeds_dev, targets=cyc.targets, sync=False, export=export)
+            if with_reduce:
+                reduce_best()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()

@@ -63,20 +63,24 @@ def _u64_less(a_cost: int, a_idx: int, b_cost: int, b_idx: int) -> bool:
     return (a_idx & 0xFFFFFFFFFFFFFFFF) < (b_idx & 0xFFFFFFFFFFFFFFFF)
 
 
-def allgather_argmin(rec: torch.Tensor, group=None) -> Tuple[int, int, int]:
-    """rec = int64[2] (orderable cost bits, GLOBAL candidate index or -1).  One all-gather, then the local lexicographic
-    minimum.  Returns (cost_bits, global_index, winner_rank); global_index = -1 when no rank has a survivor."""
+def allgather_argmin(rec: torch.Tensor, group=None, index_map=None) -> Tuple[int, int, int]:
+    """rec = int64[2] (orderable cost bits, candidate index or -1).  One all-gather (16 B per rank), one device-to-host
+    copy of the gathered table, then the lexicographic minimum on the host.  ``index_map(rank, idx)`` turns a rank-local
+    index into the global one (default: the indices are already global).  Returns (cost_bits, global_index, winner_rank);
+    global_index = -1 when no rank has a survivor."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
-        c, i = int(rec[0].item()), int(rec[1].item())
-        return c, i, 0
-    parts = [torch.empty_like(rec) for _ in range(world)]
-    dist.all_gather(parts, rec, group=group)
-    table = torch.stack(parts).cpu().tolist()
+        table = [rec.cpu().tolist()]
+    else:
+        out = torch.empty((world, 2), dtype=rec.dtype, device=rec.device)
+        dist.all_gather_into_tensor(out, rec, group=group) if rec.is_cuda else dist.all_gather(list(out.unbind(0)), rec, group=group)
+        table = out.cpu().tolist()
     best = None
     for r, (c, i) in enumerate(table):
         if i == NO_CANDIDATE:
             continue
+        if index_map is not None:
+            i = index_map(r, i)
         if best is None or _u64_less(c, i, best[0], best[1]):
             best = (c, i, r)
     return best if best is not None else (table[0][0], -1, 0)
