@@ -40,6 +40,11 @@ struct jssp_handle {
   const uint8_t* src_valid = nullptr;
   float4 *d_broad = nullptr, *d_narrow = nullptr;
   double *d_obs64 = nullptr, *d_ext64 = nullptr;
+  float2* d_sint = nullptr;       // reachable arc-length interval per obstacle state
+  float* d_probf = nullptr;
+  double* d_knot_xy = nullptr;
+  double cull_reach = 0, cull_ds = 0;
+  bool cull_ok = false;
   int O = 0, M = 0, Tt = 0, n_dict = 0;
   bool obs_set = false, obs_dirty = false;
   // selection
@@ -129,7 +134,8 @@ int pack_if_dirty(jssp_handle* h, cudaStream_t st) {
     const double r_ego = std::sqrt(h->cfg.ego_length * h->cfg.ego_length + h->cfg.ego_width * h->cfg.ego_width) / 2.0;
     pack_obstacles_kernel<<<(total + 255) / 256, 256, 0, st>>>(h->src_state, h->src_valid, h->src_size, h->src_prob, OM, OMpad, h->M, h->Tt,
                                                                h->ox, h->oy, h->cfg.obstacle_inflation, r_ego, h->d_broad, h->d_narrow,
-                                                               h->d_obs64, h->d_ext64);
+                                                               h->d_obs64, h->d_ext64, h->d_probf, h->d_sint, h->d_knot, h->d_knot_xy, h->K,
+                                                               h->cull_reach, h->cull_ds);
     h->launches++;
     CK(cudaGetLastError());
   }
@@ -283,6 +289,9 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(cudaMalloc(&h->d_narrow, om * tt * sizeof(float4)));
   CKC(cudaMalloc(&h->d_obs64, om * tt * 4 * sizeof(double)));
   CKC(cudaMalloc(&h->d_ext64, om * 2 * sizeof(double)));
+  CKC(cudaMalloc(&h->d_sint, ((om + 31) & ~(size_t)31) * tt * sizeof(float2)));
+  CKC(cudaMalloc(&h->d_probf, om * sizeof(float)));
+  CKC(cudaMalloc(&h->d_knot_xy, (size_t)cfg->max_knots * 2 * sizeof(double)));
   h->max_blocks = (int)(((size_t)cfg->max_seeds * JSSP_MAX_WIDTHS + EVAL_THREADS - 1) / EVAL_THREADS);
   CKC(cudaMalloc(&h->d_blk_cost, (size_t)h->max_blocks * sizeof(double)));
   CKC(cudaMalloc(&h->d_blk_idx, (size_t)h->max_blocks * sizeof(int)));
@@ -293,8 +302,9 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(cudaMallocHost(&h->h_best, sizeof(BestRecord)));
   CKC(cudaMalloc(&h->d_best_traj, (size_t)h->P * JSSP_TRAJ_COLS * sizeof(double)));
   CKC(cudaMallocHost(&h->h_best_traj, (size_t)h->P * JSSP_TRAJ_COLS * sizeof(double)));
-  CKC(cudaFuncSetAttribute(evaluate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  CKC(cudaFuncSetAttribute(evaluate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CKC(cudaFuncSetAttribute(evaluate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CKC(cudaFuncSetAttribute(evaluate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CKC(cudaFuncSetAttribute(evaluate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CKC(cudaFuncSetAttribute(dump_states_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CKC(cudaDeviceSynchronize());
 #undef CKC
@@ -307,7 +317,7 @@ int32_t jssp_destroy(jssp_handle* h) {
   cudaSetDevice(h->device);
   void* dev[] = {h->d_time, h->d_j1, h->d_t1, h->d_t2, h->d_j3, h->d_t3, h->d_t4, h->d_jneg, h->d_jpos, h->d_ts, h->d_seeds,
                  h->d_list_main, h->d_list_stop, h->d_counts, h->d_knot, h->d_coef, h->d_raw_state, h->d_raw_valid, h->d_raw_size,
-                 h->d_raw_prob, h->d_broad, h->d_narrow, h->d_obs64, h->d_ext64, h->d_blk_cost, h->d_blk_idx, h->d_ticket, h->d_best,
+                 h->d_raw_prob, h->d_broad, h->d_narrow, h->d_obs64, h->d_ext64, h->d_sint, h->d_probf, h->d_knot_xy, h->d_blk_cost, h->d_blk_idx, h->d_ticket, h->d_best,
                  h->d_best_traj};
   for (void* p : dev) if (p) cudaFree(p);
   if (h->h_counts) cudaFreeHost(h->h_counts);
@@ -330,10 +340,31 @@ int32_t jssp_set_refline(jssp_handle* h, const double* knot_s, const double* coe
     for (int c = 0; c < 8; ++c) soa[(size_t)c * h->kpad + i] = coef[(size_t)i * 8 + c];
   CK(cudaMemcpyAsync(h->d_knot, knot_s, (size_t)K * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h->d_coef, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(cudaStreamSynchronize(st));   // soa is a temporary
+  // block-level culling tables: knot positions, the longest knot spacing and a rigorous bound on |r'(s)| (triangle
+  // inequality on the per-segment quadratics), so that "within reach of a knot" covers every point of the curve
+  std::vector<double> kxy((size_t)K * 2);
+  double hmax = 0.0, gmax = 0.0;
+  for (int i = 0; i < K - 1; ++i) {
+    const double* c = coef + (size_t)i * 8;
+    const double hh = knot_s[i + 1] - knot_s[i];
+    kxy[2 * i] = c[0]; kxy[2 * i + 1] = c[4];
+    hmax = std::max(hmax, hh);
+    const double bx = std::fabs(c[1]) + 2.0 * std::fabs(c[2]) * hh + 3.0 * std::fabs(c[3]) * hh * hh;
+    const double by = std::fabs(c[5]) + 2.0 * std::fabs(c[6]) * hh + 3.0 * std::fabs(c[7]) * hh * hh;
+    gmax = std::max(gmax, std::hypot(bx, by));
+    if (i == K - 2) {
+      kxy[2 * (K - 1)] = ((c[0] + c[1] * hh) + c[2] * (hh * hh)) + c[3] * ((hh * hh) * hh);
+      kxy[2 * (K - 1) + 1] = ((c[4] + c[5] * hh) + c[6] * (hh * hh)) + c[7] * ((hh * hh) * hh);
+    }
+  }
+  CK(cudaMemcpyAsync(h->d_knot_xy, kxy.data(), kxy.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));   // soa, kxy are temporaries
   h->K = K;
-  const double nox = coef[0], noy = coef[4];   // first knot = local origin of the fp32 collision frame
-  if (nox != h->ox || noy != h->oy) { h->ox = nox; h->oy = noy; if (h->obs_set) h->obs_dirty = true; }
+  h->cull_ok = std::isfinite(gmax) && gmax < 8.0;
+  h->cull_reach = h->cfg.max_road_width + gmax * hmax;   // lateral cap + longest knot-to-knot arc (+ radii, added per obstacle)
+  h->cull_ds = hmax;
+  h->ox = coef[0]; h->oy = coef[4];   // first knot = local origin of the fp32 collision frame
+  if (h->obs_set) h->obs_dirty = true;
   return JSSP_OK;
 }
 
@@ -476,13 +507,25 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   if (p.tcap > 0 && p.now >= 0) rows = (std::min(p.P, p.tcap) + c.check_res - 1) / c.check_res;
   if (p.now < 0) return JSSP_ERR_INVALID_ARG;
   p.win_rows = p.OM > 0 ? rows : 0;
-  p.smem_obs = 1;
-  SmemLayout L = eval_smem_layout(p.win_rows, p.OMpad, 1, p.K, p.kpad, p.P, p.W);
-  if (p.win_rows == 0 || L.total > (size_t)h->max_smem_optin) {
-    p.smem_obs = 0;
+  p.sint = h->d_sint; p.probf = h->d_probf;
+  p.list_cap = std::min(p.win_rows * p.OMpad, 2048);
+  // block-level culling is valid while every lateral offset of this cycle stays inside the cap the intervals were built for
+  double dlat = 0.0;
+  for (int w = 0; w < W; ++w)
+    for (int i = 0; i < h->P; ++i) {
+      double d, d1, d2, d3;
+      quintic_eval(p.quintic[w], c.plan_horizon * i / (h->P - 1), d, d1, d2, d3);
+      dlat = std::max(dlat, std::fabs(d));
+    }
+  int mode = (h->cull_ok && p.win_rows > 0 && dlat * 1.001 + 1e-6 <= c.max_road_width && !(in->flags & JSSP_FLAG_NO_CULL)) ? 2 : 1;
+  SmemLayout L = eval_smem_layout(p.win_rows, p.OMpad, mode, p.K, p.kpad, p.P, p.W, p.list_cap);
+  if (mode == 2 && L.total > (size_t)h->max_smem_optin) { mode = 1; L = eval_smem_layout(p.win_rows, p.OMpad, 1, p.K, p.kpad, p.P, p.W); }
+  if (mode == 1 && (p.win_rows == 0 || L.total > (size_t)h->max_smem_optin)) {
+    mode = 0;
     L = eval_smem_layout(p.win_rows, p.OMpad, 0, p.K, p.kpad, p.P, p.W);
     if (L.total > (size_t)h->max_smem_optin) return JSSP_ERR_CAPACITY;
   }
+  p.smem_obs = mode;
   p.feasible = out->feasible_dev; p.collision = out->collision_dev; p.cost = out->cost_dev;
   p.blk_cost = h->d_blk_cost; p.blk_idx = h->d_blk_idx; p.ticket = h->d_ticket; p.best = h->d_best;
   p.best_traj = (in->flags & JSSP_FLAG_NO_EXPORT) ? nullptr : h->d_best_traj;
@@ -491,12 +534,13 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   int blocks = (int)((n_max + EVAL_THREADS - 1) / EVAL_THREADS);
   if (blocks < 1) blocks = 1;
   if (blocks > h->max_blocks) return JSSP_ERR_CAPACITY;
-  if (p.smem_obs) evaluate_kernel<true><<<blocks, EVAL_THREADS, L.total, st>>>(p);
-  else evaluate_kernel<false><<<blocks, EVAL_THREADS, L.total, st>>>(p);
+  if (mode == 2) evaluate_kernel<2><<<blocks, EVAL_THREADS, L.total, st>>>(p);
+  else if (mode == 1) evaluate_kernel<1><<<blocks, EVAL_THREADS, L.total, st>>>(p);
+  else evaluate_kernel<0><<<blocks, EVAL_THREADS, L.total, st>>>(p);
   h->launches++;
   CK(cudaGetLastError());
   EvalParams q = p;
-  q.smem_obs = 0; q.win_rows = 0;
+  q.smem_obs = 0; q.win_rows = 0; q.list_cap = 0;
   const SmemLayout L2 = eval_smem_layout(0, q.OMpad, 0, q.K, q.kpad, q.P, q.W);
   if (out->states_dev) {
     dump_states_kernel<<<blocks, EVAL_THREADS, L2.total, st>>>(q, out->states_dev);

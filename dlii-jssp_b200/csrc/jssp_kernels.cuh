@@ -221,10 +221,13 @@ constexpr float BROAD_CANCEL = 0.5f;      // [m^2] covers fp32 cancellation of t
 __global__ void pack_obstacles_kernel(const double* __restrict__ state, const uint8_t* __restrict__ valid,
                                       const double* __restrict__ size, const double* __restrict__ prob, int OM, int OMpad, int M,
                                       int Tt, double ox, double oy, double inflation, double r_ego, float4* __restrict__ broad,
-                                      float4* __restrict__ narrow, double* __restrict__ obs64, double* __restrict__ ext64) {
+                                      float4* __restrict__ narrow, double* __restrict__ obs64, double* __restrict__ ext64,
+                                      float* __restrict__ probf, float2* __restrict__ sint, const double* __restrict__ knot_s,
+                                      const double* __restrict__ knot_xy, int K, double cull_reach, double cull_ds) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // idx = t * OMpad + om
   if (idx >= OMpad * Tt) return;
   const int t = idx / OMpad, om = idx - t * OMpad;
+  sint[idx] = make_float2(FAR_AWAY, -FAR_AWAY);            // empty arc-length interval
   if (om >= OM) { broad[idx] = make_float4(0.f, 0.f, FAR_AWAY, 0.f); return; }
   const int o = om / M;
   const double a2 = (size[2 * o] + inflation) / 2.0, b2 = (size[2 * o + 1] + inflation) / 2.0;
@@ -241,6 +244,20 @@ __global__ void pack_obstacles_kernel(const double* __restrict__ state, const ui
   narrow[gi] = make_float4((float)cs, (float)sn, (float)a2, (float)b2);
   double* q64 = obs64 + gi * 4;
   q64[0] = s[0]; q64[1] = s[1]; q64[2] = cs; q64[3] = sn;
+  if (t == 0) probf[om] = (float)prob[om];
+  // Arc-length interval of the reference line from which this obstacle state can be reached by any candidate footprint:
+  // every curve point within (lateral cap + R) of the obstacle lies within cull_reach of one of its segment's knots
+  // (cull_reach includes the longest knot-to-knot arc), so the hull of those knots widened by cull_ds is conservative.
+  if (ok && K > 0) {
+    const double reach = cull_reach + (double)r;
+    const double r2 = reach * reach;
+    double lo = 1e300, hi = -1e300;
+    for (int k = 0; k < K; ++k) {
+      const double dx = knot_xy[2 * k] - s[0], dy = knot_xy[2 * k + 1] - s[1];
+      if (dx * dx + dy * dy <= r2) { lo = fmin(lo, knot_s[k]); hi = fmax(hi, knot_s[k]); }
+    }
+    if (hi >= lo) sint[idx] = make_float2(__double2float_rd(lo - cull_ds), __double2float_ru(hi + cull_ds));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -270,6 +287,9 @@ struct EvalParams {
   const double* obs64;
   const double* ext64;
   int OM, OMpad, Tt, win_rows, smem_obs;
+  const float2* sint;             // [Tt][OMpad] reachable arc-length interval of every obstacle state (block-level culling)
+  const float* probf;             // [OM]
+  int list_cap;                   // entries of the per-block compacted obstacle lists (mode 2)
   // outputs
   uint8_t* feasible;
   uint8_t* collision;
@@ -288,6 +308,11 @@ struct BlockTables {
   SplineView sp;
   const double* time;
   const double* lat;     // [W][P][4]
+  // mode 2: per-row lists of the obstacle states this block's candidates can reach: (x', y', |o'|^2 - R^2, om bits)
+  const float4* list;
+  const int* row_off;
+  const int* row_cnt;
+  bool use_lists;
 };
 
 // Walks one candidate through the horizon and hands every derived quantity to `sink`, in the order the reference
@@ -380,6 +405,16 @@ struct EvalSink {
     }
   }
 
+  // separating-axis test of the ego rectangle at (x, y, heading (c, sn)) against obstacle mode om at abs_step
+  __device__ __forceinline__ bool narrow_hit(int abs_step, int om, float dxf, float dyf, double x, double y, double c, double sn) const {
+    const size_t gi = (size_t)abs_step * p.OM + om;
+    const float4 nb = __ldg(p.narrow + gi);
+    const int cls = sat_classify_f32(dxf, dyf, (float)c, (float)sn, (float)p.ea, (float)p.eb, nb.x, nb.y, nb.z, nb.w, SAT_EPS);
+    if (cls != 0) return cls < 0;
+    const double* q = p.obs64 + gi * 4;
+    return sat_intersects_f64(q[0] - x, q[1] - y, c, sn, p.ea, p.eb, q[2], q[3], p.ext64[2 * om], p.ext64[2 * om + 1]);
+  }
+
   __device__ __forceinline__ void collide(int i, double x, double y, double c, double sn) {
     if (collided || p.n_dict <= 0 || i >= p.tcap || (i % p.check_res) != 0) return;
     const int abs_step = p.now + i;
@@ -388,6 +423,22 @@ struct EvalSink {
     const float4* row = tb.broad + (size_t)(tb.broad_row0 + r * tb.broad_stride) * p.OMpad;
     const float fx = (float)(x - p.ox), fy = (float)(y - p.oy);
     const float m2x = -2.0f * fx, m2y = -2.0f * fy, ne2 = -fmaf(fx, fx, fy * fy);
+    if (tb.use_lists) {      // block-level culled rows: a handful of entries instead of OMpad
+      const int cnt = tb.row_cnt[r];
+      const float4* e = tb.list + tb.row_off[r];
+      for (int k = 0; k < cnt; ++k) {
+        const float4 b = e[k];
+        if (fmaf(b.x, m2x, fmaf(b.y, m2y, b.z)) <= ne2) {
+          const int om = __float_as_int(b.w);
+          if (narrow_hit(abs_step, om, b.x - fx, b.y - fy, x, y, c, sn)) {
+            const float pr = __ldg(p.probf + om);
+            if ((double)pr >= p.p_min) { collided = true; return; }
+            risk = risk + (double)pr;
+          }
+        }
+      }
+      return;
+    }
     for (int base = 0; base < p.OMpad; base += 32) {
       unsigned int mask = 0u;
 #pragma unroll
@@ -400,15 +451,7 @@ struct EvalSink {
         const int om = base + __ffs(mask) - 1;
         mask &= mask - 1u;
         const float4 b = row[om];
-        const size_t gi = (size_t)abs_step * p.OM + om;
-        const float4 nb = __ldg(p.narrow + gi);
-        const int cls = sat_classify_f32(b.x - fx, b.y - fy, (float)c, (float)sn, (float)p.ea, (float)p.eb, nb.x, nb.y, nb.z, nb.w, SAT_EPS);
-        bool hit = cls < 0;
-        if (cls == 0) {
-          const double* q = p.obs64 + gi * 4;
-          hit = sat_intersects_f64(q[0] - x, q[1] - y, c, sn, p.ea, p.eb, q[2], q[3], p.ext64[2 * om], p.ext64[2 * om + 1]);
-        }
-        if (hit) {
+        if (narrow_hit(abs_step, om, b.x - fx, b.y - fy, x, y, c, sn)) {
           if ((double)b.w >= p.p_min) { collided = true; return; }
           risk = risk + (double)b.w;
         }
@@ -441,12 +484,14 @@ __device__ __forceinline__ double candidate_cost(const EvalParams& p, const Eval
 
 // dynamic shared memory carve-up (the host uses the same function to size the launch)
 struct SmemLayout {
-  size_t off_broad, off_knot, off_coef, off_time, off_lat, off_latcost, total;
+  size_t off_broad, off_rows, off_knot, off_coef, off_time, off_lat, off_latcost, total;
 };
-__host__ __device__ inline SmemLayout eval_smem_layout(int win_rows, int OMpad, int smem_obs, int K, int kpad, int P, int W) {
+// mode: 0 = obstacle table read from global memory, 1 = the cycle's window staged by TMA, 2 = per-block culled lists
+__host__ __device__ inline SmemLayout eval_smem_layout(int win_rows, int OMpad, int mode, int K, int kpad, int P, int W, int list_cap = 0) {
   SmemLayout L;
-  size_t o = 16;   // mbarrier
-  L.off_broad = o; o += smem_obs ? (size_t)win_rows * OMpad * 16 : 0;
+  size_t o = 16;   // mbarrier / list cursor
+  L.off_broad = o; o += mode == 1 ? (size_t)win_rows * OMpad * 16 : (mode == 2 ? (size_t)list_cap * 16 : 0);
+  L.off_rows = o; o += mode == 2 ? (size_t)((4 * win_rows + 3) & ~3) * 4 : 0;   // row_off, row_cnt, row_smin, row_smax
   L.off_knot = o; o += (size_t)((K + 1) & ~1) * 8;
   L.off_coef = o; o += (size_t)8 * kpad * 8;
   L.off_time = o; o += (size_t)((P + 1) & ~1) * 8;
@@ -458,9 +503,10 @@ __host__ __device__ inline SmemLayout eval_smem_layout(int win_rows, int OMpad, 
 
 // Stage the per-block tables: obstacle window by bulk copy (TMA engine; one row per issued copy, all completing on one
 // mbarrier), spline, time grid and the lateral quintic samples (jerk_space_sampling_planner.py:118-122) by ordinary loads.
-template <bool kSmem>
+template <int kMode>
 __device__ __forceinline__ void stage_tables(const EvalParams& p, unsigned char* smem, BlockTables& tb, const double*& latcost) {
-  const SmemLayout L = eval_smem_layout(p.win_rows, p.OMpad, kSmem ? 1 : 0, p.K, p.kpad, p.P, p.W);
+  constexpr bool kSmem = kMode == 1;
+  const SmemLayout L = eval_smem_layout(p.win_rows, p.OMpad, kMode, p.K, p.kpad, p.P, p.W, p.list_cap);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   float4* sm_broad = reinterpret_cast<float4*>(smem + L.off_broad);
   double* sm_knot = reinterpret_cast<double*>(smem + L.off_knot);
@@ -514,7 +560,76 @@ __device__ __forceinline__ void stage_tables(const EvalParams& p, unsigned char*
   }
   tb.sp.knot = sm_knot; tb.sp.coef = sm_coef; tb.sp.K = p.K; tb.sp.kpad = p.kpad;
   tb.time = sm_time; tb.lat = sm_lat;
+  tb.list = sm_broad; tb.row_off = reinterpret_cast<const int*>(smem + L.off_rows); tb.row_cnt = tb.row_off + p.win_rows;
+  tb.use_lists = false;
   latcost = sm_latcost;
+}
+
+// Mode 2, after stage_tables: cull the obstacle states of this cycle against the arc-length range the block's candidates
+// cover at every collision row, and compact the survivors into shared memory (order within a row = obstacle-mode order).
+//   phase A  every thread unrolls its longitudinal profile at the collision steps; warp REDUX + shared atomics give
+//            [s_min, s_max] per row (fp32, rounded outwards, clamped to the reference line);
+//   phase B  one warp per row: ballot-compaction of the states whose reachable interval (pack_obstacles_kernel)
+//            overlaps the row's range.
+// Falls back to the global table (tb.use_lists stays false) when the lists would not fit.
+__device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* smem, BlockTables& tb, const LonProfile& lp, bool active) {
+  const SmemLayout L = eval_smem_layout(p.win_rows, p.OMpad, 2, p.K, p.kpad, p.P, p.W, p.list_cap);
+  float4* list = reinterpret_cast<float4*>(smem + L.off_broad);
+  int* row_off = reinterpret_cast<int*>(smem + L.off_rows);
+  int* row_cnt = row_off + p.win_rows;
+  unsigned int* row_min = reinterpret_cast<unsigned int*>(row_cnt + p.win_rows);
+  unsigned int* row_max = row_min + p.win_rows;
+  int* cursor = reinterpret_cast<int*>(smem);        // [0] next free list entry, [1] overflow flag
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  for (int r = tid; r < p.win_rows; r += blockDim.x) { row_min[r] = 0x7f800000u; row_max[r] = 0u; row_cnt[r] = 0; row_off[r] = 0; }
+  if (tid == 0) { cursor[0] = 0; cursor[1] = 0; }
+  __syncthreads();
+  const double s_end = tb.sp.knot[p.K - 1];
+  for (int r = 0; r < p.win_rows; ++r) {
+    unsigned int lo = 0x7f800000u, hi = 0u;
+    if (active) {
+      double s, sd, sdd, sddd;
+      lon_eval(lp, p.s0, p.v0, p.a0, tb.time[r * p.check_res], s, sd, sdd, sddd);
+      s = fmin(fmax(s, 0.0), s_end);                  // off-line samples are never collision-checked
+      lo = __float_as_uint(__double2float_rd(s));     // s >= 0: the bit patterns order like the values
+      hi = __float_as_uint(__double2float_ru(s));
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if (lane == 0) { atomicMin(&row_min[r], lo); atomicMax(&row_max[r], hi); }
+  }
+  __syncthreads();
+  for (int r = wid; r < p.win_rows; r += nw) {
+    const int t = p.now + r * p.check_res;
+    if (t >= p.Tt) continue;                          // no obstacle state exists beyond the scenario
+    const float smin = __uint_as_float(row_min[r]) - 1e-3f, smax = __uint_as_float(row_max[r]) + 1e-3f;
+    const float2* iv = p.sint + (size_t)t * p.OMpad;
+    int cnt = 0;
+    for (int base = 0; base < p.OMpad; base += 32) {
+      const float2 v = iv[base + lane];
+      cnt += __popc(__ballot_sync(0xffffffffu, v.y >= smin && v.x <= smax));
+    }
+    int off = 0;
+    if (lane == 0) off = atomicAdd(&cursor[0], cnt);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (off + cnt > p.list_cap) { if (lane == 0) cursor[1] = 1; continue; }
+    if (lane == 0) { row_off[r] = off; row_cnt[r] = cnt; }
+    const float4* src = p.broad + (size_t)t * p.OMpad;
+    for (int base = 0; base < p.OMpad; base += 32) {
+      const float2 v = iv[base + lane];
+      const bool keep = v.y >= smin && v.x <= smax;
+      const unsigned int m = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        float4 b = src[base + lane];
+        b.w = __int_as_float(base + lane);
+        list[off + __popc(m & ((1u << lane) - 1u))] = b;
+      }
+      off += __popc(m);
+    }
+  }
+  __syncthreads();
+  tb.use_lists = cursor[1] == 0;
+  tb.broad = p.broad; tb.broad_row0 = p.now; tb.broad_stride = p.check_res;   // fallback path
 }
 
 __device__ __forceinline__ int resolve_n_seeds(const EvalParams& p) {
@@ -585,7 +700,7 @@ __device__ __forceinline__ void export_block(const EvalParams& p, const BlockTab
   if (i == 0) p.best->n_pts = np;
 }
 
-template <bool kSmem>
+template <int kMode>
 __global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_kernel(const __grid_constant__ EvalParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ double red_cost[EVAL_THREADS / 32];
@@ -601,11 +716,13 @@ __global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_kernel
   const double* latcost;
   const bool staged = blockIdx.x * blockDim.x < N;   // block-uniform
   if (staged) {
-    stage_tables<kSmem>(p, smem, tb, latcost);
-    if (n < N) {
-      const int w = n / Ns, k = n - w * Ns;
-      LonProfile lp;
-      lon_profile_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
+    stage_tables<kMode>(p, smem, tb, latcost);
+    const bool active = n < N;
+    const int w = active ? n / Ns : 0, k = active ? n - w * Ns : 0;
+    LonProfile lp;
+    lon_profile_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
+    if (kMode == 2) build_lists(p, smem, tb, lp, active);
+    if (active) {
       EvalSink sink(p, tb);
       const int seg0 = spline_bisect(tb.sp, fmin(fmax(p.s0, tb.sp.knot[0]), tb.sp.knot[p.K - 1]));
       walk_candidate(p, tb, lp, w, seg0, sink);
@@ -673,7 +790,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_kernel
   __syncthreads();
   const int best = red_idx[0];
   if (best < 0) return;
-  if (!staged) stage_tables<kSmem>(p, smem, tb, latcost);
+  if (!staged) stage_tables<kMode>(p, smem, tb, latcost);
   export_block(p, tb, best, p.best_traj, &sm_npts);
 }
 
@@ -714,7 +831,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) dump_states_kernel(const __grid_
   if (blockIdx.x * blockDim.x >= N) return;
   BlockTables tb;
   const double* latcost;
-  stage_tables<false>(p, smem, tb, latcost);
+  stage_tables<0>(p, smem, tb, latcost);
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int w = n / Ns, k = n - w * Ns;

@@ -163,3 +163,26 @@ def test_c3_full_size_properties_and_subsample_parity():
     assert abs(res3.best_cost - res.best_cost) <= 1e-12 and w3 == w1
     assert np.array_equal(cyc.seeds[::-1][k3], cyc.seeds[k1]) or res3.best_cost == res.best_cost
     eng.close()
+
+
+@pytest.mark.parametrize("n_seeds,n_widths,O_,M,horizon,seed", [(1024, 4, 32, 3, 5.0, 41), (700, 3, 6, 1, 5.0, 42), (512, 8, 64, 3, 8.0, 43)])
+def test_block_level_culling_changes_nothing(n_seeds, n_widths, O_, M, horizon, seed):
+    """The per-block culled obstacle lists (default) and the exhaustive table walk (JSSP_FLAG_NO_CULL) give identical
+    masks, costs and selection - and both match the oracle."""
+    cyc, cfg, spline, eng = _dense(n_seeds, n_widths, O_, M, horizon, seed, p_min=0.15, w_risk=0.7)
+    seeds = torch.from_numpy(cyc.seeds).cuda()
+    out = []
+    for cull in (True, False):
+        r = eng.evaluate(cyc.frenet0, 0, cyc.final_time_step, seeds=seeds, targets=cyc.targets, cull=cull)
+        out.append((r.feasible.cpu().numpy().copy(), r.collision.cpu().numpy().copy(), r.cost.cpu().numpy().copy(), r.best_idx, r.best_cost))
+    ok = out[0][1] == 0          # a vetoed candidate stops accumulating risk at the veto, wherever the walk is then
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2][ok], out[1][2][ok])
+    assert out[0][3:] == out[1][3:]
+    ref = O.plan_cycle(cfg, spline, cyc.frenet0, H.oracle_obstacles(cyc.obstacles), 0, cyc.final_time_step, seeds=cyc.seeds, targets=cyc.targets)
+    res = eng.evaluate(cyc.frenet0, 0, cyc.final_time_step, seeds=seeds, targets=cyc.targets)
+    H.compare_cycle(res, ref)
+    # a start offset beyond the lateral cap switches culling off instead of risking a miss
+    wide = (cyc.frenet0[0], cyc.frenet0[1], 0.0, 4.2, 0.0, 0.0)
+    ref = O.plan_cycle(cfg, spline, wide, H.oracle_obstacles(cyc.obstacles), 0, cyc.final_time_step, seeds=cyc.seeds, targets=cyc.targets)
+    H.compare_cycle(eng.evaluate(wide, 0, cyc.final_time_step, seeds=seeds, targets=cyc.targets), ref)
+    eng.close()
