@@ -324,7 +324,7 @@ struct BlockTables {
 //                                                            and unit vector ((1, 0) when the length is 0: atan2(0,0) = 0)
 //   sink.finish(n_pts, x_L, y_L)                             once; L = n_pts - 1
 template <class Sink>
-__device__ __forceinline__ void walk_candidate(const EvalParams& p, const BlockTables& tb, const LonProfile& lp, int w,
+__device__ __forceinline__ void walk_candidate(const EvalParams& p, const BlockTables& tb, LonWalk& lp, int w,
                                                int seg, Sink& sink) {
   const int P = p.P;
   const double* lat = tb.lat + (size_t)w * P * 4;
@@ -334,7 +334,7 @@ __device__ __forceinline__ void walk_candidate(const EvalParams& p, const BlockT
   for (int i = 0; i < P; ++i) {
     const double t = tb.time[i];
     double s, sd, sdd, sddd;
-    lon_eval(lp, p.s0, p.v0, p.a0, t, s, sd, sdd, sddd);
+    lon_walk_eval(lp, t, s, sd, sdd, sddd);
     sink.sample(i, t, s, sd, sdd, sddd);
     if (!live) continue;
     if (!spline_in_range(tb.sp, s)) {   // calc_position returned None -> break (jerk_space_sampling_planner.py:138-139)
@@ -367,6 +367,7 @@ struct EvalSink {
   const BlockTables& tb;
   double sum_a = 0, sum_j = 0, sum_v = 0, s_first = 0, s_last = 0, risk = 0;
   double pdx = 0, pdy = 0, pds = 0, pc = 1, psn = 0;   // previous segment (difference, length, unit vector)
+  int next_check = 0, row = 0;                         // next sample index to collision-check and its window row
   bool curv_fail = false, collided = false;
   __device__ __forceinline__ EvalSink(const EvalParams& p_, const BlockTables& tb_) : p(p_), tb(tb_) {}
 
@@ -388,16 +389,20 @@ struct EvalSink {
   // un-unwrapped difference from the exact signs, and a relative guard band inside which the float64 atan2 decides.
   __device__ __forceinline__ void curvature_step(double dx, double dy, double ds, double c, double sn) {
     const double phi = p.kmax * pds;
-    bool exact = !(pds > 0.0) || !(ds > 0.0);
+    bool exact = !(pds > 0.0) || !(ds > 0.0) || !(phi < 0.5);
     if (!exact) {
-      const double cr = pc * sn - psn * c, dt = pc * c + psn * sn;      // unit vectors: |cr|, |dt| <= 1
-      const float w = fabsf(atan2f((float)cr, (float)dt));
-      const bool na = signbit(pdy), nb = signbit(dy);
-      const bool wrap = (na != nb) && (nb ? (cr > 0.0) : (cr < 0.0));
-      const float dabs = wrap ? 6.2831853071795864769f - w : w;
-      const float pf = (float)phi;
-      if (fabsf(dabs - pf) > 4e-6f * fmaxf(dabs, pf) && pf > 1e-30f) { if (dabs > pf) curv_fail = true; }
-      else exact = true;
+      const double cr = pc * sn - psn * c, dt = pc * c + psn * sn;      // sin / cos of the wrapped angle (unit vectors)
+      const bool nb = signbit(dy);
+      if ((signbit(pdy) != nb) && (nb ? (cr > 0.0) : (cr < 0.0))) exact = true;   // the difference jumps by 2*pi: rare
+      else if (!(dt > 0.0)) curv_fail = true;                                      // |angle| >= pi/2 > phi
+      else {
+        // |angle| < pi/2:  |angle| > phi  <=>  |sin angle| > sin phi;  sin phi by its series (phi < 0.5: 1e-11 relative)
+        const double p2 = phi * phi;
+        const double sp = phi * fma(p2, fma(p2, fma(p2, fma(p2, 1.0 / 362880.0, -1.0 / 5040.0), 1.0 / 120.0), -1.0 / 6.0), 1.0);
+        const double a = fabs(cr);
+        if (fabs(a - sp) > 1e-6 * fmax(a, sp)) { if (a > sp) curv_fail = true; }
+        else exact = true;
+      }
     }
     if (exact) {
       const double dyaw = heading_of(dx, dy) - heading_of(pdx, pdy);
@@ -416,10 +421,12 @@ struct EvalSink {
   }
 
   __device__ __forceinline__ void collide(int i, double x, double y, double c, double sn) {
-    if (collided || p.n_dict <= 0 || i >= p.tcap || (i % p.check_res) != 0) return;
+    if (i != next_check) return;               // i % check_res == 0 without the division
+    next_check += p.check_res;
+    const int r = row++;
+    if (collided || p.n_dict <= 0 || i >= p.tcap) return;
     const int abs_step = p.now + i;
     if (abs_step >= p.Tt) return;
-    const int r = i / p.check_res;
     const float4* row = tb.broad + (size_t)(tb.broad_row0 + r * tb.broad_stride) * p.OMpad;
     const float fx = (float)(x - p.ox), fy = (float)(y - p.oy);
     const float m2x = -2.0f * fx, m2y = -2.0f * fy, ne2 = -fmaf(fx, fx, fy * fy);
@@ -559,6 +566,7 @@ __device__ __forceinline__ void stage_tables(const EvalParams& p, unsigned char*
     tb.broad = p.broad; tb.broad_row0 = p.now; tb.broad_stride = p.check_res;
   }
   tb.sp.knot = sm_knot; tb.sp.coef = sm_coef; tb.sp.K = p.K; tb.sp.kpad = p.kpad;
+  tb.sp.inv_h = (double)(p.K - 1) / sm_knot[p.K - 1];
   tb.time = sm_time; tb.lat = sm_lat;
   tb.list = sm_broad; tb.row_off = reinterpret_cast<const int*>(smem + L.off_rows); tb.row_cnt = tb.row_off + p.win_rows;
   tb.use_lists = false;
@@ -572,7 +580,7 @@ __device__ __forceinline__ void stage_tables(const EvalParams& p, unsigned char*
 //   phase B  one warp per row: ballot-compaction of the states whose reachable interval (pack_obstacles_kernel)
 //            overlaps the row's range.
 // Falls back to the global table (tb.use_lists stays false) when the lists would not fit.
-__device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* smem, BlockTables& tb, const LonProfile& lp, bool active) {
+__device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* smem, BlockTables& tb, LonWalk lp, bool active) {
   const SmemLayout L = eval_smem_layout(p.win_rows, p.OMpad, 2, p.K, p.kpad, p.P, p.W, p.list_cap);
   float4* list = reinterpret_cast<float4*>(smem + L.off_broad);
   int* row_off = reinterpret_cast<int*>(smem + L.off_rows);
@@ -589,7 +597,7 @@ __device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* 
     unsigned int lo = 0x7f800000u, hi = 0u;
     if (active) {
       double s, sd, sdd, sddd;
-      lon_eval(lp, p.s0, p.v0, p.a0, tb.time[r * p.check_res], s, sd, sdd, sddd);
+      lon_walk_eval(lp, tb.time[r * p.check_res], s, sd, sdd, sddd);
       s = fmin(fmax(s, 0.0), s_end);                  // off-line samples are never collision-checked
       lo = __float_as_uint(__double2float_rd(s));     // s >= 0: the bit patterns order like the values
       hi = __float_as_uint(__double2float_ru(s));
@@ -719,8 +727,8 @@ __global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_kernel
     stage_tables<kMode>(p, smem, tb, latcost);
     const bool active = n < N;
     const int w = active ? n / Ns : 0, k = active ? n - w * Ns : 0;
-    LonProfile lp;
-    lon_profile_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
+    LonWalk lp;
+    lon_walk_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
     if (kMode == 2) build_lists(p, smem, tb, lp, active);
     if (active) {
       EvalSink sink(p, tb);
@@ -835,8 +843,8 @@ __global__ void __launch_bounds__(EVAL_THREADS) dump_states_kernel(const __grid_
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int w = n / Ns, k = n - w * Ns;
-  LonProfile lp;
-  lon_profile_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
+  LonWalk lp;
+  lon_walk_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
   DumpSink sink{states + (size_t)n * p.P * JSSP_STATE_COLS, tb.lat + (size_t)w * p.P * 4, 0.0, 0.0};
   const int seg0 = spline_bisect(tb.sp, fmin(fmax(p.s0, tb.sp.knot[0]), tb.sp.knot[p.K - 1]));
   walk_candidate(p, tb, lp, w, seg0, sink);
