@@ -176,6 +176,36 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def replay_latency(device: int, cpu: bool = True) -> dict:
+    """p50 plan-cycle latency (host call -> best trajectory on the host) on BASELINE configs[0]: the bundled scenario
+    8_3_4_565 replayed through the reference-shaped interface (IntersectionPlanner.plan), default sampling grid.  The CPU
+    figure is the loop-form port on the first cycles of the same replay, 1 core."""
+    import dlii_jssp_b200 as J
+    sc = J.scenario.scenario_from_fixture(os.path.join(ROOT, "tests", "golden", "scenario_8_3_4_565.npz"))
+    J.replay.run_replay(sc, device=device, max_cycles=5)                       # warm-up (allocations, first launches)
+    res = J.replay.run_replay(sc, device=device)
+    out = {"workload": "inputs/8_3_4_565 replay, default grid (3 widths x (main + stop seeds)), 6 background vehicles", "cycles": res.cycles,
+           "end": res.end, "candidates_per_cycle_median": int(np.median(res.n_candidates)), "gpu_p50_ms": res.p50_ms,
+           "gpu_p95_ms": 1e3 * float(np.quantile(res.plan_seconds, 0.95))}
+    if cpu:
+        from oracle import jssp_oracle as O, jssp_loop as L
+        cfg = O.OracleConfig(ego_length=sc.ego["length"], ego_width=sc.ego["width"])
+        spline = O.CubicSpline2D(sc.route_xy[:, 0], sc.route_xy[:, 1])
+        final = int(sc.max_t / sc.dt)
+        t = J.scenario.pack_obstacle_dict(sc.vehicle_traj, sc.dt, final + cfg.n_steps + 2)
+        obs = (t.state, t.valid.astype(bool), t.size, t.prob)
+        lat = []
+        for now, fr in ((0, (2.93, 5.67, 0.0, 0.6, -0.4, 0.0)), (20, (14.0, 5.2, -0.3, 0.1, 0.0, 0.0)), (50, (27.0, 4.0, 0.2, 0.0, 0.0, 0.0))):
+            t0 = time.perf_counter()
+            with np.errstate(all="ignore"):
+                seeds = O.sample_seeds(fr[0], fr[1], fr[2], cfg)               # vectorised: faster than the reference's nested loops
+                L.plan_cycle_loop(cfg, spline, fr, obs, now, final, seeds=seeds)
+            lat.append(time.perf_counter() - t0)
+        out["cpu_p50_ms"] = 1e3 * float(np.median(lat))
+        out["cpu_note"] = "loop-form float64 port, 1 core, 3 representative cycles (seed enumeration vectorised)"
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -318,6 +348,8 @@ def run_ours(args):
                              "note": "algorithmic flops = (128 + 48*O*M/2) per candidate-timestep (SURVEY 8d); broad-phase culling skips most of "
                                      "the 48-flop rectangle tests, so achieved can exceed the executed-flop rate - see profiles/ for pipe utilisation"},
                 "selected": {"best_idx": res.best_idx, "best_cost": res.best_cost}}
+        if world == 1:
+            line["plan_cycle"] = replay_latency(local, cpu=not args.no_cpu)
         if world == 1 and not args.no_cpu:
             n_s = max(64, cyc.n_candidates // args.cpu_sample_div)
             rate, used, dt = cpu_port_rate(args.workload, cyc, n_s, 1)

@@ -38,7 +38,8 @@ def needs_build() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+    extra = os.environ.get("JSSP_NVCC_EXTRA", "").split()      # e.g. -DJSSP_EVAL_THREADS=128 -DJSSP_EVAL_MIN_BLOCKS=5 (tuning experiments)
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)

@@ -13,8 +13,14 @@
 
 namespace jssp {
 
-constexpr int EVAL_THREADS = 256;
-constexpr int EVAL_MIN_BLOCKS = 2;
+#ifndef JSSP_EVAL_THREADS
+#define JSSP_EVAL_THREADS 256
+#endif
+#ifndef JSSP_EVAL_MIN_BLOCKS
+#define JSSP_EVAL_MIN_BLOCKS 2
+#endif
+constexpr int EVAL_THREADS = JSSP_EVAL_THREADS;
+constexpr int EVAL_MIN_BLOCKS = JSSP_EVAL_MIN_BLOCKS;
 constexpr float SAT_EPS = 2e-3f;        // fp32 guard band [m]; inside it the pair is re-decided in float64
 constexpr float FAR_AWAY = 1e30f;       // x of an absent obstacle state: squared distance overflows to +inf -> culled
 
@@ -328,20 +334,16 @@ __device__ __forceinline__ void walk_candidate(const EvalParams& p, const BlockT
                                                int seg, Sink& sink) {
   const int P = p.P;
   const double* lat = tb.lat + (size_t)w * P * 4;
-  bool live = true;
   int n_pts = P;
   double xp = 0, yp = 0;
-  for (int i = 0; i < P; ++i) {
-    const double t = tb.time[i];
+  int i = 0;
+  // live part: ends at the first sample whose s is off the reference line (calc_position returned None -> break,
+  // jerk_space_sampling_planner.py:138-139)
+  for (; i < P; ++i) {
     double s, sd, sdd, sddd;
-    lon_walk_eval(lp, t, s, sd, sdd, sddd);
-    sink.sample(i, t, s, sd, sdd, sddd);
-    if (!live) continue;
-    if (!spline_in_range(tb.sp, s)) {   // calc_position returned None -> break (jerk_space_sampling_planner.py:138-139)
-      live = false;
-      n_pts = i;
-      continue;
-    }
+    lon_walk_eval(lp, tb.time[i], s, sd, sdd, sddd);
+    sink.sample(i, tb.time[i], s, sd, sdd, sddd);
+    if (!spline_in_range(tb.sp, s)) { n_pts = i; ++i; break; }
     seg = spline_walk(tb.sp, s, seg);
     double x, y;
     frenet_point(tb.sp, seg, s, lat[i * 4], x, y);
@@ -355,6 +357,12 @@ __device__ __forceinline__ void walk_candidate(const EvalParams& p, const BlockT
       sink.segment(i - 1, xp, yp, dx, dy, ds, c, sn);
     }
     xp = x; yp = y;
+  }
+  // Frenet-only tail (the cost still sums over every sample)
+  for (; i < P; ++i) {
+    double s, sd, sdd, sddd;
+    lon_walk_eval(lp, tb.time[i], s, sd, sdd, sddd);
+    sink.sample(i, tb.time[i], s, sd, sdd, sddd);
   }
   sink.finish(n_pts, xp, yp);
 }
