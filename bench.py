@@ -361,18 +361,72 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_sweep(args):
+    """BASELINE configs[3]: replay sweep over seeded synthetic intersections (the reference's scenes_all(800) archive is
+    absent), scenario ids dealt round-robin to the ranks, no data-path collective; only the result rows are gathered."""
+    import torch
+    import torch.distributed as dist
+    import dlii_jssp_b200 as J
+    from dlii_jssp_b200 import distributed as D
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ids = D.shard_scenarios(range(args.scenarios), world, rank)
+    scs = [J.scenario.synthetic_intersection(i) for i in ids]                   # generated before the clock starts
+    planner = J.IntersectionPlanner(J.PlannerSettings(), scs[0].observation(), "JSSP", device=local)   # workspace allocated before the clock
+    J.replay.run_sweep(scs[:2], device=local, max_cycles=5, planner=planner)    # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    results = J.replay.run_sweep(scs, device=local, max_cycles=args.cycles, planner=planner)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    units = sum(sum(r.n_candidates) for r in results) * 51
+    cycles = sum(r.cycles for r in results)
+    lat = [x for r in results for x in r.plan_seconds]
+    tot = torch.tensor([dt, float(units), float(cycles), float(len(results))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = tot.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        tot[0] = tmax[0]
+        rows = D.gather_results([(r.name, r.end, r.cycles) for r in results])
+    else:
+        rows = [[(r.name, r.end, r.cycles) for r in results]]
+    if rank == 0:
+        dt_max, units_all, cycles_all, n_all = [float(v) for v in tot.tolist()]
+        ends = {}
+        for part in rows:
+            for _, e, _ in part:
+                ends[str(e)] = ends.get(str(e), 0) + 1
+        print(json.dumps({"metric": METRIC, "value": units_all / dt_max, "unit": UNIT, "n_gpus": world, "steps": int(cycles_all), "warmup": 10,
+                          "ms_per_step": 1e3 * dt_max * world / max(cycles_all, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f64 geometry + f32 collision", "data": "synthetic",
+                          "config": {"workload": f"{int(n_all)}-scenario synthetic intersection replay sweep, default grid, <= {args.cycles} cycles each "
+                                                 "(BASELINE configs[3]; reference data absent)", "parallelism": f"scenario shards over {world} ranks, no collective"},
+                          "scenarios_per_s": n_all / dt_max, "cycles_per_s": cycles_all / dt_max, "p50_cycle_ms_rank0": 1e3 * statistics.median(lat),
+                          "end_status_counts": ends}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C3", choices=["C3", "C5"])
+    ap.add_argument("--workload", default="C3", choices=["C3", "C5", "C4"])
+    ap.add_argument("--scenarios", type=int, default=800, help="C4: number of synthetic scenarios in the sweep")
+    ap.add_argument("--cycles", type=int, default=100, help="C4: plan cycles per scenario (upper bound)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--cpu-sample-div", type=int, default=32, help="cpu_baseline sample = candidates / this")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "C4":
+        run_sweep(args)
     else:
         run_ours(args)
 

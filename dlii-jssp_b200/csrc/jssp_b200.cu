@@ -56,6 +56,8 @@ struct jssp_handle {
   BestRecord* h_best = nullptr;   // pinned
   double* d_best_traj = nullptr;
   double* h_best_traj = nullptr;  // pinned
+  unsigned char *d_result = nullptr, *h_result = nullptr;   // contiguous [best | counts | trajectory]
+  size_t result_bytes = 0;
   EvalParams last{};
   bool last_valid = false;
   int last_flags = 0;
@@ -274,9 +276,6 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(cudaMalloc(&h->d_seeds, (size_t)cfg->max_seeds * 10 * sizeof(double)));
   CKC(cudaMalloc(&h->d_list_main, (size_t)SORT_CAP * sizeof(uint32_t)));
   CKC(cudaMalloc(&h->d_list_stop, (size_t)SORT_CAP * sizeof(uint32_t)));
-  CKC(cudaMalloc(&h->d_counts, 4 * sizeof(int)));
-  CKC(cudaMemset(h->d_counts, 0, 4 * sizeof(int)));
-  CKC(cudaMallocHost(&h->h_counts, 4 * sizeof(int)));
   h->kpad = (cfg->max_knots + 1) & ~1;   // capacity; the per-scenario stride is set in jssp_set_refline
   CKC(cudaMalloc(&h->d_knot, (size_t)cfg->max_knots * sizeof(double)));
   CKC(cudaMalloc(&h->d_coef, (size_t)8 * h->kpad * sizeof(double)));
@@ -297,11 +296,19 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(cudaMalloc(&h->d_blk_idx, (size_t)h->max_blocks * sizeof(int)));
   CKC(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
   CKC(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
-  CKC(cudaMalloc(&h->d_best, sizeof(BestRecord)));
-  CKC(cudaMemset(h->d_best, 0, sizeof(BestRecord)));
-  CKC(cudaMallocHost(&h->h_best, sizeof(BestRecord)));
-  CKC(cudaMalloc(&h->d_best_traj, (size_t)h->P * JSSP_TRAJ_COLS * sizeof(double)));
-  CKC(cudaMallocHost(&h->h_best_traj, (size_t)h->P * JSSP_TRAJ_COLS * sizeof(double)));
+  // one contiguous result block so that a cycle's results come back with a single copy:
+  // [BestRecord, padded to 48 B][seed counts 16 B][selected trajectory P x 16 float64]
+  static_assert(sizeof(BestRecord) <= 48, "result block layout");
+  h->result_bytes = 64 + (size_t)h->P * JSSP_TRAJ_COLS * sizeof(double);
+  CKC(cudaMalloc(&h->d_result, h->result_bytes));
+  CKC(cudaMemset(h->d_result, 0, h->result_bytes));
+  CKC(cudaMallocHost(&h->h_result, h->result_bytes));
+  h->d_best = reinterpret_cast<BestRecord*>(h->d_result);
+  h->d_counts = reinterpret_cast<int*>(h->d_result + 48);
+  h->d_best_traj = reinterpret_cast<double*>(h->d_result + 64);
+  h->h_best = reinterpret_cast<BestRecord*>(h->h_result);
+  h->h_counts = reinterpret_cast<int*>(h->h_result + 48);
+  h->h_best_traj = reinterpret_cast<double*>(h->h_result + 64);
   CKC(cudaFuncSetAttribute(evaluate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CKC(cudaFuncSetAttribute(evaluate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CKC(cudaFuncSetAttribute(evaluate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
@@ -316,13 +323,10 @@ int32_t jssp_destroy(jssp_handle* h) {
   if (!h) return JSSP_OK;
   cudaSetDevice(h->device);
   void* dev[] = {h->d_time, h->d_j1, h->d_t1, h->d_t2, h->d_j3, h->d_t3, h->d_t4, h->d_jneg, h->d_jpos, h->d_ts, h->d_seeds,
-                 h->d_list_main, h->d_list_stop, h->d_counts, h->d_knot, h->d_coef, h->d_raw_state, h->d_raw_valid, h->d_raw_size,
-                 h->d_raw_prob, h->d_broad, h->d_narrow, h->d_obs64, h->d_ext64, h->d_sint, h->d_probf, h->d_knot_xy, h->d_blk_cost, h->d_blk_idx, h->d_ticket, h->d_best,
-                 h->d_best_traj};
+                 h->d_list_main, h->d_list_stop, h->d_knot, h->d_coef, h->d_raw_state, h->d_raw_valid, h->d_raw_size,
+                 h->d_raw_prob, h->d_broad, h->d_narrow, h->d_obs64, h->d_ext64, h->d_sint, h->d_probf, h->d_knot_xy, h->d_blk_cost, h->d_blk_idx, h->d_ticket, h->d_result};
   for (void* p : dev) if (p) cudaFree(p);
-  if (h->h_counts) cudaFreeHost(h->h_counts);
-  if (h->h_best) cudaFreeHost(h->h_best);
-  if (h->h_best_traj) cudaFreeHost(h->h_best_traj);
+  if (h->h_result) cudaFreeHost(h->h_result);
   delete h;
   return JSSP_OK;
 }
@@ -450,10 +454,8 @@ int32_t jssp_fetch_best(jssp_handle* h, void* stream, jssp_cycle_out* out) {
   if (!h->last_valid) return JSSP_ERR_NOT_READY;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
-  CK(cudaMemcpyAsync(h->h_best, h->d_best, sizeof(BestRecord), cudaMemcpyDeviceToHost, st));
   const bool want_traj = out->best_traj_host && !(h->last_flags & JSSP_FLAG_NO_EXPORT);
-  if (want_traj)
-    CK(cudaMemcpyAsync(h->h_best_traj, h->d_best_traj, (size_t)h->P * JSSP_TRAJ_COLS * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h->h_result, h->d_result, want_traj ? h->result_bytes : 64, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   out->n_candidates = h->h_best->n_candidates;
   out->n_seeds = h->h_best->n_seeds;
@@ -461,17 +463,18 @@ int32_t jssp_fetch_best(jssp_handle* h, void* stream, jssp_cycle_out* out) {
   out->best_cost = h->h_best->cost;
   out->best_n_pts = h->h_best->n_pts;
   if (want_traj && out->best_idx >= 0) memcpy(out->best_traj_host, h->h_best_traj, (size_t)h->P * JSSP_TRAJ_COLS * sizeof(double));
-  if (!h->last.n_seeds_ptr) return JSSP_OK;
   // enumerated seeds: surface an overflow detected on the device
-  CK(cudaMemcpyAsync(h->h_counts, h->d_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return h->h_counts[3] ? JSSP_ERR_SEED_OVERFLOW : JSSP_OK;
+  return (h->last.n_seeds_ptr && h->h_counts[3]) ? JSSP_ERR_SEED_OVERFLOW : JSSP_OK;
 }
 
 int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jssp_cycle_out* out) {
   if (!h || !in || !out) return JSSP_ERR_INVALID_ARG;
   if (h->K < 2 || !h->obs_set) return JSSP_ERR_NOT_READY;
   const bool ext = in->seeds_dev != nullptr;
+  if (!ext && (in->flags & JSSP_FLAG_ENUMERATE)) {
+    const int rc0 = jssp_enumerate_seeds(h, in->s0, in->v0, in->a0, stream, nullptr, nullptr);
+    if (rc0 != JSSP_OK) return rc0;
+  }
   if (!ext && !h->seeds_ready) return JSSP_ERR_NOT_READY;
   if (ext && (in->n_seeds < 0 || in->n_seeds > h->cfg.max_seeds)) return JSSP_ERR_CAPACITY;
   const int W = in->n_widths > 0 ? in->n_widths : h->cfg.num_width;

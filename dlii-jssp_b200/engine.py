@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import JsspError, JsspConfigC, JsspCycleIn, JsspCycleOut, JsspImmParams, FLAG_NO_SYNC, FLAG_NO_EXPORT, FLAG_NO_CULL, TRAJ_COLUMNS
+from ._lib import JsspError, JsspConfigC, JsspCycleIn, JsspCycleOut, JsspImmParams, FLAG_NO_SYNC, FLAG_NO_EXPORT, FLAG_NO_CULL, FLAG_ENUMERATE, TRAJ_COLUMNS
 
 
 @dataclass
@@ -95,6 +95,10 @@ class JsspEngine:
         self._alloc(cap)
         self._best_host = np.zeros((self.P, _lib.JSSP_TRAJ_COLS), dtype=np.float64)
         self._states: Optional[torch.Tensor] = None
+        self._fixed_stream: Optional[int] = None
+        # persistent structs of the one-call plan cycle (plan_cycle): only the start state changes between cycles
+        self._pc_in, self._pc_out = JsspCycleIn(), JsspCycleOut()
+        self._pc_in.flags = FLAG_ENUMERATE
 
     # -- buffers ------------------------------------------------------------------------------------------------
     def _alloc(self, cap: int):
@@ -112,7 +116,14 @@ class JsspEngine:
 
     @property
     def stream(self) -> int:
+        """The CUDA stream handed to the library: torch's current stream, unless pinned with use_stream()."""
+        if self._fixed_stream is not None:
+            return self._fixed_stream
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def use_stream(self, stream: Optional[torch.cuda.Stream]):
+        """Pin every following call to ``stream`` (None = follow torch's current stream again); saves the per-call lookup."""
+        self._fixed_stream = None if stream is None else stream.cuda_stream
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -208,6 +219,27 @@ class JsspEngine:
         self._last = (cin, cout, want_states)
         self._check(self.lib.jssp_evaluate(self._h, C.byref(cin), self.stream, C.byref(cout)), "jssp_evaluate")
         return self._result(cout, want_states, export) if sync else None
+
+    def plan_cycle(self, frenet0, time_step_now: int, final_time_step: int) -> JsspCycleOut:
+        """One whole plan cycle in ONE library call: device-side seed enumeration from (s, s_d, s_dd), fused evaluation,
+        selection and export; blocks until the selected trajectory is in ``best_traj_host``.  Returns the (reused)
+        jssp_cycle_out struct: n_candidates, n_seeds, best_idx, best_cost, best_n_pts; masks and costs stay in
+        ``self.feasible / collision / cost`` on the device."""
+        cin, cout = self._pc_in, self._pc_out
+        cin.s0, cin.v0, cin.a0, cin.d0, cin.d_d0, cin.d_dd0 = frenet0
+        cin.time_step_now, cin.final_time_step = time_step_now, final_time_step
+        if not cout.best_traj_host:
+            self._alloc(self.cfg.num_width * self.cfg.max_seeds)
+            cout.feasible_dev, cout.collision_dev, cout.cost_dev = self.feasible.data_ptr(), self.collision.data_ptr(), self.cost.data_ptr()
+            cout.best_traj_host = self._best_host.ctypes.data
+        rc = self.lib.jssp_evaluate(self._h, C.byref(cin), self.stream, C.byref(cout))
+        if rc != 0:
+            self._check(rc, "jssp_evaluate")
+        return cout
+
+    def result_of(self, cout: JsspCycleOut, want_states: bool = False) -> CycleResult:
+        """Full CycleResult view (device mask / cost slices) for a struct returned by plan_cycle."""
+        return self._result(cout, want_states, True)
 
     def fetch(self) -> CycleResult:
         cin, cout, want_states = self._last

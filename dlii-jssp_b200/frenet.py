@@ -76,15 +76,12 @@ class JerkSpaceSamplingFrenetTrajectory:
     def from_rows(cls, rows: np.ndarray, n_pts: int, idx: int, path_id: int, cost: float) -> "JerkSpaceSamplingFrenetTrajectory":
         """rows = [P, 16] float64 as exported by jssp_evaluate (columns = FIELDS)."""
         tr = cls()
-        P = rows.shape[0]
-        for k, f in enumerate(cls.FIELDS[:9]):
-            setattr(tr, f, rows[:, k].copy())
+        cols = np.ascontiguousarray(rows.T)          # one copy; the fields below are views of it
         n = max(int(n_pts), 0)
-        tr.x, tr.y, tr.yaw = rows[:n, 9].copy(), rows[:n, 10].copy(), rows[:n, 11].copy()
-        if n < 2:
-            tr.yaw = np.zeros(0)
-        tr.ds, tr.c = rows[:max(n - 1, 0), 12].copy(), rows[:max(n - 1, 0), 13].copy()
-        tr.c_d, tr.c_dd = rows[:max(n - 2, 0), 14].copy(), rows[:max(n - 3, 0), 15].copy()
+        tr.t, tr.s, tr.s_d, tr.s_dd, tr.s_ddd, tr.d, tr.d_d, tr.d_dd, tr.d_ddd = cols[:9]
+        tr.x, tr.y, tr.yaw = cols[9, :n], cols[10, :n], (cols[11, :n] if n >= 2 else cols[11, :0])
+        tr.ds, tr.c = cols[12, :max(n - 1, 0)], cols[13, :max(n - 1, 0)]
+        tr.c_d, tr.c_dd = cols[14, :max(n - 2, 0)], cols[15, :max(n - 3, 0)]
         tr.idx, tr.path_id, tr.cost_total = idx, path_id, float(cost)
         tr.constraint_passed = tr.collision_passed = True
         return tr

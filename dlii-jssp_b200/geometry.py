@@ -40,13 +40,14 @@ class CubicSpline1D:
         h = np.diff(self.x)
         if np.any(h <= 0):
             raise ValueError("spline knots must be strictly increasing (remove duplicate centre-line points first)")
+        self._xl = self.x.tolist()
         self.a = y.copy()
         self.c = _natural_spline_c(h, y)
         self.d = (self.c[1:] - self.c[:-1]) / (3.0 * h)
         self.b = (y[1:] - y[:-1]) / h - h / 3.0 * (2.0 * self.c[:-1] + self.c[1:])
 
     def _seg(self, x: float) -> int:
-        return min(max(bisect.bisect_right(self.x.tolist(), x) - 1, 0), len(self.x) - 2)
+        return min(max(bisect.bisect_right(self._xl, x) - 1, 0), len(self.x) - 2)
 
     def calc_position(self, x: float):
         if x < self.x[0] or x > self.x[-1]:
@@ -93,6 +94,22 @@ class CubicSpline2D:
         if dx is None:
             return None
         return (ddy * dx - ddx * dy) / ((dx ** 2 + dy ** 2) ** 1.5)
+
+    def sample(self, s: np.ndarray) -> np.ndarray:
+        """[len(s), 4] = x, y, yaw, curvature at the arc lengths ``s`` (all inside the line): the vectorised form of the
+        per-point calls of generate_frenet_frame (jerk_space_sampling_planner.py:366-371), same expressions per element."""
+        s = np.asarray(s, dtype=np.float64)
+        i = np.clip(np.searchsorted(self.s_list, s, side="right") - 1, 0, len(self.s_list) - 2)
+        dx = s - self.s_list[i]
+        out = np.empty((len(s), 4))
+        d1, d2 = [], []
+        for col, sp in enumerate((self.sx, self.sy)):
+            out[:, col] = ((sp.a[i] + sp.b[i] * dx) + sp.c[i] * (dx * dx)) + sp.d[i] * ((dx * dx) * dx)
+            d1.append((sp.b[i] + (2.0 * sp.c[i]) * dx) + (3.0 * sp.d[i]) * (dx * dx))
+            d2.append(2.0 * sp.c[i] + (6.0 * sp.d[i]) * dx)
+        out[:, 2] = np.arctan2(d1[1], d1[0])
+        out[:, 3] = (d2[1] * d1[0] - d2[0] * d1[1]) / ((d1[0] ** 2 + d1[1] ** 2) ** 1.5)
+        return out
 
     def coefficient_table(self) -> np.ndarray:
         """[K-1, 8] = ax, bx, cx, dx, ay, by, cy, dy per segment: the layout jssp_set_refline uploads."""

@@ -89,7 +89,7 @@ class JerkSpaceSamplingPlanner(object):
         self.engine = JsspEngine(cfg, device=device)
         self._cubic_spline = None
         self._obstacle_key = None
-        self.last_result: Optional[CycleResult] = None
+        self.last_result = None            # jssp_cycle_out of the last cycle (n_candidates, n_seeds, best_idx, best_cost, best_n_pts)
 
     # -- reference line -------------------------------------------------------------------------------------------
     @property
@@ -109,10 +109,7 @@ class JerkSpaceSamplingPlanner(object):
         """Same contract as jerk_space_sampling_planner.py:364-371: returns (spline, [x, y, yaw, curvature] every 0.1 m)."""
         self.cubic_spline = CubicSpline2D(centerline_pts[:, 0], centerline_pts[:, 1])
         s = np.arange(0, self._cubic_spline.s_list[-1], 0.1)
-        ref_xy = [self._cubic_spline.calc_position(i_s) for i_s in s]
-        ref_yaw = [self._cubic_spline.calc_yaw(i_s) for i_s in s]
-        ref_rk = [self._cubic_spline.calc_curvature(i_s) for i_s in s]
-        return self._cubic_spline, np.column_stack((ref_xy, ref_yaw, ref_rk))
+        return self._cubic_spline, self._cubic_spline.sample(s)
 
     # -- obstacles ------------------------------------------------------------------------------------------------
     def set_obstacles(self, obstacles, dt: float, final_time_step: int):
@@ -150,14 +147,12 @@ class JerkSpaceSamplingPlanner(object):
         time_step_now = int(ts["t"] / ts["dt"])                       # :300 (float truncation is part of the contract)
         final_time_step = int(ts["max_t"] / ts["dt"])                 # :244
         self.set_obstacles(obstacles, ts["dt"], final_time_step)
-        self.engine.enumerate_seeds(frenet_state.s, frenet_state.s_d, frenet_state.s_dd, sync=False)
-        res = self.engine.evaluate(frenet_state.as_tuple() if hasattr(frenet_state, "as_tuple") else
-                                   (frenet_state.s, frenet_state.s_d, frenet_state.s_dd, frenet_state.d, frenet_state.d_d, frenet_state.d_dd),
-                                   time_step_now, final_time_step)
+        res = self.engine.plan_cycle((frenet_state.s, frenet_state.s_d, frenet_state.s_dd, frenet_state.d, frenet_state.d_d, frenet_state.d_dd),
+                                     time_step_now, final_time_step)
         self.last_result = res
         self.all_path_sampling_trajs.append(res.n_candidates)
         if res.best_idx >= 0:
-            self.best_traj = JerkSpaceSamplingFrenetTrajectory.from_rows(res.best_traj, res.best_n_pts, res.best_idx,
+            self.best_traj = JerkSpaceSamplingFrenetTrajectory.from_rows(self.engine._best_host, res.best_n_pts, res.best_idx,
                                                                        res.best_idx // max(res.n_seeds, 1), res.best_cost)
         elif self.verbose:
             print("##log## No solution.")
@@ -179,7 +174,10 @@ class JerkSpaceSamplingPlanner(object):
     def count_passed(self) -> int:
         """Number of candidates that passed both checks in the last cycle (the reference prints it, :324)."""
         r = self.last_result
-        return int(((r.feasible == 1) & (r.collision == 0)).sum().item()) if r is not None else 0
+        if r is None:
+            return 0
+        n = r.n_candidates
+        return int(((self.engine.feasible[:n] == 1) & (self.engine.collision[:n] == 0)).sum().item())
 
 
 class PlannerSettings(object):

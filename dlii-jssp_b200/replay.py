@@ -115,10 +115,12 @@ def run_replay(scenario: ReplayScenario, device: int = 0, max_cycles: Optional[i
     return res
 
 
-def run_sweep(scenarios, device: int = 0, max_cycles: Optional[int] = None) -> List[ReplayResult]:
+def run_sweep(scenarios, device: int = 0, max_cycles: Optional[int] = None, planner: Optional[IntersectionPlanner] = None) -> List[ReplayResult]:
     """Replay a shard of independent scenarios on one GPU (BASELINE config 4: each rank calls this on its shard).  The
     planner (device workspace) is reused while the ego footprint stays the same."""
-    out, planner, dims = [], None, None
+    out, dims = [], None
+    if planner is not None:
+        dims = (planner.ego_vehicle.l, planner.ego_vehicle.w)
     for sc in scenarios:
         d = (sc.ego["length"], sc.ego["width"])
         if planner is None or d != dims:
