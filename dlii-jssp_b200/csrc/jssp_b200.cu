@@ -291,7 +291,7 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(cudaMalloc(&h->d_sint, ((om + 31) & ~(size_t)31) * tt * sizeof(float2)));
   CKC(cudaMalloc(&h->d_probf, om * sizeof(float)));
   CKC(cudaMalloc(&h->d_knot_xy, (size_t)cfg->max_knots * 2 * sizeof(double)));
-  h->max_blocks = (int)(((size_t)cfg->max_seeds * JSSP_MAX_WIDTHS + EVAL_THREADS - 1) / EVAL_THREADS);
+  h->max_blocks = (int)(((size_t)cfg->max_seeds * JSSP_MAX_WIDTHS + SMALL_WARPS - 1) / SMALL_WARPS);   // warp-per-candidate grid
   CKC(cudaMalloc(&h->d_blk_cost, (size_t)h->max_blocks * sizeof(double)));
   CKC(cudaMalloc(&h->d_blk_idx, (size_t)h->max_blocks * sizeof(int)));
   CKC(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
@@ -312,6 +312,7 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(cudaFuncSetAttribute(evaluate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CKC(cudaFuncSetAttribute(evaluate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CKC(cudaFuncSetAttribute(evaluate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CKC(cudaFuncSetAttribute(evaluate_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CKC(cudaFuncSetAttribute(dump_states_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CKC(cudaDeviceSynchronize());
 #undef CKC
@@ -534,10 +535,17 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   p.best_traj = (in->flags & JSSP_FLAG_NO_EXPORT) ? nullptr : h->d_best_traj;
 
   const long long n_max = (long long)W * (ext ? in->n_seeds : c.max_seeds);
-  int blocks = (int)((n_max + EVAL_THREADS - 1) / EVAL_THREADS);
+  // small cycles (the default sampling grid: ~10^3 candidates) run one warp per candidate: latency, not throughput, matters
+  const SmemLayout Ls = eval_smem_layout(0, p.OMpad, 0, p.K, p.kpad, p.P, p.W);
+  const size_t small_bytes = Ls.total + small_scratch_bytes(p.P);
+  bool small = n_max <= 16384 && small_bytes <= (size_t)h->max_smem_optin;
+  if (in->flags & JSSP_FLAG_FORCE_THREAD) small = false;
+  if ((in->flags & JSSP_FLAG_FORCE_WARP) && small_bytes <= (size_t)h->max_smem_optin) small = true;
+  int blocks = small ? (int)((n_max + SMALL_WARPS - 1) / SMALL_WARPS) : (int)((n_max + EVAL_THREADS - 1) / EVAL_THREADS);
   if (blocks < 1) blocks = 1;
   if (blocks > h->max_blocks) return JSSP_ERR_CAPACITY;
-  if (mode == 2) evaluate_kernel<2><<<blocks, EVAL_THREADS, L.total, st>>>(p);
+  if (small) { p.smem_obs = 0; p.win_rows = 0; p.list_cap = 0; evaluate_small_kernel<<<blocks, SMALL_WARPS * 32, small_bytes, st>>>(p); }
+  else if (mode == 2) evaluate_kernel<2><<<blocks, EVAL_THREADS, L.total, st>>>(p);
   else if (mode == 1) evaluate_kernel<1><<<blocks, EVAL_THREADS, L.total, st>>>(p);
   else evaluate_kernel<0><<<blocks, EVAL_THREADS, L.total, st>>>(p);
   h->launches++;

@@ -369,6 +369,33 @@ __device__ __forceinline__ void walk_candidate(const EvalParams& p, const BlockT
 
 __device__ __forceinline__ double heading_of(double dx, double dy) { return atan2(dy, dx); }   // np.arctan2(y_d, x_d)
 
+// c_{i-1} = (yaw_i - yaw_{i-1}) / ds_{i-1} with yaw = arctan2 of the forward differences and NO unwrapping
+// (jerk_space_sampling_planner.py:155-163); the candidate fails when |c| > kmax (:175).  (p*) = segment i-1, the others
+// segment i, each as difference vector, length and unit vector.  Fast path: sin / cos of the wrapped angle from the unit
+// vectors, compared against the series of sin(kmax * ds); the +-2*pi jump of the un-unwrapped difference is detected from
+// the exact signs; inside a 1e-6 relative guard band, for zero-length segments and for jumps the float64 atan2 decides.
+__device__ __forceinline__ bool curvature_fails(double kmax, double pdx, double pdy, double pds, double pc, double psn, double dx,
+                                                double dy, double ds, double c, double sn) {
+  const double phi = kmax * pds;
+  bool exact = !(pds > 0.0) || !(ds > 0.0) || !(phi < 0.5);
+  if (!exact) {
+    const double cr = pc * sn - psn * c, dt = pc * c + psn * sn;      // sin / cos of the wrapped angle (unit vectors)
+    const bool nb = signbit(dy);
+    if ((signbit(pdy) != nb) && (nb ? (cr > 0.0) : (cr < 0.0))) exact = true;   // the difference jumps by 2*pi: rare
+    else if (!(dt > 0.0)) return true;                                           // |angle| >= pi/2 > phi
+    else {
+      // |angle| < pi/2:  |angle| > phi  <=>  |sin angle| > sin phi;  sin phi by its series (phi < 0.5: 1e-11 relative)
+      const double p2 = phi * phi;
+      const double sp = phi * fma(p2, fma(p2, fma(p2, fma(p2, 1.0 / 362880.0, -1.0 / 5040.0), 1.0 / 120.0), -1.0 / 6.0), 1.0);
+      const double a = fabs(cr);
+      if (fabs(a - sp) > 1e-6 * fmax(a, sp)) return a > sp;
+      exact = true;
+    }
+  }
+  const double dyaw = heading_of(dx, dy) - heading_of(pdx, pdy);
+  return fabs(dyaw) > phi;      // pds == 0: inf fails (dyaw != 0), nan passes (dyaw == 0)
+}
+
 // -- the evaluation sink ---------------------------------------------------------------------------------------------
 struct EvalSink {
   const EvalParams& p;
@@ -391,31 +418,8 @@ struct EvalSink {
   }
   __device__ __forceinline__ void point(int, double, double) {}
 
-  // c_{i-1} = (yaw_i - yaw_{i-1}) / ds_{i-1} with yaw = arctan2 of the forward differences and NO unwrapping
-  // (jerk_space_sampling_planner.py:155-163); the candidate fails when |c| > kmax (:175).  Fast path: the wrapped angle
-  // between the two difference vectors from fp32 atan2f of their float64 cross / dot products, the +-2*pi jump of the
-  // un-unwrapped difference from the exact signs, and a relative guard band inside which the float64 atan2 decides.
   __device__ __forceinline__ void curvature_step(double dx, double dy, double ds, double c, double sn) {
-    const double phi = p.kmax * pds;
-    bool exact = !(pds > 0.0) || !(ds > 0.0) || !(phi < 0.5);
-    if (!exact) {
-      const double cr = pc * sn - psn * c, dt = pc * c + psn * sn;      // sin / cos of the wrapped angle (unit vectors)
-      const bool nb = signbit(dy);
-      if ((signbit(pdy) != nb) && (nb ? (cr > 0.0) : (cr < 0.0))) exact = true;   // the difference jumps by 2*pi: rare
-      else if (!(dt > 0.0)) curv_fail = true;                                      // |angle| >= pi/2 > phi
-      else {
-        // |angle| < pi/2:  |angle| > phi  <=>  |sin angle| > sin phi;  sin phi by its series (phi < 0.5: 1e-11 relative)
-        const double p2 = phi * phi;
-        const double sp = phi * fma(p2, fma(p2, fma(p2, fma(p2, 1.0 / 362880.0, -1.0 / 5040.0), 1.0 / 120.0), -1.0 / 6.0), 1.0);
-        const double a = fabs(cr);
-        if (fabs(a - sp) > 1e-6 * fmax(a, sp)) { if (a > sp) curv_fail = true; }
-        else exact = true;
-      }
-    }
-    if (exact) {
-      const double dyaw = heading_of(dx, dy) - heading_of(pdx, pdy);
-      if (fabs(dyaw) > phi) curv_fail = true;      // pds == 0: inf fails (dyaw != 0), nan passes (dyaw == 0)
-    }
+    if (curvature_fails(p.kmax, pdx, pdy, pds, pc, psn, dx, dy, ds, c, sn)) curv_fail = true;
   }
 
   // separating-axis test of the ego rectangle at (x, y, heading (c, sn)) against obstacle mode om at abs_step
@@ -484,17 +488,21 @@ struct EvalSink {
   }
 };
 
-__device__ __forceinline__ double candidate_cost(const EvalParams& p, const EvalSink& k, const double* latcost) {
+__device__ __forceinline__ double candidate_cost(const EvalParams& p, double sum_a, double sum_j, double sum_v, double s_first,
+                                                 double s_last, double risk, const double* latcost) {
   const double P = (double)p.P;
-  double cost = p.cw[1] * (1.0 - (k.s_last - k.s_first) / p.max_distance);
+  double cost = p.cw[1] * (1.0 - (s_last - s_first) / p.max_distance);
   cost = cost + p.cw[2] * (latcost[0] / P / (p.half_w * p.half_w));
   cost = cost + p.cw[3] * (latcost[1] / P);
   cost = cost + p.cw[4] * (latcost[2] / P);
-  cost = cost + p.cw[5] * (k.sum_a / P);
-  cost = cost + p.cw[6] * (k.sum_j / P);
-  cost = cost + p.cw[7] * (k.sum_v / P);
-  cost = cost + p.w_risk * k.risk;
+  cost = cost + p.cw[5] * (sum_a / P);
+  cost = cost + p.cw[6] * (sum_j / P);
+  cost = cost + p.cw[7] * (sum_v / P);
+  cost = cost + p.w_risk * risk;
   return cost;
+}
+__device__ __forceinline__ double candidate_cost(const EvalParams& p, const EvalSink& k, const double* latcost) {
+  return candidate_cost(p, k.sum_a, k.sum_j, k.sum_v, k.s_first, k.s_last, k.risk, latcost);
 }
 
 // dynamic shared memory carve-up (the host uses the same function to size the launch)
@@ -716,6 +724,76 @@ __device__ __forceinline__ void export_block(const EvalParams& p, const BlockTab
   if (i == 0) p.best->n_pts = np;
 }
 
+// Selection shared by both evaluation kernels: block argmin of (cost, index) by warp shuffles, one record per block,
+// and the last block to finish (ticket counter) reduces the per-block winners - deterministic, lexicographic, no
+// floating-point atomics - and exports the winning trajectory in the same launch.
+template <int kMode>
+__device__ __forceinline__ void select_and_export(const EvalParams& p, unsigned char* smem, BlockTables& tb, const double*& latcost,
+                                                  bool staged, double my_cost, int my_idx, int N, int Ns, double* red_cost,
+                                                  int* red_idx, bool* is_last_p, int* sm_npts_p) {
+  const int nwarps = blockDim.x >> 5;
+  // block argmin (cost, index) - warp shuffles, then one value per warp through shared memory
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oc = __shfl_down_sync(0xffffffffu, my_cost, o);
+    const int oi = __shfl_down_sync(0xffffffffu, my_idx, o);
+    if (lex_less(oc, oi, my_cost, my_idx)) { my_cost = oc; my_idx = oi; }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { red_cost[wid] = my_cost; red_idx[wid] = my_idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < nwarps; ++q)
+      if (lex_less(red_cost[q], red_idx[q], my_cost, my_idx)) { my_cost = red_cost[q]; my_idx = red_idx[q]; }
+    p.blk_cost[blockIdx.x] = my_cost;
+    p.blk_idx[blockIdx.x] = my_idx;
+    __threadfence();
+    const unsigned int t = atomicAdd(p.ticket, 1u);
+    *is_last_p = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!*is_last_p) return;
+  // the last block to finish reduces the per-block winners: deterministic, no floating-point atomics
+  __threadfence();
+  my_cost = INFINITY; my_idx = -1;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+    const double c = __ldcg(p.blk_cost + b);
+    const int i = __ldcg(p.blk_idx + b);
+    if (lex_less(c, i, my_cost, my_idx)) { my_cost = c; my_idx = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oc = __shfl_down_sync(0xffffffffu, my_cost, o);
+    const int oi = __shfl_down_sync(0xffffffffu, my_idx, o);
+    if (lex_less(oc, oi, my_cost, my_idx)) { my_cost = oc; my_idx = oi; }
+  }
+  if (lane == 0) { red_cost[wid] = my_cost; red_idx[wid] = my_idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < nwarps; ++q)
+      if (lex_less(red_cost[q], red_idx[q], my_cost, my_idx)) { my_cost = red_cost[q]; my_idx = red_idx[q]; }
+    BestRecord r;
+    r.key = orderable_bits(my_idx >= 0 ? my_cost : INFINITY);
+    r.idx = my_idx;
+    r.cost = my_cost;
+    r.n_pts = 0;
+    r.n_candidates = N;
+    r.n_seeds = Ns;
+    r.pad = 0;
+    *p.best = r;
+    *p.ticket = 0u;   // re-arm for the next launch (stream-ordered)
+    red_idx[0] = my_idx;
+  }
+  // the same block exports the winner: no second launch, no host round trip in between
+  if (p.best_traj == nullptr) return;
+  __syncthreads();
+  const int best = red_idx[0];
+  if (best < 0) return;
+  if (!staged) stage_tables<kMode>(p, smem, tb, latcost);
+  export_block(p, tb, best, p.best_traj, sm_npts_p);
+}
+
+
 template <int kMode>
 __global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_kernel(const __grid_constant__ EvalParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -749,65 +827,138 @@ __global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_kernel
       if (!sink.curv_fail && !sink.collided && isfinite(cost)) { my_cost = cost; my_idx = n; }
     }
   }
-  // block argmin (cost, index) - warp shuffles, then one value per warp through shared memory
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double oc = __shfl_down_sync(0xffffffffu, my_cost, o);
-    const int oi = __shfl_down_sync(0xffffffffu, my_idx, o);
-    if (lex_less(oc, oi, my_cost, my_idx)) { my_cost = oc; my_idx = oi; }
-  }
+  select_and_export<kMode>(p, smem, tb, latcost, staged, my_cost, my_idx, N, Ns, red_cost, red_idx, &is_last, &sm_npts);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2b: the same evaluation with ONE WARP PER CANDIDATE for small cycles (the default grid yields ~10^3 candidates: with a
+// thread per candidate the kernel's duration is one thread walking 51 samples serially, ~100 us).  Lanes own samples
+// i = lane, lane + 32, ...; positions, segments and per-sample cost terms go through shared memory, curvature is tested in
+// parallel over segments, each collision row tests 32 obstacle states at once (ballot), and lane 0 adds the cost terms
+// in time order so that the cost is bit-identical to the thread-per-candidate kernel.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SMALL_WARPS = 8;                 // candidates per block
+constexpr int SMALL_ROW = 10;                  // doubles per sample in the warp scratch: x, y | dx, dy, ds, c, sn | ea2, ej2, ev2
+__host__ __device__ inline size_t small_scratch_bytes(int P) { return (size_t)SMALL_WARPS * ((size_t)P * SMALL_ROW + 2) * 8; }
+
+__global__ void __launch_bounds__(SMALL_WARPS * 32) evaluate_small_kernel(const __grid_constant__ EvalParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ double red_cost[SMALL_WARPS];
+  __shared__ int red_idx[SMALL_WARPS];
+  __shared__ bool is_last;
+  __shared__ int sm_npts;
+  const int Ns = resolve_n_seeds(p);
+  const int N = Ns * p.W;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) { red_cost[wid] = my_cost; red_idx[wid] = my_idx; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int q = 1; q < EVAL_THREADS / 32; ++q)
-      if (lex_less(red_cost[q], red_idx[q], my_cost, my_idx)) { my_cost = red_cost[q]; my_idx = red_idx[q]; }
-    p.blk_cost[blockIdx.x] = my_cost;
-    p.blk_idx[blockIdx.x] = my_idx;
-    __threadfence();
-    const unsigned int t = atomicAdd(p.ticket, 1u);
-    is_last = (t == gridDim.x - 1);
+  const int n = blockIdx.x * SMALL_WARPS + wid;
+  const int P = p.P;
+  double my_cost = INFINITY;
+  int my_idx = -1;
+  BlockTables tb;
+  const double* latcost;
+  const bool staged = blockIdx.x * SMALL_WARPS < N;   // block-uniform
+  if (staged) {
+    stage_tables<0>(p, smem, tb, latcost);
+    const SmemLayout L = eval_smem_layout(0, p.OMpad, 0, p.K, p.kpad, p.P, p.W);
+    double* scr = reinterpret_cast<double*>(smem + L.total) + (size_t)wid * ((size_t)P * SMALL_ROW + 2);
+    double* ends = scr + (size_t)P * SMALL_ROW;        // s at the first / last sample
+    if (n < N) {                                       // warp-uniform
+      const int w = n / Ns, k = n - w * Ns;
+      const double* lat = tb.lat + (size_t)w * P * 4;
+      LonProfile lp;
+      lon_profile_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
+      // 1) samples: Frenet state, cost terms, position; n_pts = first sample off the reference line
+      int n_pts = P;
+      for (int base = 0; base < P; base += 32) {
+        const int i = base + lane;
+        bool off = false;
+        if (i < P) {
+          double s, sd, sdd, sddd;
+          lon_eval(lp, p.s0, p.v0, p.a0, tb.time[i], s, sd, sdd, sddd);
+          const double ea = fmax(fabs(sdd) - p.thr_lon_a, 0.0), ej = fmax(fabs(sddd) - p.thr_lon_j, 0.0), ev = (p.vmax - sd) * p.inv_vmax;
+          double* r = scr + (size_t)i * SMALL_ROW;
+          r[7] = ea * ea; r[8] = ej * ej; r[9] = ev * ev;
+          if (i == 0) ends[0] = s;
+          if (i == P - 1) ends[1] = s;
+          off = !spline_in_range(tb.sp, s);
+          if (!off) frenet_point(tb.sp, spline_walk(tb.sp, s, 0), s, lat[i * 4], r[0], r[1]);
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, off);
+        if (m != 0u && n_pts == P) n_pts = base + __ffs(m) - 1;
+      }
+      __syncwarp();
+      // 2) forward differences p_{i+1} - p_i: length and unit vector (same expressions as walk_candidate)
+      for (int base = 0; base + 1 < n_pts; base += 32) {
+        const int i = base + lane;
+        if (i + 1 < n_pts) {
+          double* r = scr + (size_t)i * SMALL_ROW;
+          const double dx = r[SMALL_ROW] - r[0], dy = r[SMALL_ROW + 1] - r[1];
+          const double q = dx * dx + dy * dy;
+          double ds, c = 1.0, sn = 0.0;
+          if (q > 1e-200 && q < 1e200) { const double inv = rsqrt(q); ds = q * inv; c = dx * inv; sn = dy * inv; }
+          else { ds = hypot(dx, dy); if (ds > 0.0) { c = dx / ds; sn = dy / ds; } }
+          r[2] = dx; r[3] = dy; r[4] = ds; r[5] = c; r[6] = sn;
+        }
+      }
+      __syncwarp();
+      // 3) curvature of every interior segment pair
+      bool fail = false;
+      for (int base = 0; base + 2 < n_pts; base += 32) {
+        const int i = base + lane + 1;                 // segment i against segment i - 1
+        if (i + 1 < n_pts) {
+          const double* a = scr + (size_t)(i - 1) * SMALL_ROW;
+          const double* b = scr + (size_t)i * SMALL_ROW;
+          fail |= curvature_fails(p.kmax, a[2], a[3], a[4], a[5], a[6], b[2], b[3], b[4], b[5], b[6]);
+        }
+      }
+      fail = __any_sync(0xffffffffu, fail);
+      // 4) collision rows, 32 obstacle states at a time
+      bool collided = false;
+      double risk = 0.0;
+      if (p.n_dict > 0) {
+        if (n_pts == 1 && p.tcap >= 1) collided = true;                 // bare except -> collision (:250-254)
+        const int lim = n_pts >= 2 ? min(n_pts, p.tcap) : 0;
+        EvalSink probe(p, tb);                                          // for narrow_hit()
+        for (int i = 0; i < lim && !collided; i += p.check_res) {
+          const int abs_step = p.now + i;
+          if (abs_step >= p.Tt) break;
+          const double* r = scr + (size_t)i * SMALL_ROW;
+          const double* h = scr + (size_t)(i == n_pts - 1 ? i - 1 : i) * SMALL_ROW;   // last point reuses the previous heading
+          const double x = r[0], y = r[1], c = h[5], sn = h[6];
+          const float fx = (float)(x - p.ox), fy = (float)(y - p.oy);
+          const float m2x = -2.0f * fx, m2y = -2.0f * fy, ne2 = -fmaf(fx, fx, fy * fy);
+          const float4* row = p.broad + (size_t)abs_step * p.OMpad;
+          for (int base = 0; base < p.OMpad; base += 32) {
+            const float4 b = __ldg(row + base + lane);
+            bool hit = fmaf(b.x, m2x, fmaf(b.y, m2y, b.z)) <= ne2;
+            if (hit) hit = probe.narrow_hit(abs_step, base + lane, b.x - fx, b.y - fy, x, y, c, sn);
+            const bool hard = hit && (double)b.w >= p.p_min;
+            if (__any_sync(0xffffffffu, hard)) { collided = true; break; }
+            unsigned int soft = __ballot_sync(0xffffffffu, hit);
+            while (soft) {                                              // risk in obstacle order, like the serial walk
+              const int j = __ffs(soft) - 1;
+              soft &= soft - 1u;
+              risk = risk + (double)__shfl_sync(0xffffffffu, b.w, j);
+            }
+          }
+        }
+      }
+      // 5) cost: lane 0 adds the per-sample terms in time order
+      if (lane == 0) {
+        double sum_a = 0, sum_j = 0, sum_v = 0;
+        for (int i = 0; i < P; ++i) {
+          const double* r = scr + (size_t)i * SMALL_ROW;
+          sum_a = sum_a + r[7]; sum_j = sum_j + r[8]; sum_v = sum_v + r[9];
+        }
+        const double cost = candidate_cost(p, sum_a, sum_j, sum_v, ends[0], ends[1], risk, latcost + w * 4);
+        if (p.feasible) p.feasible[n] = fail ? 0 : 1;
+        if (p.collision) p.collision[n] = collided ? 1 : 0;
+        if (p.cost) p.cost[n] = (float)cost;
+        if (!fail && !collided && isfinite(cost)) { my_cost = cost; my_idx = n; }
+      }
+    }
   }
-  __syncthreads();
-  if (!is_last) return;
-  // the last block to finish reduces the per-block winners: deterministic, no floating-point atomics
-  __threadfence();
-  my_cost = INFINITY; my_idx = -1;
-  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
-    const double c = __ldcg(p.blk_cost + b);
-    const int i = __ldcg(p.blk_idx + b);
-    if (lex_less(c, i, my_cost, my_idx)) { my_cost = c; my_idx = i; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double oc = __shfl_down_sync(0xffffffffu, my_cost, o);
-    const int oi = __shfl_down_sync(0xffffffffu, my_idx, o);
-    if (lex_less(oc, oi, my_cost, my_idx)) { my_cost = oc; my_idx = oi; }
-  }
-  if (lane == 0) { red_cost[wid] = my_cost; red_idx[wid] = my_idx; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int q = 1; q < EVAL_THREADS / 32; ++q)
-      if (lex_less(red_cost[q], red_idx[q], my_cost, my_idx)) { my_cost = red_cost[q]; my_idx = red_idx[q]; }
-    BestRecord r;
-    r.key = orderable_bits(my_idx >= 0 ? my_cost : INFINITY);
-    r.idx = my_idx;
-    r.cost = my_cost;
-    r.n_pts = 0;
-    r.n_candidates = N;
-    r.n_seeds = Ns;
-    r.pad = 0;
-    *p.best = r;
-    *p.ticket = 0u;   // re-arm for the next launch (stream-ordered)
-    red_idx[0] = my_idx;
-  }
-  // the same block exports the winner: no second launch, no host round trip in between
-  if (p.best_traj == nullptr) return;
-  __syncthreads();
-  const int best = red_idx[0];
-  if (best < 0) return;
-  if (!staged) stage_tables<kMode>(p, smem, tb, latcost);
-  export_block(p, tb, best, p.best_traj, &sm_npts);
+  select_and_export<0>(p, smem, tb, latcost, staged, my_cost, my_idx, N, Ns, red_cost, red_idx, &is_last, &sm_npts);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

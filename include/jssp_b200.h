@@ -93,6 +93,8 @@ typedef struct jssp_cycle_in {
 #define JSSP_FLAG_NO_SYNC 1      /* do not wait / do not fill the host fields of jssp_cycle_out */
 #define JSSP_FLAG_NO_EXPORT 2    /* skip the export of the selected trajectory */
 #define JSSP_FLAG_ENUMERATE 8    /* run jssp_enumerate_seeds(s0, v0, a0) first: one call = one whole plan cycle */
+#define JSSP_FLAG_FORCE_WARP 16  /* use the warp-per-candidate kernel (default for <= 16384 candidates) */
+#define JSSP_FLAG_FORCE_THREAD 32 /* use the thread-per-candidate kernel (default for larger cycles); same results */
 #define JSSP_FLAG_NO_CULL 4      /* test every obstacle state instead of the per-block culled lists (same results) */
 
 /* Outputs.  Candidate n = w * n_seeds + k (width-major, jssp.py:106,124-125).  All dev pointers may be NULL. */

@@ -186,3 +186,28 @@ def test_block_level_culling_changes_nothing(n_seeds, n_widths, O_, M, horizon, 
     ref = O.plan_cycle(cfg, spline, wide, H.oracle_obstacles(cyc.obstacles), 0, cyc.final_time_step, seeds=cyc.seeds, targets=cyc.targets)
     H.compare_cycle(eng.evaluate(wide, 0, cyc.final_time_step, seeds=seeds, targets=cyc.targets), ref)
     eng.close()
+
+
+@pytest.mark.parametrize("n_seeds,n_widths,O_,M,horizon,seed", [(300, 3, 6, 1, 5.0, 51), (257, 4, 40, 3, 5.0, 52), (90, 5, 70, 2, 8.0, 53), (64, 2, 0, 1, 5.0, 54)])
+def test_warp_and_thread_kernels_agree(n_seeds, n_widths, O_, M, horizon, seed):
+    """The warp-per-candidate kernel (small cycles) and the thread-per-candidate kernel give bit-identical masks, fp32
+    costs, selection and exported trajectory - and match the oracle, including truncated trajectories."""
+    cyc, cfg, spline, eng = _dense(n_seeds, n_widths, O_, M, horizon, seed, p_min=0.2, w_risk=0.9)
+    seeds = torch.from_numpy(cyc.seeds).cuda()
+    s_end = spline.s_list[-1]
+    for fr, now, final in [(cyc.frenet0, 0, cyc.final_time_step), ((s_end - 9.0, 8.0, 0.5, -0.3, 0.1, 0.0), 0, 100),
+                           ((s_end - 0.04, 3.0, 0.0, 0.1, 0.0, 0.0), 0, 100), ((4.0, 5.0, 0.0, 0.0, 0.0, 0.0), 43, 50)]:
+        out = {}
+        for kern in ("warp", "thread"):
+            r = eng.evaluate(fr, now, final, seeds=seeds, targets=cyc.targets, kernel=kern)
+            out[kern] = (r.feasible.cpu().numpy().copy(), r.collision.cpu().numpy().copy(), r.cost.cpu().numpy().copy(), r.best_idx, r.best_cost,
+                         r.best_n_pts, None if r.best_traj is None else r.best_traj.copy())
+        a, b = out["warp"], out["thread"]
+        ok = a[1] == 0
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2][ok], b[2][ok])
+        assert a[3:6] == b[3:6]
+        if a[6] is not None:
+            assert np.array_equal(a[6], b[6], equal_nan=True)
+        ref = O.plan_cycle(cfg, spline, fr, H.oracle_obstacles(cyc.obstacles), now, final, seeds=cyc.seeds, targets=cyc.targets)
+        H.compare_cycle(eng.evaluate(fr, now, final, seeds=seeds, targets=cyc.targets, kernel="warp"), ref)
+    eng.close()
