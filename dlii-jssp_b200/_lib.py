@@ -59,6 +59,28 @@ class JsspImmParams(C.Structure):
                 ("k_lat", C.c_double), ("p_stay", C.c_double), ("mu_floor", C.c_double)]
 
 
+class JsspCycleRecord(C.Structure):
+    _fields_ = [("best_idx", C.c_int32), ("n_candidates", C.c_int32), ("best_cost", C.c_double),
+                ("t", C.c_double), ("x", C.c_double), ("y", C.c_double), ("v", C.c_double), ("a", C.c_double), ("yaw", C.c_double)]
+
+
+class JsspScenarioResult(C.Structure):
+    _fields_ = [("end", C.c_double), ("cycles", C.c_int32), ("reserved0", C.c_int32)]
+
+
+class JsspScenarioIn(C.Structure):
+    _fields_ = [
+        ("knot_s", C.c_void_p), ("coef", C.c_void_p), ("K", C.c_int32), ("reserved0", C.c_int32),
+        ("state", C.c_void_p), ("valid", C.c_void_p), ("size", C.c_void_p), ("prob", C.c_void_p),
+        ("O", C.c_int32), ("M", C.c_int32), ("Tt", C.c_int32), ("n_dict", C.c_int32),
+        ("gt_state", C.c_void_p), ("gt_valid", C.c_void_p), ("gt_size", C.c_void_p), ("gt_O", C.c_int32), ("reserved1", C.c_int32),
+        ("frenet0", C.c_double * 6), ("max_t", C.c_double), ("final_time_step", C.c_int32), ("n_cycles", C.c_int32),
+        ("cycle_time", C.c_void_p), ("cycle_now", C.c_void_p), ("cycle_end_step", C.c_void_p),
+        ("goal_x", C.c_double), ("goal_y", C.c_double), ("goal_yaw", C.c_double),
+        ("ego_length", C.c_double), ("ego_width", C.c_double),
+    ]
+
+
 # every symbol include/jssp_b200.h declares (tests check that the library exports exactly these)
 SYMBOLS = {
     "jssp_abi_version": (C.c_int32, []),
@@ -82,6 +104,14 @@ SYMBOLS = {
     "jssp_imm_update": (C.c_int32, [C.c_void_p, C.POINTER(JsspImmParams)] + [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_void_p]),
     "jssp_predict_modes": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "jssp_batch_create": (C.c_int32, [C.POINTER(JsspConfigC), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "jssp_batch_destroy": (C.c_int32, [C.c_void_p]),
+    "jssp_batch_last_cuda_error": (C.c_char_p, [C.c_void_p]),
+    "jssp_batch_set_scenario": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(JsspScenarioIn), C.c_void_p]),
+    "jssp_batch_run": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "jssp_batch_fetch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "jssp_batch_best_traj": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "jssp_batch_launch_count": (C.c_int64, [C.c_void_p]),
 }
 
 _lib = None

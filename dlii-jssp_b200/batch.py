@@ -1,0 +1,267 @@
+"""Batched, device-resident replay (SURVEY.md section 8 rows f1 + f2): many independent scenarios advance in lock-step, one
+plan cycle per step, and the per-cycle hand-off of the reference driver (code/__main__.py:124-167, env.py:24-30,
+intersection_planner.py:312, controller.py:303,338-380) runs on the device, so that a replay sweep costs two kernel launches
+per step for the whole batch instead of one host round trip per scenario and cycle.
+
+``pack_scenario`` is the scenario -> tensor packer (obstacle dictionary -> dense tables, route -> spline coefficient table,
+initial Frenet state, the clock tables that carry the reference's float/str time-key semantics); ``save_packed`` /
+``load_packed`` are its on-disk cache (.npz), so a sweep parses and packs every scenario once.
+
+Results are ``replay.ReplayResult`` objects, identical to what ``replay.run_replay`` returns for the same scenario.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import JsspError, JsspCycleRecord, JsspScenarioIn, JsspScenarioResult, FLAG_FORCE_THREAD, FLAG_FORCE_WARP
+from .engine import JsspConfig
+from .frenet import FrenetState, State
+from .geometry import CubicSpline2D
+from .replay import END_RUNNING, ReplayResult, end_status, goal_pose_of
+from .scenario import ReplayScenario, pack_obstacle_dict, time_key
+
+RECORD_DTYPE = np.dtype([("best_idx", "<i4"), ("n_candidates", "<i4"), ("best_cost", "<f8"), ("t", "<f8"), ("x", "<f8"), ("y", "<f8"),
+                         ("v", "<f8"), ("a", "<f8"), ("yaw", "<f8")])
+RESULT_DTYPE = np.dtype([("end", "<f8"), ("cycles", "<i4"), ("reserved0", "<i4")])
+assert RECORD_DTYPE.itemsize == C.sizeof(JsspCycleRecord) and RESULT_DTYPE.itemsize == C.sizeof(JsspScenarioResult)
+
+
+@dataclass
+class PackedScenario:
+    """Everything the device needs to replay one scenario (all float64 / uint8 / int32 NumPy arrays)."""
+    name: str
+    knot_s: np.ndarray            # [K]
+    coef: np.ndarray              # [K-1, 8]
+    state: np.ndarray             # [O, M, Tt, 3]
+    valid: np.ndarray             # [O, M, Tt]
+    size: np.ndarray              # [O, 2]
+    prob: np.ndarray              # [O, M]
+    n_dict: int
+    frenet0: np.ndarray           # [6]
+    ego: np.ndarray               # [7] x, y, v, a, yaw, length, width
+    dt: float
+    max_t: float
+    final_time_step: int
+    cycle_time: np.ndarray        # [C+1] float64
+    cycle_now: np.ndarray         # [C+1] int32
+    cycle_end_step: np.ndarray    # [C+1] int32
+    goal_pose: np.ndarray         # [3] x, y, yaw
+    initial_end: float            # end status before the first cycle (a scenario can be over at t = 0)
+    gt_state: Optional[np.ndarray] = None     # ground truth for the end-status test when the planner sees predictions (M > 1)
+    gt_valid: Optional[np.ndarray] = None
+    gt_size: Optional[np.ndarray] = None
+
+    @property
+    def n_cycles(self) -> int:
+        return len(self.cycle_time) - 1
+
+
+def clock_tables(dt: float, n_cycles: int, n_total: int):
+    """The replay clock as the reference advances it: t <- float(t + dt) (controller.py:303); time_step_now = int(t / dt)
+    (jerk_space_sampling_planner.py:300, float truncation included); the end-status test looks the background vehicles up by
+    the key str(np.around(t, 3)) (controller.py:345) - resolved here to the step of the packed table with that key."""
+    key_to_step = {time_key(k, dt): k for k in range(n_total)}
+    times, now, end = np.zeros(n_cycles + 1), np.zeros(n_cycles + 1, dtype=np.int32), np.full(n_cycles + 1, -1, dtype=np.int32)
+    t = 0.0
+    for c in range(n_cycles + 1):
+        times[c], now[c] = t, int(t / dt)
+        end[c] = key_to_step.get(str(np.around(t, 3)), -1)
+        t = float(t + dt)
+    return times, now, end
+
+
+def pack_scenario(sc: ReplayScenario, plan_steps: int = 50, max_cycles: Optional[int] = None, predictions=None) -> PackedScenario:
+    """``predictions`` (ObstacleTensors, M >= 1) replaces the ground-truth dictionary as what the planner sees; the
+    end-status collision test always uses the dictionary."""
+    spline = CubicSpline2D(sc.route_xy[:, 0], sc.route_xy[:, 1])
+    ref = spline.sample(np.arange(0, spline.s_list[-1], 0.1))                       # generate_frenet_frame, jssp.py:366-371
+    e = sc.ego
+    fr0 = FrenetState().from_state(State(0.0, e["x"], e["y"], e["yaw"], e["v"], e["a"]), ref).as_tuple()   # intersection_planner.py:309-310
+    final = int(sc.max_t / sc.dt)                                                   # jssp.py:244
+    n_total = final + plan_steps + 2
+    gt = pack_obstacle_dict(sc.vehicle_traj, sc.dt, n_total)
+    n_cycles = final + 2 if max_cycles is None else int(max_cycles)
+    times, now, end = clock_tables(sc.dt, n_cycles, n_total)
+    obs = sc.observation()
+    gp = goal_pose_of(sc)
+    p = PackedScenario(sc.name, spline.s_list.copy(), spline.coefficient_table(), gt.state, gt.valid, gt.size, gt.prob, gt.n_dict,
+                       np.array(fr0, dtype=np.float64), np.array([e["x"], e["y"], e["v"], e["a"], e["yaw"], e["length"], e["width"]], dtype=np.float64),
+                       float(sc.dt), float(sc.max_t), final, times, now, end, np.array(gp, dtype=np.float64),
+                       float(end_status(obs, sc, gp)))
+    if predictions is not None:
+        assert predictions.state.shape[2] >= n_total, "predictions must cover final_time_step + horizon + 2 steps"
+        p.gt_state, p.gt_valid, p.gt_size = gt.state[:, 0].copy(), gt.valid[:, 0].copy(), gt.size
+        p.state, p.valid, p.size, p.prob = predictions.state[:, :, :n_total].copy(), predictions.valid[:, :, :n_total].copy(), predictions.size, predictions.prob
+        p.n_dict = predictions.n_dict
+    return p
+
+
+_ARRAY_FIELDS = ("knot_s", "coef", "state", "valid", "size", "prob", "frenet0", "ego", "cycle_time", "cycle_now", "cycle_end_step", "goal_pose",
+                 "gt_state", "gt_valid", "gt_size")
+
+
+def save_packed(path: str, packed: Sequence[PackedScenario]):
+    """On-disk cache of packed scenarios (one .npz for a whole shard)."""
+    out = {"names": np.array([p.name for p in packed]), "n": np.array(len(packed))}
+    for i, p in enumerate(packed):
+        for f in _ARRAY_FIELDS:
+            v = getattr(p, f)
+            if v is not None:
+                out[f"{i}/{f}"] = v
+        out[f"{i}/scalars"] = np.array([p.n_dict, p.dt, p.max_t, p.final_time_step, p.initial_end], dtype=np.float64)
+    np.savez_compressed(path, **out)
+
+
+def load_packed(path: str) -> List[PackedScenario]:
+    z = np.load(path)
+    res = []
+    for i, name in enumerate(z["names"]):
+        sc = z[f"{i}/scalars"]
+        kw = {f: (z[f"{i}/{f}"] if f"{i}/{f}" in z.files else None) for f in _ARRAY_FIELDS}
+        res.append(PackedScenario(name=str(name), n_dict=int(sc[0]), dt=float(sc[1]), max_t=float(sc[2]), final_time_step=int(sc[3]),
+                                  initial_end=float(sc[4]), **kw))
+    return res
+
+
+def _c(a: Optional[np.ndarray], dtype):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+class BatchReplay:
+    """Owner of a ``jssp_batch`` handle: capacity for ``max_scenarios`` slots x ``max_cycles`` plan cycles."""
+
+    def __init__(self, config: Optional[JsspConfig] = None, device: int = 0, max_scenarios: int = 64, max_cycles: int = 128):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dlii_jssp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.cfg = config or JsspConfig(max_seeds=1024, max_knots=512, max_obstacle_modes=32, max_total_steps=256)
+        self.device = torch.device("cuda", device)
+        self.S, self.C = int(max_scenarios), int(max_cycles)
+        self._h = C.c_void_p()
+        cc = self.cfg.to_c()
+        rc = self.lib.jssp_batch_create(C.byref(cc), device, self.S, self.C, C.byref(self._h))
+        if rc != 0:
+            raise JsspError(rc, "jssp_batch_create")
+        self._n = 0
+        self._packed: List[PackedScenario] = []
+
+    def _check(self, rc: int, where: str):
+        if rc != 0:
+            detail = self.lib.jssp_batch_last_cuda_error(self._h).decode() if rc == -2 else ""
+            raise JsspError(rc, where, detail)
+
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.jssp_batch_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.jssp_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load(self, packed: Sequence[PackedScenario]):
+        """Upload the scenarios into slots 0..len-1 and reset their replay state."""
+        assert 1 <= len(packed) <= self.S, (len(packed), self.S)
+        for slot, p in enumerate(packed):
+            O, M, Tt, _ = p.state.shape
+            keep = [_c(p.knot_s, np.float64), _c(p.coef, np.float64), _c(p.state, np.float64), _c(p.valid, np.uint8), _c(p.size, np.float64),
+                    _c(p.prob, np.float64), _c(p.gt_state, np.float64), _c(p.gt_valid, np.uint8), _c(p.gt_size, np.float64),
+                    _c(p.cycle_time, np.float64), _c(p.cycle_now, np.int32), _c(p.cycle_end_step, np.int32)]
+            ptr = [None if a is None else a.ctypes.data for a in keep]
+            si = JsspScenarioIn()
+            si.knot_s, si.coef, si.K = ptr[0], ptr[1], len(p.knot_s)
+            si.state, si.valid, si.size, si.prob = ptr[2], ptr[3], ptr[4], ptr[5]
+            si.O, si.M, si.Tt, si.n_dict = O, M, Tt, int(p.n_dict)
+            si.gt_state, si.gt_valid, si.gt_size = ptr[6], ptr[7], ptr[8]
+            si.gt_O = 0 if p.gt_state is None else p.gt_state.shape[0]
+            for i in range(6):
+                si.frenet0[i] = float(p.frenet0[i])
+            si.max_t, si.final_time_step, si.n_cycles = p.max_t, p.final_time_step, min(p.n_cycles, self.C)
+            si.cycle_time, si.cycle_now, si.cycle_end_step = ptr[9], ptr[10], ptr[11]
+            si.goal_x, si.goal_y, si.goal_yaw = [float(v) for v in p.goal_pose]
+            si.ego_length, si.ego_width = float(p.ego[5]), float(p.ego[6])
+            self._check(self.lib.jssp_batch_set_scenario(self._h, slot, C.byref(si), self.stream), f"jssp_batch_set_scenario[{slot}]")
+        self._n, self._packed = len(packed), list(packed)
+
+    def run(self, n_cycles: Optional[int] = None, kernel: Optional[str] = None):
+        """Enqueue ``n_cycles`` lock-step plan cycles (default: enough for every loaded scenario to finish).  Asynchronous."""
+        if n_cycles is None:
+            n_cycles = max(min(p.n_cycles, self.C) for p in self._packed)
+        flags = {None: 0, "warp": FLAG_FORCE_WARP, "thread": FLAG_FORCE_THREAD}[kernel]
+        self._check(self.lib.jssp_batch_run(self._h, self._n, int(n_cycles), flags, self.stream), "jssp_batch_run")
+        return n_cycles
+
+    def fetch(self):
+        """(results [S] structured array, records [S, C] structured array); synchronises."""
+        res = np.zeros(self._n, dtype=RESULT_DTYPE)
+        rec = np.zeros((self._n, self.C), dtype=RECORD_DTYPE)
+        self._check(self.lib.jssp_batch_fetch(self._h, self._n, res.ctypes.data, rec.ctypes.data, self.stream), "jssp_batch_fetch")
+        return res, rec
+
+    def best_traj(self, slot: int) -> np.ndarray:
+        """[P, 16] float64 rows (columns = _lib.TRAJ_COLUMNS) of the trajectory selected in the last cycle of ``slot``."""
+        out = np.zeros((self.cfg.n_points, _lib.JSSP_TRAJ_COLS), dtype=np.float64)
+        self._check(self.lib.jssp_batch_best_traj(self._h, slot, out.ctypes.data, self.stream), "jssp_batch_best_traj")
+        return out
+
+    def results(self) -> List[ReplayResult]:
+        res, rec = self.fetch()
+        out = []
+        for s, p in enumerate(self._packed):
+            n = int(res["cycles"][s])
+            r = rec[s, :n]
+            rr = ReplayResult(p.name, float(res["end"][s]), n)
+            rr.best_idx = [int(v) for v in r["best_idx"]]
+            rr.n_candidates = [int(v) for v in r["n_candidates"]]
+            ok = ~np.isnan(r["t"])
+            rr.ego_rows = [tuple(float(r[f][i]) for f in ("t", "x", "y", "v", "a", "yaw")) for i in np.nonzero(ok)[0]]
+            out.append(rr)
+        return out
+
+
+def run_batch(scenarios: Sequence, device: int = 0, max_cycles: Optional[int] = None, batch: Optional[BatchReplay] = None,
+              kernel: Optional[str] = None) -> List[ReplayResult]:
+    """Replay independent scenarios (ReplayScenario or PackedScenario) in lock-step on one GPU; same results as
+    ``replay.run_sweep``.  Scenarios that are over before the first cycle are answered on the host."""
+    packed = [s if isinstance(s, PackedScenario) else pack_scenario(s, max_cycles=max_cycles) for s in scenarios]
+    live = [i for i, p in enumerate(packed) if p.initial_end == END_RUNNING]
+    out: List[Optional[ReplayResult]] = [None if i in set(live) else ReplayResult(p.name, p.initial_end, 0) for i, p in enumerate(packed)]
+    if live:
+        todo = [packed[i] for i in live]
+        e = todo[0].ego
+        need_c = max(min(p.n_cycles, max_cycles or p.n_cycles) for p in todo)
+        if batch is None:
+            cfg = JsspConfig(ego_length=float(e[5]), ego_width=float(e[6]), max_seeds=1024,
+                             max_knots=max(64, max(len(p.knot_s) for p in todo)),
+                             max_obstacle_modes=max(1, max(p.state.shape[0] * p.state.shape[1] for p in todo)),
+                             max_total_steps=max(p.state.shape[2] for p in todo))
+            batch = BatchReplay(cfg, device=device, max_scenarios=len(todo), max_cycles=need_c)
+        t0 = time.perf_counter()
+        for lo in range(0, len(todo), batch.S):
+            chunk = todo[lo:lo + batch.S]
+            batch.load(chunk)
+            batch.run(min(need_c, batch.C), kernel=kernel)
+            for i, rr in zip(live[lo:lo + batch.S], batch.results()):
+                out[i] = rr
+        dt_s = time.perf_counter() - t0
+        cyc = sum(r.cycles for r in out if r is not None)
+        for r in out:
+            r.plan_seconds = [dt_s / max(cyc, 1)] * r.cycles        # amortised: cycles of a batch are not timed individually
+    return out

@@ -27,6 +27,7 @@ struct jssp_handle {
   double* d_seeds = nullptr;
   uint32_t *d_list_main = nullptr, *d_list_stop = nullptr;
   int* d_counts = nullptr;
+  int* d_seed_work = nullptr; // scratch counters of the fused enumeration kernel (zero between launches)
   int* h_counts = nullptr;   // pinned
   bool seeds_ready = false;
   // reference line
@@ -127,6 +128,51 @@ cudaError_t upload(T** dst, const std::vector<T>& v) {
   return e;
 }
 
+// sampling grids -> device arrays (dst order: time, j1, t1, t2, j3, t3, t4, jneg, jpos, ts) and the kernel-side view
+cudaError_t upload_grids(const jssp_config* cfg, double** dst[10], SeedGrids* sgp, int* n_time) {
+  HostGrids g = make_grids(cfg->plan_horizon, cfg->highest_jerk, cfg->num_jerk, cfg->delta_t);
+  std::vector<double> jneg, jpos;
+  for (double j : g.js) { if (!(j > 0)) jneg.push_back(j); if (!(j < 0)) jpos.push_back(j); }   // polyvt_sampling.py:275,287
+  const std::vector<double>* v[10] = {&g.time, &g.j1, &g.t1, &g.t2, &g.j3, &g.t3, &g.t4, &jneg, &jpos, &g.ts};
+  for (int k = 0; k < 10; ++k) {
+    cudaError_t e = upload(dst[k], *v[k]);
+    if (e != cudaSuccess) return e;
+  }
+  SeedGrids& sg = *sgp;
+  sg.j1 = *dst[1]; sg.t1 = *dst[2]; sg.t2 = *dst[3]; sg.j3 = *dst[4]; sg.t3 = *dst[5]; sg.t4 = *dst[6];
+  sg.n_j1 = (int)g.j1.size(); sg.n_t1 = (int)g.t1.size(); sg.n_t2 = (int)g.t2.size(); sg.n_j3 = (int)g.j3.size();
+  sg.n_t3 = (int)g.t3.size(); sg.n_t4 = (int)g.t4.size();
+  sg.jneg = *dst[7]; sg.jpos = *dst[8]; sg.ts = *dst[9];
+  sg.n_jneg = (int)jneg.size(); sg.n_jpos = (int)jpos.size(); sg.n_ts = (int)g.ts.size();
+  sg.total_time = cfg->plan_horizon;
+  sg.acc_max = cfg->lon_accel_max - 1e-9; sg.vel_max = cfg->speed_max - 1e-9; sg.v_max = cfg->speed_max;
+  sg.jmin5 = -cfg->highest_jerk * 0.3; sg.jmax5 = cfg->highest_jerk * 0.3;
+  sg.lim2 = cfg->plan_horizon - 0.8 * 3; sg.lim3 = cfg->plan_horizon - 1.0 * 2; sg.lim4 = cfg->plan_horizon - 1.5;
+  *n_time = (int)g.time.size();
+  return cudaSuccess;
+}
+
+// planner constants of a plan cycle (everything of EvalParams that does not depend on the scenario or the cycle)
+void fill_constants(EvalParams& p, const jssp_config& c, int P) {
+  p.P = P; p.check_res = c.check_res;
+  p.kmax = c.max_curvature; p.ea = c.ego_length / 2.0; p.eb = c.ego_width / 2.0; p.p_min = c.p_min; p.w_risk = c.w_risk;
+  p.vmax = c.speed_max; p.inv_vmax = 1.0 / c.speed_max; p.max_distance = c.max_distance; p.half_w = c.max_road_width / 2.0;
+  p.thr_lon_a = c.thr_lon_accel; p.thr_lon_j = c.thr_lon_jerk; p.thr_lat_a = c.thr_lat_accel; p.thr_lat_j = c.thr_lat_jerk;
+  memcpy(p.cw, c.cost_weights, sizeof(p.cw));
+}
+
+// lateral targets: linspace(-(max_road_width - w)/2, +(max_road_width - w)/2, num_width) (jerk_space_sampling_planner.py:100-104)
+std::vector<double> default_targets(const jssp_config& c, int W) {
+  if (W <= 1) return std::vector<double>(1, 0.0);
+  const double sw = c.max_road_width - c.ego_width;
+  return np_linspace(-sw / 2, sw / 2, W);
+}
+
+bool config_ok(const jssp_config* cfg) {
+  return !(cfg->plan_horizon <= 0 || cfg->delta_t <= 0 || cfg->num_jerk < 4 || cfg->num_width < 1 || cfg->num_width > JSSP_MAX_WIDTHS ||
+           cfg->check_res < 1 || cfg->max_seeds < 1 || cfg->max_knots < 2 || cfg->max_obstacle_modes < 0 || cfg->max_total_steps < 1);
+}
+
 int pack_if_dirty(jssp_handle* h, cudaStream_t st) {
   if (!h->obs_dirty) return JSSP_OK;
   const int OM = h->O * h->M;
@@ -171,6 +217,8 @@ static int32_t measure_fma(int device, double* tflops) {
   *tflops = best;
   return JSSP_OK;
 }
+
+constexpr int SEED_BLOCKS_SINGLE = 88;   // 45,075 enumeration tasks / 512 threads
 
 }  // namespace
 
@@ -231,9 +279,7 @@ void jssp_quintic_coeffs(double xs, double vxs, double axs, double xe, double vx
 int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   if (!cfg || !out) return JSSP_ERR_INVALID_ARG;
   *out = nullptr;
-  if (cfg->plan_horizon <= 0 || cfg->delta_t <= 0 || cfg->num_jerk < 4 || cfg->num_width < 1 || cfg->num_width > JSSP_MAX_WIDTHS ||
-      cfg->check_res < 1 || cfg->max_seeds < 1 || cfg->max_knots < 2 || cfg->max_obstacle_modes < 0 || cfg->max_total_steps < 1)
-    return JSSP_ERR_INVALID_ARG;
+  if (!config_ok(cfg)) return JSSP_ERR_INVALID_ARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
     cudaGetLastError();
@@ -253,29 +299,20 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(cudaSetDevice(device));
   CKC(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   h->max_smem_optin -= 1024;   // static shared memory of the kernels + slack
-  HostGrids g = make_grids(cfg->plan_horizon, cfg->highest_jerk, cfg->num_jerk, cfg->delta_t);
-  std::vector<double> jneg, jpos;
-  for (double j : g.js) { if (!(j > 0)) jneg.push_back(j); if (!(j < 0)) jpos.push_back(j); }   // polyvt_sampling.py:275,287
-  CKC(upload(&h->d_time, g.time)); CKC(upload(&h->d_j1, g.j1)); CKC(upload(&h->d_t1, g.t1)); CKC(upload(&h->d_t2, g.t2));
-  CKC(upload(&h->d_j3, g.j3)); CKC(upload(&h->d_t3, g.t3)); CKC(upload(&h->d_t4, g.t4));
-  CKC(upload(&h->d_jneg, jneg)); CKC(upload(&h->d_jpos, jpos)); CKC(upload(&h->d_ts, g.ts));
-  SeedGrids& sg = h->grids;
-  sg.j1 = h->d_j1; sg.t1 = h->d_t1; sg.t2 = h->d_t2; sg.j3 = h->d_j3; sg.t3 = h->d_t3; sg.t4 = h->d_t4;
-  sg.n_j1 = (int)g.j1.size(); sg.n_t1 = (int)g.t1.size(); sg.n_t2 = (int)g.t2.size(); sg.n_j3 = (int)g.j3.size();
-  sg.n_t3 = (int)g.t3.size(); sg.n_t4 = (int)g.t4.size();
-  sg.jneg = h->d_jneg; sg.jpos = h->d_jpos; sg.ts = h->d_ts;
-  sg.n_jneg = (int)jneg.size(); sg.n_jpos = (int)jpos.size(); sg.n_ts = (int)g.ts.size();
-  sg.total_time = cfg->plan_horizon;
-  sg.acc_max = cfg->lon_accel_max - 1e-9; sg.vel_max = cfg->speed_max - 1e-9; sg.v_max = cfg->speed_max;
-  sg.jmin5 = -cfg->highest_jerk * 0.3; sg.jmax5 = cfg->highest_jerk * 0.3;
-  sg.lim2 = cfg->plan_horizon - 0.8 * 3; sg.lim3 = cfg->plan_horizon - 1.0 * 2; sg.lim4 = cfg->plan_horizon - 1.5;
-  h->main_total = (uint32_t)((size_t)sg.n_j1 * sg.n_t1 * sg.n_t2 * sg.n_j3 * sg.n_t3 * sg.n_t4);
-  h->stop_total = (uint32_t)((size_t)sg.n_jneg * sg.n_ts * sg.n_jpos * sg.n_ts);
-  if ((int)g.time.size() != h->P) return bail(JSSP_ERR_INVALID_ARG);
+  {
+    double** slots[10] = {&h->d_time, &h->d_j1, &h->d_t1, &h->d_t2, &h->d_j3, &h->d_t3, &h->d_t4, &h->d_jneg, &h->d_jpos, &h->d_ts};
+    int n_time = 0;
+    CKC(upload_grids(cfg, slots, &h->grids, &n_time));
+    if (n_time != h->P) return bail(JSSP_ERR_INVALID_ARG);
+  }
+  h->main_total = (uint32_t)((size_t)h->grids.n_j1 * h->grids.n_t1 * h->grids.n_t2 * h->grids.n_j3 * h->grids.n_t3 * h->grids.n_t4);
+  h->stop_total = (uint32_t)((size_t)h->grids.n_jneg * h->grids.n_ts * h->grids.n_jpos * h->grids.n_ts);
 
   CKC(cudaMalloc(&h->d_seeds, (size_t)cfg->max_seeds * 10 * sizeof(double)));
   CKC(cudaMalloc(&h->d_list_main, (size_t)SORT_CAP * sizeof(uint32_t)));
   CKC(cudaMalloc(&h->d_list_stop, (size_t)SORT_CAP * sizeof(uint32_t)));
+  CKC(cudaMalloc(&h->d_seed_work, 4 * sizeof(int)));
+  CKC(cudaMemset(h->d_seed_work, 0, 4 * sizeof(int)));
   h->kpad = (cfg->max_knots + 1) & ~1;   // capacity; the per-scenario stride is set in jssp_set_refline
   CKC(cudaMalloc(&h->d_knot, (size_t)cfg->max_knots * sizeof(double)));
   CKC(cudaMalloc(&h->d_coef, (size_t)8 * h->kpad * sizeof(double)));
@@ -324,7 +361,7 @@ int32_t jssp_destroy(jssp_handle* h) {
   if (!h) return JSSP_OK;
   cudaSetDevice(h->device);
   void* dev[] = {h->d_time, h->d_j1, h->d_t1, h->d_t2, h->d_j3, h->d_t3, h->d_t4, h->d_jneg, h->d_jpos, h->d_ts, h->d_seeds,
-                 h->d_list_main, h->d_list_stop, h->d_knot, h->d_coef, h->d_raw_state, h->d_raw_valid, h->d_raw_size,
+                 h->d_list_main, h->d_list_stop, h->d_seed_work, h->d_knot, h->d_coef, h->d_raw_state, h->d_raw_valid, h->d_raw_size,
                  h->d_raw_prob, h->d_broad, h->d_narrow, h->d_obs64, h->d_ext64, h->d_sint, h->d_probf, h->d_knot_xy, h->d_blk_cost, h->d_blk_idx, h->d_ticket, h->d_result};
   for (void* p : dev) if (p) cudaFree(p);
   if (h->h_result) cudaFreeHost(h->h_result);
@@ -415,12 +452,10 @@ int32_t jssp_enumerate_seeds(jssp_handle* h, double s0, double v0, double a0, vo
   if (!h) return JSSP_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
-  CK(cudaMemsetAsync(h->d_counts, 0, 4 * sizeof(int), st));
   SeedState ss{s0, v0, a0};
-  seed_flag_main<<<(h->main_total + 255) / 256, 256, 0, st>>>(h->grids, ss, h->main_total, h->d_list_main, h->d_counts, SORT_CAP);
-  seed_flag_stop<<<(h->stop_total + 255) / 256, 256, 0, st>>>(h->grids, ss, h->stop_total, h->d_list_stop, h->d_counts, SORT_CAP);
-  seed_sort_emit<<<1, 1024, 0, st>>>(h->grids, ss, h->d_list_main, h->d_list_stop, h->d_counts, h->d_seeds, SORT_CAP, h->cfg.max_seeds);
-  h->launches += 3;
+  SeedWork wk{h->d_list_main, h->d_list_stop, h->d_seed_work, h->d_counts, h->d_seeds, SORT_CAP, h->cfg.max_seeds, 4};
+  seed_enum_kernel<false><<<dim3(SEED_BLOCKS_SINGLE, 1), SEED_THREADS, 0, st>>>(h->grids, ss, nullptr, wk);
+  h->launches += 1;
   CK(cudaGetLastError());
   h->seeds_ready = true;
   if (n_main || n_stop) {
@@ -491,15 +526,11 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   // lateral targets: linspace(-(max_road_width - w)/2, +(max_road_width - w)/2, num_width) (jerk_space_sampling_planner.py:100-104)
   std::vector<double> tg;
   if (in->n_widths > 0) tg.assign(in->targets, in->targets + W);
-  else if (W <= 1) tg.assign(1, 0.0);
-  else { const double sw = c.max_road_width - c.ego_width; tg = np_linspace(-sw / 2, sw / 2, W); }
+  else tg = default_targets(c, W);
   for (int w = 0; w < W; ++w) quintic_coeffs(in->d0, in->d_d0, in->d_dd0, tg[w], 0.0, 0.0, c.plan_horizon, p.quintic[w]);
-  p.W = W; p.P = h->P; p.now = in->time_step_now; p.tcap = in->final_time_step - in->time_step_now;
-  p.n_dict = h->n_dict; p.check_res = c.check_res;
-  p.kmax = c.max_curvature; p.ea = c.ego_length / 2.0; p.eb = c.ego_width / 2.0; p.p_min = c.p_min; p.w_risk = c.w_risk;
-  p.vmax = c.speed_max; p.inv_vmax = 1.0 / c.speed_max; p.max_distance = c.max_distance; p.half_w = c.max_road_width / 2.0;
-  p.thr_lon_a = c.thr_lon_accel; p.thr_lon_j = c.thr_lon_jerk; p.thr_lat_a = c.thr_lat_accel; p.thr_lat_j = c.thr_lat_jerk;
-  memcpy(p.cw, c.cost_weights, sizeof(p.cw));
+  fill_constants(p, c, h->P);
+  p.W = W; p.now = in->time_step_now; p.tcap = in->final_time_step - in->time_step_now;
+  p.n_dict = h->n_dict;
   p.time = h->d_time; p.knot = h->d_knot; p.coef = h->d_coef; p.K = h->K; p.kpad = h->kpad; p.ox = h->ox; p.oy = h->oy;
   p.seeds = ext ? in->seeds_dev : h->d_seeds;
   p.n_seeds_ptr = ext ? nullptr : h->d_counts;
@@ -605,6 +636,327 @@ int32_t jssp_predict_modes(jssp_handle* h, const double* lanes_dev, int32_t L, i
                                                                                O, M, Tt, state_dev, valid_dev);
   h->launches++;
   CK(cudaGetLastError());
+  return JSSP_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// Batched, device-resident replay (include/jssp_b200.h, "batched replay")
+// =====================================================================================================================
+struct jssp_batch {
+  jssp_config cfg;
+  int device = 0, P = 0, S = 0, C = 0;
+  int W = 0;
+  double* d_grid[10] = {nullptr};
+  SeedGrids grids{};
+  // strides (elements per scenario)
+  size_t n_knot = 0, n_coef = 0, n_om = 0, n_ompad = 0, n_tt = 0;
+  int blocks_thread = 0, blocks_warp = 0, max_blocks = 0;
+  // per-scenario strided device arrays
+  double *d_knot = nullptr, *d_coef = nullptr;
+  double *d_raw_state = nullptr, *d_raw_size = nullptr, *d_raw_prob = nullptr, *d_gt_state = nullptr, *d_gt_size = nullptr;
+  uint8_t *d_raw_valid = nullptr, *d_gt_valid = nullptr;
+  float4 *d_broad = nullptr, *d_narrow = nullptr;
+  double *d_obs64 = nullptr, *d_ext64 = nullptr;
+  float* d_probf = nullptr;
+  double* d_seeds = nullptr;
+  uint32_t *d_list_main = nullptr, *d_list_stop = nullptr;
+  int *d_work = nullptr, *d_counts = nullptr;
+  double* d_blk_cost = nullptr;
+  int* d_blk_idx = nullptr;
+  unsigned int* d_ticket = nullptr;
+  BestRecord* d_best = nullptr;
+  double* d_best_traj = nullptr;
+  EvalParams* d_slots = nullptr;
+  BatchSlot* d_bslots = nullptr;
+  jssp_cycle_record* d_records = nullptr;
+  double* d_cycle_time = nullptr;
+  int *d_cycle_now = nullptr, *d_cycle_end = nullptr;
+  // launch sizing: maxima over the scenarios set so far
+  int max_K = 2, max_kpad = 2, max_OMpad = 0;
+  std::vector<unsigned char> is_set;
+  int max_smem_optin = 0;
+  int64_t launches = 0;
+  char cuda_err[256] = {0};
+};
+
+namespace {
+int fail_cuda_b(jssp_batch* b, cudaError_t e, const char* what) {
+  if (b) snprintf(b->cuda_err, sizeof(b->cuda_err), "%s: %s", what, cudaGetErrorString(e));
+  return JSSP_ERR_CUDA;
+}
+#define CKB(call)                                                   \
+  do {                                                              \
+    cudaError_t e__ = (call);                                       \
+    if (e__ != cudaSuccess) return fail_cuda_b(b, e__, #call);      \
+  } while (0)
+}  // namespace
+
+extern "C" {
+
+const char* jssp_batch_last_cuda_error(const jssp_batch* b) { return b ? b->cuda_err : ""; }
+int64_t jssp_batch_launch_count(const jssp_batch* b) { return b ? b->launches : 0; }
+
+int32_t jssp_batch_destroy(jssp_batch* b) {
+  if (!b) return JSSP_OK;
+  cudaSetDevice(b->device);
+  void* dev[] = {b->d_knot, b->d_coef, b->d_raw_state, b->d_raw_size, b->d_raw_prob, b->d_gt_state, b->d_gt_size, b->d_raw_valid,
+                 b->d_gt_valid, b->d_broad, b->d_narrow, b->d_obs64, b->d_ext64, b->d_probf, b->d_seeds, b->d_list_main, b->d_list_stop,
+                 b->d_work, b->d_counts, b->d_blk_cost, b->d_blk_idx, b->d_ticket, b->d_best, b->d_best_traj, b->d_slots, b->d_bslots,
+                 b->d_records, b->d_cycle_time, b->d_cycle_now, b->d_cycle_end};
+  for (void* q : dev) if (q) cudaFree(q);
+  for (double* q : b->d_grid) if (q) cudaFree(q);
+  delete b;
+  return JSSP_OK;
+}
+
+int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_scenarios, int32_t max_cycles, jssp_batch** out) {
+  if (!cfg || !out || max_scenarios < 1 || max_scenarios > 65535 || max_cycles < 1) return JSSP_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (!config_ok(cfg)) return JSSP_ERR_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return JSSP_ERR_NO_DEVICE;
+  }
+  jssp_batch* b = new (std::nothrow) jssp_batch();
+  if (!b) return JSSP_ERR_INVALID_ARG;
+  b->cfg = *cfg; b->device = device; b->S = max_scenarios; b->C = max_cycles; b->W = cfg->num_width;
+  b->P = (int)(cfg->plan_horizon / cfg->delta_t) + 1;
+  auto bail = [&](int code) { jssp_batch_destroy(b); return code; };
+#define CKC(call)                                                                     \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) { fprintf(stderr, "jssp_batch_create: %s: %s\n", #call, cudaGetErrorString(e__)); return bail(JSSP_ERR_CUDA); } \
+  } while (0)
+  CKC(cudaSetDevice(device));
+  CKC(cudaDeviceGetAttribute(&b->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  b->max_smem_optin -= 4096;   // static shared memory of the batch kernels (parameter record, reduction scratch) + slack
+  {
+    double** slots[10];
+    for (int k = 0; k < 10; ++k) slots[k] = &b->d_grid[k];
+    int n_time = 0;
+    CKC(upload_grids(cfg, slots, &b->grids, &n_time));
+    if (n_time != b->P) return bail(JSSP_ERR_INVALID_ARG);
+  }
+  const size_t S = (size_t)b->S;
+  b->n_knot = (size_t)cfg->max_knots;
+  b->n_coef = (size_t)8 * ((cfg->max_knots + 1) & ~1);
+  b->n_om = (size_t)(cfg->max_obstacle_modes > 0 ? cfg->max_obstacle_modes : 1);
+  b->n_ompad = (b->n_om + 31) & ~(size_t)31;
+  b->n_tt = (size_t)cfg->max_total_steps;
+  b->blocks_thread = (int)(((size_t)cfg->max_seeds * b->W + EVAL_THREADS - 1) / EVAL_THREADS);
+  b->blocks_warp = (int)(((size_t)cfg->max_seeds * b->W + SMALL_WARPS - 1) / SMALL_WARPS);
+  b->max_blocks = std::max(b->blocks_thread, b->blocks_warp);
+  CKC(cudaMalloc(&b->d_knot, S * b->n_knot * sizeof(double)));
+  CKC(cudaMalloc(&b->d_coef, S * b->n_coef * sizeof(double)));
+  CKC(cudaMalloc(&b->d_raw_state, S * b->n_om * b->n_tt * 3 * sizeof(double)));
+  CKC(cudaMalloc(&b->d_raw_valid, S * b->n_om * b->n_tt));
+  CKC(cudaMalloc(&b->d_raw_size, S * b->n_om * 2 * sizeof(double)));
+  CKC(cudaMalloc(&b->d_raw_prob, S * b->n_om * sizeof(double)));
+  CKC(cudaMalloc(&b->d_gt_state, S * b->n_om * b->n_tt * 3 * sizeof(double)));
+  CKC(cudaMalloc(&b->d_gt_valid, S * b->n_om * b->n_tt));
+  CKC(cudaMalloc(&b->d_gt_size, S * b->n_om * 2 * sizeof(double)));
+  CKC(cudaMalloc(&b->d_broad, S * b->n_ompad * b->n_tt * sizeof(float4)));
+  CKC(cudaMalloc(&b->d_narrow, S * b->n_om * b->n_tt * sizeof(float4)));
+  CKC(cudaMalloc(&b->d_obs64, S * b->n_om * b->n_tt * 4 * sizeof(double)));
+  CKC(cudaMalloc(&b->d_ext64, S * b->n_om * 2 * sizeof(double)));
+  CKC(cudaMalloc(&b->d_probf, S * b->n_om * sizeof(float)));
+  CKC(cudaMalloc(&b->d_seeds, S * (size_t)cfg->max_seeds * 10 * sizeof(double)));
+  CKC(cudaMalloc(&b->d_list_main, S * SORT_CAP * sizeof(uint32_t)));
+  CKC(cudaMalloc(&b->d_list_stop, S * SORT_CAP * sizeof(uint32_t)));
+  CKC(cudaMalloc(&b->d_work, S * 4 * sizeof(int)));
+  CKC(cudaMemset(b->d_work, 0, S * 4 * sizeof(int)));
+  CKC(cudaMalloc(&b->d_counts, S * 4 * sizeof(int)));
+  CKC(cudaMemset(b->d_counts, 0, S * 4 * sizeof(int)));
+  CKC(cudaMalloc(&b->d_blk_cost, S * b->max_blocks * sizeof(double)));
+  CKC(cudaMalloc(&b->d_blk_idx, S * b->max_blocks * sizeof(int)));
+  CKC(cudaMalloc(&b->d_ticket, S * sizeof(unsigned int)));
+  CKC(cudaMemset(b->d_ticket, 0, S * sizeof(unsigned int)));
+  CKC(cudaMalloc(&b->d_best, S * sizeof(BestRecord)));
+  CKC(cudaMemset(b->d_best, 0, S * sizeof(BestRecord)));
+  CKC(cudaMalloc(&b->d_best_traj, S * (size_t)b->P * JSSP_TRAJ_COLS * sizeof(double)));
+  CKC(cudaMalloc(&b->d_slots, S * sizeof(EvalParams)));
+  CKC(cudaMemset(b->d_slots, 0, S * sizeof(EvalParams)));
+  CKC(cudaMalloc(&b->d_bslots, S * sizeof(BatchSlot)));
+  CKC(cudaMemset(b->d_bslots, 0, S * sizeof(BatchSlot)));
+  CKC(cudaMalloc(&b->d_records, S * (size_t)b->C * sizeof(jssp_cycle_record)));
+  CKC(cudaMalloc(&b->d_cycle_time, S * (size_t)(b->C + 1) * sizeof(double)));
+  CKC(cudaMalloc(&b->d_cycle_now, S * (size_t)(b->C + 1) * sizeof(int)));
+  CKC(cudaMalloc(&b->d_cycle_end, S * (size_t)(b->C + 1) * sizeof(int)));
+  b->is_set.assign(S, 0);
+  CKC(cudaFuncSetAttribute(evaluate_batch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->max_smem_optin));
+  CKC(cudaFuncSetAttribute(evaluate_batch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->max_smem_optin));
+  CKC(cudaFuncSetAttribute(evaluate_small_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->max_smem_optin));
+  CKC(cudaDeviceSynchronize());
+#undef CKC
+  *out = b;
+  return JSSP_OK;
+}
+
+int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario_in* in, void* stream) {
+  if (!b || !in || slot < 0 || slot >= b->S) return JSSP_ERR_INVALID_ARG;
+  if (!in->knot_s || !in->coef || in->K < 2 || in->O < 0 || in->M < 1 || in->Tt < 1 || !in->cycle_time || !in->cycle_now || !in->cycle_end_step ||
+      in->n_cycles < 1)
+    return JSSP_ERR_INVALID_ARG;
+  if (in->O > 0 && (!in->state || !in->valid || !in->size || !in->prob)) return JSSP_ERR_INVALID_ARG;
+  if (in->gt_state && (!in->gt_valid || !in->gt_size || in->gt_O < 0)) return JSSP_ERR_INVALID_ARG;
+  if (!in->gt_state && in->M != 1 && in->O > 0) return JSSP_ERR_INVALID_ARG;   // the ground truth must be given for multi-modal predictions
+  const int OM = in->O * in->M;
+  const int gtO = in->gt_state ? in->gt_O : in->O;
+  if (in->K > b->cfg.max_knots || OM > b->cfg.max_obstacle_modes || gtO > b->cfg.max_obstacle_modes || in->Tt > b->cfg.max_total_steps ||
+      in->n_cycles > b->C)
+    return JSSP_ERR_CAPACITY;
+  for (int i = 1; i < in->K; ++i) if (!(in->knot_s[i] > in->knot_s[i - 1])) return JSSP_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  CKB(cudaSetDevice(b->device));
+  const size_t s = (size_t)slot;
+  const double ego_l = in->ego_length > 0 ? in->ego_length : b->cfg.ego_length, ego_w = in->ego_width > 0 ? in->ego_width : b->cfg.ego_width;
+  const int K = in->K, kpad = (K + 1) & ~1, Tt = in->Tt, OMpad = (OM + 31) & ~31;
+  double* knot = b->d_knot + s * b->n_knot;
+  double* coef = b->d_coef + s * b->n_coef;
+  std::vector<double> soa((size_t)8 * kpad, 0.0);
+  for (int i = 0; i < K - 1; ++i)
+    for (int c = 0; c < 8; ++c) soa[(size_t)c * kpad + i] = in->coef[(size_t)i * 8 + c];
+  CKB(cudaMemcpyAsync(knot, in->knot_s, (size_t)K * sizeof(double), cudaMemcpyHostToDevice, st));
+  CKB(cudaMemcpyAsync(coef, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  const double ox = in->coef[0], oy = in->coef[4];
+  double* raw_state = b->d_raw_state + s * b->n_om * b->n_tt * 3;
+  uint8_t* raw_valid = b->d_raw_valid + s * b->n_om * b->n_tt;
+  double* raw_size = b->d_raw_size + s * b->n_om * 2;
+  double* raw_prob = b->d_raw_prob + s * b->n_om;
+  float4* broad = b->d_broad + s * b->n_ompad * b->n_tt;
+  float4* narrow = b->d_narrow + s * b->n_om * b->n_tt;
+  double* obs64 = b->d_obs64 + s * b->n_om * b->n_tt * 4;
+  double* ext64 = b->d_ext64 + s * b->n_om * 2;
+  float* probf = b->d_probf + s * b->n_om;
+  if (OM > 0) {
+    CKB(cudaMemcpyAsync(raw_state, in->state, (size_t)OM * Tt * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CKB(cudaMemcpyAsync(raw_valid, in->valid, (size_t)OM * Tt, cudaMemcpyHostToDevice, st));
+    CKB(cudaMemcpyAsync(raw_size, in->size, (size_t)in->O * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CKB(cudaMemcpyAsync(raw_prob, in->prob, (size_t)OM * sizeof(double), cudaMemcpyHostToDevice, st));
+    const double r_ego = std::sqrt(ego_l * ego_l + ego_w * ego_w) / 2.0;
+    const int total = OMpad * Tt;
+    pack_obstacles_kernel<<<(total + 255) / 256, 256, 0, st>>>(raw_state, raw_valid, raw_size, raw_prob, OM, OMpad, in->M, Tt, ox, oy,
+                                                               b->cfg.obstacle_inflation, r_ego, broad, narrow, obs64, ext64, probf, nullptr,
+                                                               nullptr, nullptr, 0, 0.0, 0.0);
+    b->launches++;
+    CKB(cudaGetLastError());
+  }
+  const double *gt_state = raw_state, *gt_size = raw_size;
+  const uint8_t* gt_valid = raw_valid;
+  if (in->gt_state) {
+    double* gs = b->d_gt_state + s * b->n_om * b->n_tt * 3;
+    uint8_t* gv = b->d_gt_valid + s * b->n_om * b->n_tt;
+    double* gz = b->d_gt_size + s * b->n_om * 2;
+    if (gtO > 0) {
+      CKB(cudaMemcpyAsync(gs, in->gt_state, (size_t)gtO * Tt * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+      CKB(cudaMemcpyAsync(gv, in->gt_valid, (size_t)gtO * Tt, cudaMemcpyHostToDevice, st));
+      CKB(cudaMemcpyAsync(gz, in->gt_size, (size_t)gtO * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    gt_state = gs; gt_valid = gv; gt_size = gz;
+  }
+  const size_t nc = (size_t)in->n_cycles + 1;
+  double* ctime = b->d_cycle_time + s * (b->C + 1);
+  int* cnow = b->d_cycle_now + s * (b->C + 1);
+  int* cend = b->d_cycle_end + s * (b->C + 1);
+  CKB(cudaMemcpyAsync(ctime, in->cycle_time, nc * sizeof(double), cudaMemcpyHostToDevice, st));
+  CKB(cudaMemcpyAsync(cnow, in->cycle_now, nc * sizeof(int), cudaMemcpyHostToDevice, st));
+  CKB(cudaMemcpyAsync(cend, in->cycle_end_step, nc * sizeof(int), cudaMemcpyHostToDevice, st));
+
+  jssp_config c = b->cfg;
+  c.ego_length = ego_l; c.ego_width = ego_w;
+  EvalParams p{};
+  fill_constants(p, c, b->P);
+  p.s0 = in->frenet0[0]; p.v0 = in->frenet0[1]; p.a0 = in->frenet0[2];
+  const std::vector<double> tg = default_targets(c, b->W);
+  for (int w = 0; w < b->W; ++w) quintic_coeffs(in->frenet0[3], in->frenet0[4], in->frenet0[5], tg[w], 0.0, 0.0, c.plan_horizon, p.quintic[w]);
+  p.W = b->W; p.now = in->cycle_now[0]; p.tcap = in->final_time_step - p.now; p.n_dict = in->n_dict;
+  p.time = b->d_grid[0]; p.knot = knot; p.coef = coef; p.K = K; p.kpad = kpad; p.ox = ox; p.oy = oy;
+  p.seeds = b->d_seeds + s * (size_t)c.max_seeds * 10;
+  p.n_seeds_ptr = b->d_counts + s * 4; p.n_seeds_fixed = 0; p.seed_cap = c.max_seeds;
+  p.broad = broad; p.narrow = narrow; p.obs64 = obs64; p.ext64 = ext64;
+  p.OM = OM; p.OMpad = OMpad; p.Tt = Tt;
+  int rows = 0;
+  if (p.tcap > 0) rows = (std::min(p.P, p.tcap) + c.check_res - 1) / c.check_res;
+  p.win_rows = OM > 0 ? rows : 0;
+  p.smem_obs = 1; p.sint = nullptr; p.probf = probf; p.list_cap = 0;
+  p.feasible = nullptr; p.collision = nullptr; p.cost = nullptr;
+  p.blk_cost = b->d_blk_cost + s * b->max_blocks; p.blk_idx = b->d_blk_idx + s * b->max_blocks;
+  p.ticket = b->d_ticket + s; p.best = b->d_best + s;
+  p.best_traj = b->d_best_traj + s * (size_t)b->P * JSSP_TRAJ_COLS;
+  p.batch = b->d_bslots + s; p.self = b->d_slots + s;
+  BatchSlot q{};
+  q.live = 1; q.cycle = 0; q.n_cycles_cap = in->n_cycles; q.final_step = in->final_time_step;
+  q.gt_O = gtO; q.gt_Tt = Tt;
+  q.end = -1.0; q.max_t = in->max_t; q.horizon = c.plan_horizon;
+  q.goal_x = in->goal_x; q.goal_y = in->goal_y; q.goal_cos = std::cos(in->goal_yaw); q.goal_sin = std::sin(in->goal_yaw);
+  q.ego_l = c.ego_length; q.ego_w = c.ego_width;
+  for (int w = 0; w < b->W; ++w) q.targets[w] = tg[w];
+  q.cycle_time = ctime; q.cycle_now = cnow; q.cycle_end_step = cend;
+  q.gt_state = gt_state; q.gt_valid = gt_valid; q.gt_size = gt_size;
+  q.records = b->d_records + s * (size_t)b->C;
+  CKB(cudaMemcpyAsync(b->d_slots + s, &p, sizeof(p), cudaMemcpyHostToDevice, st));
+  CKB(cudaMemcpyAsync(b->d_bslots + s, &q, sizeof(q), cudaMemcpyHostToDevice, st));
+  CKB(cudaMemsetAsync(b->d_ticket + s, 0, sizeof(unsigned int), st));
+  CKB(cudaMemsetAsync(b->d_work + s * 4, 0, 4 * sizeof(int), st));
+  CKB(cudaStreamSynchronize(st));   // soa, p, q are temporaries; the caller's arrays may be released
+  b->max_K = std::max(b->max_K, K); b->max_kpad = std::max(b->max_kpad, kpad); b->max_OMpad = std::max(b->max_OMpad, OMpad);
+  b->is_set[s] = 1;
+  return JSSP_OK;
+}
+
+int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int32_t flags, void* stream) {
+  if (!b || n_scenarios < 1 || n_scenarios > b->S || n_cycles < 0) return JSSP_ERR_INVALID_ARG;
+  for (int s = 0; s < n_scenarios; ++s) if (!b->is_set[s]) return JSSP_ERR_NOT_READY;
+  cudaStream_t st = (cudaStream_t)stream;
+  CKB(cudaSetDevice(b->device));
+  const int max_rows = (b->P + b->cfg.check_res - 1) / b->cfg.check_res;
+  // the evaluation kernel: one warp per candidate while the whole batch is small (latency), one thread per candidate otherwise
+  const SmemLayout Ls = eval_smem_layout(0, b->max_OMpad, 0, b->max_K, b->max_kpad, b->P, b->W);
+  const size_t small_bytes = Ls.total + small_scratch_bytes(b->P);
+  bool small = (long long)n_scenarios * b->cfg.max_seeds * b->W <= 65536 && small_bytes <= (size_t)b->max_smem_optin;
+  if (flags & JSSP_FLAG_FORCE_THREAD) small = false;
+  if ((flags & JSSP_FLAG_FORCE_WARP) && small_bytes <= (size_t)b->max_smem_optin) small = true;
+  int mode = b->max_OMpad > 0 ? 1 : 0;
+  SmemLayout L = eval_smem_layout(max_rows, b->max_OMpad, mode, b->max_K, b->max_kpad, b->P, b->W);
+  if (mode == 1 && L.total > (size_t)b->max_smem_optin) { mode = 0; L = eval_smem_layout(0, b->max_OMpad, 0, b->max_K, b->max_kpad, b->P, b->W); }
+  if (!small && L.total > (size_t)b->max_smem_optin) return JSSP_ERR_CAPACITY;
+  const int seed_blocks = std::max(1, std::min(SEED_BLOCKS_SINGLE, 592 / n_scenarios));
+  SeedWork wk{b->d_list_main, b->d_list_stop, b->d_work, b->d_counts, b->d_seeds, SORT_CAP, b->cfg.max_seeds, 4};
+  for (int c = 0; c < n_cycles; ++c) {
+    seed_enum_kernel<true><<<dim3(seed_blocks, n_scenarios), SEED_THREADS, 0, st>>>(b->grids, SeedState{0, 0, 0}, b->d_slots, wk);
+    if (small) evaluate_small_batch_kernel<<<dim3(b->blocks_warp, n_scenarios), SMALL_WARPS * 32, small_bytes, st>>>(b->d_slots);
+    else if (mode == 1) evaluate_batch_kernel<1><<<dim3(b->blocks_thread, n_scenarios), EVAL_THREADS, L.total, st>>>(b->d_slots);
+    else evaluate_batch_kernel<0><<<dim3(b->blocks_thread, n_scenarios), EVAL_THREADS, L.total, st>>>(b->d_slots);
+    b->launches += 2;
+  }
+  CKB(cudaGetLastError());
+  return JSSP_OK;
+}
+
+int32_t jssp_batch_fetch(jssp_batch* b, int32_t n_scenarios, jssp_scenario_result* results_host, jssp_cycle_record* records_host,
+                         void* stream) {
+  if (!b || !results_host || n_scenarios < 1 || n_scenarios > b->S) return JSSP_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  CKB(cudaSetDevice(b->device));
+  std::vector<BatchSlot> q((size_t)n_scenarios);
+  CKB(cudaMemcpyAsync(q.data(), b->d_bslots, q.size() * sizeof(BatchSlot), cudaMemcpyDeviceToHost, st));
+  if (records_host)
+    CKB(cudaMemcpyAsync(records_host, b->d_records, (size_t)n_scenarios * b->C * sizeof(jssp_cycle_record), cudaMemcpyDeviceToHost, st));
+  CKB(cudaStreamSynchronize(st));
+  for (int s = 0; s < n_scenarios; ++s) { results_host[s].end = q[s].end; results_host[s].cycles = q[s].cycle; results_host[s].reserved0 = 0; }
+  return JSSP_OK;
+}
+
+int32_t jssp_batch_best_traj(jssp_batch* b, int32_t slot, double* out, void* stream) {
+  if (!b || !out || slot < 0 || slot >= b->S) return JSSP_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  CKB(cudaSetDevice(b->device));
+  CKB(cudaMemcpyAsync(out, b->d_best_traj + (size_t)slot * b->P * JSSP_TRAJ_COLS, (size_t)b->P * JSSP_TRAJ_COLS * sizeof(double),
+                      cudaMemcpyDefault, st));
+  CKB(cudaStreamSynchronize(st));
   return JSSP_OK;
 }
 

@@ -117,15 +117,49 @@ __device__ __forceinline__ void decode_main(const SeedGrids& g, uint32_t f, doub
   j1 = g.j1[r]; t1 = g.t1[i1]; t2 = g.t2[i2]; j3 = g.j3[ij3]; t3 = g.t3[i3]; t4 = g.t4[i4];
 }
 
-__global__ void seed_flag_main(SeedGrids g, SeedState st, uint32_t total, uint32_t* __restrict__ list, int* __restrict__ counts,
-                               int cap) {
-  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= total) return;
-  double j1, t1, t2, j3, t3, t4, j5, t5;
-  decode_main(g, f, j1, t1, t2, j3, t3, t4);
-  if (main_seed_ok(g, st, j1, t1, t2, j3, t3, t4, j5, t5)) {
-    const int pos = atomicAdd(&counts[0], 1);
-    if (pos < cap) list[pos] = f; else counts[3] = 1;
+// decode helpers of the hierarchical enumeration: a MAIN task fixes (j1, t1, t2, j3) and loops t3 x t4, a STOP task fixes
+// (j1, t1, j2) and loops t2; the flat index of a survivor is the same as the reference's nested-loop position.
+__device__ __forceinline__ void main_task(const SeedGrids& g, const SeedState& st, uint32_t f4, uint32_t* __restrict__ list,
+                                          int* __restrict__ found, int* __restrict__ overflow, int cap) {
+  uint32_t r = f4;
+  const uint32_t ij3 = r % g.n_j3; r /= g.n_j3;
+  const uint32_t i2 = r % g.n_t2; r /= g.n_t2;
+  const uint32_t i1 = r % g.n_t1; r /= g.n_t1;
+  const double j1 = g.j1[r], t1 = g.t1[i1], t2 = g.t2[i2], j3 = g.j3[ij3];
+  const double T = g.total_time;
+  // the predicate chain of main_seed_ok, hoisted level by level (same expressions, same operand order)
+  if (t1 < 0.55) return;
+  const double s1 = st_by_jt(st.s0, st.v0, st.a0, j1, t1), v1 = vt_by_jt(st.v0, st.a0, j1, t1), a1 = at_by_jt(st.a0, j1, t1);
+  if (!check_state(s1, v1, a1, st.s0, g.acc_max, g.vel_max)) return;
+  if (t1 + t2 >= g.lim2) return;
+  const double s2 = st_by_jt(s1, v1, a1, 0.0, t2), v2 = vt_by_jt(v1, a1, 0.0, t2), a2 = at_by_jt(a1, 0.0, t2);
+  if (!check_state(s2, v2, a2, s1, g.acc_max, g.vel_max)) return;
+  if (t1 + t2 > T + 1e-9) return;
+  if (j3 * j1 > 0) return;
+  for (int i3 = 0; i3 < g.n_t3; ++i3) {
+    const double t3 = g.t3[i3];
+    if (t1 + t2 + t3 > g.lim3) continue;
+    const double s3 = st_by_jt(s2, v2, a2, j3, t3), v3 = vt_by_jt(v2, a2, j3, t3), a3 = at_by_jt(a2, j3, t3);
+    if (!check_state(s3, v3, a3, s2, g.acc_max, g.vel_max)) continue;
+    if (a3 * a1 > 0) continue;
+    if (a3 * a2 < 0) {
+      const double t25 = (0.0 - a2) / j3;
+      const double v25 = vt_by_jt(v2, a2, j3, t25);
+      if (v25 > g.v_max || v25 < 0.0 + 1e-9) continue;
+    }
+    for (int i4 = 0; i4 < g.n_t4; ++i4) {
+      const double t4 = g.t4[i4];
+      if (t1 + t2 + t3 + t4 > g.lim4) continue;
+      const double s4 = st_by_jt(s3, v3, a3, 0.0, t4), v4 = vt_by_jt(v3, a3, 0.0, t4), a4 = at_by_jt(a3, 0.0, t4);
+      if (!check_state(s4, v4, a4, s3, g.acc_max, g.vel_max)) continue;
+      const double t5 = T - t1 - t2 - t3 - t4;
+      const double j5 = (0.0 - a4) / t5;
+      if (j5 > g.jmax5 || j5 < g.jmin5) continue;
+      const double s5 = st_by_jt(s4, v4, a4, j5, t5), v5 = vt_by_jt(v4, a4, j5, t5), a5 = at_by_jt(a4, j5, t5);
+      if (!check_state(s5, v5, a5, s4, g.acc_max, g.vel_max)) continue;
+      const int pos = atomicAdd(found, 1);
+      if (pos < cap) list[pos] = (f4 * g.n_t3 + i3) * g.n_t4 + i4; else *overflow = 1;
+    }
   }
 }
 
@@ -137,23 +171,26 @@ __device__ __forceinline__ void decode_stop(const SeedGrids& g, uint32_t f, doub
   j1 = g.jneg[r]; t1 = g.ts[i1]; j2 = g.jpos[ij2]; t2 = g.ts[i2];
 }
 
-__global__ void seed_flag_stop(SeedGrids g, SeedState st, uint32_t total, uint32_t* __restrict__ list, int* __restrict__ counts,
-                               int cap) {
-  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= total) return;
-  double j1, t1, j2, t2;
-  decode_stop(g, f, j1, t1, j2, t2);
+__device__ __forceinline__ void stop_task(const SeedGrids& g, const SeedState& st, uint32_t f3, uint32_t* __restrict__ list,
+                                          int* __restrict__ found, int* __restrict__ overflow, int cap) {
+  uint32_t r = f3;
+  const uint32_t ij2 = r % g.n_jpos; r /= g.n_jpos;
+  const uint32_t i1 = r % g.n_ts; r /= g.n_ts;
+  const double j1 = g.jneg[r], t1 = g.ts[i1], j2 = g.jpos[ij2];
   const double s1 = st_by_jt(st.s0, st.v0, st.a0, j1, t1), v1 = vt_by_jt(st.v0, st.a0, j1, t1), a1 = at_by_jt(st.a0, j1, t1);
   if (!check_state(s1, v1, a1, st.s0, g.acc_max, g.vel_max)) return;                     // :283
-  if (t1 + t2 >= g.total_time) return;                                                   // :291
-  const double a2 = at_by_jt(a1, j2, t2);
-  if (a2 > 0.0 || a2 < -0.3) return;                                                     // :293
-  const double v2 = vt_by_jt(v1, a1, j2, t2);
-  if (v2 > 0.0 || v2 < -0.3) return;                                                     // :296
-  const double s2 = st_by_jt(s1, v1, a1, j2, t2);
-  if (s2 < s1 - 0.1) return;                                                             // :299
-  const int pos = atomicAdd(&counts[1], 1);
-  if (pos < cap) list[pos] = f; else counts[3] = 1;
+  for (int i2 = 0; i2 < g.n_ts; ++i2) {
+    const double t2 = g.ts[i2];
+    if (t1 + t2 >= g.total_time) continue;                                               // :291
+    const double a2 = at_by_jt(a1, j2, t2);
+    if (a2 > 0.0 || a2 < -0.3) continue;                                                 // :293
+    const double v2 = vt_by_jt(v1, a1, j2, t2);
+    if (v2 > 0.0 || v2 < -0.3) continue;                                                 // :296
+    const double s2 = st_by_jt(s1, v1, a1, j2, t2);
+    if (s2 < s1 - 0.1) continue;                                                         // :299
+    const int pos = atomicAdd(found, 1);
+    if (pos < cap) list[pos] = f3 * g.n_ts + i2; else *overflow = 1;
+  }
 }
 
 // bitonic sort of n <= SORT_CAP keys held in shared memory (padding = 0xffffffff)
@@ -174,24 +211,69 @@ __device__ void bitonic_sort_smem(uint32_t* key, int npow2) {
   }
 }
 
-// counts: [0] main found, [1] stop found, [2] total emitted, [3] overflow flag
-__global__ void __launch_bounds__(1024) seed_sort_emit(SeedGrids g, SeedState st, const uint32_t* __restrict__ list_main,
-                                                       const uint32_t* __restrict__ list_stop, int* __restrict__ counts,
-                                                       double* __restrict__ seeds, int cap_list, int cap_seeds) {
+// Per-scenario workspace of the enumeration (arrays are strided by the scenario index blockIdx.y).
+//   work   [S][4]  scratch counters: 0 main found, 1 stop found, 2 block ticket, 3 overflow; zero between launches
+//   counts [S][4]  results: 0 main found, 1 stop found, 2 seeds emitted, 3 overflow flag
+struct SeedWork {
+  uint32_t* list_main;
+  uint32_t* list_stop;
+  int* work;
+  int* counts;
+  double* seeds;            // [S][cap_seeds][10]
+  int cap_list, cap_seeds;
+  size_t counts_stride;     // ints between the count records of consecutive scenarios
+};
+
+struct EvalParams;
+__device__ __forceinline__ SeedState seed_state_of(const EvalParams* slots, int sc);
+__device__ __forceinline__ bool slot_live(const EvalParams* slots, int sc);
+
+// One launch per plan cycle (and per batch of scenarios): every block takes a strided share of the MAIN and STOP tasks,
+// survivors append their flat grid index, and the last block of a scenario to finish (ticket) sorts the (few hundred)
+// indices so that the emitted order is the reference's nested-loop order, decodes them into seeds and re-arms the counters.
+constexpr int SEED_THREADS = 512;
+template <bool kBatch>
+__global__ void __launch_bounds__(SEED_THREADS) seed_enum_kernel(SeedGrids g, SeedState st1, const EvalParams* __restrict__ slots,
+                                                                 SeedWork wk) {
   __shared__ uint32_t key[SORT_CAP];
-  const int n_main = min(counts[0], cap_list), n_stop = min(counts[1], cap_list);
+  __shared__ bool is_last;
+  const int sc = blockIdx.y;
+  if (kBatch && !slot_live(slots, sc)) return;
+  const SeedState st = kBatch ? seed_state_of(slots, sc) : st1;
+  uint32_t* list_main = wk.list_main + (size_t)sc * wk.cap_list;
+  uint32_t* list_stop = wk.list_stop + (size_t)sc * wk.cap_list;
+  int* work = wk.work + (size_t)sc * 4;
+  int* counts = wk.counts + (size_t)sc * wk.counts_stride;
+  double* seeds = wk.seeds + (size_t)sc * wk.cap_seeds * 10;
+  const uint32_t n_main = (uint32_t)g.n_j1 * g.n_t1 * g.n_t2 * g.n_j3;
+  const uint32_t n_stop = (uint32_t)g.n_jneg * g.n_ts * g.n_jpos;
+  for (uint32_t task = blockIdx.x * blockDim.x + threadIdx.x; task < n_main + n_stop; task += gridDim.x * blockDim.x) {
+    if (task < n_main) main_task(g, st, task, list_main, &work[0], &work[3], wk.cap_list);
+    else stop_task(g, st, task - n_main, list_stop, &work[1], &work[3], wk.cap_list);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = atomicAdd(&work[2], 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int found_main = __ldcg(&work[0]), found_stop = __ldcg(&work[1]);
+  int overflow = __ldcg(&work[3]);
+  const int n_m = min(found_main, wk.cap_list), n_s = min(found_stop, wk.cap_list);
   int emitted = 0;
   for (int pass = 0; pass < 2; ++pass) {
-    const int n = pass == 0 ? n_main : n_stop;
+    const int n = pass == 0 ? n_m : n_s;
     const uint32_t* list = pass == 0 ? list_main : list_stop;
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
-    for (int i = threadIdx.x; i < np2; i += blockDim.x) key[i] = i < n ? list[i] : 0xffffffffu;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) key[i] = i < n ? __ldcg(list + i) : 0xffffffffu;
     __syncthreads();
     bitonic_sort_smem(key, np2);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const int row = emitted + i;
-      if (row >= cap_seeds) continue;
+      if (row >= wk.cap_seeds) continue;
       double* o = seeds + (size_t)row * 10;
       if (pass == 0) {
         double j1, t1, t2, j3, t3, t4, j5 = 0, t5 = 0;
@@ -209,8 +291,9 @@ __global__ void __launch_bounds__(1024) seed_sort_emit(SeedGrids g, SeedState st
     emitted += n;
   }
   if (threadIdx.x == 0) {
-    if (emitted > cap_seeds) { counts[3] = 1; emitted = cap_seeds; }
-    counts[2] = emitted;
+    if (emitted > wk.cap_seeds) { overflow = 1; emitted = wk.cap_seeds; }
+    counts[0] = found_main; counts[1] = found_stop; counts[2] = emitted; counts[3] = overflow;
+    work[0] = 0; work[1] = 0; work[2] = 0; work[3] = 0;      // re-arm for the next launch (stream-ordered)
   }
 }
 
@@ -233,7 +316,7 @@ __global__ void pack_obstacles_kernel(const double* __restrict__ state, const ui
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // idx = t * OMpad + om
   if (idx >= OMpad * Tt) return;
   const int t = idx / OMpad, om = idx - t * OMpad;
-  sint[idx] = make_float2(FAR_AWAY, -FAR_AWAY);            // empty arc-length interval
+  if (sint) sint[idx] = make_float2(FAR_AWAY, -FAR_AWAY);  // empty arc-length interval (NULL: no block-level culling tables)
   if (om >= OM) { broad[idx] = make_float4(0.f, 0.f, FAR_AWAY, 0.f); return; }
   const int o = om / M;
   const double a2 = (size[2 * o] + inflation) / 2.0, b2 = (size[2 * o + 1] + inflation) / 2.0;
@@ -254,7 +337,7 @@ __global__ void pack_obstacles_kernel(const double* __restrict__ state, const ui
   // Arc-length interval of the reference line from which this obstacle state can be reached by any candidate footprint:
   // every curve point within (lateral cap + R) of the obstacle lies within cull_reach of one of its segment's knots
   // (cull_reach includes the longest knot-to-knot arc), so the hull of those knots widened by cull_ds is conservative.
-  if (ok && K > 0) {
+  if (sint && ok && K > 0) {
     const double reach = cull_reach + (double)r;
     const double r2 = reach * reach;
     double lo = 1e300, hi = -1e300;
@@ -305,7 +388,37 @@ struct EvalParams {
   unsigned int* ticket;
   BestRecord* best;
   double* best_traj;              // [P][16] export of the selected trajectory (NULL = skip)
+  // batched replay (NULL / unused for a single plan cycle)
+  struct BatchSlot* batch;        // per-scenario replay state, updated by the hand-off at the end of every cycle
+  EvalParams* self;               // this scenario's parameter record in device memory (the hand-off writes the next cycle's inputs)
 };
+
+// Replay state of one scenario of a batch (device memory).  The hand-off at the end of a plan cycle - the last block of
+// the evaluation kernel - moves the ego to sample 1 of the selected trajectory (code/onsite_trans/env.py:24-30), makes
+// that sample the next cycle's Frenet start (intersection_planner.py:312), advances the clock (controller.py:303) and
+// evaluates the end-of-scenario status (controller.py:338-380), so that a whole replay runs without host round trips.
+struct BatchSlot {
+  int live;                       // 1 while the scenario is running
+  int cycle;                      // plan cycles done
+  int final_step;                 // int(max_t / dt)
+  int gt_O, gt_Tt;                // ground-truth background vehicles and steps of their table
+  int n_cycles_cap;               // the per-cycle tables hold n_cycles_cap + 1 entries: the replay pauses after that many cycles
+  double end;                     // end status: -1 running, 1 max_t, 1.5 goal, 2 collision, -2 no solution, -3 short trajectory
+  double max_t, horizon;
+  double goal_x, goal_y, goal_cos, goal_sin;
+  double ego_l, ego_w;
+  double targets[JSSP_MAX_WIDTHS];
+  const double* cycle_time;       // [C+1] clock at the start of cycle c (host-accumulated float additions)
+  const int* cycle_now;           // [C+1] int(t / dt)
+  const int* cycle_end_step;      // [C+1] table step whose key equals str(around(t, 3)), -1 = none
+  const double* gt_state;         // [gt_O][gt_Tt][3] x, y, yaw of the background vehicles
+  const uint8_t* gt_valid;        // [gt_O][gt_Tt]
+  const double* gt_size;          // [gt_O][2] length, width
+  jssp_cycle_record* records;     // [C]
+};
+
+__device__ __forceinline__ SeedState seed_state_of(const EvalParams* slots, int sc) { return SeedState{slots[sc].s0, slots[sc].v0, slots[sc].a0}; }
+__device__ __forceinline__ bool slot_live(const EvalParams* slots, int sc) { return slots[sc].batch->live != 0; }
 
 struct BlockTables {
   const float4* broad;   // window rows [win_rows][OMpad] (shared) or the global table [Tt][OMpad]
@@ -724,6 +837,69 @@ __device__ __forceinline__ void export_block(const EvalParams& p, const BlockTab
   if (i == 0) p.best->n_pts = np;
 }
 
+// Closed-set overlap of two centred rectangles, float64 (ReplayController._collision_detect, controller.py:382-415).
+__device__ __forceinline__ bool rect_overlap_f64(double x1, double y1, double yaw1, double l1, double w1, double x2, double y2,
+                                                 double yaw2, double l2, double w2) {
+  double s1, c1, s2, c2;
+  sincos(yaw1, &s1, &c1);
+  sincos(yaw2, &s2, &c2);
+  return sat_intersects_f64(x2 - x1, y2 - y1, c1, s1, l1 / 2.0, w1 / 2.0, c2, s2, l2 / 2.0, w2 / 2.0);
+}
+
+// Batched replay: end-of-cycle hand-off of one scenario, run by the block that exported the selected trajectory.
+__device__ __forceinline__ void batch_handoff(const EvalParams& p, int best, int N, int* sm_flag) {
+  BatchSlot* b = p.batch;
+  __syncthreads();                                   // the exported rows (global) are visible to the whole block
+  if (threadIdx.x == 0) *sm_flag = 0;
+  __syncthreads();
+  const int c = b->cycle;
+  const int np = best >= 0 ? p.best->n_pts : 0;
+  const bool ok = best >= 0 && np >= 2;              // "No solution" / env.py:26 needs best_traj.x[1]
+  const double* row1 = p.best_traj + JSSP_TRAJ_COLS;
+  double tn = 0.0, x = 0.0, y = 0.0, yaw = 0.0;
+  if (ok) {
+    tn = b->cycle_time[c + 1];                       // t + dt (controller.py:303)
+    x = row1[9]; y = row1[10]; yaw = row1[11];
+    const int k = b->cycle_end_step[c + 1];
+    if (tn > 0.5 && k >= 0 && k < b->gt_Tt) {        // collision with a background vehicle (controller.py:343-349)
+      for (int o = threadIdx.x; o < b->gt_O; o += blockDim.x) {
+        if (!b->gt_valid[(size_t)o * b->gt_Tt + k]) continue;
+        const double* st = b->gt_state + ((size_t)o * b->gt_Tt + k) * 3;
+        if (rect_overlap_f64(x, y, yaw, b->ego_l, b->ego_w, st[0], st[1], st[2], b->gt_size[2 * o], b->gt_size[2 * o + 1])) atomicOr(sm_flag, 1);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  jssp_cycle_record* rec = b->records + c;
+  rec->best_idx = best; rec->n_candidates = N; rec->best_cost = best >= 0 ? p.best->cost : nan("");
+  if (!ok) {
+    rec->t = rec->x = rec->y = rec->v = rec->a = rec->yaw = nan("");
+    b->end = best < 0 ? -2.0 : -3.0;
+    b->live = 0;
+  } else {
+    rec->t = tn; rec->x = x; rec->y = y; rec->v = row1[2]; rec->a = row1[3]; rec->yaw = yaw;
+    double status = -1.0;
+    if (*sm_flag) status = 2.0;
+    if (tn >= b->max_t) status = fmax(status, 1.0);                                          // controller.py:352-353
+    const double dx = x - b->goal_x, dy = y - b->goal_y;
+    if (b->goal_sin * dy + b->goal_cos * dx >= 0.0) status = fmax(status, 1.5);               // goal line passed
+    b->end = status;
+    if (status != -1.0) b->live = 0;
+    // next cycle starts from sample 1 of the selected trajectory (intersection_planner.py:312)
+    EvalParams* q = p.self;
+    q->s0 = row1[1]; q->v0 = row1[2]; q->a0 = row1[3];
+    for (int w = 0; w < p.W; ++w) quintic_coeffs(row1[5], row1[6], row1[7], b->targets[w], 0.0, 0.0, b->horizon, q->quintic[w]);
+    const int now = b->cycle_now[c + 1];
+    q->now = now; q->tcap = b->final_step - now;
+    int rows = 0;
+    if (q->tcap > 0) rows = (min(p.P, q->tcap) + p.check_res - 1) / p.check_res;
+    q->win_rows = p.OM > 0 ? rows : 0;
+  }
+  b->cycle = c + 1;
+  if (c + 1 >= b->n_cycles_cap) b->live = 0;         // table end: stays "running" (end = -1) like a max_cycles stop
+}
+
 // Selection shared by both evaluation kernels: block argmin of (cost, index) by warp shuffles, one record per block,
 // and the last block to finish (ticket counter) reduces the per-block winners - deterministic, lexicographic, no
 // floating-point atomics - and exports the winning trajectory in the same launch.
@@ -788,19 +964,17 @@ __device__ __forceinline__ void select_and_export(const EvalParams& p, unsigned 
   if (p.best_traj == nullptr) return;
   __syncthreads();
   const int best = red_idx[0];
-  if (best < 0) return;
-  if (!staged) stage_tables<kMode>(p, smem, tb, latcost);
-  export_block(p, tb, best, p.best_traj, sm_npts_p);
+  if (best >= 0) {
+    if (!staged) stage_tables<kMode>(p, smem, tb, latcost);
+    export_block(p, tb, best, p.best_traj, sm_npts_p);
+  }
+  if (p.batch) batch_handoff(p, best, N, sm_npts_p);
 }
 
 
 template <int kMode>
-__global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_kernel(const __grid_constant__ EvalParams p) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ double red_cost[EVAL_THREADS / 32];
-  __shared__ int red_idx[EVAL_THREADS / 32];
-  __shared__ bool is_last;
-  __shared__ int sm_npts;
+__device__ __forceinline__ void evaluate_body(const EvalParams& p, unsigned char* smem, double* red_cost, int* red_idx, bool* is_last,
+                                              int* sm_npts) {
   const int Ns = resolve_n_seeds(p);
   const int N = Ns * p.W;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -827,7 +1001,39 @@ __global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_kernel
       if (!sink.curv_fail && !sink.collided && isfinite(cost)) { my_cost = cost; my_idx = n; }
     }
   }
-  select_and_export<kMode>(p, smem, tb, latcost, staged, my_cost, my_idx, N, Ns, red_cost, red_idx, &is_last, &sm_npts);
+  select_and_export<kMode>(p, smem, tb, latcost, staged, my_cost, my_idx, N, Ns, red_cost, red_idx, is_last, sm_npts);
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_kernel(const __grid_constant__ EvalParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ double red_cost[EVAL_THREADS / 32];
+  __shared__ int red_idx[EVAL_THREADS / 32];
+  __shared__ bool is_last;
+  __shared__ int sm_npts;
+  evaluate_body<kMode>(p, smem, red_cost, red_idx, &is_last, &sm_npts);
+}
+
+// Batched replay: blockIdx.y = scenario; the scenario's parameter record is copied into shared memory once per block.
+__device__ __forceinline__ void load_slot(EvalParams* dst, const EvalParams* src) {
+  static_assert(sizeof(EvalParams) % 8 == 0, "EvalParams is copied as 8-byte words");
+  const unsigned long long* s = reinterpret_cast<const unsigned long long*>(src);
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(dst);
+  for (int i = threadIdx.x; i < (int)(sizeof(EvalParams) / 8); i += blockDim.x) d[i] = s[i];
+  __syncthreads();
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_batch_kernel(const EvalParams* __restrict__ slots) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(16) EvalParams sp;
+  __shared__ double red_cost[EVAL_THREADS / 32];
+  __shared__ int red_idx[EVAL_THREADS / 32];
+  __shared__ bool is_last;
+  __shared__ int sm_npts;
+  if (!slot_live(slots, blockIdx.y)) return;           // block-uniform; stable until the scenario's last block hands off
+  load_slot(&sp, slots + blockIdx.y);
+  evaluate_body<kMode>(sp, smem, red_cost, red_idx, &is_last, &sm_npts);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -841,12 +1047,8 @@ constexpr int SMALL_WARPS = 8;                 // candidates per block
 constexpr int SMALL_ROW = 10;                  // doubles per sample in the warp scratch: x, y | dx, dy, ds, c, sn | ea2, ej2, ev2
 __host__ __device__ inline size_t small_scratch_bytes(int P) { return (size_t)SMALL_WARPS * ((size_t)P * SMALL_ROW + 2) * 8; }
 
-__global__ void __launch_bounds__(SMALL_WARPS * 32) evaluate_small_kernel(const __grid_constant__ EvalParams p) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ double red_cost[SMALL_WARPS];
-  __shared__ int red_idx[SMALL_WARPS];
-  __shared__ bool is_last;
-  __shared__ int sm_npts;
+__device__ __forceinline__ void evaluate_small_body(const EvalParams& p, unsigned char* smem, double* red_cost, int* red_idx,
+                                                    bool* is_last_p, int* sm_npts_p) {
   const int Ns = resolve_n_seeds(p);
   const int N = Ns * p.W;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -958,7 +1160,28 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) evaluate_small_kernel(const 
       }
     }
   }
-  select_and_export<0>(p, smem, tb, latcost, staged, my_cost, my_idx, N, Ns, red_cost, red_idx, &is_last, &sm_npts);
+  select_and_export<0>(p, smem, tb, latcost, staged, my_cost, my_idx, N, Ns, red_cost, red_idx, is_last_p, sm_npts_p);
+}
+
+__global__ void __launch_bounds__(SMALL_WARPS * 32) evaluate_small_kernel(const __grid_constant__ EvalParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ double red_cost[SMALL_WARPS];
+  __shared__ int red_idx[SMALL_WARPS];
+  __shared__ bool is_last;
+  __shared__ int sm_npts;
+  evaluate_small_body(p, smem, red_cost, red_idx, &is_last, &sm_npts);
+}
+
+__global__ void __launch_bounds__(SMALL_WARPS * 32) evaluate_small_batch_kernel(const EvalParams* __restrict__ slots) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(16) EvalParams sp;
+  __shared__ double red_cost[SMALL_WARPS];
+  __shared__ int red_idx[SMALL_WARPS];
+  __shared__ bool is_last;
+  __shared__ int sm_npts;
+  if (!slot_live(slots, blockIdx.y)) return;
+  load_slot(&sp, slots + blockIdx.y);
+  evaluate_small_body(sp, smem, red_cost, red_idx, &is_last, &sm_npts);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -190,6 +190,68 @@ int32_t jssp_predict_modes(jssp_handle* h, const double* lanes_dev, int32_t L, i
                            const double* s_start_dev, const double* speed_dev, double dt, int32_t O, int32_t M,
                            int32_t Tt, double* state_dev, uint8_t* valid_dev, void* stream);
 
+/* -- batched, device-resident replay ------------------------------------------------
+ * Replaces the per-scenario driver loop of code/__main__.py:124-167 for MANY independent scenarios at once: in every
+ * step all running scenarios execute one plan cycle (seed enumeration -> evaluation -> selection -> export) and the
+ * device itself performs the hand-off the reference does on the host - ego := sample 1 of best_traj
+ * (code/onsite_trans/env.py:24-30), next Frenet start := best_traj.frenet_state_at_time_step(1)
+ * (intersection_planner.py:312), t += dt (controller.py:303), end status (controller.py:338-380: collision with a
+ * background vehicle for t > 0.5, t >= max_t, goal line passed; no map-bounds test) - so that a whole replay of S
+ * scenarios costs 2 kernel launches per step and one result copy at the end.  Scenarios share one jssp_config
+ * (sampling grids, limits, cost weights; the ego footprint may differ per scenario); capacities per scenario come from cfg.max_seeds / max_knots / max_obstacle_modes / max_total_steps. */
+typedef struct jssp_batch jssp_batch;
+
+typedef struct jssp_cycle_record {  /* one plan cycle of one scenario = one row of the reference's recorder */
+  int32_t best_idx;                 /* selected candidate, -1 = "No solution" */
+  int32_t n_candidates;
+  double best_cost;
+  double t, x, y, v, a, yaw;        /* ego after the cycle (NaN when the cycle ended the replay without a move) */
+} jssp_cycle_record;
+
+typedef struct jssp_scenario_result {
+  double end;                       /* -1 still running, 1 max_t, 1.5 goal, 2 collision, -2 no solution, -3 short trajectory */
+  int32_t cycles;                   /* plan cycles executed */
+  int32_t reserved0;
+} jssp_scenario_result;
+
+typedef struct jssp_scenario_in {
+  /* reference line, as jssp_set_refline */
+  const double* knot_s; const double* coef; int32_t K; int32_t reserved0;
+  /* obstacles the planner sees, as jssp_set_obstacles (host pointers) */
+  const double* state; const uint8_t* valid; const double* size; const double* prob;
+  int32_t O, M, Tt, n_dict;
+  /* ground-truth background vehicles for the end-status collision test: state [gt_O][Tt][3], valid [gt_O][Tt],
+   * size [gt_O][2]; NULL -> mode 0 of the planner's table (the replay case M = 1) */
+  const double* gt_state; const uint8_t* gt_valid; const double* gt_size; int32_t gt_O; int32_t reserved1;
+  /* initial Frenet state (s, s_d, s_dd, d, d_d, d_dd) of cycle 0 (FrenetState.from_state, intersection_planner.py:309-310) */
+  double frenet0[6];
+  double max_t;                     /* test_setting["max_t"] */
+  int32_t final_time_step;          /* int(max_t / dt), jssp.py:244 */
+  int32_t n_cycles;                 /* entries - 1 of the three per-cycle tables below */
+  /* host-computed clock tables, index c = plan cycles done: cycle_time[c] = t after c float additions of dt,
+   * cycle_now[c] = int(t / dt) (jssp.py:300), cycle_end_step[c] = table step whose key equals str(around(t, 3))
+   * (controller.py:345) or -1 */
+  const double* cycle_time; const int32_t* cycle_now; const int32_t* cycle_end_step;
+  double goal_x, goal_y, goal_yaw;  /* goal pose: passed when sin(yaw)*dy + cos(yaw)*dx >= 0 */
+  double ego_length, ego_width;     /* this scenario's ego footprint (observation["vehicle_info"]["ego"]); 0 -> jssp_config's */
+} jssp_scenario_in;
+
+int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_scenarios, int32_t max_cycles, jssp_batch** out);
+int32_t jssp_batch_destroy(jssp_batch* b);
+const char* jssp_batch_last_cuda_error(const jssp_batch* b);
+/* upload one scenario into `slot` and reset its replay state (synchronises the stream: host arrays may be freed) */
+int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario_in* in, void* stream);
+/* enqueue `n_cycles` lock-step plan cycles for slots [0, n_scenarios) (finished scenarios idle); flags:
+ * JSSP_FLAG_FORCE_WARP / JSSP_FLAG_FORCE_THREAD select the evaluation kernel, default by batch size.  Asynchronous. */
+int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int32_t flags, void* stream);
+/* copy results back (synchronises): results_host[n_scenarios], records_host[n_scenarios][max_cycles] (may be NULL) */
+int32_t jssp_batch_fetch(jssp_batch* b, int32_t n_scenarios, jssp_scenario_result* results_host,
+                         jssp_cycle_record* records_host, void* stream);
+/* copy the trajectory selected in the last cycle of `slot` ([n_steps+1][16] float64, columns as jssp_cycle_out.best_traj)
+ * into `out`, a host or device buffer (unified addressing decides); synchronises */
+int32_t jssp_batch_best_traj(jssp_batch* b, int32_t slot, double* out, void* stream);
+int64_t jssp_batch_launch_count(const jssp_batch* b);
+
 #ifdef __cplusplus
 }
 #endif

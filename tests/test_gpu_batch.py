@@ -1,0 +1,79 @@
+"""GPU tests of the batched, device-resident replay (jssp_batch_*): every scenario of a batch must reproduce, cycle by cycle,
+what the one-scenario-at-a-time replay through the reference-shaped planner interface produces (and hence the oracle's
+replay), with the hand-off, the clock and the end-of-scenario status evaluated on the device."""
+import numpy as np
+import pytest
+
+import dlii_jssp_b200 as J
+from dlii_jssp_b200 import batch as B, replay as R, scenario as S
+from oracle import replay_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(a, b, exact=True):
+    assert a.best_idx == b.best_idx, (a.name, a.best_idx[:12], b.best_idx[:12])
+    assert a.n_candidates == b.n_candidates
+    assert a.end == b.end and a.cycles == b.cycles, (a.name, a.end, b.end, a.cycles, b.cycles)
+    if exact:
+        assert a.ego_rows == b.ego_rows
+    elif b.ego_rows:
+        np.testing.assert_allclose(np.array(a.ego_rows), np.array(b.ego_rows), rtol=1e-9, atol=1e-9)
+
+
+def test_batch_matches_single_scenario_replays(scenario_fixture):
+    """Bundled scenario + synthetic left / straight / right intersections in ONE batch, full length."""
+    scs = [scenario_fixture] + [S.synthetic_intersection(i) for i in (0, 1, 2, 7)]
+    got = B.run_batch(scs)
+    for sc, g in zip(scs, got):
+        _same(g, R.run_replay(sc))
+    assert any(g.end in (1, 1.5, 2) for g in got)           # at least one scenario ran to a real end status
+
+
+@pytest.mark.parametrize("kernel", ["warp", "thread"])
+def test_batch_kernels_agree_with_oracle_replay(kernel):
+    scs = [S.synthetic_intersection(i) for i in (3, 4)]
+    got = B.run_batch(scs, max_cycles=20, kernel=kernel)
+    for sc, g in zip(scs, got):
+        p = B.pack_scenario(sc)
+        cpu = replay_oracle.replay(sc, tuple(p.frenet0), S.pack_obstacle_dict, R.end_status, R.goal_pose_of(sc), max_cycles=20)
+        assert g.best_idx == cpu["best_idx"] and g.n_candidates == cpu["n"] and g.end == cpu["end"]
+        np.testing.assert_allclose(np.array(g.ego_rows), np.array(cpu["rows"]), rtol=1e-9, atol=1e-9)
+
+
+def test_batch_larger_than_capacity_is_chunked_and_perturbed_scenes(scenario_fixture):
+    """BASELINE config 2 shape: the bundled scene + seeded variants, replayed through a 3-slot batch."""
+    scs = [S.perturbed_scenario(scenario_fixture, s) for s in range(5)]
+    cfg = J.JsspConfig(ego_length=scenario_fixture.ego["length"], ego_width=scenario_fixture.ego["width"], max_seeds=1024, max_knots=256,
+                       max_obstacle_modes=8, max_total_steps=256)
+    bt = B.BatchReplay(cfg, max_scenarios=3, max_cycles=16)
+    got = B.run_batch(scs, max_cycles=16, batch=bt)
+    for sc, g in zip(scs, got):
+        _same(g, R.run_replay(sc, max_cycles=16))
+    assert bt.launch_count >= 2 * 16 * 2
+    tr = bt.best_traj(0)
+    assert tr.shape == (51, 16) and np.isfinite(tr[:, :9]).all()
+    bt.close()
+
+
+def test_batch_resume_continues_where_it_stopped():
+    """run(k) twice == run(2k): the replay state lives on the device between calls."""
+    sc = S.synthetic_intersection(5)
+    p = B.pack_scenario(sc, max_cycles=12)
+    cfg = J.JsspConfig(max_seeds=1024, max_knots=512, max_obstacle_modes=16, max_total_steps=256)
+    bt = B.BatchReplay(cfg, max_scenarios=1, max_cycles=12)
+    bt.load([p]); bt.run(12)
+    whole = bt.results()[0]
+    bt.load([p]); bt.run(5); bt.run(7)
+    _same(bt.results()[0], whole)
+    bt.close()
+
+
+def test_batch_scenario_without_obstacles_and_finished_scenario():
+    sc = S.synthetic_intersection(6)
+    empty = S.ReplayScenario("empty", dict(sc.ego), {}, sc.goal, sc.dt, sc.max_t, sc.route_xy)
+    done = S.ReplayScenario("done", dict(sc.ego), sc.vehicle_traj, sc.goal, sc.dt, 0.0, sc.route_xy)     # t >= max_t before the first cycle
+    got = B.run_batch([empty, done, sc], max_cycles=10)
+    _same(got[0], R.run_replay(empty, max_cycles=10))
+    assert got[1].cycles == 0 and got[1].end == 1
+    _same(got[2], R.run_replay(sc, max_cycles=10))

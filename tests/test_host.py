@@ -141,3 +141,36 @@ def test_synthetic_generators_are_seeded_and_valid():
     d = S.tensors_to_dict(t, sc.dt)
     t2 = S.pack_obstacle_dict(d, sc.dt, 130)
     assert np.array_equal(t.valid, t2.valid) and np.allclose(t.state, t2.state)
+
+
+def test_clock_tables_follow_the_reference_clock(scenario_fixture):
+    """The batched replay's per-cycle tables against the reference's own expressions evaluated step by step."""
+    from dlii_jssp_b200 import batch as B
+    dt, n_total = 0.1, 180
+    times, now, end = B.clock_tables(dt, 120, n_total)
+    t = 0.0
+    for c in range(121):
+        assert times[c] == t and now[c] == int(t / dt)
+        key = str(np.around(t, 3))
+        assert (end[c] == -1 and key not in {S.time_key(k, dt) for k in range(n_total)}) or S.time_key(int(end[c]), dt) == key
+        t = float(t + dt)
+    assert now[8] == 7 and end[8] == 8          # 0.7999999999999999 / 0.1 truncates to 7, but its 3-dp key is "0.8"
+
+
+def test_packed_scenario_cache_round_trip(tmp_path, scenario_fixture):
+    from dlii_jssp_b200 import batch as B
+    packed = [B.pack_scenario(scenario_fixture), B.pack_scenario(S.synthetic_intersection(2), max_cycles=30)]
+    B.save_packed(str(tmp_path / "shard.npz"), packed)
+    back = B.load_packed(str(tmp_path / "shard.npz"))
+    assert [p.name for p in back] == [p.name for p in packed]
+    for a, b in zip(packed, back):
+        for f in B._ARRAY_FIELDS:
+            va, vb = getattr(a, f), getattr(b, f)
+            assert (va is None and vb is None) or (va.dtype == vb.dtype and np.array_equal(va, vb)), f
+        assert (a.n_dict, a.dt, a.max_t, a.final_time_step, a.initial_end) == (b.n_dict, b.dt, b.max_t, b.final_time_step, b.initial_end)
+    # the packed obstacle table holds exactly the dictionary's states
+    p = packed[0]
+    tr = scenario_fixture.vehicle_traj
+    for o, vid in enumerate(tr):
+        keys = [k for k in tr[vid] if k != "shape"]
+        assert int(p.valid[o, 0].sum()) == len([k for k in keys if round(float(k) / p.dt) < p.state.shape[2]])
