@@ -200,6 +200,10 @@ class BatchReplay:
             self._check(self.lib.jssp_batch_set_scenario(self._h, slot, C.byref(si), self.stream), f"jssp_batch_set_scenario[{slot}]")
         self._n, self._packed = len(packed), list(packed)
 
+    def reset(self):
+        """Back to the freshly loaded state without uploading anything (device-to-device)."""
+        self._check(self.lib.jssp_batch_reset(self._h, self._n, self.stream), "jssp_batch_reset")
+
     def run(self, n_cycles: Optional[int] = None, kernel: Optional[str] = None):
         """Enqueue ``n_cycles`` lock-step plan cycles (default: enough for every loaded scenario to finish).  Asynchronous."""
         if n_cycles is None:

@@ -668,8 +668,8 @@ struct jssp_batch {
   unsigned int* d_ticket = nullptr;
   BestRecord* d_best = nullptr;
   double* d_best_traj = nullptr;
-  EvalParams* d_slots = nullptr;
-  BatchSlot* d_bslots = nullptr;
+  EvalParams *d_slots = nullptr, *d_slots0 = nullptr;    // live records and their pristine copies (jssp_batch_reset)
+  BatchSlot *d_bslots = nullptr, *d_bslots0 = nullptr;
   jssp_cycle_record* d_records = nullptr;
   double* d_cycle_time = nullptr;
   int *d_cycle_now = nullptr, *d_cycle_end = nullptr;
@@ -704,7 +704,7 @@ int32_t jssp_batch_destroy(jssp_batch* b) {
   void* dev[] = {b->d_knot, b->d_coef, b->d_raw_state, b->d_raw_size, b->d_raw_prob, b->d_gt_state, b->d_gt_size, b->d_raw_valid,
                  b->d_gt_valid, b->d_broad, b->d_narrow, b->d_obs64, b->d_ext64, b->d_probf, b->d_seeds, b->d_list_main, b->d_list_stop,
                  b->d_work, b->d_counts, b->d_blk_cost, b->d_blk_idx, b->d_ticket, b->d_best, b->d_best_traj, b->d_slots, b->d_bslots,
-                 b->d_records, b->d_cycle_time, b->d_cycle_now, b->d_cycle_end};
+                 b->d_slots0, b->d_bslots0, b->d_records, b->d_cycle_time, b->d_cycle_now, b->d_cycle_end};
   for (void* q : dev) if (q) cudaFree(q);
   for (double* q : b->d_grid) if (q) cudaFree(q);
   delete b;
@@ -781,6 +781,8 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   CKC(cudaMemset(b->d_slots, 0, S * sizeof(EvalParams)));
   CKC(cudaMalloc(&b->d_bslots, S * sizeof(BatchSlot)));
   CKC(cudaMemset(b->d_bslots, 0, S * sizeof(BatchSlot)));
+  CKC(cudaMalloc(&b->d_slots0, S * sizeof(EvalParams)));
+  CKC(cudaMalloc(&b->d_bslots0, S * sizeof(BatchSlot)));
   CKC(cudaMalloc(&b->d_records, S * (size_t)b->C * sizeof(jssp_cycle_record)));
   CKC(cudaMalloc(&b->d_cycle_time, S * (size_t)(b->C + 1) * sizeof(double)));
   CKC(cudaMalloc(&b->d_cycle_now, S * (size_t)(b->C + 1) * sizeof(int)));
@@ -899,11 +901,26 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
   q.records = b->d_records + s * (size_t)b->C;
   CKB(cudaMemcpyAsync(b->d_slots + s, &p, sizeof(p), cudaMemcpyHostToDevice, st));
   CKB(cudaMemcpyAsync(b->d_bslots + s, &q, sizeof(q), cudaMemcpyHostToDevice, st));
+  CKB(cudaMemcpyAsync(b->d_slots0 + s, &p, sizeof(p), cudaMemcpyHostToDevice, st));
+  CKB(cudaMemcpyAsync(b->d_bslots0 + s, &q, sizeof(q), cudaMemcpyHostToDevice, st));
   CKB(cudaMemsetAsync(b->d_ticket + s, 0, sizeof(unsigned int), st));
   CKB(cudaMemsetAsync(b->d_work + s * 4, 0, 4 * sizeof(int), st));
   CKB(cudaStreamSynchronize(st));   // soa, p, q are temporaries; the caller's arrays may be released
   b->max_K = std::max(b->max_K, K); b->max_kpad = std::max(b->max_kpad, kpad); b->max_OMpad = std::max(b->max_OMpad, OMpad);
   b->is_set[s] = 1;
+  return JSSP_OK;
+}
+
+int32_t jssp_batch_reset(jssp_batch* b, int32_t n_scenarios, void* stream) {
+  if (!b || n_scenarios < 1 || n_scenarios > b->S) return JSSP_ERR_INVALID_ARG;
+  for (int s = 0; s < n_scenarios; ++s) if (!b->is_set[s]) return JSSP_ERR_NOT_READY;
+  cudaStream_t st = (cudaStream_t)stream;
+  CKB(cudaSetDevice(b->device));
+  const size_t n = (size_t)n_scenarios;
+  CKB(cudaMemcpyAsync(b->d_slots, b->d_slots0, n * sizeof(EvalParams), cudaMemcpyDeviceToDevice, st));
+  CKB(cudaMemcpyAsync(b->d_bslots, b->d_bslots0, n * sizeof(BatchSlot), cudaMemcpyDeviceToDevice, st));
+  CKB(cudaMemsetAsync(b->d_ticket, 0, n * sizeof(unsigned int), st));
+  CKB(cudaMemsetAsync(b->d_work, 0, n * 4 * sizeof(int), st));
   return JSSP_OK;
 }
 

@@ -179,7 +179,16 @@ __device__ __forceinline__ void stop_task(const SeedGrids& g, const SeedState& s
   const double j1 = g.jneg[r], t1 = g.ts[i1], j2 = g.jpos[ij2];
   const double s1 = st_by_jt(st.s0, st.v0, st.a0, j1, t1), v1 = vt_by_jt(st.v0, st.a0, j1, t1), a1 = at_by_jt(st.a0, j1, t1);
   if (!check_state(s1, v1, a1, st.s0, g.acc_max, g.vel_max)) return;                     // :283
-  for (int i2 = 0; i2 < g.n_ts; ++i2) {
+  // a2 = a1 + j2*t2 is monotone in t2, so only a short run of the (uniform, np.arange) t2 grid can pass -0.3 <= a2 <= 0:
+  // bracket it in closed form with a two-sample margin; the exact predicates below decide inside the bracket.
+  int lo = 0, hi = g.n_ts - 1;
+  if (j2 > 1e-9 && g.n_ts >= 2) {
+    const double inv_dt = 1.0 / (g.ts[1] - g.ts[0]);
+    const double flo = ((-0.3 - a1) / j2 - g.ts[0]) * inv_dt, fhi = ((0.0 - a1) / j2 - g.ts[0]) * inv_dt;
+    lo = (int)fmax(0.0, fmin(floor(flo) - 2.0, (double)g.n_ts));
+    hi = (int)fmin((double)(g.n_ts - 1), fmax(ceil(fhi) + 2.0, -1.0));
+  }
+  for (int i2 = lo; i2 <= hi; ++i2) {
     const double t2 = g.ts[i2];
     if (t1 + t2 >= g.total_time) continue;                                               // :291
     const double a2 = at_by_jt(a1, j2, t2);

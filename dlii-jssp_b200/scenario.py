@@ -349,3 +349,37 @@ def perturbed_scenario(base: ReplayScenario, seed: int) -> ReplayScenario:
         traj[vid] = entry
     ego = dict(base.ego); ego["v"] = float(rng.uniform(2.0, 10.0))
     return ReplayScenario(f"{base.name}_v{seed}", ego, traj, base.goal, base.dt, base.max_t, base.route_xy)
+
+
+def multimodal_predictions(sc: ReplayScenario, M: int = 3, seed: int = 0, plan_steps: int = 50) -> ObstacleTensors:
+    """Builder-specified stand-in for the DLII predictor's output (the reference publishes no predictor code, SURVEY.md
+    section 0.3): per background vehicle M intention hypotheses over the whole scenario - mode 0 is the recorded trajectory
+    (lane keeping), mode m > 0 is the recorded trajectory bent about its first state by a constant yaw rate of
+    +-0.12 rad/s * ceil(m / 2) (turn hypotheses) - with intention probabilities p0 ~ U(0.5, 0.8) for mode 0 and a
+    Dirichlet split of the rest.  Covers final_time_step + plan_steps + 2 steps like the planner's own packing."""
+    final = int(sc.max_t / sc.dt)
+    n_total = final + plan_steps + 2
+    gt = pack_obstacle_dict(sc.vehicle_traj, sc.dt, n_total)
+    O = gt.state.shape[0]
+    state = np.repeat(gt.state, M, axis=1)
+    valid = np.repeat(gt.valid, M, axis=1)
+    rng = np.random.default_rng(9000 + seed)
+    prob = np.zeros((O, M))
+    for o in range(O):
+        p0 = rng.uniform(0.5, 0.8) if M > 1 else 1.0
+        prob[o, 0] = p0
+        if M > 1:
+            prob[o, 1:] = rng.dirichlet(np.ones(M - 1)) * (1.0 - p0)
+        ks = np.nonzero(gt.valid[o, 0])[0]
+        if len(ks) == 0:
+            continue
+        k0 = ks[0]
+        x0, y0 = gt.state[o, 0, k0, :2]
+        for m in range(1, M):
+            omega = (0.12 if m % 2 else -0.12) * ((m + 1) // 2)
+            ang = omega * (ks - k0) * sc.dt
+            dx, dy = gt.state[o, 0, ks, 0] - x0, gt.state[o, 0, ks, 1] - y0
+            state[o, m, ks, 0] = x0 + np.cos(ang) * dx - np.sin(ang) * dy
+            state[o, m, ks, 1] = y0 + np.sin(ang) * dx + np.cos(ang) * dy
+            state[o, m, ks, 2] = (gt.state[o, 0, ks, 2] + ang + np.pi) % (2 * np.pi) - np.pi
+    return ObstacleTensors(state, valid, gt.size, prob, gt.n_dict, gt.ids)

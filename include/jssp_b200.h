@@ -241,6 +241,9 @@ int32_t jssp_batch_destroy(jssp_batch* b);
 const char* jssp_batch_last_cuda_error(const jssp_batch* b);
 /* upload one scenario into `slot` and reset its replay state (synchronises the stream: host arrays may be freed) */
 int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario_in* in, void* stream);
+/* put slots [0, n_scenarios) back to the state jssp_batch_set_scenario left them in (device-to-device; asynchronous):
+ * a sweep can be repeated without uploading the scenarios again */
+int32_t jssp_batch_reset(jssp_batch* b, int32_t n_scenarios, void* stream);
 /* enqueue `n_cycles` lock-step plan cycles for slots [0, n_scenarios) (finished scenarios idle); flags:
  * JSSP_FLAG_FORCE_WARP / JSSP_FLAG_FORCE_THREAD select the evaluation kernel, default by batch size.  Asynchronous. */
 int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int32_t flags, void* stream);

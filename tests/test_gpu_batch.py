@@ -77,3 +77,24 @@ def test_batch_scenario_without_obstacles_and_finished_scenario():
     _same(got[0], R.run_replay(empty, max_cycles=10))
     assert got[1].cycles == 0 and got[1].end == 1
     _same(got[2], R.run_replay(sc, max_cycles=10))
+
+
+def test_c2_multimodal_predictions_batch_matches_oracle(scenario_fixture):
+    """BASELINE config 2 shape: scenes with M = 3 predicted intention modes per vehicle (the planner sees the predictions,
+    the end-of-scenario test the ground truth); p_min / w_risk semantics as in the single-cycle tests."""
+    scs = [S.perturbed_scenario(scenario_fixture, s) for s in (0, 2, 3)]
+    preds = [S.multimodal_predictions(sc, M=3, seed=i) for i, sc in enumerate(scs)]
+    packed = [B.pack_scenario(sc, max_cycles=18, predictions=pr) for sc, pr in zip(scs, preds)]
+    cfg = J.JsspConfig(ego_length=scenario_fixture.ego["length"], ego_width=scenario_fixture.ego["width"], p_min=0.3, w_risk=1.0,
+                       max_seeds=1024, max_knots=256, max_obstacle_modes=32, max_total_steps=256)
+    bt = B.BatchReplay(cfg, max_scenarios=4, max_cycles=18)
+    got = B.run_batch(packed, max_cycles=18, batch=bt)
+    differs = False
+    for sc, pr, p, g in zip(scs, preds, packed, got):
+        cpu = replay_oracle.replay(sc, tuple(p.frenet0), lambda *_a, _pr=pr: _pr, R.end_status, R.goal_pose_of(sc), max_cycles=18,
+                                   cfg_overrides=dict(p_min=0.3, w_risk=1.0))
+        assert g.best_idx == cpu["best_idx"] and g.n_candidates == cpu["n"] and g.end == cpu["end"], (g.best_idx, cpu["best_idx"])
+        np.testing.assert_allclose(np.array(g.ego_rows), np.array(cpu["rows"]), rtol=1e-9, atol=1e-9)
+        differs |= g.best_idx != R.run_replay(sc, max_cycles=18).best_idx
+    assert differs                   # the predicted modes change at least one selection w.r.t. the ground-truth-only replay
+    bt.close()
