@@ -35,8 +35,9 @@ struct jssp_handle {
   int K = 0, kpad = 0;
   double ox = 0, oy = 0;
   // obstacles
-  double *d_raw_state = nullptr, *d_raw_size = nullptr, *d_raw_prob = nullptr;
-  uint8_t* d_raw_valid = nullptr;
+  unsigned char *d_raw = nullptr, *h_raw = nullptr;   // one device block + pinned staging block: [state | size | prob | valid]
+  size_t raw_bytes = 0;
+  cudaEvent_t raw_done = nullptr;                     // the last upload out of h_raw has completed
   const double *src_state = nullptr, *src_size = nullptr, *src_prob = nullptr;   // what the pack kernel reads
   const uint8_t* src_valid = nullptr;
   float4 *d_broad = nullptr, *d_narrow = nullptr;
@@ -64,6 +65,7 @@ struct jssp_handle {
   int last_flags = 0;
   int64_t launches = 0;
   int max_smem_optin = 0;
+  unsigned long long* phase_ts = nullptr;   // profiling builds only
   char cuda_err[256] = {0};
 };
 
@@ -133,7 +135,9 @@ cudaError_t upload_grids(const jssp_config* cfg, double** dst[10], SeedGrids* sg
   HostGrids g = make_grids(cfg->plan_horizon, cfg->highest_jerk, cfg->num_jerk, cfg->delta_t);
   std::vector<double> jneg, jpos;
   for (double j : g.js) { if (!(j > 0)) jneg.push_back(j); if (!(j < 0)) jpos.push_back(j); }   // polyvt_sampling.py:275,287
-  const std::vector<double>* v[10] = {&g.time, &g.j1, &g.t1, &g.t2, &g.j3, &g.t3, &g.t4, &jneg, &jpos, &g.ts};
+  std::vector<double> time_padded = g.time;           // bulk copies move an even number of doubles
+  time_padded.resize((g.time.size() + 2) & ~(size_t)1, 0.0);
+  const std::vector<double>* v[10] = {&time_padded, &g.j1, &g.t1, &g.t2, &g.j3, &g.t3, &g.t4, &jneg, &jpos, &g.ts};
   for (int k = 0; k < 10; ++k) {
     cudaError_t e = upload(dst[k], *v[k]);
     if (e != cudaSuccess) return e;
@@ -180,7 +184,7 @@ int pack_if_dirty(jssp_handle* h, cudaStream_t st) {
   const int total = OMpad * h->Tt;
   if (total > 0) {
     const double r_ego = std::sqrt(h->cfg.ego_length * h->cfg.ego_length + h->cfg.ego_width * h->cfg.ego_width) / 2.0;
-    pack_obstacles_kernel<<<(total + 255) / 256, 256, 0, st>>>(h->src_state, h->src_valid, h->src_size, h->src_prob, OM, OMpad, h->M, h->Tt,
+    pack_obstacles_kernel<<<(total * PACK_LANES + 255) / 256, 256, 0, st>>>(h->src_state, h->src_valid, h->src_size, h->src_prob, OM, OMpad, h->M, h->Tt,
                                                                h->ox, h->oy, h->cfg.obstacle_inflation, r_ego, h->d_broad, h->d_narrow,
                                                                h->d_obs64, h->d_ext64, h->d_probf, h->d_sint, h->d_knot, h->d_knot_xy, h->K,
                                                                h->cull_reach, h->cull_ds);
@@ -314,13 +318,13 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(cudaMalloc(&h->d_seed_work, 4 * sizeof(int)));
   CKC(cudaMemset(h->d_seed_work, 0, 4 * sizeof(int)));
   h->kpad = (cfg->max_knots + 1) & ~1;   // capacity; the per-scenario stride is set in jssp_set_refline
-  CKC(cudaMalloc(&h->d_knot, (size_t)cfg->max_knots * sizeof(double)));
+  CKC(cudaMalloc(&h->d_knot, ((size_t)cfg->max_knots + 2) * sizeof(double)));   // the kernels bulk-copy kpad = K rounded up to even
   CKC(cudaMalloc(&h->d_coef, (size_t)8 * h->kpad * sizeof(double)));
   const size_t om = (size_t)(cfg->max_obstacle_modes > 0 ? cfg->max_obstacle_modes : 1), tt = (size_t)cfg->max_total_steps;
-  CKC(cudaMalloc(&h->d_raw_state, om * tt * 3 * sizeof(double)));
-  CKC(cudaMalloc(&h->d_raw_valid, om * tt));
-  CKC(cudaMalloc(&h->d_raw_size, om * 2 * sizeof(double)));
-  CKC(cudaMalloc(&h->d_raw_prob, om * sizeof(double)));
+  h->raw_bytes = om * tt * 3 * sizeof(double) + om * 2 * sizeof(double) + om * sizeof(double) + om * tt;
+  CKC(cudaMalloc(&h->d_raw, h->raw_bytes));
+  CKC(cudaMallocHost(&h->h_raw, h->raw_bytes));
+  CKC(cudaEventCreateWithFlags(&h->raw_done, cudaEventDisableTiming));
   CKC(cudaMalloc(&h->d_broad, ((om + 31) & ~(size_t)31) * tt * sizeof(float4)));
   CKC(cudaMalloc(&h->d_narrow, om * tt * sizeof(float4)));
   CKC(cudaMalloc(&h->d_obs64, om * tt * 4 * sizeof(double)));
@@ -328,7 +332,7 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(cudaMalloc(&h->d_sint, ((om + 31) & ~(size_t)31) * tt * sizeof(float2)));
   CKC(cudaMalloc(&h->d_probf, om * sizeof(float)));
   CKC(cudaMalloc(&h->d_knot_xy, (size_t)cfg->max_knots * 2 * sizeof(double)));
-  h->max_blocks = (int)(((size_t)cfg->max_seeds * JSSP_MAX_WIDTHS + SMALL_WARPS - 1) / SMALL_WARPS);   // warp-per-candidate grid
+  h->max_blocks = (int)(((size_t)cfg->max_seeds * JSSP_MAX_WIDTHS + SMALL_WARPS - 1) / SMALL_WARPS);   // warp-per-candidate grid (the largest)
   CKC(cudaMalloc(&h->d_blk_cost, (size_t)h->max_blocks * sizeof(double)));
   CKC(cudaMalloc(&h->d_blk_idx, (size_t)h->max_blocks * sizeof(int)));
   CKC(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
@@ -350,6 +354,9 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(cudaFuncSetAttribute(evaluate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CKC(cudaFuncSetAttribute(evaluate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CKC(cudaFuncSetAttribute(evaluate_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CKC(cudaFuncSetAttribute(evaluate_group_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CKC(cudaFuncSetAttribute(evaluate_group_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CKC(cudaFuncSetAttribute(evaluate_group_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CKC(cudaFuncSetAttribute(dump_states_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CKC(cudaDeviceSynchronize());
 #undef CKC
@@ -361,10 +368,11 @@ int32_t jssp_destroy(jssp_handle* h) {
   if (!h) return JSSP_OK;
   cudaSetDevice(h->device);
   void* dev[] = {h->d_time, h->d_j1, h->d_t1, h->d_t2, h->d_j3, h->d_t3, h->d_t4, h->d_jneg, h->d_jpos, h->d_ts, h->d_seeds,
-                 h->d_list_main, h->d_list_stop, h->d_seed_work, h->d_knot, h->d_coef, h->d_raw_state, h->d_raw_valid, h->d_raw_size,
-                 h->d_raw_prob, h->d_broad, h->d_narrow, h->d_obs64, h->d_ext64, h->d_sint, h->d_probf, h->d_knot_xy, h->d_blk_cost, h->d_blk_idx, h->d_ticket, h->d_result};
+                 h->d_list_main, h->d_list_stop, h->d_seed_work, h->d_knot, h->d_coef, h->d_raw, h->d_broad, h->d_narrow, h->d_obs64, h->d_ext64, h->d_sint, h->d_probf, h->d_knot_xy, h->d_blk_cost, h->d_blk_idx, h->d_ticket, h->d_result};
   for (void* p : dev) if (p) cudaFree(p);
   if (h->h_result) cudaFreeHost(h->h_result);
+  if (h->h_raw) cudaFreeHost(h->h_raw);
+  if (h->raw_done) cudaEventDestroy(h->raw_done);
   delete h;
   return JSSP_OK;
 }
@@ -426,14 +434,20 @@ int32_t jssp_set_obstacles(jssp_handle* h, const double* state, const uint8_t* v
   if (rc != JSSP_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
+  // one staged upload: the four host arrays are gathered in pinned memory and cross the bus as a single copy
   const size_t om = (size_t)O * M;
+  const size_t b_state = om * Tt * 3 * sizeof(double), b_size = (size_t)O * 2 * sizeof(double), b_prob = om * sizeof(double), b_valid = om * Tt;
+  unsigned char* d = h->d_raw;
   if (om > 0) {
-    CK(cudaMemcpyAsync(h->d_raw_state, state, om * Tt * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_raw_valid, valid, om * Tt, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_raw_size, size, (size_t)O * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_raw_prob, prob, om * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaEventSynchronize(h->raw_done));             // the previous upload has left the staging block
+    unsigned char* s = h->h_raw;
+    memcpy(s, state, b_state); memcpy(s + b_state, size, b_size); memcpy(s + b_state + b_size, prob, b_prob);
+    memcpy(s + b_state + b_size + b_prob, valid, b_valid);
+    CK(cudaMemcpyAsync(d, s, b_state + b_size + b_prob + b_valid, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(h->raw_done, st));
   }
-  h->src_state = h->d_raw_state; h->src_valid = h->d_raw_valid; h->src_size = h->d_raw_size; h->src_prob = h->d_raw_prob;
+  h->src_state = reinterpret_cast<const double*>(d); h->src_size = reinterpret_cast<const double*>(d + b_state);
+  h->src_prob = reinterpret_cast<const double*>(d + b_state + b_size); h->src_valid = d + b_state + b_size + b_prob;
   return pack_if_dirty(h, st);
 }
 
@@ -564,6 +578,9 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   p.feasible = out->feasible_dev; p.collision = out->collision_dev; p.cost = out->cost_dev;
   p.blk_cost = h->d_blk_cost; p.blk_idx = h->d_blk_idx; p.ticket = h->d_ticket; p.best = h->d_best;
   p.best_traj = (in->flags & JSSP_FLAG_NO_EXPORT) ? nullptr : h->d_best_traj;
+#ifdef JSSP_PROFILE_PHASES
+  p.phase_ts = h->phase_ts;
+#endif
 
   const long long n_max = (long long)W * (ext ? in->n_seeds : c.max_seeds);
   // small cycles (the default sampling grid: ~10^3 candidates) run one warp per candidate: latency, not throughput, matters
@@ -572,10 +589,18 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   bool small = n_max <= 16384 && small_bytes <= (size_t)h->max_smem_optin;
   if (in->flags & JSSP_FLAG_FORCE_THREAD) small = false;
   if ((in->flags & JSSP_FLAG_FORCE_WARP) && small_bytes <= (size_t)h->max_smem_optin) small = true;
-  int blocks = small ? (int)((n_max + SMALL_WARPS - 1) / SMALL_WARPS) : (int)((n_max + EVAL_THREADS - 1) / EVAL_THREADS);
+  if (in->flags & JSSP_FLAG_FORCE_GROUP) small = false;
+  const bool group = !small && !(in->flags & JSSP_FLAG_FORCE_THREAD);
+  const long long seeds_max = ext ? in->n_seeds : c.max_seeds;
+  const int spb = group_seeds_per_block(W);
+  int blocks = small ? (int)((n_max + SMALL_WARPS - 1) / SMALL_WARPS)
+                     : (group ? (int)((seeds_max + spb - 1) / spb) : (int)((n_max + EVAL_THREADS - 1) / EVAL_THREADS));
   if (blocks < 1) blocks = 1;
   if (blocks > h->max_blocks) return JSSP_ERR_CAPACITY;
   if (small) { p.smem_obs = 0; p.win_rows = 0; p.list_cap = 0; evaluate_small_kernel<<<blocks, SMALL_WARPS * 32, small_bytes, st>>>(p); }
+  else if (group && mode == 2) evaluate_group_kernel<2><<<blocks, EVAL_THREADS, L.total, st>>>(p);
+  else if (group && mode == 1) evaluate_group_kernel<1><<<blocks, EVAL_THREADS, L.total, st>>>(p);
+  else if (group) evaluate_group_kernel<0><<<blocks, EVAL_THREADS, L.total, st>>>(p);
   else if (mode == 2) evaluate_kernel<2><<<blocks, EVAL_THREADS, L.total, st>>>(p);
   else if (mode == 1) evaluate_kernel<1><<<blocks, EVAL_THREADS, L.total, st>>>(p);
   else evaluate_kernel<0><<<blocks, EVAL_THREADS, L.total, st>>>(p);
@@ -585,7 +610,8 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   q.smem_obs = 0; q.win_rows = 0; q.list_cap = 0;
   const SmemLayout L2 = eval_smem_layout(0, q.OMpad, 0, q.K, q.kpad, q.P, q.W);
   if (out->states_dev) {
-    dump_states_kernel<<<blocks, EVAL_THREADS, L2.total, st>>>(q, out->states_dev);
+    const int dump_blocks = std::max(1, (int)((n_max + EVAL_THREADS - 1) / EVAL_THREADS));
+    dump_states_kernel<<<dump_blocks, EVAL_THREADS, L2.total, st>>>(q, out->states_dev);
     h->launches++;
     CK(cudaGetLastError());
   }
@@ -605,6 +631,11 @@ int32_t jssp_best_record_dev(jssp_handle* h, int64_t index_offset, void* stream,
 }
 
 int64_t jssp_launch_count(const jssp_handle* h) { return h ? h->launches : 0; }
+
+#ifdef JSSP_PROFILE_PHASES
+/* profiling builds only (tools/phase_probe.py): device buffer [blocks][8] receiving per-block globaltimer stamps */
+int32_t jssp_debug_phase_buffer(jssp_handle* h, unsigned long long* dev) { if (!h) return JSSP_ERR_INVALID_ARG; h->phase_ts = dev; return JSSP_OK; }
+#endif
 
 int32_t jssp_measure_fma_peak(int32_t device, int32_t bits, double* tflops) {
   if (!tflops || (bits != 32 && bits != 64)) return JSSP_ERR_INVALID_ARG;
@@ -741,7 +772,7 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
     if (n_time != b->P) return bail(JSSP_ERR_INVALID_ARG);
   }
   const size_t S = (size_t)b->S;
-  b->n_knot = (size_t)cfg->max_knots;
+  b->n_knot = ((size_t)cfg->max_knots + 2) & ~(size_t)1;   // even stride: every scenario's knots stay 16-byte aligned
   b->n_coef = (size_t)8 * ((cfg->max_knots + 1) & ~1);
   b->n_om = (size_t)(cfg->max_obstacle_modes > 0 ? cfg->max_obstacle_modes : 1);
   b->n_ompad = (b->n_om + 31) & ~(size_t)31;
@@ -791,6 +822,8 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   CKC(cudaFuncSetAttribute(evaluate_batch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->max_smem_optin));
   CKC(cudaFuncSetAttribute(evaluate_batch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->max_smem_optin));
   CKC(cudaFuncSetAttribute(evaluate_small_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->max_smem_optin));
+  CKC(cudaFuncSetAttribute(evaluate_group_batch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->max_smem_optin));
+  CKC(cudaFuncSetAttribute(evaluate_group_batch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->max_smem_optin));
   CKC(cudaDeviceSynchronize());
 #undef CKC
   *out = b;
@@ -840,7 +873,7 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
     CKB(cudaMemcpyAsync(raw_prob, in->prob, (size_t)OM * sizeof(double), cudaMemcpyHostToDevice, st));
     const double r_ego = std::sqrt(ego_l * ego_l + ego_w * ego_w) / 2.0;
     const int total = OMpad * Tt;
-    pack_obstacles_kernel<<<(total + 255) / 256, 256, 0, st>>>(raw_state, raw_valid, raw_size, raw_prob, OM, OMpad, in->M, Tt, ox, oy,
+    pack_obstacles_kernel<<<(total * PACK_LANES + 255) / 256, 256, 0, st>>>(raw_state, raw_valid, raw_size, raw_prob, OM, OMpad, in->M, Tt, ox, oy,
                                                                b->cfg.obstacle_inflation, r_ego, broad, narrow, obs64, ext64, probf, nullptr,
                                                                nullptr, nullptr, 0, 0.0, 0.0);
     b->launches++;
@@ -934,8 +967,11 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   const SmemLayout Ls = eval_smem_layout(0, b->max_OMpad, 0, b->max_K, b->max_kpad, b->P, b->W);
   const size_t small_bytes = Ls.total + small_scratch_bytes(b->P);
   bool small = (long long)n_scenarios * b->cfg.max_seeds * b->W <= 65536 && small_bytes <= (size_t)b->max_smem_optin;
-  if (flags & JSSP_FLAG_FORCE_THREAD) small = false;
+  if (flags & (JSSP_FLAG_FORCE_THREAD | JSSP_FLAG_FORCE_GROUP)) small = false;
   if ((flags & JSSP_FLAG_FORCE_WARP) && small_bytes <= (size_t)b->max_smem_optin) small = true;
+  const bool group = !small && !(flags & JSSP_FLAG_FORCE_THREAD);
+  const int spb = group_seeds_per_block(b->W);
+  const int blocks_group = (b->cfg.max_seeds + spb - 1) / spb;
   int mode = b->max_OMpad > 0 ? 1 : 0;
   SmemLayout L = eval_smem_layout(max_rows, b->max_OMpad, mode, b->max_K, b->max_kpad, b->P, b->W);
   if (mode == 1 && L.total > (size_t)b->max_smem_optin) { mode = 0; L = eval_smem_layout(0, b->max_OMpad, 0, b->max_K, b->max_kpad, b->P, b->W); }
@@ -945,6 +981,8 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   for (int c = 0; c < n_cycles; ++c) {
     seed_enum_kernel<true><<<dim3(seed_blocks, n_scenarios), SEED_THREADS, 0, st>>>(b->grids, SeedState{0, 0, 0}, b->d_slots, wk);
     if (small) evaluate_small_batch_kernel<<<dim3(b->blocks_warp, n_scenarios), SMALL_WARPS * 32, small_bytes, st>>>(b->d_slots);
+    else if (group && mode == 1) evaluate_group_batch_kernel<1><<<dim3(blocks_group, n_scenarios), EVAL_THREADS, L.total, st>>>(b->d_slots);
+    else if (group) evaluate_group_batch_kernel<0><<<dim3(blocks_group, n_scenarios), EVAL_THREADS, L.total, st>>>(b->d_slots);
     else if (mode == 1) evaluate_batch_kernel<1><<<dim3(b->blocks_thread, n_scenarios), EVAL_THREADS, L.total, st>>>(b->d_slots);
     else evaluate_batch_kernel<0><<<dim3(b->blocks_thread, n_scenarios), EVAL_THREADS, L.total, st>>>(b->d_slots);
     b->launches += 2;

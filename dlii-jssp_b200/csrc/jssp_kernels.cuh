@@ -24,6 +24,15 @@ constexpr int EVAL_MIN_BLOCKS = JSSP_EVAL_MIN_BLOCKS;
 constexpr float SAT_EPS = 2e-3f;        // fp32 guard band [m]; inside it the pair is re-decided in float64
 constexpr float FAR_AWAY = 1e30f;       // x of an absent obstacle state: squared distance overflows to +inf -> culled
 
+#ifdef JSSP_PROFILE_PHASES
+__device__ __forceinline__ void phase_stamp(unsigned long long* ts, int slot) {
+  if (ts && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); ts[(size_t)blockIdx.x * 8 + slot] = t; }
+}
+#define PHASE(p, k) phase_stamp((p).phase_ts, k)
+#else
+#define PHASE(p, k)
+#endif
+
 struct BestRecord {
   unsigned long long key;   // orderable_bits(cost)
   long long idx;            // candidate index (+ offset for candidate-split runs), -1 = none
@@ -315,6 +324,7 @@ __global__ void __launch_bounds__(SEED_THREADS) seed_enum_kernel(SeedGrids g, Se
 //   obs64  [Tt][OM][4]     = x, y, cos yaw, sin yaw in float64 for the guard-band re-decision
 // ------------------------------------------------------------------------------------------------------------------
 constexpr float BROAD_PAD = 0.05f;        // [m] added to the bounding-circle radius sum
+constexpr int PACK_LANES = 8;             // lanes sharing one obstacle state in pack_obstacles_kernel
 constexpr float BROAD_CANCEL = 0.5f;      // [m^2] covers fp32 cancellation of the expanded form for |coord| <= 1000 m
 __global__ void pack_obstacles_kernel(const double* __restrict__ state, const uint8_t* __restrict__ valid,
                                       const double* __restrict__ size, const double* __restrict__ prob, int OM, int OMpad, int M,
@@ -322,40 +332,53 @@ __global__ void pack_obstacles_kernel(const double* __restrict__ state, const ui
                                       float4* __restrict__ narrow, double* __restrict__ obs64, double* __restrict__ ext64,
                                       float* __restrict__ probf, float2* __restrict__ sint, const double* __restrict__ knot_s,
                                       const double* __restrict__ knot_xy, int K, double cull_reach, double cull_ds) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // idx = t * OMpad + om
-  if (idx >= OMpad * Tt) return;
+  // PACK_LANES consecutive lanes own one table entry idx = t * OMpad + om: lane 0 of the group writes the rows, all of them
+  // share the scan over the reference-line knots
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = gtid / PACK_LANES, sub = gtid % PACK_LANES;
+  if (idx >= OMpad * Tt) return;               // whole groups leave together (blockDim is a multiple of PACK_LANES)
   const int t = idx / OMpad, om = idx - t * OMpad;
-  if (sint) sint[idx] = make_float2(FAR_AWAY, -FAR_AWAY);  // empty arc-length interval (NULL: no block-level culling tables)
-  if (om >= OM) { broad[idx] = make_float4(0.f, 0.f, FAR_AWAY, 0.f); return; }
+  if (om >= OM) {
+    if (sub == 0) { broad[idx] = make_float4(0.f, 0.f, FAR_AWAY, 0.f); if (sint) sint[idx] = make_float2(FAR_AWAY, -FAR_AWAY); }
+    return;
+  }
   const int o = om / M;
   const double a2 = (size[2 * o] + inflation) / 2.0, b2 = (size[2 * o + 1] + inflation) / 2.0;
-  if (t == 0) { ext64[2 * om] = a2; ext64[2 * om + 1] = b2; }
   const double* s = state + ((size_t)om * Tt + t) * 3;
   const bool ok = valid[(size_t)om * Tt + t] != 0;
-  double sn, cs;
-  sincos(s[2], &sn, &cs);
   const float r = (float)(r_ego + sqrt(a2 * a2 + b2 * b2)) + BROAD_PAD;
-  const float fx = (float)(s[0] - ox), fy = (float)(s[1] - oy);
-  const float q = fmaf(fx, fx, fy * fy) - (r * r * 1.0001f + BROAD_CANCEL);
-  broad[idx] = ok ? make_float4(fx, fy, q, (float)prob[om]) : make_float4(0.f, 0.f, FAR_AWAY, 0.f);
-  const size_t gi = (size_t)t * OM + om;
-  narrow[gi] = make_float4((float)cs, (float)sn, (float)a2, (float)b2);
-  double* q64 = obs64 + gi * 4;
-  q64[0] = s[0]; q64[1] = s[1]; q64[2] = cs; q64[3] = sn;
-  if (t == 0) probf[om] = (float)prob[om];
+  if (sub == 0) {
+    if (t == 0) { ext64[2 * om] = a2; ext64[2 * om + 1] = b2; probf[om] = (float)prob[om]; }
+    double sn, cs;
+    sincos(s[2], &sn, &cs);
+    const float fx = (float)(s[0] - ox), fy = (float)(s[1] - oy);
+    const float q = fmaf(fx, fx, fy * fy) - (r * r * 1.0001f + BROAD_CANCEL);
+    broad[idx] = ok ? make_float4(fx, fy, q, (float)prob[om]) : make_float4(0.f, 0.f, FAR_AWAY, 0.f);
+    const size_t gi = (size_t)t * OM + om;
+    narrow[gi] = make_float4((float)cs, (float)sn, (float)a2, (float)b2);
+    double* q64 = obs64 + gi * 4;
+    q64[0] = s[0]; q64[1] = s[1]; q64[2] = cs; q64[3] = sn;
+  }
   // Arc-length interval of the reference line from which this obstacle state can be reached by any candidate footprint:
   // every curve point within (lateral cap + R) of the obstacle lies within cull_reach of one of its segment's knots
   // (cull_reach includes the longest knot-to-knot arc), so the hull of those knots widened by cull_ds is conservative.
-  if (sint && ok && K > 0) {
+  if (!sint) return;
+  double lo = 1e300, hi = -1e300;
+  if (ok && K > 0) {
     const double reach = cull_reach + (double)r;
     const double r2 = reach * reach;
-    double lo = 1e300, hi = -1e300;
-    for (int k = 0; k < K; ++k) {
+    for (int k = sub; k < K; k += PACK_LANES) {
       const double dx = knot_xy[2 * k] - s[0], dy = knot_xy[2 * k + 1] - s[1];
       if (dx * dx + dy * dy <= r2) { lo = fmin(lo, knot_s[k]); hi = fmax(hi, knot_s[k]); }
     }
-    if (hi >= lo) sint[idx] = make_float2(__double2float_rd(lo - cull_ds), __double2float_ru(hi + cull_ds));
   }
+  const unsigned int gmask = ((1u << PACK_LANES) - 1u) << ((threadIdx.x & 31) & ~(PACK_LANES - 1));
+#pragma unroll
+  for (int d = PACK_LANES / 2; d > 0; d >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(gmask, lo, d));
+    hi = fmax(hi, __shfl_xor_sync(gmask, hi, d));
+  }
+  if (sub == 0) sint[idx] = hi >= lo ? make_float2(__double2float_rd(lo - cull_ds), __double2float_ru(hi + cull_ds)) : make_float2(FAR_AWAY, -FAR_AWAY);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -398,6 +421,9 @@ struct EvalParams {
   BestRecord* best;
   double* best_traj;              // [P][16] export of the selected trajectory (NULL = skip)
   // batched replay (NULL / unused for a single plan cycle)
+#ifdef JSSP_PROFILE_PHASES
+  unsigned long long* phase_ts;   // [blocks][8] globaltimer stamps (tools/phase_probe.py; profiling builds only)
+#endif
   struct BatchSlot* batch;        // per-scenario replay state, updated by the hand-off at the end of every cycle
   EvalParams* self;               // this scenario's parameter record in device memory (the hand-off writes the next cycle's inputs)
 };
@@ -538,6 +564,12 @@ struct EvalSink {
     sum_j = sum_j + ej * ej;
     sum_v = sum_v + ev * ev;
   }
+  // the same accumulation from per-sample cost terms computed elsewhere (group kernel: by the lane that owns the sample)
+  __device__ __forceinline__ void sample_terms(double ea2, double ej2, double ev2) {
+    sum_a = sum_a + ea2;
+    sum_j = sum_j + ej2;
+    sum_v = sum_v + ev2;
+  }
   __device__ __forceinline__ void point(int, double, double) {}
 
   __device__ __forceinline__ void curvature_step(double dx, double dy, double ds, double c, double sn) {
@@ -610,6 +642,66 @@ struct EvalSink {
   }
 };
 
+// ------------------------------------------------------------------------------------------------------------------
+// Group form of the walk: the W candidates that share a longitudinal seed (one per lateral target) sit in W consecutive
+// lanes.  Everything that depends on the seed only - the unrolled s, s_d, s_dd, s_ddd, the cost terms, the spline segment,
+// the reference point and its unit normal - is computed ONCE per sample by the lane that owns the sample (lane j owns
+// samples j, j + W, ...) and handed to the group by warp shuffles; every lane then adds its own lateral offset and runs the
+// per-candidate part (difference, length, curvature test, collision rows).  Same expressions, same order of the cost
+// sums: results are bit-identical to walk_candidate.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_f64(unsigned int mask, double v, int src) { return __shfl_sync(mask, v, src); }
+
+__device__ __forceinline__ void walk_group(const EvalParams& p, const BlockTables& tb, LonWalk& lp, int w, int W, unsigned int gmask,
+                                           int glane0, EvalSink& sink) {
+  const int P = p.P;
+  const double* lat = tb.lat + (size_t)w * P * 4;
+  int n_pts = P;
+  bool live = true;
+  double xp = 0, yp = 0;
+  for (int base = 0; base < P; base += W) {
+    // the sample this lane owns in this round
+    const int io = base + w;
+    double o_s = 0, o_ea = 0, o_ej = 0, o_ev = 0, o_ix = 0, o_iy = 0, o_u = 0, o_v = 0;
+    int o_in = 0;
+    if (io < P) {
+      double sd, sdd, sddd;
+      lon_walk_eval(lp, tb.time[io], o_s, sd, sdd, sddd);
+      const double ea = fmax(fabs(sdd) - p.thr_lon_a, 0.0);
+      const double ej = fmax(fabs(sddd) - p.thr_lon_j, 0.0);
+      const double ev = (p.vmax - sd) * p.inv_vmax;
+      o_ea = ea * ea; o_ej = ej * ej; o_ev = ev * ev;
+      if (live && spline_in_range(tb.sp, o_s)) {
+        o_in = 1;
+        frenet_base(tb.sp, spline_walk(tb.sp, o_s, 0), o_s, o_ix, o_iy, o_u, o_v);
+      }
+    }
+    const int cnt = min(W, P - base);
+    for (int jj = 0; jj < cnt; ++jj) {
+      const int i = base + jj, src = glane0 + jj;
+      sink.sample_terms(shfl_f64(gmask, o_ea, src), shfl_f64(gmask, o_ej, src), shfl_f64(gmask, o_ev, src));
+      if (i == 0) sink.s_first = shfl_f64(gmask, o_s, src);
+      if (i == P - 1) sink.s_last = shfl_f64(gmask, o_s, src);
+      if (!live) continue;
+      if (!__shfl_sync(gmask, o_in, src)) { n_pts = i; live = false; continue; }   // first sample off the reference line (:138-139)
+      const double ix = shfl_f64(gmask, o_ix, src), iy = shfl_f64(gmask, o_iy, src);
+      const double u = shfl_f64(gmask, o_u, src), v = shfl_f64(gmask, o_v, src);
+      const double d = lat[i * 4];
+      const double x = ix - d * u, y = iy + d * v;
+      if (i >= 1) {
+        const double dx = x - xp, dy = y - yp;
+        const double q = dx * dx + dy * dy;
+        double ds, c = 1.0, sn = 0.0;
+        if (q > 1e-200 && q < 1e200) { const double inv = rsqrt(q); ds = q * inv; c = dx * inv; sn = dy * inv; }
+        else { ds = hypot(dx, dy); if (ds > 0.0) { c = dx / ds; sn = dy / ds; } }
+        sink.segment(i - 1, xp, yp, dx, dy, ds, c, sn);
+      }
+      xp = x; yp = y;
+    }
+  }
+  sink.finish(n_pts, xp, yp);
+}
+
 __device__ __forceinline__ double candidate_cost(const EvalParams& p, double sum_a, double sum_j, double sum_v, double s_first,
                                                  double s_last, double risk, const double* latcost) {
   const double P = (double)p.P;
@@ -661,24 +753,26 @@ __device__ __forceinline__ void stage_tables(const EvalParams& p, unsigned char*
   double* sm_latcost = reinterpret_cast<double*>(smem + L.off_latcost);
   const int tid = threadIdx.x, nt = blockDim.x;
   const uint32_t row_bytes = (uint32_t)p.OMpad * 16u;
+  // Everything that is copied verbatim goes through the TMA engine (1-D bulk copies completing on one mbarrier): the
+  // reference-line knots and coefficients, the time grid and - mode 1 - the rows of the obstacle window.
   int rows_avail = 0;
-  if (kSmem) {
-    // rows of the window that exist in the scenario table: absolute step now + r*check_res < Tt
-    for (int r = 0; r < p.win_rows; ++r) rows_avail += (p.now + r * p.check_res < p.Tt) ? 1 : 0;
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (tid < 32) {
-      if (tid == 0) mbar_arrive_expect_tx(bar, row_bytes * (uint32_t)rows_avail);
-      __syncwarp();
-      for (int r = tid; r < rows_avail; r += 32)
-        bulk_copy_g2s(sm_broad + (size_t)r * p.OMpad, p.broad + (size_t)(p.now + r * p.check_res) * p.OMpad, row_bytes, bar);
-    }
-    for (int e = rows_avail * p.OMpad + tid; e < p.win_rows * p.OMpad; e += nt) sm_broad[e] = make_float4(0.f, 0.f, FAR_AWAY, 0.f);
-  }
-  for (int e = tid; e < p.K; e += nt) sm_knot[e] = p.knot[e];
-  for (int e = tid; e < 8 * p.kpad; e += nt) sm_coef[e] = p.coef[e];
-  for (int e = tid; e < p.P; e += nt) sm_time[e] = p.time[e];
+  if (kSmem) for (int r = 0; r < p.win_rows; ++r) rows_avail += (p.now + r * p.check_res < p.Tt) ? 1 : 0;   // rows that exist in the scenario table
+  const uint32_t knot_bytes = (uint32_t)p.kpad * 8u, coef_bytes = (uint32_t)p.kpad * 64u, time_bytes = (uint32_t)((p.P + 1) & ~1) * 8u;
+  if (tid == 0) mbar_init(bar, 1);
   __syncthreads();
+  if (tid < 32) {
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar, knot_bytes + coef_bytes + time_bytes + row_bytes * (uint32_t)rows_avail);
+      bulk_copy_g2s(sm_knot, p.knot, knot_bytes, bar);
+      bulk_copy_g2s(sm_coef, p.coef, coef_bytes, bar);
+      bulk_copy_g2s(sm_time, p.time, time_bytes, bar);
+    }
+    __syncwarp();
+    for (int r = tid; r < rows_avail; r += 32)
+      bulk_copy_g2s(sm_broad + (size_t)r * p.OMpad, p.broad + (size_t)(p.now + r * p.check_res) * p.OMpad, row_bytes, bar);
+  }
+  if (kSmem) for (int e = rows_avail * p.OMpad + tid; e < p.win_rows * p.OMpad; e += nt) sm_broad[e] = make_float4(0.f, 0.f, FAR_AWAY, 0.f);
+  mbar_wait(bar, 0);
   for (int e = tid; e < p.W * p.P; e += nt) {
     const int w = e / p.P, i = e - w * p.P;
     double d, d1, d2, d3;
@@ -687,18 +781,25 @@ __device__ __forceinline__ void stage_tables(const EvalParams& p, unsigned char*
     o[0] = d; o[1] = d1; o[2] = d2; o[3] = d3;
   }
   __syncthreads();
-  if (tid < p.W) {   // per-width lateral cost sums, sequential in time like the oracle
+  // per-width lateral cost sums: one warp per width, lane l adds samples l, l + 32, ... in time order, then a fixed
+  // shuffle tree (deterministic; every kernel stages its tables through this function, so all of them see the same sums)
+  for (int w = tid >> 5; w < p.W; w += nt >> 5) {
     double s0 = 0, s1 = 0, s2 = 0;
-    for (int i = 0; i < p.P; ++i) {
-      const double* o = sm_lat + ((size_t)tid * p.P + i) * 4;
+    for (int i = tid & 31; i < p.P; i += 32) {
+      const double* o = sm_lat + ((size_t)w * p.P + i) * 4;
       const double e1 = fmax(fabs(o[2]) - p.thr_lat_a, 0.0), e2 = fmax(fabs(o[3]) - p.thr_lat_j, 0.0);
       s0 = s0 + o[0] * o[0]; s1 = s1 + e1 * e1; s2 = s2 + e2 * e2;
     }
-    sm_latcost[tid * 4] = s0; sm_latcost[tid * 4 + 1] = s1; sm_latcost[tid * 4 + 2] = s2;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s0 = s0 + __shfl_down_sync(0xffffffffu, s0, off);
+      s1 = s1 + __shfl_down_sync(0xffffffffu, s1, off);
+      s2 = s2 + __shfl_down_sync(0xffffffffu, s2, off);
+    }
+    if ((tid & 31) == 0) { sm_latcost[w * 4] = s0; sm_latcost[w * 4 + 1] = s1; sm_latcost[w * 4 + 2] = s2; }
   }
   __syncthreads();
   if (kSmem) {
-    if (rows_avail > 0) mbar_wait(bar, 0);
     tb.broad = sm_broad; tb.broad_row0 = 0; tb.broad_stride = 1;
   } else {
     tb.broad = p.broad; tb.broad_row0 = p.now; tb.broad_stride = p.check_res;
@@ -718,7 +819,10 @@ __device__ __forceinline__ void stage_tables(const EvalParams& p, unsigned char*
 //   phase B  one warp per row: ballot-compaction of the states whose reachable interval (pack_obstacles_kernel)
 //            overlaps the row's range.
 // Falls back to the global table (tb.use_lists stays false) when the lists would not fit.
-__device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* smem, BlockTables& tb, LonWalk lp, bool active) {
+// Phase A lets every thread scan the rows row_first, row_first + row_stride, ... of ITS seed: (0, 1) when every thread has a
+// seed of its own, (lane-in-group, W) when the W lanes of a group share one.
+__device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* smem, BlockTables& tb, LonWalk lp, bool active,
+                                            int row_first = 0, int row_stride = 1) {
   const SmemLayout L = eval_smem_layout(p.win_rows, p.OMpad, 2, p.K, p.kpad, p.P, p.W, p.list_cap);
   float4* list = reinterpret_cast<float4*>(smem + L.off_broad);
   int* row_off = reinterpret_cast<int*>(smem + L.off_rows);
@@ -731,25 +835,79 @@ __device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* 
   if (tid == 0) { cursor[0] = 0; cursor[1] = 0; }
   __syncthreads();
   const double s_end = tb.sp.knot[p.K - 1];
-  for (int r = 0; r < p.win_rows; ++r) {
-    unsigned int lo = 0x7f800000u, hi = 0u;
-    if (active) {
-      double s, sd, sdd, sddd;
-      lon_walk_eval(lp, tb.time[r * p.check_res], s, sd, sdd, sddd);
-      s = fmin(fmax(s, 0.0), s_end);                  // off-line samples are never collision-checked
-      lo = __float_as_uint(__double2float_rd(s));     // s >= 0: the bit patterns order like the values
-      hi = __float_as_uint(__double2float_ru(s));
+  if (row_stride == 1) {
+    for (int r = 0; r < p.win_rows; ++r) {
+      unsigned int lo = 0x7f800000u, hi = 0u;
+      if (active) {
+        double s, sd, sdd, sddd;
+        lon_walk_eval(lp, tb.time[r * p.check_res], s, sd, sdd, sddd);
+        s = fmin(fmax(s, 0.0), s_end);                  // off-line samples are never collision-checked
+        lo = __float_as_uint(__double2float_rd(s));     // s >= 0: the bit patterns order like the values
+        hi = __float_as_uint(__double2float_ru(s));
+      }
+      lo = __reduce_min_sync(0xffffffffu, lo);
+      hi = __reduce_max_sync(0xffffffffu, hi);
+      if (lane == 0) { atomicMin(&row_min[r], lo); atomicMax(&row_max[r], hi); }
     }
-    lo = __reduce_min_sync(0xffffffffu, lo);
-    hi = __reduce_max_sync(0xffffffffu, hi);
-    if (lane == 0) { atomicMin(&row_min[r], lo); atomicMax(&row_max[r], hi); }
+  } else {
+    // the lanes of a group share the seed: lane j of the group evaluates the rows r = j (mod W); in one round every lane
+    // with the same j holds the same row, so a stride-W shuffle tree leaves the warp's range in the lanes of group 0
+    const int W = row_stride;
+    for (int r0 = 0; r0 < p.win_rows; r0 += W) {
+      const int r = r0 + row_first;
+      unsigned int lo = 0x7f800000u, hi = 0u;
+      if (active && r < p.win_rows) {
+        double s, sd, sdd, sddd;
+        lon_walk_eval(lp, tb.time[r * p.check_res], s, sd, sdd, sddd);
+        s = fmin(fmax(s, 0.0), s_end);
+        lo = __float_as_uint(__double2float_rd(s));
+        hi = __float_as_uint(__double2float_ru(s));
+      }
+      for (int off = W; off < 32; off <<= 1) {
+        const unsigned int lo2 = __shfl_down_sync(0xffffffffu, lo, off), hi2 = __shfl_down_sync(0xffffffffu, hi, off);
+        if (lane + off < 32) { lo = min(lo, lo2); hi = max(hi, hi2); }
+      }
+      if (lane < W && r < p.win_rows) { atomicMin(&row_min[r], lo); atomicMax(&row_max[r], hi); }
+    }
   }
   __syncthreads();
+  constexpr int CH = 8;                               // chunks of 32 obstacle states held in registers per pass
   for (int r = wid; r < p.win_rows; r += nw) {
     const int t = p.now + r * p.check_res;
     if (t >= p.Tt) continue;                          // no obstacle state exists beyond the scenario
     const float smin = __uint_as_float(row_min[r]) - 1e-3f, smax = __uint_as_float(row_max[r]) + 1e-3f;
     const float2* iv = p.sint + (size_t)t * p.OMpad;
+    const float4* src = p.broad + (size_t)t * p.OMpad;
+    if (p.OMpad <= 32 * CH) {
+      // single pass: every load of the row is in flight at once
+      float2 v[CH];
+      float4 bb[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int e = c * 32 + lane;
+        v[c] = e < p.OMpad ? __ldg(iv + e) : make_float2(FAR_AWAY, -FAR_AWAY);
+        bb[c] = e < p.OMpad ? __ldg(src + e) : make_float4(0.f, 0.f, FAR_AWAY, 0.f);
+      }
+      unsigned int m[CH];
+      int cnt = 0;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) { m[c] = __ballot_sync(0xffffffffu, v[c].y >= smin && v[c].x <= smax); cnt += __popc(m[c]); }
+      int off = 0;
+      if (lane == 0) off = atomicAdd(&cursor[0], cnt);
+      off = __shfl_sync(0xffffffffu, off, 0);
+      if (off + cnt > p.list_cap) { if (lane == 0) cursor[1] = 1; continue; }
+      if (lane == 0) { row_off[r] = off; row_cnt[r] = cnt; }
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        if ((m[c] >> lane) & 1u) {
+          float4 b = bb[c];
+          b.w = __int_as_float(c * 32 + lane);
+          list[off + __popc(m[c] & ((1u << lane) - 1u))] = b;
+        }
+        off += __popc(m[c]);
+      }
+      continue;
+    }
     int cnt = 0;
     for (int base = 0; base < p.OMpad; base += 32) {
       const float2 v = iv[base + lane];
@@ -760,7 +918,6 @@ __device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* 
     off = __shfl_sync(0xffffffffu, off, 0);
     if (off + cnt > p.list_cap) { if (lane == 0) cursor[1] = 1; continue; }
     if (lane == 0) { row_off[r] = off; row_cnt[r] = cnt; }
-    const float4* src = p.broad + (size_t)t * p.OMpad;
     for (int base = 0; base < p.OMpad; base += 32) {
       const float2 v = iv[base + lane];
       const bool keep = v.y >= smin && v.x <= smax;
@@ -1023,6 +1180,63 @@ __global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_kernel
   evaluate_body<kMode>(p, smem, red_cost, red_idx, &is_last, &sm_npts);
 }
 
+// K2 (default for large cycles): the group form - W consecutive lanes evaluate the W lateral targets of one seed and share
+// the seed-only work (walk_group).  Seeds per block = warps * floor(32 / W); lanes beyond floor(32 / W) * W idle.
+__host__ __device__ inline int group_seeds_per_block(int W) { return (EVAL_THREADS / 32) * (32 / W); }
+
+template <int kMode>
+__device__ __forceinline__ void evaluate_group_body(const EvalParams& p, unsigned char* smem, double* red_cost, int* red_idx,
+                                                    bool* is_last, int* sm_npts) {
+  const int Ns = resolve_n_seeds(p);
+  const int W = p.W;
+  const int N = Ns * W;
+  const int gpw = 32 / W;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int g = lane / W, j = lane - g * W;
+  const int spb = (EVAL_THREADS / 32) * gpw;
+  const int k = blockIdx.x * spb + wid * gpw + g;
+  const bool active = g < gpw && k < Ns;
+  double my_cost = INFINITY;
+  int my_idx = -1;
+  BlockTables tb;
+  const double* latcost;
+  const bool staged = blockIdx.x * spb < Ns;   // block-uniform
+  PHASE(p, 0);
+  if (staged) {
+    stage_tables<kMode>(p, smem, tb, latcost);
+    PHASE(p, 1);
+    LonWalk lp;
+    lon_walk_init(lp, p.seeds + (size_t)(active ? k : 0) * 10, p.s0, p.v0, p.a0);
+    if (kMode == 2) build_lists(p, smem, tb, lp, active, j, W);
+    PHASE(p, 2);
+    if (active) {
+      const unsigned int gmask = (W >= 32 ? 0xffffffffu : ((1u << W) - 1u)) << (g * W);
+      EvalSink sink(p, tb);
+      walk_group(p, tb, lp, j, W, gmask, g * W, sink);
+      const int n = j * Ns + k;                // candidate index: width-major (jerk_space_sampling_planner.py:106,124-125)
+      const double cost = candidate_cost(p, sink, latcost + j * 4);
+      if (p.feasible) p.feasible[n] = sink.curv_fail ? 0 : 1;
+      if (p.collision) p.collision[n] = sink.collided ? 1 : 0;
+      if (p.cost) p.cost[n] = (float)cost;
+      if (!sink.curv_fail && !sink.collided && isfinite(cost)) { my_cost = cost; my_idx = n; }
+    }
+  }
+  __syncthreads();
+  PHASE(p, 3);
+  select_and_export<kMode>(p, smem, tb, latcost, staged, my_cost, my_idx, N, Ns, red_cost, red_idx, is_last, sm_npts);
+  PHASE(p, 4);
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_group_kernel(const __grid_constant__ EvalParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ double red_cost[EVAL_THREADS / 32];
+  __shared__ int red_idx[EVAL_THREADS / 32];
+  __shared__ bool is_last;
+  __shared__ int sm_npts;
+  evaluate_group_body<kMode>(p, smem, red_cost, red_idx, &is_last, &sm_npts);
+}
+
 // Batched replay: blockIdx.y = scenario; the scenario's parameter record is copied into shared memory once per block.
 __device__ __forceinline__ void load_slot(EvalParams* dst, const EvalParams* src) {
   static_assert(sizeof(EvalParams) % 8 == 0, "EvalParams is copied as 8-byte words");
@@ -1043,6 +1257,19 @@ __global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_batch_
   if (!slot_live(slots, blockIdx.y)) return;           // block-uniform; stable until the scenario's last block hands off
   load_slot(&sp, slots + blockIdx.y);
   evaluate_body<kMode>(sp, smem, red_cost, red_idx, &is_last, &sm_npts);
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_group_batch_kernel(const EvalParams* __restrict__ slots) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(16) EvalParams sp;
+  __shared__ double red_cost[EVAL_THREADS / 32];
+  __shared__ int red_idx[EVAL_THREADS / 32];
+  __shared__ bool is_last;
+  __shared__ int sm_npts;
+  if (!slot_live(slots, blockIdx.y)) return;
+  load_slot(&sp, slots + blockIdx.y);
+  evaluate_group_body<kMode>(sp, smem, red_cost, red_idx, &is_last, &sm_npts);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

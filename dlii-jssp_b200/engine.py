@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import JsspError, JsspConfigC, JsspCycleIn, JsspCycleOut, JsspImmParams, FLAG_NO_SYNC, FLAG_NO_EXPORT, FLAG_NO_CULL, FLAG_ENUMERATE, FLAG_FORCE_WARP, FLAG_FORCE_THREAD, TRAJ_COLUMNS
+from ._lib import JsspError, JsspConfigC, JsspCycleIn, JsspCycleOut, JsspImmParams, FLAG_NO_SYNC, FLAG_NO_EXPORT, FLAG_NO_CULL, FLAG_ENUMERATE, FLAG_FORCE_WARP, FLAG_FORCE_THREAD, FLAG_FORCE_GROUP, TRAJ_COLUMNS
 
 
 @dataclass
@@ -215,7 +215,7 @@ class JsspEngine:
         """One plan cycle.  frenet0 = (s, s_d, s_dd, d, d_d, d_dd); seeds = device float64 [Ns, 10] or None (use the
         enumerated seeds).  With sync=False the kernels are only enqueued; call fetch() later."""
         flags = (0 if sync else FLAG_NO_SYNC) | (0 if export else FLAG_NO_EXPORT) | (0 if cull else FLAG_NO_CULL)
-        flags |= {None: 0, "warp": FLAG_FORCE_WARP, "thread": FLAG_FORCE_THREAD}[kernel]
+        flags |= {None: 0, "warp": FLAG_FORCE_WARP, "thread": FLAG_FORCE_THREAD, "group": FLAG_FORCE_GROUP}[kernel]
         cin, cout = self._cycle_structs(frenet0, time_step_now, final_time_step, seeds, targets, flags, want_states, None)
         self._last = (cin, cout, want_states)
         self._check(self.lib.jssp_evaluate(self._h, C.byref(cin), self.stream, C.byref(cout)), "jssp_evaluate")

@@ -85,8 +85,9 @@ def test_synthetic_cycle_matches_oracle(n_seeds, n_widths, O_, M, horizon, seed)
     ref = O.plan_cycle(cfg, spline, cyc.frenet0, H.oracle_obstacles(cyc.obstacles), cyc.time_step_now, cyc.final_time_step,
                        seeds=cyc.seeds, targets=cyc.targets)
     seeds = torch.from_numpy(cyc.seeds).cuda()
-    res = eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=seeds, targets=cyc.targets)
-    H.compare_cycle(res, ref)
+    for kern in (None, "group", "thread", "warp"):
+        res = eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=seeds, targets=cyc.targets, kernel=kern)
+        H.compare_cycle(res, ref)
     assert ref["collision"].any() or O_ == 0
     eng.close()
 
@@ -125,8 +126,8 @@ def test_truncated_trajectories_and_end_of_scenario():
                            ((s_end + 1.0, 3.0, 0.0, 0.0, 0.0, 0.0), 0, 100), ((5.0, 6.0, 0.0, 0.0, 0.0, 0.0), 40, 47),
                            ((5.0, 6.0, 0.0, 0.0, 0.0, 0.0), 49, 50), ((5.0, 6.0, 0.0, 0.0, 0.0, 0.0), 50, 50)]:
         ref = O.plan_cycle(cfg, spline, fr, H.oracle_obstacles(cyc.obstacles), now, final, seeds=cyc.seeds, targets=cyc.targets)
-        res = eng.evaluate(fr, now, final, seeds=seeds, targets=cyc.targets)
-        H.compare_cycle(res, ref)
+        for kern in (None, "group"):
+            H.compare_cycle(eng.evaluate(fr, now, final, seeds=seeds, targets=cyc.targets, kernel=kern), ref)
     eng.close()
 
 
@@ -172,25 +173,28 @@ def test_block_level_culling_changes_nothing(n_seeds, n_widths, O_, M, horizon, 
     cyc, cfg, spline, eng = _dense(n_seeds, n_widths, O_, M, horizon, seed, p_min=0.15, w_risk=0.7)
     seeds = torch.from_numpy(cyc.seeds).cuda()
     out = []
-    for cull in (True, False):
-        r = eng.evaluate(cyc.frenet0, 0, cyc.final_time_step, seeds=seeds, targets=cyc.targets, cull=cull)
-        out.append((r.feasible.cpu().numpy().copy(), r.collision.cpu().numpy().copy(), r.cost.cpu().numpy().copy(), r.best_idx, r.best_cost))
+    for kern in ("group", "thread"):           # the kernels that build the per-block lists (small cycles default to the warp kernel)
+        for cull in (True, False):
+            r = eng.evaluate(cyc.frenet0, 0, cyc.final_time_step, seeds=seeds, targets=cyc.targets, cull=cull, kernel=kern)
+            out.append((r.feasible.cpu().numpy().copy(), r.collision.cpu().numpy().copy(), r.cost.cpu().numpy().copy(), r.best_idx, r.best_cost))
     ok = out[0][1] == 0          # a vetoed candidate stops accumulating risk at the veto, wherever the walk is then
-    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2][ok], out[1][2][ok])
-    assert out[0][3:] == out[1][3:]
+    for other in out[1:]:
+        assert np.array_equal(out[0][0], other[0]) and np.array_equal(out[0][1], other[1]) and np.array_equal(out[0][2][ok], other[2][ok])
+        assert out[0][3:] == other[3:]
     ref = O.plan_cycle(cfg, spline, cyc.frenet0, H.oracle_obstacles(cyc.obstacles), 0, cyc.final_time_step, seeds=cyc.seeds, targets=cyc.targets)
-    res = eng.evaluate(cyc.frenet0, 0, cyc.final_time_step, seeds=seeds, targets=cyc.targets)
+    res = eng.evaluate(cyc.frenet0, 0, cyc.final_time_step, seeds=seeds, targets=cyc.targets, kernel="group")
     H.compare_cycle(res, ref)
     # a start offset beyond the lateral cap switches culling off instead of risking a miss
     wide = (cyc.frenet0[0], cyc.frenet0[1], 0.0, 4.2, 0.0, 0.0)
     ref = O.plan_cycle(cfg, spline, wide, H.oracle_obstacles(cyc.obstacles), 0, cyc.final_time_step, seeds=cyc.seeds, targets=cyc.targets)
-    H.compare_cycle(eng.evaluate(wide, 0, cyc.final_time_step, seeds=seeds, targets=cyc.targets), ref)
+    for kern in ("group", "thread"):
+        H.compare_cycle(eng.evaluate(wide, 0, cyc.final_time_step, seeds=seeds, targets=cyc.targets, kernel=kern), ref)
     eng.close()
 
 
 @pytest.mark.parametrize("n_seeds,n_widths,O_,M,horizon,seed", [(300, 3, 6, 1, 5.0, 51), (257, 4, 40, 3, 5.0, 52), (90, 5, 70, 2, 8.0, 53), (64, 2, 0, 1, 5.0, 54)])
 def test_warp_and_thread_kernels_agree(n_seeds, n_widths, O_, M, horizon, seed):
-    """The warp-per-candidate kernel (small cycles) and the thread-per-candidate kernel give bit-identical masks, fp32
+    """The warp-per-candidate kernel (small cycles), the group kernel (large cycles) and the thread-per-candidate kernel give bit-identical masks, fp32
     costs, selection and exported trajectory - and match the oracle, including truncated trajectories."""
     cyc, cfg, spline, eng = _dense(n_seeds, n_widths, O_, M, horizon, seed, p_min=0.2, w_risk=0.9)
     seeds = torch.from_numpy(cyc.seeds).cuda()
@@ -198,16 +202,17 @@ def test_warp_and_thread_kernels_agree(n_seeds, n_widths, O_, M, horizon, seed):
     for fr, now, final in [(cyc.frenet0, 0, cyc.final_time_step), ((s_end - 9.0, 8.0, 0.5, -0.3, 0.1, 0.0), 0, 100),
                            ((s_end - 0.04, 3.0, 0.0, 0.1, 0.0, 0.0), 0, 100), ((4.0, 5.0, 0.0, 0.0, 0.0, 0.0), 43, 50)]:
         out = {}
-        for kern in ("warp", "thread"):
+        for kern in ("warp", "thread", "group"):
             r = eng.evaluate(fr, now, final, seeds=seeds, targets=cyc.targets, kernel=kern)
             out[kern] = (r.feasible.cpu().numpy().copy(), r.collision.cpu().numpy().copy(), r.cost.cpu().numpy().copy(), r.best_idx, r.best_cost,
                          r.best_n_pts, None if r.best_traj is None else r.best_traj.copy())
-        a, b = out["warp"], out["thread"]
-        ok = a[1] == 0
-        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2][ok], b[2][ok])
-        assert a[3:6] == b[3:6]
-        if a[6] is not None:
-            assert np.array_equal(a[6], b[6], equal_nan=True)
+        b = out["thread"]
+        for a in (out["warp"], out["group"]):
+            ok = a[1] == 0
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2][ok], b[2][ok])
+            assert a[3:6] == b[3:6]
+            if a[6] is not None:
+                assert np.array_equal(a[6], b[6], equal_nan=True)
         ref = O.plan_cycle(cfg, spline, fr, H.oracle_obstacles(cyc.obstacles), now, final, seeds=cyc.seeds, targets=cyc.targets)
         H.compare_cycle(eng.evaluate(fr, now, final, seeds=seeds, targets=cyc.targets, kernel="warp"), ref)
     eng.close()
