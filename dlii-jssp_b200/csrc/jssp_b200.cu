@@ -25,9 +25,9 @@ struct jssp_handle {
   uint32_t main_total = 0, stop_total = 0;
   // seeds
   double* d_seeds = nullptr;
-  uint32_t *d_list_main = nullptr, *d_list_stop = nullptr;
   int* d_counts = nullptr;
-  int* d_seed_work = nullptr; // scratch counters of the fused enumeration kernel (zero between launches)
+  SeedWork seed_work{};
+  size_t seed_smem = 0;
   int* h_counts = nullptr;   // pinned
   bool seeds_ready = false;
   // reference line
@@ -222,7 +222,34 @@ static int32_t measure_fma(int device, double* tflops) {
   return JSSP_OK;
 }
 
-constexpr int SEED_BLOCKS_SINGLE = 88;   // 45,075 enumeration tasks / 512 threads
+// launch of the seed enumeration: n_scenarios clusters of `csize` CTAs
+template <bool kBatch>
+cudaError_t launch_seed_enum(const SeedGrids& g, SeedState ss, const EvalParams* slots, const SeedWork& wk, int n_scenarios, int csize,
+                             int threads, size_t smem, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_scenarios * csize), 1, 1);
+  cfg.blockDim = dim3((unsigned)threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, seed_enum_kernel<kBatch>, g, ss, slots, wk);
+}
+
+// shared-memory list capacities of the seed enumeration kernel for the handle's sampling grids
+SeedWork make_seed_work(const SeedGrids& g, int* counts, double* seeds, int cap_seeds) {
+  SeedWork w{};
+  w.counts = counts; w.seeds = seeds; w.cap_seeds = cap_seeds;
+  w.cap_a_main = g.n_j1 * g.n_t1;                                     // worst case: every (j1, t1) survives
+  w.cap_a_stop = g.n_jneg * g.n_ts;
+  w.cap_b = std::min(g.n_j1 * g.n_t1 * g.n_t2, 512);                  // (j1, t1, t2) prefixes: ~150 for the default grid
+  int keys = 1;
+  while (keys < cap_seeds) keys <<= 1;                                 // the sort works on a power of two
+  w.cap_keys = std::max(keys, 64);
+  return w;
+}
 
 }  // namespace
 
@@ -313,10 +340,6 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   h->stop_total = (uint32_t)((size_t)h->grids.n_jneg * h->grids.n_ts * h->grids.n_jpos * h->grids.n_ts);
 
   CKC(cudaMalloc(&h->d_seeds, (size_t)cfg->max_seeds * 10 * sizeof(double)));
-  CKC(cudaMalloc(&h->d_list_main, (size_t)SORT_CAP * sizeof(uint32_t)));
-  CKC(cudaMalloc(&h->d_list_stop, (size_t)SORT_CAP * sizeof(uint32_t)));
-  CKC(cudaMalloc(&h->d_seed_work, 4 * sizeof(int)));
-  CKC(cudaMemset(h->d_seed_work, 0, 4 * sizeof(int)));
   h->kpad = (cfg->max_knots + 1) & ~1;   // capacity; the per-scenario stride is set in jssp_set_refline
   CKC(cudaMalloc(&h->d_knot, ((size_t)cfg->max_knots + 2) * sizeof(double)));   // the kernels bulk-copy kpad = K rounded up to even
   CKC(cudaMalloc(&h->d_coef, (size_t)8 * h->kpad * sizeof(double)));
@@ -350,6 +373,10 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   h->h_best = reinterpret_cast<BestRecord*>(h->h_result);
   h->h_counts = reinterpret_cast<int*>(h->h_result + 48);
   h->h_best_traj = reinterpret_cast<double*>(h->h_result + 64);
+  h->seed_work = make_seed_work(h->grids, h->d_counts, h->d_seeds, cfg->max_seeds);
+  h->seed_smem = seed_smem_bytes(h->seed_work);
+  if (h->seed_smem > (size_t)h->max_smem_optin) return bail(JSSP_ERR_CAPACITY);
+  CKC(cudaFuncSetAttribute(seed_enum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CKC(cudaFuncSetAttribute(evaluate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CKC(cudaFuncSetAttribute(evaluate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CKC(cudaFuncSetAttribute(evaluate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
@@ -368,7 +395,7 @@ int32_t jssp_destroy(jssp_handle* h) {
   if (!h) return JSSP_OK;
   cudaSetDevice(h->device);
   void* dev[] = {h->d_time, h->d_j1, h->d_t1, h->d_t2, h->d_j3, h->d_t3, h->d_t4, h->d_jneg, h->d_jpos, h->d_ts, h->d_seeds,
-                 h->d_list_main, h->d_list_stop, h->d_seed_work, h->d_knot, h->d_coef, h->d_raw, h->d_broad, h->d_narrow, h->d_obs64, h->d_ext64, h->d_sint, h->d_probf, h->d_knot_xy, h->d_blk_cost, h->d_blk_idx, h->d_ticket, h->d_result};
+                 h->d_knot, h->d_coef, h->d_raw, h->d_broad, h->d_narrow, h->d_obs64, h->d_ext64, h->d_sint, h->d_probf, h->d_knot_xy, h->d_blk_cost, h->d_blk_idx, h->d_ticket, h->d_result};
   for (void* p : dev) if (p) cudaFree(p);
   if (h->h_result) cudaFreeHost(h->h_result);
   if (h->h_raw) cudaFreeHost(h->h_raw);
@@ -467,8 +494,7 @@ int32_t jssp_enumerate_seeds(jssp_handle* h, double s0, double v0, double a0, vo
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
   SeedState ss{s0, v0, a0};
-  SeedWork wk{h->d_list_main, h->d_list_stop, h->d_seed_work, h->d_counts, h->d_seeds, SORT_CAP, h->cfg.max_seeds, 4};
-  seed_enum_kernel<false><<<dim3(SEED_BLOCKS_SINGLE, 1), SEED_THREADS, 0, st>>>(h->grids, ss, nullptr, wk);
+  CK(launch_seed_enum<false>(h->grids, ss, nullptr, h->seed_work, 1, SEED_MAX_CLUSTER, SEED_THREADS, h->seed_smem, st));
   h->launches += 1;
   CK(cudaGetLastError());
   h->seeds_ready = true;
@@ -635,6 +661,7 @@ int64_t jssp_launch_count(const jssp_handle* h) { return h ? h->launches : 0; }
 #ifdef JSSP_PROFILE_PHASES
 /* profiling builds only (tools/phase_probe.py): device buffer [blocks][8] receiving per-block globaltimer stamps */
 int32_t jssp_debug_phase_buffer(jssp_handle* h, unsigned long long* dev) { if (!h) return JSSP_ERR_INVALID_ARG; h->phase_ts = dev; return JSSP_OK; }
+int32_t jssp_debug_seed_stamps(unsigned long long* host16) { return cudaMemcpyFromSymbol(host16, g_seed_ts, sizeof(g_seed_ts)) == cudaSuccess ? JSSP_OK : JSSP_ERR_CUDA; }
 #endif
 
 int32_t jssp_measure_fma_peak(int32_t device, int32_t bits, double* tflops) {
@@ -692,8 +719,9 @@ struct jssp_batch {
   double *d_obs64 = nullptr, *d_ext64 = nullptr;
   float* d_probf = nullptr;
   double* d_seeds = nullptr;
-  uint32_t *d_list_main = nullptr, *d_list_stop = nullptr;
-  int *d_work = nullptr, *d_counts = nullptr;
+  int* d_counts = nullptr;
+  SeedWork seed_work{};
+  size_t seed_smem = 0;
   double* d_blk_cost = nullptr;
   int* d_blk_idx = nullptr;
   unsigned int* d_ticket = nullptr;
@@ -733,8 +761,8 @@ int32_t jssp_batch_destroy(jssp_batch* b) {
   if (!b) return JSSP_OK;
   cudaSetDevice(b->device);
   void* dev[] = {b->d_knot, b->d_coef, b->d_raw_state, b->d_raw_size, b->d_raw_prob, b->d_gt_state, b->d_gt_size, b->d_raw_valid,
-                 b->d_gt_valid, b->d_broad, b->d_narrow, b->d_obs64, b->d_ext64, b->d_probf, b->d_seeds, b->d_list_main, b->d_list_stop,
-                 b->d_work, b->d_counts, b->d_blk_cost, b->d_blk_idx, b->d_ticket, b->d_best, b->d_best_traj, b->d_slots, b->d_bslots,
+                 b->d_gt_valid, b->d_broad, b->d_narrow, b->d_obs64, b->d_ext64, b->d_probf, b->d_seeds,
+                 b->d_counts, b->d_blk_cost, b->d_blk_idx, b->d_ticket, b->d_best, b->d_best_traj, b->d_slots, b->d_bslots,
                  b->d_slots0, b->d_bslots0, b->d_records, b->d_cycle_time, b->d_cycle_now, b->d_cycle_end};
   for (void* q : dev) if (q) cudaFree(q);
   for (double* q : b->d_grid) if (q) cudaFree(q);
@@ -795,12 +823,12 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   CKC(cudaMalloc(&b->d_ext64, S * b->n_om * 2 * sizeof(double)));
   CKC(cudaMalloc(&b->d_probf, S * b->n_om * sizeof(float)));
   CKC(cudaMalloc(&b->d_seeds, S * (size_t)cfg->max_seeds * 10 * sizeof(double)));
-  CKC(cudaMalloc(&b->d_list_main, S * SORT_CAP * sizeof(uint32_t)));
-  CKC(cudaMalloc(&b->d_list_stop, S * SORT_CAP * sizeof(uint32_t)));
-  CKC(cudaMalloc(&b->d_work, S * 4 * sizeof(int)));
-  CKC(cudaMemset(b->d_work, 0, S * 4 * sizeof(int)));
   CKC(cudaMalloc(&b->d_counts, S * 4 * sizeof(int)));
   CKC(cudaMemset(b->d_counts, 0, S * 4 * sizeof(int)));
+  b->seed_work = make_seed_work(b->grids, b->d_counts, b->d_seeds, cfg->max_seeds);
+  b->seed_smem = seed_smem_bytes(b->seed_work);
+  if (b->seed_smem > (size_t)b->max_smem_optin) return bail(JSSP_ERR_CAPACITY);
+  CKC(cudaFuncSetAttribute(seed_enum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->max_smem_optin));
   CKC(cudaMalloc(&b->d_blk_cost, S * b->max_blocks * sizeof(double)));
   CKC(cudaMalloc(&b->d_blk_idx, S * b->max_blocks * sizeof(int)));
   CKC(cudaMalloc(&b->d_ticket, S * sizeof(unsigned int)));
@@ -937,7 +965,6 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
   CKB(cudaMemcpyAsync(b->d_slots0 + s, &p, sizeof(p), cudaMemcpyHostToDevice, st));
   CKB(cudaMemcpyAsync(b->d_bslots0 + s, &q, sizeof(q), cudaMemcpyHostToDevice, st));
   CKB(cudaMemsetAsync(b->d_ticket + s, 0, sizeof(unsigned int), st));
-  CKB(cudaMemsetAsync(b->d_work + s * 4, 0, 4 * sizeof(int), st));
   CKB(cudaStreamSynchronize(st));   // soa, p, q are temporaries; the caller's arrays may be released
   b->max_K = std::max(b->max_K, K); b->max_kpad = std::max(b->max_kpad, kpad); b->max_OMpad = std::max(b->max_OMpad, OMpad);
   b->is_set[s] = 1;
@@ -953,7 +980,6 @@ int32_t jssp_batch_reset(jssp_batch* b, int32_t n_scenarios, void* stream) {
   CKB(cudaMemcpyAsync(b->d_slots, b->d_slots0, n * sizeof(EvalParams), cudaMemcpyDeviceToDevice, st));
   CKB(cudaMemcpyAsync(b->d_bslots, b->d_bslots0, n * sizeof(BatchSlot), cudaMemcpyDeviceToDevice, st));
   CKB(cudaMemsetAsync(b->d_ticket, 0, n * sizeof(unsigned int), st));
-  CKB(cudaMemsetAsync(b->d_work, 0, n * 4 * sizeof(int), st));
   return JSSP_OK;
 }
 
@@ -976,10 +1002,12 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   SmemLayout L = eval_smem_layout(max_rows, b->max_OMpad, mode, b->max_K, b->max_kpad, b->P, b->W);
   if (mode == 1 && L.total > (size_t)b->max_smem_optin) { mode = 0; L = eval_smem_layout(0, b->max_OMpad, 0, b->max_K, b->max_kpad, b->P, b->W); }
   if (!small && L.total > (size_t)b->max_smem_optin) return JSSP_ERR_CAPACITY;
-  const int seed_blocks = std::max(1, std::min(SEED_BLOCKS_SINGLE, 592 / n_scenarios));
-  SeedWork wk{b->d_list_main, b->d_list_stop, b->d_work, b->d_counts, b->d_seeds, SORT_CAP, b->cfg.max_seeds, 4};
+  // few scenarios: clusters of up to 8 CTAs x 1024 threads answer with the lowest latency; many: one 512-thread CTA each
+  int seed_cluster = 1;
+  while (seed_cluster < SEED_MAX_CLUSTER && n_scenarios * seed_cluster * 2 <= 148) seed_cluster *= 2;
+  const int seed_threads = n_scenarios >= 296 ? 512 : SEED_THREADS;
   for (int c = 0; c < n_cycles; ++c) {
-    seed_enum_kernel<true><<<dim3(seed_blocks, n_scenarios), SEED_THREADS, 0, st>>>(b->grids, SeedState{0, 0, 0}, b->d_slots, wk);
+    CKB(launch_seed_enum<true>(b->grids, SeedState{0, 0, 0}, b->d_slots, b->seed_work, n_scenarios, seed_cluster, seed_threads, b->seed_smem, st));
     if (small) evaluate_small_batch_kernel<<<dim3(b->blocks_warp, n_scenarios), SMALL_WARPS * 32, small_bytes, st>>>(b->d_slots);
     else if (group && mode == 1) evaluate_group_batch_kernel<1><<<dim3(blocks_group, n_scenarios), EVAL_THREADS, L.total, st>>>(b->d_slots);
     else if (group) evaluate_group_batch_kernel<0><<<dim3(blocks_group, n_scenarios), EVAL_THREADS, L.total, st>>>(b->d_slots);
