@@ -206,6 +206,26 @@ def replay_latency(device: int, cpu: bool = True) -> dict:
     return out
 
 
+def ncu_evidence(kernel_s=None) -> dict:
+    """Counters of the dominant kernel from the committed ncu capture (profiles/, `ncu --set full` of this very command):
+    evidence about the kernel measured under the profiler, never a bench value.  With ``kernel_s`` (the live kernel time)
+    the executed floating-point rate is expressed per second of the live run."""
+    path = os.path.join(ROOT, "profiles", "r01_evaluate_group_kernel_ncu.json")
+    if not os.path.exists(path):
+        return {}
+    d = json.load(open(path))
+    if kernel_s is None:
+        return d
+    out = {k: d.get(k) for k in ("issue_active_pct", "pipe_fp64_pct", "pipe_fma_pct", "pipe_alu_pct", "pipe_lsu_pct", "warps_active_pct",
+                                 "eligible_warps_per_cycle", "warp_instructions", "registers_per_thread")}
+    out["fp64_tflops"] = d.get("executed_fp64_flops", 0.0) / kernel_s / 1e12
+    out["fp32_tflops"] = d.get("executed_fp32_flops", 0.0) / kernel_s / 1e12
+    out["source"] = "profiles/r01_evaluate_group_kernel_ncu.json (ncu --set full, same command; counters under the profiler, rates over the live kernel time)"
+    out["reading"] = ("the kernel is issue/latency bound (about half of the issue slots used with 16 resident warps per SM at 128 registers); "
+                      "broad-phase culling removes almost all of the 48-flop rectangle tests that dominate the algorithmic count")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -339,8 +359,9 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "p50_cycle_ms": 1e3 * statistics.median(lat)},
                 "gpu_launches": int(launches), "clocks": sampler.summary(),
-                "roofline": {"bound": "fp32", "kernel": "evaluate_kernel", "achieved": achieved, "peak": peak32.value, "unit": "TFLOP/s",
-                             "frac": achieved / peak32.value if peak32.value else None, "traffic": None,
+                "roofline": {"bound": "fp32", "kernel": "evaluate_group_kernel", "achieved": achieved, "peak": peak32.value, "unit": "TFLOP/s",
+                             "frac": achieved / peak32.value if peak32.value else None, "traffic": ncu_evidence().get("dram_traffic_bytes"),
+                             "executed": ncu_evidence(k_avg_s),
                              "peak_source": "measured live: FFMA micro-benchmark in libjssp_b200 (MEASURED_PEAKS.json has no CUDA-core figure); "
                                             "fp64 FMA peak %.1f TFLOP/s" % peak64.value,
                              "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes,

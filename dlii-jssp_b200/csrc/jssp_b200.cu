@@ -245,9 +245,9 @@ SeedWork make_seed_work(const SeedGrids& g, int* counts, double* seeds, int cap_
   w.cap_a_main = g.n_j1 * g.n_t1;                                     // worst case: every (j1, t1) survives
   w.cap_a_stop = g.n_jneg * g.n_ts;
   w.cap_b = std::min(g.n_j1 * g.n_t1 * g.n_t2, 512);                  // (j1, t1, t2) prefixes: ~150 for the default grid
-  int keys = 1;
-  while (keys < cap_seeds) keys <<= 1;                                 // the sort works on a power of two
-  w.cap_keys = std::max(keys, 64);
+  int keys = 64;
+  while (keys < cap_seeds && keys < 4096) keys <<= 1;                  // the sort works on a power of two; the default grid yields < 1000 seeds
+  w.cap_keys = keys;
   return w;
 }
 
