@@ -13,8 +13,8 @@ print(f"generate {t1-t0:.2f}s pack {t2-t1:.2f}s for {n} scenarios")
 cfg = J.JsspConfig(max_seeds=1024, max_knots=max(len(p.knot_s) for p in packed), max_obstacle_modes=max(1, max(p.state.shape[0] for p in packed)),
                    max_total_steps=max(p.state.shape[2] for p in packed))
 bt = B.BatchReplay(cfg, max_scenarios=n, max_cycles=cyc)
-for kernel in (None, "thread", "warp"):
-    if kernel == "warp" and n > 64:
+for kernel in (None, "thread", "group", "warp"):
+    if kernel == "warp" and n > 256:
         continue
     t3 = time.perf_counter(); bt.load(packed); torch.cuda.synchronize(); t4 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
