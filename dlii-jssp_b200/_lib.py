@@ -120,7 +120,8 @@ _lib = None
 
 
 def library_path() -> str:
-    return _build.LIB
+    """In-tree libjssp_b200.so; JSSP_B200_LIB overrides it (A/B runs of two builds on the same box)."""
+    return os.environ.get("JSSP_B200_LIB") or _build.LIB
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:
