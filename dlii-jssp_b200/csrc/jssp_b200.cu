@@ -222,6 +222,18 @@ static int32_t measure_fma(int device, double* tflops) {
   return JSSP_OK;
 }
 
+// opt a kernel in to the largest dynamic shared memory the device allows next to the kernel's own static shared memory;
+// *budget is lowered to the smallest such limit seen (the host sizes launches against it)
+template <class F>
+cudaError_t allow_max_dynamic_smem(F* func, int optin, int* budget) {
+  cudaFuncAttributes a;
+  cudaError_t e = cudaFuncGetAttributes(&a, func);
+  if (e != cudaSuccess) return e;
+  const int dyn = optin - (int)a.sharedSizeBytes - 256;
+  if (dyn < *budget) *budget = dyn;
+  return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+}
+
 // launch of the seed enumeration: n_scenarios clusters of `csize` CTAs
 template <bool kBatch>
 cudaError_t launch_seed_enum(const SeedGrids& g, SeedState ss, const EvalParams* slots, const SeedWork& wk, int n_scenarios, int csize,
@@ -328,8 +340,9 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
     if (e__ != cudaSuccess) { fprintf(stderr, "jssp_create: %s: %s\n", #call, cudaGetErrorString(e__)); return bail(JSSP_ERR_CUDA); } \
   } while (0)
   CKC(cudaSetDevice(device));
-  CKC(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  h->max_smem_optin -= 1024;   // static shared memory of the kernels + slack
+  int optin = 0;
+  CKC(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  h->max_smem_optin = optin;   // lowered below to the tightest per-kernel limit (device limit - the kernel's static shared memory)
   {
     double** slots[10] = {&h->d_time, &h->d_j1, &h->d_t1, &h->d_t2, &h->d_j3, &h->d_t3, &h->d_t4, &h->d_jneg, &h->d_jpos, &h->d_ts};
     int n_time = 0;
@@ -376,15 +389,15 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   h->seed_work = make_seed_work(h->grids, h->d_counts, h->d_seeds, cfg->max_seeds);
   h->seed_smem = seed_smem_bytes(h->seed_work);
   if (h->seed_smem > (size_t)h->max_smem_optin) return bail(JSSP_ERR_CAPACITY);
-  CKC(cudaFuncSetAttribute(seed_enum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  CKC(cudaFuncSetAttribute(evaluate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  CKC(cudaFuncSetAttribute(evaluate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  CKC(cudaFuncSetAttribute(evaluate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  CKC(cudaFuncSetAttribute(evaluate_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  CKC(cudaFuncSetAttribute(evaluate_group_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  CKC(cudaFuncSetAttribute(evaluate_group_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  CKC(cudaFuncSetAttribute(evaluate_group_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  CKC(cudaFuncSetAttribute(dump_states_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CKC(allow_max_dynamic_smem(seed_enum_kernel<false>, optin, &h->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_kernel<0>, optin, &h->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_kernel<1>, optin, &h->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_kernel<2>, optin, &h->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_small_kernel, optin, &h->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_group_kernel<0>, optin, &h->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_group_kernel<1>, optin, &h->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_group_kernel<2>, optin, &h->max_smem_optin));
+  CKC(allow_max_dynamic_smem(dump_states_kernel, optin, &h->max_smem_optin));
   CKC(cudaDeviceSynchronize());
 #undef CKC
   *out = h;
@@ -790,8 +803,9 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
     if (e__ != cudaSuccess) { fprintf(stderr, "jssp_batch_create: %s: %s\n", #call, cudaGetErrorString(e__)); return bail(JSSP_ERR_CUDA); } \
   } while (0)
   CKC(cudaSetDevice(device));
-  CKC(cudaDeviceGetAttribute(&b->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  b->max_smem_optin -= 4096;   // static shared memory of the batch kernels (parameter record, reduction scratch) + slack
+  int optin = 0;
+  CKC(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  b->max_smem_optin = optin;   // lowered below to the tightest per-kernel limit
   {
     double** slots[10];
     for (int k = 0; k < 10; ++k) slots[k] = &b->d_grid[k];
@@ -828,7 +842,7 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   b->seed_work = make_seed_work(b->grids, b->d_counts, b->d_seeds, cfg->max_seeds);
   b->seed_smem = seed_smem_bytes(b->seed_work);
   if (b->seed_smem > (size_t)b->max_smem_optin) return bail(JSSP_ERR_CAPACITY);
-  CKC(cudaFuncSetAttribute(seed_enum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->max_smem_optin));
+  CKC(allow_max_dynamic_smem(seed_enum_kernel<true>, optin, &b->max_smem_optin));
   CKC(cudaMalloc(&b->d_blk_cost, S * b->max_blocks * sizeof(double)));
   CKC(cudaMalloc(&b->d_blk_idx, S * b->max_blocks * sizeof(int)));
   CKC(cudaMalloc(&b->d_ticket, S * sizeof(unsigned int)));
@@ -847,11 +861,11 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   CKC(cudaMalloc(&b->d_cycle_now, S * (size_t)(b->C + 1) * sizeof(int)));
   CKC(cudaMalloc(&b->d_cycle_end, S * (size_t)(b->C + 1) * sizeof(int)));
   b->is_set.assign(S, 0);
-  CKC(cudaFuncSetAttribute(evaluate_batch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->max_smem_optin));
-  CKC(cudaFuncSetAttribute(evaluate_batch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->max_smem_optin));
-  CKC(cudaFuncSetAttribute(evaluate_small_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->max_smem_optin));
-  CKC(cudaFuncSetAttribute(evaluate_group_batch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->max_smem_optin));
-  CKC(cudaFuncSetAttribute(evaluate_group_batch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_batch_kernel<0>, optin, &b->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_batch_kernel<1>, optin, &b->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_small_batch_kernel, optin, &b->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_group_batch_kernel<0>, optin, &b->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_group_batch_kernel<1>, optin, &b->max_smem_optin));
   CKC(cudaDeviceSynchronize());
 #undef CKC
   *out = b;

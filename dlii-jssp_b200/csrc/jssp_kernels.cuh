@@ -1053,8 +1053,67 @@ __device__ __forceinline__ bool lex_less(double ca, int ia, double cb, int ib) {
 // lon_eval / frenet_point arithmetic as the evaluation walk (bisect and walk select the same spline segment), headings are
 // the float64 arctan2 of the forward differences exactly as jerk_space_sampling_planner.py:155-165 derives them.
 // `out` (global, [P][16]) doubles as the exchange buffer between the phases.
+__device__ __forceinline__ void export_block_global(const EvalParams& p, const BlockTables& tb, int best, double* __restrict__ out,
+                                                    int* sm_npts);
+
+// Fast form for P <= EXPORT_MAX_P samples and blockDim >= P: thread i owns sample i, neighbours are exchanged through
+// shared memory and every row is written to global memory once.  Same expressions as export_block_global.
+constexpr int EXPORT_MAX_P = 128;
 __device__ __forceinline__ void export_block(const EvalParams& p, const BlockTables& tb, int best, double* __restrict__ out,
                                              int* sm_npts) {
+  const int P = p.P, i = threadIdx.x;
+  if (P > EXPORT_MAX_P || (int)blockDim.x < P) { export_block_global(p, tb, best, out, sm_npts); return; }
+  __shared__ double ex[6][EXPORT_MAX_P];          // x, y, yaw, ds, c, c_d
+  const int Ns = resolve_n_seeds(p);
+  const int w = best / Ns, k = best - w * Ns;
+  const double* lat = tb.lat + (size_t)w * P * 4;
+  if (i == 0) *sm_npts = P;
+  __syncthreads();
+  const double nanv = nan("");
+  double row[JSSP_TRAJ_COLS];
+  if (i < P) {
+    LonProfile lp;
+    lon_profile_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
+    lon_eval(lp, p.s0, p.v0, p.a0, tb.time[i], row[1], row[2], row[3], row[4]);
+    row[0] = tb.time[i];
+    row[5] = lat[i * 4]; row[6] = lat[i * 4 + 1]; row[7] = lat[i * 4 + 2]; row[8] = lat[i * 4 + 3];
+#pragma unroll
+    for (int c = 9; c < JSSP_TRAJ_COLS; ++c) row[c] = nanv;
+    if (!spline_in_range(tb.sp, row[1])) atomicMin(sm_npts, i);   // first sample off the reference line ends the Cartesian path (:138-139)
+  }
+  __syncthreads();
+  const int np = *sm_npts;
+  if (i < np) {
+    frenet_point(tb.sp, spline_bisect(tb.sp, row[1]), row[1], lat[i * 4], row[9], row[10]);
+    ex[0][i] = row[9]; ex[1][i] = row[10];
+  }
+  __syncthreads();
+  if (i + 1 < np) {
+    const double dx = ex[0][i + 1] - row[9], dy = ex[1][i + 1] - row[10];
+    const double q = dx * dx + dy * dy;
+    row[11] = heading_of(dx, dy);
+    row[12] = (q > 1e-200 && q < 1e200) ? q * rsqrt(q) : hypot(dx, dy);
+    ex[2][i] = row[11];
+  }
+  __syncthreads();
+  if (np >= 2 && i == np - 1) { row[11] = ex[2][np - 2]; ex[2][i] = row[11]; }     // yaw[-1] repeated (:158-160)
+  __syncthreads();
+  if (i + 1 < np) { row[13] = (ex[2][i + 1] - row[11]) / row[12]; ex[4][i] = row[13]; }
+  __syncthreads();
+  const double dt = tb.time[1] - tb.time[0];
+  if (i + 2 < np) { row[14] = (ex[4][i + 1] - row[13]) / dt; ex[5][i] = row[14]; }
+  __syncthreads();
+  if (i + 3 < np) row[15] = (ex[5][i + 1] - row[14]) / dt;
+  if (i < P) {
+    double* r = out + (size_t)i * JSSP_TRAJ_COLS;
+#pragma unroll
+    for (int c = 0; c < JSSP_TRAJ_COLS; ++c) r[c] = row[c];
+  }
+  if (i == 0) p.best->n_pts = np;
+}
+
+__device__ __forceinline__ void export_block_global(const EvalParams& p, const BlockTables& tb, int best, double* __restrict__ out,
+                                                    int* sm_npts) {
   const int P = p.P, i = threadIdx.x;
   const int Ns = resolve_n_seeds(p);
   const int w = best / Ns, k = best - w * Ns;
