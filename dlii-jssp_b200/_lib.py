@@ -105,6 +105,7 @@ SYMBOLS = {
     "jssp_imm_update": (C.c_int32, [C.c_void_p, C.POINTER(JsspImmParams)] + [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_void_p]),
     "jssp_predict_modes": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "jssp_project_states": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]),
     "jssp_batch_create": (C.c_int32, [C.POINTER(JsspConfigC), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "jssp_batch_destroy": (C.c_int32, [C.c_void_p]),
     "jssp_batch_last_cuda_error": (C.c_char_p, [C.c_void_p]),

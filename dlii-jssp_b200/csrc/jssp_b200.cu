@@ -33,7 +33,7 @@ struct jssp_handle {
   // reference line
   double *d_knot = nullptr, *d_coef = nullptr;
   int K = 0, kpad = 0;
-  double ox = 0, oy = 0;
+  double ox = 0, oy = 0, s_end = 0;
   // obstacles
   unsigned char *d_raw = nullptr, *h_raw = nullptr;   // one device block + pinned staging block: [state | size | prob | valid]
   size_t raw_bytes = 0;
@@ -450,6 +450,7 @@ int32_t jssp_set_refline(jssp_handle* h, const double* knot_s, const double* coe
   CK(cudaMemcpyAsync(h->d_knot_xy, kxy.data(), kxy.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaStreamSynchronize(st));   // soa, kxy are temporaries
   h->K = K;
+  h->s_end = knot_s[K - 1];
   h->cull_ok = std::isfinite(gmax) && gmax < 8.0;
   h->cull_reach = h->cfg.max_road_width + gmax * hmax;   // lateral cap + longest knot-to-knot arc (+ radii, added per obstacle)
   h->cull_ds = hmax;
@@ -682,6 +683,20 @@ int32_t jssp_measure_fma_peak(int32_t device, int32_t bits, double* tflops) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return JSSP_ERR_NO_DEVICE; }
   return bits == 32 ? measure_fma<float>(device, tflops) : measure_fma<double>(device, tflops);
+}
+
+int32_t jssp_project_states(jssp_handle* h, const double* state_dev, int32_t n, double step, double* frenet_dev, void* stream) {
+  if (!h || n < 0 || !(step > 0) || (n > 0 && (!state_dev || !frenet_dev))) return JSSP_ERR_INVALID_ARG;
+  if (h->K < 2) return JSSP_ERR_NOT_READY;
+  if (n == 0) return JSSP_OK;
+  CK(cudaSetDevice(h->device));
+  // samples of np.arange(0, s_end, step): ceil(s_end / step)
+  const int n_samples = (int)std::ceil(h->s_end / step);
+  if (n_samples < 1) return JSSP_ERR_INVALID_ARG;
+  project_states_kernel<<<n, PROJECT_THREADS, 0, (cudaStream_t)stream>>>(h->d_knot, h->d_coef, h->K, h->kpad, step, n_samples, state_dev, frenet_dev);
+  h->launches++;
+  CK(cudaGetLastError());
+  return JSSP_OK;
 }
 
 int32_t jssp_imm_update(jssp_handle* h, const jssp_imm_params* prm, double* mean_dev, double* cov_dev, double* mu_dev,

@@ -1636,6 +1636,90 @@ __global__ void best_record_kernel(const BestRecord* __restrict__ best, long lon
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// K5: batched Cartesian -> Frenet projection: FrenetState.from_state(state, polyline) as the
+// driver uses it at t <= 0.05 and in kinematics mode (intersection_planner.py:140-142, 308-310).  The class is absent from
+// the reference tree; the specification is dlii-jssp_b200/frenet.py::FrenetState.from_state: nearest point of the
+// reference line re-discretised every `step` metres (generate_frenet_frame, jssp.py:366-371), arc length = sum of the chord
+// lengths up to it plus the tangential offset, signed lateral offset by the left-hand normal, speed / acceleration split
+// by the heading error.  One block per state: threads stride over the polyline samples.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int PROJECT_THREADS = 256;
+__global__ void __launch_bounds__(PROJECT_THREADS) project_states_kernel(const double* __restrict__ knot, const double* __restrict__ coef,
+                                                                         int K, int kpad, double step, int n_samples,
+                                                                         const double* __restrict__ state, double* __restrict__ frenet) {
+  __shared__ double red_d[PROJECT_THREADS / 32];
+  __shared__ int red_i[PROJECT_THREADS / 32];
+  __shared__ double red_s[PROJECT_THREADS / 32];
+  __shared__ int best_i;
+  const double* st = state + (size_t)blockIdx.x * 5;        // x, y, yaw, v, a
+  const double px = st[0], py = st[1];
+  SplineView sp{knot, coef, K, kpad, (double)(K - 1) / knot[K - 1]};
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // 1) nearest sample (first occurrence on ties, like numpy.argmin)
+  double bd = INFINITY;
+  int bi = -1;
+  for (int m = tid; m < n_samples; m += blockDim.x) {
+    const double s = (double)m * step;
+    double x, y;
+    frenet_point(sp, spline_bisect(sp, s), s, 0.0, x, y);
+    const double d2 = (x - px) * (x - px) + (y - py) * (y - py);
+    if (d2 < bd) { bd = d2; bi = m; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double od = __shfl_down_sync(0xffffffffu, bd, o);
+    const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+    if (oi >= 0 && (bi < 0 || od < bd || (od == bd && oi < bi))) { bd = od; bi = oi; }
+  }
+  if (lane == 0) { red_d[wid] = bd; red_i[wid] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int q = 1; q < (int)(blockDim.x >> 5); ++q)
+      if (red_i[q] >= 0 && (bi < 0 || red_d[q] < bd || (red_d[q] == bd && red_i[q] < bi))) { bd = red_d[q]; bi = red_i[q]; }
+    best_i = bi;
+  }
+  __syncthreads();
+  const int ib = best_i;
+  // 2) arc length of the polyline up to the nearest sample
+  double acc = 0.0;
+  for (int m = tid; m < ib; m += blockDim.x) {
+    const double s0 = (double)m * step, s1 = (double)(m + 1) * step;
+    double x0, y0, x1, y1;
+    frenet_point(sp, spline_bisect(sp, s0), s0, 0.0, x0, y0);
+    frenet_point(sp, spline_bisect(sp, s1), s1, 0.0, x1, y1);
+    acc = acc + hypot(x1 - x0, y1 - y0);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc = acc + __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane == 0) red_s[wid] = acc;
+  __syncthreads();
+  if (tid != 0) return;
+  for (int q = 1; q < (int)(blockDim.x >> 5); ++q) acc = acc + red_s[q];
+  // 3) projection on the tangent / left-hand normal of the nearest sample
+  const double sb = (double)ib * step;
+  const int seg = spline_bisect(sp, sb);
+  double rx, ry;
+  frenet_point(sp, seg, sb, 0.0, rx, ry);
+  const double h = sb - knot[seg];
+  const double* c = coef + seg;
+  const double tx = (c[kpad] + (2.0 * c[2 * kpad]) * h) + (3.0 * c[3 * kpad]) * (h * h);
+  const double ty = (c[5 * kpad] + (2.0 * c[6 * kpad]) * h) + (3.0 * c[7 * kpad]) * (h * h);
+  const double ryaw = atan2(ty, tx);
+  double sy, cy;
+  sincos(ryaw, &sy, &cy);
+  const double dx = px - rx, dy = py - ry;
+  double sdy, cdy;
+  sincos(st[2] - ryaw, &sdy, &cdy);
+  double* o = frenet + (size_t)blockIdx.x * 6;              // s, s_d, s_dd, d, d_d, d_dd
+  o[0] = acc + (dx * cy + dy * sy);
+  o[1] = st[3] * cdy;
+  o[2] = st[4] * cdy;
+  o[3] = -dx * sy + dy * cy;
+  o[4] = st[3] * sdy;
+  o[5] = st[4] * sdy;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // K4: batched IMM lane-intention update (builder-specified; no reference code exists)
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int IMM_MAX_MODES = 8;

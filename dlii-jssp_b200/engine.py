@@ -260,6 +260,15 @@ class JsspEngine:
         self._check(self.lib.jssp_best_record_dev(self._h, int(index_offset), self.stream, rec.data_ptr()), "jssp_best_record_dev")
         return rec
 
+    def project_states(self, states: torch.Tensor, step: float = 0.1) -> torch.Tensor:
+        """Batched FrenetState.from_state on the uploaded reference line: states [n, 5] = x, y, yaw, v, a (device, float64)
+        -> [n, 6] = s, s_d, s_dd, d, d_d, d_dd (device)."""
+        assert states.is_cuda and states.dtype == torch.float64 and states.is_contiguous() and states.shape[-1] == 5
+        out = torch.empty((states.shape[0], 6), dtype=torch.float64, device=self.device)
+        self._check(self.lib.jssp_project_states(self._h, states.data_ptr(), states.shape[0], float(step), out.data_ptr(), self.stream),
+                    "jssp_project_states")
+        return out
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.jssp_launch_count(self._h))

@@ -192,6 +192,13 @@ int32_t jssp_predict_modes(jssp_handle* h, const double* lanes_dev, int32_t L, i
                            const double* s_start_dev, const double* speed_dev, double dt, int32_t O, int32_t M,
                            int32_t Tt, double* state_dev, uint8_t* valid_dev, void* stream);
 
+/* -- batched Cartesian -> Frenet projection ------------------------------------------
+ * replaces FrenetState().from_state(ego_state, ref_ego_lane_pts) (intersection_planner.py:140-142, 308-310) for n states
+ * at once on the handle's reference line re-discretised every `step` metres (0.1 in jssp.py:366): state_dev [n][5] =
+ * x, y, yaw, v, a -> frenet_dev [n][6] = s, s_d, s_dd, d, d_d, d_dd (both device pointers).  The class is absent from the
+ * reference tree; dlii-jssp_b200/frenet.py documents the formulation. */
+int32_t jssp_project_states(jssp_handle* h, const double* state_dev, int32_t n, double step, double* frenet_dev, void* stream);
+
 /* -- batched, device-resident replay ------------------------------------------------
  * Replaces the per-scenario driver loop of code/__main__.py:124-167 for MANY independent scenarios at once: in every
  * step all running scenarios execute one plan cycle (seed enumeration -> evaluation -> selection -> export) and the

@@ -60,3 +60,23 @@ def test_predicted_modes_feed_the_collision_check():
     H.compare_cycle(res, ref)
     assert ref["collision"].any() and not ref["collision"].all() and (ref["risk"] > 0).any()
     eng.close()
+
+
+def test_batched_frenet_projection_matches_host_from_state(scenario_fixture):
+    """jssp_project_states against FrenetState.from_state (the host formulation the replay uses for cycle 0) on the bundled
+    route and on a synthetic turn: states scattered around the reference line, all headings."""
+    from dlii_jssp_b200 import scenario as S
+    rng = np.random.default_rng(4)
+    for route in (scenario_fixture.route_xy, S.synthetic_intersection(0).route_xy):
+        sp = J.CubicSpline2D(route[:, 0], route[:, 1])
+        ref = sp.sample(np.arange(0, sp.s_list[-1], 0.1))
+        eng = J.JsspEngine(J.JsspConfig(max_knots=512))
+        eng.set_refline(sp.s_list, sp.coefficient_table())
+        k = rng.integers(0, len(ref), 64)
+        st = np.column_stack([ref[k, 0] + rng.normal(0, 1.5, 64), ref[k, 1] + rng.normal(0, 1.5, 64), rng.uniform(-np.pi, np.pi, 64),
+                              rng.uniform(0, 15, 64), rng.normal(0, 2, 64)])
+        st[0] = (ref[0, 0], ref[0, 1], ref[0, 2], 5.0, 0.0)                       # exactly on the first sample
+        got = eng.project_states(torch.from_numpy(st).cuda()).cpu().numpy()
+        want = np.array([J.FrenetState().from_state(J.State(0.0, *row), ref).as_tuple() for row in st])
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9)
+        eng.close()
