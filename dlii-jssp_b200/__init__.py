@@ -14,9 +14,10 @@ from .planner import (JerkSpaceSamplingPlanner, JerkSpaceSamplingPlannerSettings
 from . import scenario
 from . import distributed
 from . import replay
+from .fop import FrenetOptimalPlanner, FrenetOptimalPlannerSettings, GoalSamplingFrenetTrajectory
 from . import batch
 from .batch import BatchReplay, PackedScenario, pack_scenario, run_batch
 
 __all__ = ["JsspConfig", "JsspEngine", "CycleResult", "JsspError", "State", "FrenetState", "JerkSpaceSamplingFrenetTrajectory", "Vehicle",
            "CubicSpline2D", "QuinticPolynomial", "spline_tables", "JerkSpaceSamplingPlanner", "JerkSpaceSamplingPlannerSettings",
-           "IntersectionPlanner", "PlannerSettings", "scenario", "distributed", "replay", "batch", "BatchReplay", "PackedScenario", "pack_scenario", "run_batch", "TRAJ_COLUMNS", "STATE_COLUMNS"]
+           "IntersectionPlanner", "PlannerSettings", "scenario", "distributed", "replay", "FrenetOptimalPlanner", "FrenetOptimalPlannerSettings", "GoalSamplingFrenetTrajectory", "batch", "BatchReplay", "PackedScenario", "pack_scenario", "run_batch", "TRAJ_COLUMNS", "STATE_COLUMNS"]

@@ -55,6 +55,13 @@ class JsspCycleOut(C.Structure):
     ]
 
 
+class JsspFopIn(C.Structure):
+    _fields_ = [("s0", C.c_double), ("v0", C.c_double), ("a0", C.c_double), ("d0", C.c_double), ("d_d0", C.c_double), ("d_dd0", C.c_double),
+                ("time_step_now", C.c_int32), ("final_time_step", C.c_int32), ("num_width", C.c_int32), ("num_speed", C.c_int32),
+                ("num_t", C.c_int32), ("flags", C.c_int32), ("min_t", C.c_double), ("max_t", C.c_double),
+                ("lowest_speed", C.c_double), ("highest_speed", C.c_double), ("max_accel", C.c_double), ("max_jerk", C.c_double)]
+
+
 class JsspImmParams(C.Structure):
     _fields_ = [("dt", C.c_double), ("q_pos", C.c_double), ("q_vel", C.c_double), ("r_pos", C.c_double),
                 ("k_lat", C.c_double), ("p_stay", C.c_double), ("mu_floor", C.c_double)]
@@ -105,6 +112,7 @@ SYMBOLS = {
     "jssp_imm_update": (C.c_int32, [C.c_void_p, C.POINTER(JsspImmParams)] + [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_void_p]),
     "jssp_predict_modes": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "jssp_fop_evaluate": (C.c_int32, [C.c_void_p, C.POINTER(JsspFopIn), C.c_void_p, C.POINTER(JsspCycleOut)]),
     "jssp_project_states": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]),
     "jssp_batch_create": (C.c_int32, [C.POINTER(JsspConfigC), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "jssp_batch_destroy": (C.c_int32, [C.c_void_p]),

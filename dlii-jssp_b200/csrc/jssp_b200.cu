@@ -65,6 +65,9 @@ struct jssp_handle {
   int last_flags = 0;
   int64_t launches = 0;
   int max_smem_optin = 0;
+  double* d_fop_tab = nullptr;              // FOP grids: horizons | speeds, then n_samples (int) in d_fop_int
+  int* d_fop_int = nullptr;
+  int fop_cap_t = 0, fop_cap_v = 0;
   unsigned long long* phase_ts = nullptr;   // profiling builds only
   char cuda_err[256] = {0};
 };
@@ -398,6 +401,8 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(allow_max_dynamic_smem(evaluate_group_kernel<1>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_group_kernel<2>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(dump_states_kernel, optin, &h->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_fop_kernel, optin, &h->max_smem_optin));
+  CKC(allow_max_dynamic_smem(fop_select_export_kernel, optin, &h->max_smem_optin));
   CKC(cudaDeviceSynchronize());
 #undef CKC
   *out = h;
@@ -411,6 +416,8 @@ int32_t jssp_destroy(jssp_handle* h) {
                  h->d_knot, h->d_coef, h->d_raw, h->d_broad, h->d_narrow, h->d_obs64, h->d_ext64, h->d_sint, h->d_probf, h->d_knot_xy, h->d_blk_cost, h->d_blk_idx, h->d_ticket, h->d_result};
   for (void* p : dev) if (p) cudaFree(p);
   if (h->h_result) cudaFreeHost(h->h_result);
+  if (h->d_fop_tab) cudaFree(h->d_fop_tab);
+  if (h->d_fop_int) cudaFree(h->d_fop_int);
   if (h->h_raw) cudaFreeHost(h->h_raw);
   if (h->raw_done) cudaEventDestroy(h->raw_done);
   delete h;
@@ -683,6 +690,73 @@ int32_t jssp_measure_fma_peak(int32_t device, int32_t bits, double* tflops) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return JSSP_ERR_NO_DEVICE; }
   return bits == 32 ? measure_fma<float>(device, tflops) : measure_fma<double>(device, tflops);
+}
+
+int32_t jssp_fop_evaluate(jssp_handle* h, const jssp_fop_in* in, void* stream, jssp_cycle_out* out) {
+  if (!h || !in || !out) return JSSP_ERR_INVALID_ARG;
+  if (h->K < 2 || !h->obs_set) return JSSP_ERR_NOT_READY;
+  const jssp_config& c = h->cfg;
+  if (in->num_width < 1 || in->num_width > JSSP_MAX_WIDTHS || in->num_speed < 1 || in->num_t < 1 || !(in->min_t > 0) || !(in->max_t >= in->min_t) ||
+      in->time_step_now < 0)
+    return JSSP_ERR_INVALID_ARG;
+  if (in->max_t > c.plan_horizon + 1e-9) return JSSP_ERR_CAPACITY;      // the handle's sample capacity follows plan_horizon
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  int rc = pack_if_dirty(h, st);
+  if (rc != JSSP_OK) return rc;
+  const int W = in->num_width, NT = in->num_t, NV = in->num_speed;
+  const long long N = (long long)W * NT * NV;
+  const int blocks = (int)((N + EVAL_THREADS - 1) / EVAL_THREADS);
+  if (blocks > h->max_blocks) return JSSP_ERR_CAPACITY;
+  // grids: np.linspace(min_t, max_t, num_t), np.linspace(lowest, highest, num_speed), len(np.arange(0, T, dt)) = ceil(T / dt)
+  std::vector<double> tab = np_linspace(in->min_t, in->max_t, NT);
+  std::vector<int> ns((size_t)NT);
+  for (int i = 0; i < NT; ++i) {
+    ns[i] = (int)std::ceil((tab[i] - 0.0) / c.delta_t);
+    if (ns[i] < 1 || ns[i] > h->P) return JSSP_ERR_CAPACITY;
+  }
+  const std::vector<double> sp = np_linspace(in->lowest_speed, in->highest_speed, NV);
+  tab.insert(tab.end(), sp.begin(), sp.end());
+  if (NT > h->fop_cap_t || NV > h->fop_cap_v) {                          // first FOP call on this handle (or a larger grid)
+    CK(cudaStreamSynchronize(st));
+    if (h->d_fop_tab) cudaFree(h->d_fop_tab);
+    if (h->d_fop_int) cudaFree(h->d_fop_int);
+    h->fop_cap_t = std::max(NT, h->fop_cap_t); h->fop_cap_v = std::max(NV, h->fop_cap_v);
+    CK(cudaMalloc(&h->d_fop_tab, (size_t)(h->fop_cap_t + h->fop_cap_v) * sizeof(double)));
+    CK(cudaMalloc(&h->d_fop_int, (size_t)h->fop_cap_t * sizeof(int)));
+  }
+  CK(cudaMemcpyAsync(h->d_fop_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_fop_int, ns.data(), ns.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));                                          // tab, ns are temporaries
+
+  FopParams fp{};
+  EvalParams& p = fp.base;
+  fill_constants(p, c, h->P);
+  p.s0 = in->s0; p.v0 = in->v0; p.a0 = in->a0;
+  p.W = W; p.now = in->time_step_now; p.tcap = in->final_time_step - in->time_step_now; p.n_dict = h->n_dict;
+  p.time = h->d_time; p.knot = h->d_knot; p.coef = h->d_coef; p.K = h->K; p.kpad = h->kpad; p.ox = h->ox; p.oy = h->oy;
+  p.seeds = nullptr; p.n_seeds_ptr = nullptr; p.n_seeds_fixed = NT * NV; p.seed_cap = c.max_seeds;
+  p.broad = h->d_broad; p.narrow = h->d_narrow; p.obs64 = h->d_obs64; p.ext64 = h->d_ext64;
+  p.OM = h->O * h->M; p.OMpad = (p.OM + 31) & ~31; p.Tt = h->Tt;
+  p.win_rows = 0; p.smem_obs = 0; p.sint = h->d_sint; p.probf = h->d_probf; p.list_cap = 0;
+  p.feasible = out->feasible_dev; p.collision = out->collision_dev; p.cost = out->cost_dev;
+  p.blk_cost = h->d_blk_cost; p.blk_idx = h->d_blk_idx; p.ticket = h->d_ticket; p.best = h->d_best;
+  p.best_traj = (in->flags & JSSP_FLAG_NO_EXPORT) ? nullptr : h->d_best_traj;
+  fp.num_t = NT; fp.num_speed = NV;
+  fp.horizon = h->d_fop_tab; fp.speed = h->d_fop_tab + NT; fp.n_samples = h->d_fop_int;
+  fp.d0 = in->d0; fp.d_d0 = in->d_d0; fp.d_dd0 = in->d_dd0;
+  const std::vector<double> tg = default_targets(c, W);                   // :99-101, same expression as the JSSP lateral grid
+  for (int w = 0; w < W; ++w) fp.targets[w] = tg[w];
+  fp.dt = c.delta_t; fp.max_accel = in->max_accel; fp.max_jerk = in->max_jerk; fp.t_min = in->min_t; fp.t_max = in->max_t;
+  const FopSmem L = fop_smem_layout(p.K, p.kpad, p.P, W, NT);
+  if (L.total > (size_t)h->max_smem_optin) return JSSP_ERR_CAPACITY;
+  evaluate_fop_kernel<<<blocks, EVAL_THREADS, L.total, st>>>(fp);
+  fop_select_export_kernel<<<1, EVAL_THREADS, L.total, st>>>(fp, blocks);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  h->last = p; h->last_valid = true; h->last_flags = in->flags;
+  if (in->flags & JSSP_FLAG_NO_SYNC) return JSSP_OK;
+  return jssp_fetch_best(h, stream, out);
 }
 
 int32_t jssp_project_states(jssp_handle* h, const double* state_dev, int32_t n, double step, double* frenet_dev, void* stream) {

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import JsspError, JsspConfigC, JsspCycleIn, JsspCycleOut, JsspImmParams, FLAG_NO_SYNC, FLAG_NO_EXPORT, FLAG_NO_CULL, FLAG_ENUMERATE, FLAG_FORCE_WARP, FLAG_FORCE_THREAD, FLAG_FORCE_GROUP, TRAJ_COLUMNS
+from ._lib import JsspError, JsspConfigC, JsspCycleIn, JsspCycleOut, JsspFopIn, JsspImmParams, FLAG_NO_SYNC, FLAG_NO_EXPORT, FLAG_NO_CULL, FLAG_ENUMERATE, FLAG_FORCE_WARP, FLAG_FORCE_THREAD, FLAG_FORCE_GROUP, TRAJ_COLUMNS
 
 
 @dataclass
@@ -259,6 +259,24 @@ class JsspEngine:
         rec = torch.empty(2, dtype=torch.int64, device=self.device)
         self._check(self.lib.jssp_best_record_dev(self._h, int(index_offset), self.stream, rec.data_ptr()), "jssp_best_record_dev")
         return rec
+
+    def evaluate_fop(self, frenet0, time_step_now: int, final_time_step: int, num_width: int, num_speed: int, num_t: int, min_t: float,
+                     max_t: float, lowest_speed: float, highest_speed: float, max_accel: float, max_jerk: float,
+                     export: bool = True) -> CycleResult:
+        """One plan cycle of the FOP baseline (jssp_fop_evaluate): candidate n = (w * num_t + it) * num_speed + iv."""
+        fin = JsspFopIn()
+        fin.s0, fin.v0, fin.a0, fin.d0, fin.d_d0, fin.d_dd0 = [float(v) for v in frenet0]
+        fin.time_step_now, fin.final_time_step = int(time_step_now), int(final_time_step)
+        fin.num_width, fin.num_speed, fin.num_t = int(num_width), int(num_speed), int(num_t)
+        fin.flags = 0 if export else FLAG_NO_EXPORT
+        fin.min_t, fin.max_t, fin.lowest_speed, fin.highest_speed = float(min_t), float(max_t), float(lowest_speed), float(highest_speed)
+        fin.max_accel, fin.max_jerk = float(max_accel), float(max_jerk)
+        self._alloc(num_width * num_speed * num_t)
+        cout = JsspCycleOut()
+        cout.feasible_dev, cout.collision_dev, cout.cost_dev = self.feasible.data_ptr(), self.collision.data_ptr(), self.cost.data_ptr()
+        cout.best_traj_host = self._best_host.ctypes.data
+        self._check(self.lib.jssp_fop_evaluate(self._h, C.byref(fin), self.stream, C.byref(cout)), "jssp_fop_evaluate")
+        return self._result(cout, False, export)
 
     def project_states(self, states: torch.Tensor, step: float = 0.1) -> torch.Tensor:
         """Batched FrenetState.from_state on the uploaded reference line: states [n, 5] = x, y, yaw, v, a (device, float64)

@@ -201,7 +201,7 @@ class IntersectionPlanner:
     route centre line is given to ``generate_frenet_frame`` directly."""
 
     def __init__(self, planner_settings: PlannerSettings, observation: dict, method: str = "JSSP", device: int = 0, **planner_kwargs):
-        if method != "JSSP":
+        if method not in ("JSSP", "frenet"):
             print("##log## ERROR: Planning method entered is not recognized!")
             raise ValueError(method)
         self.fplanner_settings = planner_settings
@@ -213,7 +213,11 @@ class IntersectionPlanner:
         self.ref_ego_lane_pts = None
         self.ego_vehicle = self._get_ego_vehicle_parameters(observation)
         self.ego_state = self._get_ego_states(observation)
-        self.fplanner = JerkSpaceSamplingPlanner(JerkSpaceSamplingPlannerSettings.intended(), self.ego_vehicle, device=device, **planner_kwargs)
+        if method == "frenet":                      # the baseline branch of init_local_planner (intersection_planner.py:99-110)
+            from .fop import FrenetOptimalPlanner, FrenetOptimalPlannerSettings
+            self.fplanner = FrenetOptimalPlanner(FrenetOptimalPlannerSettings.intended(planner_settings.speed_max), self.ego_vehicle, device=device)
+        else:
+            self.fplanner = JerkSpaceSamplingPlanner(JerkSpaceSamplingPlannerSettings.intended(), self.ego_vehicle, device=device, **planner_kwargs)
 
     def _get_ego_vehicle_parameters(self, observation) -> Vehicle:
         s = self.fplanner_settings

@@ -192,6 +192,29 @@ int32_t jssp_predict_modes(jssp_handle* h, const double* lanes_dev, int32_t L, i
                            const double* s_start_dev, const double* speed_dev, double dt, int32_t O, int32_t M,
                            int32_t Tt, double* state_dev, uint8_t* valid_dev, void* stream);
 
+/* -- FOP baseline planner through the same stages ------------------------------------
+ * replaces the body of FrenetOptimalPlanner.plan_traj (code/intersection_local_planner/frenet_optimal_planner.py:301-333):
+ * sampling_frenet_trajectories (:97-144: lateral quintic x horizon x longitudinal quartic to a target speed, samples
+ * arange(0, T, dt)), calc_global_paths (:146-183), check_constraints (:185-225: |s_dd| <= max_accel, |s_ddd| <= max_jerk),
+ * check_collisions (:249-299: check_res 2, rectangles NOT inflated - create the handle with obstacle_inflation = 0), cost and
+ * the `min_cost >= cost` selection (:328-333: the LAST minimum wins).  Candidate n = (w * num_t + it) * num_speed + iv.
+ * The handle supplies reference line, obstacles, delta_t, ego footprint, cost weights (configuration_parameters.py:48:
+ * {1.0, 0.0, 99.4, 0.2, 0.1, 0.8, 0.4, 10.0}), thresholds, speed_max = target speed (highest_speed) and must have
+ * plan_horizon >= max_t.  Outputs as jssp_evaluate (masks / costs [N], selected trajectory rows; rows beyond the
+ * candidate's own length are NaN).  QuarticPolynomial and GoalSamplingCostFunction are absent from the reference tree:
+ * builder-specified, see oracle/fop_oracle.py. */
+typedef struct jssp_fop_in {
+  double s0, v0, a0;           /* frenet_state.s, s_d, s_dd */
+  double d0, d_d0, d_dd0;      /* frenet_state.d, d_d, d_dd */
+  int32_t time_step_now, final_time_step;
+  int32_t num_width, num_speed, num_t;   /* FrenetOptimalPlannerSettings (:56-83); paras_planner["planner_frenet"]: 3, 250, 10 */
+  int32_t flags;               /* JSSP_FLAG_NO_SYNC / JSSP_FLAG_NO_EXPORT */
+  double min_t, max_t;         /* 5.0, 5.5 */
+  double lowest_speed, highest_speed;    /* 0.0, speed_max */
+  double max_accel, max_jerk;  /* Vehicle.max_accel, max_jerk = lon_accel_max, lon_jerk_max (8.0, 10.0) */
+} jssp_fop_in;
+int32_t jssp_fop_evaluate(jssp_handle* h, const jssp_fop_in* in, void* stream, jssp_cycle_out* out);
+
 /* -- batched Cartesian -> Frenet projection ------------------------------------------
  * replaces FrenetState().from_state(ego_state, ref_ego_lane_pts) (intersection_planner.py:140-142, 308-310) for n states
  * at once on the handle's reference line re-discretised every `step` metres (0.1 in jssp.py:366): state_dev [n][5] =

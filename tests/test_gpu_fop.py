@@ -1,0 +1,75 @@
+"""FOP baseline planner through the CUDA path (jssp_fop_evaluate) against its CPU oracle (oracle/fop_oracle.py):
+masks and the selected index bit-exact, costs and trajectory rows to tolerance."""
+import numpy as np
+import pytest
+
+import dlii_jssp_b200 as J
+from dlii_jssp_b200 import scenario as S
+from oracle import fop_oracle as F, jssp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(sc, cfg: F.FopConfig, frenet0, now):
+    spline = O.CubicSpline2D(sc.route_xy[:, 0], sc.route_xy[:, 1])
+    final = int(sc.max_t / sc.dt)
+    obs = S.pack_obstacle_dict(sc.vehicle_traj, sc.dt, final + int(np.ceil(cfg.max_t / cfg.delta_t)) + 2)
+    with np.errstate(all="ignore"):
+        ref = F.plan_cycle(cfg, spline, frenet0, (obs.state, obs.valid.astype(bool), obs.size, obs.prob), now, final)
+    veh = J.Vehicle(cfg.ego_length, cfg.ego_width, longitudinal_a_max=cfg.max_accel, longitudinal_jerk_max=cfg.max_jerk)
+    st = J.FrenetOptimalPlannerSettings(num_width=cfg.num_width, num_speed=cfg.num_speed, num_t=cfg.num_t, highest_speed=cfg.highest_speed,
+                                        lowest_speed=cfg.lowest_speed, min_planning_t=cfg.min_t, max_planning_t=cfg.max_t)
+    pl = J.FrenetOptimalPlanner(st, veh)
+    pl.cubic_spline = J.CubicSpline2D(sc.route_xy[:, 0], sc.route_xy[:, 1])
+    observation = sc.observation()
+    observation["test_setting"]["t"] = now * sc.dt
+    best = pl.plan_traj(J.FrenetState(s=frenet0[0], s_d=frenet0[1], s_dd=frenet0[2], d=frenet0[3], d_d=frenet0[4], d_dd=frenet0[5]),
+                        J.State(), sc.vehicle_traj, observation)
+    return ref, pl, best
+
+
+def _compare(ref, pl, best):
+    res = pl.last_result
+    n = ref["n"]
+    assert res.n_candidates == n
+    assert np.array_equal(res.feasible.cpu().numpy().astype(bool), ref["feasible"])
+    assert np.array_equal(res.collision.cpu().numpy().astype(bool), ref["collision"])
+    np.testing.assert_allclose(res.cost.cpu().numpy(), ref["cost"], rtol=1e-4)
+    assert res.best_idx == ref["best"], (res.best_idx, ref["best"])
+    if ref["best"] >= 0:
+        b = ref["best"]
+        own = int(np.count_nonzero(~np.isnan(ref["s"][b])))
+        assert len(best.s) == own and len(best.x) == int(ref["n_pts"][b])
+        for key in ("s", "s_d", "s_dd", "s_ddd", "d", "d_d", "d_dd", "d_ddd"):
+            np.testing.assert_allclose(getattr(best, key), ref[key][b][:own], rtol=1e-9, atol=1e-9, err_msg=key)
+        npts = int(ref["n_pts"][b])
+        for key in ("x", "y", "yaw"):
+            np.testing.assert_allclose(getattr(best, key), ref[key][b][:npts], rtol=1e-9, atol=1e-9, err_msg=key)
+        assert abs(best.cost_total - ref["cost"][b]) <= 1e-9 * max(1.0, abs(ref["cost"][b]))
+
+
+def test_fop_default_grid_on_bundled_scenario(scenario_fixture):
+    """paras_planner["planner_frenet"]: 3 widths x 10 horizons (5.0 .. 5.5 s) x 250 target speeds = 7500 candidates."""
+    sc = scenario_fixture
+    cfg = F.FopConfig(ego_length=sc.ego["length"], ego_width=sc.ego["width"])
+    for fr, now in (((2.93, 5.67, 0.0, 0.6, -0.4, 0.0), 0), ((14.0, 5.2, -0.3, 0.1, 0.0, 0.0), 20), ((27.0, 4.0, 0.2, 0.0, 0.0, 0.0), 50)):
+        ref, pl, best = _run(sc, cfg, fr, now)
+        _compare(ref, pl, best)
+        assert ref["collision"].any() or now == 50
+        pl.engine.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_fop_reference_class_defaults_on_synthetic_intersections(seed):
+    """FrenetOptimalPlannerSettings' own defaults (5 x 5 x 5, horizons 5 .. 8 s => per-candidate lengths 50 .. 80), trajectories that
+    leave the reference line, end-of-scenario windows."""
+    sc = S.synthetic_intersection(seed)
+    cfg = F.FopConfig(num_width=5, num_speed=5, num_t=5, highest_speed=13.4112, min_t=5.0, max_t=8.0, max_accel=2.5, max_jerk=2.0)
+    s_end = O.CubicSpline2D(sc.route_xy[:, 0], sc.route_xy[:, 1]).s_list[-1]
+    some_infeasible = False
+    for fr, now in (((2.0, 6.0, 0.0, 0.3, 0.0, 0.0), 3), ((s_end - 25.0, 9.0, 0.5, -0.2, 0.1, 0.0), 40), ((s_end - 0.3, 2.0, 0.0, 0.0, 0.0, 0.0), 110)):
+        ref, pl, best = _run(sc, cfg, fr, now)
+        _compare(ref, pl, best)
+        some_infeasible |= not ref["feasible"].all()
+        pl.engine.close()
+    assert some_infeasible                                    # tight acceleration / jerk limits reject the fast targets

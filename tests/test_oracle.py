@@ -140,3 +140,24 @@ def test_time_key_lookup_matches_reference_rounding(scenario_fixture):
     assert np.array_equal(a.state, st) and np.array_equal(a.valid.astype(bool), va) and np.array_equal(a.size, sz)
     assert a.valid.sum() == sum(len([k for k in tr if k != "shape"]) for tr in sc.vehicle_traj.values()) == 271
     assert int(sc.max_t / sc.dt) == 121                       # float truncation of 12.2 / 0.1 (jerk_space_sampling_planner.py:244)
+
+
+def test_fop_oracle_known_answers():
+    """FOP baseline oracle: quartic boundary conditions, per-horizon sample counts, and the `>=` rule (last minimum wins)."""
+    from oracle import fop_oracle as F
+    q = F.QuarticPolynomial(3.0, 5.0, -1.0, 9.0, 0.0, 5.5)
+    assert np.isclose(q.calc_point(0.0), 3.0) and np.isclose(q.calc_first_derivative(0.0), 5.0) and np.isclose(q.calc_second_derivative(0.0), -1.0)
+    assert np.isclose(q.calc_first_derivative(5.5), 9.0) and abs(q.calc_second_derivative(5.5)) < 1e-12
+    cfg = F.FopConfig(num_width=3, num_speed=4, num_t=3, min_t=5.0, max_t=5.5, ego_length=4.9, ego_width=1.9)
+    widths, horizons, speeds, n = F.grids(cfg)
+    assert list(n) == [len(np.arange(0.0, T, 0.1)) for T in horizons] and n[0] == 50 and n[-1] == 55
+    route = np.column_stack([np.linspace(0, 200, 401), np.zeros(401)])
+    spline = O.CubicSpline2D(route[:, 0], route[:, 1])
+    empty = (np.zeros((0, 1, 10, 3)), np.zeros((0, 1, 10), bool), np.zeros((0, 2)), np.zeros((0, 1)))
+    r = F.plan_cycle(cfg, spline, (5.0, 6.0, 0.0, 0.0, 0.0, 0.0), empty, 0, 100)
+    assert r["n"] == 36 and not r["collision"].any()
+    # d0 = 0 on a straight line: the outer lateral targets are mirror images -> equal costs; the LAST one must be selected
+    ok = r["feasible"]
+    best_cost = r["cost"][ok].min()
+    ties = np.nonzero(ok & (r["cost"] == best_cost))[0]
+    assert r["best"] == ties[-1]
