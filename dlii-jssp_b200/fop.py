@@ -92,6 +92,10 @@ class FrenetOptimalPlanner(object):
             self.engine.set_obstacles(t.state, t.valid, t.size, t.prob, t.n_dict)
             self._obstacle_key = key
 
+    def reset(self):
+        """Forget the previous scenario (reference line, obstacles, best trajectory); the device workspace is kept."""
+        self.best_traj, self.all_trajs, self._cubic_spline, self._obstacle_key, self.last_result = None, [], None, None, None
+
     def plan_traj(self, frenet_state: FrenetState, ego_state: State, obstacles, observation) -> Optional[GoalSamplingFrenetTrajectory]:
         """Same contract as frenet_optimal_planner.py:301-360 (without the plotting side effects)."""
         if self._cubic_spline is None:

@@ -77,11 +77,12 @@ def end_status(observation: dict, scenario: ReplayScenario, goal_pose: tuple) ->
 
 
 def run_replay(scenario: ReplayScenario, device: int = 0, max_cycles: Optional[int] = None, planner: Optional[IntersectionPlanner] = None,
-               **planner_kwargs) -> ReplayResult:
-    """Replay one scenario with the CUDA planner.  Returns per-cycle selections and the ego rows the reference would record."""
+               method: str = "JSSP", **planner_kwargs) -> ReplayResult:
+    """Replay one scenario with the CUDA planner (``method`` = "JSSP" or the "frenet" baseline, paras_planner["planner_type"]).
+    Returns per-cycle selections and the ego rows the reference would record."""
     obs = scenario.observation()
     if planner is None:
-        planner = IntersectionPlanner(PlannerSettings(), obs, "JSSP", device=device, **planner_kwargs)
+        planner = IntersectionPlanner(PlannerSettings(), obs, method, device=device, **planner_kwargs)
     route = scenario.route_xy
     planner.generate_frenet_frame(route)                       # __main__.py:100
     goal_pose = goal_pose_of(scenario)

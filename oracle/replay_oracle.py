@@ -10,14 +10,16 @@ import numpy as np
 from . import jssp_oracle as O
 
 
-def replay(scenario, frenet0, pack_obstacles, end_status, goal_pose, max_cycles=None, cfg_overrides=None):
+def replay(scenario, frenet0, pack_obstacles, end_status, goal_pose, max_cycles=None, cfg_overrides=None, fop_cfg=None):
     """``frenet0`` = initial Frenet state (s, s_d, s_dd, d, d_d, d_dd); ``pack_obstacles`` / ``end_status`` are the
     host-logic callables of the product (dict -> tensors, end-of-scenario test), passed in so that this file only
     supplies the planner arithmetic."""
+    """With ``fop_cfg`` (oracle.fop_oracle.FopConfig) the FOP baseline planner replaces the JSSP planner in the loop."""
     cfg = O.OracleConfig(ego_length=scenario.ego["length"], ego_width=scenario.ego["width"], **(cfg_overrides or {}))
+    horizon_steps = cfg.n_steps if fop_cfg is None else int(math.ceil(fop_cfg.max_t / fop_cfg.delta_t))
     spline = O.CubicSpline2D(scenario.route_xy[:, 0], scenario.route_xy[:, 1])
     final = int(scenario.max_t / scenario.dt)
-    t = pack_obstacles(scenario.vehicle_traj, scenario.dt, final + cfg.n_steps + 2)
+    t = pack_obstacles(scenario.vehicle_traj, scenario.dt, final + horizon_steps + 2)
     obs_t = (t.state, t.valid.astype(bool), t.size, t.prob)
     obs = scenario.observation()
     out = dict(best_idx=[], n=[], rows=[], end=-1)
@@ -27,7 +29,11 @@ def replay(scenario, frenet0, pack_obstacles, end_status, goal_pose, max_cycles=
         ts = obs["test_setting"]
         now = int(ts["t"] / ts["dt"])
         with np.errstate(all="ignore"):
-            r = O.plan_cycle(cfg, spline, fr, obs_t, now, final, n_obstacles_in_dict=t.n_dict)
+            if fop_cfg is None:
+                r = O.plan_cycle(cfg, spline, fr, obs_t, now, final, n_obstacles_in_dict=t.n_dict)
+            else:
+                from . import fop_oracle
+                r = fop_oracle.plan_cycle(fop_cfg, spline, fr, obs_t, now, final, n_obstacles_in_dict=t.n_dict)
         b = r["best"]
         out["best_idx"].append(b); out["n"].append(r["n"])
         if b < 0:

@@ -73,3 +73,21 @@ def test_fop_reference_class_defaults_on_synthetic_intersections(seed):
         some_infeasible |= not ref["feasible"].all()
         pl.engine.close()
     assert some_infeasible                                    # tight acceleration / jerk limits reject the fast targets
+
+
+def test_fop_replay_matches_oracle_replay(scenario_fixture):
+    """The baseline planner in the replay loop (paras_planner["planner_type"] = "frenet"): cycle-by-cycle selections and ego
+    rows against the oracle's FOP replay, reduced grid (3 x 4 x 40) to keep the CPU side short."""
+    from dlii_jssp_b200 import replay as R, batch as B
+    from oracle import replay_oracle
+    sc = scenario_fixture
+    cfg = F.FopConfig(num_width=3, num_speed=40, num_t=4, ego_length=sc.ego["length"], ego_width=sc.ego["width"])
+    planner = J.IntersectionPlanner(J.PlannerSettings(), sc.observation(), "frenet")
+    planner.fplanner.engine.close()
+    planner.fplanner = J.FrenetOptimalPlanner(J.FrenetOptimalPlannerSettings(num_width=3, num_speed=40, num_t=4, highest_speed=18.0, min_planning_t=5.0,
+                                                                            max_planning_t=5.5), planner.ego_vehicle)
+    gpu = R.run_replay(sc, max_cycles=15, planner=planner, method="frenet")
+    fr0 = tuple(B.pack_scenario(sc).frenet0)
+    cpu = replay_oracle.replay(sc, fr0, S.pack_obstacle_dict, R.end_status, R.goal_pose_of(sc), max_cycles=15, fop_cfg=cfg)
+    assert gpu.best_idx == cpu["best_idx"] and gpu.n_candidates == cpu["n"] and gpu.end == cpu["end"]
+    np.testing.assert_allclose(np.array(gpu.ego_rows), np.array(cpu["rows"]), rtol=1e-9, atol=1e-9)
