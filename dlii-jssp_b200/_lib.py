@@ -73,7 +73,7 @@ class JsspCycleRecord(C.Structure):
 
 
 class JsspScenarioResult(C.Structure):
-    _fields_ = [("end", C.c_double), ("cycles", C.c_int32), ("reserved0", C.c_int32)]
+    _fields_ = [("end", C.c_double), ("cycles", C.c_int32), ("seed_overflow", C.c_int32)]
 
 
 class JsspScenarioIn(C.Structure):

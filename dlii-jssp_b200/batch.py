@@ -29,7 +29,7 @@ from .scenario import ReplayScenario, pack_obstacle_dict, time_key
 
 RECORD_DTYPE = np.dtype([("best_idx", "<i4"), ("n_candidates", "<i4"), ("best_cost", "<f8"), ("t", "<f8"), ("x", "<f8"), ("y", "<f8"),
                          ("v", "<f8"), ("a", "<f8"), ("yaw", "<f8")])
-RESULT_DTYPE = np.dtype([("end", "<f8"), ("cycles", "<i4"), ("reserved0", "<i4")])
+RESULT_DTYPE = np.dtype([("end", "<f8"), ("cycles", "<i4"), ("seed_overflow", "<i4")])
 assert RECORD_DTYPE.itemsize == C.sizeof(JsspCycleRecord) and RESULT_DTYPE.itemsize == C.sizeof(JsspScenarioResult)
 
 

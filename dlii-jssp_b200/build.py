@@ -9,7 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjssp_b200.so")
 SOURCES = ["jssp_b200.cu"]
-HEADERS = ["jssp_kernels.cuh", "jssp_device.cuh", os.path.join("..", "..", "include", "jssp_b200.h")]
+HEADERS = ["jssp_kernels.cuh", "jssp_common.cuh", "jssp_seed.cuh", "jssp_pack.cuh", "jssp_eval.cuh", "jssp_eval_small.cuh", "jssp_fop.cuh",
+           "jssp_aux.cuh", "jssp_device.cuh", os.path.join("..", "..", "include", "jssp_b200.h")]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3",

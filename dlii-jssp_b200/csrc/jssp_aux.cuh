@@ -1,0 +1,246 @@
+// jssp_aux.cuh - K3 state dump, K5 Cartesian->Frenet projection, K4 IMM, FMA peak micro-benchmark
+#pragma once
+#include "jssp_eval.cuh"
+
+namespace jssp {
+
+// ------------------------------------------------------------------------------------------------------------------
+// K3: export of the selected trajectory (float64 rows) and optional fp32 state dump of every candidate
+// ------------------------------------------------------------------------------------------------------------------
+struct DumpSink {
+  float* out;   // [P][8] of this candidate: s, s_d, s_dd, d, x, y, yaw, c
+  const double* lat;
+  double pyaw, pds;
+  __device__ __forceinline__ void sample(int i, double, double s, double sd, double sdd, double) {
+    float4* r = reinterpret_cast<float4*>(out + (size_t)i * JSSP_STATE_COLS);
+    const float nanv = __int_as_float(0x7fc00000);
+    r[0] = make_float4((float)s, (float)sd, (float)sdd, (float)lat[i * 4]);
+    r[1] = make_float4(nanv, nanv, nanv, nanv);
+  }
+  __device__ __forceinline__ void point(int i, double x, double y) {
+    out[(size_t)i * JSSP_STATE_COLS + 4] = (float)x; out[(size_t)i * JSSP_STATE_COLS + 5] = (float)y;
+  }
+  __device__ __forceinline__ void segment(int i, double, double, double dx, double dy, double ds, double, double) {
+    const double yaw = heading_of(dx, dy);
+    out[(size_t)i * JSSP_STATE_COLS + 6] = (float)yaw;
+    if (i >= 1) out[(size_t)(i - 1) * JSSP_STATE_COLS + 7] = (float)((yaw - pyaw) / pds);
+    pyaw = yaw; pds = ds;
+  }
+  __device__ __forceinline__ void finish(int n_pts, double, double) {
+    if (n_pts >= 2) {
+      out[(size_t)(n_pts - 1) * JSSP_STATE_COLS + 6] = (float)pyaw;
+      out[(size_t)(n_pts - 2) * JSSP_STATE_COLS + 7] = (float)((pyaw - pyaw) / pds);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(EVAL_THREADS) dump_states_kernel(const __grid_constant__ EvalParams p, float* __restrict__ states) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int Ns = resolve_n_seeds(p);
+  const int N = Ns * p.W;
+  if (blockIdx.x * blockDim.x >= N) return;
+  BlockTables tb;
+  const double* latcost;
+  stage_tables<0>(p, smem, tb, latcost);
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int w = n / Ns, k = n - w * Ns;
+  LonWalk lp;
+  lon_walk_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
+  DumpSink sink{states + (size_t)n * p.P * JSSP_STATE_COLS, tb.lat + (size_t)w * p.P * 4, 0.0, 0.0};
+  const int seg0 = spline_bisect(tb.sp, fmin(fmax(p.s0, tb.sp.knot[0]), tb.sp.knot[p.K - 1]));
+  walk_candidate(p, tb, lp, w, seg0, sink);
+}
+
+__global__ void best_record_kernel(const BestRecord* __restrict__ best, long long offset, unsigned long long* __restrict__ rec) {
+  rec[0] = best->key;
+  rec[1] = best->idx >= 0 ? (unsigned long long)(best->idx + offset) : 0xffffffffffffffffull;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K5: batched Cartesian -> Frenet projection: FrenetState.from_state(state, polyline) as the
+// driver uses it at t <= 0.05 and in kinematics mode (intersection_planner.py:140-142, 308-310).  The class is absent from
+// the reference tree; the specification is dlii-jssp_b200/frenet.py::FrenetState.from_state: nearest point of the
+// reference line re-discretised every `step` metres (generate_frenet_frame, jssp.py:366-371), arc length = sum of the chord
+// lengths up to it plus the tangential offset, signed lateral offset by the left-hand normal, speed / acceleration split
+// by the heading error.  One block per state: threads stride over the polyline samples.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int PROJECT_THREADS = 256;
+__global__ void __launch_bounds__(PROJECT_THREADS) project_states_kernel(const double* __restrict__ knot, const double* __restrict__ coef,
+                                                                         int K, int kpad, double step, int n_samples,
+                                                                         const double* __restrict__ state, double* __restrict__ frenet) {
+  __shared__ double red_d[PROJECT_THREADS / 32];
+  __shared__ int red_i[PROJECT_THREADS / 32];
+  __shared__ double red_s[PROJECT_THREADS / 32];
+  __shared__ int best_i;
+  const double* st = state + (size_t)blockIdx.x * 5;        // x, y, yaw, v, a
+  const double px = st[0], py = st[1];
+  SplineView sp{knot, coef, K, kpad, (double)(K - 1) / knot[K - 1]};
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // 1) nearest sample (first occurrence on ties, like numpy.argmin)
+  double bd = INFINITY;
+  int bi = -1;
+  for (int m = tid; m < n_samples; m += blockDim.x) {
+    const double s = (double)m * step;
+    double x, y;
+    frenet_point(sp, spline_bisect(sp, s), s, 0.0, x, y);
+    const double d2 = (x - px) * (x - px) + (y - py) * (y - py);
+    if (d2 < bd) { bd = d2; bi = m; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double od = __shfl_down_sync(0xffffffffu, bd, o);
+    const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+    if (oi >= 0 && (bi < 0 || od < bd || (od == bd && oi < bi))) { bd = od; bi = oi; }
+  }
+  if (lane == 0) { red_d[wid] = bd; red_i[wid] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int q = 1; q < (int)(blockDim.x >> 5); ++q)
+      if (red_i[q] >= 0 && (bi < 0 || red_d[q] < bd || (red_d[q] == bd && red_i[q] < bi))) { bd = red_d[q]; bi = red_i[q]; }
+    best_i = bi;
+  }
+  __syncthreads();
+  const int ib = best_i;
+  // 2) arc length of the polyline up to the nearest sample
+  double acc = 0.0;
+  for (int m = tid; m < ib; m += blockDim.x) {
+    const double s0 = (double)m * step, s1 = (double)(m + 1) * step;
+    double x0, y0, x1, y1;
+    frenet_point(sp, spline_bisect(sp, s0), s0, 0.0, x0, y0);
+    frenet_point(sp, spline_bisect(sp, s1), s1, 0.0, x1, y1);
+    acc = acc + hypot(x1 - x0, y1 - y0);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc = acc + __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane == 0) red_s[wid] = acc;
+  __syncthreads();
+  if (tid != 0) return;
+  for (int q = 1; q < (int)(blockDim.x >> 5); ++q) acc = acc + red_s[q];
+  // 3) projection on the tangent / left-hand normal of the nearest sample
+  const double sb = (double)ib * step;
+  const int seg = spline_bisect(sp, sb);
+  double rx, ry;
+  frenet_point(sp, seg, sb, 0.0, rx, ry);
+  const double h = sb - knot[seg];
+  const double* c = coef + seg;
+  const double tx = (c[kpad] + (2.0 * c[2 * kpad]) * h) + (3.0 * c[3 * kpad]) * (h * h);
+  const double ty = (c[5 * kpad] + (2.0 * c[6 * kpad]) * h) + (3.0 * c[7 * kpad]) * (h * h);
+  const double ryaw = atan2(ty, tx);
+  double sy, cy;
+  sincos(ryaw, &sy, &cy);
+  const double dx = px - rx, dy = py - ry;
+  double sdy, cdy;
+  sincos(st[2] - ryaw, &sdy, &cdy);
+  double* o = frenet + (size_t)blockIdx.x * 6;              // s, s_d, s_dd, d, d_d, d_dd
+  o[0] = acc + (dx * cy + dy * sy);
+  o[1] = st[3] * cdy;
+  o[2] = st[4] * cdy;
+  o[3] = -dx * sy + dy * cy;
+  o[4] = st[3] * sdy;
+  o[5] = st[4] * sdy;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K4: batched IMM lane-intention update (builder-specified; no reference code exists)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int IMM_MAX_MODES = 8;
+__global__ void imm_update_kernel(jssp_imm_params prm, double* __restrict__ mean, double* __restrict__ cov, double* __restrict__ mu,
+                                  const double* __restrict__ z, int O, int M) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= O) return;
+  double e[IMM_MAX_MODES], ed[IMM_MAX_MODES], p00[IMM_MAX_MODES], p01[IMM_MAX_MODES], p11[IMM_MAX_MODES], m[IMM_MAX_MODES],
+      zz[IMM_MAX_MODES], cbar[IMM_MAX_MODES], lik[IMM_MAX_MODES];
+  for (int i = 0; i < M; ++i) {
+    e[i] = mean[((size_t)o * M + i) * 2]; ed[i] = mean[((size_t)o * M + i) * 2 + 1];
+    p00[i] = cov[((size_t)o * M + i) * 3]; p01[i] = cov[((size_t)o * M + i) * 3 + 1]; p11[i] = cov[((size_t)o * M + i) * 3 + 2];
+    m[i] = mu[(size_t)o * M + i]; zz[i] = z[(size_t)o * M + i];
+  }
+  const double p_off = M > 1 ? (1.0 - prm.p_stay) / (double)(M - 1) : 0.0;
+  double ne[IMM_MAX_MODES], ned[IMM_MAX_MODES], n00[IMM_MAX_MODES], n01[IMM_MAX_MODES], n11[IMM_MAX_MODES];
+  for (int j = 0; j < M; ++j) {
+    // 1) interaction / mixing, expressed in mode j's lane frame: e_i + (z_j - z_i)
+    double cb = 0.0;
+    for (int i = 0; i < M; ++i) cb = cb + (i == j ? prm.p_stay : p_off) * m[i];
+    cbar[j] = cb;
+    double x0 = 0.0, x1 = 0.0;
+    for (int i = 0; i < M; ++i) {
+      const double wgt = cb > 0.0 ? (i == j ? prm.p_stay : p_off) * m[i] / cb : (i == j ? 1.0 : 0.0);
+      x0 = x0 + wgt * (e[i] + (zz[j] - zz[i]));
+      x1 = x1 + wgt * ed[i];
+    }
+    double q00 = 0.0, q01 = 0.0, q11 = 0.0;
+    for (int i = 0; i < M; ++i) {
+      const double wgt = cb > 0.0 ? (i == j ? prm.p_stay : p_off) * m[i] / cb : (i == j ? 1.0 : 0.0);
+      const double d0 = e[i] + (zz[j] - zz[i]) - x0, d1 = ed[i] - x1;
+      q00 = q00 + wgt * (p00[i] + d0 * d0); q01 = q01 + wgt * (p01[i] + d0 * d1); q11 = q11 + wgt * (p11[i] + d1 * d1);
+    }
+    // 2) mode-matched prediction, F = [[1, dt], [-k dt, 1]] (lane keeping towards this mode's centre line)
+    const double dt = prm.dt, kd = -prm.k_lat * dt;
+    const double xp0 = x0 + dt * x1, xp1 = kd * x0 + x1;
+    const double f00 = q00 + dt * q01, f01 = q01 + dt * q11;      // (F P) rows
+    const double f10 = kd * q00 + q01, f11 = kd * q01 + q11;
+    const double pp00 = f00 + f01 * dt + prm.q_pos;
+    const double pp01 = f00 * kd + f01;
+    const double pp11 = f10 * kd + f11 + prm.q_vel;
+    // 3) update with z_j (H = [1 0])
+    const double nu = zz[j] - xp0, S = pp00 + prm.r_pos;
+    const double k0 = pp00 / S, k1 = pp01 / S;
+    ne[j] = xp0 + k0 * nu; ned[j] = xp1 + k1 * nu;
+    n00[j] = pp00 - k0 * pp00; n01[j] = pp01 - k0 * pp01; n11[j] = pp11 - k1 * pp01;
+    lik[j] = exp(-0.5 * nu * nu / S) / sqrt(2.0 * 3.14159265358979323846 * S);
+  }
+  // 4) mode probabilities
+  double tot = 0.0;
+  for (int j = 0; j < M; ++j) { m[j] = fmax(lik[j] * cbar[j], prm.mu_floor); tot = tot + m[j]; }
+  for (int j = 0; j < M; ++j) {
+    mean[((size_t)o * M + j) * 2] = ne[j]; mean[((size_t)o * M + j) * 2 + 1] = ned[j];
+    cov[((size_t)o * M + j) * 3] = n00[j]; cov[((size_t)o * M + j) * 3 + 1] = n01[j]; cov[((size_t)o * M + j) * 3 + 2] = n11[j];
+    mu[(size_t)o * M + j] = m[j] / tot;
+  }
+}
+
+// one thread per (obstacle, mode): walk the mode's lane polyline at constant speed
+__global__ void predict_modes_kernel(const double* __restrict__ lanes, int L, int Pn, const int* __restrict__ lane_of,
+                                     const double* __restrict__ s_start, const double* __restrict__ speed, double dt, int O,
+                                     int M, int Tt, double* __restrict__ state, uint8_t* __restrict__ valid) {
+  const int om = blockIdx.x * blockDim.x + threadIdx.x;
+  if (om >= O * M) return;
+  const int lane = lane_of[om];
+  double* st = state + (size_t)om * Tt * 3;
+  uint8_t* va = valid + (size_t)om * Tt;
+  if (lane < 0 || lane >= L) { for (int t = 0; t < Tt; ++t) { va[t] = 0; st[t * 3] = st[t * 3 + 1] = st[t * 3 + 2] = 0.0; } return; }
+  const double* pl = lanes + (size_t)lane * Pn * 2;
+  const double v = speed[om / M];
+  int seg = 0;
+  double acc = 0.0;   // arc length at the start of segment `seg`
+  double seg_len = hypot(pl[2] - pl[0], pl[3] - pl[1]);
+  for (int t = 0; t < Tt; ++t) {
+    const double s = s_start[om] + v * ((double)t * dt);
+    while (seg < Pn - 2 && s > acc + seg_len) {
+      acc = acc + seg_len; ++seg;
+      seg_len = hypot(pl[(seg + 1) * 2] - pl[seg * 2], pl[(seg + 1) * 2 + 1] - pl[seg * 2 + 1]);
+    }
+    const bool ok = s >= 0.0 && s <= acc + seg_len && seg_len > 0.0;
+    const double dx = pl[(seg + 1) * 2] - pl[seg * 2], dy = pl[(seg + 1) * 2 + 1] - pl[seg * 2 + 1];
+    const double u = seg_len > 0.0 ? (s - acc) / seg_len : 0.0;
+    st[t * 3] = pl[seg * 2] + u * dx; st[t * 3 + 1] = pl[seg * 2 + 1] + u * dy; st[t * 3 + 2] = atan2(dy, dx);
+    va[t] = ok ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// bench utility: dense FMA throughput of the CUDA cores (the roofline denominator of the evaluation kernel)
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* __restrict__ out, int iters, T a, T b) {
+  T x0 = (T)threadIdx.x, x1 = x0 + (T)1, x2 = x0 + (T)2, x3 = x0 + (T)3, x4 = x0 + (T)4, x5 = x0 + (T)5, x6 = x0 + (T)6, x7 = x0 + (T)7;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+}  // namespace jssp

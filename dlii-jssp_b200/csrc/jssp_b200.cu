@@ -1132,8 +1132,12 @@ int32_t jssp_batch_fetch(jssp_batch* b, int32_t n_scenarios, jssp_scenario_resul
   if (records_host)
     CKB(cudaMemcpyAsync(records_host, b->d_records, (size_t)n_scenarios * b->C * sizeof(jssp_cycle_record), cudaMemcpyDeviceToHost, st));
   CKB(cudaStreamSynchronize(st));
-  for (int s = 0; s < n_scenarios; ++s) { results_host[s].end = q[s].end; results_host[s].cycles = q[s].cycle; results_host[s].reserved0 = 0; }
-  return JSSP_OK;
+  bool overflow = false;
+  for (int s = 0; s < n_scenarios; ++s) {
+    results_host[s].end = q[s].end; results_host[s].cycles = q[s].cycle; results_host[s].seed_overflow = q[s].seed_overflow;
+    overflow |= q[s].seed_overflow != 0;
+  }
+  return overflow ? JSSP_ERR_SEED_OVERFLOW : JSSP_OK;
 }
 
 int32_t jssp_batch_best_traj(jssp_batch* b, int32_t slot, double* out, void* stream) {

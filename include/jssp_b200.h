@@ -243,7 +243,8 @@ typedef struct jssp_cycle_record {  /* one plan cycle of one scenario = one row 
 typedef struct jssp_scenario_result {
   double end;                       /* -1 still running, 1 max_t, 1.5 goal, 2 collision, -2 no solution, -3 short trajectory */
   int32_t cycles;                   /* plan cycles executed */
-  int32_t reserved0;
+  int32_t seed_overflow;            /* 1: some cycle enumerated more than cfg.max_seeds seeds (jssp_batch_fetch then returns
+                                       JSSP_ERR_SEED_OVERFLOW; results are still filled in) */
 } jssp_scenario_result;
 
 typedef struct jssp_scenario_in {

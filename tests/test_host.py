@@ -174,3 +174,23 @@ def test_packed_scenario_cache_round_trip(tmp_path, scenario_fixture):
     for o, vid in enumerate(tr):
         keys = [k for k in tr[vid] if k != "shape"]
         assert int(p.valid[o, 0].sum()) == len([k for k in keys if round(float(k) / p.dt) < p.state.shape[2]])
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Argument checks of the batched-replay / FOP / projection entry points run before any device work; without a GPU the
+    constructors report JSSP_ERR_NO_DEVICE instead of falling back."""
+    import torch
+    lib = _lib.load()
+    cfg = J.JsspConfig().to_c()
+    h = C.c_void_p()
+    assert lib.jssp_batch_create(C.byref(cfg), 0, 0, 10, C.byref(h)) == -1            # max_scenarios < 1
+    assert lib.jssp_batch_create(C.byref(cfg), 0, 4, 0, C.byref(h)) == -1             # max_cycles < 1
+    assert lib.jssp_batch_run(None, 1, 1, 0, None) == -1 and lib.jssp_batch_reset(None, 1, None) == -1
+    assert lib.jssp_fop_evaluate(None, None, None, None) == -1
+    assert lib.jssp_project_states(None, None, 0, 0.1, None, None) == -1
+    assert lib.jssp_batch_destroy(None) == 0 and lib.jssp_batch_launch_count(None) == 0
+    if not torch.cuda.is_available():
+        assert lib.jssp_batch_create(C.byref(cfg), 0, 4, 10, C.byref(h)) == -6        # JSSP_ERR_NO_DEVICE
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            J.BatchReplay()
+    assert C.sizeof(_lib.JsspCycleRecord) == 64 and C.sizeof(_lib.JsspScenarioResult) == 16 and C.sizeof(_lib.JsspFopIn) == 6 * 8 + 6 * 4 + 6 * 8
