@@ -896,7 +896,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_kernel
 
 // K2 (default for large cycles): the group form - W consecutive lanes evaluate the W lateral targets of one seed and share
 // the seed-only work (walk_group).  Seeds per block = warps * floor(32 / W); lanes beyond floor(32 / W) * W idle.
-__host__ __device__ inline int group_seeds_per_block(int W) { return (EVAL_THREADS / 32) * (32 / W); }
+__host__ __device__ inline int group_seeds_per_block(int W, int threads = EVAL_THREADS) { return (threads / 32) * (32 / W); }
 
 template <int kMode>
 __device__ __forceinline__ void evaluate_group_body(const EvalParams& p, unsigned char* smem, double* red_cost, int* red_idx,
@@ -907,7 +907,7 @@ __device__ __forceinline__ void evaluate_group_body(const EvalParams& p, unsigne
   const int gpw = 32 / W;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int g = lane / W, j = lane - g * W;
-  const int spb = (EVAL_THREADS / 32) * gpw;
+  const int spb = (blockDim.x >> 5) * gpw;     // the host picks the block size (<= EVAL_THREADS)
   const int k = blockIdx.x * spb + wid * gpw + g;
   const bool active = g < gpw && k < Ns;
   double my_cost = INFINITY;

@@ -20,7 +20,6 @@ __device__ __forceinline__ void evaluate_small_body(const EvalParams& p, unsigne
   const int Ns = resolve_n_seeds(p);
   const int N = Ns * p.W;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int n = blockIdx.x * SMALL_WARPS + wid;
   const int P = p.P;
   double my_cost = INFINITY;
   int my_idx = -1;
@@ -32,7 +31,9 @@ __device__ __forceinline__ void evaluate_small_body(const EvalParams& p, unsigne
     const SmemLayout L = eval_smem_layout(0, p.OMpad, 0, p.K, p.kpad, p.P, p.W);
     double* scr = reinterpret_cast<double*>(smem + L.total) + (size_t)wid * ((size_t)P * SMALL_ROW + 2);
     double* ends = scr + (size_t)P * SMALL_ROW;        // s at the first / last sample
-    if (n < N) {                                       // warp-uniform
+    // grid-stride over groups of SMALL_WARPS candidates: the candidate count is only known on the device, the grid is sized
+    // from a hint and stays small (no thousands of empty blocks in front of a ~100-block cycle)
+    for (int n = blockIdx.x * SMALL_WARPS + wid; n < N; n += gridDim.x * SMALL_WARPS) {     // warp-uniform
       const int w = n / Ns, k = n - w * Ns;
       const double* lat = tb.lat + (size_t)w * P * 4;
       LonProfile lp;
@@ -124,8 +125,9 @@ __device__ __forceinline__ void evaluate_small_body(const EvalParams& p, unsigne
         if (p.feasible) p.feasible[n] = fail ? 0 : 1;
         if (p.collision) p.collision[n] = collided ? 1 : 0;
         if (p.cost) p.cost[n] = (float)cost;
-        if (!fail && !collided && isfinite(cost)) { my_cost = cost; my_idx = n; }
+        if (!fail && !collided && isfinite(cost) && lex_less(cost, n, my_cost, my_idx)) { my_cost = cost; my_idx = n; }
       }
+      __syncwarp();                                    // the warp's scratch is reused by its next candidate
     }
   }
   select_and_export<0>(p, smem, tb, latcost, staged, my_cost, my_idx, N, Ns, red_cost, red_idx, is_last_p, sm_npts_p);
