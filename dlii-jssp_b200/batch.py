@@ -232,10 +232,10 @@ class BatchReplay:
             n = int(res["cycles"][s])
             r = rec[s, :n]
             rr = ReplayResult(p.name, float(res["end"][s]), n)
-            rr.best_idx = [int(v) for v in r["best_idx"]]
-            rr.n_candidates = [int(v) for v in r["n_candidates"]]
+            rr.best_idx = r["best_idx"].tolist()
+            rr.n_candidates = r["n_candidates"].tolist()
             ok = ~np.isnan(r["t"])
-            rr.ego_rows = [tuple(float(r[f][i]) for f in ("t", "x", "y", "v", "a", "yaw")) for i in np.nonzero(ok)[0]]
+            rr.ego_rows = [tuple(row) for row in np.stack([r[f][ok] for f in ("t", "x", "y", "v", "a", "yaw")], 1).tolist()]
             out.append(rr)
         return out
 

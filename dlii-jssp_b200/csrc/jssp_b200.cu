@@ -846,6 +846,9 @@ struct jssp_batch {
   jssp_cycle_record* d_records = nullptr;
   double* d_cycle_time = nullptr;
   int *d_cycle_now = nullptr, *d_cycle_end = nullptr;
+  // pinned staging ring of the uploads: host arrays are copied here, the H2D copies out of it are truly asynchronous
+  unsigned char* h_stage = nullptr;
+  size_t stage_cap = 0, stage_off = 0;
   // launch sizing: maxima over the scenarios set so far
   int max_K = 2, max_kpad = 2, max_OMpad = 0;
   std::vector<unsigned char> is_set;
@@ -864,6 +867,25 @@ int fail_cuda_b(jssp_batch* b, cudaError_t e, const char* what) {
     cudaError_t e__ = (call);                                       \
     if (e__ != cudaSuccess) return fail_cuda_b(b, e__, #call);      \
   } while (0)
+
+// host -> device through the pinned staging ring: on return `src` may be released, the copy runs asynchronously on `st`
+cudaError_t upload_staged(jssp_batch* b, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return cudaSuccess;
+  const size_t need = (bytes + 15) & ~(size_t)15;
+  if (need > b->stage_cap) {                                 // larger than the ring: plain (synchronous) copy
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(st);
+  }
+  if (b->stage_off + need > b->stage_cap) {                  // wrap: everything staged so far must have left the ring
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    b->stage_off = 0;
+  }
+  unsigned char* h = b->h_stage + b->stage_off;
+  b->stage_off += need;
+  memcpy(h, src, bytes);
+  return cudaMemcpyAsync(dst, h, bytes, cudaMemcpyHostToDevice, st);
+}
 }  // namespace
 
 extern "C" {
@@ -880,6 +902,7 @@ int32_t jssp_batch_destroy(jssp_batch* b) {
                  b->d_slots0, b->d_bslots0, b->d_records, b->d_cycle_time, b->d_cycle_now, b->d_cycle_end};
   for (void* q : dev) if (q) cudaFree(q);
   for (double* q : b->d_grid) if (q) cudaFree(q);
+  if (b->h_stage) cudaFreeHost(b->h_stage);
   delete b;
   return JSSP_OK;
 }
@@ -961,6 +984,8 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   CKC(cudaMalloc(&b->d_cycle_time, S * (size_t)(b->C + 1) * sizeof(double)));
   CKC(cudaMalloc(&b->d_cycle_now, S * (size_t)(b->C + 1) * sizeof(int)));
   CKC(cudaMalloc(&b->d_cycle_end, S * (size_t)(b->C + 1) * sizeof(int)));
+  b->stage_cap = (size_t)32 << 20;
+  CKC(cudaMallocHost(&b->h_stage, b->stage_cap));
   b->is_set.assign(S, 0);
   CKC(allow_max_dynamic_smem(evaluate_batch_kernel<0>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_batch_kernel<1>, optin, &b->max_smem_optin));
@@ -997,8 +1022,8 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
   std::vector<double> soa((size_t)8 * kpad, 0.0);
   for (int i = 0; i < K - 1; ++i)
     for (int c = 0; c < 8; ++c) soa[(size_t)c * kpad + i] = in->coef[(size_t)i * 8 + c];
-  CKB(cudaMemcpyAsync(knot, in->knot_s, (size_t)K * sizeof(double), cudaMemcpyHostToDevice, st));
-  CKB(cudaMemcpyAsync(coef, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CKB(upload_staged(b, knot, in->knot_s, (size_t)K * sizeof(double), st));
+  CKB(upload_staged(b, coef, soa.data(), soa.size() * sizeof(double), st));
   const double ox = in->coef[0], oy = in->coef[4];
   double* raw_state = b->d_raw_state + s * b->n_om * b->n_tt * 3;
   uint8_t* raw_valid = b->d_raw_valid + s * b->n_om * b->n_tt;
@@ -1010,10 +1035,10 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
   double* ext64 = b->d_ext64 + s * b->n_om * 2;
   float* probf = b->d_probf + s * b->n_om;
   if (OM > 0) {
-    CKB(cudaMemcpyAsync(raw_state, in->state, (size_t)OM * Tt * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
-    CKB(cudaMemcpyAsync(raw_valid, in->valid, (size_t)OM * Tt, cudaMemcpyHostToDevice, st));
-    CKB(cudaMemcpyAsync(raw_size, in->size, (size_t)in->O * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-    CKB(cudaMemcpyAsync(raw_prob, in->prob, (size_t)OM * sizeof(double), cudaMemcpyHostToDevice, st));
+    CKB(upload_staged(b, raw_state, in->state, (size_t)OM * Tt * 3 * sizeof(double), st));
+    CKB(upload_staged(b, raw_valid, in->valid, (size_t)OM * Tt, st));
+    CKB(upload_staged(b, raw_size, in->size, (size_t)in->O * 2 * sizeof(double), st));
+    CKB(upload_staged(b, raw_prob, in->prob, (size_t)OM * sizeof(double), st));
     const double r_ego = std::sqrt(ego_l * ego_l + ego_w * ego_w) / 2.0;
     const int total = OMpad * Tt;
     pack_obstacles_kernel<<<(total * PACK_LANES + 255) / 256, 256, 0, st>>>(raw_state, raw_valid, raw_size, raw_prob, OM, OMpad, in->M, Tt, ox, oy,
@@ -1029,9 +1054,9 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
     uint8_t* gv = b->d_gt_valid + s * b->n_om * b->n_tt;
     double* gz = b->d_gt_size + s * b->n_om * 2;
     if (gtO > 0) {
-      CKB(cudaMemcpyAsync(gs, in->gt_state, (size_t)gtO * Tt * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
-      CKB(cudaMemcpyAsync(gv, in->gt_valid, (size_t)gtO * Tt, cudaMemcpyHostToDevice, st));
-      CKB(cudaMemcpyAsync(gz, in->gt_size, (size_t)gtO * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+      CKB(upload_staged(b, gs, in->gt_state, (size_t)gtO * Tt * 3 * sizeof(double), st));
+      CKB(upload_staged(b, gv, in->gt_valid, (size_t)gtO * Tt, st));
+      CKB(upload_staged(b, gz, in->gt_size, (size_t)gtO * 2 * sizeof(double), st));
     }
     gt_state = gs; gt_valid = gv; gt_size = gz;
   }
@@ -1039,9 +1064,9 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
   double* ctime = b->d_cycle_time + s * (b->C + 1);
   int* cnow = b->d_cycle_now + s * (b->C + 1);
   int* cend = b->d_cycle_end + s * (b->C + 1);
-  CKB(cudaMemcpyAsync(ctime, in->cycle_time, nc * sizeof(double), cudaMemcpyHostToDevice, st));
-  CKB(cudaMemcpyAsync(cnow, in->cycle_now, nc * sizeof(int), cudaMemcpyHostToDevice, st));
-  CKB(cudaMemcpyAsync(cend, in->cycle_end_step, nc * sizeof(int), cudaMemcpyHostToDevice, st));
+  CKB(upload_staged(b, ctime, in->cycle_time, nc * sizeof(double), st));
+  CKB(upload_staged(b, cnow, in->cycle_now, nc * sizeof(int), st));
+  CKB(upload_staged(b, cend, in->cycle_end_step, nc * sizeof(int), st));
 
   jssp_config c = b->cfg;
   c.ego_length = ego_l; c.ego_width = ego_w;
@@ -1075,12 +1100,12 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
   q.cycle_time = ctime; q.cycle_now = cnow; q.cycle_end_step = cend;
   q.gt_state = gt_state; q.gt_valid = gt_valid; q.gt_size = gt_size;
   q.records = b->d_records + s * (size_t)b->C;
-  CKB(cudaMemcpyAsync(b->d_slots + s, &p, sizeof(p), cudaMemcpyHostToDevice, st));
-  CKB(cudaMemcpyAsync(b->d_bslots + s, &q, sizeof(q), cudaMemcpyHostToDevice, st));
-  CKB(cudaMemcpyAsync(b->d_slots0 + s, &p, sizeof(p), cudaMemcpyHostToDevice, st));
-  CKB(cudaMemcpyAsync(b->d_bslots0 + s, &q, sizeof(q), cudaMemcpyHostToDevice, st));
+  CKB(upload_staged(b, b->d_slots + s, &p, sizeof(p), st));
+  CKB(upload_staged(b, b->d_bslots + s, &q, sizeof(q), st));
+  CKB(upload_staged(b, b->d_slots0 + s, &p, sizeof(p), st));
+  CKB(upload_staged(b, b->d_bslots0 + s, &q, sizeof(q), st));
   CKB(cudaMemsetAsync(b->d_ticket + s, 0, sizeof(unsigned int), st));
-  CKB(cudaStreamSynchronize(st));   // soa, p, q are temporaries; the caller's arrays may be released
+  // everything went through the staging ring: soa, p, q and the caller's arrays may be released, the copies are in flight
   b->max_K = std::max(b->max_K, K); b->max_kpad = std::max(b->max_kpad, kpad); b->max_OMpad = std::max(b->max_OMpad, OMpad);
   b->is_set[s] = 1;
   return JSSP_OK;

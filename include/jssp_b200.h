@@ -272,7 +272,8 @@ typedef struct jssp_scenario_in {
 int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_scenarios, int32_t max_cycles, jssp_batch** out);
 int32_t jssp_batch_destroy(jssp_batch* b);
 const char* jssp_batch_last_cuda_error(const jssp_batch* b);
-/* upload one scenario into `slot` and reset its replay state (synchronises the stream: host arrays may be freed) */
+/* upload one scenario into `slot` and reset its replay state.  The host arrays are copied into a pinned staging ring before
+ * the call returns (they may be freed); the transfers themselves are asynchronous on `stream` */
 int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario_in* in, void* stream);
 /* put slots [0, n_scenarios) back to the state jssp_batch_set_scenario left them in (device-to-device; asynchronous):
  * a sweep can be repeated without uploading the scenarios again */
