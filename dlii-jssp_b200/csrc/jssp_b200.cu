@@ -38,6 +38,11 @@ struct jssp_handle {
   unsigned char *d_raw = nullptr, *h_raw = nullptr;   // one device block + pinned staging block: [state | size | prob | valid]
   size_t raw_bytes = 0;
   cudaEvent_t raw_done = nullptr;                     // the last upload out of h_raw has completed
+  // host-buffer obstacle uploads run on a private stream, next to whatever the caller's stream is doing (e.g. the H2D copy of
+  // the cycle's seeds): tables_ready = upload + pack finished, tables_free = the last evaluation has finished reading them
+  cudaStream_t up_stream = nullptr;
+  cudaEvent_t tables_ready = nullptr, tables_free = nullptr;
+  bool wait_tables = false, tables_in_use = false;
   const double *src_state = nullptr, *src_size = nullptr, *src_prob = nullptr;   // what the pack kernel reads
   const uint8_t* src_valid = nullptr;
   float4 *d_broad = nullptr, *d_narrow = nullptr;
@@ -368,6 +373,9 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(cudaMalloc(&h->d_raw, h->raw_bytes));
   CKC(cudaMallocHost(&h->h_raw, h->raw_bytes));
   CKC(cudaEventCreateWithFlags(&h->raw_done, cudaEventDisableTiming));
+  CKC(cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking));
+  CKC(cudaEventCreateWithFlags(&h->tables_ready, cudaEventDisableTiming));
+  CKC(cudaEventCreateWithFlags(&h->tables_free, cudaEventDisableTiming));
   CKC(cudaMalloc(&h->d_broad, ((om + 31) & ~(size_t)31) * tt * sizeof(float4)));
   CKC(cudaMalloc(&h->d_narrow, om * tt * sizeof(float4)));
   CKC(cudaMalloc(&h->d_obs64, om * tt * 4 * sizeof(double)));
@@ -424,6 +432,9 @@ int32_t jssp_destroy(jssp_handle* h) {
   if (h->d_fop_int) cudaFree(h->d_fop_int);
   if (h->h_raw) cudaFreeHost(h->h_raw);
   if (h->raw_done) cudaEventDestroy(h->raw_done);
+  if (h->tables_ready) cudaEventDestroy(h->tables_ready);
+  if (h->tables_free) cudaEventDestroy(h->tables_free);
+  if (h->up_stream) cudaStreamDestroy(h->up_stream);
   delete h;
   return JSSP_OK;
 }
@@ -495,12 +506,35 @@ int32_t jssp_set_obstacles(jssp_handle* h, const double* state, const uint8_t* v
     unsigned char* s = h->h_raw;
     memcpy(s, state, b_state); memcpy(s + b_state, size, b_size); memcpy(s + b_state + b_size, prob, b_prob);
     memcpy(s + b_state + b_size + b_prob, valid, b_valid);
-    CK(cudaMemcpyAsync(d, s, b_state + b_size + b_prob + b_valid, cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(h->raw_done, st));
+    // upload + pack on the private stream, after the last evaluation has finished with the tables; the caller's stream is not
+    // touched here, so e.g. the H2D copy of this cycle's seeds proceeds in parallel.  jssp_evaluate waits for tables_ready.
+    (void)st;
+    if (h->tables_in_use) CK(cudaStreamWaitEvent(h->up_stream, h->tables_free, 0));
+    CK(cudaMemcpyAsync(d, s, b_state + b_size + b_prob + b_valid, cudaMemcpyHostToDevice, h->up_stream));
+    CK(cudaEventRecord(h->raw_done, h->up_stream));
   }
   h->src_state = reinterpret_cast<const double*>(d); h->src_size = reinterpret_cast<const double*>(d + b_state);
   h->src_prob = reinterpret_cast<const double*>(d + b_state + b_size); h->src_valid = d + b_state + b_size + b_prob;
-  return pack_if_dirty(h, st);
+  rc = pack_if_dirty(h, h->up_stream);
+  if (rc != JSSP_OK) return rc;
+  CK(cudaEventRecord(h->tables_ready, h->up_stream));
+  h->wait_tables = true;
+  return JSSP_OK;
+}
+
+// make `st` wait for a pending private-stream upload of the obstacle tables
+static int32_t join_tables(jssp_handle* h, cudaStream_t st) {
+  if (h->wait_tables) {
+    CK(cudaStreamWaitEvent(st, h->tables_ready, 0));
+    h->wait_tables = false;
+  }
+  return JSSP_OK;
+}
+// the evaluation just enqueued on `st` reads the tables: the next private-stream upload must wait for it
+static int32_t mark_tables_in_use(jssp_handle* h, cudaStream_t st) {
+  CK(cudaEventRecord(h->tables_free, st));
+  h->tables_in_use = true;
+  return JSSP_OK;
 }
 
 int32_t jssp_set_obstacles_dev(jssp_handle* h, const double* state_dev, const uint8_t* valid_dev, const double* size_dev,
@@ -510,6 +544,8 @@ int32_t jssp_set_obstacles_dev(jssp_handle* h, const double* state_dev, const ui
   int rc = set_obstacles_common(h, O, M, Tt, n_dict);
   if (rc != JSSP_OK) return rc;
   CK(cudaSetDevice(h->device));
+  rc = join_tables(h, (cudaStream_t)stream);
+  if (rc != JSSP_OK) return rc;
   h->src_state = state_dev; h->src_valid = valid_dev; h->src_size = size_dev; h->src_prob = prob_dev;
   return pack_if_dirty(h, (cudaStream_t)stream);
 }
@@ -582,7 +618,8 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   if (W < 1 || W > JSSP_MAX_WIDTHS) return JSSP_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
-  int rc = pack_if_dirty(h, st);
+  int rc = join_tables(h, st);
+  if (rc == JSSP_OK) rc = pack_if_dirty(h, st);
   if (rc != JSSP_OK) return rc;
 
   EvalParams p{};
@@ -665,6 +702,8 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   else evaluate_kernel<0><<<blocks, EVAL_THREADS, L.total, st>>>(p);
   h->launches++;
   CK(cudaGetLastError());
+  rc = mark_tables_in_use(h, st);
+  if (rc != JSSP_OK) return rc;
   EvalParams q = p;
   q.smem_obs = 0; q.win_rows = 0; q.list_cap = 0;
   const SmemLayout L2 = eval_smem_layout(0, q.OMpad, 0, q.K, q.kpad, q.P, q.W);
@@ -714,7 +753,8 @@ int32_t jssp_fop_evaluate(jssp_handle* h, const jssp_fop_in* in, void* stream, j
   if (in->max_t > c.plan_horizon + 1e-9) return JSSP_ERR_CAPACITY;      // the handle's sample capacity follows plan_horizon
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
-  int rc = pack_if_dirty(h, st);
+  int rc = join_tables(h, st);
+  if (rc == JSSP_OK) rc = pack_if_dirty(h, st);
   if (rc != JSSP_OK) return rc;
   const int W = in->num_width, NT = in->num_t, NV = in->num_speed;
   const long long N = (long long)W * NT * NV;
@@ -766,6 +806,8 @@ int32_t jssp_fop_evaluate(jssp_handle* h, const jssp_fop_in* in, void* stream, j
   fop_select_export_kernel<<<1, EVAL_THREADS, L.total, st>>>(fp, blocks);
   h->launches += 2;
   CK(cudaGetLastError());
+  rc = mark_tables_in_use(h, st);
+  if (rc != JSSP_OK) return rc;
   h->last = p; h->last_valid = true; h->last_flags = in->flags;
   if (in->flags & JSSP_FLAG_NO_SYNC) return JSSP_OK;
   return jssp_fetch_best(h, stream, out);

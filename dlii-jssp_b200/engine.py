@@ -92,6 +92,7 @@ class JsspEngine:
         self.P = self.cfg.n_points
         cap = max_candidates or self.cfg.max_seeds * max(self.cfg.num_width, 1)
         self._cap = 0
+        self._views = {}
         self._alloc(cap)
         self._best_host = np.zeros((self.P, _lib.JSSP_TRAJ_COLS), dtype=np.float64)
         self._states: Optional[torch.Tensor] = None
@@ -250,8 +251,13 @@ class JsspEngine:
     def _result(self, cout, want_states, export) -> CycleResult:
         n = cout.n_candidates
         traj = self._best_host.copy() if (export and cout.best_idx >= 0) else None
-        return CycleResult(n, cout.n_seeds, cout.best_idx, cout.best_cost, cout.best_n_pts, traj, self.feasible[:n], self.collision[:n],
-                           self.cost[:n], self._states[:n] if want_states else None)
+        views = self._views.get(n)                     # tensor slicing costs microseconds per call: keep the views per size
+        if views is None or views[3] != self._cap:
+            if len(self._views) > 64:
+                self._views.clear()
+            views = self._views[n] = (self.feasible[:n], self.collision[:n], self.cost[:n], self._cap)
+        return CycleResult(n, cout.n_seeds, cout.best_idx, cout.best_cost, cout.best_n_pts, traj, views[0], views[1], views[2],
+                           self._states[:n] if want_states else None)
 
     def best_record(self, index_offset: int = 0) -> torch.Tensor:
         """Device int64[2] view of (orderable cost bits, global candidate index) of the last evaluate: the payload of the

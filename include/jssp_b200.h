@@ -143,6 +143,9 @@ int32_t jssp_set_refline(jssp_handle* h, const double* knot_s, const double* coe
  * host state[O][M][Tt][3] = x, y, yaw; host valid[O][M][Tt]; host size[O][2] = length, width (not inflated);
  * host prob[O][M]; n_dict = len(obstacles) for the `len(obstacles) <= 0` early-out (jssp.py:241).  M = 1, prob = 1
  * is the reference's ground-truth replay case. */
+/* The upload and the table packing run on a stream private to the handle (after the last evaluation has finished reading the
+ * tables); the next jssp_evaluate / jssp_fop_evaluate makes its stream wait for them.  `stream` is therefore not blocked: the
+ * caller can keep it busy with the other input of the cycle (e.g. the H2D copy of external seeds). */
 int32_t jssp_set_obstacles(jssp_handle* h, const double* state, const uint8_t* valid, const double* size,
                            const double* prob, int32_t O, int32_t M, int32_t Tt, int32_t n_dict, void* stream);
 /* same, from caller-owned DEVICE buffers (e.g. the output of jssp_imm_update / jssp_predict_modes) */
