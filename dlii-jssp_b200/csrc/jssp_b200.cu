@@ -391,16 +391,22 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   // one contiguous result block so that a cycle's results come back with a single copy:
   // [BestRecord, padded to 48 B][seed counts 16 B][selected trajectory P x 16 float64]
   static_assert(sizeof(BestRecord) <= 48, "result block layout");
+  // The result block [BestRecord, padded to 64 B][selected trajectory P x 16 float64] lives in MAPPED pinned host memory: the
+  // last block of the evaluation kernel writes the selection and the exported rows straight across the bus, so a cycle's
+  // results need no copy call at all - the host only waits for the stream.  The seed counters stay in device memory (every
+  // block reads them) with a 16-byte pinned mirror for the calls that report them.
+  static_assert(sizeof(BestRecord) <= 64, "result block layout");
   h->result_bytes = 64 + (size_t)h->P * JSSP_TRAJ_COLS * sizeof(double);
-  CKC(cudaMalloc(&h->d_result, h->result_bytes));
-  CKC(cudaMemset(h->d_result, 0, h->result_bytes));
-  CKC(cudaMallocHost(&h->h_result, h->result_bytes));
+  CKC(cudaHostAlloc(&h->h_result, h->result_bytes, cudaHostAllocMapped));
+  memset(h->h_result, 0, h->result_bytes);
+  CKC(cudaHostGetDevicePointer((void**)&h->d_result, h->h_result, 0));
   h->d_best = reinterpret_cast<BestRecord*>(h->d_result);
-  h->d_counts = reinterpret_cast<int*>(h->d_result + 48);
   h->d_best_traj = reinterpret_cast<double*>(h->d_result + 64);
   h->h_best = reinterpret_cast<BestRecord*>(h->h_result);
-  h->h_counts = reinterpret_cast<int*>(h->h_result + 48);
   h->h_best_traj = reinterpret_cast<double*>(h->h_result + 64);
+  CKC(cudaMalloc(&h->d_counts, 4 * sizeof(int)));
+  CKC(cudaMemset(h->d_counts, 0, 4 * sizeof(int)));
+  CKC(cudaMallocHost(&h->h_counts, 4 * sizeof(int)));
   h->seed_work = make_seed_work(h->grids, h->d_counts, h->d_seeds, cfg->max_seeds);
   h->seed_smem = seed_smem_bytes(h->seed_work);
   if (h->seed_smem > (size_t)h->max_smem_optin) return bail(JSSP_ERR_CAPACITY);
@@ -425,9 +431,10 @@ int32_t jssp_destroy(jssp_handle* h) {
   if (!h) return JSSP_OK;
   cudaSetDevice(h->device);
   void* dev[] = {h->d_time, h->d_j1, h->d_t1, h->d_t2, h->d_j3, h->d_t3, h->d_t4, h->d_jneg, h->d_jpos, h->d_ts, h->d_seeds,
-                 h->d_knot, h->d_coef, h->d_raw, h->d_broad, h->d_narrow, h->d_obs64, h->d_ext64, h->d_sint, h->d_probf, h->d_knot_xy, h->d_blk_cost, h->d_blk_idx, h->d_ticket, h->d_result};
+                 h->d_knot, h->d_coef, h->d_raw, h->d_broad, h->d_narrow, h->d_obs64, h->d_ext64, h->d_sint, h->d_probf, h->d_knot_xy, h->d_blk_cost, h->d_blk_idx, h->d_ticket, h->d_counts};
   for (void* p : dev) if (p) cudaFree(p);
   if (h->h_result) cudaFreeHost(h->h_result);
+  if (h->h_counts) cudaFreeHost(h->h_counts);
   if (h->d_fop_tab) cudaFree(h->d_fop_tab);
   if (h->d_fop_int) cudaFree(h->d_fop_int);
   if (h->h_raw) cudaFreeHost(h->h_raw);
@@ -592,8 +599,7 @@ int32_t jssp_fetch_best(jssp_handle* h, void* stream, jssp_cycle_out* out) {
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
   const bool want_traj = out->best_traj_host && !(h->last_flags & JSSP_FLAG_NO_EXPORT);
-  CK(cudaMemcpyAsync(h->h_result, h->d_result, want_traj ? h->result_bytes : 64, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  CK(cudaStreamSynchronize(st));      // the kernel wrote the result block into mapped host memory: nothing to copy
   out->n_candidates = h->h_best->n_candidates;
   out->n_seeds = h->h_best->n_seeds;
   out->best_idx = (int32_t)h->h_best->idx;
@@ -601,7 +607,7 @@ int32_t jssp_fetch_best(jssp_handle* h, void* stream, jssp_cycle_out* out) {
   out->best_n_pts = h->h_best->n_pts;
   if (want_traj && out->best_idx >= 0) memcpy(out->best_traj_host, h->h_best_traj, (size_t)h->P * JSSP_TRAJ_COLS * sizeof(double));
   // enumerated seeds: surface an overflow detected on the device
-  return (h->last.n_seeds_ptr && h->h_counts[3]) ? JSSP_ERR_SEED_OVERFLOW : JSSP_OK;
+  return (h->last.n_seeds_ptr && h->h_best->pad) ? JSSP_ERR_SEED_OVERFLOW : JSSP_OK;   // pad = the enumeration's overflow flag
 }
 
 int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jssp_cycle_out* out) {

@@ -835,7 +835,7 @@ __device__ __forceinline__ void select_and_export(const EvalParams& p, unsigned 
     r.n_pts = 0;
     r.n_candidates = N;
     r.n_seeds = Ns;
-    r.pad = 0;
+    r.pad = p.n_seeds_ptr ? p.n_seeds_ptr[3] : 0;   // seed-enumeration overflow flag, reported with the selection
     *p.best = r;
     *p.ticket = 0u;   // re-arm for the next launch (stream-ordered)
     red_idx[0] = my_idx;
