@@ -18,6 +18,12 @@ What it restates (reference = byChenZhifa/DLII-JSSP, paths relative to the refer
   rectangle collision, check_res=2   jerk_space_sampling_planner.py:211-286                     logic pinned; shapely -> SAT, ego footprint UNPINNED
   cost + argmin                      jerk_space_sampling_planner.py:288-294,326-327             cost function and tie rule UNPINNED
 
+Second pin (tests/golden/jssp_cycle_golden.npz, oracle/make_golden_cycle.py): the reference's own
+JerkSpaceSamplingPlanner.plan_traj is executed on four plan cycles of inputs/8_3_4_565 with stubs for the absent LEAF
+classes only, so the stage logic above the leaves (sampling order, truncation, forward-difference headings, un-unwrapped
+curvature, collision rows / time keys / inflation / window, survivor filtering, heap selection) is pinned by executable
+reference code: tests/test_oracle.py::test_oracle_matches_the_reference_plan_cycle.
+
 "parity unpinned" pieces: the reference's ``code/common/**`` package (CubicSpline2D, QuinticPolynomial,
 JerkSpaceSamplingCostFunction, Vehicle, the trajectory ordering) is absent from the published tree and
 the upstream it derives from (SS47816/fiss_plus_planner, cited README.md:199, which itself follows the

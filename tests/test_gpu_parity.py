@@ -216,3 +216,41 @@ def test_warp_and_thread_kernels_agree(n_seeds, n_widths, O_, M, horizon, seed):
         ref = O.plan_cycle(cfg, spline, fr, H.oracle_obstacles(cyc.obstacles), now, final, seeds=cyc.seeds, targets=cyc.targets)
         H.compare_cycle(eng.evaluate(fr, now, final, seeds=seeds, targets=cyc.targets, kernel="warp"), ref)
     eng.close()
+
+
+def test_cuda_path_matches_the_reference_plan_cycle(golden_dir, scenario_fixture):
+    """The CUDA plan cycle (device seed enumeration + evaluation + selection + export) directly against
+    tests/golden/jssp_cycle_golden.npz = the reference's own JerkSpaceSamplingPlanner.plan_traj run by
+    oracle/make_golden_cycle.py: candidate count, curvature mask, collision mask (where the reference evaluates it), survivor
+    costs, selected index and the selected trajectory - through every evaluation kernel."""
+    import os
+    sc = scenario_fixture
+    g = np.load(os.path.join(golden_dir, "jssp_cycle_golden.npz"))
+    final = int(sc.max_t / sc.dt)
+    obs = J.scenario.pack_obstacle_dict(sc.vehicle_traj, sc.dt, final + 52)
+    eng = J.JsspEngine(J.JsspConfig(ego_length=sc.ego["length"], ego_width=sc.ego["width"]))
+    sp = J.CubicSpline2D(sc.route_xy[:, 0], sc.route_xy[:, 1])
+    eng.set_refline(sp.s_list, sp.coefficient_table())
+    eng.set_obstacles(obs.state, obs.valid, obs.size, obs.prob, obs.n_dict)
+    for k, label in enumerate(g["labels"]):
+        label, fr, now = str(label), tuple(g["frenet0"][k]), int(float(g["t"][k]) / sc.dt)
+        eng.enumerate_seeds(*fr[:3])
+        for kern in (None, "thread", "group"):
+            res = eng.evaluate(fr, now, final, kernel=kern)
+            feas_ref = g[f"{label}_feasible"]
+            assert res.n_candidates == int(g[f"{label}_n"])
+            feas = res.feasible.cpu().numpy().astype(bool); coll = res.collision.cpu().numpy().astype(bool)
+            assert np.array_equal(feas, feas_ref), (label, kern)
+            assert np.array_equal(coll[feas_ref], ~g[f"{label}_collision_passed"][feas_ref]), (label, kern)
+            surv = ~np.isnan(g[f"{label}_cost"])
+            np.testing.assert_allclose(res.cost.cpu().numpy()[surv], g[f"{label}_cost"][surv], rtol=1e-4)
+            assert res.best_idx == int(g[f"{label}_best"]), (label, kern, res.best_idx)
+            if res.best_idx >= 0:
+                rows, tr = g[f"{label}_best_rows"], res.best_traj
+                npts = int(g[f"{label}_n_pts"][res.best_idx])
+                assert res.best_n_pts == npts
+                assert np.array_equal(tr[:, 1:5], rows[:, 1:5])                                  # s, s_d, s_dd, s_ddd bit-identical
+                np.testing.assert_allclose(tr[:, 5:9], rows[:, 5:9], rtol=1e-9, atol=1e-12)     # lateral quintic (closed form vs solve)
+                np.testing.assert_allclose(tr[:npts, 9:12], rows[:npts, 9:12], rtol=1e-9, atol=1e-9)
+                assert abs(res.best_cost - g[f"{label}_cost"][res.best_idx]) <= 1e-9 * abs(res.best_cost)
+    eng.close()

@@ -6,6 +6,8 @@ import warnings
 import numpy as np
 import pytest
 
+import os
+
 from oracle import jssp_oracle as O
 from oracle import jssp_loop as L
 
@@ -161,3 +163,66 @@ def test_fop_oracle_known_answers():
     best_cost = r["cost"][ok].min()
     ties = np.nonzero(ok & (r["cost"] == best_cost))[0]
     assert r["best"] == ties[-1]
+
+
+def _golden_cycles(golden_dir):
+    g = np.load(os.path.join(golden_dir, "jssp_cycle_golden.npz"))
+    for k, label in enumerate(g["labels"]):
+        yield str(label), tuple(g["frenet0"][k]), float(g["t"][k]), g
+
+
+def _check_against_reference_cycle(res, label, g, rtol_cost):
+    """res = dict with n, feasible, collision, cost, best, n_pts, and per-candidate arrays (oracle layout)."""
+    n = int(g[f"{label}_n"])
+    assert res["n"] == n
+    feas = g[f"{label}_feasible"]
+    assert np.array_equal(np.asarray(res["feasible"], bool), feas), label
+    # the reference only collision-checks the candidates that passed the curvature check (jssp.py:310-311)
+    coll_ref = ~g[f"{label}_collision_passed"][feas]
+    assert np.array_equal(np.asarray(res["collision"], bool)[feas], coll_ref), label
+    assert np.array_equal(np.asarray(res["n_pts"]), g[f"{label}_n_pts"]), label
+    surv = ~np.isnan(g[f"{label}_cost"])
+    assert np.array_equal(surv, feas & ~np.asarray(res["collision"], bool))
+    np.testing.assert_allclose(np.asarray(res["cost"], np.float64)[surv], g[f"{label}_cost"][surv], rtol=rtol_cost)
+    assert res["best"] == int(g[f"{label}_best"]), (label, res["best"], int(g[f"{label}_best"]))
+
+
+def test_oracle_matches_the_reference_plan_cycle(golden_dir, scenario_fixture):
+    """oracle.plan_cycle against tests/golden/jssp_cycle_golden.npz, produced by oracle/make_golden_cycle.py from the
+    reference's own JerkSpaceSamplingPlanner.plan_traj (leaf classes stubbed): sampled count, curvature mask, collision mask,
+    survivor costs, selected index, the selected trajectory and the Cartesian paths of a candidate subsample."""
+    sc = scenario_fixture
+    cfg = O.OracleConfig(ego_length=sc.ego["length"], ego_width=sc.ego["width"])
+    spline = O.CubicSpline2D(sc.route_xy[:, 0], sc.route_xy[:, 1])
+    final = int(sc.max_t / sc.dt)
+    state, valid, size = O.pack_obstacles(sc.vehicle_traj, sc.dt, final + cfg.n_steps + 2)[:3]
+    prob = np.ones(valid.shape[:2])
+    seen_no_solution = False
+    for label, fr, t, g in _golden_cycles(golden_dir):
+        with np.errstate(all="ignore"):
+            r = O.plan_cycle(cfg, spline, fr, (state, valid.astype(bool), size, prob), int(t / sc.dt), final)
+        _check_against_reference_cycle(r, label, g, rtol_cost=1e-12)
+        b = r["best"]
+        seen_no_solution |= b < 0
+        if b >= 0:
+            rows = g[f"{label}_best_rows"]
+            for col, key in ((1, "s"), (2, "s_d"), (3, "s_dd"), (4, "s_ddd")):
+                assert np.array_equal(r[key][b], rows[:, col]), key                      # the unroll is the reference's, bit for bit
+            for col, key in ((5, "d"), (6, "d_d"), (7, "d_dd"), (8, "d_ddd")):
+                np.testing.assert_allclose(r[key][b], rows[:, col], rtol=1e-12, atol=1e-14, err_msg=key)
+            npts = int(r["n_pts"][b])
+            for col, key in ((9, "x"), (10, "y"), (11, "yaw")):
+                np.testing.assert_allclose(r[key][b][:npts], rows[:npts, col], rtol=1e-12, atol=1e-12, err_msg=key)
+            np.testing.assert_allclose(r["c"][b][:npts - 1], rows[:npts - 1, 13], rtol=1e-9, atol=1e-12)
+        pick = g[f"{label}_pick"]
+        xy = g[f"{label}_pick_xyyawc"]
+        for q, n in enumerate(pick):
+            k = int(r["n_pts"][n])
+            np.testing.assert_allclose(r["x"][n][:k], xy[q, :k, 0], rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(r["y"][n][:k], xy[q, :k, 1], rtol=1e-12, atol=1e-12)
+            if k >= 2:
+                np.testing.assert_allclose(r["yaw"][n][:k], xy[q, :k, 2], rtol=1e-12, atol=1e-12)
+                with np.errstate(invalid="ignore"):
+                    fin = np.isfinite(xy[q, :k - 1, 3])
+                    np.testing.assert_allclose(r["c"][n][:k - 1][fin], xy[q, :k - 1, 3][fin], rtol=1e-9, atol=1e-12)
+    assert seen_no_solution                      # the t = 2 s cycle has no feasible candidate ("No solution", jssp.py:359-360)
