@@ -12,6 +12,11 @@ Restates code/intersection_local_planner/frenet_optimal_planner.py of byChenZhif
   cost  GoalSamplingCostFunction("WX1")   :128-133 (common.cost.cost_function)     UNPINNED: class absent -> builder specification
   best = LAST minimum (min_cost >= cost)  :328-333                                 pinned by reading
 
+Pin (tests/golden/fop_cycle_golden.npz, oracle/make_golden_fop.py): the reference's own FrenetOptimalPlanner methods
+(sampling_frenet_trajectories, calc_global_paths, check_constraints, check_collisions and the `>=` loop) are executed on
+plan cycles of inputs/8_3_4_565 with stubs for the absent leaf classes only; this oracle and the CUDA path reproduce the
+masks, costs, selection and trajectory (tests/test_oracle.py, tests/test_gpu_fop.py).
+
 Builder-specified cost (the class is absent; weights and layout are configuration_parameters.py:42-51, the same 8-entry
 vector the JSSP cost uses): the JSSP terms of jssp_oracle.cost_total over the candidate's own samples, with
 target speed = highest_speed, plus w_time * (1 - (Ti - t_min) / (t_max - t_min)) (0 when t_max == t_min).

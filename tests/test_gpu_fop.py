@@ -91,3 +91,36 @@ def test_fop_replay_matches_oracle_replay(scenario_fixture):
     cpu = replay_oracle.replay(sc, fr0, S.pack_obstacle_dict, R.end_status, R.goal_pose_of(sc), max_cycles=15, fop_cfg=cfg)
     assert gpu.best_idx == cpu["best_idx"] and gpu.n_candidates == cpu["n"] and gpu.end == cpu["end"]
     np.testing.assert_allclose(np.array(gpu.ego_rows), np.array(cpu["rows"]), rtol=1e-9, atol=1e-9)
+
+
+def test_fop_cuda_path_matches_the_reference_fop_methods(golden_dir, scenario_fixture):
+    """jssp_fop_evaluate directly against tests/golden/fop_cycle_golden.npz (the reference's own FOP methods run with stubbed
+    leaf classes, oracle/make_golden_fop.py): masks, costs, the last-minimum selection and the selected trajectory."""
+    import os
+    sc = scenario_fixture
+    g = np.load(os.path.join(golden_dir, "fop_cycle_golden.npz"))
+    W, NV, NT = [int(v) for v in g["grid"]]
+    veh = J.Vehicle(sc.ego["length"], sc.ego["width"], longitudinal_a_max=float(g["limits"][0]), longitudinal_jerk_max=float(g["limits"][1]))
+    st = J.FrenetOptimalPlannerSettings(num_width=W, num_speed=NV, num_t=NT, highest_speed=18.0, lowest_speed=0.0, min_planning_t=5.0, max_planning_t=5.5)
+    pl = J.FrenetOptimalPlanner(st, veh)
+    pl.cubic_spline = J.CubicSpline2D(sc.route_xy[:, 0], sc.route_xy[:, 1])
+    for k, label in enumerate(g["labels"]):
+        label, fr, t = str(label), tuple(g["frenet0"][k]), float(g["t"][k])
+        observation = sc.observation()
+        observation["test_setting"]["t"] = t
+        best = pl.plan_traj(J.FrenetState(s=fr[0], s_d=fr[1], s_dd=fr[2], d=fr[3], d_d=fr[4], d_dd=fr[5]), J.State(), sc.vehicle_traj, observation)
+        res = pl.last_result
+        feas = g[f"{label}_feasible"]
+        assert res.n_candidates == int(g[f"{label}_n"])
+        assert np.array_equal(res.feasible.cpu().numpy().astype(bool), feas)
+        assert np.array_equal(res.collision.cpu().numpy().astype(bool)[feas], ~g[f"{label}_collision_passed"][feas])
+        np.testing.assert_allclose(res.cost.cpu().numpy(), g[f"{label}_cost"], rtol=1e-4)
+        assert res.best_idx == int(g[f"{label}_best"])
+        rows = g[f"{label}_best_rows"]
+        assert len(best.s) == len(rows) and len(best.x) == int(g[f"{label}_n_pts"][res.best_idx])
+        for col, key in ((1, "s"), (2, "s_d"), (3, "s_dd"), (4, "s_ddd"), (5, "d"), (6, "d_d"), (7, "d_dd"), (8, "d_ddd")):
+            np.testing.assert_allclose(getattr(best, key), rows[:, col], rtol=1e-9, atol=1e-9, err_msg=key)
+        n = len(best.x)
+        for col, key in ((9, "x"), (10, "y"), (11, "yaw")):
+            np.testing.assert_allclose(getattr(best, key), rows[:n, col], rtol=1e-9, atol=1e-9, err_msg=key)
+    pl.engine.close()

@@ -226,3 +226,42 @@ def test_oracle_matches_the_reference_plan_cycle(golden_dir, scenario_fixture):
                     fin = np.isfinite(xy[q, :k - 1, 3])
                     np.testing.assert_allclose(r["c"][n][:k - 1][fin], xy[q, :k - 1, 3][fin], rtol=1e-9, atol=1e-12)
     assert seen_no_solution                      # the t = 2 s cycle has no feasible candidate ("No solution", jssp.py:359-360)
+
+
+def _fop_golden_cfg(g, sc):
+    from oracle import fop_oracle as F
+    W, NV, NT = [int(v) for v in g["grid"]]
+    return F.FopConfig(num_width=W, num_speed=NV, num_t=NT, min_t=5.0, max_t=5.5, highest_speed=18.0, max_accel=float(g["limits"][0]),
+                       max_jerk=float(g["limits"][1]), ego_length=sc.ego["length"], ego_width=sc.ego["width"])
+
+
+def test_fop_oracle_matches_the_reference_fop_methods(golden_dir, scenario_fixture):
+    """oracle.fop_oracle.plan_cycle against tests/golden/fop_cycle_golden.npz = the reference's own FrenetOptimalPlanner methods
+    (sampling_frenet_trajectories, calc_global_paths, check_constraints, check_collisions, `>=` selection) run by
+    oracle/make_golden_fop.py with the leaf classes stubbed."""
+    from oracle import fop_oracle as F
+    sc = scenario_fixture
+    g = np.load(os.path.join(golden_dir, "fop_cycle_golden.npz"))
+    cfg = _fop_golden_cfg(g, sc)
+    spline = O.CubicSpline2D(sc.route_xy[:, 0], sc.route_xy[:, 1])
+    final = int(sc.max_t / sc.dt)
+    state, valid, size = O.pack_obstacles(sc.vehicle_traj, sc.dt, final + 57)[:3]
+    prob = np.ones(valid.shape[:2])
+    for k, label in enumerate(g["labels"]):
+        label, fr, now = str(label), tuple(g["frenet0"][k]), int(float(g["t"][k]) / sc.dt)
+        with np.errstate(all="ignore"):
+            r = F.plan_cycle(cfg, spline, fr, (state, valid.astype(bool), size, prob), now, final)
+        feas = g[f"{label}_feasible"]
+        assert r["n"] == int(g[f"{label}_n"]) and np.array_equal(r["feasible"], feas)
+        assert np.array_equal(r["collision"][feas], ~g[f"{label}_collision_passed"][feas])
+        assert np.array_equal(r["n_pts"], g[f"{label}_n_pts"])
+        assert np.array_equal(np.count_nonzero(~np.isnan(r["s"]), axis=1), g[f"{label}_n_own"])       # per-candidate sample counts
+        np.testing.assert_allclose(r["cost"], g[f"{label}_cost"], rtol=1e-12)
+        assert r["best"] == int(g[f"{label}_best"])
+        b, rows = r["best"], g[f"{label}_best_rows"]
+        own = len(rows)
+        for col, key in ((1, "s"), (2, "s_d"), (3, "s_dd"), (4, "s_ddd"), (5, "d"), (6, "d_d"), (7, "d_dd"), (8, "d_ddd")):
+            np.testing.assert_allclose(r[key][b][:own], rows[:, col], rtol=1e-12, atol=1e-13, err_msg=key)
+        npts = int(r["n_pts"][b])
+        for col, key in ((9, "x"), (10, "y"), (11, "yaw")):
+            np.testing.assert_allclose(r[key][b][:npts], rows[:npts, col], rtol=1e-12, atol=1e-12, err_msg=key)
