@@ -86,6 +86,7 @@ class JsspScenarioIn(C.Structure):
         ("cycle_time", C.c_void_p), ("cycle_now", C.c_void_p), ("cycle_end_step", C.c_void_p),
         ("goal_x", C.c_double), ("goal_y", C.c_double), ("goal_yaw", C.c_double),
         ("ego_length", C.c_double), ("ego_width", C.c_double),
+        ("ego0", C.c_double * 4), ("bounds", C.c_double * 4), ("has_bounds", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 

@@ -54,6 +54,7 @@ class PackedScenario:
     cycle_end_step: np.ndarray    # [C+1] int32
     goal_pose: np.ndarray         # [3] x, y, yaw
     initial_end: float            # end status before the first cycle (a scenario can be over at t = 0)
+    bounds: Optional[np.ndarray] = None       # [4] x_min, x_max, y_min, y_max of the map (None: no map, no bounds test)
     gt_state: Optional[np.ndarray] = None     # ground truth for the end-status test when the planner sees predictions (M > 1)
     gt_valid: Optional[np.ndarray] = None
     gt_size: Optional[np.ndarray] = None
@@ -94,7 +95,8 @@ def pack_scenario(sc: ReplayScenario, plan_steps: int = 50, max_cycles: Optional
     p = PackedScenario(sc.name, spline.s_list.copy(), spline.coefficient_table(), gt.state, gt.valid, gt.size, gt.prob, gt.n_dict,
                        np.array(fr0, dtype=np.float64), np.array([e["x"], e["y"], e["v"], e["a"], e["yaw"], e["length"], e["width"]], dtype=np.float64),
                        float(sc.dt), float(sc.max_t), final, times, now, end, np.array(gp, dtype=np.float64),
-                       float(end_status(obs, sc, gp)))
+                       float(end_status(obs, sc, None)),                        # _get_initial_observation: no goal pose yet
+                       None if sc.bounds is None else np.array(sc.bounds, dtype=np.float64))
     if predictions is not None:
         assert predictions.state.shape[2] >= n_total, "predictions must cover final_time_step + horizon + 2 steps"
         p.gt_state, p.gt_valid, p.gt_size = gt.state[:, 0].copy(), gt.valid[:, 0].copy(), gt.size
@@ -104,7 +106,7 @@ def pack_scenario(sc: ReplayScenario, plan_steps: int = 50, max_cycles: Optional
 
 
 _ARRAY_FIELDS = ("knot_s", "coef", "state", "valid", "size", "prob", "frenet0", "ego", "cycle_time", "cycle_now", "cycle_end_step", "goal_pose",
-                 "gt_state", "gt_valid", "gt_size")
+                 "bounds", "gt_state", "gt_valid", "gt_size")
 
 
 def save_packed(path: str, packed: Sequence[PackedScenario]):
@@ -197,6 +199,11 @@ class BatchReplay:
             si.cycle_time, si.cycle_now, si.cycle_end_step = ptr[9], ptr[10], ptr[11]
             si.goal_x, si.goal_y, si.goal_yaw = [float(v) for v in p.goal_pose]
             si.ego_length, si.ego_width = float(p.ego[5]), float(p.ego[6])
+            si.ego0[0], si.ego0[1], si.ego0[2], si.ego0[3] = float(p.ego[0]), float(p.ego[1]), float(p.ego[4]), float(p.ego[2])   # x, y, yaw, v
+            si.has_bounds = 0 if p.bounds is None else 1
+            if p.bounds is not None:
+                for i in range(4):
+                    si.bounds[i] = float(p.bounds[i])
             self._check(self.lib.jssp_batch_set_scenario(self._h, slot, C.byref(si), self.stream), f"jssp_batch_set_scenario[{slot}]")
         self._n, self._packed = len(packed), list(packed)
 

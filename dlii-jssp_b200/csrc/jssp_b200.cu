@@ -9,6 +9,7 @@
 #include <new>
 #include <vector>
 #include <algorithm>
+#include <limits>
 
 #include "jssp_kernels.cuh"
 
@@ -1144,6 +1145,11 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
   q.end = -1.0; q.max_t = in->max_t; q.horizon = c.plan_horizon;
   q.goal_x = in->goal_x; q.goal_y = in->goal_y; q.goal_cos = std::cos(in->goal_yaw); q.goal_sin = std::sin(in->goal_yaw);
   q.ego_l = c.ego_length; q.ego_w = c.ego_width;
+  q.ego_x = in->ego0[0]; q.ego_y = in->ego0[1]; q.ego_yaw = in->ego0[2]; q.ego_v = in->ego0[3];
+  q.dt = c.delta_t;
+  const double inf = std::numeric_limits<double>::infinity();
+  q.bx_min = in->has_bounds ? in->bounds[0] : -inf; q.bx_max = in->has_bounds ? in->bounds[1] : inf;
+  q.by_min = in->has_bounds ? in->bounds[2] : -inf; q.by_max = in->has_bounds ? in->bounds[3] : inf;
   for (int w = 0; w < b->W; ++w) q.targets[w] = tg[w];
   q.cycle_time = ctime; q.cycle_now = cnow; q.cycle_end_step = cend;
   q.gt_state = gt_state; q.gt_valid = gt_valid; q.gt_size = gt_size;

@@ -67,6 +67,9 @@ struct BatchSlot {
   double max_t, horizon;
   double goal_x, goal_y, goal_cos, goal_sin;
   double ego_l, ego_w;
+  double ego_x, ego_y, ego_yaw, ego_v;   // the ego as the last Env.step left it (initially the scenario's start pose)
+  double dt;
+  double bx_min, bx_max, by_min, by_max; // map bounds (+-inf without a map)
   double targets[JSSP_MAX_WIDTHS];
   const double* cycle_time;       // [C+1] clock at the start of cycle c (host-accumulated float additions)
   const int* cycle_now;           // [C+1] int(t / dt)
@@ -736,15 +739,21 @@ __device__ __forceinline__ void batch_handoff(const EvalParams& p, int best, int
   const bool ok = best >= 0 && np >= 2;              // "No solution" / env.py:26 needs best_traj.x[1]
   const double* row1 = p.best_traj + JSSP_TRAJ_COLS;
   double tn = 0.0, x = 0.0, y = 0.0, yaw = 0.0;
+  // Env.step in planner_expected_value mode (env.py:21-33 -> controller.py:256-263): the ego is first advanced by the
+  // kinematic model with the action (0, 0) (controller.py:301-319) and the END STATUS is evaluated on that pose; only then is
+  // the ego overwritten with sample 1 of the selected trajectory.
+  const double kx = b->ego_x + b->ego_v * cos(b->ego_yaw) * b->dt, ky = b->ego_y + b->ego_v * sin(b->ego_yaw) * b->dt;
+  const double kyaw = fmod(b->ego_yaw + b->ego_v / b->ego_l * 1.7 * 0.0 * b->dt + 3.14159265358979323846, 2.0 * 3.14159265358979323846) -
+                      3.14159265358979323846;
   if (ok) {
     tn = b->cycle_time[c + 1];                       // t + dt (controller.py:303)
     x = row1[9]; y = row1[10]; yaw = row1[11];
     const int k = b->cycle_end_step[c + 1];
-    if (tn > 0.5 && k >= 0 && k < b->gt_Tt) {        // collision with a background vehicle (controller.py:343-349)
+    if (tn > 0.5 && k >= 0 && k < b->gt_Tt) {        // collision with a background vehicle (controller.py:343-349, 382-398)
       for (int o = threadIdx.x; o < b->gt_O; o += blockDim.x) {
         if (!b->gt_valid[(size_t)o * b->gt_Tt + k]) continue;
         const double* st = b->gt_state + ((size_t)o * b->gt_Tt + k) * 3;
-        if (rect_overlap_f64(x, y, yaw, b->ego_l, b->ego_w, st[0], st[1], st[2], b->gt_size[2 * o], b->gt_size[2 * o + 1])) atomicOr(sm_flag, 1);
+        if (rect_overlap_f64(kx, ky, kyaw, b->ego_l, b->ego_w, st[0], st[1], st[2], b->gt_size[2 * o], b->gt_size[2 * o + 1])) atomicOr(sm_flag, 1);
       }
     }
   }
@@ -762,8 +771,10 @@ __device__ __forceinline__ void batch_handoff(const EvalParams& p, int best, int
     double status = -1.0;
     if (*sm_flag) status = 2.0;
     if (tn >= b->max_t) status = fmax(status, 1.0);                                          // controller.py:352-353
-    const double dx = x - b->goal_x, dy = y - b->goal_y;
-    if (b->goal_sin * dy + b->goal_cos * dx >= 0.0) status = fmax(status, 1.5);               // goal line passed
+    if (kx > b->bx_max || kx < b->bx_min || ky > b->by_max || ky < b->by_min) status = fmax(status, 1.5);   // out of the map (:362-369)
+    const double dx = kx - b->goal_x, dy = ky - b->goal_y;
+    if (b->goal_sin * dy + b->goal_cos * dx >= 0.0) status = fmax(status, 1.5);               // goal line passed (:372-377)
+    b->ego_x = x; b->ego_y = y; b->ego_yaw = yaw; b->ego_v = row1[2];                         // env.py:26-30
     b->end = status;
     if (status != -1.0) b->live = 0;
     // next cycle starts from sample 1 of the selected trajectory (intersection_planner.py:312)

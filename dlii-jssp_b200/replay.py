@@ -5,7 +5,9 @@ the ego is moved to sample 1 of the selected trajectory (code/onsite_trans/env.p
 
 Only what the hot path needs is here: the state hand-off, the clock, and the end-of-scenario status of
 ReplayController._update_end_status (controller.py:338-380: collision with a background vehicle after t > 0.5, t >= max_t,
-goal line passed).  Map parsing, route search, visualisation, CSV recording and the kinematic-bicycle mode are out of scope
+map bounds, goal line passed) - evaluated, as in the reference, on the ego advanced by the kinematic model with the (0, 0)
+action, before Env.step overwrites it with sample 1 of the selected trajectory; pinned by tests/golden/replay_golden_*.npz,
+which oracle/make_golden_replay.py records from the reference's own Env.step / ReplayController.step.  Map parsing, route search, visualisation, CSV recording and the kinematic-bicycle mode are out of scope
 (SURVEY.md section 2); the route centre line comes with the scenario."""
 from __future__ import annotations
 
@@ -55,8 +57,25 @@ def goal_pose_of(scenario: ReplayScenario) -> tuple:
     return gx, gy, math.atan2(r[-1, 1] - r[-2, 1], r[-1, 0] - r[-2, 0])
 
 
-def end_status(observation: dict, scenario: ReplayScenario, goal_pose: tuple) -> float:
-    """ReplayController._update_end_status (controller.py:338-380) without the map-bounds test (no map here)."""
+def kinematic_ego(ego: dict, dt: float) -> dict:
+    """ReplayController._update_ego_and_t (controller.py:301-319) with the action (a, rot) = (0.0, 0.0) the driver passes in
+    ``planner_expected_value`` mode (code/__main__.py:139-140): the pose on which the end status of the new step is evaluated,
+    before Env.step overwrites the ego with sample 1 of the selected trajectory (env.py:23-30)."""
+    x, y, v, yaw = float(ego["x"]), float(ego["y"]), float(ego["v"]), float(ego["yaw"])
+    out = dict(ego)
+    out["x"] = x + v * np.cos(yaw) * dt
+    out["y"] = y + v * np.sin(yaw) * dt
+    yaw_new = yaw + v / float(ego["length"]) * 1.7 * np.tan(0.0) * dt
+    out["yaw"] = (yaw_new + np.pi) % (2 * np.pi) - np.pi
+    out["v"] = v + 0.0 * dt
+    out["a"] = 0.0
+    return out
+
+
+def end_status(observation: dict, scenario: ReplayScenario, goal_pose: Optional[tuple]) -> float:
+    """ReplayController._update_end_status (controller.py:338-380): collision of the ego with a background vehicle for
+    t > 0.5 (:382-398), t >= max_t, the bounds of an "intersection" map (``scenario.bounds``; scenarios without a map skip
+    it), goal line passed (``goal_pose`` None at initialisation, :297)."""
     status = [END_RUNNING]
     t = observation["test_setting"]["t"]
     ego = observation["vehicle_info"]["ego"]
@@ -70,10 +89,28 @@ def end_status(observation: dict, scenario: ReplayScenario, goal_pose: tuple) ->
                 break
     if t >= scenario.max_t:
         status.append(END_MAX_T)
-    dx, dy = ego["x"] - goal_pose[0], ego["y"] - goal_pose[1]
-    if math.sin(goal_pose[2]) * dy + math.cos(goal_pose[2]) * dx >= 0.0:
-        status.append(END_GOAL)
+    if scenario.bounds is not None:
+        x_min, x_max, y_min, y_max = scenario.bounds
+        if ego["x"] > x_max or ego["x"] < x_min or ego["y"] > y_max or ego["y"] < y_min:
+            status.append(END_GOAL)                            # 1.5: out of the map (:362-369)
+    if goal_pose is not None:
+        dx, dy = ego["x"] - goal_pose[0], ego["y"] - goal_pose[1]
+        if math.sin(goal_pose[2]) * dy + math.cos(goal_pose[2]) * dx >= 0.0:
+            status.append(END_GOAL)
     return max(status)
+
+
+def advance(observation: dict, scenario: ReplayScenario, goal_pose: tuple, best) -> None:
+    """One Env.step in ``planner_expected_value`` mode (env.py:21-33 -> controller.py:256-263): clock, kinematic ego with the
+    (0, 0) action, end status ON THAT POSE, then the ego is overwritten with sample 1 of the selected trajectory."""
+    ts = observation["test_setting"]
+    ego = observation["vehicle_info"]["ego"]
+    ts["t"] = float(ts["t"] + ts["dt"])                        # controller.py:303
+    observation["vehicle_info"]["ego"] = kinematic_ego(ego, ts["dt"])
+    ts["end"] = end_status(observation, scenario, goal_pose)   # controller.py:260
+    ego["x"], ego["y"], ego["yaw"] = float(best.x[1]), float(best.y[1]), float(best.yaw[1])     # env.py:26-30
+    ego["v"], ego["a"] = float(best.s_d[1]), float(best.s_dd[1])
+    observation["vehicle_info"]["ego"] = ego
 
 
 def run_replay(scenario: ReplayScenario, device: int = 0, max_cycles: Optional[int] = None, planner: Optional[IntersectionPlanner] = None,
@@ -87,7 +124,7 @@ def run_replay(scenario: ReplayScenario, device: int = 0, max_cycles: Optional[i
     planner.generate_frenet_frame(route)                       # __main__.py:100
     goal_pose = goal_pose_of(scenario)
     res = ReplayResult(scenario.name, END_RUNNING, 0)
-    obs["test_setting"]["end"] = end_status(obs, scenario, goal_pose)
+    obs["test_setting"]["end"] = end_status(obs, scenario, None)       # _get_initial_observation: no goal pose yet (controller.py:297)
     while obs["test_setting"]["end"] == END_RUNNING and (max_cycles is None or res.cycles < max_cycles):
         t0 = time.perf_counter()
         before = planner.fplanner.best_traj
@@ -105,13 +142,9 @@ def run_replay(scenario: ReplayScenario, device: int = 0, max_cycles: Optional[i
         if len(best.x) < 2:
             obs["test_setting"]["end"] = END_SHORT_TRAJ        # env.py:26 would raise IndexError on best_traj.x[1]
             break
-        ts = obs["test_setting"]
-        ts["t"] = float(ts["t"] + ts["dt"])                    # controller.py:303
-        ego = obs["vehicle_info"]["ego"]
-        ego["x"], ego["y"], ego["yaw"] = float(best.x[1]), float(best.y[1]), float(best.yaw[1])     # env.py:26-30
-        ego["v"], ego["a"] = float(best.s_d[1]), float(best.s_dd[1])
+        advance(obs, scenario, goal_pose, best)
+        ts, ego = obs["test_setting"], obs["vehicle_info"]["ego"]
         res.ego_rows.append((ts["t"], ego["x"], ego["y"], ego["v"], ego["a"], ego["yaw"]))
-        ts["end"] = end_status(obs, scenario, goal_pose)
     res.end = obs["test_setting"]["end"]
     return res
 

@@ -81,6 +81,7 @@ class ReplayScenario:
     dt: float
     max_t: float
     route_xy: Optional[np.ndarray] = None   # sparse centre line of the ego route [K, 2]
+    bounds: Optional[tuple] = None          # (x_min, x_max, y_min, y_max) of the map's lane vertices (controller.py:279-288); None = no map
 
     def observation(self) -> dict:
         """Initial observation dict in the reference's schema (code/onsite_trans/observation.py:25-46)."""
@@ -141,7 +142,8 @@ def scenario_from_fixture(npz_path: str, name: str = "8_3_4_565") -> ReplayScena
     for vid, t, x, y, v, a, yaw in z["obs_rows"]:
         traj[int(vid)][str(float(t))] = {"x": float(x), "y": float(y), "v": float(v), "a": float(a), "yaw": float(yaw)}
     goal = {"x": [float(v) for v in z["goal"][0]], "y": [float(v) for v in z["goal"][1]]}
-    return ReplayScenario(name, ego, traj, goal, float(z["dt"]), float(z["max_t"]), np.asarray(z["route_xy"], dtype=np.float64))
+    bounds = tuple(float(v) for v in z["bounds"]) if "bounds" in z.files else None
+    return ReplayScenario(name, ego, traj, goal, float(z["dt"]), float(z["max_t"]), np.asarray(z["route_xy"], dtype=np.float64), bounds)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -348,7 +350,7 @@ def perturbed_scenario(base: ReplayScenario, seed: int) -> ReplayScenario:
             entry[time_key(k, base.dt)] = {"x": round(st["x"] + off * nx, 2), "y": round(st["y"] + off * ny, 2), "v": st["v"], "a": st["a"], "yaw": st["yaw"]}
         traj[vid] = entry
     ego = dict(base.ego); ego["v"] = float(rng.uniform(2.0, 10.0))
-    return ReplayScenario(f"{base.name}_v{seed}", ego, traj, base.goal, base.dt, base.max_t, base.route_xy)
+    return ReplayScenario(f"{base.name}_v{seed}", ego, traj, base.goal, base.dt, base.max_t, base.route_xy, base.bounds)
 
 
 def multimodal_predictions(sc: ReplayScenario, M: int = 3, seed: int = 0, plan_steps: int = 50) -> ObstacleTensors:

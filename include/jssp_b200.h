@@ -231,7 +231,8 @@ int32_t jssp_project_states(jssp_handle* h, const double* state_dev, int32_t n, 
  * device itself performs the hand-off the reference does on the host - ego := sample 1 of best_traj
  * (code/onsite_trans/env.py:24-30), next Frenet start := best_traj.frenet_state_at_time_step(1)
  * (intersection_planner.py:312), t += dt (controller.py:303), end status (controller.py:338-380: collision with a
- * background vehicle for t > 0.5, t >= max_t, goal line passed; no map-bounds test) - so that a whole replay of S
+ * background vehicle for t > 0.5, t >= max_t, map bounds, goal line passed - evaluated, as in the reference, on the ego
+ * advanced by the kinematic model with the (0, 0) action) - so that a whole replay of S
  * scenarios costs 2 kernel launches per step and one result copy at the end.  Scenarios share one jssp_config
  * (sampling grids, limits, cost weights; the ego footprint may differ per scenario); capacities per scenario come from cfg.max_seeds / max_knots / max_obstacle_modes / max_total_steps. */
 typedef struct jssp_batch jssp_batch;
@@ -270,6 +271,12 @@ typedef struct jssp_scenario_in {
   const double* cycle_time; const int32_t* cycle_now; const int32_t* cycle_end_step;
   double goal_x, goal_y, goal_yaw;  /* goal pose: passed when sin(yaw)*dy + cos(yaw)*dx >= 0 */
   double ego_length, ego_width;     /* this scenario's ego footprint (observation["vehicle_info"]["ego"]); 0 -> jssp_config's */
+  double ego0[4];                   /* initial ego x, y, yaw, v: the end status of a step is evaluated on the ego advanced by the
+                                       kinematic model with the (0, 0) action (controller.py:256-263, 301-319), before the ego is
+                                       overwritten with sample 1 of the selected trajectory (env.py:23-30) */
+  double bounds[4];                 /* x_min, x_max, y_min, y_max of the map's lane vertices (controller.py:279-288) */
+  int32_t has_bounds;               /* 0: no map, the bounds test is skipped */
+  int32_t reserved2;
 } jssp_scenario_in;
 
 int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_scenarios, int32_t max_cycles, jssp_batch** out);

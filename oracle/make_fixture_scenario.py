@@ -93,8 +93,10 @@ def main(out):
             if key == "shape" or not isinstance(key, str):   # add_vehicle(t=-1, ...) leaves an empty {-1: {}} entry
                 continue
             rows.append((int(vid), float(key), st["x"], st["y"], st["v"], st["a"], st["yaw"]))
+    pv = np.concatenate([np.concatenate([l.left_vertices, l.right_vertices, l.center_vertices], 0) for l in info.road_info.discretelanes], 0)
+    bounds = np.array([pv[:, 0].min(), pv[:, 0].max(), pv[:, 1].min(), pv[:, 1].max()])       # controller.py:279-288 (x_min, x_max, y_min, y_max)
     np.savez_compressed(
-        out, route_xy=pts, route_lanes=np.array(route), ego=np.array([ego["x"], ego["y"], ego["v"], ego["a"], ego["yaw"], ego["length"], ego["width"]]),
+        out, bounds=bounds, route_xy=pts, route_lanes=np.array(route), ego=np.array([ego["x"], ego["y"], ego["v"], ego["a"], ego["yaw"], ego["length"], ego["width"]]),
         goal=np.array([goal["x"], goal["y"]]), dt=float(info.test_setting["dt"]), max_t=float(info.test_setting["max_t"]),
         obs_ids=np.array(ids), obs_shape=np.array(shape), obs_rows=np.array(rows))
     print("ego", ego, "goal", goal, "dt", info.test_setting["dt"], "max_t", info.test_setting["max_t"], "obstacles", len(ids), "rows", len(rows))

@@ -24,7 +24,7 @@ def replay(scenario, frenet0, pack_obstacles, end_status, goal_pose, max_cycles=
     obs = scenario.observation()
     out = dict(best_idx=[], n=[], rows=[], end=-1)
     fr = tuple(float(v) for v in frenet0)
-    obs["test_setting"]["end"] = end_status(obs, scenario, goal_pose)
+    obs["test_setting"]["end"] = end_status(obs, scenario, None)
     while obs["test_setting"]["end"] == -1 and (max_cycles is None or len(out["best_idx"]) < max_cycles):
         ts = obs["test_setting"]
         now = int(ts["t"] / ts["dt"])
@@ -42,12 +42,20 @@ def replay(scenario, frenet0, pack_obstacles, end_status, goal_pose, max_cycles=
         if r["n_pts"][b] < 2:
             ts["end"] = -3
             break
+        # Env.step in planner_expected_value mode (env.py:21-33, controller.py:256-263, 301-319): clock, kinematic ego with the
+        # (0, 0) action, end status on THAT pose, then the ego is overwritten with sample 1 of the selected trajectory
         ts["t"] = float(ts["t"] + ts["dt"])
         ego = obs["vehicle_info"]["ego"]
+        x0, y0, v0, yaw0 = float(ego["x"]), float(ego["y"]), float(ego["v"]), float(ego["yaw"])
+        kin = dict(ego)
+        kin["x"], kin["y"] = x0 + v0 * np.cos(yaw0) * ts["dt"], y0 + v0 * np.sin(yaw0) * ts["dt"]
+        kin["yaw"] = (yaw0 + v0 / float(ego["length"]) * 1.7 * np.tan(0.0) * ts["dt"] + np.pi) % (2 * np.pi) - np.pi
+        obs["vehicle_info"]["ego"] = kin
+        ts["end"] = end_status(obs, scenario, goal_pose)
         ego["x"], ego["y"], ego["yaw"] = float(r["x"][b, 1]), float(r["y"][b, 1]), float(r["yaw"][b, 1])
         ego["v"], ego["a"] = float(r["s_d"][b, 1]), float(r["s_dd"][b, 1])
+        obs["vehicle_info"]["ego"] = ego
         out["rows"].append((ts["t"], ego["x"], ego["y"], ego["v"], ego["a"], ego["yaw"]))
         fr = (r["s"][b, 1], r["s_d"][b, 1], r["s_dd"][b, 1], r["d"][b, 1], r["d_d"][b, 1], r["d_dd"][b, 1])
-        ts["end"] = end_status(obs, scenario, goal_pose)
     out["end"] = obs["test_setting"]["end"]
     return out

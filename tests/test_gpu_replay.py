@@ -59,3 +59,16 @@ def test_sweep_reuses_planner_and_matches_individual_replays():
     solo = [R.run_replay(sc, max_cycles=8) for sc in scs]
     for a, b in zip(sweep, solo):
         assert a.best_idx == b.best_idx and a.ego_rows == b.ego_rows and a.end == b.end
+
+
+def test_c1_replay_matches_the_reference_environment_golden(scenario_fixture, golden_dir):
+    """Full replay of inputs/8_3_4_565 - one scenario at a time and through the batched device-resident replay - against
+    tests/golden/replay_golden_8_3_4_565.npz, recorded from the reference's own Env.step / ReplayController.step driven by the
+    oracle planner (oracle/make_golden_replay.py): selected index per cycle, ego rows, end status."""
+    import os
+    from dlii_jssp_b200 import batch as B
+    g = np.load(os.path.join(golden_dir, "replay_golden_8_3_4_565.npz"))
+    for res in (R.run_replay(scenario_fixture), B.run_batch([scenario_fixture])[0]):
+        assert res.best_idx == g["best_idx"].tolist()
+        assert res.end == g["ends"][-1] and res.cycles == len(g["rows"])
+        np.testing.assert_allclose(np.array(res.ego_rows), g["rows"], rtol=1e-9, atol=1e-9)

@@ -194,3 +194,33 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             J.BatchReplay()
     assert C.sizeof(_lib.JsspCycleRecord) == 64 and C.sizeof(_lib.JsspScenarioResult) == 16 and C.sizeof(_lib.JsspFopIn) == 6 * 8 + 6 * 4 + 6 * 8
+
+
+def test_replay_step_semantics_match_the_reference_environment(golden_dir, scenario_fixture):
+    """tests/golden/replay_golden_8_3_4_565.npz was recorded from the reference's own Env.step / ReplayController.step
+    (oracle/make_golden_replay.py).  Replaying its ego rows through the product's host logic must give the same end status
+    at every step: clock, kinematic ego with the (0, 0) action, status on THAT pose (collision, max_t, map bounds, goal line)."""
+    from dlii_jssp_b200 import replay as R
+    g = np.load(os.path.join(golden_dir, "replay_golden_8_3_4_565.npz"))
+    sc = scenario_fixture
+    assert sc.bounds is not None and np.allclose(sc.bounds, g["bounds"])
+    gp = R.goal_pose_of(sc)
+    assert np.allclose(gp, g["goal_pose"])
+    obs = sc.observation()
+    assert R.end_status(obs, sc, None) == g["ends"][0]
+    rows, ends = g["rows"], g["ends"]
+    for k in range(len(rows)):
+        class Best:                                    # the fields Env.step reads from best_traj (env.py:26-30)
+            x = [None, rows[k, 1]]; y = [None, rows[k, 2]]; yaw = [None, rows[k, 5]]; s_d = [None, rows[k, 3]]; s_dd = [None, rows[k, 4]]
+        R.advance(obs, sc, gp, Best)
+        assert obs["test_setting"]["t"] == rows[k, 0]
+        assert obs["test_setting"]["end"] == ends[k + 1], (k, obs["test_setting"]["end"], ends[k + 1])
+        e = obs["vehicle_info"]["ego"]
+        assert (e["x"], e["y"], e["v"], e["a"], e["yaw"]) == tuple(rows[k, 1:6])
+    assert ends[-1] == 1.5 and (ends[:-1] == -1).all()
+    # the status is taken on the kinematic pose, not on the planner's: a goal line just behind the planner pose of the last
+    # step but ahead of the kinematic pose must not end the replay
+    k = len(rows) - 1
+    prev = dict(sc.ego); prev.update(x=rows[k - 1, 1], y=rows[k - 1, 2], v=rows[k - 1, 3], a=rows[k - 1, 4], yaw=rows[k - 1, 5])
+    kin = R.kinematic_ego(prev, sc.dt)
+    assert np.hypot(kin["x"] - rows[k, 1], kin["y"] - rows[k, 2]) > 1e-6          # the two poses differ
