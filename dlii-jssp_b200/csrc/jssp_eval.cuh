@@ -62,7 +62,8 @@ struct BatchSlot {
   int final_step;                 // int(max_t / dt)
   int gt_O, gt_Tt;                // ground-truth background vehicles and steps of their table
   int n_cycles_cap;               // the per-cycle tables hold n_cycles_cap + 1 entries: the replay pauses after that many cycles
-  int seed_overflow, pad1;        // a cycle enumerated more seeds than max_seeds (the surplus was dropped): reported, never silent
+  int seed_overflow;              // a cycle enumerated more seeds than max_seeds (the surplus was dropped): reported, never silent
+  int last_n_pts;                 // Cartesian points of the trajectory in best_traj (0 = no trajectory selected yet)
   double end;                     // end status: -1 running, 1 max_t, 1.5 goal, 2 collision, -2 no solution, -3 short trajectory
   double max_t, horizon;
   double goal_x, goal_y, goal_cos, goal_sin;
@@ -735,8 +736,11 @@ __device__ __forceinline__ void batch_handoff(const EvalParams& p, int best, int
   if (threadIdx.x == 0) *sm_flag = 0;
   __syncthreads();
   const int c = b->cycle;
-  const int np = best >= 0 ? p.best->n_pts : 0;
-  const bool ok = best >= 0 && np >= 2;              // "No solution" / env.py:26 needs best_traj.x[1]
+  // "No solution" keeps the previous best_traj (jerk_space_sampling_planner.py:359-362) and the driver re-applies ITS sample 1:
+  // the export buffer still holds that trajectory.  Without a previous one (first cycle) the replay ends (-2).
+  const bool fresh = best >= 0;
+  const int np = fresh ? p.best->n_pts : b->last_n_pts;
+  const bool ok = np >= 2;                           // env.py:26 needs best_traj.x[1]
   const double* row1 = p.best_traj + JSSP_TRAJ_COLS;
   double tn = 0.0, x = 0.0, y = 0.0, yaw = 0.0;
   // Env.step in planner_expected_value mode (env.py:21-33 -> controller.py:256-263): the ego is first advanced by the
@@ -764,7 +768,7 @@ __device__ __forceinline__ void batch_handoff(const EvalParams& p, int best, int
   rec->best_idx = best; rec->n_candidates = N; rec->best_cost = best >= 0 ? p.best->cost : nan("");
   if (!ok) {
     rec->t = rec->x = rec->y = rec->v = rec->a = rec->yaw = nan("");
-    b->end = best < 0 ? -2.0 : -3.0;
+    b->end = (!fresh && b->last_n_pts == 0) ? -2.0 : -3.0;
     b->live = 0;
   } else {
     rec->t = tn; rec->x = x; rec->y = y; rec->v = row1[2]; rec->a = row1[3]; rec->yaw = yaw;
@@ -775,6 +779,7 @@ __device__ __forceinline__ void batch_handoff(const EvalParams& p, int best, int
     const double dx = kx - b->goal_x, dy = ky - b->goal_y;
     if (b->goal_sin * dy + b->goal_cos * dx >= 0.0) status = fmax(status, 1.5);               // goal line passed (:372-377)
     b->ego_x = x; b->ego_y = y; b->ego_yaw = yaw; b->ego_v = row1[2];                         // env.py:26-30
+    if (fresh) b->last_n_pts = np;
     b->end = status;
     if (status != -1.0) b->live = 0;
     // next cycle starts from sample 1 of the selected trajectory (intersection_planner.py:312)

@@ -127,7 +127,6 @@ def run_replay(scenario: ReplayScenario, device: int = 0, max_cycles: Optional[i
     obs["test_setting"]["end"] = end_status(obs, scenario, None)       # _get_initial_observation: no goal pose yet (controller.py:297)
     while obs["test_setting"]["end"] == END_RUNNING and (max_cycles is None or res.cycles < max_cycles):
         t0 = time.perf_counter()
-        before = planner.fplanner.best_traj
         try:
             planner.plan(obs, scenario.vehicle_traj, ego_update_mode="planner_expected_value")     # __main__.py:129
         except ValueError:                                         # "No solution available" on the very first cycle
@@ -135,9 +134,12 @@ def run_replay(scenario: ReplayScenario, device: int = 0, max_cycles: Optional[i
         res.plan_seconds.append(time.perf_counter() - t0)
         r = planner.fplanner.last_result
         res.best_idx.append(r.best_idx); res.n_candidates.append(r.n_candidates); res.cycles += 1
+        # "No solution" keeps the previous best_traj (jerk_space_sampling_planner.py:359-362): the driver then re-applies ITS
+        # sample 1 - the ego stays where it is, the clock advances, the next cycle starts from the same Frenet state.  Without a
+        # previous trajectory (first cycle) the reference's fallback raises (intersection_planner.py:332-337) and the scenario ends.
         best = planner.fplanner.best_traj
-        if r.best_idx < 0 or best is before:
-            obs["test_setting"]["end"] = END_NO_SOLUTION       # the reference's fallback is broken here
+        if best is None:
+            obs["test_setting"]["end"] = END_NO_SOLUTION
             break
         if len(best.x) < 2:
             obs["test_setting"]["end"] = END_SHORT_TRAJ        # env.py:26 would raise IndexError on best_traj.x[1]

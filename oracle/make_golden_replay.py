@@ -76,7 +76,7 @@ def main(out):
     state, valid, size = O.pack_obstacles(info.vehicle_traj, ts["dt"], final + cfg.n_steps + 2)[:3]
     prob = np.ones(valid.shape[:2])
     fr = tuple(B.pack_scenario(sc).frenet0)
-    rows, ends, best_idx = [], [float(ts["end"])], []
+    rows, ends, best_idx, prev = [], [float(ts["end"])], [], None
     while obs["test_setting"]["end"] == -1:
         t = obs["test_setting"]["t"]
         now = int(t / obs["test_setting"]["dt"])
@@ -84,7 +84,12 @@ def main(out):
             r = O.plan_cycle(cfg, spline, fr, (state, valid.astype(bool), size, prob), now, final)
         b = r["best"]
         best_idx.append(b)
-        if b < 0 or r["n_pts"][b] < 2:
+        if b < 0:                                                   # "No solution": plan_traj returns the previous best_traj (jssp.py:359-362)
+            if prev is None:
+                break                                               # first cycle: the reference's fallback raises (intersection_planner.py:332-337)
+            r, b = prev
+        prev = (r, b)
+        if r["n_pts"][b] < 2:
             break
         best = types.SimpleNamespace(x=r["x"][b], y=r["y"][b], yaw=r["yaw"][b], s_d=r["s_d"][b], s_dd=r["s_dd"][b])
         with contextlib.redirect_stdout(io.StringIO()):

@@ -24,6 +24,7 @@ def replay(scenario, frenet0, pack_obstacles, end_status, goal_pose, max_cycles=
     obs = scenario.observation()
     out = dict(best_idx=[], n=[], rows=[], end=-1)
     fr = tuple(float(v) for v in frenet0)
+    prev = None
     obs["test_setting"]["end"] = end_status(obs, scenario, None)
     while obs["test_setting"]["end"] == -1 and (max_cycles is None or len(out["best_idx"]) < max_cycles):
         ts = obs["test_setting"]
@@ -37,8 +38,13 @@ def replay(scenario, frenet0, pack_obstacles, end_status, goal_pose, max_cycles=
         b = r["best"]
         out["best_idx"].append(b); out["n"].append(r["n"])
         if b < 0:
-            ts["end"] = -2
-            break
+            # "No solution": plan_traj returns the PREVIOUS best_traj (jerk_space_sampling_planner.py:359-362), whose sample 1 the
+            # driver re-applies; on the first cycle there is none and the reference's fallback raises (intersection_planner.py:332-337)
+            if prev is None:
+                ts["end"] = -2
+                break
+            r, b = prev
+        prev = (r, b)
         if r["n_pts"][b] < 2:
             ts["end"] = -3
             break
