@@ -1189,7 +1189,9 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   bool small = (long long)n_scenarios * b->cfg.max_seeds * b->W <= 65536 && small_bytes <= (size_t)b->max_smem_optin;
   if (flags & (JSSP_FLAG_FORCE_THREAD | JSSP_FLAG_FORCE_GROUP)) small = false;
   if ((flags & JSSP_FLAG_FORCE_WARP) && small_bytes <= (size_t)b->max_smem_optin) small = true;
-  const bool group = !small && !(flags & JSSP_FLAG_FORCE_THREAD);
+  // thread per candidate for the default 3 lateral targets (a scenario's ~150 seeds fill the group kernel's 40-seed blocks and
+  // 30-of-32 lanes poorly: measured 49.0 vs 53.9 ms on the 800-scenario sweep), the group kernel from 4 targets on
+  const bool group = !small && !(flags & JSSP_FLAG_FORCE_THREAD) && ((flags & JSSP_FLAG_FORCE_GROUP) || b->W >= 4);
   // 128-thread blocks in the batch: a scenario has only a few hundred candidates, so smaller blocks leave fewer idle
   // lanes in its last block and spread its work over more SMs (measured: 800-scenario sweep 50.3 -> 47.7 ms)
   const int bthreads = BATCH_EVAL_THREADS;
