@@ -254,3 +254,67 @@ def test_cuda_path_matches_the_reference_plan_cycle(golden_dir, scenario_fixture
                 np.testing.assert_allclose(tr[:npts, 9:12], rows[:npts, 9:12], rtol=1e-9, atol=1e-9)
                 assert abs(res.best_cost - g[f"{label}_cost"][res.best_idx]) <= 1e-9 * abs(res.best_cost)
     eng.close()
+
+
+@pytest.mark.parametrize("yaw_o", [0.0, 0.3])
+def test_guard_band_decisions_near_touching_rectangles(yaw_o):
+    """The fp32 separating-axis classification with its 2 mm guard band must hand every near-tie to the float64 test: obstacles
+    placed so that their rectangle is within -3 mm .. +3 mm (down to 1e-12 m, and exactly touching) of the ego footprint's side
+    give the oracle's collision mask bit for bit - shapely's closed-set ``intersects`` counts touching as a hit."""
+    route = np.column_stack([np.linspace(0.0, 120.0, 241), np.zeros(241)])
+    rng = np.random.default_rng(5)
+    seeds = J.scenario.random_seeds(96, rng)
+    cfg = H.oracle_config(4.924, 1.872)
+    spline = O.CubicSpline2D(route[:, 0], route[:, 1])
+    eng = H.engine_for(J, cfg, max_seeds=96, max_obstacle_modes=1, max_total_steps=60)
+    eng.set_refline(spline.s_list, spline.coefficient_table())
+    seeds_d = torch.from_numpy(seeds).cuda()
+    fr = (0.0, 6.0, 0.0, 0.0, 0.0, 0.0)                     # d = 0 towards target 0: the ego rectangle stays axis-aligned
+    L, Wd = 8.0, 2.0
+    a, b = (L + 0.1) / 2.0, (Wd + 0.1) / 2.0                 # inflated half sizes (jssp.py:263-265)
+    # lateral extent of the rotated obstacle rectangle; gap = y_o - extent - ego half width
+    ext = a * abs(np.sin(yaw_o)) + b * abs(np.cos(yaw_o))
+    seen = set()
+    for delta in (0.0, 1e-12, -1e-12, 1e-9, -1e-9, 1e-6, -1e-6, 1e-4, -1e-4, 1.9e-3, -1.9e-3, 2.1e-3, -2.1e-3, 3e-3, -3e-3):
+        y_o = 1.872 / 2.0 + ext + delta
+        state = np.zeros((1, 1, 60, 3)); state[0, 0, :, 0] = 14.0; state[0, 0, :, 1] = y_o; state[0, 0, :, 2] = yaw_o
+        valid = np.ones((1, 1, 60), dtype=np.uint8); size = np.array([[L, Wd]]); prob = np.ones((1, 1))
+        eng.set_obstacles(state, valid, size, prob, 1)
+        ref = O.plan_cycle(cfg, spline, fr, (state, valid.astype(bool), size, prob), 0, 55, seeds=seeds, targets=[0.0])
+        for kern in ("warp", "thread", "group"):
+            res = eng.evaluate(fr, 0, 55, seeds=seeds_d, targets=[0.0], kernel=kern)
+            assert np.array_equal(res.collision.cpu().numpy().astype(bool), ref["collision"]), (delta, kern)
+            assert res.best_idx == ref["best"]
+        seen.add(bool(ref["collision"].any()))
+    assert seen == {True, False}                              # both sides of the tie were exercised
+    eng.close()
+
+
+def test_guard_band_decisions_near_the_curvature_limit():
+    """The square-root/atan-free curvature fast path must hand every near-tie to the float64 atan2 form: with max_curvature set
+    within 1e-10 .. 1e-3 (relative) above and below a candidate's own largest |c|, the feasible mask equals the oracle's."""
+    cyc = J.scenario.dense_cycle(n_seeds=48, n_widths=1, O=0, M=1, seed=9)
+    spline = O.CubicSpline2D(cyc.route_xy[:, 0], cyc.route_xy[:, 1])
+    fr = (22.0, 7.0, 0.0, 0.3, 0.0, 0.0)                     # starts just before the 15 m-radius arc
+    base = H.oracle_config(cyc.ego_length, cyc.ego_width)
+    empty = H.oracle_obstacles(cyc.obstacles)
+    with np.errstate(all="ignore"):
+        r0 = O.plan_cycle(base, spline, fr, empty, 0, 100, seeds=cyc.seeds, targets=[0.0])
+        cmax = np.nanmax(np.abs(r0["c"]), axis=1)
+    pivot = float(np.sort(cmax[np.isfinite(cmax) & (cmax < 1.0)])[len(cmax) // 2])      # a candidate in the middle of the pack
+    seeds_d = torch.from_numpy(cyc.seeds).cuda()
+    flips = set()
+    for eps in (1e-10, -1e-10, 1e-8, -1e-8, 9e-7, -9e-7, 1.1e-6, -1.1e-6, 1e-5, -1e-5, 1e-3, -1e-3):
+        cfg = H.oracle_config(cyc.ego_length, cyc.ego_width, max_curvature=pivot * (1.0 + eps))
+        with np.errstate(all="ignore"):
+            ref = O.plan_cycle(cfg, spline, fr, empty, 0, 100, seeds=cyc.seeds, targets=[0.0])
+        eng = H.engine_for(J, cfg, max_seeds=48, max_obstacle_modes=1, max_total_steps=cyc.obstacles.state.shape[2])
+        eng.set_refline(spline.s_list, spline.coefficient_table())
+        o = cyc.obstacles
+        eng.set_obstacles(o.state, o.valid, o.size, o.prob, o.n_dict)
+        for kern in ("warp", "thread", "group"):
+            res = eng.evaluate(fr, 0, 100, seeds=seeds_d, targets=[0.0], kernel=kern)
+            assert np.array_equal(res.feasible.cpu().numpy().astype(bool), ref["feasible"]), (eps, kern)
+        flips.add(int(ref["feasible"].sum()))
+        eng.close()
+    assert len(flips) >= 2                                    # the pivot candidate changes side across the sweep
