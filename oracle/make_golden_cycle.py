@@ -116,6 +116,24 @@ def install_stubs():
         def __init__(self, t=0.0, s=0.0, s_d=0.0, s_dd=0.0, s_ddd=0.0, d=0.0, d_d=0.0, d_dd=0.0, d_ddd=0.0):
             self.t, self.s, self.s_d, self.s_dd, self.s_ddd, self.d, self.d_d, self.d_dd, self.d_ddd = t, s, s_d, s_dd, s_ddd, d, d_d, d_dd, d_ddd
 
+        def from_state(self, state, polyline):
+            """Builder-specified projection (the class is absent): nearest point of the re-discretised reference line, chord-length
+            arc sum, left-hand normal, speed / acceleration split by the heading error (dlii-jssp_b200/frenet.py states the same)."""
+            d2 = (polyline[:, 0] - state.x) ** 2 + (polyline[:, 1] - state.y) ** 2
+            i = int(np.argmin(d2))
+            seg = np.hypot(np.diff(polyline[:, 0]), np.diff(polyline[:, 1]))
+            rx, ry, ryaw = polyline[i, 0], polyline[i, 1], polyline[i, 2]
+            dx, dy = state.x - rx, state.y - ry
+            tx, ty = math.cos(ryaw), math.sin(ryaw)
+            self.t = state.t
+            self.s = float(seg[:i].sum()) + (dx * tx + dy * ty)
+            self.d = -dx * ty + dy * tx
+            dyaw = state.yaw - ryaw
+            self.s_d, self.d_d = state.v * math.cos(dyaw), state.v * math.sin(dyaw)
+            self.s_dd, self.d_dd = state.a * math.cos(dyaw), state.a * math.sin(dyaw)
+            self.s_ddd = self.d_ddd = 0.0
+            return self
+
     class JerkSpaceSamplingFrenetTrajectory:
         def __init__(self):
             for f in FIELDS:
@@ -135,9 +153,14 @@ def install_stubs():
         def __lt__(self, other):
             return False
 
+        def frenet_state_at_time_step(self, t=1):                    # intersection_planner.py:312
+            return FrenetState(t=self.t[t], s=self.s[t], s_d=self.s_d[t], s_dd=self.s_dd[t], s_ddd=self.s_ddd[t],
+                               d=self.d[t], d_d=self.d_d[t], d_dd=self.d_dd[t], d_ddd=self.d_ddd[t])
+
     class Vehicle:
-        def __init__(self, length, width, max_curvature=0.2, **_):
+        def __init__(self, length, width, max_curvature=0.2, longitudinal_a_max=8.0, longitudinal_jerk_max=10.0, **_):
             self.l, self.w, self.max_curvature = length, width, max_curvature
+            self.max_accel, self.max_jerk = longitudinal_a_max, longitudinal_jerk_max
             self.polygon = Polygon([(length / 2, width / 2), (length / 2, -width / 2), (-length / 2, -width / 2), (-length / 2, width / 2)])
 
     class JerkSpaceSamplingCostFunction:
@@ -172,6 +195,10 @@ def install_stubs():
     poly = mod("common.geometry.polynomial"); poly.QuinticPolynomial = O.QuinticPolynomial; poly.QuarticPolynomial = object
     fr = mod("common.scenario.frenet")
     fr.State, fr.FrenetState, fr.JerkSpaceSamplingFrenetTrajectory = State, FrenetState, JerkSpaceSamplingFrenetTrajectory
+    fr.GoalSamplingFrenetTrajectory = JerkSpaceSamplingFrenetTrajectory
+    mod("common.tool")
+    sys.modules["common"].tool = sys.modules["common.tool"]
+    mod("common.cost.cost_function").GoalSamplingCostFunction = JerkSpaceSamplingCostFunction    # constructed, never used, by the "frenet" wiring
     mod("common.vehicle.vehicle").Vehicle = Vehicle
     mod("spatio_temporal_graph_node").StNode = object
     mod("common.plot_scripts.plot_polyvt_sampling").plot_jerk_sampling_of_best_traj = lambda *a, **k: None

@@ -16,7 +16,10 @@ What this pins - by executable reference code - is the driver-side semantics of 
     "intersection" map, goal line) - BEFORE Env.step overwrites the ego with sample 1 of the selected trajectory,
   * the overwritten ego is what the next step starts from.
 
-Usage:  python oracle/make_golden_replay.py  [out.npz]
+With ``--full`` the planner in the loop is the reference's own too (IntersectionPlanner.plan -> JerkSpaceSamplingPlanner.plan_traj,
+leaf classes stubbed; ~7 minutes of Python); the result is stored under ``full_*`` and must equal the oracle-planner loop.
+
+Usage:  python oracle/make_golden_replay.py  [--full]
 """
 import contextlib
 import io
@@ -33,6 +36,56 @@ REF = "/root/reference"
 NAME = "8_3_4_565"
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
+
+
+def full_reference_loop(parser0, sc, goal_pose):
+    """The WHOLE reference loop (code/__main__.py:124-167): its own IntersectionPlanner.plan (intersection_planner.py:304-343)
+    calling its own JerkSpaceSamplingPlanner.plan_traj, and its own Env.step - with the leaf stubs only.  Two pieces of wiring
+    are supplied here because the published tree lacks them: init_local_planner has no "JSSP" branch (the planner object is
+    built with the intended settings) and plan_global_route needs the absent common.tool (the route
+    centre line of the fixture is handed to the reference's own generate_frenet_frame)."""
+    import types
+    from onsite_trans.controller import Controller, ReplayController, ReplayParser
+    from onsite_trans.env import Env
+    sys.path.insert(0, os.path.join(REF, "code", "intersection_local_planner"))
+    import intersection_local_planner.intersection_planner as ip   # the unmodified reference façade
+    import intersection_local_planner.jerk_space_sampling_planner as jp
+    base = os.path.join(REF, "inputs", NAME)
+    parser = ReplayParser()
+    parser._parse_openscenario(os.path.join(base, NAME + "_exam.xosc"))
+    parser._parse_opendrive(os.path.join(base, NAME + ".xodr"))
+    info = parser.replay_info
+    ctl = Controller()
+    ctl.mode, ctl.parser, ctl.control_info, ctl.controller = "replay", parser, info, ReplayController()
+    ctl.observation = ctl.controller.init(info)
+    ctl.traj = info.vehicle_traj
+    env = object.__new__(Env)
+    env.controller = ctl
+    env.recorder = types.SimpleNamespace(record=lambda obs: None)
+    obs = ctl.observation.format()
+    with contextlib.redirect_stdout(io.StringIO()):
+        planner = ip.IntersectionPlanner(ip.PlannerSettings(), obs, "frenet")          # the only branch the published wiring has
+        planner.method = "JSSP"
+        planner.fplanner = jp.JerkSpaceSamplingPlanner(
+            jp.JerkSpaceSamplingPlannerSettings(num_width=3, num_jerk=25, delta_t=0.1, max_road_width=3.5, highest_jerk=10.0, plan_horizon=5.0,
+                                                traj_num_max=50), planner.ego_vehicle)
+        planner.fplanner.cubic_spline, _ = planner.generate_frenet_frame(sc.route_xy)   # __main__.py:100
+    rows, ends, best_idx = [], [float(obs["test_setting"]["end"])], []
+    while obs["test_setting"]["end"] == -1:
+        with contextlib.redirect_stdout(io.StringIO()):
+            before = planner.fplanner.best_traj
+            planner.plan(obs, info.vehicle_traj, ego_update_mode="planner_expected_value")          # __main__.py:129
+            best = planner.fplanner.best_traj
+            sampled = planner.fplanner.all_path_sampling_trajs[-1]
+            pos = [n for n, tr in enumerate(sampled) if tr is best]
+            best_idx.append(pos[0] if pos and best is not before else -1)
+            obs = env.step(action=(0.0, 0.0), observation_last=100, traj=info.vehicle_traj, best_traj_ego=best,
+                           ego_update_mode="planner_expected_value", goal_pose=goal_pose)             # __main__.py:158-165
+        e = obs["vehicle_info"]["ego"]
+        rows.append((obs["test_setting"]["t"], e["x"], e["y"], e["v"], e["a"], e["yaw"]))
+        ends.append(float(obs["test_setting"]["end"]))
+        print(f"  full loop step {len(rows)} t={rows[-1][0]:.1f} best={best_idx[-1]} end={ends[-1]}", flush=True)
+    return {"full_rows": np.array(rows), "full_ends": np.array(ends), "full_best_idx": np.array(best_idx)}
 
 
 def main(out):
@@ -99,11 +152,20 @@ def main(out):
         rows.append((obs["test_setting"]["t"], e["x"], e["y"], e["v"], e["a"], e["yaw"]))
         ends.append(float(obs["test_setting"]["end"]))
         fr = (r["s"][b, 1], r["s_d"][b, 1], r["s_dd"][b, 1], r["d"][b, 1], r["d_d"][b, 1], r["d_dd"][b, 1])
+    extra = {}
+    if "--full" in sys.argv:
+        extra = full_reference_loop(parser, sc, goal_pose)
+        assert extra["full_best_idx"].tolist() == best_idx and np.array_equal(extra["full_ends"], np.array(ends))
+        np.testing.assert_allclose(extra["full_rows"], np.array(rows), rtol=1e-12, atol=1e-12)
+        print("full reference loop == oracle-planner loop:", len(extra["full_rows"]), "steps")
+    elif os.path.exists(out):                                        # keep a previously recorded full loop
+        old = np.load(out)
+        extra = {k: old[k] for k in old.files if k.startswith("full_")}
     np.savez_compressed(out, rows=np.array(rows), ends=np.array(ends), best_idx=np.array(best_idx), bounds=bounds,
-                        goal_pose=np.array(goal_pose), map_type=np.array(str(info.test_setting["map_type"])))
+                        goal_pose=np.array(goal_pose), map_type=np.array(str(info.test_setting["map_type"])), **extra)
     print(f"{len(rows)} steps, final end {ends[-1]}, last t {rows[-1][0] if rows else None}")
     print("wrote", out, os.path.getsize(out), "bytes")
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "tests", "golden", f"replay_golden_{NAME}.npz"))
+    main(os.path.join(ROOT, "tests", "golden", f"replay_golden_{NAME}.npz"))

@@ -69,6 +69,6 @@ def test_c1_replay_matches_the_reference_environment_golden(scenario_fixture, go
     from dlii_jssp_b200 import batch as B
     g = np.load(os.path.join(golden_dir, "replay_golden_8_3_4_565.npz"))
     for res in (R.run_replay(scenario_fixture), B.run_batch([scenario_fixture])[0]):
-        assert res.best_idx == g["best_idx"].tolist()
-        assert res.end == g["ends"][-1] and res.cycles == len(g["rows"])
-        np.testing.assert_allclose(np.array(res.ego_rows), g["rows"], rtol=1e-9, atol=1e-9)
+        assert res.best_idx == g["best_idx"].tolist() == g["full_best_idx"].tolist()          # full_*: the reference's own planner in the loop
+        assert res.end == g["ends"][-1] == g["full_ends"][-1] and res.cycles == len(g["rows"])
+        np.testing.assert_allclose(np.array(res.ego_rows), g["full_rows"], rtol=1e-9, atol=1e-9)

@@ -218,6 +218,10 @@ def test_replay_step_semantics_match_the_reference_environment(golden_dir, scena
         e = obs["vehicle_info"]["ego"]
         assert (e["x"], e["y"], e["v"], e["a"], e["yaw"]) == tuple(rows[k, 1:6])
     assert ends[-1] == 1.5 and (ends[:-1] == -1).all()
+    # the same file holds the run of the WHOLE reference loop (its own IntersectionPlanner.plan -> JerkSpaceSamplingPlanner.plan_traj
+    # -> Env.step, leaf classes stubbed; make_golden_replay.py --full): identical, cycle by cycle
+    assert g["full_best_idx"].tolist() == g["best_idx"].tolist() and np.array_equal(g["full_ends"], ends)
+    np.testing.assert_allclose(g["full_rows"], rows, rtol=1e-12, atol=1e-12)
     # the status is taken on the kinematic pose, not on the planner's: a goal line just behind the planner pose of the last
     # step but ahead of the kinematic pose must not end the replay
     k = len(rows) - 1
