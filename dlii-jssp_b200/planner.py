@@ -26,6 +26,8 @@ VEHICLE_PARA = {"speed_max": 18.0, "lon_accel_max": 8.0, "lon_jerk_max": 10.0, "
                 "centripetal_accel_max": 2.0}
 PARA_THRESHOLD = {"speed_max": 18.0, "lon_accel_max": 3.0, "lon_jerk_max": 6.0, "lateral_accel_max": 0.5, "lateral_jerk_max": 1.0,
                   "centripetal_accel_max": 1.0}
+# paras_control["pure_pursuit"] (configuration_parameters.py:27-33)
+PURE_PURSUIT = {"kv_ld0": [0.35, 4.8], "coff_wheel_base": 1.7}
 PLANNER_JSSP = {"num_width": 3, "num_jerk": 25, "plan_horizon": 5.0, "cost_wights": [0.0, 3.0, 5.4, 0.2, 0.1, 0.8, 0.4, 4.0],
                 "max_distance": 140.0, "traj_num_max": 50}
 
@@ -241,6 +243,31 @@ class IntersectionPlanner:
     def generate_frenet_frame(self, centerline_pts: np.ndarray):
         self.cubic_spline, self.ref_ego_lane_pts = self.fplanner.generate_frenet_frame(centerline_pts)
         return self.cubic_spline, self.ref_ego_lane_pts
+
+    # -- path tracking of the "kinematics" ego-update mode (intersection_planner.py:363-443) ---------------------------------
+    @staticmethod
+    def find_lookahead_point_by_curve_distance(pos: np.ndarray, ref_pos: np.ndarray, ld: float = 5.0):
+        """Same contract as intersection_planner.py:365-389: from the way point nearest to ``pos`` walk along the path until
+        the accumulated arc length reaches ``ld``; returns (point, index)."""
+        dist = np.linalg.norm(ref_pos - pos, axis=1)
+        idx = int(np.argmin(dist))
+        l_steps = 0
+        while l_steps < ld and idx + 1 < len(ref_pos):
+            l_steps += np.linalg.norm(ref_pos[idx + 1] - ref_pos[idx])
+            idx += 1
+        return ref_pos[idx], idx
+
+    def pure_pursuit_control(self, kv: float = PURE_PURSUIT["kv_ld0"][0], ld0: float = PURE_PURSUIT["kv_ld0"][1],
+                             tracing: str = "plan_path") -> float:
+        """Front-wheel angle of the pure-pursuit tracker (intersection_planner.py:416-443) on the selected trajectory
+        (``plan_path``, the published configuration) or on the re-discretised reference line (``ref_path``)."""
+        ref_pos = self.ref_ego_lane_pts[:, 0:2] if tracing == "ref_path" else np.column_stack((self.fplanner.best_traj.x, self.fplanner.best_traj.y))
+        ld = kv * self.ego_state.v + ld0
+        pos = np.array([self.ego_state.x, self.ego_state.y])
+        point, idx = self.find_lookahead_point_by_curve_distance(pos, ref_pos, ld)
+        alpha = np.arctan2(point[1] - pos[1], point[0] - pos[0]) - self.ego_state.yaw
+        wheel_base = self.ego_vehicle.l / PURE_PURSUIT["coff_wheel_base"]
+        return np.arctan2(2 * wheel_base * np.sin(alpha), ld)
 
     def plan(self, observation, traj_future=None, ego_update_mode="planner_expected_value"):
         self.ego_state = self._get_ego_states(observation)

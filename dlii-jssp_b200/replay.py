@@ -57,18 +57,22 @@ def goal_pose_of(scenario: ReplayScenario) -> tuple:
     return gx, gy, math.atan2(r[-1, 1] - r[-2, 1], r[-1, 0] - r[-2, 0])
 
 
-def kinematic_ego(ego: dict, dt: float) -> dict:
-    """ReplayController._update_ego_and_t (controller.py:301-319) with the action (a, rot) = (0.0, 0.0) the driver passes in
-    ``planner_expected_value`` mode (code/__main__.py:139-140): the pose on which the end status of the new step is evaluated,
-    before Env.step overwrites the ego with sample 1 of the selected trajectory (env.py:23-30)."""
+def kinematic_ego(ego: dict, dt: float, action=(0.0, 0.0)) -> dict:
+    """ReplayController._update_ego_and_t (controller.py:301-319) after _action_cheaker's clipping (:265-268).  With the action
+    (a, rot) = (0.0, 0.0) the driver passes in ``planner_expected_value`` mode (code/__main__.py:139-140) this is the pose on
+    which the end status of the new step is evaluated, before Env.step overwrites the ego with sample 1 of the selected
+    trajectory (env.py:23-30); in ``kinematics`` mode (acceleration, front-wheel angle) it IS the new ego."""
+    a, rot = np.clip(action[0], -15, 15), np.clip(action[1], -1, 1)
     x, y, v, yaw = float(ego["x"]), float(ego["y"]), float(ego["v"]), float(ego["yaw"])
     out = dict(ego)
     out["x"] = x + v * np.cos(yaw) * dt
     out["y"] = y + v * np.sin(yaw) * dt
-    yaw_new = yaw + v / float(ego["length"]) * 1.7 * np.tan(0.0) * dt
+    yaw_new = yaw + v / float(ego["length"]) * 1.7 * np.tan(rot) * dt
     out["yaw"] = (yaw_new + np.pi) % (2 * np.pi) - np.pi
-    out["v"] = v + 0.0 * dt
-    out["a"] = 0.0
+    out["v"] = v + a * dt
+    if out["v"] < 0:
+        out["v"] = 0
+    out["a"] = a
     return out
 
 
@@ -100,23 +104,28 @@ def end_status(observation: dict, scenario: ReplayScenario, goal_pose: Optional[
     return max(status)
 
 
-def advance(observation: dict, scenario: ReplayScenario, goal_pose: tuple, best) -> None:
-    """One Env.step in ``planner_expected_value`` mode (env.py:21-33 -> controller.py:256-263): clock, kinematic ego with the
-    (0, 0) action, end status ON THAT POSE, then the ego is overwritten with sample 1 of the selected trajectory."""
+def advance(observation: dict, scenario: ReplayScenario, goal_pose: tuple, best, ego_update_mode: str = "planner_expected_value",
+            action=(0.0, 0.0)) -> None:
+    """One Env.step (env.py:21-33 -> controller.py:256-263): clock, kinematic ego with ``action``, end status ON THAT POSE;
+    in ``planner_expected_value`` mode (action = (0, 0)) the ego is then overwritten with sample 1 of the selected trajectory."""
     ts = observation["test_setting"]
     ego = observation["vehicle_info"]["ego"]
     ts["t"] = float(ts["t"] + ts["dt"])                        # controller.py:303
-    observation["vehicle_info"]["ego"] = kinematic_ego(ego, ts["dt"])
+    observation["vehicle_info"]["ego"] = kinematic_ego(ego, ts["dt"], action)
     ts["end"] = end_status(observation, scenario, goal_pose)   # controller.py:260
-    ego["x"], ego["y"], ego["yaw"] = float(best.x[1]), float(best.y[1]), float(best.yaw[1])     # env.py:26-30
-    ego["v"], ego["a"] = float(best.s_d[1]), float(best.s_dd[1])
-    observation["vehicle_info"]["ego"] = ego
+    if ego_update_mode == "planner_expected_value":
+        ego["x"], ego["y"], ego["yaw"] = float(best.x[1]), float(best.y[1]), float(best.yaw[1])     # env.py:26-30
+        ego["v"], ego["a"] = float(best.s_d[1]), float(best.s_dd[1])
+        observation["vehicle_info"]["ego"] = ego
 
 
 def run_replay(scenario: ReplayScenario, device: int = 0, max_cycles: Optional[int] = None, planner: Optional[IntersectionPlanner] = None,
-               method: str = "JSSP", **planner_kwargs) -> ReplayResult:
-    """Replay one scenario with the CUDA planner (``method`` = "JSSP" or the "frenet" baseline, paras_planner["planner_type"]).
-    Returns per-cycle selections and the ego rows the reference would record."""
+               method: str = "JSSP", ego_update_mode: str = "planner_expected_value", **planner_kwargs) -> ReplayResult:
+    """Replay one scenario with the CUDA planner (``method`` = "JSSP" or the "frenet" baseline, paras_planner["planner_type"];
+    ``ego_update_mode`` = parameters["sim_config"]["ego_update_mode"]: the default "planner_expected_value", or "kinematics" -
+    every cycle starts from the projected ego state and the ego follows the kinematic model driven by the planned acceleration
+    and the pure-pursuit steering angle, code/__main__.py:136-138).  Returns per-cycle selections and the ego rows the reference
+    would record."""
     obs = scenario.observation()
     if planner is None:
         planner = IntersectionPlanner(PlannerSettings(), obs, method, device=device, **planner_kwargs)
@@ -127,8 +136,9 @@ def run_replay(scenario: ReplayScenario, device: int = 0, max_cycles: Optional[i
     obs["test_setting"]["end"] = end_status(obs, scenario, None)       # _get_initial_observation: no goal pose yet (controller.py:297)
     while obs["test_setting"]["end"] == END_RUNNING and (max_cycles is None or res.cycles < max_cycles):
         t0 = time.perf_counter()
+        plan_acc = 0.0
         try:
-            planner.plan(obs, scenario.vehicle_traj, ego_update_mode="planner_expected_value")     # __main__.py:129
+            plan_acc = planner.plan(obs, scenario.vehicle_traj, ego_update_mode=ego_update_mode)    # __main__.py:129
         except ValueError:                                         # "No solution available" on the very first cycle
             pass
         res.plan_seconds.append(time.perf_counter() - t0)
@@ -144,7 +154,8 @@ def run_replay(scenario: ReplayScenario, device: int = 0, max_cycles: Optional[i
         if len(best.x) < 2:
             obs["test_setting"]["end"] = END_SHORT_TRAJ        # env.py:26 would raise IndexError on best_traj.x[1]
             break
-        advance(obs, scenario, goal_pose, best)
+        action = (plan_acc, planner.pure_pursuit_control()) if ego_update_mode == "kinematics" else (0.0, 0.0)     # __main__.py:136-140
+        advance(obs, scenario, goal_pose, best, ego_update_mode, action)
         ts, ego = obs["test_setting"], obs["vehicle_info"]["ego"]
         res.ego_rows.append((ts["t"], ego["x"], ego["y"], ego["v"], ego["a"], ego["yaw"]))
     res.end = obs["test_setting"]["end"]

@@ -19,7 +19,11 @@ What this pins - by executable reference code - is the driver-side semantics of 
 With ``--full`` the planner in the loop is the reference's own too (IntersectionPlanner.plan -> JerkSpaceSamplingPlanner.plan_traj,
 leaf classes stubbed; ~7 minutes of Python); the result is stored under ``full_*`` and must equal the oracle-planner loop.
 
-Usage:  python oracle/make_golden_replay.py  [--full]
+``--kinematics`` records the same complete loop in the reference's other ego-update mode (parameters["sim_config"]
+["ego_update_mode"] = "kinematics": every cycle starts from FrenetState.from_state of the ego, the action is the planned
+acceleration and the reference's own pure_pursuit_control, the ego follows the kinematic model) under ``kin_*``.
+
+Usage:  python oracle/make_golden_replay.py  [--full] [--kinematics]
 """
 import contextlib
 import io
@@ -38,7 +42,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
 
-def full_reference_loop(parser0, sc, goal_pose):
+def full_reference_loop(parser0, sc, goal_pose, mode="planner_expected_value", prefix="full_"):
     """The WHOLE reference loop (code/__main__.py:124-167): its own IntersectionPlanner.plan (intersection_planner.py:304-343)
     calling its own JerkSpaceSamplingPlanner.plan_traj, and its own Env.step - with the leaf stubs only.  Two pieces of wiring
     are supplied here because the published tree lacks them: init_local_planner has no "JSSP" branch (the planner object is
@@ -70,22 +74,25 @@ def full_reference_loop(parser0, sc, goal_pose):
             jp.JerkSpaceSamplingPlannerSettings(num_width=3, num_jerk=25, delta_t=0.1, max_road_width=3.5, highest_jerk=10.0, plan_horizon=5.0,
                                                 traj_num_max=50), planner.ego_vehicle)
         planner.fplanner.cubic_spline, _ = planner.generate_frenet_frame(sc.route_xy)   # __main__.py:100
-    rows, ends, best_idx = [], [float(obs["test_setting"]["end"])], []
+    rows, ends, best_idx, actions = [], [float(obs["test_setting"]["end"])], [], []
     while obs["test_setting"]["end"] == -1:
         with contextlib.redirect_stdout(io.StringIO()):
             before = planner.fplanner.best_traj
-            planner.plan(obs, info.vehicle_traj, ego_update_mode="planner_expected_value")          # __main__.py:129
+            plan_acc = planner.plan(obs, info.vehicle_traj, ego_update_mode=mode)                    # __main__.py:129
             best = planner.fplanner.best_traj
             sampled = planner.fplanner.all_path_sampling_trajs[-1]
             pos = [n for n, tr in enumerate(sampled) if tr is best]
             best_idx.append(pos[0] if pos and best is not before else -1)
-            obs = env.step(action=(0.0, 0.0), observation_last=100, traj=info.vehicle_traj, best_traj_ego=best,
-                           ego_update_mode="planner_expected_value", goal_pose=goal_pose)             # __main__.py:158-165
+            action = (plan_acc, planner.pure_pursuit_control()) if mode == "kinematics" else (0.0, 0.0)   # __main__.py:136-140
+            obs = env.step(action=action, observation_last=100, traj=info.vehicle_traj, best_traj_ego=best,
+                           ego_update_mode=mode, goal_pose=goal_pose)                                 # __main__.py:158-165
         e = obs["vehicle_info"]["ego"]
         rows.append((obs["test_setting"]["t"], e["x"], e["y"], e["v"], e["a"], e["yaw"]))
         ends.append(float(obs["test_setting"]["end"]))
-        print(f"  full loop step {len(rows)} t={rows[-1][0]:.1f} best={best_idx[-1]} end={ends[-1]}", flush=True)
-    return {"full_rows": np.array(rows), "full_ends": np.array(ends), "full_best_idx": np.array(best_idx)}
+        actions.append((float(action[0]), float(action[1])))
+        print(f"  {prefix}loop step {len(rows)} t={rows[-1][0]:.1f} best={best_idx[-1]} end={ends[-1]}", flush=True)
+    return {prefix + "rows": np.array(rows), prefix + "ends": np.array(ends), prefix + "best_idx": np.array(best_idx),
+            prefix + "actions": np.array(actions)}
 
 
 def main(out):
@@ -158,9 +165,11 @@ def main(out):
         assert extra["full_best_idx"].tolist() == best_idx and np.array_equal(extra["full_ends"], np.array(ends))
         np.testing.assert_allclose(extra["full_rows"], np.array(rows), rtol=1e-12, atol=1e-12)
         print("full reference loop == oracle-planner loop:", len(extra["full_rows"]), "steps")
-    elif os.path.exists(out):                                        # keep a previously recorded full loop
+    elif os.path.exists(out):                                        # keep previously recorded full loops
         old = np.load(out)
-        extra = {k: old[k] for k in old.files if k.startswith("full_")}
+        extra = {k: old[k] for k in old.files if k.startswith("full_") or k.startswith("kin_")}
+    if "--kinematics" in sys.argv:                                   # ego_update_mode = "kinematics": projected start state every cycle,
+        extra.update(full_reference_loop(parser, sc, goal_pose, mode="kinematics", prefix="kin_"))   # pure-pursuit steering, kinematic ego
     np.savez_compressed(out, rows=np.array(rows), ends=np.array(ends), best_idx=np.array(best_idx), bounds=bounds,
                         goal_pose=np.array(goal_pose), map_type=np.array(str(info.test_setting["map_type"])), **extra)
     print(f"{len(rows)} steps, final end {ends[-1]}, last t {rows[-1][0] if rows else None}")

@@ -72,3 +72,15 @@ def test_c1_replay_matches_the_reference_environment_golden(scenario_fixture, go
         assert res.best_idx == g["best_idx"].tolist() == g["full_best_idx"].tolist()          # full_*: the reference's own planner in the loop
         assert res.end == g["ends"][-1] == g["full_ends"][-1] and res.cycles == len(g["rows"])
         np.testing.assert_allclose(np.array(res.ego_rows), g["full_rows"], rtol=1e-9, atol=1e-9)
+
+
+def test_c1_kinematics_mode_replay_matches_the_reference_loop(scenario_fixture, golden_dir):
+    """parameters["sim_config"]["ego_update_mode"] = "kinematics": every cycle starts from the projected ego state, the ego follows
+    the kinematic model driven by the planned acceleration and the pure-pursuit steering angle.  Against kin_* of
+    replay_golden_8_3_4_565.npz = the reference's own complete loop in that mode (make_golden_replay.py --kinematics)."""
+    import os
+    g = np.load(os.path.join(golden_dir, "replay_golden_8_3_4_565.npz"))
+    res = R.run_replay(scenario_fixture, ego_update_mode="kinematics")
+    assert res.best_idx == g["kin_best_idx"].tolist()
+    assert res.end == g["kin_ends"][-1] and res.cycles == len(g["kin_rows"])
+    np.testing.assert_allclose(np.array(res.ego_rows), g["kin_rows"], rtol=1e-8, atol=1e-8)

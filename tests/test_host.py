@@ -228,3 +228,22 @@ def test_replay_step_semantics_match_the_reference_environment(golden_dir, scena
     prev = dict(sc.ego); prev.update(x=rows[k - 1, 1], y=rows[k - 1, 2], v=rows[k - 1, 3], a=rows[k - 1, 4], yaw=rows[k - 1, 5])
     kin = R.kinematic_ego(prev, sc.dt)
     assert np.hypot(kin["x"] - rows[k, 1], kin["y"] - rows[k, 2]) > 1e-6          # the two poses differ
+
+
+def test_pure_pursuit_and_kinematic_update_match_the_reference_loop(golden_dir, scenario_fixture):
+    """kin_* of the replay golden (the reference's own loop in "kinematics" mode): applying the recorded actions through the
+    product's kinematic update reproduces the recorded ego rows and end statuses; the pure-pursuit look-ahead walk is the
+    reference's (intersection_planner.py:365-389)."""
+    from dlii_jssp_b200 import replay as R
+    g = np.load(os.path.join(golden_dir, "replay_golden_8_3_4_565.npz"))
+    sc = scenario_fixture
+    gp = R.goal_pose_of(sc)
+    obs = sc.observation()
+    for k, (acc, steer) in enumerate(g["kin_actions"]):
+        R.advance(obs, sc, gp, None, "kinematics", (acc, steer))
+        e = obs["vehicle_info"]["ego"]
+        np.testing.assert_allclose((obs["test_setting"]["t"], e["x"], e["y"], e["v"], e["a"], e["yaw"]), g["kin_rows"][k], rtol=0, atol=1e-12)
+        assert obs["test_setting"]["end"] == g["kin_ends"][k + 1]
+    path = np.column_stack([np.linspace(0, 10, 21), np.zeros(21)])
+    pt, idx = J.IntersectionPlanner.find_lookahead_point_by_curve_distance(np.array([1.1, 0.3]), path, 2.2)
+    assert idx == 7 and np.allclose(pt, [3.5, 0.0])                    # nearest way point 2 (x = 1.0), then 5 steps of 0.5 m >= 2.2 m
