@@ -206,6 +206,14 @@ def replay_latency(device: int, cpu: bool = True) -> dict:
     return out
 
 
+def measured_hbm_gbs() -> float:
+    """HBM copy bandwidth of this pool's B200s from the driver-written MEASURED_PEAKS.json (fallback: the figure it held in round 1)."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6544.3
+
+
 def ncu_evidence(kernel_s=None) -> dict:
     """Counters of the dominant kernel from the committed ncu capture (profiles/, `ncu --set full` of this very command):
     evidence about the kernel measured under the profiler, never a bench value.  With ``kernel_s`` (the live kernel time)
@@ -366,7 +374,7 @@ def run_ours(args):
                              "peak_source": "measured live: FFMA micro-benchmark in libjssp_b200 (MEASURED_PEAKS.json has no CUDA-core figure); "
                                             "fp64 FMA peak %.1f TFLOP/s" % peak64.value,
                              "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes,
-                             "kernel_ms": 1e3 * k_avg_s, "hbm_frac_of_measured": (alg_bytes / k_avg_s / 1e9) / 6544.3,
+                             "kernel_ms": 1e3 * k_avg_s, "hbm_frac_of_measured": (alg_bytes / k_avg_s / 1e9) / measured_hbm_gbs(),
                              "note": "achieved / frac follow the contract: algorithmic flops = (128 + 48*O*M/2) per candidate-timestep (SURVEY 8d) over "
                                      "the live kernel time; broad-phase culling skips almost all of the 48-flop rectangle tests, so frac exceeds 1. "
                                      "frac_executed is the bound that actually limits the kernel (SURVEY 8d asks for the ncu-measured utilisation): "
