@@ -118,6 +118,7 @@ SYMBOLS = {
     "jssp_batch_create": (C.c_int32, [C.POINTER(JsspConfigC), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "jssp_batch_destroy": (C.c_int32, [C.c_void_p]),
     "jssp_batch_last_cuda_error": (C.c_char_p, [C.c_void_p]),
+    "jssp_batch_set_fop": (C.c_int32, [C.c_void_p, C.POINTER(JsspFopIn)]),
     "jssp_batch_set_scenario": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(JsspScenarioIn), C.c_void_p]),
     "jssp_batch_reset": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
     "jssp_batch_run": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import JsspError, JsspCycleRecord, JsspScenarioIn, JsspScenarioResult, FLAG_FORCE_THREAD, FLAG_FORCE_WARP, FLAG_FORCE_GROUP
+from ._lib import JsspError, JsspCycleRecord, JsspFopIn, JsspScenarioIn, JsspScenarioResult, FLAG_FORCE_THREAD, FLAG_FORCE_WARP, FLAG_FORCE_GROUP
 from .engine import JsspConfig
 from .frenet import FrenetState, State
 from .geometry import CubicSpline2D
@@ -139,7 +139,10 @@ def _c(a: Optional[np.ndarray], dtype):
 class BatchReplay:
     """Owner of a ``jssp_batch`` handle: capacity for ``max_scenarios`` slots x ``max_cycles`` plan cycles."""
 
-    def __init__(self, config: Optional[JsspConfig] = None, device: int = 0, max_scenarios: int = 64, max_cycles: int = 128):
+    def __init__(self, config: Optional[JsspConfig] = None, device: int = 0, max_scenarios: int = 64, max_cycles: int = 128, fop=None,
+                 max_accel: float = 8.0, max_jerk: float = 10.0):
+        """``fop`` = a FrenetOptimalPlannerSettings: the batch replays with the FOP baseline planner instead of JSSP (``config`` must
+        then be the FOP configuration, see ``fop_batch_config``); ``max_accel`` / ``max_jerk`` = Vehicle.max_accel / max_jerk."""
         if not torch.cuda.is_available():
             raise RuntimeError("dlii_jssp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -153,6 +156,13 @@ class BatchReplay:
             raise JsspError(rc, "jssp_batch_create")
         self._n = 0
         self._packed: List[PackedScenario] = []
+        self.fop = fop
+        if fop is not None:
+            g = JsspFopIn()
+            g.num_width, g.num_speed, g.num_t = fop.num_width, fop.num_speed, fop.num_t
+            g.min_t, g.max_t, g.lowest_speed, g.highest_speed = fop.min_t, fop.max_t, fop.lowest_speed, fop.highest_speed
+            g.max_accel, g.max_jerk = float(max_accel), float(max_jerk)
+            self._check(self.lib.jssp_batch_set_fop(self._h, C.byref(g)), "jssp_batch_set_fop")
 
     def _check(self, rc: int, where: str):
         if rc != 0:
@@ -182,6 +192,8 @@ class BatchReplay:
         """Upload the scenarios into slots 0..len-1 and reset their replay state."""
         assert 1 <= len(packed) <= self.S, (len(packed), self.S)
         for slot, p in enumerate(packed):
+            if abs(p.dt - self.cfg.delta_t) > 1e-12:
+                raise ValueError(f"scenario {p.name}: dt = {p.dt} but the batch was created for delta_t = {self.cfg.delta_t}")
             O, M, Tt, _ = p.state.shape
             keep = [_c(p.knot_s, np.float64), _c(p.coef, np.float64), _c(p.state, np.float64), _c(p.valid, np.uint8), _c(p.size, np.float64),
                     _c(p.prob, np.float64), _c(p.gt_state, np.float64), _c(p.gt_valid, np.uint8), _c(p.gt_size, np.float64),
@@ -247,11 +259,23 @@ class BatchReplay:
         return out
 
 
+def fop_batch_config(fop, ego_length: float, ego_width: float, **caps) -> JsspConfig:
+    """The jssp_config of a batch that replays with the FOP baseline (same fields FrenetOptimalPlanner sets for its engine)."""
+    from .fop import PLANNER_FRENET, PARA_THRESHOLD
+    return JsspConfig(delta_t=fop.delta_t, plan_horizon=fop.max_t, max_road_width=fop.max_road_width, num_width=fop.num_width,
+                      speed_max=fop.highest_speed, ego_length=ego_length, ego_width=ego_width, obstacle_inflation=0.0,
+                      cost_weights=tuple(PLANNER_FRENET["cost_wights"]), max_distance=PLANNER_FRENET["max_distance"],
+                      thr_lon_accel=PARA_THRESHOLD["lon_accel_max"], thr_lon_jerk=PARA_THRESHOLD["lon_jerk_max"],
+                      thr_lat_accel=PARA_THRESHOLD["lateral_accel_max"], thr_lat_jerk=PARA_THRESHOLD["lateral_jerk_max"], **caps)
+
+
 def run_batch(scenarios: Sequence, device: int = 0, max_cycles: Optional[int] = None, batch: Optional[BatchReplay] = None,
-              kernel: Optional[str] = None) -> List[ReplayResult]:
+              kernel: Optional[str] = None, fop=None, max_accel: float = 8.0, max_jerk: float = 10.0) -> List[ReplayResult]:
     """Replay independent scenarios (ReplayScenario or PackedScenario) in lock-step on one GPU; same results as
-    ``replay.run_sweep``.  Scenarios that are over before the first cycle are answered on the host."""
-    packed = [s if isinstance(s, PackedScenario) else pack_scenario(s, max_cycles=max_cycles) for s in scenarios]
+    ``replay.run_sweep``.  Scenarios that are over before the first cycle are answered on the host.  ``fop`` (a
+    FrenetOptimalPlannerSettings) replays with the FOP baseline planner instead of JSSP."""
+    plan_steps = 50 if fop is None else int(np.ceil(fop.max_t / fop.delta_t))
+    packed = [s if isinstance(s, PackedScenario) else pack_scenario(s, plan_steps=plan_steps, max_cycles=max_cycles) for s in scenarios]
     live = [i for i, p in enumerate(packed) if p.initial_end == END_RUNNING]
     out: List[Optional[ReplayResult]] = [None if i in set(live) else ReplayResult(p.name, p.initial_end, 0) for i, p in enumerate(packed)]
     if live:
@@ -259,11 +283,11 @@ def run_batch(scenarios: Sequence, device: int = 0, max_cycles: Optional[int] = 
         e = todo[0].ego
         need_c = max(min(p.n_cycles, max_cycles or p.n_cycles) for p in todo)
         if batch is None:
-            cfg = JsspConfig(ego_length=float(e[5]), ego_width=float(e[6]), max_seeds=1024,
-                             max_knots=max(64, max(len(p.knot_s) for p in todo)),
-                             max_obstacle_modes=max(1, max(p.state.shape[0] * p.state.shape[1] for p in todo)),
-                             max_total_steps=max(p.state.shape[2] for p in todo))
-            batch = BatchReplay(cfg, device=device, max_scenarios=len(todo), max_cycles=need_c)
+            caps = dict(max_seeds=1024, max_knots=max(64, max(len(p.knot_s) for p in todo)),
+                        max_obstacle_modes=max(1, max(p.state.shape[0] * p.state.shape[1] for p in todo)),
+                        max_total_steps=max(p.state.shape[2] for p in todo))
+            cfg = JsspConfig(ego_length=float(e[5]), ego_width=float(e[6]), **caps) if fop is None else fop_batch_config(fop, float(e[5]), float(e[6]), **caps)
+            batch = BatchReplay(cfg, device=device, max_scenarios=len(todo), max_cycles=need_c, fop=fop, max_accel=max_accel, max_jerk=max_jerk)
         t0 = time.perf_counter()
         for lo in range(0, len(todo), batch.S):
             chunk = todo[lo:lo + batch.S]

@@ -453,6 +453,8 @@ int32_t jssp_set_refline(jssp_handle* h, const double* knot_s, const double* coe
   for (int i = 1; i < K; ++i) if (!(knot_s[i] > knot_s[i - 1])) return JSSP_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
+  if (h->wait_tables) CK(cudaEventSynchronize(h->tables_ready));   // a pending obstacle packing on the private stream reads the knots
+  if (h->tables_in_use) CK(cudaEventSynchronize(h->tables_free));  // ... and so does the last evaluation
   // structure-of-arrays [8][kpad] so that lanes on neighbouring segments hit different shared-memory banks
   h->kpad = (K + 1) & ~1;
   std::vector<double> soa((size_t)8 * h->kpad, 0.0);
@@ -895,6 +897,14 @@ struct jssp_batch {
   jssp_cycle_record* d_records = nullptr;
   double* d_cycle_time = nullptr;
   int *d_cycle_now = nullptr, *d_cycle_end = nullptr;
+  // FOP baseline in the batch (jssp_batch_set_fop): per-scenario FopParams records instead of EvalParams
+  bool fop = false;
+  jssp_fop_in fop_grid{};
+  FopParams *d_fslots = nullptr, *d_fslots0 = nullptr;
+  double* d_fop_tab = nullptr;
+  int* d_fop_int = nullptr;
+  int fop_blocks = 0;
+  size_t fop_smem = 0;
   // pinned staging ring of the uploads: host arrays are copied here, the H2D copies out of it are truly asynchronous
   unsigned char* h_stage = nullptr;
   size_t stage_cap = 0, stage_off = 0;
@@ -952,6 +962,8 @@ int32_t jssp_batch_destroy(jssp_batch* b) {
   for (void* q : dev) if (q) cudaFree(q);
   for (double* q : b->d_grid) if (q) cudaFree(q);
   if (b->h_stage) cudaFreeHost(b->h_stage);
+  void* fopdev[] = {b->d_fslots, b->d_fslots0, b->d_fop_tab, b->d_fop_int};
+  for (void* q : fopdev) if (q) cudaFree(q);
   delete b;
   return JSSP_OK;
 }
@@ -1044,6 +1056,46 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   CKC(cudaDeviceSynchronize());
 #undef CKC
   *out = b;
+  return JSSP_OK;
+}
+
+int32_t jssp_batch_set_fop(jssp_batch* b, const jssp_fop_in* grid) {
+  if (!b || !grid) return JSSP_ERR_INVALID_ARG;
+  const jssp_config& c = b->cfg;
+  if (grid->num_width != c.num_width || grid->num_speed < 1 || grid->num_t < 1 || !(grid->min_t > 0) || !(grid->max_t >= grid->min_t))
+    return JSSP_ERR_INVALID_ARG;
+  if (grid->max_t > c.plan_horizon + 1e-9) return JSSP_ERR_CAPACITY;
+  CKB(cudaSetDevice(b->device));
+  const int NT = grid->num_t, NV = grid->num_speed;
+  const long long N = (long long)b->W * NT * NV;
+  b->fop_blocks = (int)((N + EVAL_THREADS - 1) / EVAL_THREADS);
+  if (b->fop_blocks > b->max_blocks) return JSSP_ERR_CAPACITY;      // per-scenario block records follow max_seeds * num_width
+  std::vector<double> tab = np_linspace(grid->min_t, grid->max_t, NT);
+  std::vector<int> ns((size_t)NT);
+  for (int i = 0; i < NT; ++i) {
+    ns[i] = (int)std::ceil((tab[i] - 0.0) / c.delta_t);
+    if (ns[i] < 1 || ns[i] > b->P) return JSSP_ERR_CAPACITY;
+  }
+  const std::vector<double> sp = np_linspace(grid->lowest_speed, grid->highest_speed, NV);
+  tab.insert(tab.end(), sp.begin(), sp.end());
+  void* old[] = {b->d_fslots, b->d_fslots0, b->d_fop_tab, b->d_fop_int};
+  for (void* q : old) if (q) cudaFree(q);
+  b->d_fslots = b->d_fslots0 = nullptr; b->d_fop_tab = nullptr; b->d_fop_int = nullptr;
+  CKB(cudaMalloc(&b->d_fslots, (size_t)b->S * sizeof(FopParams)));
+  CKB(cudaMalloc(&b->d_fslots0, (size_t)b->S * sizeof(FopParams)));
+  CKB(cudaMalloc(&b->d_fop_tab, tab.size() * sizeof(double)));
+  CKB(cudaMalloc(&b->d_fop_int, ns.size() * sizeof(int)));
+  CKB(cudaMemcpy(b->d_fop_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CKB(cudaMemcpy(b->d_fop_int, ns.data(), ns.size() * sizeof(int), cudaMemcpyHostToDevice));
+  int optin = 0;
+  CKB(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device));
+  CKB(allow_max_dynamic_smem(evaluate_fop_batch_kernel, optin, &b->max_smem_optin));
+  CKB(allow_max_dynamic_smem(fop_select_export_batch_kernel, optin, &b->max_smem_optin));
+  b->fop_smem = fop_smem_layout(c.max_knots, (c.max_knots + 1) & ~1, b->P, b->W, NT).total;   // sized for the knot capacity
+  if (b->fop_smem > (size_t)b->max_smem_optin) return JSSP_ERR_CAPACITY;
+  b->fop_grid = *grid;
+  b->fop = true;
+  std::fill(b->is_set.begin(), b->is_set.end(), 0);      // scenarios must be (re)loaded in FOP mode
   return JSSP_OK;
 }
 
@@ -1154,6 +1206,22 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
   q.cycle_time = ctime; q.cycle_now = cnow; q.cycle_end_step = cend;
   q.gt_state = gt_state; q.gt_valid = gt_valid; q.gt_size = gt_size;
   q.records = b->d_records + s * (size_t)b->C;
+  if (b->fop) {
+    const jssp_fop_in& g = b->fop_grid;
+    q.is_fop = 1;
+    p.n_seeds_ptr = nullptr; p.n_seeds_fixed = g.num_t * g.num_speed; p.seeds = nullptr;
+    p.smem_obs = 0; p.win_rows = 0;
+    p.self = &b->d_fslots[s].base;
+    FopParams fp{};
+    fp.base = p;
+    fp.num_t = g.num_t; fp.num_speed = g.num_speed;
+    fp.horizon = b->d_fop_tab; fp.speed = b->d_fop_tab + g.num_t; fp.n_samples = b->d_fop_int;
+    fp.d0 = in->frenet0[3]; fp.d_d0 = in->frenet0[4]; fp.d_dd0 = in->frenet0[5];
+    for (int w = 0; w < b->W; ++w) fp.targets[w] = tg[w];
+    fp.dt = c.delta_t; fp.max_accel = g.max_accel; fp.max_jerk = g.max_jerk; fp.t_min = g.min_t; fp.t_max = g.max_t;
+    CKB(upload_staged(b, b->d_fslots + s, &fp, sizeof(fp), st));
+    CKB(upload_staged(b, b->d_fslots0 + s, &fp, sizeof(fp), st));
+  }
   CKB(upload_staged(b, b->d_slots + s, &p, sizeof(p), st));
   CKB(upload_staged(b, b->d_bslots + s, &q, sizeof(q), st));
   CKB(upload_staged(b, b->d_slots0 + s, &p, sizeof(p), st));
@@ -1173,6 +1241,7 @@ int32_t jssp_batch_reset(jssp_batch* b, int32_t n_scenarios, void* stream) {
   const size_t n = (size_t)n_scenarios;
   CKB(cudaMemcpyAsync(b->d_slots, b->d_slots0, n * sizeof(EvalParams), cudaMemcpyDeviceToDevice, st));
   CKB(cudaMemcpyAsync(b->d_bslots, b->d_bslots0, n * sizeof(BatchSlot), cudaMemcpyDeviceToDevice, st));
+  if (b->fop) CKB(cudaMemcpyAsync(b->d_fslots, b->d_fslots0, n * sizeof(FopParams), cudaMemcpyDeviceToDevice, st));
   CKB(cudaMemsetAsync(b->d_ticket, 0, n * sizeof(unsigned int), st));
   return JSSP_OK;
 }
@@ -1182,6 +1251,15 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   for (int s = 0; s < n_scenarios; ++s) if (!b->is_set[s]) return JSSP_ERR_NOT_READY;
   cudaStream_t st = (cudaStream_t)stream;
   CKB(cudaSetDevice(b->device));
+  if (b->fop) {                       // FOP baseline: no seed enumeration, evaluation + (selection, export, hand-off) per step
+    for (int c = 0; c < n_cycles; ++c) {
+      evaluate_fop_batch_kernel<<<dim3(b->fop_blocks, n_scenarios), EVAL_THREADS, b->fop_smem, st>>>(b->d_fslots);
+      fop_select_export_batch_kernel<<<n_scenarios, EVAL_THREADS, b->fop_smem, st>>>(b->d_fslots, b->fop_blocks);
+      b->launches += 2;
+    }
+    CKB(cudaGetLastError());
+    return JSSP_OK;
+  }
   const int max_rows = (b->P + b->cfg.check_res - 1) / b->cfg.check_res;
   // the evaluation kernel: one warp per candidate while the whole batch is small (latency), one thread per candidate otherwise
   const SmemLayout Ls = eval_smem_layout(0, b->max_OMpad, 0, b->max_K, b->max_kpad, b->P, b->W);

@@ -64,6 +64,7 @@ struct BatchSlot {
   int n_cycles_cap;               // the per-cycle tables hold n_cycles_cap + 1 entries: the replay pauses after that many cycles
   int seed_overflow;              // a cycle enumerated more seeds than max_seeds (the surplus was dropped): reported, never silent
   int last_n_pts;                 // Cartesian points of the trajectory in best_traj (0 = no trajectory selected yet)
+  int is_fop, pad2;               // the scenario's parameter record is a FopParams (FOP baseline in the batch)
   double end;                     // end status: -1 running, 1 max_t, 1.5 goal, 2 collision, -2 no solution, -3 short trajectory
   double max_t, horizon;
   double goal_x, goal_y, goal_cos, goal_sin;
@@ -729,6 +730,8 @@ __device__ __forceinline__ bool rect_overlap_f64(double x1, double y1, double ya
   return sat_intersects_f64(x2 - x1, y2 - y1, c1, s1, l1 / 2.0, w1 / 2.0, c2, s2, l2 / 2.0, w2 / 2.0);
 }
 
+__device__ __forceinline__ void fop_store_lateral_start(EvalParams* self, double d, double d_d, double d_dd);   // jssp_fop.cuh
+
 // Batched replay: end-of-cycle hand-off of one scenario, run by the block that exported the selected trajectory.
 __device__ __forceinline__ void batch_handoff(const EvalParams& p, int best, int N, int* sm_flag) {
   BatchSlot* b = p.batch;
@@ -785,7 +788,8 @@ __device__ __forceinline__ void batch_handoff(const EvalParams& p, int best, int
     // next cycle starts from sample 1 of the selected trajectory (intersection_planner.py:312)
     EvalParams* q = p.self;
     q->s0 = row1[1]; q->v0 = row1[2]; q->a0 = row1[3];
-    for (int w = 0; w < p.W; ++w) quintic_coeffs(row1[5], row1[6], row1[7], b->targets[w], 0.0, 0.0, b->horizon, q->quintic[w]);
+    if (b->is_fop) fop_store_lateral_start(q, row1[5], row1[6], row1[7]);
+    else for (int w = 0; w < p.W; ++w) quintic_coeffs(row1[5], row1[6], row1[7], b->targets[w], 0.0, 0.0, b->horizon, q->quintic[w]);
     const int now = b->cycle_now[c + 1];
     q->now = now; q->tcap = b->final_step - now;
     int rows = 0;

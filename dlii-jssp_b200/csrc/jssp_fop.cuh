@@ -1,6 +1,7 @@
 // jssp_fop.cuh - K6: FOP baseline planner through the same stages (frenet_optimal_planner.py)
 #pragma once
 #include "jssp_eval.cuh"
+#include <cstddef>
 
 namespace jssp {
 
@@ -121,10 +122,13 @@ __device__ __forceinline__ void fop_stage(const FopParams& fp, unsigned char* sm
   latcost = sm_latcost; quint = sm_quint;
 }
 
-__global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_fop_kernel(const __grid_constant__ FopParams fp) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ double red_cost[EVAL_THREADS / 32];
-  __shared__ int red_idx[EVAL_THREADS / 32];
+// the lateral start state of the next cycle lives next to the EvalParams record inside the scenario's FopParams
+__device__ __forceinline__ void fop_store_lateral_start(EvalParams* self, double d, double d_d, double d_dd) {
+  FopParams* f = reinterpret_cast<FopParams*>(self);           // `base` is the first member
+  f->d0 = d; f->d_d0 = d_d; f->d_dd0 = d_dd;
+}
+
+__device__ __forceinline__ void evaluate_fop_body(const FopParams& fp, unsigned char* smem, double* red_cost, int* red_idx) {
   const EvalParams& p = fp.base;
   const int N = p.W * fp.num_t * fp.num_speed;
   BlockTables tb;
@@ -174,13 +178,38 @@ __global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_fop_ke
   }
 }
 
-// one block: reduce the per-block winners, write the selection record and export the selected trajectory
-__global__ void __launch_bounds__(EVAL_THREADS) fop_select_export_kernel(const __grid_constant__ FopParams fp, int n_blocks) {
+__global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_fop_kernel(const __grid_constant__ FopParams fp) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ double red_cost[EVAL_THREADS / 32];
   __shared__ int red_idx[EVAL_THREADS / 32];
-  __shared__ int sm_best, sm_npts;
-  __shared__ double ex[6][EXPORT_MAX_P];
+  evaluate_fop_body(fp, smem, red_cost, red_idx);
+}
+
+__device__ __forceinline__ void load_fop_slot(FopParams* dst, const FopParams* src) {
+  static_assert(sizeof(FopParams) % 8 == 0 && offsetof(FopParams, base) == 0, "FopParams is copied as 8-byte words, base first");
+  const unsigned long long* s = reinterpret_cast<const unsigned long long*>(src);
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(dst);
+  for (int i = threadIdx.x; i < (int)(sizeof(FopParams) / 8); i += blockDim.x) d[i] = s[i];
+  __syncthreads();
+}
+
+// batched replay with the FOP baseline: blockIdx.y = scenario
+__global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_fop_batch_kernel(const FopParams* __restrict__ fslots) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(16) FopParams sfp;
+  __shared__ double red_cost[EVAL_THREADS / 32];
+  __shared__ int red_idx[EVAL_THREADS / 32];
+  if (!fslots[blockIdx.y].base.batch->live) return;
+  load_fop_slot(&sfp, fslots + blockIdx.y);
+  evaluate_fop_body(sfp, smem, red_cost, red_idx);
+}
+
+// one block: reduce the per-block winners, write the selection record and export the selected trajectory; returns the
+// selected candidate (-1 = none) to every thread
+__device__ __forceinline__ int fop_select_export_body(const FopParams& fp, int n_blocks, unsigned char* smem, double* red_cost, int* red_idx,
+                                                      int* sm_best_p, int* sm_npts_p, double (*ex)[EXPORT_MAX_P]) {
+  int& sm_best = *sm_best_p;
+  int& sm_npts = *sm_npts_p;
   const EvalParams& p = fp.base;
   const int N = p.W * fp.num_t * fp.num_speed;
   double my_cost = INFINITY;
@@ -211,7 +240,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) fop_select_export_kernel(const _
   }
   __syncthreads();
   const int best = sm_best;
-  if (best < 0 || p.best_traj == nullptr || p.P > EXPORT_MAX_P) return;
+  if (best < 0 || p.best_traj == nullptr || p.P > EXPORT_MAX_P) return best;
   BlockTables tb;
   const double *latcost, *quint;
   fop_stage(fp, smem, tb, latcost, quint);
@@ -234,6 +263,30 @@ __global__ void __launch_bounds__(EVAL_THREADS) fop_select_export_kernel(const _
   }
   // rows beyond the candidate's own length stay NaN; the exported block always has P rows
   export_tail(tb, row, p.P, i < Pc ? lat[i * 4] : 0.0, fp.dt, p.best_traj, &sm_npts, p.best, ex);
+  return best;
+}
+
+__global__ void __launch_bounds__(EVAL_THREADS) fop_select_export_kernel(const __grid_constant__ FopParams fp, int n_blocks) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ double red_cost[EVAL_THREADS / 32];
+  __shared__ int red_idx[EVAL_THREADS / 32];
+  __shared__ int sm_best, sm_npts;
+  __shared__ double ex[6][EXPORT_MAX_P];
+  fop_select_export_body(fp, n_blocks, smem, red_cost, red_idx, &sm_best, &sm_npts, ex);
+}
+
+// batched replay: one block per scenario selects, exports and hands off (blockIdx.x = scenario)
+__global__ void __launch_bounds__(EVAL_THREADS) fop_select_export_batch_kernel(const FopParams* __restrict__ fslots, int n_blocks) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(16) FopParams sfp;
+  __shared__ double red_cost[EVAL_THREADS / 32];
+  __shared__ int red_idx[EVAL_THREADS / 32];
+  __shared__ int sm_best, sm_npts;
+  __shared__ double ex[6][EXPORT_MAX_P];
+  if (!fslots[blockIdx.x].base.batch->live) return;
+  load_fop_slot(&sfp, fslots + blockIdx.x);
+  const int best = fop_select_export_body(sfp, n_blocks, smem, red_cost, red_idx, &sm_best, &sm_npts, ex);
+  batch_handoff(sfp.base, best, sfp.base.W * sfp.num_t * sfp.num_speed, &sm_npts);
 }
 
 }  // namespace jssp

@@ -282,6 +282,11 @@ typedef struct jssp_scenario_in {
 int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_scenarios, int32_t max_cycles, jssp_batch** out);
 int32_t jssp_batch_destroy(jssp_batch* b);
 const char* jssp_batch_last_cuda_error(const jssp_batch* b);
+/* switch the batch to the FOP baseline planner (jssp_fop_evaluate's candidate model) for every scenario loaded afterwards:
+ * `grid` supplies num_width (= cfg.num_width), num_speed, num_t, min_t, max_t, lowest/highest speed, max_accel, max_jerk; its
+ * start-state and time-step fields are ignored.  The jssp_config of the batch should be the FOP one (obstacle_inflation 0,
+ * plan_horizon >= max_t, speed_max = highest_speed, planner_frenet cost weights).  Two launches per lock-step cycle. */
+int32_t jssp_batch_set_fop(jssp_batch* b, const jssp_fop_in* grid);
 /* upload one scenario into `slot` and reset its replay state.  The host arrays are copied into a pinned staging ring before
  * the call returns (they may be freed); the transfers themselves are asynchronous on `stream` */
 int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario_in* in, void* stream);

@@ -124,3 +124,25 @@ def test_fop_cuda_path_matches_the_reference_fop_methods(golden_dir, scenario_fi
         for col, key in ((9, "x"), (10, "y"), (11, "yaw")):
             np.testing.assert_allclose(getattr(best, key), rows[:n, col], rtol=1e-9, atol=1e-9, err_msg=key)
     pl.engine.close()
+
+
+def test_fop_batched_replay_matches_single_replays_and_oracle(scenario_fixture):
+    """The FOP baseline in the batched device-resident replay (jssp_batch_set_fop): every scenario of the batch reproduces the
+    one-at-a-time FOP replay exactly and the oracle's FOP replay to tolerance (reduced grid 3 x 4 x 40)."""
+    from dlii_jssp_b200 import replay as R, batch as B
+    from oracle import replay_oracle
+    st = J.FrenetOptimalPlannerSettings(num_width=3, num_speed=40, num_t=4, highest_speed=18.0, lowest_speed=0.0, min_planning_t=5.0, max_planning_t=5.5)
+    scs = [scenario_fixture, S.perturbed_scenario(scenario_fixture, 2)]
+    got = B.run_batch(scs, max_cycles=15, fop=st)
+    for sc, g in zip(scs, got):
+        planner = J.IntersectionPlanner(J.PlannerSettings(), sc.observation(), "frenet")
+        planner.fplanner.engine.close()
+        planner.fplanner = J.FrenetOptimalPlanner(st, planner.ego_vehicle)
+        solo = R.run_replay(sc, max_cycles=15, planner=planner, method="frenet")
+        assert g.best_idx == solo.best_idx and g.n_candidates == solo.n_candidates and g.end == solo.end and g.ego_rows == solo.ego_rows
+        planner.fplanner.engine.close()
+    sc = scs[0]
+    cfg = F.FopConfig(num_width=3, num_speed=40, num_t=4, ego_length=sc.ego["length"], ego_width=sc.ego["width"])
+    cpu = replay_oracle.replay(sc, tuple(B.pack_scenario(sc).frenet0), S.pack_obstacle_dict, R.end_status, R.goal_pose_of(sc), max_cycles=15, fop_cfg=cfg)
+    assert got[0].best_idx == cpu["best_idx"] and got[0].end == cpu["end"]
+    np.testing.assert_allclose(np.array(got[0].ego_rows), np.array(cpu["rows"]), rtol=1e-9, atol=1e-9)
