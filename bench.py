@@ -422,12 +422,22 @@ def run_sweep(args):
         kw = dict(p_min=0.3, w_risk=1.0)
     else:
         packed = [B.pack_scenario(J.scenario.synthetic_intersection(i), max_cycles=args.cycles) for i in ids]   # packed before the clock starts
+    fop = None
+    if args.planner == "frenet":                 # FOP baseline planner in the same batched replay: 3 x 10 x 250 candidates
+        fop = J.FrenetOptimalPlannerSettings.intended()
+        steps_fop = int(np.ceil(fop.max_t / fop.delta_t))
+        packed = [B.pack_scenario(J.scenario.synthetic_intersection(i), plan_steps=steps_fop, max_cycles=args.cycles) for i in ids]
     packed = [p for p in packed if p.initial_end == -1]
     e = packed[0].ego
     cfg = J.JsspConfig(ego_length=float(e[5]), ego_width=float(e[6]), max_seeds=1024, max_knots=max(64, max(len(p.knot_s) for p in packed)),
                        max_obstacle_modes=max(1, max(p.state.shape[0] * p.state.shape[1] for p in packed)),
                        max_total_steps=max(p.state.shape[2] for p in packed), **kw)
-    bt = B.BatchReplay(cfg, device=local, max_scenarios=len(packed), max_cycles=args.cycles)
+    pts = cfg.n_points
+    if fop is not None:
+        cfg = B.fop_batch_config(fop, float(e[5]), float(e[6]), max_seeds=1024, max_knots=cfg.max_knots, max_obstacle_modes=cfg.max_obstacle_modes,
+                                 max_total_steps=cfg.max_total_steps)
+        pts = float(np.mean([len(np.arange(0.0, T, fop.delta_t)) for T in np.linspace(fop.min_t, fop.max_t, fop.num_t)]))   # samples per candidate
+    bt = B.BatchReplay(cfg, device=local, max_scenarios=len(packed), max_cycles=args.cycles, fop=fop)
     bt.load(packed)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sampler = ClockSampler(local)
@@ -451,8 +461,8 @@ def run_sweep(args):
     launches = bt.launch_count - l0
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     results = bt.results()
-    units = sum(sum(r.n_candidates) for r in results) * cfg.n_points
-    flops = sum(sum(r.n_candidates) * cfg.n_points * (F_BASE + F_SAT * p.state.shape[0] * p.state.shape[1] / 2.0) for r, p in zip(results, packed))
+    units = sum(sum(r.n_candidates) for r in results) * pts
+    flops = sum(sum(r.n_candidates) * pts * (F_BASE + F_SAT * p.state.shape[0] * p.state.shape[1] / 2.0) for r, p in zip(results, packed))
     cycles = sum(r.cycles for r in results)
     # end to end: upload the packed scenarios from host memory, replay, fetch the per-cycle records
     h2d = sum(sum(getattr(p, f).nbytes for f in ("knot_s", "coef", "state", "valid", "size", "prob", "cycle_time", "cycle_now", "cycle_end_step")) for p in packed)
@@ -484,7 +494,8 @@ def run_sweep(args):
         peak32 = __import__("ctypes").c_double(0)
         bt.lib.jssp_measure_fma_peak(local, 32, peak32)
         sweep_s = 1e-3 * ms_max / args.steps
-        desc = (f"{int(n_all)}-scenario synthetic intersection replay sweep, default grid, <= {args.cycles} cycles each (BASELINE configs[3]; reference data absent)"
+        grid = "default grid" if fop is None else f"FOP baseline planner {fop.num_width} x {fop.num_t} x {fop.num_speed} candidates per cycle"
+        desc = (f"{int(n_all)}-scenario synthetic intersection replay sweep, {grid}, <= {args.cycles} cycles each (BASELINE configs[3]; reference data absent)"
                 if not c2 else f"{int(n_all)}-scene demo: 8_3_4_565 + seeded variants, JSSP + 3 predicted intention modes per vehicle, <= {args.cycles} cycles each "
                                "(BASELINE configs[1]; the reference's demo scenes are empty files, its predictor is unpublished)")
         line = {"metric": METRIC, "value": units_all / sweep_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
@@ -496,7 +507,8 @@ def run_sweep(args):
                 "e2e": {"value": units_all / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
                         "sweep_ms": 1e3 * e2e_max},
                 "gpu_launches": int(launches), "clocks": sampler.summary(),
-                "roofline": {"bound": "fp32", "kernel": "seed_enum_kernel + evaluate_batch_kernel (whole lock-step cycle)",
+                "roofline": {"bound": "fp32", "kernel": "seed_enum_kernel + evaluate_batch_kernel (whole lock-step cycle)" if fop is None else
+                             "evaluate_fop_batch_kernel + fop_select_export_batch_kernel (whole lock-step cycle)",
                              "achieved": flops_all / sweep_s / 1e12 / world, "peak": peak32.value, "unit": "TFLOP/s",
                              "frac": (flops_all / sweep_s / 1e12 / world) / peak32.value if peak32.value else None, "traffic": None,
                              "note": "per GPU; algorithmic flops of the evaluation only ((128 + 48*O*M/2) per candidate-timestep); the seed "
@@ -518,6 +530,7 @@ def main():
     ap.add_argument("--workload", default="C3", choices=["C3", "C5", "C4", "C2"])
     ap.add_argument("--scenarios", type=int, default=800, help="C4: number of synthetic scenarios in the sweep")
     ap.add_argument("--cycles", type=int, default=100, help="C4: plan cycles per scenario (upper bound)")
+    ap.add_argument("--planner", default="JSSP", choices=["JSSP", "frenet"], help="C4: planner of the replay (frenet = the FOP baseline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--cpu-sample-div", type=int, default=32, help="cpu_baseline sample = candidates / this")
     args = ap.parse_args()

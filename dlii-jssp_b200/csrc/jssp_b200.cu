@@ -1283,7 +1283,9 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   // few scenarios: clusters of up to 8 CTAs x 1024 threads answer with the lowest latency; many: one 512-thread CTA each
   int seed_cluster = 1;
   while (seed_cluster < SEED_MAX_CLUSTER && n_scenarios * seed_cluster * 2 <= 148) seed_cluster *= 2;
-  const int seed_threads = n_scenarios >= 296 ? 512 : SEED_THREADS;
+  int seed_threads = n_scenarios >= 296 ? 512 : SEED_THREADS;
+  if (const char* e = getenv("JSSP_B200_TUNE_SEED_CLUSTER")) seed_cluster = std::max(1, std::min(SEED_MAX_CLUSTER, atoi(e)));    // tools/ only
+  if (const char* e = getenv("JSSP_B200_TUNE_SEED_THREADS")) seed_threads = atoi(e) == 512 ? 512 : SEED_THREADS;
   for (int c = 0; c < n_cycles; ++c) {
     CKB(launch_seed_enum<true>(b->grids, SeedState{0, 0, 0}, b->d_slots, b->seed_work, n_scenarios, seed_cluster, seed_threads, b->seed_smem, st));
     if (small) evaluate_small_batch_kernel<<<dim3(std::min(b->blocks_warp, 128), n_scenarios), SMALL_WARPS * 32, small_bytes, st>>>(b->d_slots);

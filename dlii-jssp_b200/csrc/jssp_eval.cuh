@@ -864,10 +864,12 @@ __device__ __forceinline__ void select_and_export(const EvalParams& p, unsigned 
   if (p.best_traj == nullptr) return;
   __syncthreads();
   const int best = red_idx[0];
+  PHASE(p, 5);
   if (best >= 0) {
     if (!staged) stage_tables<kMode>(p, smem, tb, latcost);
     export_block(p, tb, best, p.best_traj, sm_npts_p);
   }
+  PHASE(p, 6);
   if (p.batch) batch_handoff(p, best, N, sm_npts_p);
 }
 
@@ -883,13 +885,16 @@ __device__ __forceinline__ void evaluate_body(const EvalParams& p, unsigned char
   BlockTables tb;
   const double* latcost;
   const bool staged = blockIdx.x * blockDim.x < N;   // block-uniform
+  PHASE(p, 0);
   if (staged) {
     stage_tables<kMode>(p, smem, tb, latcost);
+    PHASE(p, 1);
     const bool active = n < N;
     const int w = active ? n / Ns : 0, k = active ? n - w * Ns : 0;
     LonWalk lp;
     lon_walk_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
     if (kMode == 2) build_lists(p, smem, tb, lp, active);
+    PHASE(p, 2);
     if (active) {
       EvalSink sink(p, tb);
       const int seg0 = spline_bisect(tb.sp, fmin(fmax(p.s0, tb.sp.knot[0]), tb.sp.knot[p.K - 1]));
@@ -901,7 +906,12 @@ __device__ __forceinline__ void evaluate_body(const EvalParams& p, unsigned char
       if (!sink.curv_fail && !sink.collided && isfinite(cost)) { my_cost = cost; my_idx = n; }
     }
   }
+#ifdef JSSP_PROFILE_PHASES
+  __syncthreads();
+#endif
+  PHASE(p, 3);
   select_and_export<kMode>(p, smem, tb, latcost, staged, my_cost, my_idx, N, Ns, red_cost, red_idx, is_last, sm_npts);
+  PHASE(p, 4);
 }
 
 template <int kMode>

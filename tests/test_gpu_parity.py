@@ -166,6 +166,34 @@ def test_c3_full_size_properties_and_subsample_parity():
     eng.close()
 
 
+def test_c5_full_size_properties_and_subsample_parity():
+    """BASELINE config 5 at full size on one GPU (1,048,576 candidates x 81 samples x 64 obstacles x 3 modes): argmin property,
+    exact mask parity on a candidate subsample, and the candidate split of the multi-GPU path (8 contiguous seed ranges
+    evaluated one after the other, reduced by (cost, index)) selects the same candidate."""
+    cyc, cfg, spline, eng = _dense(131072, 8, 64, 3, 8.0, 20251020)
+    seeds = torch.from_numpy(cyc.seeds).cuda()
+    res = eng.evaluate(cyc.frenet0, 0, cyc.final_time_step, seeds=seeds, targets=cyc.targets)
+    Ns = len(cyc.seeds)
+    assert res.n_candidates == 8 * Ns == 1048576
+    feas = res.feasible.cpu().numpy().astype(bool); coll = res.collision.cpu().numpy().astype(bool); cost = res.cost.cpu().numpy()
+    ok = feas & ~coll
+    assert ok.any() and ok[res.best_idx] and cost[res.best_idx] <= cost[ok].min()
+    step = 256
+    ref = O.plan_cycle(cfg, spline, cyc.frenet0, H.oracle_obstacles(cyc.obstacles), 0, cyc.final_time_step, seeds=cyc.seeds[::step], targets=cyc.targets)
+    pick = np.concatenate([w * Ns + np.arange(0, Ns, step) for w in range(8)])
+    assert np.array_equal(feas[pick], ref["feasible"]) and np.array_equal(coll[pick], ref["collision"])
+    np.testing.assert_allclose(cost[pick], ref["cost"], rtol=1e-4)
+    best = (np.inf, -1)
+    for r in range(8):                                       # distributed.candidate_range: contiguous seed ranges per rank
+        lo, hi = r * Ns // 8, (r + 1) * Ns // 8
+        part = eng.evaluate(cyc.frenet0, 0, cyc.final_time_step, seeds=seeds[lo:hi].contiguous(), targets=cyc.targets)
+        if part.best_idx >= 0:
+            w, k = divmod(part.best_idx, hi - lo)
+            best = min(best, (part.best_cost, w * Ns + lo + k))
+    assert best[1] == res.best_idx and abs(best[0] - res.best_cost) <= 1e-12
+    eng.close()
+
+
 @pytest.mark.parametrize("n_seeds,n_widths,O_,M,horizon,seed", [(1024, 4, 32, 3, 5.0, 41), (700, 3, 6, 1, 5.0, 42), (512, 8, 64, 3, 8.0, 43)])
 def test_block_level_culling_changes_nothing(n_seeds, n_widths, O_, M, horizon, seed):
     """The per-block culled obstacle lists (default) and the exhaustive table walk (JSSP_FLAG_NO_CULL) give identical
