@@ -86,13 +86,19 @@ class JsspScenarioIn(C.Structure):
         ("cycle_time", C.c_void_p), ("cycle_now", C.c_void_p), ("cycle_end_step", C.c_void_p),
         ("goal_x", C.c_double), ("goal_y", C.c_double), ("goal_yaw", C.c_double),
         ("ego_length", C.c_double), ("ego_width", C.c_double),
-        ("ego0", C.c_double * 4), ("bounds", C.c_double * 4), ("has_bounds", C.c_int32), ("reserved2", C.c_int32),
+        ("ego0", C.c_double * 4), ("bounds", C.c_double * 4), ("has_bounds", C.c_int32), ("ego_update_mode", C.c_int32),
+        ("polyline", C.c_void_p), ("n_polyline", C.c_int32), ("reserved2", C.c_int32),
+        ("pp_kv", C.c_double), ("pp_ld0", C.c_double), ("pp_wheel_base", C.c_double),
     ]
 
+
+# jssp_struct_size's numbering
+STRUCTS = (JsspConfigC, JsspCycleIn, JsspCycleOut, JsspFopIn, JsspImmParams, JsspCycleRecord, JsspScenarioResult, JsspScenarioIn)
 
 # every symbol include/jssp_b200.h declares (tests check that the library exports exactly these)
 SYMBOLS = {
     "jssp_abi_version": (C.c_int32, []),
+    "jssp_struct_size": (C.c_int32, [C.c_int32]),
     "jssp_strerror": (C.c_char_p, [C.c_int32]),
     "jssp_last_cuda_error": (C.c_char_p, [C.c_void_p]),
     "jssp_default_config": (None, [C.POINTER(JsspConfigC)]),
@@ -152,6 +158,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         fn.argtypes = args
     if lib.jssp_abi_version() != 1:
         raise RuntimeError("libjssp_b200.so ABI version mismatch; rebuild")
+    for which, st in enumerate(STRUCTS):
+        if lib.jssp_struct_size(which) != C.sizeof(st):
+            raise RuntimeError(f"libjssp_b200.so was built from another jssp_b200.h ({st.__name__} differs); rebuild")
     _lib = lib
     return lib
 

@@ -58,6 +58,7 @@ class PackedScenario:
     gt_state: Optional[np.ndarray] = None     # ground truth for the end-status test when the planner sees predictions (M > 1)
     gt_valid: Optional[np.ndarray] = None
     gt_size: Optional[np.ndarray] = None
+    polyline: Optional[np.ndarray] = None     # [n, 6] x, y, yaw, arc, cos yaw, sin yaw: the re-discretised reference line (kinematics mode)
 
     @property
     def n_cycles(self) -> int:
@@ -78,9 +79,21 @@ def clock_tables(dt: float, n_cycles: int, n_total: int):
     return times, now, end
 
 
-def pack_scenario(sc: ReplayScenario, plan_steps: int = 50, max_cycles: Optional[int] = None, predictions=None) -> PackedScenario:
+def polyline_table(ref: np.ndarray) -> np.ndarray:
+    """The columns FrenetState.from_state reads of the re-discretised reference line ``ref`` [n, >=3] = x, y, yaw, with the
+    arc length up to every point accumulated exactly as from_state does (``seg[:i].sum()``) and the unit tangent by math.cos /
+    math.sin, so that the device projection sees the host's numbers."""
+    import math
+    seg = np.hypot(np.diff(ref[:, 0]), np.diff(ref[:, 1]))
+    arc = np.array([float(seg[:i].sum()) for i in range(len(ref))])
+    return np.column_stack([ref[:, 0], ref[:, 1], ref[:, 2], arc, [math.cos(v) for v in ref[:, 2]], [math.sin(v) for v in ref[:, 2]]])
+
+
+def pack_scenario(sc: ReplayScenario, plan_steps: int = 50, max_cycles: Optional[int] = None, predictions=None,
+                  kinematics: bool = False) -> PackedScenario:
     """``predictions`` (ObstacleTensors, M >= 1) replaces the ground-truth dictionary as what the planner sees; the
-    end-status collision test always uses the dictionary."""
+    end-status collision test always uses the dictionary.  ``kinematics`` also packs the re-discretised reference line the
+    "kinematics" ego-update mode projects the ego on every cycle."""
     spline = CubicSpline2D(sc.route_xy[:, 0], sc.route_xy[:, 1])
     ref = spline.sample(np.arange(0, spline.s_list[-1], 0.1))                       # generate_frenet_frame, jssp.py:366-371
     e = sc.ego
@@ -97,6 +110,8 @@ def pack_scenario(sc: ReplayScenario, plan_steps: int = 50, max_cycles: Optional
                        float(sc.dt), float(sc.max_t), final, times, now, end, np.array(gp, dtype=np.float64),
                        float(end_status(obs, sc, None)),                        # _get_initial_observation: no goal pose yet
                        None if sc.bounds is None else np.array(sc.bounds, dtype=np.float64))
+    if kinematics:
+        p.polyline = polyline_table(ref)
     if predictions is not None:
         assert predictions.state.shape[2] >= n_total, "predictions must cover final_time_step + horizon + 2 steps"
         p.gt_state, p.gt_valid, p.gt_size = gt.state[:, 0].copy(), gt.valid[:, 0].copy(), gt.size
@@ -106,7 +121,7 @@ def pack_scenario(sc: ReplayScenario, plan_steps: int = 50, max_cycles: Optional
 
 
 _ARRAY_FIELDS = ("knot_s", "coef", "state", "valid", "size", "prob", "frenet0", "ego", "cycle_time", "cycle_now", "cycle_end_step", "goal_pose",
-                 "bounds", "gt_state", "gt_valid", "gt_size")
+                 "bounds", "gt_state", "gt_valid", "gt_size", "polyline")
 
 
 def save_packed(path: str, packed: Sequence[PackedScenario]):
@@ -140,9 +155,13 @@ class BatchReplay:
     """Owner of a ``jssp_batch`` handle: capacity for ``max_scenarios`` slots x ``max_cycles`` plan cycles."""
 
     def __init__(self, config: Optional[JsspConfig] = None, device: int = 0, max_scenarios: int = 64, max_cycles: int = 128, fop=None,
-                 max_accel: float = 8.0, max_jerk: float = 10.0):
+                 max_accel: float = 8.0, max_jerk: float = 10.0, ego_update_mode: str = "planner_expected_value"):
         """``fop`` = a FrenetOptimalPlannerSettings: the batch replays with the FOP baseline planner instead of JSSP (``config`` must
-        then be the FOP configuration, see ``fop_batch_config``); ``max_accel`` / ``max_jerk`` = Vehicle.max_accel / max_jerk."""
+        then be the FOP configuration, see ``fop_batch_config``); ``max_accel`` / ``max_jerk`` = Vehicle.max_accel / max_jerk.
+        ``ego_update_mode`` = parameters["sim_config"]["ego_update_mode"]: "planner_expected_value" or "kinematics" (the
+        scenarios must then be packed with ``kinematics=True``)."""
+        assert ego_update_mode in ("planner_expected_value", "kinematics"), ego_update_mode
+        self.ego_update_mode = ego_update_mode
         if not torch.cuda.is_available():
             raise RuntimeError("dlii_jssp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -197,7 +216,7 @@ class BatchReplay:
             O, M, Tt, _ = p.state.shape
             keep = [_c(p.knot_s, np.float64), _c(p.coef, np.float64), _c(p.state, np.float64), _c(p.valid, np.uint8), _c(p.size, np.float64),
                     _c(p.prob, np.float64), _c(p.gt_state, np.float64), _c(p.gt_valid, np.uint8), _c(p.gt_size, np.float64),
-                    _c(p.cycle_time, np.float64), _c(p.cycle_now, np.int32), _c(p.cycle_end_step, np.int32)]
+                    _c(p.cycle_time, np.float64), _c(p.cycle_now, np.int32), _c(p.cycle_end_step, np.int32), _c(p.polyline, np.float64)]
             ptr = [None if a is None else a.ctypes.data for a in keep]
             si = JsspScenarioIn()
             si.knot_s, si.coef, si.K = ptr[0], ptr[1], len(p.knot_s)
@@ -216,6 +235,13 @@ class BatchReplay:
             if p.bounds is not None:
                 for i in range(4):
                     si.bounds[i] = float(p.bounds[i])
+            if self.ego_update_mode == "kinematics":
+                if p.polyline is None:
+                    raise ValueError(f"scenario {p.name}: kinematics mode needs pack_scenario(..., kinematics=True)")
+                from .planner import PURE_PURSUIT
+                si.ego_update_mode, si.polyline, si.n_polyline = 1, ptr[12], len(p.polyline)
+                si.pp_kv, si.pp_ld0 = PURE_PURSUIT["kv_ld0"]
+                si.pp_wheel_base = float(p.ego[5]) / PURE_PURSUIT["coff_wheel_base"]
             self._check(self.lib.jssp_batch_set_scenario(self._h, slot, C.byref(si), self.stream), f"jssp_batch_set_scenario[{slot}]")
         self._n, self._packed = len(packed), list(packed)
 
@@ -270,12 +296,14 @@ def fop_batch_config(fop, ego_length: float, ego_width: float, **caps) -> JsspCo
 
 
 def run_batch(scenarios: Sequence, device: int = 0, max_cycles: Optional[int] = None, batch: Optional[BatchReplay] = None,
-              kernel: Optional[str] = None, fop=None, max_accel: float = 8.0, max_jerk: float = 10.0) -> List[ReplayResult]:
+              kernel: Optional[str] = None, fop=None, max_accel: float = 8.0, max_jerk: float = 10.0,
+              ego_update_mode: str = "planner_expected_value") -> List[ReplayResult]:
     """Replay independent scenarios (ReplayScenario or PackedScenario) in lock-step on one GPU; same results as
     ``replay.run_sweep``.  Scenarios that are over before the first cycle are answered on the host.  ``fop`` (a
     FrenetOptimalPlannerSettings) replays with the FOP baseline planner instead of JSSP."""
     plan_steps = 50 if fop is None else int(np.ceil(fop.max_t / fop.delta_t))
-    packed = [s if isinstance(s, PackedScenario) else pack_scenario(s, plan_steps=plan_steps, max_cycles=max_cycles) for s in scenarios]
+    packed = [s if isinstance(s, PackedScenario) else pack_scenario(s, plan_steps=plan_steps, max_cycles=max_cycles,
+                                                                    kinematics=ego_update_mode == "kinematics") for s in scenarios]
     live = [i for i, p in enumerate(packed) if p.initial_end == END_RUNNING]
     out: List[Optional[ReplayResult]] = [None if i in set(live) else ReplayResult(p.name, p.initial_end, 0) for i, p in enumerate(packed)]
     if live:
@@ -287,7 +315,8 @@ def run_batch(scenarios: Sequence, device: int = 0, max_cycles: Optional[int] = 
                         max_obstacle_modes=max(1, max(p.state.shape[0] * p.state.shape[1] for p in todo)),
                         max_total_steps=max(p.state.shape[2] for p in todo))
             cfg = JsspConfig(ego_length=float(e[5]), ego_width=float(e[6]), **caps) if fop is None else fop_batch_config(fop, float(e[5]), float(e[6]), **caps)
-            batch = BatchReplay(cfg, device=device, max_scenarios=len(todo), max_cycles=need_c, fop=fop, max_accel=max_accel, max_jerk=max_jerk)
+            batch = BatchReplay(cfg, device=device, max_scenarios=len(todo), max_cycles=need_c, fop=fop, max_accel=max_accel, max_jerk=max_jerk,
+                                ego_update_mode=ego_update_mode)
         t0 = time.perf_counter()
         for lo in range(0, len(todo), batch.S):
             chunk = todo[lo:lo + batch.S]

@@ -280,6 +280,11 @@ SeedWork make_seed_work(const SeedGrids& g, int* counts, double* seeds, int cap_
 extern "C" {
 
 int32_t jssp_abi_version(void) { return JSSP_ABI_VERSION; }
+int32_t jssp_struct_size(int32_t which) {
+  const size_t sizes[] = {sizeof(jssp_config), sizeof(jssp_cycle_in), sizeof(jssp_cycle_out), sizeof(jssp_fop_in), sizeof(jssp_imm_params),
+                          sizeof(jssp_cycle_record), sizeof(jssp_scenario_result), sizeof(jssp_scenario_in)};
+  return which >= 0 && which < (int)(sizeof(sizes) / sizeof(sizes[0])) ? (int32_t)sizes[which] : -1;
+}
 
 const char* jssp_strerror(int32_t s) {
   switch (s) {
@@ -911,6 +916,8 @@ struct jssp_batch {
   // launch sizing: maxima over the scenarios set so far
   int max_K = 2, max_kpad = 2, max_OMpad = 0;
   std::vector<unsigned char> is_set;
+  std::vector<double*> d_poly;      // kinematics mode: the scenario's re-discretised reference line [n][6] (allocated on first use)
+  std::vector<int> poly_cap;
   int max_smem_optin = 0;
   int64_t launches = 0;
   char cuda_err[256] = {0};
@@ -964,6 +971,7 @@ int32_t jssp_batch_destroy(jssp_batch* b) {
   if (b->h_stage) cudaFreeHost(b->h_stage);
   void* fopdev[] = {b->d_fslots, b->d_fslots0, b->d_fop_tab, b->d_fop_int};
   for (void* q : fopdev) if (q) cudaFree(q);
+  for (double* q : b->d_poly) if (q) cudaFree(q);
   delete b;
   return JSSP_OK;
 }
@@ -1048,6 +1056,8 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   b->stage_cap = (size_t)32 << 20;
   CKC(cudaMallocHost(&b->h_stage, b->stage_cap));
   b->is_set.assign(S, 0);
+  b->d_poly.assign(S, nullptr);
+  b->poly_cap.assign(S, 0);
   CKC(allow_max_dynamic_smem(evaluate_batch_kernel<0>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_batch_kernel<1>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_small_batch_kernel, optin, &b->max_smem_optin));
@@ -1107,6 +1117,8 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
   if (in->O > 0 && (!in->state || !in->valid || !in->size || !in->prob)) return JSSP_ERR_INVALID_ARG;
   if (in->gt_state && (!in->gt_valid || !in->gt_size || in->gt_O < 0)) return JSSP_ERR_INVALID_ARG;
   if (!in->gt_state && in->M != 1 && in->O > 0) return JSSP_ERR_INVALID_ARG;   // the ground truth must be given for multi-modal predictions
+  if (in->ego_update_mode != 0 && in->ego_update_mode != 1) return JSSP_ERR_INVALID_ARG;
+  if (in->ego_update_mode == 1 && (!in->polyline || in->n_polyline < 1 || !(in->pp_wheel_base > 0.0))) return JSSP_ERR_INVALID_ARG;
   const int OM = in->O * in->M;
   const int gtO = in->gt_state ? in->gt_O : in->O;
   if (in->K > b->cfg.max_knots || OM > b->cfg.max_obstacle_modes || gtO > b->cfg.max_obstacle_modes || in->Tt > b->cfg.max_total_steps ||
@@ -1206,6 +1218,16 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
   q.cycle_time = ctime; q.cycle_now = cnow; q.cycle_end_step = cend;
   q.gt_state = gt_state; q.gt_valid = gt_valid; q.gt_size = gt_size;
   q.records = b->d_records + s * (size_t)b->C;
+  if (in->ego_update_mode == 1) {
+    if (b->poly_cap[s] < in->n_polyline) {
+      if (b->d_poly[s]) { CKB(cudaFree(b->d_poly[s])); b->d_poly[s] = nullptr; b->poly_cap[s] = 0; }
+      CKB(cudaMalloc(&b->d_poly[s], (size_t)in->n_polyline * 6 * sizeof(double)));
+      b->poly_cap[s] = in->n_polyline;
+    }
+    CKB(upload_staged(b, b->d_poly[s], in->polyline, (size_t)in->n_polyline * 6 * sizeof(double), st));
+    q.kin = 1; q.n_poly = in->n_polyline; q.poly = b->d_poly[s];
+    q.pp_kv = in->pp_kv; q.pp_ld0 = in->pp_ld0; q.pp_wb = in->pp_wheel_base;
+  }
   if (b->fop) {
     const jssp_fop_in& g = b->fop_grid;
     q.is_fop = 1;

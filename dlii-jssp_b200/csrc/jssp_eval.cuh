@@ -64,7 +64,11 @@ struct BatchSlot {
   int n_cycles_cap;               // the per-cycle tables hold n_cycles_cap + 1 entries: the replay pauses after that many cycles
   int seed_overflow;              // a cycle enumerated more seeds than max_seeds (the surplus was dropped): reported, never silent
   int last_n_pts;                 // Cartesian points of the trajectory in best_traj (0 = no trajectory selected yet)
-  int is_fop, pad2;               // the scenario's parameter record is a FopParams (FOP baseline in the batch)
+  int is_fop;                     // the scenario's parameter record is a FopParams (FOP baseline in the batch)
+  int kin;                        // ego_update_mode "kinematics": kinematic ego + pure pursuit + projected start state
+  int n_poly, pad3;
+  const double* poly;             // [n_poly][6] re-discretised reference line: x, y, yaw, arc, cos yaw, sin yaw
+  double pp_kv, pp_ld0, pp_wb;    // pure pursuit: ld = kv * v + ld0, wheel base
   double end;                     // end status: -1 running, 1 max_t, 1.5 goal, 2 collision, -2 no solution, -3 short trajectory
   double max_t, horizon;
   double goal_x, goal_y, goal_cos, goal_sin;
@@ -732,8 +736,43 @@ __device__ __forceinline__ bool rect_overlap_f64(double x1, double y1, double ya
 
 __device__ __forceinline__ void fop_store_lateral_start(EvalParams* self, double d, double d_d, double d_dd);   // jssp_fop.cuh
 
+// a % m with Python's sign convention (result in [0, m) for m > 0): controller.py:312 wraps the yaw with it
+__device__ __forceinline__ double py_mod(double a, double m) {
+  double r = fmod(a, m);
+  if (r != 0.0 && (r < 0.0) != (m < 0.0)) r += m;
+  return r;
+}
+
+// Front-wheel angle of the pure-pursuit tracker on the selected path (intersection_planner.py:365-389, 416-443, tracing
+// "plan_path"): nearest way point to the ego, walk along the path until the accumulated chord length reaches
+// ld = kv * v + ld0, steer towards that point.  `traj` = exported rows [n_pts][JSSP_TRAJ_COLS] (x, y in columns 9, 10).
+__device__ inline double pure_pursuit_angle(const double* traj, int n_pts, double x, double y, double yaw, double v, double kv,
+                                            double ld0, double wheel_base) {
+  const double ld = kv * v + ld0;
+  int idx = 0;
+  double bd = INFINITY;
+  for (int i = 0; i < n_pts; ++i) {                  // np.argmin(np.linalg.norm(ref_pos - pos, axis=1)): first minimum
+    const double dx = traj[(size_t)i * JSSP_TRAJ_COLS + 9] - x, dy = traj[(size_t)i * JSSP_TRAJ_COLS + 10] - y;
+    const double d = sqrt(dx * dx + dy * dy);
+    if (d < bd) { bd = d; idx = i; }
+  }
+  double l_steps = 0.0;
+  while (l_steps < ld && idx + 1 < n_pts) {
+    const double dx = traj[(size_t)(idx + 1) * JSSP_TRAJ_COLS + 9] - traj[(size_t)idx * JSSP_TRAJ_COLS + 9];
+    const double dy = traj[(size_t)(idx + 1) * JSSP_TRAJ_COLS + 10] - traj[(size_t)idx * JSSP_TRAJ_COLS + 10];
+    l_steps = l_steps + sqrt(dx * dx + dy * dy);
+    ++idx;
+  }
+  const double px = traj[(size_t)idx * JSSP_TRAJ_COLS + 9], py = traj[(size_t)idx * JSSP_TRAJ_COLS + 10];
+  const double alpha = atan2(py - y, px - x) - yaw;
+  return atan2(2.0 * wheel_base * sin(alpha), ld);
+}
+
 // Batched replay: end-of-cycle hand-off of one scenario, run by the block that exported the selected trajectory.
 __device__ __forceinline__ void batch_handoff(const EvalParams& p, int best, int N, int* sm_flag) {
+  __shared__ double hk[5];                           // the ego after Env.step's kinematic update: x, y, yaw, v, a
+  __shared__ double pr_d[32];
+  __shared__ int pr_i[32];
   BatchSlot* b = p.batch;
   __syncthreads();                                   // the exported rows (global) are visible to the whole block
   if (threadIdx.x == 0) *sm_flag = 0;
@@ -749,9 +788,26 @@ __device__ __forceinline__ void batch_handoff(const EvalParams& p, int best, int
   // Env.step in planner_expected_value mode (env.py:21-33 -> controller.py:256-263): the ego is first advanced by the
   // kinematic model with the action (0, 0) (controller.py:301-319) and the END STATUS is evaluated on that pose; only then is
   // the ego overwritten with sample 1 of the selected trajectory.
-  const double kx = b->ego_x + b->ego_v * cos(b->ego_yaw) * b->dt, ky = b->ego_y + b->ego_v * sin(b->ego_yaw) * b->dt;
-  const double kyaw = fmod(b->ego_yaw + b->ego_v / b->ego_l * 1.7 * 0.0 * b->dt + 3.14159265358979323846, 2.0 * 3.14159265358979323846) -
-                      3.14159265358979323846;
+  // In kinematics mode the action is (planned acceleration s_dd[1], pure-pursuit angle) (code/__main__.py:129-138; after "No
+  // solution" plan_traj hands the previous trajectory back, so both come from it again) and that pose IS the new ego.
+  const bool kin = b->kin != 0;
+  if (threadIdx.x == 0) {
+    double a = 0.0, rot = 0.0;
+    if (kin && ok) {
+      a = row1[3];
+      rot = pure_pursuit_angle(p.best_traj, np, b->ego_x, b->ego_y, b->ego_yaw, b->ego_v, b->pp_kv, b->pp_ld0, b->pp_wb);
+    }
+    a = fmin(fmax(a, -15.0), 15.0); rot = fmin(fmax(rot, -1.0), 1.0);                          // _action_cheaker (controller.py:265-268)
+    const double PI = 3.14159265358979323846;
+    hk[0] = b->ego_x + b->ego_v * cos(b->ego_yaw) * b->dt;
+    hk[1] = b->ego_y + b->ego_v * sin(b->ego_yaw) * b->dt;
+    hk[2] = py_mod(b->ego_yaw + b->ego_v / b->ego_l * 1.7 * tan(rot) * b->dt + PI, 2.0 * PI) - PI;
+    const double vn = b->ego_v + a * b->dt;
+    hk[3] = vn < 0.0 ? 0.0 : vn;
+    hk[4] = a;
+  }
+  __syncthreads();
+  const double kx = hk[0], ky = hk[1], kyaw = hk[2];
   if (ok) {
     tn = b->cycle_time[c + 1];                       // t + dt (controller.py:303)
     x = row1[9]; y = row1[10]; yaw = row1[11];
@@ -764,8 +820,34 @@ __device__ __forceinline__ void batch_handoff(const EvalParams& p, int best, int
       }
     }
   }
+  // kinematics mode: the next cycle starts from FrenetState.from_state(new ego, polyline) - nearest polyline point (first
+  // minimum of the squared distance, like numpy.argmin), found by the whole block
+  int near = 0;
+  if (kin && ok) {
+    double bd = INFINITY;
+    int bi = -1;
+    for (int m = threadIdx.x; m < b->n_poly; m += blockDim.x) {
+      const double ex = b->poly[(size_t)m * 6] - kx, ey = b->poly[(size_t)m * 6 + 1] - ky;
+      const double d2 = ex * ex + ey * ey;
+      if (d2 < bd) { bd = d2; bi = m; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_down_sync(0xffffffffu, bd, o);
+      const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+      if (oi >= 0 && (bi < 0 || od < bd || (od == bd && oi < bi))) { bd = od; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { pr_d[threadIdx.x >> 5] = bd; pr_i[threadIdx.x >> 5] = bi; }
+  }
   __syncthreads();
   if (threadIdx.x != 0) return;
+  if (kin && ok) {
+    double bd = pr_d[0];
+    int bi = pr_i[0];
+    for (int q = 1; q < (int)((blockDim.x + 31) >> 5); ++q)
+      if (pr_i[q] >= 0 && (bi < 0 || pr_d[q] < bd || (pr_d[q] == bd && pr_i[q] < bi))) { bd = pr_d[q]; bi = pr_i[q]; }
+    near = bi < 0 ? 0 : bi;
+  }
   jssp_cycle_record* rec = b->records + c;
   if (p.n_seeds_ptr && p.n_seeds_ptr[3]) b->seed_overflow = 1;
   rec->best_idx = best; rec->n_candidates = N; rec->best_cost = best >= 0 ? p.best->cost : nan("");
@@ -774,22 +856,35 @@ __device__ __forceinline__ void batch_handoff(const EvalParams& p, int best, int
     b->end = (!fresh && b->last_n_pts == 0) ? -2.0 : -3.0;
     b->live = 0;
   } else {
-    rec->t = tn; rec->x = x; rec->y = y; rec->v = row1[2]; rec->a = row1[3]; rec->yaw = yaw;
+    if (kin) { x = kx; y = ky; yaw = kyaw; }
+    const double vnew = kin ? hk[3] : row1[2], anew = kin ? hk[4] : row1[3];
+    rec->t = tn; rec->x = x; rec->y = y; rec->v = vnew; rec->a = anew; rec->yaw = yaw;
     double status = -1.0;
     if (*sm_flag) status = 2.0;
     if (tn >= b->max_t) status = fmax(status, 1.0);                                          // controller.py:352-353
     if (kx > b->bx_max || kx < b->bx_min || ky > b->by_max || ky < b->by_min) status = fmax(status, 1.5);   // out of the map (:362-369)
     const double dx = kx - b->goal_x, dy = ky - b->goal_y;
     if (b->goal_sin * dy + b->goal_cos * dx >= 0.0) status = fmax(status, 1.5);               // goal line passed (:372-377)
-    b->ego_x = x; b->ego_y = y; b->ego_yaw = yaw; b->ego_v = row1[2];                         // env.py:26-30
+    b->ego_x = x; b->ego_y = y; b->ego_yaw = yaw; b->ego_v = vnew;                            // env.py:26-30 (kinematics: the model's pose)
     if (fresh) b->last_n_pts = np;
     b->end = status;
     if (status != -1.0) b->live = 0;
-    // next cycle starts from sample 1 of the selected trajectory (intersection_planner.py:312)
+    // next cycle starts from sample 1 of the selected trajectory (intersection_planner.py:312) or, in kinematics mode, from
+    // the projection of the new ego on the re-discretised reference line (:308-310; dlii_jssp_b200.frenet.FrenetState.from_state)
+    double fs = row1[1], fsd = row1[2], fsdd = row1[3], fd = row1[5], fdd = row1[6], fddd = row1[7];
+    if (kin) {
+      const double* pl = b->poly + (size_t)near * 6;
+      const double ex = x - pl[0], ey = y - pl[1], tx = pl[4], ty = pl[5];
+      const double dyaw = yaw - pl[2];
+      fs = pl[3] + (ex * tx + ey * ty);
+      fd = -ex * ty + ey * tx;
+      fsd = vnew * cos(dyaw); fdd = vnew * sin(dyaw);
+      fsdd = anew * cos(dyaw); fddd = anew * sin(dyaw);
+    }
     EvalParams* q = p.self;
-    q->s0 = row1[1]; q->v0 = row1[2]; q->a0 = row1[3];
-    if (b->is_fop) fop_store_lateral_start(q, row1[5], row1[6], row1[7]);
-    else for (int w = 0; w < p.W; ++w) quintic_coeffs(row1[5], row1[6], row1[7], b->targets[w], 0.0, 0.0, b->horizon, q->quintic[w]);
+    q->s0 = fs; q->v0 = fsd; q->a0 = fsdd;
+    if (b->is_fop) fop_store_lateral_start(q, fd, fdd, fddd);
+    else for (int w = 0; w < p.W; ++w) quintic_coeffs(fd, fdd, fddd, b->targets[w], 0.0, 0.0, b->horizon, q->quintic[w]);
     const int now = b->cycle_now[c + 1];
     q->now = now; q->tcap = b->final_step - now;
     int rows = 0;

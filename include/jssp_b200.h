@@ -117,6 +117,10 @@ typedef struct jssp_cycle_out {
 
 /* -- lifecycle ------------------------------------------------------------------------------------------ */
 int32_t jssp_abi_version(void);
+/* sizeof of the public structs as this library was compiled, for a binding to check its own declarations against:
+ * which = 0 jssp_config, 1 jssp_cycle_in, 2 jssp_cycle_out, 3 jssp_fop_in, 4 jssp_imm_params, 5 jssp_cycle_record,
+ * 6 jssp_scenario_result, 7 jssp_scenario_in; -1 for anything else */
+int32_t jssp_struct_size(int32_t which);
 const char* jssp_strerror(int32_t status);
 /* last CUDA error string seen by this handle (for JSSP_ERR_CUDA) */
 const char* jssp_last_cuda_error(const jssp_handle* h);
@@ -276,7 +280,17 @@ typedef struct jssp_scenario_in {
                                        overwritten with sample 1 of the selected trajectory (env.py:23-30) */
   double bounds[4];                 /* x_min, x_max, y_min, y_max of the map's lane vertices (controller.py:279-288) */
   int32_t has_bounds;               /* 0: no map, the bounds test is skipped */
-  int32_t reserved2;
+  /* parameters["sim_config"]["ego_update_mode"] (configuration_parameters.py:4): 0 = "planner_expected_value" (default: the ego
+   * jumps to sample 1 of the selected trajectory and the next cycle starts from its Frenet state); 1 = "kinematics"
+   * (code/__main__.py:136-138): the ego follows the kinematic model (controller.py:301-319) driven by the planned acceleration
+   * s_dd[1] and the pure-pursuit front-wheel angle on the selected path (intersection_planner.py:365-443), and every cycle
+   * starts from the projection of that ego on the re-discretised reference line (FrenetState.from_state, :308-310) */
+  int32_t ego_update_mode;
+  /* kinematics mode only: the re-discretised reference line [n_polyline][6] = x, y, yaw, arc length of the polyline up to the
+   * point (sum of the chord lengths before it), cos(yaw), sin(yaw)  (generate_frenet_frame, jssp.py:366-371) */
+  const double* polyline; int32_t n_polyline; int32_t reserved2;
+  double pp_kv, pp_ld0;             /* pure pursuit look-ahead ld = kv * v + ld0  (paras_control["pure_pursuit"]["kv_ld0"]) */
+  double pp_wheel_base;             /* ego length / coff_wheel_base */
 } jssp_scenario_in;
 
 int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_scenarios, int32_t max_cycles, jssp_batch** out);

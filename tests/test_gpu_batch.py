@@ -98,3 +98,24 @@ def test_c2_multimodal_predictions_batch_matches_oracle(scenario_fixture):
         differs |= g.best_idx != R.run_replay(sc, max_cycles=18).best_idx
     assert differs                   # the predicted modes change at least one selection w.r.t. the ground-truth-only replay
     bt.close()
+
+
+def test_batch_kinematics_mode_matches_host_loop_and_reference_golden(scenario_fixture, golden_dir):
+    """ego_update_mode "kinematics" in the batched device-resident replay (kinematic ego, pure pursuit on the selected path and
+    the Frenet projection of the new ego all in the hand-off): same selections as the host-driven loop and as the reference's own
+    complete loop in that mode (kin_* of replay_golden_8_3_4_565.npz), ego rows to 1e-8 (device vs libm trigonometry)."""
+    import os
+    g = np.load(os.path.join(golden_dir, "replay_golden_8_3_4_565.npz"))
+    scs = [scenario_fixture, S.perturbed_scenario(scenario_fixture, 3)]
+    got = B.run_batch(scs, ego_update_mode="kinematics")
+    assert got[0].best_idx == g["kin_best_idx"].tolist()
+    assert got[0].end == g["kin_ends"][-1] and got[0].cycles == len(g["kin_rows"])
+    np.testing.assert_allclose(np.array(got[0].ego_rows), g["kin_rows"], rtol=1e-8, atol=1e-8)
+    for sc, r in zip(scs, got):
+        solo = R.run_replay(sc, ego_update_mode="kinematics")
+        assert r.best_idx == solo.best_idx and r.n_candidates == solo.n_candidates and r.end == solo.end
+        np.testing.assert_allclose(np.array(r.ego_rows), np.array(solo.ego_rows), rtol=1e-9, atol=1e-9)
+    # the default mode is untouched by the packed polyline
+    a = B.run_batch([B.pack_scenario(scs[0], kinematics=True)], max_cycles=12)[0]
+    b = B.run_batch([scs[0]], max_cycles=12)[0]
+    assert a.best_idx == b.best_idx and a.ego_rows == b.ego_rows

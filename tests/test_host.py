@@ -39,6 +39,9 @@ def test_struct_layouts_match_header():
             assert list(v) == list(d.cost_weights)
         else:
             assert v == getattr(d, f), f          # ctypes layout == C layout, field by field
+    for which, st in enumerate(_lib.STRUCTS):        # every ctypes declaration against the compiled header
+        assert lib.jssp_struct_size(which) == C.sizeof(st), st.__name__
+    assert lib.jssp_struct_size(len(_lib.STRUCTS)) == -1
     assert C.sizeof(_lib.JsspCycleIn) == 6 * 8 + 4 * 4 + 16 * 8 + 8 + 8
     assert C.sizeof(_lib.JsspCycleOut) == 5 * 8 + 4 * 4 + 8
 
