@@ -232,7 +232,6 @@ static int32_t measure_fma(int device, double* tflops) {
   return JSSP_OK;
 }
 
-constexpr int BATCH_EVAL_THREADS = 128;   // block size of the thread / group evaluation kernels in the batched replay
 
 // opt a kernel in to the largest dynamic shared memory the device allows next to the kernel's own static shared memory;
 // *budget is lowered to the smallest such limit seen (the host sizes launches against it)
@@ -916,6 +915,9 @@ struct jssp_batch {
   // launch sizing: maxima over the scenarios set so far
   int max_K = 2, max_kpad = 2, max_OMpad = 0;
   std::vector<unsigned char> is_set;
+#ifdef JSSP_PROFILE_PHASES
+  unsigned long long* phase_ts = nullptr;
+#endif
   std::vector<double*> d_poly;      // kinematics mode: the scenario's re-discretised reference line [n][6] (allocated on first use)
   std::vector<int> poly_cap;
   int max_smem_optin = 0;
@@ -1203,6 +1205,9 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
   p.ticket = b->d_ticket + s; p.best = b->d_best + s;
   p.best_traj = b->d_best_traj + s * (size_t)b->P * JSSP_TRAJ_COLS;
   p.batch = b->d_bslots + s; p.self = b->d_slots + s;
+#ifdef JSSP_PROFILE_PHASES
+  p.phase_ts = b->phase_ts;
+#endif
   BatchSlot q{};
   q.live = 1; q.cycle = 0; q.n_cycles_cap = in->n_cycles; q.final_step = in->final_time_step;
   q.gt_O = gtO; q.gt_Tt = Tt;
@@ -1348,5 +1353,10 @@ int32_t jssp_batch_best_traj(jssp_batch* b, int32_t slot, double* out, void* str
   CKB(cudaStreamSynchronize(st));
   return JSSP_OK;
 }
+
+#ifdef JSSP_PROFILE_PHASES
+/* same for the batched replay (tools/batch_phase_probe.py): [scenarios * blocks][8]; call before jssp_batch_set_scenario */
+int32_t jssp_batch_debug_phase_buffer(jssp_batch* b, unsigned long long* dev) { if (!b) return JSSP_ERR_INVALID_ARG; b->phase_ts = dev; return JSSP_OK; }
+#endif
 
 }  // extern "C"

@@ -1086,7 +1086,7 @@ __device__ __forceinline__ void load_slot(EvalParams* dst, const EvalParams* src
 }
 
 template <int kMode>
-__global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_batch_kernel(const EvalParams* __restrict__ slots) {
+__global__ void __launch_bounds__(BATCH_EVAL_THREADS, BATCH_MIN_BLOCKS) evaluate_batch_kernel(const EvalParams* __restrict__ slots) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(16) EvalParams sp;
   __shared__ double red_cost[EVAL_THREADS / 32];
@@ -1099,7 +1099,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_batch_
 }
 
 template <int kMode>
-__global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_group_batch_kernel(const EvalParams* __restrict__ slots) {
+__global__ void __launch_bounds__(BATCH_EVAL_THREADS, BATCH_MIN_BLOCKS) evaluate_group_batch_kernel(const EvalParams* __restrict__ slots) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(16) EvalParams sp;
   __shared__ double red_cost[EVAL_THREADS / 32];
