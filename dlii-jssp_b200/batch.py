@@ -64,6 +64,46 @@ class PackedScenario:
     def n_cycles(self) -> int:
         return len(self.cycle_time) - 1
 
+    def c_view(self, kinematics: bool = False) -> JsspScenarioIn:
+        """The scenario as the ``jssp_scenario_in`` of the C ABI (built once and kept with the arrays it points into: loading
+        a packed scenario again costs one library call)."""
+        cache = self.__dict__.setdefault("_cview", {})
+        hit = cache.get(kinematics)
+        if hit is not None:
+            return hit[0]
+        p = self
+        O, M, Tt, _ = p.state.shape
+        keep = [_c(p.knot_s, np.float64), _c(p.coef, np.float64), _c(p.state, np.float64), _c(p.valid, np.uint8), _c(p.size, np.float64),
+                _c(p.prob, np.float64), _c(p.gt_state, np.float64), _c(p.gt_valid, np.uint8), _c(p.gt_size, np.float64),
+                _c(p.cycle_time, np.float64), _c(p.cycle_now, np.int32), _c(p.cycle_end_step, np.int32), _c(p.polyline, np.float64)]
+        ptr = [None if a is None else a.ctypes.data for a in keep]
+        si = JsspScenarioIn()
+        si.knot_s, si.coef, si.K = ptr[0], ptr[1], len(p.knot_s)
+        si.state, si.valid, si.size, si.prob = ptr[2], ptr[3], ptr[4], ptr[5]
+        si.O, si.M, si.Tt, si.n_dict = O, M, Tt, int(p.n_dict)
+        si.gt_state, si.gt_valid, si.gt_size = ptr[6], ptr[7], ptr[8]
+        si.gt_O = 0 if p.gt_state is None else p.gt_state.shape[0]
+        for i in range(6):
+            si.frenet0[i] = float(p.frenet0[i])
+        si.max_t, si.final_time_step, si.n_cycles = p.max_t, p.final_time_step, p.n_cycles
+        si.cycle_time, si.cycle_now, si.cycle_end_step = ptr[9], ptr[10], ptr[11]
+        si.goal_x, si.goal_y, si.goal_yaw = [float(v) for v in p.goal_pose]
+        si.ego_length, si.ego_width = float(p.ego[5]), float(p.ego[6])
+        si.ego0[0], si.ego0[1], si.ego0[2], si.ego0[3] = float(p.ego[0]), float(p.ego[1]), float(p.ego[4]), float(p.ego[2])   # x, y, yaw, v
+        si.has_bounds = 0 if p.bounds is None else 1
+        if p.bounds is not None:
+            for i in range(4):
+                si.bounds[i] = float(p.bounds[i])
+        if kinematics:
+            if p.polyline is None:
+                raise ValueError(f"scenario {p.name}: kinematics mode needs pack_scenario(..., kinematics=True)")
+            from .planner import PURE_PURSUIT
+            si.ego_update_mode, si.polyline, si.n_polyline = 1, ptr[12], len(p.polyline)
+            si.pp_kv, si.pp_ld0 = PURE_PURSUIT["kv_ld0"]
+            si.pp_wheel_base = float(p.ego[5]) / PURE_PURSUIT["coff_wheel_base"]
+        cache[kinematics] = (si, keep)
+        return si
+
 
 def clock_tables(dt: float, n_cycles: int, n_total: int):
     """The replay clock as the reference advances it: t <- float(t + dt) (controller.py:303); time_step_now = int(t / dt)
@@ -210,39 +250,14 @@ class BatchReplay:
     def load(self, packed: Sequence[PackedScenario]):
         """Upload the scenarios into slots 0..len-1 and reset their replay state."""
         assert 1 <= len(packed) <= self.S, (len(packed), self.S)
+        stream = self.stream
+        kin = self.ego_update_mode == "kinematics"
         for slot, p in enumerate(packed):
             if abs(p.dt - self.cfg.delta_t) > 1e-12:
                 raise ValueError(f"scenario {p.name}: dt = {p.dt} but the batch was created for delta_t = {self.cfg.delta_t}")
-            O, M, Tt, _ = p.state.shape
-            keep = [_c(p.knot_s, np.float64), _c(p.coef, np.float64), _c(p.state, np.float64), _c(p.valid, np.uint8), _c(p.size, np.float64),
-                    _c(p.prob, np.float64), _c(p.gt_state, np.float64), _c(p.gt_valid, np.uint8), _c(p.gt_size, np.float64),
-                    _c(p.cycle_time, np.float64), _c(p.cycle_now, np.int32), _c(p.cycle_end_step, np.int32), _c(p.polyline, np.float64)]
-            ptr = [None if a is None else a.ctypes.data for a in keep]
-            si = JsspScenarioIn()
-            si.knot_s, si.coef, si.K = ptr[0], ptr[1], len(p.knot_s)
-            si.state, si.valid, si.size, si.prob = ptr[2], ptr[3], ptr[4], ptr[5]
-            si.O, si.M, si.Tt, si.n_dict = O, M, Tt, int(p.n_dict)
-            si.gt_state, si.gt_valid, si.gt_size = ptr[6], ptr[7], ptr[8]
-            si.gt_O = 0 if p.gt_state is None else p.gt_state.shape[0]
-            for i in range(6):
-                si.frenet0[i] = float(p.frenet0[i])
-            si.max_t, si.final_time_step, si.n_cycles = p.max_t, p.final_time_step, min(p.n_cycles, self.C)
-            si.cycle_time, si.cycle_now, si.cycle_end_step = ptr[9], ptr[10], ptr[11]
-            si.goal_x, si.goal_y, si.goal_yaw = [float(v) for v in p.goal_pose]
-            si.ego_length, si.ego_width = float(p.ego[5]), float(p.ego[6])
-            si.ego0[0], si.ego0[1], si.ego0[2], si.ego0[3] = float(p.ego[0]), float(p.ego[1]), float(p.ego[4]), float(p.ego[2])   # x, y, yaw, v
-            si.has_bounds = 0 if p.bounds is None else 1
-            if p.bounds is not None:
-                for i in range(4):
-                    si.bounds[i] = float(p.bounds[i])
-            if self.ego_update_mode == "kinematics":
-                if p.polyline is None:
-                    raise ValueError(f"scenario {p.name}: kinematics mode needs pack_scenario(..., kinematics=True)")
-                from .planner import PURE_PURSUIT
-                si.ego_update_mode, si.polyline, si.n_polyline = 1, ptr[12], len(p.polyline)
-                si.pp_kv, si.pp_ld0 = PURE_PURSUIT["kv_ld0"]
-                si.pp_wheel_base = float(p.ego[5]) / PURE_PURSUIT["coff_wheel_base"]
-            self._check(self.lib.jssp_batch_set_scenario(self._h, slot, C.byref(si), self.stream), f"jssp_batch_set_scenario[{slot}]")
+            si = p.c_view(kin)
+            si.n_cycles = min(p.n_cycles, self.C)
+            self._check(self.lib.jssp_batch_set_scenario(self._h, slot, C.byref(si), stream), f"jssp_batch_set_scenario[{slot}]")
         self._n, self._packed = len(packed), list(packed)
 
     def reset(self):
@@ -270,17 +285,24 @@ class BatchReplay:
         self._check(self.lib.jssp_batch_best_traj(self._h, slot, out.ctypes.data, self.stream), "jssp_batch_best_traj")
         return out
 
-    def results(self) -> List[ReplayResult]:
+    def results(self, lists: bool = True) -> List[ReplayResult]:
+        """Fetch and decode: one ReplayResult per loaded scenario.  ``lists=False`` leaves ``best_idx`` / ``n_candidates`` /
+        ``ego_rows`` as NumPy views of the fetched records ([n], [n], [n, 6]) instead of Python lists of ints / tuples."""
         res, rec = self.fetch()
+        rows_all = np.stack([rec[f] for f in ("t", "x", "y", "v", "a", "yaw")], -1)     # [S, C, 6]
+        ok_all = ~np.isnan(rec["t"])
+        bi_all, nc_all, cyc, ends = rec["best_idx"], rec["n_candidates"], res["cycles"].tolist(), res["end"].tolist()
         out = []
         for s, p in enumerate(self._packed):
-            n = int(res["cycles"][s])
-            r = rec[s, :n]
-            rr = ReplayResult(p.name, float(res["end"][s]), n)
-            rr.best_idx = r["best_idx"].tolist()
-            rr.n_candidates = r["n_candidates"].tolist()
-            ok = ~np.isnan(r["t"])
-            rr.ego_rows = [tuple(row) for row in np.stack([r[f][ok] for f in ("t", "x", "y", "v", "a", "yaw")], 1).tolist()]
+            n = cyc[s]
+            rows = rows_all[s, :n]
+            if not ok_all[s, :n].all():
+                rows = rows[ok_all[s, :n]]
+            rr = ReplayResult(p.name, ends[s], n)
+            if lists:
+                rr.best_idx, rr.n_candidates, rr.ego_rows = bi_all[s, :n].tolist(), nc_all[s, :n].tolist(), list(map(tuple, rows.tolist()))
+            else:
+                rr.best_idx, rr.n_candidates, rr.ego_rows = bi_all[s, :n], nc_all[s, :n], rows
             out.append(rr)
         return out
 
