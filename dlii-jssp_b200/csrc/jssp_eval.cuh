@@ -189,6 +189,73 @@ __device__ __forceinline__ bool curvature_fails(double kmax, double pdx, double 
   return fabs(dyaw) > phi;      // pds == 0: inf fails (dyaw != 0), nan passes (dyaw == 0)
 }
 
+// separating-axis test of the ego rectangle at (x, y, heading (c, sn)) against obstacle mode om at abs_step
+__device__ __forceinline__ bool narrow_hit(const EvalParams& p, int abs_step, int om, float dxf, float dyf, double x, double y, double c,
+                                           double sn) {
+  const size_t gi = (size_t)abs_step * p.OM + om;
+  const float4 nb = __ldg(p.narrow + gi);
+  const int cls = sat_classify_f32(dxf, dyf, (float)c, (float)sn, (float)p.ea, (float)p.eb, nb.x, nb.y, nb.z, nb.w, SAT_EPS);
+  if (cls != 0) return cls < 0;
+  const double* q = p.obs64 + gi * 4;
+  return sat_intersects_f64(q[0] - x, q[1] - y, c, sn, p.ea, p.eb, q[2], q[3], p.ext64[2 * om], p.ext64[2 * om + 1]);
+}
+
+// Collision row r (sample i of the candidate, pose (x, y, heading (c, sn))) against the obstacle states of that step: a
+// hit by a mode with prob >= p_min vetoes the candidate, a hit by a weaker mode adds its probability to the risk term.
+__device__ __forceinline__ void collide_row(const EvalParams& p, const BlockTables& tb, int r, int i, double x, double y, double c, double sn,
+                                            bool& collided, double& risk) {
+  if (collided || p.n_dict <= 0 || i >= p.tcap) return;
+  const int abs_step = p.now + i;
+  if (abs_step >= p.Tt) return;
+  const float4* row = tb.broad + (size_t)(tb.broad_row0 + r * tb.broad_stride) * p.OMpad;
+  const float fx = (float)(x - p.ox), fy = (float)(y - p.oy);
+  const float m2x = -2.0f * fx, m2y = -2.0f * fy, ne2 = -fmaf(fx, fx, fy * fy);
+  if (tb.use_lists) {      // block-level culled rows: a handful of entries instead of OMpad
+    const int cnt = tb.row_cnt[r];
+    const float4* e = tb.list + tb.row_off[r];
+    for (int k = 0; k < cnt; ++k) {
+      const float4 b = e[k];
+      if (fmaf(b.x, m2x, fmaf(b.y, m2y, b.z)) <= ne2) {
+        const int om = __float_as_int(b.w);
+        if (narrow_hit(p, abs_step, om, b.x - fx, b.y - fy, x, y, c, sn)) {
+          const float pr = __ldg(p.probf + om);
+          if ((double)pr >= p.p_min) { collided = true; return; }
+          risk = risk + (double)pr;
+        }
+      }
+    }
+    return;
+  }
+  for (int base = 0; base < p.OM; base += 32) {
+    unsigned int mask = 0u;
+    if (p.OM - base >= 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float4 b = row[base + j];
+        const float t = fmaf(b.x, m2x, fmaf(b.y, m2y, b.z));
+        mask |= (t <= ne2) ? (1u << j) : 0u;
+      }
+    } else {                                  // last, partial chunk: the padding up to OMpad is never touched
+      const int nj = p.OM - base;
+#pragma unroll 4
+      for (int j = 0; j < nj; ++j) {
+        const float4 b = row[base + j];
+        const float t = fmaf(b.x, m2x, fmaf(b.y, m2y, b.z));
+        mask |= (t <= ne2) ? (1u << j) : 0u;
+      }
+    }
+    while (mask) {      // rare: bounding circles overlap -> separating-axis test
+      const int om = base + __ffs(mask) - 1;
+      mask &= mask - 1u;
+      const float4 b = row[om];
+      if (narrow_hit(p, abs_step, om, b.x - fx, b.y - fy, x, y, c, sn)) {
+        if ((double)b.w >= p.p_min) { collided = true; return; }
+        risk = risk + (double)b.w;
+      }
+    }
+  }
+}
+
 // -- the evaluation sink ---------------------------------------------------------------------------------------------
 struct EvalSink {
   const EvalParams& p;
@@ -221,70 +288,10 @@ struct EvalSink {
     if (curvature_fails(p.kmax, pdx, pdy, pds, pc, psn, dx, dy, ds, c, sn)) curv_fail = true;
   }
 
-  // separating-axis test of the ego rectangle at (x, y, heading (c, sn)) against obstacle mode om at abs_step
-  __device__ __forceinline__ bool narrow_hit(int abs_step, int om, float dxf, float dyf, double x, double y, double c, double sn) const {
-    const size_t gi = (size_t)abs_step * p.OM + om;
-    const float4 nb = __ldg(p.narrow + gi);
-    const int cls = sat_classify_f32(dxf, dyf, (float)c, (float)sn, (float)p.ea, (float)p.eb, nb.x, nb.y, nb.z, nb.w, SAT_EPS);
-    if (cls != 0) return cls < 0;
-    const double* q = p.obs64 + gi * 4;
-    return sat_intersects_f64(q[0] - x, q[1] - y, c, sn, p.ea, p.eb, q[2], q[3], p.ext64[2 * om], p.ext64[2 * om + 1]);
-  }
-
   __device__ __forceinline__ void collide(int i, double x, double y, double c, double sn) {
     if (i != next_check) return;               // i % check_res == 0 without the division
     next_check += p.check_res;
-    const int r = row++;
-    if (collided || p.n_dict <= 0 || i >= p.tcap) return;
-    const int abs_step = p.now + i;
-    if (abs_step >= p.Tt) return;
-    const float4* row = tb.broad + (size_t)(tb.broad_row0 + r * tb.broad_stride) * p.OMpad;
-    const float fx = (float)(x - p.ox), fy = (float)(y - p.oy);
-    const float m2x = -2.0f * fx, m2y = -2.0f * fy, ne2 = -fmaf(fx, fx, fy * fy);
-    if (tb.use_lists) {      // block-level culled rows: a handful of entries instead of OMpad
-      const int cnt = tb.row_cnt[r];
-      const float4* e = tb.list + tb.row_off[r];
-      for (int k = 0; k < cnt; ++k) {
-        const float4 b = e[k];
-        if (fmaf(b.x, m2x, fmaf(b.y, m2y, b.z)) <= ne2) {
-          const int om = __float_as_int(b.w);
-          if (narrow_hit(abs_step, om, b.x - fx, b.y - fy, x, y, c, sn)) {
-            const float pr = __ldg(p.probf + om);
-            if ((double)pr >= p.p_min) { collided = true; return; }
-            risk = risk + (double)pr;
-          }
-        }
-      }
-      return;
-    }
-    for (int base = 0; base < p.OM; base += 32) {
-      unsigned int mask = 0u;
-      if (p.OM - base >= 32) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float4 b = row[base + j];
-          const float t = fmaf(b.x, m2x, fmaf(b.y, m2y, b.z));
-          mask |= (t <= ne2) ? (1u << j) : 0u;
-        }
-      } else {                                  // last, partial chunk: the padding up to OMpad is never touched
-        const int nj = p.OM - base;
-#pragma unroll 4
-        for (int j = 0; j < nj; ++j) {
-          const float4 b = row[base + j];
-          const float t = fmaf(b.x, m2x, fmaf(b.y, m2y, b.z));
-          mask |= (t <= ne2) ? (1u << j) : 0u;
-        }
-      }
-      while (mask) {      // rare: bounding circles overlap -> separating-axis test
-        const int om = base + __ffs(mask) - 1;
-        mask &= mask - 1u;
-        const float4 b = row[om];
-        if (narrow_hit(abs_step, om, b.x - fx, b.y - fy, x, y, c, sn)) {
-          if ((double)b.w >= p.p_min) { collided = true; return; }
-          risk = risk + (double)b.w;
-        }
-      }
-    }
+    collide_row(p, tb, row++, i, x, y, c, sn, collided, risk);
   }
   __device__ __forceinline__ void segment(int i, double x, double y, double dx, double dy, double ds, double c, double sn) {
     if (i >= 1) curvature_step(dx, dy, ds, c, sn);

@@ -102,7 +102,7 @@ __device__ __forceinline__ void evaluate_small_body(const EvalParams& p, unsigne
           for (int base = 0; base < p.OMpad; base += 32) {
             const float4 b = __ldg(row + base + lane);
             bool hit = fmaf(b.x, m2x, fmaf(b.y, m2y, b.z)) <= ne2;
-            if (hit) hit = probe.narrow_hit(abs_step, base + lane, b.x - fx, b.y - fy, x, y, c, sn);
+            if (hit) hit = narrow_hit(p, abs_step, base + lane, b.x - fx, b.y - fy, x, y, c, sn);
             const bool hard = hit && (double)b.w >= p.p_min;
             if (__any_sync(0xffffffffu, hard)) { collided = true; break; }
             unsigned int soft = __ballot_sync(0xffffffffu, hit);

@@ -146,3 +146,18 @@ def test_fop_batched_replay_matches_single_replays_and_oracle(scenario_fixture):
     cpu = replay_oracle.replay(sc, tuple(B.pack_scenario(sc).frenet0), S.pack_obstacle_dict, R.end_status, R.goal_pose_of(sc), max_cycles=15, fop_cfg=cfg)
     assert got[0].best_idx == cpu["best_idx"] and got[0].end == cpu["end"]
     np.testing.assert_allclose(np.array(got[0].ego_rows), np.array(cpu["rows"]), rtol=1e-9, atol=1e-9)
+
+
+def test_fop_batched_replay_in_kinematics_mode(scenario_fixture):
+    """FOP baseline + "kinematics" ego-update mode together in the batched replay against the host-driven loop."""
+    from dlii_jssp_b200 import replay as R, batch as B
+    st = J.FrenetOptimalPlannerSettings(num_width=3, num_speed=40, num_t=4, highest_speed=18.0, lowest_speed=0.0, min_planning_t=5.0, max_planning_t=5.5)
+    sc = scenario_fixture
+    got = B.run_batch([sc], max_cycles=20, fop=st, ego_update_mode="kinematics")[0]
+    planner = J.IntersectionPlanner(J.PlannerSettings(), sc.observation(), "frenet")
+    planner.fplanner.engine.close()
+    planner.fplanner = J.FrenetOptimalPlanner(st, planner.ego_vehicle)
+    solo = R.run_replay(sc, max_cycles=20, planner=planner, method="frenet", ego_update_mode="kinematics")
+    assert got.best_idx == solo.best_idx and got.end == solo.end and got.cycles == solo.cycles == 20
+    np.testing.assert_allclose(np.array(got.ego_rows), np.array(solo.ego_rows), rtol=1e-9, atol=1e-9)
+    planner.fplanner.engine.close()
