@@ -133,7 +133,7 @@ __device__ __forceinline__ void walk_core(const BlockTables& tb, Lon& lon, const
       const double dx = x - xp, dy = y - yp;
       const double q = dx * dx + dy * dy;
       double ds, c = 1.0, sn = 0.0;
-      if (q > 1e-200 && q < 1e200) { const double inv = rsqrt(q); ds = q * inv; c = dx * inv; sn = dy * inv; }
+      if (q > 1e-200 && q < 1e200) { const double inv = rsqrt_fast(q); ds = q * inv; c = dx * inv; sn = dy * inv; }
       else { ds = hypot(dx, dy); if (ds > 0.0) { c = dx / ds; sn = dy / ds; } }
       sink.segment(i - 1, xp, yp, dx, dy, ds, c, sn);
     }
@@ -354,7 +354,7 @@ __device__ __forceinline__ void walk_group(const EvalParams& p, const BlockTable
         const double dx = x - xp, dy = y - yp;
         const double q = dx * dx + dy * dy;
         double ds, c = 1.0, sn = 0.0;
-        if (q > 1e-200 && q < 1e200) { const double inv = rsqrt(q); ds = q * inv; c = dx * inv; sn = dy * inv; }
+        if (q > 1e-200 && q < 1e200) { const double inv = rsqrt_fast(q); ds = q * inv; c = dx * inv; sn = dy * inv; }
         else { ds = hypot(dx, dy); if (ds > 0.0) { c = dx / ds; sn = dy / ds; } }
         sink.segment(i - 1, xp, yp, dx, dy, ds, c, sn);
       }
@@ -633,7 +633,7 @@ __device__ __forceinline__ void export_tail(const BlockTables& tb, double (&row)
     const double dx = ex[0][i + 1] - row[9], dy = ex[1][i + 1] - row[10];
     const double q = dx * dx + dy * dy;
     row[11] = heading_of(dx, dy);
-    row[12] = (q > 1e-200 && q < 1e200) ? q * rsqrt(q) : hypot(dx, dy);
+    row[12] = (q > 1e-200 && q < 1e200) ? q * rsqrt_fast(q) : hypot(dx, dy);
     ex[2][i] = row[11];
   }
   __syncthreads();
@@ -715,7 +715,7 @@ __device__ __forceinline__ void export_block_global(const EvalParams& p, const B
     const double dy = out[(size_t)(j + 1) * JSSP_TRAJ_COLS + 10] - out[(size_t)j * JSSP_TRAJ_COLS + 10];
     const double q = dx * dx + dy * dy;
     out[(size_t)j * JSSP_TRAJ_COLS + 11] = heading_of(dx, dy);
-    out[(size_t)j * JSSP_TRAJ_COLS + 12] = (q > 1e-200 && q < 1e200) ? q * rsqrt(q) : hypot(dx, dy);
+    out[(size_t)j * JSSP_TRAJ_COLS + 12] = (q > 1e-200 && q < 1e200) ? q * rsqrt_fast(q) : hypot(dx, dy);
   }
   __syncthreads();
   if (i == 0 && np >= 2) out[(size_t)(np - 1) * JSSP_TRAJ_COLS + 11] = out[(size_t)(np - 2) * JSSP_TRAJ_COLS + 11];   // yaw[-1] repeated

@@ -66,7 +66,7 @@ __device__ __forceinline__ void evaluate_small_body(const EvalParams& p, unsigne
           const double dx = r[SMALL_ROW] - r[0], dy = r[SMALL_ROW + 1] - r[1];
           const double q = dx * dx + dy * dy;
           double ds, c = 1.0, sn = 0.0;
-          if (q > 1e-200 && q < 1e200) { const double inv = rsqrt(q); ds = q * inv; c = dx * inv; sn = dy * inv; }
+          if (q > 1e-200 && q < 1e200) { const double inv = rsqrt_fast(q); ds = q * inv; c = dx * inv; sn = dy * inv; }
           else { ds = hypot(dx, dy); if (ds > 0.0) { c = dx / ds; sn = dy / ds; } }
           r[2] = dx; r[3] = dy; r[4] = ds; r[5] = c; r[6] = sn;
         }
