@@ -880,10 +880,11 @@ struct jssp_batch {
   // strides (elements per scenario)
   size_t n_knot = 0, n_coef = 0, n_om = 0, n_ompad = 0, n_tt = 0;
   int blocks_thread = 0, blocks_warp = 0, max_blocks = 0;
-  // per-scenario strided device arrays
-  double *d_knot = nullptr, *d_coef = nullptr;
-  double *d_raw_state = nullptr, *d_raw_size = nullptr, *d_raw_prob = nullptr, *d_gt_state = nullptr, *d_gt_size = nullptr;
-  uint8_t *d_raw_valid = nullptr, *d_gt_valid = nullptr;
+  // everything jssp_batch_set_scenario uploads for one scenario (reference line, raw obstacle tables, ground truth, clock
+  // tables) lives in ONE arena slice per scenario, packed in the order of the upload blob: one H2D copy per scenario
+  unsigned char* d_arena = nullptr;
+  size_t arena_cap = 0;             // bytes per scenario
+  // per-scenario strided device arrays (written by the pack kernel / the replay)
   float4 *d_broad = nullptr, *d_narrow = nullptr;
   double *d_obs64 = nullptr, *d_ext64 = nullptr;
   float* d_probf = nullptr;
@@ -899,8 +900,7 @@ struct jssp_batch {
   EvalParams *d_slots = nullptr, *d_slots0 = nullptr;    // live records and their pristine copies (jssp_batch_reset)
   BatchSlot *d_bslots = nullptr, *d_bslots0 = nullptr;
   jssp_cycle_record* d_records = nullptr;
-  double* d_cycle_time = nullptr;
-  int *d_cycle_now = nullptr, *d_cycle_end = nullptr;
+  std::vector<unsigned char> pristine_stale;   // slots whose pristine copy (d_slots0 ...) has not been taken yet
   // FOP baseline in the batch (jssp_batch_set_fop): per-scenario FopParams records instead of EvalParams
   bool fop = false;
   jssp_fop_in fop_grid{};
@@ -964,10 +964,9 @@ int64_t jssp_batch_launch_count(const jssp_batch* b) { return b ? b->launches : 
 int32_t jssp_batch_destroy(jssp_batch* b) {
   if (!b) return JSSP_OK;
   cudaSetDevice(b->device);
-  void* dev[] = {b->d_knot, b->d_coef, b->d_raw_state, b->d_raw_size, b->d_raw_prob, b->d_gt_state, b->d_gt_size, b->d_raw_valid,
-                 b->d_gt_valid, b->d_broad, b->d_narrow, b->d_obs64, b->d_ext64, b->d_probf, b->d_seeds,
+  void* dev[] = {b->d_arena, b->d_broad, b->d_narrow, b->d_obs64, b->d_ext64, b->d_probf, b->d_seeds,
                  b->d_counts, b->d_blk_cost, b->d_blk_idx, b->d_ticket, b->d_best, b->d_best_traj, b->d_slots, b->d_bslots,
-                 b->d_slots0, b->d_bslots0, b->d_records, b->d_cycle_time, b->d_cycle_now, b->d_cycle_end};
+                 b->d_slots0, b->d_bslots0, b->d_records};
   for (void* q : dev) if (q) cudaFree(q);
   for (double* q : b->d_grid) if (q) cudaFree(q);
   if (b->h_stage) cudaFreeHost(b->h_stage);
@@ -1017,15 +1016,13 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   b->blocks_thread = (int)(((size_t)cfg->max_seeds * b->W + BATCH_EVAL_THREADS - 1) / BATCH_EVAL_THREADS);
   b->blocks_warp = (int)(((size_t)cfg->max_seeds * b->W + SMALL_WARPS - 1) / SMALL_WARPS);
   b->max_blocks = std::max(b->blocks_thread, b->blocks_warp);
-  CKC(cudaMalloc(&b->d_knot, S * b->n_knot * sizeof(double)));
-  CKC(cudaMalloc(&b->d_coef, S * b->n_coef * sizeof(double)));
-  CKC(cudaMalloc(&b->d_raw_state, S * b->n_om * b->n_tt * 3 * sizeof(double)));
-  CKC(cudaMalloc(&b->d_raw_valid, S * b->n_om * b->n_tt));
-  CKC(cudaMalloc(&b->d_raw_size, S * b->n_om * 2 * sizeof(double)));
-  CKC(cudaMalloc(&b->d_raw_prob, S * b->n_om * sizeof(double)));
-  CKC(cudaMalloc(&b->d_gt_state, S * b->n_om * b->n_tt * 3 * sizeof(double)));
-  CKC(cudaMalloc(&b->d_gt_valid, S * b->n_om * b->n_tt));
-  CKC(cudaMalloc(&b->d_gt_size, S * b->n_om * 2 * sizeof(double)));
+  {
+    auto a16 = [](size_t n) { return (n + 15) & ~(size_t)15; };
+    const size_t om_tt = b->n_om * b->n_tt;
+    b->arena_cap = a16(b->n_knot * 8) + a16(b->n_coef * 8) + 2 * (a16(om_tt * 24) + a16(b->n_om * 16) + a16(om_tt)) + a16(b->n_om * 8) +
+                   a16((size_t)(b->C + 1) * 8) + 2 * a16((size_t)(b->C + 1) * 4);
+    CKC(cudaMalloc(&b->d_arena, S * b->arena_cap));
+  }
   CKC(cudaMalloc(&b->d_broad, S * b->n_ompad * b->n_tt * sizeof(float4)));
   CKC(cudaMalloc(&b->d_narrow, S * b->n_om * b->n_tt * sizeof(float4)));
   CKC(cudaMalloc(&b->d_obs64, S * b->n_om * b->n_tt * 4 * sizeof(double)));
@@ -1052,12 +1049,10 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   CKC(cudaMalloc(&b->d_slots0, S * sizeof(EvalParams)));
   CKC(cudaMalloc(&b->d_bslots0, S * sizeof(BatchSlot)));
   CKC(cudaMalloc(&b->d_records, S * (size_t)b->C * sizeof(jssp_cycle_record)));
-  CKC(cudaMalloc(&b->d_cycle_time, S * (size_t)(b->C + 1) * sizeof(double)));
-  CKC(cudaMalloc(&b->d_cycle_now, S * (size_t)(b->C + 1) * sizeof(int)));
-  CKC(cudaMalloc(&b->d_cycle_end, S * (size_t)(b->C + 1) * sizeof(int)));
   b->stage_cap = (size_t)32 << 20;
   CKC(cudaMallocHost(&b->h_stage, b->stage_cap));
   b->is_set.assign(S, 0);
+  b->pristine_stale.assign(S, 0);
   b->d_poly.assign(S, nullptr);
   b->poly_cap.assign(S, 0);
   CKC(allow_max_dynamic_smem(evaluate_batch_kernel<0>, optin, &b->max_smem_optin));
@@ -1132,28 +1127,77 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
   const size_t s = (size_t)slot;
   const double ego_l = in->ego_length > 0 ? in->ego_length : b->cfg.ego_length, ego_w = in->ego_width > 0 ? in->ego_width : b->cfg.ego_width;
   const int K = in->K, kpad = (K + 1) & ~1, Tt = in->Tt, OMpad = (OM + 31) & ~31;
-  double* knot = b->d_knot + s * b->n_knot;
-  double* coef = b->d_coef + s * b->n_coef;
-  std::vector<double> soa((size_t)8 * kpad, 0.0);
-  for (int i = 0; i < K - 1; ++i)
-    for (int c = 0; c < 8; ++c) soa[(size_t)c * kpad + i] = in->coef[(size_t)i * 8 + c];
-  CKB(upload_staged(b, knot, in->knot_s, (size_t)K * sizeof(double), st));
-  CKB(upload_staged(b, coef, soa.data(), soa.size() * sizeof(double), st));
+  // one upload blob per scenario: [knots | coefficients (structure of arrays) | obstacle states | sizes | probabilities |
+  // ground-truth states | sizes | clock tables | validity masks], every part 16-byte aligned, assembled in the pinned ring
+  const size_t nc = (size_t)in->n_cycles + 1;
+  auto a16 = [](size_t n) { return (n + 15) & ~(size_t)15; };
+  const bool own_gt = in->gt_state != nullptr && gtO > 0;
+  size_t off = 0;
+  const size_t o_knot = off; off += a16((size_t)kpad * 8);
+  const size_t o_coef = off; off += a16((size_t)8 * kpad * 8);
+  const size_t o_state = off; off += a16((size_t)OM * Tt * 24);
+  const size_t o_size = off; off += a16((size_t)in->O * 16);
+  const size_t o_prob = off; off += a16((size_t)OM * 8);
+  const size_t o_gstate = off; off += own_gt ? a16((size_t)gtO * Tt * 24) : 0;
+  const size_t o_gsize = off; off += own_gt ? a16((size_t)gtO * 16) : 0;
+  const size_t o_ctime = off; off += a16(nc * 8);
+  const size_t o_cnow = off; off += a16(nc * 4);
+  const size_t o_cend = off; off += a16(nc * 4);
+  const size_t o_valid = off; off += a16((size_t)OM * Tt);
+  const size_t o_gvalid = off; off += own_gt ? a16((size_t)gtO * Tt) : 0;
+  const size_t blob = off;
+  if (blob > b->arena_cap) return JSSP_ERR_CAPACITY;
+  std::vector<unsigned char> big;                            // a scenario larger than the ring: pageable copy, synchronised below
+  unsigned char* hb;
+  if (blob > b->stage_cap) { big.resize(blob); hb = big.data(); }
+  else {
+    if (b->stage_off + blob > b->stage_cap) {                // wrap: everything staged so far must have left the ring
+      CKB(cudaStreamSynchronize(st));
+      b->stage_off = 0;
+    }
+    hb = b->h_stage + b->stage_off;
+    b->stage_off += blob;
+  }
+  unsigned char* arena = b->d_arena + s * b->arena_cap;
+  {
+    double* hk = reinterpret_cast<double*>(hb + o_knot);
+    memcpy(hk, in->knot_s, (size_t)K * 8);
+    if (kpad > K) hk[K] = 0.0;
+    double* hc = reinterpret_cast<double*>(hb + o_coef);
+    for (int c8 = 0; c8 < 8; ++c8) {
+      for (int i = 0; i < K - 1; ++i) hc[(size_t)c8 * kpad + i] = in->coef[(size_t)i * 8 + c8];
+      for (int i = K - 1; i < kpad; ++i) hc[(size_t)c8 * kpad + i] = 0.0;
+    }
+    if (OM > 0) {
+      memcpy(hb + o_state, in->state, (size_t)OM * Tt * 24);
+      memcpy(hb + o_size, in->size, (size_t)in->O * 16);
+      memcpy(hb + o_prob, in->prob, (size_t)OM * 8);
+      memcpy(hb + o_valid, in->valid, (size_t)OM * Tt);
+    }
+    if (own_gt) {
+      memcpy(hb + o_gstate, in->gt_state, (size_t)gtO * Tt * 24);
+      memcpy(hb + o_gsize, in->gt_size, (size_t)gtO * 16);
+      memcpy(hb + o_gvalid, in->gt_valid, (size_t)gtO * Tt);
+    }
+    memcpy(hb + o_ctime, in->cycle_time, nc * 8);
+    memcpy(hb + o_cnow, in->cycle_now, nc * 4);
+    memcpy(hb + o_cend, in->cycle_end_step, nc * 4);
+  }
+  CKB(cudaMemcpyAsync(arena, hb, blob, cudaMemcpyHostToDevice, st));
+  if (!big.empty()) CKB(cudaStreamSynchronize(st));
+  double* knot = reinterpret_cast<double*>(arena + o_knot);
+  double* coef = reinterpret_cast<double*>(arena + o_coef);
   const double ox = in->coef[0], oy = in->coef[4];
-  double* raw_state = b->d_raw_state + s * b->n_om * b->n_tt * 3;
-  uint8_t* raw_valid = b->d_raw_valid + s * b->n_om * b->n_tt;
-  double* raw_size = b->d_raw_size + s * b->n_om * 2;
-  double* raw_prob = b->d_raw_prob + s * b->n_om;
+  double* raw_state = reinterpret_cast<double*>(arena + o_state);
+  uint8_t* raw_valid = arena + o_valid;
+  double* raw_size = reinterpret_cast<double*>(arena + o_size);
+  double* raw_prob = reinterpret_cast<double*>(arena + o_prob);
   float4* broad = b->d_broad + s * b->n_ompad * b->n_tt;
   float4* narrow = b->d_narrow + s * b->n_om * b->n_tt;
   double* obs64 = b->d_obs64 + s * b->n_om * b->n_tt * 4;
   double* ext64 = b->d_ext64 + s * b->n_om * 2;
   float* probf = b->d_probf + s * b->n_om;
   if (OM > 0) {
-    CKB(upload_staged(b, raw_state, in->state, (size_t)OM * Tt * 3 * sizeof(double), st));
-    CKB(upload_staged(b, raw_valid, in->valid, (size_t)OM * Tt, st));
-    CKB(upload_staged(b, raw_size, in->size, (size_t)in->O * 2 * sizeof(double), st));
-    CKB(upload_staged(b, raw_prob, in->prob, (size_t)OM * sizeof(double), st));
     const double r_ego = std::sqrt(ego_l * ego_l + ego_w * ego_w) / 2.0;
     const int total = OMpad * Tt;
     pack_obstacles_kernel<<<(total * PACK_LANES + 255) / 256, 256, 0, st>>>(raw_state, raw_valid, raw_size, raw_prob, OM, OMpad, in->M, Tt, ox, oy,
@@ -1165,23 +1209,12 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
   const double *gt_state = raw_state, *gt_size = raw_size;
   const uint8_t* gt_valid = raw_valid;
   if (in->gt_state) {
-    double* gs = b->d_gt_state + s * b->n_om * b->n_tt * 3;
-    uint8_t* gv = b->d_gt_valid + s * b->n_om * b->n_tt;
-    double* gz = b->d_gt_size + s * b->n_om * 2;
-    if (gtO > 0) {
-      CKB(upload_staged(b, gs, in->gt_state, (size_t)gtO * Tt * 3 * sizeof(double), st));
-      CKB(upload_staged(b, gv, in->gt_valid, (size_t)gtO * Tt, st));
-      CKB(upload_staged(b, gz, in->gt_size, (size_t)gtO * 2 * sizeof(double), st));
-    }
-    gt_state = gs; gt_valid = gv; gt_size = gz;
+    gt_state = reinterpret_cast<const double*>(arena + o_gstate); gt_valid = arena + o_gvalid;
+    gt_size = reinterpret_cast<const double*>(arena + o_gsize);
   }
-  const size_t nc = (size_t)in->n_cycles + 1;
-  double* ctime = b->d_cycle_time + s * (b->C + 1);
-  int* cnow = b->d_cycle_now + s * (b->C + 1);
-  int* cend = b->d_cycle_end + s * (b->C + 1);
-  CKB(upload_staged(b, ctime, in->cycle_time, nc * sizeof(double), st));
-  CKB(upload_staged(b, cnow, in->cycle_now, nc * sizeof(int), st));
-  CKB(upload_staged(b, cend, in->cycle_end_step, nc * sizeof(int), st));
+  double* ctime = reinterpret_cast<double*>(arena + o_ctime);
+  int* cnow = reinterpret_cast<int*>(arena + o_cnow);
+  int* cend = reinterpret_cast<int*>(arena + o_cend);
 
   jssp_config c = b->cfg;
   c.ego_length = ego_l; c.ego_width = ego_w;
@@ -1247,16 +1280,31 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
     for (int w = 0; w < b->W; ++w) fp.targets[w] = tg[w];
     fp.dt = c.delta_t; fp.max_accel = g.max_accel; fp.max_jerk = g.max_jerk; fp.t_min = g.min_t; fp.t_max = g.max_t;
     CKB(upload_staged(b, b->d_fslots + s, &fp, sizeof(fp), st));
-    CKB(upload_staged(b, b->d_fslots0 + s, &fp, sizeof(fp), st));
   }
   CKB(upload_staged(b, b->d_slots + s, &p, sizeof(p), st));
   CKB(upload_staged(b, b->d_bslots + s, &q, sizeof(q), st));
-  CKB(upload_staged(b, b->d_slots0 + s, &p, sizeof(p), st));
-  CKB(upload_staged(b, b->d_bslots0 + s, &q, sizeof(q), st));
-  CKB(cudaMemsetAsync(b->d_ticket + s, 0, sizeof(unsigned int), st));
+  b->pristine_stale[s] = 1;     // the pristine copies (jssp_batch_reset) and the ticket are taken care of before the next run / reset
   // everything went through the staging ring: soa, p, q and the caller's arrays may be released, the copies are in flight
   b->max_K = std::max(b->max_K, K); b->max_kpad = std::max(b->max_kpad, kpad); b->max_OMpad = std::max(b->max_OMpad, OMpad);
   b->is_set[s] = 1;
+  return JSSP_OK;
+}
+
+// Freshly loaded slots: copy their records to the pristine arrays and clear their tickets, one device-to-device copy per
+// contiguous run of slots (a whole batch loaded in order = one copy of each array).
+static int32_t snapshot_fresh_slots(jssp_batch* b, cudaStream_t st) {
+  int s = 0;
+  while (s < b->S) {
+    if (!b->pristine_stale[s]) { ++s; continue; }
+    int e = s;
+    while (e < b->S && b->pristine_stale[e]) b->pristine_stale[e++] = 0;
+    const size_t n = (size_t)(e - s);
+    CKB(cudaMemcpyAsync(b->d_slots0 + s, b->d_slots + s, n * sizeof(EvalParams), cudaMemcpyDeviceToDevice, st));
+    CKB(cudaMemcpyAsync(b->d_bslots0 + s, b->d_bslots + s, n * sizeof(BatchSlot), cudaMemcpyDeviceToDevice, st));
+    if (b->fop) CKB(cudaMemcpyAsync(b->d_fslots0 + s, b->d_fslots + s, n * sizeof(FopParams), cudaMemcpyDeviceToDevice, st));
+    CKB(cudaMemsetAsync(b->d_ticket + s, 0, n * sizeof(unsigned int), st));
+    s = e;
+  }
   return JSSP_OK;
 }
 
@@ -1266,6 +1314,7 @@ int32_t jssp_batch_reset(jssp_batch* b, int32_t n_scenarios, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   CKB(cudaSetDevice(b->device));
   const size_t n = (size_t)n_scenarios;
+  { const int32_t rc = snapshot_fresh_slots(b, st); if (rc != JSSP_OK) return rc; }
   CKB(cudaMemcpyAsync(b->d_slots, b->d_slots0, n * sizeof(EvalParams), cudaMemcpyDeviceToDevice, st));
   CKB(cudaMemcpyAsync(b->d_bslots, b->d_bslots0, n * sizeof(BatchSlot), cudaMemcpyDeviceToDevice, st));
   if (b->fop) CKB(cudaMemcpyAsync(b->d_fslots, b->d_fslots0, n * sizeof(FopParams), cudaMemcpyDeviceToDevice, st));
@@ -1278,6 +1327,7 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   for (int s = 0; s < n_scenarios; ++s) if (!b->is_set[s]) return JSSP_ERR_NOT_READY;
   cudaStream_t st = (cudaStream_t)stream;
   CKB(cudaSetDevice(b->device));
+  { const int32_t rc = snapshot_fresh_slots(b, st); if (rc != JSSP_OK) return rc; }
   if (b->fop) {                       // FOP baseline: no seed enumeration, evaluation + (selection, export, hand-off) per step
     for (int c = 0; c < n_cycles; ++c) {
       evaluate_fop_batch_kernel<<<dim3(b->fop_blocks, n_scenarios), EVAL_THREADS, b->fop_smem, st>>>(b->d_fslots);
