@@ -179,6 +179,38 @@ def test_packed_scenario_cache_round_trip(tmp_path, scenario_fixture):
         assert int(p.valid[o, 0].sum()) == len([k for k in keys if round(float(k) / p.dt) < p.state.shape[2]])
 
 
+def test_polyline_table_reproduces_from_state(scenario_fixture):
+    """The table the kinematics mode uploads (pack_scenario(..., kinematics=True)) carries exactly the numbers
+    FrenetState.from_state derives from the re-discretised reference line: the device formula (nearest row, arc + tangential
+    offset, left-normal offset, heading-error split) evaluated on the table equals from_state bit for bit; the packed C view is
+    built once and marks the mode."""
+    import math
+    from dlii_jssp_b200 import batch as B
+    from dlii_jssp_b200.frenet import FrenetState, State
+    from dlii_jssp_b200.geometry import CubicSpline2D
+    sc = scenario_fixture
+    p = B.pack_scenario(sc, kinematics=True, max_cycles=5)
+    spline = CubicSpline2D(sc.route_xy[:, 0], sc.route_xy[:, 1])
+    ref = spline.sample(np.arange(0, spline.s_list[-1], 0.1))
+    assert p.polyline.shape == (len(ref), 6)
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        i = int(rng.integers(0, len(ref)))
+        st = State(0.0, ref[i, 0] + rng.normal(0, 0.7), ref[i, 1] + rng.normal(0, 0.7), ref[i, 2] + rng.normal(0, 0.2), rng.uniform(0, 12), rng.normal(0, 1))
+        want = FrenetState().from_state(st, ref).as_tuple()
+        t = p.polyline
+        k = int(np.argmin((t[:, 0] - st.x) ** 2 + (t[:, 1] - st.y) ** 2))
+        ex, ey, dyaw = st.x - t[k, 0], st.y - t[k, 1], st.yaw - t[k, 2]
+        got = (t[k, 3] + (ex * t[k, 4] + ey * t[k, 5]), st.v * math.cos(dyaw), st.a * math.cos(dyaw),
+               -ex * t[k, 5] + ey * t[k, 4], st.v * math.sin(dyaw), st.a * math.sin(dyaw))
+        assert got == want
+    v0, v1 = p.c_view(False), p.c_view(True)
+    assert v0 is p.c_view(False) and v1 is p.c_view(True) and v0 is not v1
+    assert (v0.ego_update_mode, v1.ego_update_mode, v1.n_polyline) == (0, 1, len(ref)) and v1.pp_wheel_base > 0
+    with pytest.raises(ValueError):
+        B.pack_scenario(sc, max_cycles=5).c_view(True)
+
+
 def test_new_entry_points_validate_arguments_without_a_gpu():
     """Argument checks of the batched-replay / FOP / projection entry points run before any device work; without a GPU the
     constructors report JSSP_ERR_NO_DEVICE instead of falling back."""
