@@ -248,17 +248,36 @@ cudaError_t allow_max_dynamic_smem(F* func, int optin, int* budget) {
 // launch of the seed enumeration: n_scenarios clusters of `csize` CTAs
 template <bool kBatch>
 cudaError_t launch_seed_enum(const SeedGrids& g, SeedState ss, const EvalParams* slots, const SeedWork& wk, int n_scenarios, int csize,
-                             int threads, size_t smem, cudaStream_t st) {
+                             int threads, size_t smem, cudaStream_t st, bool pdl = false) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_scenarios * csize), 1, 1);
   cfg.blockDim = dim3((unsigned)threads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, seed_enum_kernel<kBatch>, g, ss, slots, wk);
+}
+
+// launch of a lock-step kernel of the batched replay: chained to its predecessor by programmatic dependent launch (the
+// kernels call pdl_wait() before they touch anything the predecessor writes), so that block scheduling and the launch
+// latency overlap the predecessor's tail
+template <class... KArgs, class... Args>
+cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, int threads, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3((unsigned)threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 // shared-memory list capacities of the seed enumeration kernel for the handle's sampling grids
@@ -621,11 +640,8 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   if (!h || !in || !out) return JSSP_ERR_INVALID_ARG;
   if (h->K < 2 || !h->obs_set) return JSSP_ERR_NOT_READY;
   const bool ext = in->seeds_dev != nullptr;
-  if (!ext && (in->flags & JSSP_FLAG_ENUMERATE)) {
-    const int rc0 = jssp_enumerate_seeds(h, in->s0, in->v0, in->a0, stream, nullptr, nullptr);
-    if (rc0 != JSSP_OK) return rc0;
-  }
-  if (!ext && !h->seeds_ready) return JSSP_ERR_NOT_READY;
+  const bool enumerate = !ext && (in->flags & JSSP_FLAG_ENUMERATE);
+  if (!ext && !enumerate && !h->seeds_ready) return JSSP_ERR_NOT_READY;
   if (ext && (in->n_seeds < 0 || in->n_seeds > h->cfg.max_seeds)) return JSSP_ERR_CAPACITY;
   const int W = in->n_widths > 0 ? in->n_widths : h->cfg.num_width;
   if (W < 1 || W > JSSP_MAX_WIDTHS) return JSSP_ERR_INVALID_ARG;
@@ -634,6 +650,10 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   int rc = join_tables(h, st);
   if (rc == JSSP_OK) rc = pack_if_dirty(h, st);
   if (rc != JSSP_OK) return rc;
+  if (enumerate) {             // last, so that the evaluation kernel directly follows the seed enumeration in the stream
+    const int rc0 = jssp_enumerate_seeds(h, in->s0, in->v0, in->a0, stream, nullptr, nullptr);
+    if (rc0 != JSSP_OK) return rc0;
+  }
 
   EvalParams p{};
   const jssp_config& c = h->cfg;
@@ -706,7 +726,12 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
                      : (group ? (int)((seeds_max + spb - 1) / spb) : (int)((n_max + EVAL_THREADS - 1) / EVAL_THREADS));
   if (blocks < 1) blocks = 1;
   if (blocks > h->max_blocks) return JSSP_ERR_CAPACITY;
-  if (small) { p.smem_obs = 0; p.win_rows = 0; p.list_cap = 0; evaluate_small_kernel<<<blocks, SMALL_WARPS * 32, small_bytes, st>>>(p); }
+  if (small) {
+    p.smem_obs = 0; p.win_rows = 0; p.list_cap = 0;
+    // one-call plan cycle: the evaluation is chained to the seed enumeration just enqueued (programmatic dependent launch)
+    const bool chained = !ext && (in->flags & JSSP_FLAG_ENUMERATE) && getenv("JSSP_B200_TUNE_NO_PDL") == nullptr;
+    CK(launch_chained(evaluate_small_kernel, dim3(blocks), SMALL_WARPS * 32, small_bytes, st, chained, p));
+  }
   else if (group && mode == 2) evaluate_group_kernel<2><<<blocks, EVAL_THREADS, L.total, st>>>(p);
   else if (group && mode == 1) evaluate_group_kernel<1><<<blocks, EVAL_THREADS, L.total, st>>>(p);
   else if (group) evaluate_group_kernel<0><<<blocks, EVAL_THREADS, L.total, st>>>(p);
@@ -1328,10 +1353,11 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   cudaStream_t st = (cudaStream_t)stream;
   CKB(cudaSetDevice(b->device));
   { const int32_t rc = snapshot_fresh_slots(b, st); if (rc != JSSP_OK) return rc; }
+  const bool pdl = getenv("JSSP_B200_TUNE_NO_PDL") == nullptr;     // tools/ only: plain stream order instead of chained launches
   if (b->fop) {                       // FOP baseline: no seed enumeration, evaluation + (selection, export, hand-off) per step
     for (int c = 0; c < n_cycles; ++c) {
-      evaluate_fop_batch_kernel<<<dim3(b->fop_blocks, n_scenarios), EVAL_THREADS, b->fop_smem, st>>>(b->d_fslots);
-      fop_select_export_batch_kernel<<<n_scenarios, EVAL_THREADS, b->fop_smem, st>>>(b->d_fslots, b->fop_blocks);
+      CKB(launch_chained(evaluate_fop_batch_kernel, dim3(b->fop_blocks, n_scenarios), EVAL_THREADS, b->fop_smem, st, pdl, (const FopParams*)b->d_fslots));
+      CKB(launch_chained(fop_select_export_batch_kernel, dim3(n_scenarios), EVAL_THREADS, b->fop_smem, st, pdl, (const FopParams*)b->d_fslots, b->fop_blocks));
       b->launches += 2;
     }
     CKB(cudaGetLastError());
@@ -1364,12 +1390,13 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   if (const char* e = getenv("JSSP_B200_TUNE_SEED_CLUSTER")) seed_cluster = std::max(1, std::min(SEED_MAX_CLUSTER, atoi(e)));    // tools/ only
   if (const char* e = getenv("JSSP_B200_TUNE_SEED_THREADS")) seed_threads = atoi(e) == 512 ? 512 : SEED_THREADS;
   for (int c = 0; c < n_cycles; ++c) {
-    CKB(launch_seed_enum<true>(b->grids, SeedState{0, 0, 0}, b->d_slots, b->seed_work, n_scenarios, seed_cluster, seed_threads, b->seed_smem, st));
-    if (small) evaluate_small_batch_kernel<<<dim3(std::min(b->blocks_warp, 128), n_scenarios), SMALL_WARPS * 32, small_bytes, st>>>(b->d_slots);
-    else if (group && mode == 1) evaluate_group_batch_kernel<1><<<dim3(blocks_group, n_scenarios), bthreads, L.total, st>>>(b->d_slots);
-    else if (group) evaluate_group_batch_kernel<0><<<dim3(blocks_group, n_scenarios), bthreads, L.total, st>>>(b->d_slots);
-    else if (mode == 1) evaluate_batch_kernel<1><<<dim3(blocks_thread, n_scenarios), bthreads, L.total, st>>>(b->d_slots);
-    else evaluate_batch_kernel<0><<<dim3(blocks_thread, n_scenarios), bthreads, L.total, st>>>(b->d_slots);
+    CKB(launch_seed_enum<true>(b->grids, SeedState{0, 0, 0}, b->d_slots, b->seed_work, n_scenarios, seed_cluster, seed_threads, b->seed_smem, st, pdl));
+    const EvalParams* slots = b->d_slots;
+    if (small) CKB(launch_chained(evaluate_small_batch_kernel, dim3(std::min(b->blocks_warp, 128), n_scenarios), SMALL_WARPS * 32, small_bytes, st, pdl, slots));
+    else if (group && mode == 1) CKB(launch_chained(evaluate_group_batch_kernel<1>, dim3(blocks_group, n_scenarios), bthreads, L.total, st, pdl, slots));
+    else if (group) CKB(launch_chained(evaluate_group_batch_kernel<0>, dim3(blocks_group, n_scenarios), bthreads, L.total, st, pdl, slots));
+    else if (mode == 1) CKB(launch_chained(evaluate_batch_kernel<1>, dim3(blocks_thread, n_scenarios), bthreads, L.total, st, pdl, slots));
+    else CKB(launch_chained(evaluate_batch_kernel<0>, dim3(blocks_thread, n_scenarios), bthreads, L.total, st, pdl, slots));
     b->launches += 2;
   }
   CKB(cudaGetLastError());

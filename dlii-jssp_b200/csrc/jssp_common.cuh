@@ -41,6 +41,13 @@ __device__ __forceinline__ void phase_stamp(unsigned long long* ts, int slot) {
 #define PHASE(p, k)
 #endif
 
+// Programmatic dependent launch (the lock-step kernels of the batched replay are chained with it): a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may be scheduled while its predecessor in the stream drains;
+// pdl_wait() returns once the predecessor has completed and its writes are visible (a no-op for ordinary launches),
+// pdl_launch_dependents() tells the scheduler that the successor may start being placed.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 struct BestRecord {
   unsigned long long key;   // orderable_bits(cost)
   long long idx;            // candidate index (+ offset for candidate-split runs), -1 = none

@@ -1100,6 +1100,7 @@ __global__ void __launch_bounds__(BATCH_EVAL_THREADS, BATCH_MIN_BLOCKS) evaluate
   __shared__ int red_idx[EVAL_THREADS / 32];
   __shared__ bool is_last;
   __shared__ int sm_npts;
+  pdl_launch_dependents(); pdl_wait();                 // seeds and slot records come from the kernels ahead in the stream
   if (!slot_live(slots, blockIdx.y)) return;           // block-uniform; stable until the scenario's last block hands off
   load_slot(&sp, slots + blockIdx.y);
   evaluate_body<kMode>(sp, smem, red_cost, red_idx, &is_last, &sm_npts);
@@ -1113,6 +1114,7 @@ __global__ void __launch_bounds__(BATCH_EVAL_THREADS, BATCH_MIN_BLOCKS) evaluate
   __shared__ int red_idx[EVAL_THREADS / 32];
   __shared__ bool is_last;
   __shared__ int sm_npts;
+  pdl_launch_dependents(); pdl_wait();
   if (!slot_live(slots, blockIdx.y)) return;
   load_slot(&sp, slots + blockIdx.y);
   evaluate_group_body<kMode>(sp, smem, red_cost, red_idx, &is_last, &sm_npts);

@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) evaluate_small_kernel(const 
   __shared__ int red_idx[SMALL_WARPS];
   __shared__ bool is_last;
   __shared__ int sm_npts;
+  pdl_wait();          // one-call plan cycles chain this kernel to the seed enumeration (no-op for ordinary launches)
   evaluate_small_body(p, smem, red_cost, red_idx, &is_last, &sm_npts);
 }
 
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) evaluate_small_batch_kernel(
   __shared__ int red_idx[SMALL_WARPS];
   __shared__ bool is_last;
   __shared__ int sm_npts;
+  pdl_launch_dependents(); pdl_wait();
   if (!slot_live(slots, blockIdx.y)) return;
   load_slot(&sp, slots + blockIdx.y);
   evaluate_small_body(sp, smem, red_cost, red_idx, &is_last, &sm_npts);

@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_fop_ba
   __shared__ __align__(16) FopParams sfp;
   __shared__ double red_cost[EVAL_THREADS / 32];
   __shared__ int red_idx[EVAL_THREADS / 32];
+  pdl_launch_dependents(); pdl_wait();
   if (!fslots[blockIdx.y].base.batch->live) return;
   load_fop_slot(&sfp, fslots + blockIdx.y);
   evaluate_fop_body(sfp, smem, red_cost, red_idx);
@@ -283,6 +284,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) fop_select_export_batch_kernel(c
   __shared__ int red_idx[EVAL_THREADS / 32];
   __shared__ int sm_best, sm_npts;
   __shared__ double ex[6][EXPORT_MAX_P];
+  pdl_launch_dependents(); pdl_wait();
   if (!fslots[blockIdx.x].base.batch->live) return;
   load_fop_slot(&sfp, fslots + blockIdx.x);
   const int best = fop_select_export_body(sfp, n_blocks, smem, red_cost, red_idx, &sm_best, &sm_npts, ex);

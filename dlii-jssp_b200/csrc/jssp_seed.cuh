@@ -155,6 +155,8 @@ __global__ void __launch_bounds__(SEED_THREADS) seed_enum_kernel(SeedGrids g, Se
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
   const int sc = blockIdx.x / csize;
+  pdl_launch_dependents();                                      // the evaluation kernel behind may start being placed
+  if (kBatch) pdl_wait();                                       // the slot records are written by the previous cycle's hand-off
   if (kBatch && !slot_live(slots, sc)) return;                  // cluster-uniform
   const SeedState st = kBatch ? seed_state_of(slots, sc) : st1;
   unsigned char* seed_smem = csize > 1 ? cluster.map_shared_rank(seed_smem_local, 0) : seed_smem_local;
