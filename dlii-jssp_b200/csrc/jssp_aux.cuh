@@ -200,33 +200,57 @@ __global__ void imm_update_kernel(jssp_imm_params prm, double* __restrict__ mean
   }
 }
 
-// one thread per (obstacle, mode): walk the mode's lane polyline at constant speed
+// Constant-speed roll-out of every (obstacle, mode) along its lane polyline, two kernels:
+//   lane_tables_kernel    one block per lane: segment lengths and headings in parallel, then the running arc length
+//                         (sequential additions, the order numpy.cumsum uses) -> cum [L][Pn], yaw [L][Pn-1]
+//   predict_modes_kernel  one thread per (obstacle-mode, time step): binary search of the segment with cum[i] < s <= cum[i+1]
+//                         (numpy.searchsorted(cum, s, "left") - 1, clipped), linear interpolation; stores coalesced along t
+__global__ void lane_tables_kernel(const double* __restrict__ lanes, int Pn, double* __restrict__ cum, double* __restrict__ len,
+                                   double* __restrict__ yaw) {
+  const double* pl = lanes + (size_t)blockIdx.x * Pn * 2;
+  double* c = cum + (size_t)blockIdx.x * Pn;
+  double* ln = len + (size_t)blockIdx.x * (Pn - 1);
+  double* yw = yaw + (size_t)blockIdx.x * (Pn - 1);
+  for (int i = threadIdx.x; i < Pn - 1; i += blockDim.x) {
+    const double dx = pl[(i + 1) * 2] - pl[i * 2], dy = pl[(i + 1) * 2 + 1] - pl[i * 2 + 1];
+    ln[i] = hypot(dx, dy);
+    yw[i] = atan2(dy, dx);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double acc = 0.0;
+    c[0] = 0.0;
+    for (int i = 0; i < Pn - 1; ++i) { acc = acc + ln[i]; c[i + 1] = acc; }
+  }
+}
+
 __global__ void predict_modes_kernel(const double* __restrict__ lanes, int L, int Pn, const int* __restrict__ lane_of,
                                      const double* __restrict__ s_start, const double* __restrict__ speed, double dt, int O,
-                                     int M, int Tt, double* __restrict__ state, uint8_t* __restrict__ valid) {
-  const int om = blockIdx.x * blockDim.x + threadIdx.x;
-  if (om >= O * M) return;
+                                     int M, int Tt, const double* __restrict__ cum, const double* __restrict__ len,
+                                     const double* __restrict__ yaw, double* __restrict__ state, uint8_t* __restrict__ valid) {
+  const int om = blockIdx.x, t = blockIdx.y * blockDim.x + threadIdx.x;      // grid (O * M, ceil(Tt / blockDim.x))
+  if (t >= Tt) return;
+  const size_t gid = (size_t)om * Tt + t;
   const int lane = lane_of[om];
-  double* st = state + (size_t)om * Tt * 3;
-  uint8_t* va = valid + (size_t)om * Tt;
-  if (lane < 0 || lane >= L) { for (int t = 0; t < Tt; ++t) { va[t] = 0; st[t * 3] = st[t * 3 + 1] = st[t * 3 + 2] = 0.0; } return; }
+  double* st = state + (size_t)gid * 3;
+  if (lane < 0 || lane >= L) { valid[gid] = 0; st[0] = st[1] = st[2] = 0.0; return; }
   const double* pl = lanes + (size_t)lane * Pn * 2;
-  const double v = speed[om / M];
-  int seg = 0;
-  double acc = 0.0;   // arc length at the start of segment `seg`
-  double seg_len = hypot(pl[2] - pl[0], pl[3] - pl[1]);
-  for (int t = 0; t < Tt; ++t) {
-    const double s = s_start[om] + v * ((double)t * dt);
-    while (seg < Pn - 2 && s > acc + seg_len) {
-      acc = acc + seg_len; ++seg;
-      seg_len = hypot(pl[(seg + 1) * 2] - pl[seg * 2], pl[(seg + 1) * 2 + 1] - pl[seg * 2 + 1]);
+  const double* c = cum + (size_t)lane * Pn;
+  const double s = s_start[om] + speed[om / M] * ((double)t * dt);
+  int lo = 0, hi = Pn - 1;            // first index with c[idx] >= s (Pn when none), by bisection over c[1 .. Pn-1]
+  if (!(c[0] >= s)) {
+    lo = 1; hi = Pn;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (c[mid] >= s) hi = mid; else lo = mid + 1;
     }
-    const bool ok = s >= 0.0 && s <= acc + seg_len && seg_len > 0.0;
-    const double dx = pl[(seg + 1) * 2] - pl[seg * 2], dy = pl[(seg + 1) * 2 + 1] - pl[seg * 2 + 1];
-    const double u = seg_len > 0.0 ? (s - acc) / seg_len : 0.0;
-    st[t * 3] = pl[seg * 2] + u * dx; st[t * 3 + 1] = pl[seg * 2 + 1] + u * dy; st[t * 3 + 2] = atan2(dy, dx);
-    va[t] = ok ? 1 : 0;
-  }
+  } else lo = 0;
+  const int seg = min(max(lo - 1, 0), Pn - 2);
+  const double seg_len = len[(size_t)lane * (Pn - 1) + seg];
+  const double dx = pl[(seg + 1) * 2] - pl[seg * 2], dy = pl[(seg + 1) * 2 + 1] - pl[seg * 2 + 1];
+  const double u = seg_len > 0.0 ? (s - c[seg]) / seg_len : 0.0;
+  st[0] = pl[seg * 2] + u * dx; st[1] = pl[seg * 2 + 1] + u * dy; st[2] = yaw[(size_t)lane * (Pn - 1) + seg];
+  valid[gid] = (s >= 0.0 && s <= c[Pn - 1] && seg_len > 0.0) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------------------------

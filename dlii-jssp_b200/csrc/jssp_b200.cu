@@ -51,6 +51,8 @@ struct jssp_handle {
   float2* d_sint = nullptr;       // reachable arc-length interval per obstacle state
   float* d_probf = nullptr;
   double* d_knot_xy = nullptr;
+  double* d_lane_scratch = nullptr;   // jssp_predict_modes: per-lane arc-length / heading tables
+  size_t lane_scratch_cap = 0;        // doubles
   double cull_reach = 0, cull_ds = 0;
   bool cull_ok = false;
   int O = 0, M = 0, Tt = 0, n_dict = 0;
@@ -455,7 +457,7 @@ int32_t jssp_destroy(jssp_handle* h) {
   if (!h) return JSSP_OK;
   cudaSetDevice(h->device);
   void* dev[] = {h->d_time, h->d_j1, h->d_t1, h->d_t2, h->d_j3, h->d_t3, h->d_t4, h->d_jneg, h->d_jpos, h->d_ts, h->d_seeds,
-                 h->d_knot, h->d_coef, h->d_raw, h->d_broad, h->d_narrow, h->d_obs64, h->d_ext64, h->d_sint, h->d_probf, h->d_knot_xy, h->d_blk_cost, h->d_blk_idx, h->d_ticket, h->d_counts};
+                 h->d_knot, h->d_coef, h->d_raw, h->d_broad, h->d_narrow, h->d_obs64, h->d_ext64, h->d_sint, h->d_probf, h->d_knot_xy, h->d_lane_scratch, h->d_blk_cost, h->d_blk_idx, h->d_ticket, h->d_counts};
   for (void* p : dev) if (p) cudaFree(p);
   if (h->h_result) cudaFreeHost(h->h_result);
   if (h->h_counts) cudaFreeHost(h->h_counts);
@@ -884,9 +886,22 @@ int32_t jssp_predict_modes(jssp_handle* h, const double* lanes_dev, int32_t L, i
     return JSSP_ERR_INVALID_ARG;
   if (O == 0) return JSSP_OK;
   CK(cudaSetDevice(h->device));
-  predict_modes_kernel<<<(O * M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(lanes_dev, L, P, lane_of_dev, s_start_dev, speed_dev, dt,
-                                                                               O, M, Tt, state_dev, valid_dev);
-  h->launches++;
+  cudaStream_t st = (cudaStream_t)stream;
+  // lane tables: cum [L][P], len [L][P-1], yaw [L][P-1] in a handle-owned scratch buffer that only ever grows
+  const size_t n_cum = (size_t)L * P, n_seg = (size_t)L * (P - 1);
+  if (h->lane_scratch_cap < n_cum + 2 * n_seg) {
+    if (h->d_lane_scratch) { CK(cudaFree(h->d_lane_scratch)); h->d_lane_scratch = nullptr; h->lane_scratch_cap = 0; }
+    CK(cudaMalloc(&h->d_lane_scratch, (n_cum + 2 * n_seg) * sizeof(double)));
+    h->lane_scratch_cap = n_cum + 2 * n_seg;
+  }
+  double *cum = h->d_lane_scratch, *len = cum + n_cum, *yaw = len + n_seg;
+  lane_tables_kernel<<<L, 128, 0, st>>>(lanes_dev, P, cum, len, yaw);
+  const int pt = Tt >= 192 ? 256 : (Tt >= 96 ? 128 : 64);
+  if ((Tt + pt - 1) / pt > 65535) return JSSP_ERR_CAPACITY;
+  predict_modes_kernel<<<dim3((unsigned)(O * M), (unsigned)((Tt + pt - 1) / pt)), pt, 0, st>>>(lanes_dev, L, P, lane_of_dev, s_start_dev, speed_dev, dt, O, M, Tt,
+                                                                        cum, len, yaw, state_dev, valid_dev);
+  h->launches += 2;
+  CK(cudaGetLastError());
   CK(cudaGetLastError());
   return JSSP_OK;
 }
