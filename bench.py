@@ -284,9 +284,10 @@ def run_ours(args):
         per = len(seeds_all) // world
         return D.allgather_argmin(eng.best_record(), index_map=lambda r, i: D.global_candidate_index(i, r * per, per, len(seeds_all)))
 
-    def timed(steps, warmup, export, with_reduce=False):
+    def timed(steps, warmup, export, with_reduce=False, select_only=False):
         for _ in range(warmup):
-            eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=seeds_dev, targets=cyc.targets, sync=False, export=export)
+            eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=seeds_dev, targets=cyc.targets, sync=False, export=export,
+                         select_only=select_only)
             if with_reduce:
                 reduce_best()
         torch.cuda.synchronize()
@@ -298,7 +299,8 @@ def run_ours(args):
         for e0, e1 in evs:
             flush.fill_(1)
             e0.record()
-            eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=seeds_dev, targets=cyc.targets, sync=False, export=export)
+            eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=seeds_dev, targets=cyc.targets, sync=False, export=export,
+                         select_only=select_only)
             if with_reduce:
                 reduce_best()
             e1.record()
@@ -318,6 +320,19 @@ def run_ours(args):
     units_all = (cyc.n_candidates if split else n_local * world) * P * args.steps
     value = units_all / (total_ms * 1e-3)
     res = eng.fetch()
+
+    # (1b) the same step without per-candidate outputs (select-only: a candidate's walk stops at its first veto, like the
+    #      reference's filter chain) - reported next to the headline, never instead of it
+    so_ms, _ = timed(min(args.steps, 20), 3, export=True, with_reduce=split, select_only=True)
+    so_total = sum(so_ms)
+    if world > 1:
+        t = torch.tensor([so_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        so_total = float(t.item())
+    res_so = eng.fetch()
+    select_only = {"value": (cyc.n_candidates if split else n_local * world) * P * len(so_ms) / (so_total * 1e-3), "unit": UNIT,
+                   "ms_per_step": so_total / len(so_ms), "same_selection": bool(split or res_so.best_idx == res.best_idx),
+                   "note": "no masks / costs written: vetoed candidates stop early; selection and exported trajectory unchanged"}
 
     # (2) dominant kernel alone (no export) for the roofline
     k_ms, _ = timed(args.steps, 3, export=False)
@@ -366,7 +381,7 @@ def run_ours(args):
                 "dtype": "f64 geometry + f32 collision", "data": "synthetic", "config": workload_config(args.workload, cyc, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "p50_cycle_ms": 1e3 * statistics.median(lat)},
-                "gpu_launches": int(launches), "clocks": sampler.summary(),
+                "gpu_launches": int(launches), "clocks": sampler.summary(), "select_only": select_only,
                 "roofline": {"bound": "fp32", "kernel": "evaluate_group_kernel", "achieved": achieved, "peak": peak32.value, "unit": "TFLOP/s",
                              "frac": achieved / peak32.value if peak32.value else None, "traffic": ncu_evidence().get("dram_traffic_bytes"),
                              "executed": ncu_evidence(k_avg_s),

@@ -8,6 +8,7 @@ namespace jssp {
 // K3: export of the selected trajectory (float64 rows) and optional fp32 state dump of every candidate
 // ------------------------------------------------------------------------------------------------------------------
 struct DumpSink {
+  __device__ __forceinline__ bool vetoed() const { return false; }
   float* out;   // [P][8] of this candidate: s, s_d, s_dd, d, x, y, yaw, c
   const double* lat;
   double pyaw, pds;

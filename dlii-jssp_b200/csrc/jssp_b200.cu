@@ -699,6 +699,7 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   }
   p.smem_obs = mode;
   p.feasible = out->feasible_dev; p.collision = out->collision_dev; p.cost = out->cost_dev;
+  p.select_only = (!p.feasible && !p.collision && !p.cost) ? 1 : 0;    // nobody reads per-candidate results: walks may stop at the first veto
   p.blk_cost = h->d_blk_cost; p.blk_idx = h->d_blk_idx; p.ticket = h->d_ticket; p.best = h->d_best;
   p.best_traj = (in->flags & JSSP_FLAG_NO_EXPORT) ? nullptr : h->d_best_traj;
 #ifdef JSSP_PROFILE_PHASES
@@ -832,6 +833,7 @@ int32_t jssp_fop_evaluate(jssp_handle* h, const jssp_fop_in* in, void* stream, j
   p.OM = h->O * h->M; p.OMpad = (p.OM + 31) & ~31; p.Tt = h->Tt;
   p.win_rows = 0; p.smem_obs = 0; p.sint = h->d_sint; p.probf = h->d_probf; p.list_cap = 0;
   p.feasible = out->feasible_dev; p.collision = out->collision_dev; p.cost = out->cost_dev;
+  p.select_only = (!p.feasible && !p.collision && !p.cost) ? 1 : 0;    // nobody reads per-candidate results: walks may stop at the first veto
   p.blk_cost = h->d_blk_cost; p.blk_idx = h->d_blk_idx; p.ticket = h->d_ticket; p.best = h->d_best;
   p.best_traj = (in->flags & JSSP_FLAG_NO_EXPORT) ? nullptr : h->d_best_traj;
   fp.num_t = NT; fp.num_speed = NV;
@@ -1274,6 +1276,7 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
   p.win_rows = OM > 0 ? rows : 0;
   p.smem_obs = 1; p.sint = nullptr; p.probf = probf; p.list_cap = 0;
   p.feasible = nullptr; p.collision = nullptr; p.cost = nullptr;
+  p.select_only = getenv("JSSP_B200_TUNE_FULL_WALK") ? 0 : 1;    // the replay only needs the selected trajectory (tools/: A/B override)
   p.blk_cost = b->d_blk_cost + s * b->max_blocks; p.blk_idx = b->d_blk_idx + s * b->max_blocks;
   p.ticket = b->d_ticket + s; p.best = b->d_best + s;
   p.best_traj = b->d_best_traj + s * (size_t)b->P * JSSP_TRAJ_COLS;

@@ -35,6 +35,9 @@ struct EvalParams {
   const float2* sint;             // [Tt][OMpad] reachable arc-length interval of every obstacle state (block-level culling)
   const float* probf;             // [OM]
   int list_cap;                   // entries of the per-block compacted obstacle lists (mode 2)
+  int select_only;                // no per-candidate outputs are wanted: a candidate's walk may stop at its first veto (the
+                                  // reference filters the same way: check_constraints_curvature -> check_collisions -> cost on
+                                  // the survivors only, has_collision returns at the first hit; jerk_space_sampling_planner.py:311-319)
   // outputs
   uint8_t* feasible;
   uint8_t* collision;
@@ -136,6 +139,7 @@ __device__ __forceinline__ void walk_core(const BlockTables& tb, Lon& lon, const
       if (q > 1e-200 && q < 1e200) { const double inv = rsqrt_fast(q); ds = q * inv; c = dx * inv; sn = dy * inv; }
       else { ds = hypot(dx, dy); if (ds > 0.0) { c = dx / ds; sn = dy / ds; } }
       sink.segment(i - 1, xp, yp, dx, dy, ds, c, sn);
+      if (sink.vetoed()) return;          // select-only evaluation: this candidate can no longer be selected
     }
     xp = x; yp = y;
   }
@@ -283,6 +287,7 @@ struct EvalSink {
     sum_v = sum_v + ev2;
   }
   __device__ __forceinline__ void point(int, double, double) {}
+  __device__ __forceinline__ bool vetoed() const { return p.select_only && (curv_fail || collided); }
 
   __device__ __forceinline__ void curvature_step(double dx, double dy, double ds, double c, double sn) {
     if (curvature_fails(p.kmax, pdx, pdy, pds, pc, psn, dx, dy, ds, c, sn)) curv_fail = true;

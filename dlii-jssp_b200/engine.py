@@ -212,12 +212,17 @@ class JsspEngine:
 
     def evaluate(self, frenet0, time_step_now: int, final_time_step: int, seeds: Optional[torch.Tensor] = None,
                  targets: Optional[Sequence[float]] = None, want_states: bool = False, sync: bool = True, export: bool = True,
-                 cull: bool = True, kernel: Optional[str] = None) -> Optional[CycleResult]:
+                 cull: bool = True, kernel: Optional[str] = None, select_only: bool = False) -> Optional[CycleResult]:
         """One plan cycle.  frenet0 = (s, s_d, s_dd, d, d_d, d_dd); seeds = device float64 [Ns, 10] or None (use the
-        enumerated seeds).  With sync=False the kernels are only enqueued; call fetch() later."""
+        enumerated seeds).  With sync=False the kernels are only enqueued; call fetch() later.  ``select_only``: no
+        per-candidate masks / costs are requested (NULL pointers), only the selection and the exported trajectory - a
+        candidate's walk then stops at its first veto, as the reference's filter chain does; the masks of the returned result
+        are stale."""
         flags = (0 if sync else FLAG_NO_SYNC) | (0 if export else FLAG_NO_EXPORT) | (0 if cull else FLAG_NO_CULL)
         flags |= {None: 0, "warp": FLAG_FORCE_WARP, "thread": FLAG_FORCE_THREAD, "group": FLAG_FORCE_GROUP}[kernel]
         cin, cout = self._cycle_structs(frenet0, time_step_now, final_time_step, seeds, targets, flags, want_states, None)
+        if select_only:
+            cout.feasible_dev = cout.collision_dev = cout.cost_dev = None
         self._last = (cin, cout, want_states)
         self._check(self.lib.jssp_evaluate(self._h, C.byref(cin), self.stream, C.byref(cout)), "jssp_evaluate")
         return self._result(cout, want_states, export) if sync else None

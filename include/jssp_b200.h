@@ -99,7 +99,10 @@ typedef struct jssp_cycle_in {
                                     consecutive lanes and share the seed-only work by warp shuffles; same results */
 #define JSSP_FLAG_NO_CULL 4      /* test every obstacle state instead of the per-block culled lists (same results) */
 
-/* Outputs.  Candidate n = w * n_seeds + k (width-major, jssp.py:106,124-125).  All dev pointers may be NULL. */
+/* Outputs.  Candidate n = w * n_seeds + k (width-major, jssp.py:106,124-125).  All dev pointers may be NULL.  With
+ * feasible_dev, collision_dev and cost_dev all NULL the evaluation is select-only: a candidate's walk stops at its first
+ * veto - the reference filters the same way (check_constraints_curvature -> check_collisions on the survivors -> cost on the
+ * survivors, has_collision returning at the first hit; jssp.py:311-319) - and the selection is unchanged. */
 typedef struct jssp_cycle_out {
   uint8_t* feasible_dev;       /* [N] 1 = passes check_constraints_curvature (jssp.py:171-180) */
   uint8_t* collision_dev;      /* [N] 1 = has_collision (jssp.py:233-272), evaluated for every candidate */

@@ -166,6 +166,21 @@ def test_c3_full_size_properties_and_subsample_parity():
     eng.close()
 
 
+@pytest.mark.parametrize("n_seeds,n_widths,O_,M,horizon,seed", [(4096, 4, 32, 3, 5.0, 51), (3000, 3, 6, 1, 5.0, 52), (2048, 8, 64, 3, 8.0, 53)])
+def test_select_only_evaluation_selects_the_same_trajectory(n_seeds, n_widths, O_, M, horizon, seed):
+    """No per-candidate outputs requested (select-only: walks stop at the first veto) -> same selected index, cost and exported
+    trajectory as the full evaluation, for every kernel."""
+    cyc, cfg, spline, eng = _dense(n_seeds, n_widths, O_, M, horizon, seed, p_min=0.2, w_risk=0.5)
+    seeds = torch.from_numpy(cyc.seeds).cuda()
+    for kern in ("group", "thread", "warp"):
+        full = eng.evaluate(cyc.frenet0, 0, cyc.final_time_step, seeds=seeds, targets=cyc.targets, kernel=kern)
+        assert full.best_idx >= 0 and bool(full.collision.any())
+        sel = eng.evaluate(cyc.frenet0, 0, cyc.final_time_step, seeds=seeds, targets=cyc.targets, kernel=kern, select_only=True)
+        assert (sel.best_idx, sel.best_cost, sel.best_n_pts) == (full.best_idx, full.best_cost, full.best_n_pts)
+        assert np.array_equal(np.nan_to_num(sel.best_traj), np.nan_to_num(full.best_traj))
+    eng.close()
+
+
 def test_c5_full_size_properties_and_subsample_parity():
     """BASELINE config 5 at full size on one GPU (1,048,576 candidates x 81 samples x 64 obstacles x 3 modes): argmin property,
     exact mask parity on a candidate subsample, and the candidate split of the multi-GPU path (8 contiguous seed ranges
