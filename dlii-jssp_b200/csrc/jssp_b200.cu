@@ -1410,11 +1410,11 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   for (int c = 0; c < n_cycles; ++c) {
     CKB(launch_seed_enum<true>(b->grids, SeedState{0, 0, 0}, b->d_slots, b->seed_work, n_scenarios, seed_cluster, seed_threads, b->seed_smem, st, pdl));
     const EvalParams* slots = b->d_slots;
-    if (small) CKB(launch_chained(evaluate_small_batch_kernel, dim3(std::min(b->blocks_warp, 128), n_scenarios), SMALL_WARPS * 32, small_bytes, st, pdl, slots));
-    else if (group && mode == 1) CKB(launch_chained(evaluate_group_batch_kernel<1>, dim3(blocks_group, n_scenarios), bthreads, L.total, st, pdl, slots));
-    else if (group) CKB(launch_chained(evaluate_group_batch_kernel<0>, dim3(blocks_group, n_scenarios), bthreads, L.total, st, pdl, slots));
-    else if (mode == 1) CKB(launch_chained(evaluate_batch_kernel<1>, dim3(blocks_thread, n_scenarios), bthreads, L.total, st, pdl, slots));
-    else CKB(launch_chained(evaluate_batch_kernel<0>, dim3(blocks_thread, n_scenarios), bthreads, L.total, st, pdl, slots));
+    if (small) CKB(launch_chained(evaluate_small_batch_kernel, dim3(n_scenarios, std::min(b->blocks_warp, 128)), SMALL_WARPS * 32, small_bytes, st, pdl, slots));
+    else if (group && mode == 1) CKB(launch_chained(evaluate_group_batch_kernel<1>, dim3(n_scenarios, blocks_group), bthreads, L.total, st, pdl, slots));
+    else if (group) CKB(launch_chained(evaluate_group_batch_kernel<0>, dim3(n_scenarios, blocks_group), bthreads, L.total, st, pdl, slots));
+    else if (mode == 1) CKB(launch_chained(evaluate_batch_kernel<1>, dim3(n_scenarios, blocks_thread), bthreads, L.total, st, pdl, slots));
+    else CKB(launch_chained(evaluate_batch_kernel<0>, dim3(n_scenarios, blocks_thread), bthreads, L.total, st, pdl, slots));
     b->launches += 2;
   }
   CKB(cudaGetLastError());

@@ -602,6 +602,12 @@ __device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* 
   tb.broad = p.broad; tb.broad_row0 = p.now; tb.broad_stride = p.check_res;   // fallback path
 }
 
+// Block index within the plan cycle and blocks per cycle.  The batch kernels run a TRANSPOSED grid (x = scenario, y = block):
+// blocks are dispatched x-fastest, so block 0 of every scenario starts before any scenario's block 1, and the trailing
+// blocks that find no candidates (the grid is sized for max_seeds) come last instead of sitting between the working ones.
+__device__ __forceinline__ int blk_index(const EvalParams& p) { return p.batch ? (int)blockIdx.y : (int)blockIdx.x; }
+__device__ __forceinline__ int blk_count(const EvalParams& p) { return p.batch ? (int)gridDim.y : (int)gridDim.x; }
+
 __device__ __forceinline__ int resolve_n_seeds(const EvalParams& p) {
   return p.n_seeds_ptr ? min(p.n_seeds_ptr[2], p.seed_cap) : p.n_seeds_fixed;
 }
@@ -928,18 +934,18 @@ __device__ __forceinline__ void select_and_export(const EvalParams& p, unsigned 
   if (threadIdx.x == 0) {
     for (int q = 1; q < nwarps; ++q)
       if (lex_less(red_cost[q], red_idx[q], my_cost, my_idx)) { my_cost = red_cost[q]; my_idx = red_idx[q]; }
-    p.blk_cost[blockIdx.x] = my_cost;
-    p.blk_idx[blockIdx.x] = my_idx;
+    p.blk_cost[blk_index(p)] = my_cost;
+    p.blk_idx[blk_index(p)] = my_idx;
     __threadfence();
     const unsigned int t = atomicAdd(p.ticket, 1u);
-    *is_last_p = (t == gridDim.x - 1);
+    *is_last_p = (t == (unsigned int)blk_count(p) - 1u);
   }
   __syncthreads();
   if (!*is_last_p) return;
   // the last block to finish reduces the per-block winners: deterministic, no floating-point atomics
   __threadfence();
   my_cost = INFINITY; my_idx = -1;
-  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+  for (int b = threadIdx.x; b < blk_count(p); b += blockDim.x) {
     const double c = __ldcg(p.blk_cost + b);
     const int i = __ldcg(p.blk_idx + b);
     if (lex_less(c, i, my_cost, my_idx)) { my_cost = c; my_idx = i; }
@@ -986,12 +992,12 @@ __device__ __forceinline__ void evaluate_body(const EvalParams& p, unsigned char
                                               int* sm_npts) {
   const int Ns = resolve_n_seeds(p);
   const int N = Ns * p.W;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blk_index(p) * blockDim.x + threadIdx.x;
   double my_cost = INFINITY;
   int my_idx = -1;
   BlockTables tb;
   const double* latcost;
-  const bool staged = blockIdx.x * blockDim.x < N;   // block-uniform
+  const bool staged = blk_index(p) * (int)blockDim.x < N;   // block-uniform
   PHASE(p, 0);
   if (staged) {
     stage_tables<kMode>(p, smem, tb, latcost);
@@ -1045,13 +1051,13 @@ __device__ __forceinline__ void evaluate_group_body(const EvalParams& p, unsigne
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int g = lane / W, j = lane - g * W;
   const int spb = (blockDim.x >> 5) * gpw;     // the host picks the block size (<= EVAL_THREADS)
-  const int k = blockIdx.x * spb + wid * gpw + g;
+  const int k = blk_index(p) * spb + wid * gpw + g;
   const bool active = g < gpw && k < Ns;
   double my_cost = INFINITY;
   int my_idx = -1;
   BlockTables tb;
   const double* latcost;
-  const bool staged = blockIdx.x * spb < Ns;   // block-uniform
+  const bool staged = blk_index(p) * spb < Ns;   // block-uniform
   PHASE(p, 0);
   if (staged) {
     stage_tables<kMode>(p, smem, tb, latcost);
@@ -1088,7 +1094,7 @@ __global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_group_
   evaluate_group_body<kMode>(p, smem, red_cost, red_idx, &is_last, &sm_npts);
 }
 
-// Batched replay: blockIdx.y = scenario; the scenario's parameter record is copied into shared memory once per block.
+// Batched replay: blockIdx.x = scenario, blockIdx.y = block of the scenario (see blk_index); the scenario's parameter record is copied into shared memory once per block.
 __device__ __forceinline__ void load_slot(EvalParams* dst, const EvalParams* src) {
   static_assert(sizeof(EvalParams) % 8 == 0, "EvalParams is copied as 8-byte words");
   const unsigned long long* s = reinterpret_cast<const unsigned long long*>(src);
@@ -1106,8 +1112,8 @@ __global__ void __launch_bounds__(BATCH_EVAL_THREADS, BATCH_MIN_BLOCKS) evaluate
   __shared__ bool is_last;
   __shared__ int sm_npts;
   pdl_launch_dependents(); pdl_wait();                 // seeds and slot records come from the kernels ahead in the stream
-  if (!slot_live(slots, blockIdx.y)) return;           // block-uniform; stable until the scenario's last block hands off
-  load_slot(&sp, slots + blockIdx.y);
+  if (!slot_live(slots, blockIdx.x)) return;           // block-uniform; stable until the scenario's last block hands off
+  load_slot(&sp, slots + blockIdx.x);
   evaluate_body<kMode>(sp, smem, red_cost, red_idx, &is_last, &sm_npts);
 }
 
@@ -1120,8 +1126,8 @@ __global__ void __launch_bounds__(BATCH_EVAL_THREADS, BATCH_MIN_BLOCKS) evaluate
   __shared__ bool is_last;
   __shared__ int sm_npts;
   pdl_launch_dependents(); pdl_wait();
-  if (!slot_live(slots, blockIdx.y)) return;
-  load_slot(&sp, slots + blockIdx.y);
+  if (!slot_live(slots, blockIdx.x)) return;
+  load_slot(&sp, slots + blockIdx.x);
   evaluate_group_body<kMode>(sp, smem, red_cost, red_idx, &is_last, &sm_npts);
 }
 

@@ -25,7 +25,7 @@ __device__ __forceinline__ void evaluate_small_body(const EvalParams& p, unsigne
   int my_idx = -1;
   BlockTables tb;
   const double* latcost;
-  const bool staged = blockIdx.x * SMALL_WARPS < N;   // block-uniform
+  const bool staged = blk_index(p) * SMALL_WARPS < N;   // block-uniform
   if (staged) {
     stage_tables<0>(p, smem, tb, latcost);
     const SmemLayout L = eval_smem_layout(0, p.OMpad, 0, p.K, p.kpad, p.P, p.W);
@@ -33,7 +33,7 @@ __device__ __forceinline__ void evaluate_small_body(const EvalParams& p, unsigne
     double* ends = scr + (size_t)P * SMALL_ROW;        // s at the first / last sample
     // grid-stride over groups of SMALL_WARPS candidates: the candidate count is only known on the device, the grid is sized
     // from a hint and stays small (no thousands of empty blocks in front of a ~100-block cycle)
-    for (int n = blockIdx.x * SMALL_WARPS + wid; n < N; n += gridDim.x * SMALL_WARPS) {     // warp-uniform
+    for (int n = blk_index(p) * SMALL_WARPS + wid; n < N; n += blk_count(p) * SMALL_WARPS) {     // warp-uniform
       const int w = n / Ns, k = n - w * Ns;
       const double* lat = tb.lat + (size_t)w * P * 4;
       LonProfile lp;
@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) evaluate_small_batch_kernel(
   __shared__ bool is_last;
   __shared__ int sm_npts;
   pdl_launch_dependents(); pdl_wait();
-  if (!slot_live(slots, blockIdx.y)) return;
-  load_slot(&sp, slots + blockIdx.y);
+  if (!slot_live(slots, blockIdx.x)) return;
+  load_slot(&sp, slots + blockIdx.x);
   evaluate_small_body(sp, smem, red_cost, red_idx, &is_last, &sm_npts);
 }
 
