@@ -11,7 +11,7 @@ cyc = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 kernels = sys.argv[3:] or ["default"]
 packed = [B.pack_scenario(S.synthetic_intersection(i), max_cycles=cyc) for i in range(n)]
 packed = [p for p in packed if p.initial_end == -1]
-cfg = J.JsspConfig(max_seeds=1024, max_knots=max(len(p.knot_s) for p in packed), max_obstacle_modes=max(1, max(p.state.shape[0] for p in packed)),
+cfg = J.JsspConfig(max_seeds=int(os.environ.get("SWEEP_MAX_SEEDS", "1024")), max_knots=max(len(p.knot_s) for p in packed), max_obstacle_modes=max(1, max(p.state.shape[0] for p in packed)),
                    max_total_steps=max(p.state.shape[2] for p in packed))
 bt = B.BatchReplay(cfg, max_scenarios=len(packed), max_cycles=cyc)
 bt.load(packed)
