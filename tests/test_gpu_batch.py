@@ -66,6 +66,11 @@ def test_batch_resume_continues_where_it_stopped():
     whole = bt.results()[0]
     bt.load([p]); bt.run(5); bt.run(7)
     _same(bt.results()[0], whole)
+    # reset = back to the freshly loaded state without an upload; array-valued results are views of the same records
+    bt.reset(); bt.run(12)
+    arr = bt.results(lists=False)[0]
+    assert arr.best_idx.tolist() == whole.best_idx and arr.n_candidates.tolist() == whole.n_candidates
+    assert [tuple(r) for r in arr.ego_rows.tolist()] == whole.ego_rows and arr.end == whole.end
     bt.close()
 
 
