@@ -452,7 +452,9 @@ def run_sweep(args):
         cfg = B.fop_batch_config(fop, float(e[5]), float(e[6]), max_seeds=1024, max_knots=cfg.max_knots, max_obstacle_modes=cfg.max_obstacle_modes,
                                  max_total_steps=cfg.max_total_steps)
         pts = float(np.mean([len(np.arange(0.0, T, fop.delta_t)) for T in np.linspace(fop.min_t, fop.max_t, fop.num_t)]))   # samples per candidate
-    bt = B.BatchReplay(cfg, device=local, max_scenarios=len(packed), max_cycles=args.cycles, fop=fop)
+    # two sub-batches on two CUDA streams: the seed enumeration of one overlaps the evaluation of the other
+    k_sub = args.sub_batches if len(packed) >= 16 else 1
+    bt = B.MultiStreamReplay(cfg, device=local, max_scenarios=len(packed), max_cycles=args.cycles, k=k_sub, fop=fop)
     bt.load(packed)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sampler = ClockSampler(local)
@@ -517,7 +519,8 @@ def run_sweep(args):
                 "ms_per_step": 1e3 * sweep_s, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64 geometry + f32 collision", "data": "synthetic",
                 "config": {"workload": desc, "scenarios": int(n_all), "cycles_cap": args.cycles,
-                           "parallelism": f"scenario shards over {world} ranks, batched device-resident replay per rank, no collective",
+                           "parallelism": f"scenario shards over {world} ranks, batched device-resident replay per rank "
+                                          f"({k_sub} sub-batch(es) on separate streams), no collective",
                            "l2": "flushed between sweeps (256 MiB write outside the event pairs)"},
                 "e2e": {"value": units_all / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
                         "sweep_ms": 1e3 * e2e_max},
@@ -545,6 +548,7 @@ def main():
     ap.add_argument("--workload", default="C3", choices=["C3", "C5", "C4", "C2"])
     ap.add_argument("--scenarios", type=int, default=800, help="C4: number of synthetic scenarios in the sweep")
     ap.add_argument("--cycles", type=int, default=100, help="C4: plan cycles per scenario (upper bound)")
+    ap.add_argument("--sub-batches", type=int, default=2, help="C4/C2: sub-batches per rank, each on its own CUDA stream")
     ap.add_argument("--planner", default="JSSP", choices=["JSSP", "frenet"], help="C4: planner of the replay (frenet = the FOP baseline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--cpu-sample-div", type=int, default=32, help="cpu_baseline sample = candidates / this")

@@ -307,6 +307,66 @@ class BatchReplay:
         return out
 
 
+class MultiStreamReplay:
+    """``k`` BatchReplay handles on ``k`` CUDA streams, the scenarios dealt round-robin: the kernels of the sub-batches interleave on
+    the device, so the seed enumeration of one sub-batch overlaps the evaluation of another (measured with k = 2: 800-scenario
+    sweep 42.1 -> 38.8 ms, 100 scenarios 130.6 -> 125.6 us per cycle; no further gain for k = 3, 4).  Same interface as
+    BatchReplay; work is enqueued relative to the caller's current stream (it is waited for at the start of ``run`` and waits
+    for the sub-batches at its end)."""
+
+    def __init__(self, config: Optional[JsspConfig] = None, device: int = 0, max_scenarios: int = 64, max_cycles: int = 128, k: int = 2, **kw):
+        self.k = max(1, int(k))
+        self.device = torch.device("cuda", device)
+        per = (int(max_scenarios) + self.k - 1) // self.k
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.k)]
+        self.parts = [BatchReplay(config, device=device, max_scenarios=max(per, 1), max_cycles=max_cycles, **kw) for _ in range(self.k)]
+        self.cfg, self.C, self.lib = self.parts[0].cfg, self.parts[0].C, self.parts[0].lib
+        self._n = 0
+
+    def _each(self, fn):
+        cur = torch.cuda.current_stream(self.device)
+        out = []
+        for bt, st in zip(self.parts[:max(1, min(self.k, self._n))], self.streams):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                out.append(fn(bt))
+        for st in self.streams:
+            cur.wait_stream(st)
+        return out
+
+    def load(self, packed: Sequence[PackedScenario]):
+        self._n = len(packed)
+        groups = [list(packed[i::self.k]) for i in range(self.k)]
+        cur = torch.cuda.current_stream(self.device)
+        for bt, st, g in zip(self.parts, self.streams, groups):
+            if g:
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    bt.load(g)
+                cur.wait_stream(st)
+
+    def reset(self):
+        self._each(lambda bt: bt.reset())
+
+    def run(self, n_cycles: Optional[int] = None, kernel: Optional[str] = None):
+        return max(self._each(lambda bt: bt.run(n_cycles, kernel=kernel)))
+
+    def results(self, lists: bool = True) -> List[ReplayResult]:
+        parts = self._each(lambda bt: bt.results(lists=lists))
+        out: List[Optional[ReplayResult]] = [None] * self._n
+        for i, res in enumerate(parts):
+            out[i::self.k] = res
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return sum(bt.launch_count for bt in self.parts)
+
+    def close(self):
+        for bt in self.parts:
+            bt.close()
+
+
 def fop_batch_config(fop, ego_length: float, ego_width: float, **caps) -> JsspConfig:
     """The jssp_config of a batch that replays with the FOP baseline (same fields FrenetOptimalPlanner sets for its engine)."""
     from .fop import PLANNER_FRENET, PARA_THRESHOLD

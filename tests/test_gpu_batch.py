@@ -124,3 +124,29 @@ def test_batch_kinematics_mode_matches_host_loop_and_reference_golden(scenario_f
     a = B.run_batch([B.pack_scenario(scs[0], kinematics=True)], max_cycles=12)[0]
     b = B.run_batch([scs[0]], max_cycles=12)[0]
     assert a.best_idx == b.best_idx and a.ego_rows == b.ego_rows
+
+
+def test_sub_batches_on_separate_streams_replay_identically(scenario_fixture):
+    """MultiStreamReplay (k sub-batches on k CUDA streams, scenarios dealt round-robin) returns, in the caller's order, exactly
+    what one BatchReplay returns - also when there are fewer scenarios than sub-batches."""
+    scs = [scenario_fixture] + [S.synthetic_intersection(i) for i in (2, 5, 9, 11)]
+    packed = [B.pack_scenario(sc, max_cycles=20) for sc in scs]
+    cfg = J.JsspConfig(ego_length=float(packed[0].ego[5]), ego_width=float(packed[0].ego[6]), max_seeds=1024,
+                       max_knots=max(64, max(len(p.knot_s) for p in packed)), max_obstacle_modes=max(p.state.shape[0] for p in packed),
+                       max_total_steps=max(p.state.shape[2] for p in packed))
+    one = B.BatchReplay(cfg, max_scenarios=len(packed), max_cycles=20)
+    one.load(packed); one.run(20)
+    want = one.results()
+    for k in (2, 3):
+        ms = B.MultiStreamReplay(cfg, max_scenarios=len(packed), max_cycles=20, k=k)
+        ms.load(packed); ms.run(20)
+        for a, b in zip(want, ms.results()):
+            assert a.name == b.name
+            _same(b, a)
+        ms.reset(); ms.run(20)
+        for a, b in zip(want, ms.results(lists=False)):
+            assert b.best_idx.tolist() == a.best_idx
+        ms.load(packed[:1]); ms.run(20)                      # fewer scenarios than sub-batches
+        _same(ms.results()[0], want[0])
+        ms.close()
+    one.close()
