@@ -162,7 +162,8 @@ def test_clock_tables_follow_the_reference_clock(scenario_fixture):
 
 def test_packed_scenario_cache_round_trip(tmp_path, scenario_fixture):
     from dlii_jssp_b200 import batch as B
-    packed = [B.pack_scenario(scenario_fixture), B.pack_scenario(S.synthetic_intersection(2), max_cycles=30)]
+    packed = [B.pack_scenario(scenario_fixture), B.pack_scenario(S.synthetic_intersection(2), max_cycles=30),
+              B.pack_scenario(S.synthetic_intersection(3), max_cycles=10, kinematics=True)]      # with the kinematics-mode polyline table
     B.save_packed(str(tmp_path / "shard.npz"), packed)
     back = B.load_packed(str(tmp_path / "shard.npz"))
     assert [p.name for p in back] == [p.name for p in packed]
@@ -171,6 +172,7 @@ def test_packed_scenario_cache_round_trip(tmp_path, scenario_fixture):
             va, vb = getattr(a, f), getattr(b, f)
             assert (va is None and vb is None) or (va.dtype == vb.dtype and np.array_equal(va, vb)), f
         assert (a.n_dict, a.dt, a.max_t, a.final_time_step, a.initial_end) == (b.n_dict, b.dt, b.max_t, b.final_time_step, b.initial_end)
+    assert back[2].polyline is not None and back[0].polyline is None and back[2].c_view(True).n_polyline == len(packed[2].polyline)
     # the packed obstacle table holds exactly the dictionary's states
     p = packed[0]
     tr = scenario_fixture.vehicle_traj
