@@ -1,9 +1,8 @@
 """dlii_jssp_b200 - B200 (sm_100a) implementation of the DLII-JSSP jerk-space sampling planner's per-cycle candidate
 evaluation, behind the reference's own planner interface.
 
-The package directory is ``dlii-jssp_b200/`` (not an importable name); ``import dlii_jssp_b200`` resolves to it through
-the one-line shim module ``dlii_jssp_b200.py`` at the repository root.  All compute goes through ``libjssp_b200.so``
-(include/jssp_b200.h); there is no CPU fallback - importing the engine without the library or a GPU raises.
+All compute goes through ``libjssp_b200.so`` (include/jssp_b200.h, built in-tree by ``dlii_jssp_b200/build.py``); there is no
+CPU fallback - creating an engine without the library or a GPU raises.
 """
 from . import _lib
 from ._lib import JsspError, TRAJ_COLUMNS, STATE_COLUMNS

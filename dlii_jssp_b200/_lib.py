@@ -98,6 +98,7 @@ STRUCTS = (JsspConfigC, JsspCycleIn, JsspCycleOut, JsspFopIn, JsspImmParams, Jss
 # every symbol include/jssp_b200.h declares (tests check that the library exports exactly these)
 SYMBOLS = {
     "jssp_abi_version": (C.c_int32, []),
+    "jssp_build_id": (C.c_char_p, []),
     "jssp_struct_size": (C.c_int32, [C.c_int32]),
     "jssp_strerror": (C.c_char_p, [C.c_int32]),
     "jssp_last_cuda_error": (C.c_char_p, [C.c_void_p]),
@@ -142,20 +143,27 @@ def library_path() -> str:
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:
-    """Load libjssp_b200.so (building it in-tree with nvcc when absent).  Raises - never falls back to a CPU path."""
+    """Load libjssp_b200.so, (re)building it in-tree with nvcc when it is absent or was compiled from other sources than the
+    ones on disk (build id mismatch).  Raises - never falls back to a CPU path, never loads a stale library silently."""
     global _lib
     if _lib is not None:
         return _lib
     path = library_path()
-    if not os.path.exists(path):
+    override = bool(os.environ.get("JSSP_B200_LIB"))
+    if not override and _build.needs_build():
         if not build_if_missing:
-            raise RuntimeError(f"{path} is missing: build it with `python -m dlii_jssp_b200.build` (no CPU fallback exists)")
+            raise RuntimeError(f"{path} is missing or stale (build id {_build.library_id()} != sources {_build.source_id()}): "
+                               "build it with `python -m dlii_jssp_b200.build` (no CPU fallback exists)")
         _build.build_library()
+    elif not os.path.exists(path):
+        raise RuntimeError(f"{path} does not exist (no CPU fallback exists)")
     lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)      # AttributeError here = the library does not export what the header declares
         fn.restype = res
         fn.argtypes = args
+    if not override and lib.jssp_build_id().decode() != _build.source_id():
+        raise RuntimeError("libjssp_b200.so build id does not match the sources on disk; rebuild")
     if lib.jssp_abi_version() != 1:
         raise RuntimeError("libjssp_b200.so ABI version mismatch; rebuild")
     for which, st in enumerate(STRUCTS):

@@ -61,7 +61,7 @@ __global__ void best_record_kernel(const BestRecord* __restrict__ best, long lon
 // ------------------------------------------------------------------------------------------------------------------
 // K5: batched Cartesian -> Frenet projection: FrenetState.from_state(state, polyline) as the
 // driver uses it at t <= 0.05 and in kinematics mode (intersection_planner.py:140-142, 308-310).  The class is absent from
-// the reference tree; the specification is dlii-jssp_b200/frenet.py::FrenetState.from_state: nearest point of the
+// the reference tree; the specification is dlii_jssp_b200/frenet.py::FrenetState.from_state: nearest point of the
 // reference line re-discretised every `step` metres (generate_frenet_frame, jssp.py:366-371), arc length = sum of the chord
 // lengths up to it plus the tangential offset, signed lateral offset by the left-hand normal, speed / acceleration split
 // by the heading error.  One block per state: threads stride over the polyline samples.

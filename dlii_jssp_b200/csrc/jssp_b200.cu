@@ -15,8 +15,27 @@
 
 using namespace jssp;
 
+// tools/ A/B overrides (JSSP_B200_TUNE_* environment variables), read ONCE when a handle is created - never on the per-cycle path
+struct Tuning {
+  bool no_pdl = false;        // plain stream order instead of programmatic dependent launches
+  bool full_walk = false;     // batched replay: walk every candidate to the end instead of stopping at its first veto
+  int seed_cluster = 0;       // CTAs per seed-enumeration cluster (0 = by batch size)
+  int seed_threads = 0;       // threads per seed-enumeration CTA (0 = by batch size)
+  int lockstep = 0;           // batched replay: 1 = force the lock-step kernels instead of the persistent scenario kernel
+  static Tuning from_env() {
+    Tuning t;
+    t.no_pdl = getenv("JSSP_B200_TUNE_NO_PDL") != nullptr;
+    t.full_walk = getenv("JSSP_B200_TUNE_FULL_WALK") != nullptr;
+    if (const char* e = getenv("JSSP_B200_TUNE_SEED_CLUSTER")) t.seed_cluster = atoi(e);
+    if (const char* e = getenv("JSSP_B200_TUNE_SEED_THREADS")) t.seed_threads = atoi(e);
+    if (const char* e = getenv("JSSP_B200_TUNE_LOCKSTEP")) t.lockstep = atoi(e);
+    return t;
+  }
+};
+
 struct jssp_handle {
   jssp_config cfg;
+  Tuning tune;
   int device = 0;
   int P = 0;   // samples per trajectory = n_steps + 1
   // sampling grids (device) + lengths
@@ -299,6 +318,12 @@ SeedWork make_seed_work(const SeedGrids& g, int* counts, double* seeds, int cap_
 
 extern "C" {
 
+#ifndef JSSP_BUILD_ID_STR
+#define JSSP_BUILD_ID_STR "0000000000000000"
+#endif
+// hash of the sources and flags this library was compiled from (dlii_jssp_b200/build.py); the loader refuses a mismatch
+static const char k_build_id[] = "JSSP_BUILD_ID=" JSSP_BUILD_ID_STR;
+const char* jssp_build_id(void) { return k_build_id + 14; }
 int32_t jssp_abi_version(void) { return JSSP_ABI_VERSION; }
 int32_t jssp_struct_size(int32_t which) {
   const size_t sizes[] = {sizeof(jssp_config), sizeof(jssp_cycle_in), sizeof(jssp_cycle_out), sizeof(jssp_fop_in), sizeof(jssp_imm_params),
@@ -368,6 +393,7 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   jssp_handle* h = new (std::nothrow) jssp_handle();
   if (!h) return JSSP_ERR_INVALID_ARG;
   h->cfg = *cfg;
+  h->tune = Tuning::from_env();
   h->device = device;
   h->P = (int)(cfg->plan_horizon / cfg->delta_t) + 1;   // len(time_array), polyvt_sampling.py:44
   auto bail = [&](int code) { jssp_destroy(h); return code; };
@@ -732,7 +758,7 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   if (small) {
     p.smem_obs = 0; p.win_rows = 0; p.list_cap = 0;
     // one-call plan cycle: the evaluation is chained to the seed enumeration just enqueued (programmatic dependent launch)
-    const bool chained = !ext && (in->flags & JSSP_FLAG_ENUMERATE) && getenv("JSSP_B200_TUNE_NO_PDL") == nullptr;
+    const bool chained = !ext && (in->flags & JSSP_FLAG_ENUMERATE) && !h->tune.no_pdl;
     CK(launch_chained(evaluate_small_kernel, dim3(blocks), SMALL_WARPS * 32, small_bytes, st, chained, p));
   }
   else if (group && mode == 2) evaluate_group_kernel<2><<<blocks, EVAL_THREADS, L.total, st>>>(p);
@@ -915,6 +941,7 @@ int32_t jssp_predict_modes(jssp_handle* h, const double* lanes_dev, int32_t L, i
 // =====================================================================================================================
 struct jssp_batch {
   jssp_config cfg;
+  Tuning tune;
   int device = 0, P = 0, S = 0, C = 0;
   int W = 0;
   double* d_grid[10] = {nullptr};
@@ -1030,7 +1057,7 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   }
   jssp_batch* b = new (std::nothrow) jssp_batch();
   if (!b) return JSSP_ERR_INVALID_ARG;
-  b->cfg = *cfg; b->device = device; b->S = max_scenarios; b->C = max_cycles; b->W = cfg->num_width;
+  b->cfg = *cfg; b->tune = Tuning::from_env(); b->device = device; b->S = max_scenarios; b->C = max_cycles; b->W = cfg->num_width;
   b->P = (int)(cfg->plan_horizon / cfg->delta_t) + 1;
   auto bail = [&](int code) { jssp_batch_destroy(b); return code; };
 #define CKC(call)                                                                     \
@@ -1276,7 +1303,7 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
   p.win_rows = OM > 0 ? rows : 0;
   p.smem_obs = 1; p.sint = nullptr; p.probf = probf; p.list_cap = 0;
   p.feasible = nullptr; p.collision = nullptr; p.cost = nullptr;
-  p.select_only = getenv("JSSP_B200_TUNE_FULL_WALK") ? 0 : 1;    // the replay only needs the selected trajectory (tools/: A/B override)
+  p.select_only = b->tune.full_walk ? 0 : 1;    // the replay only needs the selected trajectory (tools/: A/B override)
   p.blk_cost = b->d_blk_cost + s * b->max_blocks; p.blk_idx = b->d_blk_idx + s * b->max_blocks;
   p.ticket = b->d_ticket + s; p.best = b->d_best + s;
   p.best_traj = b->d_best_traj + s * (size_t)b->P * JSSP_TRAJ_COLS;
@@ -1371,7 +1398,7 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   cudaStream_t st = (cudaStream_t)stream;
   CKB(cudaSetDevice(b->device));
   { const int32_t rc = snapshot_fresh_slots(b, st); if (rc != JSSP_OK) return rc; }
-  const bool pdl = getenv("JSSP_B200_TUNE_NO_PDL") == nullptr;     // tools/ only: plain stream order instead of chained launches
+  const bool pdl = !b->tune.no_pdl;     // tools/ only: plain stream order instead of chained launches
   if (b->fop) {                       // FOP baseline: no seed enumeration, evaluation + (selection, export, hand-off) per step
     for (int c = 0; c < n_cycles; ++c) {
       CKB(launch_chained(evaluate_fop_batch_kernel, dim3(b->fop_blocks, n_scenarios), EVAL_THREADS, b->fop_smem, st, pdl, (const FopParams*)b->d_fslots));
@@ -1405,8 +1432,8 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   int seed_cluster = 1;
   while (seed_cluster < SEED_MAX_CLUSTER && n_scenarios * seed_cluster * 2 <= 148) seed_cluster *= 2;
   int seed_threads = n_scenarios >= 296 ? 512 : SEED_THREADS;
-  if (const char* e = getenv("JSSP_B200_TUNE_SEED_CLUSTER")) seed_cluster = std::max(1, std::min(SEED_MAX_CLUSTER, atoi(e)));    // tools/ only
-  if (const char* e = getenv("JSSP_B200_TUNE_SEED_THREADS")) seed_threads = atoi(e) == 512 ? 512 : SEED_THREADS;
+  if (b->tune.seed_cluster > 0) seed_cluster = std::max(1, std::min(SEED_MAX_CLUSTER, b->tune.seed_cluster));    // tools/ only
+  if (b->tune.seed_threads > 0) seed_threads = b->tune.seed_threads == 512 ? 512 : SEED_THREADS;
   for (int c = 0; c < n_cycles; ++c) {
     CKB(launch_seed_enum<true>(b->grids, SeedState{0, 0, 0}, b->d_slots, b->seed_work, n_scenarios, seed_cluster, seed_threads, b->seed_smem, st, pdl));
     const EvalParams* slots = b->d_slots;

@@ -120,6 +120,10 @@ typedef struct jssp_cycle_out {
 
 /* -- lifecycle ------------------------------------------------------------------------------------------ */
 int32_t jssp_abi_version(void);
+/* 16 hex digits: hash of the sources and compiler flags the library was built from (dlii_jssp_b200/build.py).  The Python
+ * loader rebuilds / refuses the library when it differs from the sources on disk; profiles/ records it next to every ncu
+ * capture so that a counter can be tied to the code that produced it. */
+const char* jssp_build_id(void);
 /* sizeof of the public structs as this library was compiled, for a binding to check its own declarations against:
  * which = 0 jssp_config, 1 jssp_cycle_in, 2 jssp_cycle_out, 3 jssp_fop_in, 4 jssp_imm_params, 5 jssp_cycle_record,
  * 6 jssp_scenario_result, 7 jssp_scenario_in; -1 for anything else */
@@ -229,7 +233,7 @@ int32_t jssp_fop_evaluate(jssp_handle* h, const jssp_fop_in* in, void* stream, j
  * replaces FrenetState().from_state(ego_state, ref_ego_lane_pts) (intersection_planner.py:140-142, 308-310) for n states
  * at once on the handle's reference line re-discretised every `step` metres (0.1 in jssp.py:366): state_dev [n][5] =
  * x, y, yaw, v, a -> frenet_dev [n][6] = s, s_d, s_dd, d, d_d, d_dd (both device pointers).  The class is absent from the
- * reference tree; dlii-jssp_b200/frenet.py documents the formulation. */
+ * reference tree; dlii_jssp_b200/frenet.py documents the formulation. */
 int32_t jssp_project_states(jssp_handle* h, const double* state_dev, int32_t n, double step, double* frenet_dev, void* stream);
 
 /* -- batched, device-resident replay ------------------------------------------------

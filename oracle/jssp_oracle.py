@@ -2,7 +2,7 @@
 
 THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``, ``__graft_entry__.smoke()`` and
 ``bench.py``'s cpu-baseline / ``--impl reference`` legs may import it.  The product path
-(``dlii-jssp_b200``) never routes through this module and has no CPU fallback.
+(``dlii_jssp_b200``) never routes through this module and has no CPU fallback.
 
 What it restates (reference = byChenZhifa/DLII-JSSP, paths relative to the reference root):
 

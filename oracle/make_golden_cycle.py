@@ -118,7 +118,7 @@ def install_stubs():
 
         def from_state(self, state, polyline):
             """Builder-specified projection (the class is absent): nearest point of the re-discretised reference line, chord-length
-            arc sum, left-hand normal, speed / acceleration split by the heading error (dlii-jssp_b200/frenet.py states the same)."""
+            arc sum, left-hand normal, speed / acceleration split by the heading error (dlii_jssp_b200/frenet.py states the same)."""
             d2 = (polyline[:, 0] - state.x) ** 2 + (polyline[:, 1] - state.y) ** 2
             i = int(np.argmin(d2))
             seg = np.hypot(np.diff(polyline[:, 0]), np.diff(polyline[:, 1]))

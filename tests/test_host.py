@@ -125,7 +125,7 @@ def test_no_cpu_fallback():
     cfg = J.JsspConfig().to_c()
     assert _lib.load().jssp_create(C.byref(cfg), 0, C.byref(h)) == -6      # JSSP_ERR_NO_DEVICE
     # nothing under the product package imports the oracle
-    pkg = os.path.join(ROOT, "dlii-jssp_b200")
+    pkg = os.path.join(ROOT, "dlii_jssp_b200")
     for fn in os.listdir(pkg):
         if fn.endswith(".py"):
             assert not re.search(r"^\s*(from|import)\s+oracle", open(os.path.join(pkg, fn)).read(), re.M), fn

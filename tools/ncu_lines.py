@@ -15,7 +15,7 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "dlii-jssp_b200", "libjssp_b200.so")
+LIB = os.path.join(ROOT, "dlii_jssp_b200", "libjssp_b200.so")
 
 
 def main():
@@ -58,7 +58,7 @@ def main():
             continue
         f, l = key
         if f not in text:
-            p = os.path.join(ROOT, "dlii-jssp_b200", "csrc", f)
+            p = os.path.join(ROOT, "dlii_jssp_b200", "csrc", f)
             text[f] = open(p).read().split("\n") if os.path.exists(p) else []
         t = text[f][l - 1].strip()[:100] if l - 1 < len(text[f]) else ""
         print(f"{v / tot * 100:5.1f}% inst {samp[key] / ts * 100:5.1f}% samples  {f}:{l}  {t}")
