@@ -1,21 +1,29 @@
 #!/usr/bin/env python
 """bench.py - candidate-timesteps/s of the JSSP per-cycle candidate evaluation on B200 (contract: see DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3|C5|C4|C2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload all|C3|C5|C4|C2]
 
-A "step" is one plan cycle over one synthetic batch of candidates: the fused evaluation kernel (unroll -> Frenet->Cartesian
--> curvature feasibility -> rectangle collision against every obstacle mode -> cost -> argmin) plus the export of the
-selected trajectory.  Workload at N = 1: BASELINE.json configs[2] ("C3": 65,536 candidates x 50 steps x 32 obstacles x 3
-modes; configs[1] has no reference data - SURVEY.md section 0.5).  For N > 1 every rank evaluates an independent scenario
-of the same shape (rank-specific seed): the path shards over scenarios with no data-path collective ("weak").  With
---workload C5 the 1M-candidate cycle is split over the ranks and reduced with one NCCL all-gather of 16 B per rank.
+Default (--workload all), for every N: ONE JSON line whose top-level keys are the headline workload and which also carries the
+two sharded configurations the north star names:
 
-Prints ONE JSON line.  Timing: CUDA events on torch's current stream (the stream handed to the library), one event pair
-per step, L2 flushed (256 MiB write) between steps outside the event pairs, max over ranks.
+  headline  BASELINE configs[2] "C3": one synthetic dense plan cycle (65,536 candidates x 50 steps x 32 obstacles x 3 modes) per
+            rank - a "step" is one plan cycle: the fused evaluation kernel (unroll -> Frenet->Cartesian -> curvature feasibility ->
+            rectangle collision against every obstacle mode -> cost -> argmin) plus the export of the selected trajectory.  For
+            N > 1 every rank evaluates an independent scenario of that shape (no data-path collective, "weak").
+  "sweep"   BASELINE configs[3] "C4": the 800-scenario intersection replay sweep, scenario ids dealt over the N ranks (strong
+            scaling, no collective); a step is one complete sweep; `digest` hashes every scenario's (end, cycles, selected index
+            per cycle) and must be the same for every N.
+  "split"   BASELINE configs[4] "C5": one 1,048,576-candidate x 80-step x 64-obstacle x 3-mode cycle, contiguous seed ranges
+            per rank, the argmin exchange ON THE DEVICE inside the timed step (peer mailboxes over NVLink fused into the
+            evaluation launch, or one ncclAllGather of 16 B per rank); `best_idx` is the global selection, equal for every N.
+
+Timing: CUDA events on torch's current stream (the stream handed to the library), one event pair per step, L2 flushed (256 MiB
+write) between steps outside the event pairs, barrier + synchronize on both sides, max over ranks.
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import statistics
@@ -31,7 +39,7 @@ sys.path.insert(0, ROOT)
 # algorithmic work per candidate-timestep: F_base + F_sat * O * M / check_res
 F_BASE, F_SAT = 128.0, 48.0
 METRIC, UNIT = "candidate_timesteps_per_s", "candidate-timesteps/s"
-
+DTYPE = "f64 geometry + f32 collision"
 
 _WORKLOADS = {}
 
@@ -55,7 +63,7 @@ def workload_config(name, cyc, n_gpus):
     desc = {"C3": "synthetic dense plan cycle: 65,536 candidates x 50 steps x 32 obstacles x 3 intention modes (BASELINE configs[2])",
             "C5": "synthetic 1M-candidate x 80-step x 64-obstacle x 3-mode cycle split across the ranks (BASELINE configs[4])"}[name]
     return {"workload": desc, "candidates": cyc.n_candidates, "steps_per_candidate": int(cyc.plan_horizon / 0.1), "obstacles": O, "modes": M,
-            "parallelism": (f"{n_gpus} independent scenarios, no collective" if name == "C3" else f"candidate split x{n_gpus}, one 16 B/rank NCCL all-gather"),
+            "parallelism": (f"{n_gpus} independent scenarios, no collective" if name == "C3" else f"candidate split x{n_gpus}, device-side argmin exchange"),
             "l2": "flushed between steps (256 MiB write outside the event pairs)", "seed": 20251019 if name == "C3" else 20251020}
 
 
@@ -101,6 +109,11 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.005)
 
+    def finish(self):
+        self.stop_flag = True
+        self.join(timeout=1.0)
+        return self.summary()
+
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
@@ -108,6 +121,9 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# CPU legs (the only places that execute oracle/)
+# ------------------------------------------------------------------------------------------------------------------
 def oracle_inputs(cyc):
     from oracle import jssp_oracle as O
     cfg = O.OracleConfig(ego_length=cyc.ego_length, ego_width=cyc.ego_width, plan_horizon=cyc.plan_horizon)
@@ -142,7 +158,21 @@ def cpu_port_rate(name, cyc, n_sample, cores=1, pool=None):
     return len(idx) * P / dt, len(idx), dt
 
 
-# ------------------------------------------------------------------------------------------------------------------
+def cpu_vectorised_rate(name, cyc, n_seeds_sample):
+    """candidate-timesteps/s of the vectorised NumPy oracle (oracle/jssp_oracle.py) on an evenly spread seed sample x every lateral
+    target, 1 process: the fairer CPU figure SURVEY.md section 8d asks for next to the loop form."""
+    from oracle import jssp_oracle as O
+    cfg, spline, obs = oracle_inputs(cyc)
+    P = int(cyc.plan_horizon / 0.1) + 1
+    pick = np.unique(np.linspace(0, len(cyc.seeds) - 1, n_seeds_sample).astype(np.int64))
+    t0 = time.perf_counter()
+    with np.errstate(all="ignore"):
+        O.plan_cycle(cfg, spline, cyc.frenet0, obs, cyc.time_step_now, cyc.final_time_step, seeds=cyc.seeds[pick], targets=cyc.targets)
+    dt = time.perf_counter() - t0
+    n = len(pick) * len(cyc.targets)
+    return n * P / dt, n, dt
+
+
 def run_reference(args):
     """Reference arm: the reference's CPU evaluation path.  The reference itself cannot run (its `common` package is
     unpublished, shapely is absent), so this is the loop-form port (oracle/jssp_loop.py) on all host cores, each step a
@@ -152,30 +182,443 @@ def run_reference(args):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    cyc = workload(args.workload)
+    name = "C3" if args.workload == "all" else args.workload
+    cyc = workload(name)
     P = int(cyc.plan_horizon / 0.1) + 1
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        rate0, n0, _ = cpu_port_rate(args.workload, cyc, 16 * cores, cores, pool)        # calibration (+ worker warm-up)
+        rate0, n0, _ = cpu_port_rate(name, cyc, 16 * cores, cores, pool)        # calibration (+ worker warm-up)
         budget = 150.0 / max(args.steps + args.warmup, 1)
         n_sample = int(max(8 * cores, min(cyc.n_candidates, rate0 / P * budget)))
         for _ in range(args.warmup):
-            cpu_port_rate(args.workload, cyc, n_sample, cores, pool)
+            cpu_port_rate(name, cyc, n_sample, cores, pool)
         rates, times, used = [], [], 0
         for _ in range(args.steps):
-            r, used, dt = cpu_port_rate(args.workload, cyc, n_sample, cores, pool)
+            r, used, dt = cpu_port_rate(name, cyc, n_sample, cores, pool)
             rates.append(r); times.append(dt)
     value = used * P * len(times) / sum(times)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(args.workload, cyc, args.gpus),
+            "data": "synthetic", "config": workload_config(name, cyc, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{used} of {cyc.n_candidates} candidates per step (evenly spread), loop-form float64 port of the reference stages, "
-                                       f"SAT in place of shapely, {cores} processes"},
+                                       f"SAT in place of shapely, {cores} processes on {cores} host cores"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# helpers of the GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+class Ctx:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allmax(self, *vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        t = self.torch.tensor([float(v) for v in vals], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def allsum(self, *vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        t = self.torch.tensor([float(v) for v in vals], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
+    def timed(self, fn, steps, warmup):
+        """``warmup`` untimed + exactly ``steps`` timed calls of fn(), one CUDA-event pair per step, L2 flushed before each; returns the
+        per-step milliseconds of THIS rank."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for e0, e1 in evs:
+            self.flush.fill_(1)
+            e0.record()
+            fn()
+            e1.record()
+        self.barrier()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def measured_hbm_gbs():
+    """(GB/s, source) - HBM copy bandwidth of this pool's B200s from the driver-written MEASURED_PEAKS.json."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (driver-measured copy bandwidth)"
+    except Exception:
+        return 6544.3, "fallback: the figure MEASURED_PEAKS.json held in round 1 (file absent on this box)"
+
+
+def ncu_capture(kernel_substr: str, build_id: str):
+    """The committed ncu capture (profiles/r02_*_ncu.json, tools/ncu_summary.py) of the kernel whose name contains ``kernel_substr``
+    taken from a library with THIS build id, else None: counters are only ever attached to the code that produced them."""
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_*_ncu.json"))):
+        try:
+            d = json.load(open(path))
+        except Exception:
+            continue
+        if kernel_substr in d.get("kernel", "") and d.get("build_id") == build_id:
+            d["file"] = os.path.relpath(path, ROOT)
+            return d
+    return None
+
+
+def make_engine(J, cyc, n_seeds, local):
+    O, M, Tt = cyc.obstacles.shape
+    cfg = J.JsspConfig(plan_horizon=cyc.plan_horizon, ego_length=cyc.ego_length, ego_width=cyc.ego_width, max_seeds=n_seeds,
+                       max_obstacle_modes=O * M, max_total_steps=Tt, max_knots=max(1024, len(cyc.route_xy)))
+    eng = J.JsspEngine(cfg, device=local)
+    spline = J.CubicSpline2D(cyc.route_xy[:, 0], cyc.route_xy[:, 1])
+    eng.set_refline(spline.s_list, spline.coefficient_table())
+    o = cyc.obstacles
+    eng.set_obstacles(o.state, o.valid, o.size, o.prob, o.n_dict)
+    return eng
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# headline: C3, one dense plan cycle per rank
+# ------------------------------------------------------------------------------------------------------------------
+def bench_c3(ctx: Ctx, args) -> dict:
+    import ctypes as C
+    import dlii_jssp_b200 as J
+    from dlii_jssp_b200 import _lib
+    torch, world, rank, local, dev = ctx.torch, ctx.world, ctx.rank, ctx.local, ctx.dev
+    cyc = workload("C3", rank=rank)
+    P = int(cyc.plan_horizon / 0.1) + 1
+    O, M, Tt = cyc.obstacles.shape
+    o = cyc.obstacles
+    seeds_host = cyc.seeds
+    n_local = cyc.n_candidates
+    eng = make_engine(J, cyc, len(seeds_host), local)
+    seeds_pinned = torch.from_numpy(seeds_host).pin_memory()
+    seeds_dev = seeds_pinned.to(dev)
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    def step(export=True, select_only=False, states=False):
+        eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=seeds_dev, targets=cyc.targets, sync=False, export=export,
+                     select_only=select_only, want_states=states)
+
+    # (1) whole step, inputs resident in HBM
+    l0 = eng.launch_count
+    step_ms = ctx.timed(step, args.steps, args.warmup)
+    launches = (eng.launch_count - l0) * args.steps // (args.steps + args.warmup)       # launches inside the timed region
+    total_ms, = ctx.allmax(sum(step_ms))
+    units_all = n_local * world * P * args.steps
+    value = units_all / (total_ms * 1e-3)
+    res = eng.fetch()
+
+    # (1b) the same step without per-candidate outputs (select-only: a candidate's walk stops at its first veto, like the
+    #      reference's filter chain) - reported next to the headline, never instead of it
+    so_ms = ctx.timed(lambda: step(select_only=True), min(args.steps, 20), 3)
+    so_total, = ctx.allmax(sum(so_ms))
+    res_so = eng.fetch()
+    select_only = {"value": n_local * world * P * len(so_ms) / (so_total * 1e-3), "unit": UNIT, "ms_per_step": so_total / len(so_ms),
+                   "same_selection": bool(res_so.best_idx == res.best_idx),
+                   "note": "no masks / costs written: vetoed candidates stop early; selection and exported trajectory unchanged"}
+
+    # (2) dominant kernel alone (no export) for the roofline
+    k_ms = ctx.timed(lambda: step(export=False), args.steps, 3)
+    k_avg_s = 1e-3 * sum(k_ms) / len(k_ms)
+    flops = algorithmic_flops(cyc, n_local)
+    peak32, peak64 = C.c_double(0), C.c_double(0)
+    eng.lib.jssp_measure_fma_peak(local, 32, peak32)
+    eng.lib.jssp_measure_fma_peak(local, 64, peak64)
+    alg_bytes = n_local * 6 + len(seeds_host) * 80 + O * M * P * 16 + len(cyc.route_xy) * 72 + P * 48
+    build_id = eng.lib.jssp_build_id().decode()
+    cap = ncu_capture("evaluate", build_id)
+    kname = cap["kernel"] if cap else "evaluate kernel of the C3 cycle (name in the ncu capture)"
+    clocks_now = sampler.summary()
+    sm_hz = 1e6 * float(clocks_now.get("sm_mhz") or clocks_now.get("sm_max_mhz") or 1965.0)
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    issue_peak = sm_count * 4 * sm_hz / 1e9                      # warp instructions per ns: 4 schedulers per SM, one issue per cycle
+    roofline = {"bound": "issue", "kernel": kname, "unit": "Gwarp-inst/s", "peak": issue_peak,
+                "peak_source": f"{sm_count} SMs x 4 schedulers x {sm_hz / 1e6:.0f} MHz (SM clock sampled during the run): one warp instruction per scheduler "
+                               "and cycle; the kernel is bound by instruction issue / CUDA-core latency, not by HBM (see hbm) and not by tensor cores",
+                "kernel_ms": 1e3 * k_avg_s, "build_id": build_id}
+    if cap is not None:
+        inst = float(cap["warp_instructions"])
+        roofline.update({"achieved": inst / k_avg_s / 1e9, "frac": inst / k_avg_s / 1e9 / issue_peak, "traffic": cap.get("dram_traffic_bytes"),
+                         "warp_instructions_per_launch": inst,
+                         "capture": {k: cap.get(k) for k in ("file", "kernel", "build_id", "issue_active_pct", "pipe_fp64_pct", "pipe_fma_pct", "pipe_alu_pct",
+                                                             "pipe_lsu_pct", "warps_active_pct", "eligible_warps_per_cycle", "registers_per_thread", "duration_us")},
+                         "note": "frac = executed warp instructions per launch (ncu smsp__inst_executed.sum of THIS build, a constant of kernel + "
+                                 "workload) / live kernel time (CUDA events) / issue peak: the share of issue slots the kernel uses"})
+    else:
+        roofline.update({"achieved": None, "frac": None, "traffic": None,
+                         "note": f"no ncu capture of build {build_id} under profiles/ (a capture of other code is never attached): run tools/ncu_capture.sh"})
+    roofline["algorithmic"] = {"flops_per_launch": flops, "tflops": flops / k_avg_s / 1e12, "fp32_fma_peak_tflops": peak32.value,
+                               "fp64_fma_peak_tflops": peak64.value, "ratio_to_fp32_peak": flops / k_avg_s / 1e12 / peak32.value if peak32.value else None,
+                               "note": "SURVEY 8d's algorithmic count (128 + 48*O*M/2 flops per candidate-timestep) over the live kernel time, against the "
+                                       "FFMA peak measured live by a micro-benchmark in libjssp_b200 (builder-measured; MEASURED_PEAKS.json has no CUDA-core "
+                                       "figure).  NOT a utilisation: block-level culling skips almost all of the 48-flop rectangle tests, so the ratio can "
+                                       "exceed 1 - it is the algorithmic work avoided, the utilisation is roofline.frac"}
+    hbm_peak, hbm_src = measured_hbm_gbs()
+    roofline["hbm"] = {"algorithmic_bytes_per_launch": alg_bytes, "gbs": alg_bytes / k_avg_s / 1e9, "peak_gbs": hbm_peak, "frac": alg_bytes / k_avg_s / 1e9 / hbm_peak,
+                       "peak_source": hbm_src}
+
+    # (2b) dump mode: the same cycle with the per-candidate state dump [N, P, 8] fp32 (SURVEY 8d: the HBM-bound variant)
+    dump = None
+    if rank == 0:
+        step(states=True)
+        torch.cuda.synchronize()
+        l1 = eng.launch_count
+        d_ms = ctx_timed_local(ctx, lambda: step(export=False, states=True), min(args.steps, 20), 3)
+        dump_bytes = n_local * P * 32
+        d_s = 1e-3 * sum(d_ms) / len(d_ms)
+        extra_s = max(d_s - k_avg_s, 1e-9)
+        capd = ncu_capture("dump", build_id)
+        dump = {"bytes_per_launch": dump_bytes, "ms_per_step": 1e3 * d_s, "ms_dump_part": 1e3 * extra_s,
+                "gbs_whole_step": (dump_bytes + alg_bytes) / d_s / 1e9, "gbs_dump_part": dump_bytes / extra_s / 1e9, "peak_gbs": hbm_peak,
+                "frac_whole_step": (dump_bytes + alg_bytes) / d_s / 1e9 / hbm_peak, "frac_dump_part": dump_bytes / extra_s / 1e9 / hbm_peak,
+                "traffic": capd.get("dram_traffic_bytes") if capd else None, "capture": capd.get("file") if capd else None,
+                "launches_per_step": (eng.launch_count - l1) // (len(d_ms) + 3),
+                "note": "states_dev [N, 51, 8] fp32 = 1,632 B per candidate written to HBM; dump part = step with dump - step without; of measured HBM copy bandwidth"}
+        eng._states = None                   # release the 107 MB
+
+    # (3) end to end through the public API with host buffers: H2D of this cycle's seeds and obstacle predictions, evaluate,
+    #     D2H of the selected trajectory
+    h2d = seeds_host.nbytes + o.state.nbytes + o.valid.nbytes + o.size.nbytes + o.prob.nbytes
+    d2h = P * 16 * 8 + 40
+
+    def e2e_step():
+        sd = seeds_pinned.to(dev, non_blocking=True)
+        eng.set_obstacles(o.state, o.valid, o.size, o.prob, o.n_dict)
+        return eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=sd, targets=cyc.targets, sync=True)
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    ctx.barrier()
+    lat = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        e2e_step()
+        lat.append(time.perf_counter() - t0)
+    e2e_total, = ctx.allmax(sum(lat))
+    e2e_value = units_all / e2e_total
+    clocks = sampler.finish()
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": DTYPE, "data": "synthetic", "config": workload_config("C3", cyc, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "p50_cycle_ms": 1e3 * statistics.median(lat)},
+            "gpu_launches": int(launches), "clocks": clocks, "select_only": select_only, "roofline": roofline,
+            "selected": {"best_idx": res.best_idx, "best_cost": res.best_cost}, "build_id": build_id}
+    if dump is not None:
+        line["dump_mode"] = dump
+    eng.close()
+    return line
+
+
+def ctx_timed_local(ctx: Ctx, fn, steps, warmup):
+    """Like Ctx.timed but without the cross-rank barriers (legs only rank 0 runs)."""
+    torch = ctx.torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for e0, e1 in evs:
+        ctx.flush.fill_(1)
+        e0.record()
+        fn()
+        e1.record()
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# split: C5, one 1M-candidate cycle over the ranks, argmin exchange on the device
+# ------------------------------------------------------------------------------------------------------------------
+def bench_split(ctx: Ctx, args, transport="auto") -> dict:
+    import dlii_jssp_b200 as J
+    from dlii_jssp_b200 import distributed as D
+    torch, world, rank, local, dev = ctx.torch, ctx.world, ctx.rank, ctx.local, ctx.dev
+    cyc = workload("C5")
+    P = int(cyc.plan_horizon / 0.1) + 1
+    O, M, Tt = cyc.obstacles.shape
+    o = cyc.obstacles
+    Ns = len(cyc.seeds)
+    lo, hi = D.shard_range(Ns, world, rank)
+    seeds_host = np.ascontiguousarray(cyc.seeds[lo:hi])
+    eng = make_engine(J, cyc, max(len(seeds_host), 1), local)
+    split = D.CandidateSplit(eng, Ns, transport=transport)
+    seeds_pinned = torch.from_numpy(seeds_host).pin_memory()
+    seeds_dev = seeds_pinned.to(dev)
+    steps, warmup = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    def step():
+        eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=seeds_dev, targets=cyc.targets, sync=False)
+        split.exchange()
+
+    l0 = eng.launch_count
+    ms = ctx.timed(step, steps, warmup)
+    launches = (eng.launch_count - l0) // (steps + warmup)
+    total_ms, = ctx.allmax(sum(ms))
+    best_idx, best_cost, winner = split.fetch()
+    units = cyc.n_candidates * P * steps
+    # end to end: H2D of the rank's seeds + the obstacle predictions, evaluate, exchange, host wait for the global selection
+    h2d = seeds_host.nbytes + o.state.nbytes + o.valid.nbytes + o.size.nbytes + o.prob.nbytes
+    d2h = P * 16 * 8 + 40 + 48
+
+    def e2e_step():
+        sd = seeds_pinned.to(dev, non_blocking=True)
+        eng.set_obstacles(o.state, o.valid, o.size, o.prob, o.n_dict)
+        eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=sd, targets=cyc.targets, sync=False)
+        split.exchange()
+        return split.fetch()
+    for _ in range(3):
+        e2e_step()
+    ctx.barrier()
+    lat = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        e2e_step()
+        lat.append(time.perf_counter() - t0)
+    e2e_total, = ctx.allmax(sum(lat))
+    h2d_all, = ctx.allsum(h2d)
+    clocks = sampler.finish()
+    out = {"workload": workload_config("C5", cyc, world)["workload"], "ranks": world, "scaling": "strong", "steps": steps, "warmup": warmup,
+           "ms_per_step": total_ms / steps, "value": units / (total_ms * 1e-3), "unit": UNIT,
+           "e2e": {"value": units / e2e_total, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h * world),
+                   "p50_cycle_ms": 1e3 * statistics.median(lat)},
+           "best_idx": int(best_idx), "best_cost": best_cost, "winner_rank": int(winner), "digest": f"{int(best_idx)}:{best_cost!r}",
+           "exchange": {"local": "single rank: no exchange", "peer": "peer mailboxes over NVLink (CUDA IPC), fused into the evaluation launch: the "
+                        "finishing block pushes the 16 B record to every peer and one warp reduces the world's records",
+                        "nccl": "one ncclAllGather of 16 B per rank + one-warp reduction kernel, enqueued behind the evaluation"}[split.transport],
+           "transport": split.transport, "gpu_launches_per_step": int(launches), "candidates": cyc.n_candidates, "candidates_per_rank": len(seeds_host) * len(cyc.targets),
+           "clocks": clocks}
+    split.close()
+    eng.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# sweep: C4 (800-scenario replay sweep) / C2 (8-scene demo) over the ranks
+# ------------------------------------------------------------------------------------------------------------------
+def bench_sweep(ctx: Ctx, args, workload_name="C4") -> dict:
+    """BASELINE configs[3] ("C4": replay sweep over seeded synthetic intersections - the reference's scenes_all(800) archive is
+    absent) and configs[1] ("C2": the bundled scene + 7 seeded variants with M = 3 predicted intention modes per vehicle - the
+    reference's 8 demo scenes are 0-byte placeholders and it publishes no predictor).  Scenario ids are dealt round-robin to
+    the ranks; every rank replays its shard on the device (hand-off, clock and end status included); no data-path collective,
+    only the result rows are gathered.  A "step" is one complete sweep of the rank's shard (every scenario replayed for up to
+    --cycles plan cycles)."""
+    import ctypes as C
+    import dlii_jssp_b200 as J
+    from dlii_jssp_b200 import batch as B, distributed as D
+    torch, world, rank, local, dev = ctx.torch, ctx.world, ctx.rank, ctx.local, ctx.dev
+    c2 = workload_name == "C2"
+    n_scn = 8 if c2 else args.scenarios
+    ids = D.shard_scenarios(range(n_scn), world, rank)
+    kw = {}
+    if c2:
+        base = J.scenario.scenario_from_fixture(os.path.join(ROOT, "tests", "golden", "scenario_8_3_4_565.npz"))
+        scs = [J.scenario.perturbed_scenario(base, i) for i in ids]
+        packed = [B.pack_scenario(sc, max_cycles=args.cycles, predictions=J.scenario.multimodal_predictions(sc, M=3, seed=i)) for i, sc in zip(ids, scs)]
+        kw = dict(p_min=0.3, w_risk=1.0)
+    else:
+        packed = [B.pack_scenario(J.scenario.synthetic_intersection(i), max_cycles=args.cycles) for i in ids]   # packed before the clock starts
+    fop = None
+    if args.planner == "frenet":                 # FOP baseline planner (SURVEY section 8 f3) in the same batched replay: 3 x 10 x 250 candidates
+        fop = J.FrenetOptimalPlannerSettings.intended()
+        steps_fop = int(np.ceil(fop.max_t / fop.delta_t))
+        packed = [B.pack_scenario(J.scenario.synthetic_intersection(i), plan_steps=steps_fop, max_cycles=args.cycles) for i in ids]
+    pre_done = [(p.name, p.initial_end, 0, []) for p in packed if p.initial_end != -1]
+    packed = [p for p in packed if p.initial_end == -1]
+    e = packed[0].ego
+    cfg = J.JsspConfig(ego_length=float(e[5]), ego_width=float(e[6]), max_seeds=1024, max_knots=max(64, max(len(p.knot_s) for p in packed)),
+                       max_obstacle_modes=max(1, max(p.state.shape[0] * p.state.shape[1] for p in packed)),
+                       max_total_steps=max(p.state.shape[2] for p in packed), **kw)
+    pts = cfg.n_points
+    if fop is not None:
+        cfg = B.fop_batch_config(fop, float(e[5]), float(e[6]), max_seeds=1024, max_knots=cfg.max_knots, max_obstacle_modes=cfg.max_obstacle_modes,
+                                 max_total_steps=cfg.max_total_steps)
+        pts = float(np.mean([len(np.arange(0.0, T, fop.delta_t)) for T in np.linspace(fop.min_t, fop.max_t, fop.num_t)]))   # samples per candidate
+    k_sub = args.sub_batches if len(packed) >= 16 else 1
+    bt = B.MultiStreamReplay(cfg, device=local, max_scenarios=len(packed), max_cycles=args.cycles, k=k_sub, fop=fop)
+    bt.load(packed)
+    steps, warmup = max(3, min(args.steps, 10)), 3
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    def step():
+        bt.reset(); bt.run(args.cycles)
+    l0 = bt.launch_count
+    ms = ctx.timed(step, steps, warmup)
+    launches = (bt.launch_count - l0) // (steps + warmup)
+    total_ms = sum(ms)
+    results = bt.results()
+    units = sum(sum(r.n_candidates) for r in results) * pts
+    flops = sum(sum(r.n_candidates) * pts * (F_BASE + F_SAT * p.state.shape[0] * p.state.shape[1] / 2.0) for r, p in zip(results, packed))
+    cycles = sum(r.cycles for r in results)
+    # end to end: upload the packed scenarios from host memory, replay, fetch the per-cycle records
+    h2d = sum(sum(getattr(p, f).nbytes for f in ("knot_s", "coef", "state", "valid", "size", "prob", "cycle_time", "cycle_now", "cycle_end_step")) for p in packed)
+    d2h = len(packed) * (args.cycles * B.RECORD_DTYPE.itemsize + B.RESULT_DTYPE.itemsize)
+    lat = []
+    for _ in range(max(2, min(steps, 5))):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        bt.load(packed); bt.run(args.cycles); bt.results(lists=False)      # records on the host as NumPy views
+        lat.append(time.perf_counter() - t0)
+    e2e_s = statistics.median(lat)
+    clocks = sampler.finish()
+    units_all, cycles_all, n_all, flops_all, h2d_all, d2h_all = ctx.allsum(units, cycles, len(results) + len(pre_done), flops, h2d, d2h)
+    ms_max, e2e_max = ctx.allmax(total_ms, e2e_s)
+    rows = [(r.name, r.end, r.cycles, [int(b) for b in r.best_idx]) for r in results] + pre_done
+    parts = D.gather_results(rows)
+    out = None
+    if rank == 0:
+        ends = {}
+        allrows = [row for part in parts for row in part]
+        for _, en, _, _ in allrows:
+            ends[str(en)] = ends.get(str(en), 0) + 1
+        peak32 = C.c_double(0)
+        bt.lib.jssp_measure_fma_peak(local, 32, peak32)
+        sweep_s = 1e-3 * ms_max / steps
+        grid = "default grid" if fop is None else f"FOP baseline planner {fop.num_width} x {fop.num_t} x {fop.num_speed} candidates per cycle"
+        desc = (f"{int(n_all)}-scenario synthetic intersection replay sweep, {grid}, <= {args.cycles} cycles each (BASELINE configs[3]; reference data absent)"
+                if not c2 else f"{int(n_all)}-scene demo: 8_3_4_565 + seeded variants, JSSP + 3 predicted intention modes per vehicle, <= {args.cycles} cycles each "
+                               "(BASELINE configs[1]; the reference's demo scenes are empty files, its predictor is unpublished)")
+        out = {"workload": desc, "ranks": world, "scaling": "strong", "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * sweep_s,
+               "value": units_all / sweep_s, "unit": UNIT, "scenarios": int(n_all), "cycles_cap": args.cycles, "plan_cycles": int(cycles_all),
+               "e2e": {"value": units_all / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
+                       "sweep_ms": 1e3 * e2e_max},
+               "digest": D.sweep_digest(allrows), "end_status_counts": ends, "gpu_launches_per_step": int(launches),
+               "scenarios_per_s": n_all / sweep_s, "cycles_per_s": cycles_all / sweep_s, "amortised_cycle_us": 1e6 * sweep_s * world / max(cycles_all, 1),
+               "parallelism": f"scenario shards over {world} ranks ({bt.describe() if hasattr(bt, 'describe') else 'batched device-resident replay'}), no collective",
+               "algorithmic_tflops_per_gpu": flops_all / sweep_s / 1e12 / world, "fp32_fma_peak_tflops": peak32.value,
+               "clocks": clocks}
+    bt.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
 def replay_latency(device: int, cpu: bool = True) -> dict:
     """p50 plan-cycle latency (host call -> best trajectory on the host) on BASELINE configs[0]: the bundled scenario
     8_3_4_565 replayed through the reference-shaped interface (IntersectionPlanner.plan), default sampling grid.  The CPU
@@ -202,341 +645,62 @@ def replay_latency(device: int, cpu: bool = True) -> dict:
                 L.plan_cycle_loop(cfg, spline, fr, obs, now, final, seeds=seeds)
             lat.append(time.perf_counter() - t0)
         out["cpu_p50_ms"] = 1e3 * float(np.median(lat))
+        out["cpu_cores"] = 1
         out["cpu_note"] = "loop-form float64 port, 1 core, 3 representative cycles (seed enumeration vectorised)"
     return out
 
 
-def measured_hbm_gbs() -> float:
-    """HBM copy bandwidth of this pool's B200s from the driver-written MEASURED_PEAKS.json (fallback: the figure it held in round 1)."""
-    try:
-        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-    except Exception:
-        return 6544.3
+def cpu_baseline_block(args) -> dict:
+    cyc = workload("C3")
+    n_s = max(64, cyc.n_candidates // args.cpu_sample_div)
+    rate, used, dt = cpu_port_rate("C3", cyc, n_s, 1)
+    vrate, vused, vdt = cpu_vectorised_rate("C3", cyc, 2048)
+    return {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{used} of {cyc.n_candidates} candidates (evenly spread) in {dt:.1f} s; loop-form float64 port of the "
+                      "reference stages (oracle/jssp_loop.py), SAT in place of shapely, 1 process on 1 host core like the reference",
+            "vectorised": {"value": vrate, "unit": UNIT, "cores": 1,
+                           "sample": f"{vused} of {cyc.n_candidates} candidates in {vdt:.1f} s; vectorised NumPy oracle (oracle/jssp_oracle.py), 1 process"},
+            "host_cores_available": os.cpu_count(),
+            "note": "BASELINE.md holds the reference's own plan_traj timing next to both forms (1.9-2.6 s per default-grid cycle vs 0.65-0.79 s "
+                    "for this port vs 0.21-0.24 s vectorised, 1 core): the port is ~3x faster than the real reference loop"}
 
 
-def ncu_evidence(kernel_s=None) -> dict:
-    """Counters of the dominant kernel from the committed ncu capture (profiles/, `ncu --set full` of this very command):
-    evidence about the kernel measured under the profiler, never a bench value.  With ``kernel_s`` (the live kernel time)
-    the executed floating-point rate is expressed per second of the live run."""
-    path = os.path.join(ROOT, "profiles", "r01_evaluate_group_kernel_ncu.json")
-    if not os.path.exists(path):
-        return {}
-    d = json.load(open(path))
-    if kernel_s is None:
-        return d
-    out = {k: d.get(k) for k in ("issue_active_pct", "pipe_fp64_pct", "pipe_fma_pct", "pipe_alu_pct", "pipe_lsu_pct", "warps_active_pct",
-                                 "eligible_warps_per_cycle", "warp_instructions", "registers_per_thread")}
-    out["fp64_tflops"] = d.get("executed_fp64_flops", 0.0) / kernel_s / 1e12
-    out["fp32_tflops"] = d.get("executed_fp32_flops", 0.0) / kernel_s / 1e12
-    out["source"] = "profiles/r01_evaluate_group_kernel_ncu.json (ncu --set full, same command; counters under the profiler, rates over the live kernel time)"
-    out["reading"] = ("the kernel is issue/latency bound (about half of the issue slots used with 16 resident warps per SM at 128 registers); "
-                      "broad-phase culling removes almost all of the 48-flop rectangle tests that dominate the algorithmic count")
-    return out
-
-
-# ------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    import dlii_jssp_b200 as J
-    from dlii_jssp_b200 import distributed as D
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    split = args.workload == "C5"
-    cyc = workload(args.workload, rank=0 if split else rank)
-    P = int(cyc.plan_horizon / 0.1) + 1
-    O, M, Tt = cyc.obstacles.shape
-    W = len(cyc.targets)
-    seeds_all = cyc.seeds
-    if split:   # contiguous candidate ranges per rank = contiguous seed ranges for every width
-        per = len(seeds_all) // world
-        seeds_host = np.ascontiguousarray(seeds_all[rank * per:(rank + 1) * per])
-    else:
-        seeds_host = seeds_all
-    n_local = len(seeds_host) * W
-    cfg = J.JsspConfig(plan_horizon=cyc.plan_horizon, ego_length=cyc.ego_length, ego_width=cyc.ego_width, max_seeds=len(seeds_host),
-                       max_obstacle_modes=O * M, max_total_steps=Tt, max_knots=max(1024, len(cyc.route_xy)))
-    eng = J.JsspEngine(cfg, device=local)
-    spline = J.CubicSpline2D(cyc.route_xy[:, 0], cyc.route_xy[:, 1])
-    eng.set_refline(spline.s_list, spline.coefficient_table())
-    o = cyc.obstacles
-    eng.set_obstacles(o.state, o.valid, o.size, o.prob, o.n_dict)
-    seeds_pinned = torch.from_numpy(seeds_host).pin_memory()
-    seeds_dev = seeds_pinned.to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    sampler = ClockSampler(local)
-    sampler.start()
-
-    seed_lo = rank * (len(seeds_all) // world) if split else 0
-
-    def reduce_best():
-        """candidate-split exchange: per-rank winner (float64 cost bits, global index) -> one 16 B/rank NCCL all-gather"""
-        if not split:
-            return None
-        per = len(seeds_all) // world
-        return D.allgather_argmin(eng.best_record(), index_map=lambda r, i: D.global_candidate_index(i, r * per, per, len(seeds_all)))
-
-    def timed(steps, warmup, export, with_reduce=False, select_only=False):
-        for _ in range(warmup):
-            eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=seeds_dev, targets=cyc.targets, sync=False, export=export,
-                         select_only=select_only)
-            if with_reduce:
-                reduce_best()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        l0 = eng.launch_count
-        for e0, e1 in evs:
-            flush.fill_(1)
-            e0.record()
-            eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=seeds_dev, targets=cyc.targets, sync=False, export=export,
-                         select_only=select_only)
-            if with_reduce:
-                reduce_best()
-            e1.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms = [a.elapsed_time(b) for a, b in evs]
-        return ms, eng.launch_count - l0
-
-    # (1) whole step, inputs resident in HBM
-    step_ms, launches = timed(args.steps, args.warmup, export=True, with_reduce=split)
-    total_ms = sum(step_ms)
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    units_all = (cyc.n_candidates if split else n_local * world) * P * args.steps
-    value = units_all / (total_ms * 1e-3)
-    res = eng.fetch()
-
-    # (1b) the same step without per-candidate outputs (select-only: a candidate's walk stops at its first veto, like the
-    #      reference's filter chain) - reported next to the headline, never instead of it
-    so_ms, _ = timed(min(args.steps, 20), 3, export=True, with_reduce=split, select_only=True)
-    so_total = sum(so_ms)
-    if world > 1:
-        t = torch.tensor([so_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        so_total = float(t.item())
-    res_so = eng.fetch()
-    select_only = {"value": (cyc.n_candidates if split else n_local * world) * P * len(so_ms) / (so_total * 1e-3), "unit": UNIT,
-                   "ms_per_step": so_total / len(so_ms), "same_selection": bool(split or res_so.best_idx == res.best_idx),
-                   "note": "no masks / costs written: vetoed candidates stop early; selection and exported trajectory unchanged"}
-
-    # (2) dominant kernel alone (no export) for the roofline
-    k_ms, _ = timed(args.steps, 3, export=False)
-    k_avg_s = 1e-3 * sum(k_ms) / len(k_ms)
-    flops = algorithmic_flops(cyc, n_local)
-    peak32, peak64 = __import__("ctypes").c_double(0), __import__("ctypes").c_double(0)
-    eng.lib.jssp_measure_fma_peak(local, 32, peak32)
-    eng.lib.jssp_measure_fma_peak(local, 64, peak64)
-    achieved = flops / k_avg_s / 1e12
-    alg_bytes = n_local * 6 + len(seeds_host) * 80 + O * M * P * 16 + len(cyc.route_xy) * 72 + P * 48
-
-    # (3) end to end through the public API with host buffers: H2D of this cycle's seeds and obstacle predictions, evaluate,
-    #     D2H of the selected trajectory
-    h2d = seeds_host.nbytes + o.state.nbytes + o.valid.nbytes + o.size.nbytes + o.prob.nbytes
-    d2h = P * 16 * 8 + 40
-    def e2e_step():
-        sd = seeds_pinned.to(dev, non_blocking=True)
-        eng.set_obstacles(o.state, o.valid, o.size, o.prob, o.n_dict)
-        r = eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=sd, targets=cyc.targets, sync=not split)
-        if split:
-            reduce_best()
-            r = eng.fetch()
-        return r
-    for _ in range(max(args.warmup, 3)):
-        e2e_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    lat = []
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        e2e_step()
-        lat.append(time.perf_counter() - t0)
-    e2e_total = sum(lat)
-    if world > 1:
-        t = torch.tensor([e2e_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_total = float(t.item())
-    e2e_value = units_all / e2e_total
-    sampler.stop_flag = True
-    sampler.join(timeout=1.0)
-
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if split else "weak", "vs_baseline": None,
-                "dtype": "f64 geometry + f32 collision", "data": "synthetic", "config": workload_config(args.workload, cyc, world),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "p50_cycle_ms": 1e3 * statistics.median(lat)},
-                "gpu_launches": int(launches), "clocks": sampler.summary(), "select_only": select_only,
-                "roofline": {"bound": "fp32", "kernel": "evaluate_group_kernel", "achieved": achieved, "peak": peak32.value, "unit": "TFLOP/s",
-                             "frac": achieved / peak32.value if peak32.value else None, "traffic": ncu_evidence().get("dram_traffic_bytes"),
-                             "executed": ncu_evidence(k_avg_s),
-                             "frac_executed": (ncu_evidence().get("issue_active_pct") or 0.0) / 100.0 or None,
-                             "peak_source": "measured live: FFMA micro-benchmark in libjssp_b200 (MEASURED_PEAKS.json has no CUDA-core figure); "
-                                            "fp64 FMA peak %.1f TFLOP/s" % peak64.value,
-                             "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes,
-                             "kernel_ms": 1e3 * k_avg_s, "hbm_frac_of_measured": (alg_bytes / k_avg_s / 1e9) / measured_hbm_gbs(),
-                             "note": "achieved / frac follow the contract: algorithmic flops = (128 + 48*O*M/2) per candidate-timestep (SURVEY 8d) over "
-                                     "the live kernel time; broad-phase culling skips almost all of the 48-flop rectangle tests, so frac exceeds 1. "
-                                     "frac_executed is the bound that actually limits the kernel (SURVEY 8d asks for the ncu-measured utilisation): "
-                                     "the fraction of instruction-issue slots used, from the committed ncu capture; details in `executed`"},
-                "selected": {"best_idx": res.best_idx, "best_cost": res.best_cost}}
-        if world == 1:
-            line["plan_cycle"] = replay_latency(local, cpu=not args.no_cpu)
-        if world == 1 and not args.no_cpu:
-            n_s = max(64, cyc.n_candidates // args.cpu_sample_div)
-            rate, used, dt = cpu_port_rate(args.workload, cyc, n_s, 1)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": f"{used} of {cyc.n_candidates} candidates (evenly spread) in {dt:.1f} s; loop-form float64 port of the "
-                                              "reference stages (oracle/jssp_loop.py), SAT in place of shapely, 1 process like the reference"}
+    ctx = Ctx()
+    wl = args.workload
+    line = None
+    if wl in ("all", "C3"):
+        line = bench_c3(ctx, args)
+        if ctx.world == 1 and ctx.rank == 0:
+            line["plan_cycle"] = replay_latency(ctx.local, cpu=not args.no_cpu)
+            if not args.no_cpu:
+                line["cpu_baseline"] = cpu_baseline_block(args)
+    if wl == "all":
+        sweep = bench_sweep(ctx, args, "C4")
+        split = bench_split(ctx, args, args.transport)
+        if ctx.rank == 0:
+            line["sweep"], line["split"] = sweep, split
+            line["gpu_launches"] = int(line["gpu_launches"])
+            line["unpinned"] = ("parity unpinned (no reference code or tests exist): cubic spline / quintic / cost function / ego footprint / tie "
+                                "rule leaves, multi-modal collision semantics, IMM update (a13), Frenet projection formula (f4); see DESIGN.md section 2")
+    elif wl == "C5":
+        blk = bench_split(ctx, args, args.transport)
+        if ctx.rank == 0:
+            line = {"metric": METRIC, "value": blk["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": blk["steps"], "warmup": blk["warmup"],
+                    "ms_per_step": blk["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE,
+                    "data": "synthetic", "config": workload_config("C5", workload("C5"), ctx.world), "e2e": blk["e2e"],
+                    "gpu_launches": blk["gpu_launches_per_step"] * blk["steps"], "clocks": blk["clocks"], "split": blk}
+    elif wl in ("C4", "C2"):
+        blk = bench_sweep(ctx, args, wl)
+        if ctx.rank == 0:
+            line = {"metric": METRIC, "value": blk["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": blk["steps"], "warmup": blk["warmup"],
+                    "ms_per_step": blk["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE,
+                    "data": "synthetic", "config": {"workload": blk["workload"], "scenarios": blk["scenarios"], "cycles_cap": blk["cycles_cap"],
+                                                    "parallelism": blk["parallelism"], "l2": "flushed between sweeps (256 MiB write outside the event pairs)"},
+                    "e2e": blk["e2e"], "gpu_launches": blk["gpu_launches_per_step"] * blk["steps"], "clocks": blk["clocks"], "sweep": blk}
+    if ctx.rank == 0 and line is not None:
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-
-
-def run_sweep(args):
-    """BASELINE configs[3] ("C4": replay sweep over seeded synthetic intersections - the reference's scenes_all(800) archive is
-    absent) and configs[1] ("C2": the bundled scene + 7 seeded variants with M = 3 predicted intention modes per vehicle - the
-    reference's 8 demo scenes are 0-byte placeholders and it publishes no predictor).  Scenario ids are dealt round-robin to
-    the ranks; every rank replays its shard with the batched device-resident replay (all its scenarios advance in lock-step,
-    two kernel launches per step, hand-off on the device); no data-path collective, only the result rows are gathered.
-    A "step" is one complete sweep of the rank's shard (every scenario replayed for up to --cycles plan cycles)."""
-    import torch
-    import torch.distributed as dist
-    import dlii_jssp_b200 as J
-    from dlii_jssp_b200 import batch as B, distributed as D
-    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    c2 = args.workload == "C2"
-    n_scn = 8 if c2 else args.scenarios
-    ids = D.shard_scenarios(range(n_scn), world, rank)
-    kw = {}
-    if c2:
-        base = J.scenario.scenario_from_fixture(os.path.join(ROOT, "tests", "golden", "scenario_8_3_4_565.npz"))
-        scs = [J.scenario.perturbed_scenario(base, i) for i in ids]
-        packed = [B.pack_scenario(sc, max_cycles=args.cycles, predictions=J.scenario.multimodal_predictions(sc, M=3, seed=i)) for i, sc in zip(ids, scs)]
-        kw = dict(p_min=0.3, w_risk=1.0)
-    else:
-        packed = [B.pack_scenario(J.scenario.synthetic_intersection(i), max_cycles=args.cycles) for i in ids]   # packed before the clock starts
-    fop = None
-    if args.planner == "frenet":                 # FOP baseline planner (SURVEY section 8 f3) in the same batched replay: 3 x 10 x 250 candidates
-        fop = J.FrenetOptimalPlannerSettings.intended()
-        steps_fop = int(np.ceil(fop.max_t / fop.delta_t))
-        packed = [B.pack_scenario(J.scenario.synthetic_intersection(i), plan_steps=steps_fop, max_cycles=args.cycles) for i in ids]
-    packed = [p for p in packed if p.initial_end == -1]
-    e = packed[0].ego
-    cfg = J.JsspConfig(ego_length=float(e[5]), ego_width=float(e[6]), max_seeds=1024, max_knots=max(64, max(len(p.knot_s) for p in packed)),
-                       max_obstacle_modes=max(1, max(p.state.shape[0] * p.state.shape[1] for p in packed)),
-                       max_total_steps=max(p.state.shape[2] for p in packed), **kw)
-    pts = cfg.n_points
-    if fop is not None:
-        cfg = B.fop_batch_config(fop, float(e[5]), float(e[6]), max_seeds=1024, max_knots=cfg.max_knots, max_obstacle_modes=cfg.max_obstacle_modes,
-                                 max_total_steps=cfg.max_total_steps)
-        pts = float(np.mean([len(np.arange(0.0, T, fop.delta_t)) for T in np.linspace(fop.min_t, fop.max_t, fop.num_t)]))   # samples per candidate
-    # two sub-batches on two CUDA streams: the seed enumeration of one overlaps the evaluation of the other
-    k_sub = args.sub_batches if len(packed) >= 16 else 1
-    bt = B.MultiStreamReplay(cfg, device=local, max_scenarios=len(packed), max_cycles=args.cycles, k=k_sub, fop=fop)
-    bt.load(packed)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    sampler = ClockSampler(local)
-    sampler.start()
-    for _ in range(max(args.warmup, 1)):
-        bt.reset(); bt.run(args.cycles)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    l0 = bt.launch_count
-    for e0, e1 in evs:
-        flush.fill_(1)
-        e0.record()
-        bt.reset(); bt.run(args.cycles)
-        e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    launches = bt.launch_count - l0
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
-    results = bt.results()
-    units = sum(sum(r.n_candidates) for r in results) * pts
-    flops = sum(sum(r.n_candidates) * pts * (F_BASE + F_SAT * p.state.shape[0] * p.state.shape[1] / 2.0) for r, p in zip(results, packed))
-    cycles = sum(r.cycles for r in results)
-    # end to end: upload the packed scenarios from host memory, replay, fetch the per-cycle records
-    h2d = sum(sum(getattr(p, f).nbytes for f in ("knot_s", "coef", "state", "valid", "size", "prob", "cycle_time", "cycle_now", "cycle_end_step")) for p in packed)
-    d2h = len(packed) * (args.cycles * B.RECORD_DTYPE.itemsize + B.RESULT_DTYPE.itemsize)
-    lat = []
-    for _ in range(max(2, min(args.steps, 5))):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        bt.load(packed); bt.run(args.cycles); bt.results(lists=False)      # records on the host as NumPy views
-        lat.append(time.perf_counter() - t0)
-    e2e_s = statistics.median(lat)
-    sampler.stop_flag = True
-    sampler.join(timeout=1.0)
-    tot = torch.tensor([float(units), float(cycles), float(len(results)), float(flops), float(h2d), float(d2h)], dtype=torch.float64, device=dev)
-    tmax = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        rows = D.gather_results([(r.name, r.end, r.cycles) for r in results])
-    else:
-        rows = [[(r.name, r.end, r.cycles) for r in results]]
-    if rank == 0:
-        ms_max, e2e_max = [float(v) for v in tmax.tolist()]
-        units_all, cycles_all, n_all, flops_all, h2d_all, d2h_all = [float(v) for v in tot.tolist()]
-        ends = {}
-        for part in rows:
-            for _, en, _ in part:
-                ends[str(en)] = ends.get(str(en), 0) + 1
-        peak32 = __import__("ctypes").c_double(0)
-        bt.lib.jssp_measure_fma_peak(local, 32, peak32)
-        sweep_s = 1e-3 * ms_max / args.steps
-        grid = "default grid" if fop is None else f"FOP baseline planner {fop.num_width} x {fop.num_t} x {fop.num_speed} candidates per cycle"
-        desc = (f"{int(n_all)}-scenario synthetic intersection replay sweep, {grid}, <= {args.cycles} cycles each (BASELINE configs[3]; reference data absent)"
-                if not c2 else f"{int(n_all)}-scene demo: 8_3_4_565 + seeded variants, JSSP + 3 predicted intention modes per vehicle, <= {args.cycles} cycles each "
-                               "(BASELINE configs[1]; the reference's demo scenes are empty files, its predictor is unpublished)")
-        line = {"metric": METRIC, "value": units_all / sweep_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
-                "ms_per_step": 1e3 * sweep_s, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f64 geometry + f32 collision", "data": "synthetic",
-                "config": {"workload": desc, "scenarios": int(n_all), "cycles_cap": args.cycles,
-                           "parallelism": f"scenario shards over {world} ranks, batched device-resident replay per rank "
-                                          f"({k_sub} sub-batch(es) on separate streams), no collective",
-                           "l2": "flushed between sweeps (256 MiB write outside the event pairs)"},
-                "e2e": {"value": units_all / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
-                        "sweep_ms": 1e3 * e2e_max},
-                "gpu_launches": int(launches), "clocks": sampler.summary(),
-                "roofline": {"bound": "fp32", "kernel": "seed_enum_kernel + evaluate_batch_kernel (whole lock-step cycle)" if fop is None else
-                             "evaluate_fop_batch_kernel + fop_select_export_batch_kernel (whole lock-step cycle)",
-                             "achieved": flops_all / sweep_s / 1e12 / world, "peak": peak32.value, "unit": "TFLOP/s",
-                             "frac": (flops_all / sweep_s / 1e12 / world) / peak32.value if peak32.value else None, "traffic": None,
-                             "note": "per GPU; algorithmic flops of the evaluation only ((128 + 48*O*M/2) per candidate-timestep); the seed "
-                                     "enumeration's work is not counted, see profiles/ for the kernel shares"},
-                "scenarios_per_s": n_all / sweep_s, "cycles_per_s": cycles_all / sweep_s, "amortised_cycle_us": 1e6 * sweep_s * world / max(cycles_all, 1),
-                "end_status_counts": ends}
-        print(json.dumps(line))
-    bt.close()
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.close()
 
 
 def main():
@@ -545,20 +709,17 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C3", choices=["C3", "C5", "C4", "C2"])
+    ap.add_argument("--workload", default="all", choices=["all", "C3", "C5", "C4", "C2"])
     ap.add_argument("--scenarios", type=int, default=800, help="C4: number of synthetic scenarios in the sweep")
     ap.add_argument("--cycles", type=int, default=100, help="C4: plan cycles per scenario (upper bound)")
-    ap.add_argument("--sub-batches", type=int, default=2, help="C4/C2: sub-batches per rank, each on its own CUDA stream")
+    ap.add_argument("--sub-batches", type=int, default=2, help="C4/C2 lock-step replay: sub-batches per rank, each on its own CUDA stream")
     ap.add_argument("--planner", default="JSSP", choices=["JSSP", "frenet"], help="C4: planner of the replay (frenet = the FOP baseline)")
+    ap.add_argument("--transport", default="auto", choices=["auto", "peer", "nccl"], help="C5: argmin exchange transport")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--cpu-sample-div", type=int, default=32, help="cpu_baseline sample = candidates / this")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload in ("C4", "C2"):
-        if args.steps == 100 and args.warmup == 10:      # the defaults are sized for the single-cycle workloads
-            args.steps, args.warmup = 10, 3
-        run_sweep(args)
     else:
         run_ours(args)
 

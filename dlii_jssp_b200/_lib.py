@@ -115,6 +115,15 @@ SYMBOLS = {
     "jssp_evaluate": (C.c_int32, [C.c_void_p, C.POINTER(JsspCycleIn), C.c_void_p, C.POINTER(JsspCycleOut)]),
     "jssp_fetch_best": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(JsspCycleOut)]),
     "jssp_best_record_dev": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "jssp_set_split": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64]),
+    "jssp_nccl_unique_id": (C.c_int32, [C.c_void_p]),
+    "jssp_nccl_comm_create": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "jssp_nccl_comm_destroy": (C.c_int32, [C.c_void_p]),
+    "jssp_allreduce_argmin": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "jssp_peer_export": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "jssp_peer_connect": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "jssp_peer_disconnect": (C.c_int32, [C.c_void_p]),
+    "jssp_fetch_global_best": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "jssp_launch_count": (C.c_int64, [C.c_void_p]),
     "jssp_measure_fma_peak": (C.c_int32, [C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "jssp_imm_update": (C.c_int32, [C.c_void_p, C.POINTER(JsspImmParams)] + [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_void_p]),

@@ -276,7 +276,9 @@ class BatchReplay:
         """(results [S] structured array, records [S, C] structured array); synchronises."""
         res = np.zeros(self._n, dtype=RESULT_DTYPE)
         rec = np.zeros((self._n, self.C), dtype=RECORD_DTYPE)
-        self._check(self.lib.jssp_batch_fetch(self._h, self._n, res.ctypes.data, rec.ctypes.data, self.stream), "jssp_batch_fetch")
+        rc = self.lib.jssp_batch_fetch(self._h, self._n, res.ctypes.data, rec.ctypes.data, self.stream)
+        if rc != -5:       # JSSP_ERR_SEED_OVERFLOW: the results ARE filled in; the scenarios concerned carry res["seed_overflow"]
+            self._check(rc, "jssp_batch_fetch")
         return res, rec
 
     def best_traj(self, slot: int) -> np.ndarray:
@@ -298,7 +300,7 @@ class BatchReplay:
             rows = rows_all[s, :n]
             if not ok_all[s, :n].all():
                 rows = rows[ok_all[s, :n]]
-            rr = ReplayResult(p.name, ends[s], n)
+            rr = ReplayResult(p.name, ends[s], n, seed_overflow=bool(res["seed_overflow"][s]))
             if lists:
                 rr.best_idx, rr.n_candidates, rr.ego_rows = bi_all[s, :n].tolist(), nc_all[s, :n].tolist(), list(map(tuple, rows.tolist()))
             else:
@@ -379,10 +381,12 @@ def fop_batch_config(fop, ego_length: float, ego_width: float, **caps) -> JsspCo
 
 def run_batch(scenarios: Sequence, device: int = 0, max_cycles: Optional[int] = None, batch: Optional[BatchReplay] = None,
               kernel: Optional[str] = None, fop=None, max_accel: float = 8.0, max_jerk: float = 10.0,
-              ego_update_mode: str = "planner_expected_value") -> List[ReplayResult]:
+              ego_update_mode: str = "planner_expected_value", max_seeds: int = 1024) -> List[ReplayResult]:
     """Replay independent scenarios (ReplayScenario or PackedScenario) in lock-step on one GPU; same results as
     ``replay.run_sweep``.  Scenarios that are over before the first cycle are answered on the host.  ``fop`` (a
-    FrenetOptimalPlannerSettings) replays with the FOP baseline planner instead of JSSP."""
+    FrenetOptimalPlannerSettings) replays with the FOP baseline planner instead of JSSP.  ``max_seeds`` sizes the per-scenario
+    seed buffer of an auto-created batch; a scenario whose cycle enumerates more is flagged (``ReplayResult.seed_overflow``),
+    the others are unaffected."""
     plan_steps = 50 if fop is None else int(np.ceil(fop.max_t / fop.delta_t))
     packed = [s if isinstance(s, PackedScenario) else pack_scenario(s, plan_steps=plan_steps, max_cycles=max_cycles,
                                                                     kinematics=ego_update_mode == "kinematics") for s in scenarios]
@@ -393,7 +397,7 @@ def run_batch(scenarios: Sequence, device: int = 0, max_cycles: Optional[int] = 
         e = todo[0].ego
         need_c = max(min(p.n_cycles, max_cycles or p.n_cycles) for p in todo)
         if batch is None:
-            caps = dict(max_seeds=1024, max_knots=max(64, max(len(p.knot_s) for p in todo)),
+            caps = dict(max_seeds=int(max_seeds), max_knots=max(64, max(len(p.knot_s) for p in todo)),
                         max_obstacle_modes=max(1, max(p.state.shape[0] * p.state.shape[1] for p in todo)),
                         max_total_steps=max(p.state.shape[2] for p in todo))
             cfg = JsspConfig(ego_length=float(e[5]), ego_width=float(e[6]), **caps) if fop is None else fop_batch_config(fop, float(e[5]), float(e[6]), **caps)

@@ -10,6 +10,7 @@
 #include <vector>
 #include <algorithm>
 #include <limits>
+#include <dlfcn.h>
 
 #include "jssp_kernels.cuh"
 
@@ -97,6 +98,17 @@ struct jssp_handle {
   int* d_fop_int = nullptr;
   int fop_cap_t = 0, fop_cap_v = 0;
   unsigned long long* phase_ts = nullptr;   // profiling builds only
+  // candidate split over ranks (jssp_set_split / jssp_allreduce_argmin / jssp_peer_*)
+  long long split_seed_lo = 0, split_ns_global = 0;
+  SplitRecord* d_split_rec = nullptr;       // this rank's record
+  SplitRecord* d_split_table = nullptr;     // [SPLIT_MAX_WORLD] all-gather target (NCCL transport)
+  GlobalBest *h_gbest = nullptr, *d_gbest = nullptr;   // mapped pinned host memory
+  PeerSlot* d_mailbox = nullptr;            // [2][world] own mailbox (peer transport)
+  PeerView* d_peers = nullptr;              // device copy of the peer table
+  void* peer_ptr[SPLIT_MAX_WORLD] = {nullptr};   // mappings opened with cudaIpcOpenMemHandle
+  int peer_world = 0, peer_rank = 0;
+  bool peers_connected = false;
+  unsigned long long split_epoch = 0;
   char cuda_err[256] = {0};
 };
 
@@ -204,6 +216,8 @@ std::vector<double> default_targets(const jssp_config& c, int W) {
 }
 
 bool config_ok(const jssp_config* cfg) {
+  // int(T / dt) (time grid, polyvt_sampling.py:44) and round(T / dt) (lateral grid, jerk_space_sampling_planner.py:78) must agree
+  if (cfg->delta_t > 0 && (long)(cfg->plan_horizon / cfg->delta_t) != std::lround(cfg->plan_horizon / cfg->delta_t)) return false;
   return !(cfg->plan_horizon <= 0 || cfg->delta_t <= 0 || cfg->num_jerk < 4 || cfg->num_width < 1 || cfg->num_width > JSSP_MAX_WIDTHS ||
            cfg->check_res < 1 || cfg->max_seeds < 1 || cfg->max_knots < 2 || cfg->max_obstacle_modes < 0 || cfg->max_total_steps < 1);
 }
@@ -459,6 +473,12 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(cudaMalloc(&h->d_counts, 4 * sizeof(int)));
   CKC(cudaMemset(h->d_counts, 0, 4 * sizeof(int)));
   CKC(cudaMallocHost(&h->h_counts, 4 * sizeof(int)));
+  CKC(cudaMalloc(&h->d_split_rec, sizeof(SplitRecord)));
+  CKC(cudaMemset(h->d_split_rec, 0xff, sizeof(SplitRecord)));
+  CKC(cudaMalloc(&h->d_split_table, SPLIT_MAX_WORLD * sizeof(SplitRecord)));
+  CKC(cudaHostAlloc(&h->h_gbest, sizeof(GlobalBest), cudaHostAllocMapped));
+  memset(h->h_gbest, 0, sizeof(GlobalBest));
+  CKC(cudaHostGetDevicePointer((void**)&h->d_gbest, h->h_gbest, 0));
   h->seed_work = make_seed_work(h->grids, h->d_counts, h->d_seeds, cfg->max_seeds);
   h->seed_smem = seed_smem_bytes(h->seed_work);
   if (h->seed_smem > (size_t)h->max_smem_optin) return bail(JSSP_ERR_CAPACITY);
@@ -494,6 +514,10 @@ int32_t jssp_destroy(jssp_handle* h) {
   if (h->tables_ready) cudaEventDestroy(h->tables_ready);
   if (h->tables_free) cudaEventDestroy(h->tables_free);
   if (h->up_stream) cudaStreamDestroy(h->up_stream);
+  jssp_peer_disconnect(h);
+  if (h->d_split_rec) cudaFree(h->d_split_rec);
+  if (h->d_split_table) cudaFree(h->d_split_table);
+  if (h->h_gbest) cudaFreeHost(h->h_gbest);
   delete h;
   return JSSP_OK;
 }
@@ -728,6 +752,11 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   p.select_only = (!p.feasible && !p.collision && !p.cost) ? 1 : 0;    // nobody reads per-candidate results: walks may stop at the first veto
   p.blk_cost = h->d_blk_cost; p.blk_idx = h->d_blk_idx; p.ticket = h->d_ticket; p.best = h->d_best;
   p.best_traj = (in->flags & JSSP_FLAG_NO_EXPORT) ? nullptr : h->d_best_traj;
+  if (h->split_ns_global > 0) {           // candidate split: this launch covers seeds [seed_lo, seed_lo + n_seeds) of ns_global
+    if (!ext || h->split_seed_lo + in->n_seeds > h->split_ns_global) return JSSP_ERR_INVALID_ARG;
+    p.split_seed_lo = h->split_seed_lo; p.split_ns_global = h->split_ns_global; p.split_rec = h->d_split_rec;
+    if (h->peers_connected) { p.peers = h->d_peers; p.split_epoch = ++h->split_epoch; }
+  }
 #ifdef JSSP_PROFILE_PHASES
   p.phase_ts = h->phase_ts;
 #endif
@@ -792,6 +821,153 @@ int32_t jssp_best_record_dev(jssp_handle* h, int64_t index_offset, void* stream,
   best_record_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->d_best, (long long)index_offset, (unsigned long long*)record_dev);
   h->launches++;
   CK(cudaGetLastError());
+  return JSSP_OK;
+}
+
+
+// -- candidate split over ranks ----------------------------------------------------------------------------------------
+namespace {
+// NCCL is reached through dlopen of the library the process already uses (torch bundles libnccl.so.2): no link-time dependency.
+// Minimal declarations after nccl.h (ncclResult_t = int, ncclSuccess = 0, ncclUint64 = 5, ncclUniqueId = 128 opaque bytes).
+struct NcclApi {
+  struct Id128 { char b[128]; };      // ncclUniqueId, passed by value
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok() const { return lib && GetUniqueId && CommInitRank && CommDestroy && AllGather; }
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  if (api.lib) return api;
+  const char* env = getenv("JSSP_NCCL_LIB");
+  void* lib = env ? dlopen(env, RTLD_NOW | RTLD_GLOBAL) : nullptr;
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);      // already in the process (torch.distributed)
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW);
+  if (!lib) return api;
+  api.lib = lib;
+  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+  api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(lib, "ncclAllGather"));
+  api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+  return api;
+}
+}  // namespace
+
+int32_t jssp_nccl_unique_id(uint8_t id_out[128]) {
+  if (!id_out) return JSSP_ERR_INVALID_ARG;
+  NcclApi& n = nccl_api();
+  if (!n.ok()) return JSSP_ERR_NOT_READY;
+  return n.GetUniqueId(id_out) == 0 ? JSSP_OK : JSSP_ERR_CUDA;
+}
+
+int32_t jssp_nccl_comm_create(const uint8_t id[128], int32_t world, int32_t rank, int32_t device, void** comm_out) {
+  if (!id || !comm_out || world < 1 || world > SPLIT_MAX_WORLD || rank < 0 || rank >= world) return JSSP_ERR_INVALID_ARG;
+  NcclApi& n = nccl_api();
+  if (!n.ok()) return JSSP_ERR_NOT_READY;
+  if (cudaSetDevice(device) != cudaSuccess) return JSSP_ERR_NO_DEVICE;
+  NcclApi::Id128 uid;
+  memcpy(uid.b, id, 128);
+  void* comm = nullptr;
+  const int rc = n.CommInitRank(&comm, world, uid, rank);
+  if (rc != 0) { fprintf(stderr, "jssp_nccl_comm_create: %s\n", n.GetErrorString ? n.GetErrorString(rc) : "nccl error"); return JSSP_ERR_CUDA; }
+  *comm_out = comm;
+  return JSSP_OK;
+}
+
+int32_t jssp_nccl_comm_destroy(void* comm) {
+  if (!comm) return JSSP_OK;
+  NcclApi& n = nccl_api();
+  if (!n.ok()) return JSSP_ERR_NOT_READY;
+  return n.CommDestroy(comm) == 0 ? JSSP_OK : JSSP_ERR_CUDA;
+}
+
+int32_t jssp_set_split(jssp_handle* h, int64_t seed_lo, int64_t n_seeds_global) {
+  if (!h || seed_lo < 0 || n_seeds_global < 0 || seed_lo > n_seeds_global) return JSSP_ERR_INVALID_ARG;
+  h->split_seed_lo = seed_lo; h->split_ns_global = n_seeds_global;
+  return JSSP_OK;
+}
+
+int32_t jssp_allreduce_argmin(jssp_handle* h, void* nccl_comm, int32_t world, void* stream) {
+  if (!h || world < 1 || world > SPLIT_MAX_WORLD || (world > 1 && !nccl_comm)) return JSSP_ERR_INVALID_ARG;
+  if (!h->last_valid || h->split_ns_global <= 0) return JSSP_ERR_NOT_READY;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  const SplitRecord* table = h->d_split_rec;
+  if (world > 1) {
+    NcclApi& n = nccl_api();
+    if (!n.ok()) return JSSP_ERR_NOT_READY;
+    const int rc = n.AllGather(h->d_split_rec, h->d_split_table, 2, /*ncclUint64*/ 5, nccl_comm, st);
+    if (rc != 0) { snprintf(h->cuda_err, sizeof(h->cuda_err), "ncclAllGather: %s", n.GetErrorString ? n.GetErrorString(rc) : "nccl error"); return JSSP_ERR_CUDA; }
+    table = h->d_split_table;
+  }
+  split_reduce_kernel<<<1, 32, 0, st>>>(table, world, h->d_gbest);
+  h->launches++;
+  CK(cudaGetLastError());
+  return JSSP_OK;
+}
+
+int32_t jssp_fetch_global_best(jssp_handle* h, void* stream, int64_t* best_idx, double* best_cost, int32_t* winner_rank) {
+  if (!h) return JSSP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));      // GlobalBest lives in mapped pinned memory: nothing to copy
+  if (best_idx) *best_idx = h->h_gbest->idx;
+  if (best_cost) *best_cost = h->h_gbest->cost;
+  if (winner_rank) *winner_rank = h->h_gbest->rank;
+  if (h->h_gbest->timed_out) { snprintf(h->cuda_err, sizeof(h->cuda_err), "peer exchange: a rank's record did not arrive (epoch %llu)", h->h_gbest->epoch); return JSSP_ERR_NOT_READY; }
+  return JSSP_OK;
+}
+
+int32_t jssp_peer_export(jssp_handle* h, int32_t world, uint8_t handle_out[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!h || !handle_out || world < 1 || world > SPLIT_MAX_WORLD) return JSSP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(h->device));
+  jssp_peer_disconnect(h);
+  CK(cudaMalloc(&h->d_mailbox, (size_t)2 * world * sizeof(PeerSlot)));
+  CK(cudaMemset(h->d_mailbox, 0, (size_t)2 * world * sizeof(PeerSlot)));
+  CK(cudaDeviceSynchronize());
+  h->peer_world = world;
+  cudaIpcMemHandle_t ipc;
+  CK(cudaIpcGetMemHandle(&ipc, h->d_mailbox));
+  memcpy(handle_out, &ipc, 64);
+  return JSSP_OK;
+}
+
+int32_t jssp_peer_connect(jssp_handle* h, const uint8_t* handles, int32_t world, int32_t rank) {
+  if (!h || !handles || world != h->peer_world || rank < 0 || rank >= world || !h->d_mailbox) return JSSP_ERR_INVALID_ARG;
+  CK(cudaSetDevice(h->device));
+  PeerView pv{};
+  pv.world = world; pv.rank = rank; pv.out = h->d_gbest;
+  int khz = 0;
+  CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device));
+  pv.spin_budget = (long long)khz * 1000ll * 5ll;                      // ~5 s of SM clocks, then the exchange reports a time-out
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { pv.box[r] = h->d_mailbox; continue; }
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, handles + (size_t)r * 64, 64);
+    void* ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_ptr[r] = ptr;
+    pv.box[r] = reinterpret_cast<PeerSlot*>(ptr);
+  }
+  if (!h->d_peers) CK(cudaMalloc(&h->d_peers, sizeof(PeerView)));
+  CK(cudaMemcpy(h->d_peers, &pv, sizeof(pv), cudaMemcpyHostToDevice));
+  h->peer_rank = rank; h->peers_connected = true; h->split_epoch = 0;
+  return JSSP_OK;
+}
+
+int32_t jssp_peer_disconnect(jssp_handle* h) {
+  if (!h) return JSSP_OK;
+  cudaSetDevice(h->device);
+  if (h->peers_connected || h->d_mailbox) cudaDeviceSynchronize();
+  for (int r = 0; r < SPLIT_MAX_WORLD; ++r) if (h->peer_ptr[r]) { cudaIpcCloseMemHandle(h->peer_ptr[r]); h->peer_ptr[r] = nullptr; }
+  if (h->d_mailbox) { cudaFree(h->d_mailbox); h->d_mailbox = nullptr; }
+  if (h->d_peers) { cudaFree(h->d_peers); h->d_peers = nullptr; }
+  h->peers_connected = false; h->peer_world = 0;
   return JSSP_OK;
 }
 

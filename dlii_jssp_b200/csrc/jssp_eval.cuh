@@ -2,6 +2,7 @@
 #pragma once
 #include "jssp_common.cuh"
 #include "jssp_seed.cuh"
+#include "jssp_split.cuh"
 
 namespace jssp {
 
@@ -47,6 +48,12 @@ struct EvalParams {
   unsigned int* ticket;
   BestRecord* best;
   double* best_traj;              // [P][16] export of the selected trajectory (NULL = skip)
+  // candidate split over ranks (jssp_set_split; 0 / NULL = off): this launch holds seeds [split_seed_lo, +n_seeds) of
+  // split_ns_global; the record of the selection carries the GLOBAL candidate index w * split_ns_global + split_seed_lo + k
+  long long split_seed_lo, split_ns_global;
+  SplitRecord* split_rec;         // NCCL transport: the rank's record, all-gathered by jssp_allreduce_argmin
+  const PeerView* peers;          // peer-mailbox transport: exchange inside this launch (epoch = split_epoch)
+  unsigned long long split_epoch;
   // batched replay (NULL / unused for a single plan cycle)
 #ifdef JSSP_PROFILE_PHASES
   unsigned long long* phase_ts;   // [blocks][8] globaltimer stamps (tools/phase_probe.py; profiling builds only)
@@ -972,17 +979,34 @@ __device__ __forceinline__ void select_and_export(const EvalParams& p, unsigned 
     *p.best = r;
     *p.ticket = 0u;   // re-arm for the next launch (stream-ordered)
     red_idx[0] = my_idx;
+    red_cost[0] = my_cost;
   }
-  // the same block exports the winner: no second launch, no host round trip in between
-  if (p.best_traj == nullptr) return;
   __syncthreads();
   const int best = red_idx[0];
-  PHASE(p, 5);
-  if (best >= 0) {
-    if (!staged) stage_tables<kMode>(p, smem, tb, latcost);
-    export_block(p, tb, best, p.best_traj, sm_npts_p);
+  // candidate split: the rank's record with the GLOBAL candidate index - pushed to the peers' mailboxes right away (their
+  // wait overlaps this block's export) and / or left in device memory for the NCCL all-gather
+  const bool split = p.split_ns_global > 0;
+  unsigned long long skey = 0xffffffffffffffffull, sidx = 0xffffffffffffffffull;
+  if (split && threadIdx.x < 32) {
+    if (best >= 0) {
+      const long long w = best / Ns, k = best - w * Ns;
+      skey = orderable_bits(red_cost[0]);
+      sidx = (unsigned long long)(w * p.split_ns_global + p.split_seed_lo + k);
+    }
+    if (threadIdx.x == 0 && p.split_rec) { p.split_rec->key = skey; p.split_rec->idx = sidx; }
+    if (p.peers) split_push_peers(*p.peers, p.split_epoch, skey, sidx);
   }
-  PHASE(p, 6);
+  // the same block exports the winner: no second launch, no host round trip in between
+  if (p.best_traj != nullptr) {
+    PHASE(p, 5);
+    if (best >= 0) {
+      if (!staged) stage_tables<kMode>(p, smem, tb, latcost);
+      export_block(p, tb, best, p.best_traj, sm_npts_p);
+    }
+    PHASE(p, 6);
+  }
+  if (split && p.peers && threadIdx.x < 32) split_wait_peers(*p.peers, p.split_epoch);
+  if (p.best_traj == nullptr) return;
   if (p.batch) batch_handoff(p, best, N, sm_npts_p);
 }
 

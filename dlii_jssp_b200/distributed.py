@@ -10,7 +10,11 @@ Two natural shardings exist and nothing else:
   cost and a 32-bit index do not fit one 64-bit key; ``min_reduce_packed`` is the single u64 min-reduce the north star
   names, exact whenever the fp32-rounded costs of the rank winners differ (it falls back to the lowest index otherwise).
 
-Everything here works on CPU tensors with the gloo backend too, which is how the tests cover world_size 2 without GPUs.
+The candidate-split exchange itself runs on the device (``CandidateSplit``): either the evaluation kernel's last block pushes
+the rank's record into every peer's mailbox over NVLink and reduces the world's records in the same launch, or one
+``ncclAllGather`` of the records is enqueued behind the kernel (``jssp_allreduce_argmin``) - no ``.cpu()``, no Python loop inside
+a timed step.  ``allgather_argmin`` / ``min_reduce_packed`` are the host-side forms of the same reduction; they work on CPU
+tensors with the gloo backend, which is how the tests cover world_size 2 without GPUs.
 """
 from __future__ import annotations
 
@@ -53,6 +57,121 @@ def localize_record(rec: torch.Tensor, seed_lo: int, n_seeds_local: int, n_seeds
     g = w * n_seeds_global + seed_lo + (idx - w * n_seeds_local)
     out[1] = torch.where(idx < 0, idx, g)
     return out
+
+
+def gather_bytes(payload: bytes, device=None, group=None) -> List[bytes]:
+    """All-gather one fixed-size byte string per rank (CUDA IPC handles, ...) through torch.distributed: a uint8 tensor on
+    ``device`` (cuda for the nccl backend, cpu for gloo)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return [payload]
+    mine = torch.tensor(list(payload), dtype=torch.uint8, device=device)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    return [bytes(t.cpu().tolist()) for t in out]
+
+
+def broadcast_bytes(payload: Optional[bytes], n: int, src: int = 0, device=None, group=None) -> bytes:
+    """Broadcast ``n`` bytes from rank ``src`` (the NCCL unique id)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return payload
+    t = torch.tensor(list(payload) if dist.get_rank(group) == src else [0] * n, dtype=torch.uint8, device=device)
+    dist.broadcast(t, src=src, group=group)
+    return bytes(t.cpu().tolist())
+
+
+def sweep_digest(rows) -> str:
+    """Order-independent digest of a scenario sweep: rows = (name, end, cycles, best_idx list) per scenario.  Equal for every
+    number of ranks iff every scenario was replayed identically (bench.py prints it for every --gpus N)."""
+    import hashlib
+    h = hashlib.sha256()
+    for name, end, cycles, best in sorted((str(r[0]), float(r[1]), int(r[2]), tuple(int(b) for b in r[3])) for r in rows):
+        h.update(repr((name, end, cycles, best)).encode())
+    return h.hexdigest()[:16]
+
+
+def _loaded_nccl_path() -> Optional[str]:
+    """Path of the libnccl the process has already mapped (torch's bundled one), for the library's dlopen."""
+    try:
+        for line in open("/proc/self/maps"):
+            if "libnccl.so" in line:
+                return line.split()[-1]
+    except OSError:
+        pass
+    return None
+
+
+class CandidateSplit:
+    """Device-side exchange of a candidate-split cycle (BASELINE configs[4]) for one JsspEngine: rank r evaluates seeds
+    ``shard_range(n_seeds_global, world, r)`` for every lateral target, and the selection over all ranks is taken on the device.
+
+    transport "peer": CUDA-IPC mailboxes over NVLink, exchange fused into the evaluation launch (default when the peers can
+    map each other's memory); "nccl": one ncclAllGather of 16 bytes per rank behind the kernel (the library's own communicator
+    from a unique id broadcast here).  ``exchange()`` enqueues what the transport needs after an ``evaluate(..., sync=False)``;
+    ``fetch()`` waits and returns (global best index, cost, winner rank) - the same triple on every rank."""
+
+    def __init__(self, engine, n_seeds_global: int, transport: str = "auto", group=None):
+        import os
+        self.eng, self.group = engine, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_seeds_global = int(n_seeds_global)
+        self.lo, self.hi = shard_range(self.n_seeds_global, self.world, self.rank)
+        engine.set_split(self.lo, self.n_seeds_global)
+        self.comm = None
+        self.transport = "local"
+        if self.world == 1:
+            return
+        dev = engine.device
+        if transport in ("auto", "peer"):
+            ok = 1
+            try:
+                handles = gather_bytes(engine.peer_export(self.world), device=dev, group=group)
+                engine.peer_connect(b"".join(handles), self.world, self.rank)
+            except Exception as e:           # a box whose GPUs cannot map each other: fall back to NCCL on EVERY rank
+                ok, self.peer_error = 0, repr(e)
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 1:
+                self.transport = "peer"
+                return
+            engine.peer_disconnect()
+            if transport == "peer":
+                raise RuntimeError("peer mailboxes unavailable: " + getattr(self, "peer_error", "a peer failed"))
+        path = _loaded_nccl_path()
+        if path and not os.environ.get("JSSP_NCCL_LIB"):
+            os.environ["JSSP_NCCL_LIB"] = path
+        import ctypes as C
+        uid = (C.c_uint8 * 128)()
+        if self.rank == 0:
+            engine._check(engine.lib.jssp_nccl_unique_id(uid), "jssp_nccl_unique_id")
+        raw = broadcast_bytes(bytes(uid), 128, 0, device=dev, group=group)
+        comm = C.c_void_p()
+        engine._check(engine.lib.jssp_nccl_comm_create((C.c_uint8 * 128).from_buffer_copy(raw), self.world, self.rank, dev.index, C.byref(comm)),
+                      "jssp_nccl_comm_create")
+        self.comm, self.transport = comm, "nccl"
+
+    def local_seeds(self, seeds):
+        """This rank's rows of the global seed table."""
+        return seeds[self.lo:self.hi]
+
+    def exchange(self):
+        """Enqueue the exchange behind the evaluation just enqueued on the engine's stream (nothing to do for the peer
+        transport: the evaluation launch already contains it)."""
+        if self.transport == "peer":
+            return
+        self.eng.allreduce_argmin(self.comm, self.world)
+
+    def fetch(self):
+        return self.eng.fetch_global_best()
+
+    def close(self):
+        if self.transport == "peer":
+            self.eng.peer_disconnect()
+        if self.comm is not None:
+            self.eng.lib.jssp_nccl_comm_destroy(self.comm)
+            self.comm = None
+        self.eng.set_split(0, 0)
 
 
 def _u64_less(a_cost: int, a_idx: int, b_cost: int, b_idx: int) -> bool:

@@ -45,7 +45,13 @@ class JsspConfig:
 
     @property
     def n_points(self) -> int:
-        return int(self.plan_horizon / self.delta_t) + 1
+        """Samples per trajectory.  The reference uses int(T / dt) + 1 for the time grid (polyvt_sampling.py:44) and
+        round(T / dt) + 1 for the lateral grid (jerk_space_sampling_planner.py:78-79); pairs where the two disagree (0.3 / 0.1 ->
+        2 vs 3) are rejected here and by jssp_create (JSSP_ERR_INVALID_ARG) instead of silently losing a sample."""
+        n = int(self.plan_horizon / self.delta_t)
+        if n != int(round(self.plan_horizon / self.delta_t)):
+            raise ValueError(f"plan_horizon / delta_t = {self.plan_horizon} / {self.delta_t} truncates and rounds to different step counts")
+        return n + 1
 
     def to_c(self) -> JsspConfigC:
         c = JsspConfigC()
@@ -109,6 +115,8 @@ class JsspEngine:
         self.feasible = torch.zeros(self._cap, dtype=torch.uint8, device=self.device)
         self.collision = torch.zeros(self._cap, dtype=torch.uint8, device=self.device)
         self.cost = torch.zeros(self._cap, dtype=torch.float32, device=self.device)
+        if getattr(self, "_pc_out", None) is not None:      # plan_cycle's persistent struct points into the old tensors
+            self._pc_out.best_traj_host = None
 
     def _check(self, rc: int, where: str):
         if rc != 0:
@@ -270,6 +278,35 @@ class JsspEngine:
         rec = torch.empty(2, dtype=torch.int64, device=self.device)
         self._check(self.lib.jssp_best_record_dev(self._h, int(index_offset), self.stream, rec.data_ptr()), "jssp_best_record_dev")
         return rec
+
+    # -- candidate split over ranks (jssp_set_split / jssp_allreduce_argmin / jssp_peer_*) ------------------------------------
+    def set_split(self, seed_lo: int, n_seeds_global: int):
+        """The external seeds of the following evaluate() calls are rows [seed_lo, seed_lo + n) of a cycle with
+        ``n_seeds_global`` seeds: the selection record then carries the GLOBAL candidate index.  (0, 0) switches it off."""
+        self._check(self.lib.jssp_set_split(self._h, int(seed_lo), int(n_seeds_global)), "jssp_set_split")
+
+    def allreduce_argmin(self, nccl_comm: Optional[int], world: int):
+        """NCCL transport: enqueue the all-gather of the 16-byte records + the one-warp lexicographic minimum (asynchronous)."""
+        self._check(self.lib.jssp_allreduce_argmin(self._h, nccl_comm, int(world), self.stream), "jssp_allreduce_argmin")
+
+    def peer_export(self, world: int) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self._check(self.lib.jssp_peer_export(self._h, int(world), buf), "jssp_peer_export")
+        return bytes(buf)
+
+    def peer_connect(self, handles: bytes, world: int, rank: int):
+        assert len(handles) == 64 * world
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        self._check(self.lib.jssp_peer_connect(self._h, buf, int(world), int(rank)), "jssp_peer_connect")
+
+    def peer_disconnect(self):
+        self.lib.jssp_peer_disconnect(self._h)
+
+    def fetch_global_best(self):
+        """(global best index or -1, its float64 cost, rank holding it); synchronises the stream."""
+        i, c, r = C.c_int64(-1), C.c_double(0.0), C.c_int32(0)
+        self._check(self.lib.jssp_fetch_global_best(self._h, self.stream, C.byref(i), C.byref(c), C.byref(r)), "jssp_fetch_global_best")
+        return i.value, c.value, r.value
 
     def evaluate_fop(self, frenet0, time_step_now: int, final_time_step: int, num_width: int, num_speed: int, num_t: int, min_t: float,
                      max_t: float, lowest_speed: float, highest_speed: float, max_accel: float, max_jerk: float,

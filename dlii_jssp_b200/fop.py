@@ -81,20 +81,25 @@ class FrenetOptimalPlanner(object):
         return self._cubic_spline, self._cubic_spline.sample(s)
 
     def _set_obstacles(self, obstacles, dt: float, final_time_step: int):
+        # cache by object identity (strong reference + ``is``) and length / version, like JerkSpaceSamplingPlanner.set_obstacles
         if isinstance(obstacles, ObstacleTensors):
-            key, t = ("tensors", id(obstacles)), obstacles
+            key, t = ("tensors", getattr(obstacles, "version", 0), 0), obstacles
         else:
             n_total = final_time_step + int(np.ceil(self.settings.max_t / self.settings.delta_t)) + 2
-            key = ("dict", id(obstacles), len(obstacles) if obstacles is not None else 0, n_total)
+            key = ("dict", len(obstacles) if obstacles is not None else 0, n_total)
             t = None
-        if key != self._obstacle_key:
-            t = t if t is not None else pack_obstacle_dict(obstacles, dt, key[3])
+        if getattr(self, "_obstacle_ref", None) is not obstacles or key != self._obstacle_key or obstacles is None:
+            t = t if t is not None else pack_obstacle_dict(obstacles, dt, key[2])
             self.engine.set_obstacles(t.state, t.valid, t.size, t.prob, t.n_dict)
-            self._obstacle_key = key
+            self._obstacle_key, self._obstacle_ref = key, obstacles
+
+    def invalidate_obstacles(self):
+        self._obstacle_key = self._obstacle_ref = None
 
     def reset(self):
         """Forget the previous scenario (reference line, obstacles, best trajectory); the device workspace is kept."""
         self.best_traj, self.all_trajs, self._cubic_spline, self._obstacle_key, self.last_result = None, [], None, None, None
+        self._obstacle_ref = None
 
     def plan_traj(self, frenet_state: FrenetState, ego_state: State, obstacles, observation) -> Optional[GoalSamplingFrenetTrajectory]:
         """Same contract as frenet_optimal_planner.py:301-360 (without the plotting side effects)."""

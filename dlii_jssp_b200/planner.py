@@ -90,7 +90,7 @@ class JerkSpaceSamplingPlanner(object):
             max_total_steps=max_total_steps)
         self.engine = JsspEngine(cfg, device=device)
         self._cubic_spline = None
-        self._obstacle_key = None
+        self._obstacle_key = self._obstacle_ref = None
         self.last_result = None            # jssp_cycle_out of the last cycle (n_candidates, n_seeds, best_idx, best_cost, best_n_pts)
 
     # -- reference line -------------------------------------------------------------------------------------------
@@ -115,19 +115,26 @@ class JerkSpaceSamplingPlanner(object):
 
     # -- obstacles ------------------------------------------------------------------------------------------------
     def set_obstacles(self, obstacles, dt: float, final_time_step: int):
-        """``obstacles`` is the OnSite dictionary (packed once per scenario and cached by identity) or ObstacleTensors
-        (multi-modal predictions)."""
+        """``obstacles`` is the OnSite dictionary (packed once per scenario and cached) or ObstacleTensors (multi-modal
+        predictions).  The cache holds a strong reference to the object it packed and compares with ``is`` (an ``id()`` alone
+        can be recycled by a fresh temporary), plus the dictionary's length / the tensors' ``version``.  An object mutated IN
+        PLACE between cycles (per-cycle IMM updates) must either bump ``ObstacleTensors.version`` or be followed by
+        ``invalidate_obstacles()``; otherwise the device keeps the tables of the previous contents."""
         if isinstance(obstacles, ObstacleTensors):
-            key = ("tensors", id(obstacles))
-            if key != self._obstacle_key:
+            key = ("tensors", getattr(obstacles, "version", 0))
+            if self._obstacle_ref is not obstacles or key != self._obstacle_key:
                 self.engine.set_obstacles(obstacles.state, obstacles.valid, obstacles.size, obstacles.prob, obstacles.n_dict)
         else:
             n_total = final_time_step + self.time_step_max + 2
-            key = ("dict", id(obstacles), len(obstacles) if obstacles is not None else 0, n_total)
-            if key != self._obstacle_key:
+            key = ("dict", len(obstacles) if obstacles is not None else 0, n_total)
+            if self._obstacle_ref is not obstacles or key != self._obstacle_key or obstacles is None:
                 t = pack_obstacle_dict(obstacles, dt, n_total)
                 self.engine.set_obstacles(t.state, t.valid, t.size, t.prob, t.n_dict)
-        self._obstacle_key = key
+        self._obstacle_key, self._obstacle_ref = key, obstacles
+
+    def invalidate_obstacles(self):
+        """Forget the cached obstacle tables: the next plan_traj packs and uploads ``obstacles`` again."""
+        self._obstacle_key = self._obstacle_ref = None
 
     # -- one plan cycle ---------------------------------------------------------------------------------------------
     def sampling_frenet_trajectories(self, frenet_state: FrenetState, obstacles=None, time_step_now=None, observation=None) -> int:
@@ -170,7 +177,7 @@ class JerkSpaceSamplingPlanner(object):
         self.best_traj = None
         self.all_trajs, self.all_path_sampling_trajs = [], []
         self._cubic_spline = None
-        self._obstacle_key = None
+        self._obstacle_key = self._obstacle_ref = None
         self.last_result = None
 
     def count_passed(self) -> int:

@@ -33,6 +33,7 @@ class ReplayResult:
     n_candidates: List[int] = field(default_factory=list)
     ego_rows: List[tuple] = field(default_factory=list)      # per step after the cycle: (t, x, y, v, a, yaw) - the Recorder's ego columns
     plan_seconds: List[float] = field(default_factory=list)
+    seed_overflow: bool = False      # batched replay: some cycle of THIS scenario enumerated more than max_seeds seeds (surplus dropped)
 
     @property
     def p50_ms(self) -> float:

@@ -25,6 +25,7 @@ class ObstacleTensors:
     prob: np.ndarray      # [O, M]        float64  intention probability of each mode
     n_dict: int           # len(obstacles) as seen by has_collision's early-out (jerk_space_sampling_planner.py:241)
     ids: list = field(default_factory=list)
+    version: int = 0      # bump after mutating the arrays in place: the planners' table cache keys on (object, version)
 
     @property
     def shape(self):

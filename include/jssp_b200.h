@@ -180,6 +180,35 @@ int32_t jssp_fetch_best(jssp_handle* h, void* stream, jssp_cycle_out* out);
  * the float64 cost (unsigned order == numeric order), record_dev[1] = candidate index + index_offset (UINT64_MAX when
  * no candidate survived) - what a candidate-split run feeds to its NCCL reduction. */
 int32_t jssp_best_record_dev(jssp_handle* h, int64_t index_offset, void* stream, uint64_t* record_dev);
+/* -- candidate split over ranks (BASELINE configs[4]) ------------------------------------------
+ * The reference selects over ALL candidates of a cycle (PriorityQueue over calc_all_trajs_cost, jssp.py:288-294, 326-327).
+ * When one huge cycle is split over G ranks - contiguous seed ranges, every width on every rank - the only exchange is the
+ * per-rank selection record (orderable bits of the float64 cost, GLOBAL candidate index w * n_seeds_global + seed_lo + k):
+ * 16 bytes, lexicographic minimum = lowest cost, then lowest global index = the 1-GPU selection.
+ *
+ * jssp_set_split: this handle's external seeds are rows [seed_lo, seed_lo + n_seeds) of a cycle with n_seeds_global seeds
+ *   (0, 0 switches the split off).  Every following jssp_evaluate leaves the rank's record on the device.
+ * Transport A - NCCL (the "single NCCL min-reduce" of the north star, exact for a float64 cost + 64-bit index):
+ *   jssp_allreduce_argmin enqueues on `stream` one ncclAllGather of the 16-byte record (2 x ncclUint64) on `nccl_comm`
+ *   (an ncclComm_t as void*: the caller's own communicator, or one made by jssp_nccl_comm_create from a
+ *   jssp_nccl_unique_id broadcast by the caller) and a one-warp kernel that takes the lexicographic minimum.  world = 1
+ *   skips the collective.  NCCL is resolved at run time from the libnccl.so.2 already in the process (dlopen; override with
+ *   JSSP_NCCL_LIB); JSSP_ERR_NOT_READY when it cannot be found.
+ * Transport B - peer mailboxes over NVLink, fused into the evaluation launch: jssp_peer_export allocates this rank's
+ *   mailbox and returns its 64-byte CUDA IPC handle; after the caller has all-gathered the handles, jssp_peer_connect maps
+ *   every peer's mailbox.  From then on the block that finishes a rank's evaluation stores the record into every peer's
+ *   mailbox and one of its warps waits for the world's records and reduces them - no collective kernel, no host step.
+ * jssp_fetch_global_best synchronises `stream` and returns the global selection (best_idx = -1: no survivor anywhere) and
+ *   the rank that holds it (that rank's exported trajectory is the global best_traj).  Identical on every rank. */
+int32_t jssp_set_split(jssp_handle* h, int64_t seed_lo, int64_t n_seeds_global);
+int32_t jssp_nccl_unique_id(uint8_t id_out[128]);
+int32_t jssp_nccl_comm_create(const uint8_t id[128], int32_t world, int32_t rank, int32_t device, void** comm_out);
+int32_t jssp_nccl_comm_destroy(void* comm);
+int32_t jssp_allreduce_argmin(jssp_handle* h, void* nccl_comm, int32_t world, void* stream);
+int32_t jssp_peer_export(jssp_handle* h, int32_t world, uint8_t handle_out[64]);
+int32_t jssp_peer_connect(jssp_handle* h, const uint8_t* handles /* [world][64] */, int32_t world, int32_t rank);
+int32_t jssp_peer_disconnect(jssp_handle* h);
+int32_t jssp_fetch_global_best(jssp_handle* h, void* stream, int64_t* best_idx, double* best_cost, int32_t* winner_rank);
 /* number of kernels the library has launched through this handle so far */
 int64_t jssp_launch_count(const jssp_handle* h);
 /* bench utility: measured dense FMA throughput of the CUDA cores in TFLOP/s (bits = 32 or 64): the roofline

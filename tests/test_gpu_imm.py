@@ -62,13 +62,16 @@ def test_predicted_modes_feed_the_collision_check():
     eng.close()
 
 
-def test_batched_frenet_projection_matches_host_from_state(scenario_fixture):
-    """jssp_project_states against FrenetState.from_state (the host formulation the replay uses for cycle 0) on the bundled
-    route and on a synthetic turn: states scattered around the reference line, all headings."""
+def test_batched_frenet_projection_matches_oracle(scenario_fixture):
+    """jssp_project_states against the oracle's projection (oracle/frenet_oracle.py: scalar loops over the oracle's own spline
+    sampling) on the bundled route and on a synthetic turn: states scattered around the reference line, all headings.  The
+    product's host formulation (FrenetState.from_state, used for cycle 0 of a replay) is held to the same oracle."""
     from dlii_jssp_b200 import scenario as S
+    from oracle import frenet_oracle as FO
     rng = np.random.default_rng(4)
     for route in (scenario_fixture.route_xy, S.synthetic_intersection(0).route_xy):
         sp = J.CubicSpline2D(route[:, 0], route[:, 1])
+        pts = FO.rediscretise(O.CubicSpline2D(route[:, 0], route[:, 1]))
         ref = sp.sample(np.arange(0, sp.s_list[-1], 0.1))
         eng = J.JsspEngine(J.JsspConfig(max_knots=512))
         eng.set_refline(sp.s_list, sp.coefficient_table())
@@ -77,6 +80,8 @@ def test_batched_frenet_projection_matches_host_from_state(scenario_fixture):
                               rng.uniform(0, 15, 64), rng.normal(0, 2, 64)])
         st[0] = (ref[0, 0], ref[0, 1], ref[0, 2], 5.0, 0.0)                       # exactly on the first sample
         got = eng.project_states(torch.from_numpy(st).cuda()).cpu().numpy()
-        want = np.array([J.FrenetState().from_state(J.State(0.0, *row), ref).as_tuple() for row in st])
+        want = np.array([FO.project_state(pts, *row) for row in st])
         np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9)
+        host = np.array([J.FrenetState().from_state(J.State(0.0, *row), ref).as_tuple() for row in st])
+        np.testing.assert_allclose(host, want, rtol=1e-9, atol=1e-9)
         eng.close()

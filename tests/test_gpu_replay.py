@@ -84,3 +84,50 @@ def test_c1_kinematics_mode_replay_matches_the_reference_loop(scenario_fixture, 
     assert res.best_idx == g["kin_best_idx"].tolist()
     assert res.end == g["kin_ends"][-1] and res.cycles == len(g["kin_rows"])
     np.testing.assert_allclose(np.array(res.ego_rows), g["kin_rows"], rtol=1e-8, atol=1e-8)
+
+
+def _sweep_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sweep_golden.npz"))
+
+
+def test_sweep_sample_matches_oracle_replay_golden():
+    """A seeded sample of 40 of the 800 scenarios bench.py sweeps (BASELINE configs[3]), <= 100 cycles each, replayed by the
+    batched device-resident replay against the oracle planner in the reference driver's loop (tests/golden/sweep_golden.npz,
+    oracle/make_golden_sweep.py): end status, cycle count, selected index and candidate count of EVERY cycle identical, ego rows
+    to 1e-9."""
+    from dlii_jssp_b200 import batch as B
+    g = _sweep_golden()
+    ids, C = g["ids"].tolist(), int(g["max_cycles"][0])
+    got = B.run_batch([S.synthetic_intersection(i) for i in ids], max_cycles=C)
+    assert len(got) >= 32
+    for k, r in enumerate(got):
+        c = int(g["cycles"][k])
+        assert (r.end, r.cycles) == (float(g["end"][k]), c), (ids[k], r.end, r.cycles, g["end"][k], c)
+        assert list(r.best_idx) == g["best_idx"][k, :c].tolist(), ids[k]
+        assert list(r.n_candidates) == g["n_candidates"][k, :c].tolist(), ids[k]
+        nr = int(g["n_rows"][k])
+        assert len(r.ego_rows) == nr
+        if nr:
+            np.testing.assert_allclose(np.array(r.ego_rows), g["rows"][k, :nr], rtol=1e-9, atol=1e-9)
+    assert not any(r.seed_overflow for r in got)
+
+
+def test_sharded_sweep_returns_the_same_rows_as_one_gpu():
+    """The scenario sweep shards over ranks with no collective: dealing the sample to 8 ranks'
+    shards and replaying shard by shard gives, per scenario, exactly the rows of the single-batch run - and the digest bench.py
+    prints for every --gpus N is therefore the same."""
+    from dlii_jssp_b200 import batch as B, distributed as D
+    ids = _sweep_golden()["ids"].tolist()
+    packed = [B.pack_scenario(S.synthetic_intersection(i), max_cycles=100) for i in ids]
+    whole = {r.name: r for r in B.run_batch(packed, max_cycles=100)}
+    parts = {}
+    for rank in range(8):
+        for r in B.run_batch(D.shard_scenarios(packed, 8, rank), max_cycles=100):
+            parts[r.name] = r
+    assert parts.keys() == whole.keys()
+    for name, r in whole.items():
+        q = parts[name]
+        assert (r.end, r.cycles, list(r.best_idx), list(r.n_candidates), r.ego_rows) == (q.end, q.cycles, list(q.best_idx), list(q.n_candidates), q.ego_rows)
+    assert D.sweep_digest([(r.name, r.end, r.cycles, list(r.best_idx)) for r in whole.values()]) == \
+        D.sweep_digest([(r.name, r.end, r.cycles, list(r.best_idx)) for r in parts.values()])

@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """Condense an ncu capture (--set full) of one kernel into a small JSON + the raw-page CSV under profiles/.
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_evaluate_group_kernel
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r02_evaluate_kernel [kernel-name-substring] [build-id]
+
+With a kernel-name substring the first launch whose name contains it is condensed (a report may hold several kernels); the build
+id (``python -c "from dlii_jssp_b200 import build; print(build.library_id())"`` of the library that was profiled) is stored in
+the JSON: bench.py only attaches a capture to a library with the same build id.
 
 bench.py reads the JSON (if present) to fill roofline.traffic and roofline.executed - measured under the profiler, so they
 are evidence about the kernel, never a bench value."""
@@ -40,10 +44,16 @@ UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3,
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
+    want = sys.argv[3] if len(sys.argv) > 3 else ""
+    build_id = sys.argv[4] if len(sys.argv) > 4 else None
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    d = {"kernel": vals[hdr.index("Kernel Name")], "source": rep.split("/")[-1]}
+    hdr, units = rows[0], rows[1]
+    kcol = hdr.index("Kernel Name")
+    vals = next((r for r in rows[2:] if want in r[kcol]), None)
+    if vals is None:
+        raise SystemExit(f"no kernel matching {want!r} in {rep}: " + ", ".join(sorted({r[kcol] for r in rows[2:]})))
+    d = {"kernel": vals[kcol], "source": rep.split("/")[-1], "build_id": build_id}
     for i, h in enumerate(hdr):
         if h in KEYS:
             v = float(vals[i].replace(",", ""))
