@@ -490,6 +490,9 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(allow_max_dynamic_smem(evaluate_group_kernel<0>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_group_kernel<1>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_group_kernel<2>, optin, &h->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_tiled_kernel<0>, optin, &h->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_tiled_kernel<1>, optin, &h->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_tiled_kernel<2>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(dump_states_kernel, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_fop_kernel, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(fop_select_export_kernel, optin, &h->max_smem_optin));
@@ -768,8 +771,12 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   bool small = n_max <= 16384 && small_bytes <= (size_t)h->max_smem_optin;
   if (in->flags & JSSP_FLAG_FORCE_THREAD) small = false;
   if ((in->flags & JSSP_FLAG_FORCE_WARP) && small_bytes <= (size_t)h->max_smem_optin) small = true;
-  if (in->flags & JSSP_FLAG_FORCE_GROUP) small = false;
+  if (in->flags & (JSSP_FLAG_FORCE_GROUP | JSSP_FLAG_FORCE_TILED)) small = false;
   const bool group = !small && !(in->flags & JSSP_FLAG_FORCE_THREAD);
+  // large cycles: the tiled two-phase kernel unless the shuffle form is asked for (or its scratch does not fit)
+  const size_t tile_bytes = tile_scratch_bytes(W, EVAL_THREADS);
+  const size_t tiled_total = ((L.total + 15) & ~(size_t)15) + tile_bytes;
+  const bool tiled = group && !(in->flags & JSSP_FLAG_FORCE_GROUP) && tiled_total <= (size_t)h->max_smem_optin;
   const long long seeds_max = ext ? in->n_seeds : c.max_seeds;
   const int spb = group_seeds_per_block(W);
   // warp-per-candidate grid: grid-stride kernel, sized from the last cycle's candidate count (x2) when the seeds are
@@ -790,6 +797,9 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
     const bool chained = !ext && (in->flags & JSSP_FLAG_ENUMERATE) && !h->tune.no_pdl;
     CK(launch_chained(evaluate_small_kernel, dim3(blocks), SMALL_WARPS * 32, small_bytes, st, chained, p));
   }
+  else if (tiled && mode == 2) evaluate_tiled_kernel<2><<<blocks, EVAL_THREADS, tiled_total, st>>>(p);
+  else if (tiled && mode == 1) evaluate_tiled_kernel<1><<<blocks, EVAL_THREADS, tiled_total, st>>>(p);
+  else if (tiled) evaluate_tiled_kernel<0><<<blocks, EVAL_THREADS, tiled_total, st>>>(p);
   else if (group && mode == 2) evaluate_group_kernel<2><<<blocks, EVAL_THREADS, L.total, st>>>(p);
   else if (group && mode == 1) evaluate_group_kernel<1><<<blocks, EVAL_THREADS, L.total, st>>>(p);
   else if (group) evaluate_group_kernel<0><<<blocks, EVAL_THREADS, L.total, st>>>(p);
@@ -1305,6 +1315,8 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   CKC(allow_max_dynamic_smem(evaluate_small_batch_kernel, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_group_batch_kernel<0>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_group_batch_kernel<1>, optin, &b->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_tiled_batch_kernel<0>, optin, &b->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_tiled_batch_kernel<1>, optin, &b->max_smem_optin));
   CKC(cudaDeviceSynchronize());
 #undef CKC
   *out = b;
@@ -1589,7 +1601,7 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   const SmemLayout Ls = eval_smem_layout(0, b->max_OMpad, 0, b->max_K, b->max_kpad, b->P, b->W);
   const size_t small_bytes = Ls.total + small_scratch_bytes(b->P);
   bool small = (long long)n_scenarios * b->cfg.max_seeds * b->W <= 65536 && small_bytes <= (size_t)b->max_smem_optin;
-  if (flags & (JSSP_FLAG_FORCE_THREAD | JSSP_FLAG_FORCE_GROUP)) small = false;
+  if (flags & (JSSP_FLAG_FORCE_THREAD | JSSP_FLAG_FORCE_GROUP | JSSP_FLAG_FORCE_TILED)) small = false;
   if ((flags & JSSP_FLAG_FORCE_WARP) && small_bytes <= (size_t)b->max_smem_optin) small = true;
   // thread per candidate for the default 3 lateral targets (a scenario's ~150 seeds fill the group kernel's 40-seed blocks and
   // 30-of-32 lanes poorly: measured 49.0 vs 53.9 ms on the 800-scenario sweep), the group kernel from 4 targets on
@@ -1604,6 +1616,8 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   SmemLayout L = eval_smem_layout(max_rows, b->max_OMpad, mode, b->max_K, b->max_kpad, b->P, b->W);
   if (mode == 1 && L.total > (size_t)b->max_smem_optin) { mode = 0; L = eval_smem_layout(0, b->max_OMpad, 0, b->max_K, b->max_kpad, b->P, b->W); }
   if (!small && L.total > (size_t)b->max_smem_optin) return JSSP_ERR_CAPACITY;
+  const size_t tiled_total = ((L.total + 15) & ~(size_t)15) + tile_scratch_bytes(b->W, bthreads);
+  const bool tiled = !small && (flags & JSSP_FLAG_FORCE_TILED) && tiled_total <= (size_t)b->max_smem_optin;
   // few scenarios: clusters of up to 8 CTAs x 1024 threads answer with the lowest latency; many: one 512-thread CTA each
   int seed_cluster = 1;
   while (seed_cluster < SEED_MAX_CLUSTER && n_scenarios * seed_cluster * 2 <= 148) seed_cluster *= 2;
@@ -1614,6 +1628,8 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
     CKB(launch_seed_enum<true>(b->grids, SeedState{0, 0, 0}, b->d_slots, b->seed_work, n_scenarios, seed_cluster, seed_threads, b->seed_smem, st, pdl));
     const EvalParams* slots = b->d_slots;
     if (small) CKB(launch_chained(evaluate_small_batch_kernel, dim3(n_scenarios, std::min(b->blocks_warp, 128)), SMALL_WARPS * 32, small_bytes, st, pdl, slots));
+    else if (tiled && mode == 1) CKB(launch_chained(evaluate_tiled_batch_kernel<1>, dim3(n_scenarios, blocks_group), bthreads, tiled_total, st, pdl, slots));
+    else if (tiled) CKB(launch_chained(evaluate_tiled_batch_kernel<0>, dim3(n_scenarios, blocks_group), bthreads, tiled_total, st, pdl, slots));
     else if (group && mode == 1) CKB(launch_chained(evaluate_group_batch_kernel<1>, dim3(n_scenarios, blocks_group), bthreads, L.total, st, pdl, slots));
     else if (group) CKB(launch_chained(evaluate_group_batch_kernel<0>, dim3(n_scenarios, blocks_group), bthreads, L.total, st, pdl, slots));
     else if (mode == 1) CKB(launch_chained(evaluate_batch_kernel<1>, dim3(n_scenarios, blocks_thread), bthreads, L.total, st, pdl, slots));

@@ -495,7 +495,13 @@ __device__ __forceinline__ void stage_tables(const EvalParams& p, unsigned char*
 // Falls back to the global table (tb.use_lists stays false) when the lists would not fit.
 // Phase A lets every thread scan the rows row_first, row_first + row_stride, ... of ITS seed: (0, 1) when every thread has a
 // seed of its own, (lane-in-group, W) when the W lanes of a group share one.
-__device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* smem, BlockTables& tb, LonWalk lp, bool active,
+// `s_at(t)` returns the arc length of the thread's seed at time t (called with non-decreasing t).
+struct WalkSAt {
+  LonWalk lp;
+  __device__ __forceinline__ double operator()(double t) { double s, sd, sdd, sddd; lon_walk_eval(lp, t, s, sd, sdd, sddd); return s; }
+};
+template <class SAt>
+__device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* smem, BlockTables& tb, SAt& s_at, bool active,
                                             int row_first = 0, int row_stride = 1) {
   const SmemLayout L = eval_smem_layout(p.win_rows, p.OMpad, 2, p.K, p.kpad, p.P, p.W, p.list_cap);
   float4* list = reinterpret_cast<float4*>(smem + L.off_broad);
@@ -513,8 +519,7 @@ __device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* 
     for (int r = 0; r < p.win_rows; ++r) {
       unsigned int lo = 0x7f800000u, hi = 0u;
       if (active) {
-        double s, sd, sdd, sddd;
-        lon_walk_eval(lp, tb.time[r * p.check_res], s, sd, sdd, sddd);
+        double s = s_at(tb.time[r * p.check_res]);
         s = fmin(fmax(s, 0.0), s_end);                  // off-line samples are never collision-checked
         lo = __float_as_uint(__double2float_rd(s));     // s >= 0: the bit patterns order like the values
         hi = __float_as_uint(__double2float_ru(s));
@@ -531,8 +536,7 @@ __device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* 
       const int r = r0 + row_first;
       unsigned int lo = 0x7f800000u, hi = 0u;
       if (active && r < p.win_rows) {
-        double s, sd, sdd, sddd;
-        lon_walk_eval(lp, tb.time[r * p.check_res], s, sd, sdd, sddd);
+        double s = s_at(tb.time[r * p.check_res]);
         s = fmin(fmax(s, 0.0), s_end);
         lo = __float_as_uint(__double2float_rd(s));
         hi = __float_as_uint(__double2float_ru(s));
@@ -1030,7 +1034,7 @@ __device__ __forceinline__ void evaluate_body(const EvalParams& p, unsigned char
     const int w = active ? n / Ns : 0, k = active ? n - w * Ns : 0;
     LonWalk lp;
     lon_walk_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
-    if (kMode == 2) build_lists(p, smem, tb, lp, active);
+    if (kMode == 2) { WalkSAt s_at{lp}; build_lists(p, smem, tb, s_at, active); }
     PHASE(p, 2);
     if (active) {
       EvalSink sink(p, tb);
@@ -1088,7 +1092,7 @@ __device__ __forceinline__ void evaluate_group_body(const EvalParams& p, unsigne
     PHASE(p, 1);
     LonWalk lp;
     lon_walk_init(lp, p.seeds + (size_t)(active ? k : 0) * 10, p.s0, p.v0, p.a0);
-    if (kMode == 2) build_lists(p, smem, tb, lp, active, j, W);
+    if (kMode == 2) { WalkSAt s_at{lp}; build_lists(p, smem, tb, s_at, active, j, W); }
     PHASE(p, 2);
     if (active) {
       const unsigned int gmask = (W >= 32 ? 0xffffffffu : ((1u << W) - 1u)) << (g * W);

@@ -1,0 +1,247 @@
+// jssp_eval_tiled.cuh - K2 (default for large cycles and inside the persistent replay kernel): the TILED two-phase walk.
+//
+// The W candidates that share a longitudinal seed (one per lateral target) sit in W consecutive lanes, a warp holds
+// floor(32 / W) seeds, and the horizon is processed in tiles of TL = R * W samples.  Per tile:
+//   phase 1  (parallel over samples, no dependent chain): lane j of a seed's group evaluates the SEED-ONLY quantities of the
+//            samples j, j + W, ... of the tile - unrolled s, s_d, s_dd, s_ddd from the seed's segment table
+//            (polyvt_sampling.py:311-385), the three longitudinal cost terms, the spline segment, the reference point and its
+//            unit normal (jerk_space_sampling_planner.py:131-145) - and stores (ix, iy, u, v) in the warp's own shared-memory
+//            tile; the cost terms stay in per-lane partial sums;
+//   phase 2  (one lane per candidate): the lane adds its own lateral offset, forms the forward difference, its length and unit
+//            vector, tests the curvature (:155-180) and, on every check_res-th sample, the collision row (:233-286).
+// Only __syncwarp() separates the phases: warps are decoupled, one warp's phase 1 (throughput) overlaps another's phase 2
+// (latency).  Compared with the shuffle form (walk_group) nothing seed-only sits on the candidate's serial chain any more and
+// the 15 SHFL per sample are gone.  Seed-only arithmetic keeps the reference's unfused operand order (s, s_d, s_dd, s_ddd and
+// the cost terms are bit-identical to the other kernels' values); the geometry of phase 2 and the spline evaluation use
+// explicit fused multiply-adds (positions agree to an ulp; masks are decided by the same guard-banded tests).
+#pragma once
+#include "jssp_eval.cuh"
+
+namespace jssp {
+
+constexpr int TILE_PROF = 32;      // doubles per seed in the segment table: 5 x (s, v, a, j) | t1..t4 | 4 bounds | s(0), s(P-1) | pad
+
+struct TileGeom {
+  int gpw;          // seeds (groups) per warp
+  int R;            // phase-1 rounds per tile
+  int TL;           // samples per tile = R * W
+  int grp_stride;   // doubles between the tiles of two groups (TL * 4 + 2: neighbouring groups land 16 B apart in the banks)
+  int warp_doubles; // doubles of scratch per warp
+};
+__host__ __device__ inline TileGeom tile_geom(int W) {
+  TileGeom g;
+  g.gpw = 32 / W;
+  const int r_want = (16 + W - 1) / W, r_cap = 160 / (g.gpw * W);     // ~16 samples per tile, at most ~160 entries per warp
+  g.R = r_want < r_cap ? r_want : r_cap;
+  if (g.R < 1) g.R = 1;
+  g.TL = g.R * W;
+  g.grp_stride = g.TL * 4 + 2;
+  g.warp_doubles = g.gpw * g.grp_stride + g.gpw * TILE_PROF;
+  g.warp_doubles = (g.warp_doubles + 1) & ~1;
+  return g;
+}
+__host__ __device__ inline size_t tile_scratch_bytes(int W, int threads) { return (size_t)(threads / 32) * tile_geom(W).warp_doubles * 8; }
+
+// segment table of one seed: the start state and jerk of each of the five segments (the same expressions as lon_profile_init:
+// bit-identical to the reference's segment end states), the durations and the asymmetric-epsilon boundaries of
+// get_one_frenet_trajectory's branch chain (polyvt_sampling.py:334-374)
+__device__ __forceinline__ void tile_profile_store(double* prof, const double* __restrict__ seed, double s0, double v0, double a0) {
+  LonProfile lp;
+  lon_profile_init(lp, seed, s0, v0, a0);
+  prof[0] = s0; prof[1] = v0; prof[2] = a0; prof[3] = lp.j1;
+  prof[4] = lp.s1; prof[5] = lp.v1; prof[6] = lp.a1; prof[7] = lp.j2;
+  prof[8] = lp.s2; prof[9] = lp.v2; prof[10] = lp.a2; prof[11] = lp.j3;
+  prof[12] = lp.s3; prof[13] = lp.v3; prof[14] = lp.a3; prof[15] = lp.j4;
+  prof[16] = lp.s4; prof[17] = lp.v4; prof[18] = lp.a4; prof[19] = lp.j5;
+  prof[20] = lp.t1; prof[21] = lp.t2; prof[22] = lp.t3; prof[23] = lp.t4;
+  prof[24] = lp.t1 - 1e-9; prof[25] = lp.t1 + lp.t2 + 1e-9; prof[26] = lp.t1 + lp.t2 + lp.t3 + 1e-9;
+  prof[27] = lp.t1 + lp.t2 + lp.t3 + lp.t4 + 1e-9;
+}
+
+// s, s_d, s_dd, s_ddd at time t from the segment table; `k` = segment of the previous (earlier) sample of this lane, or 0
+__device__ __forceinline__ void tile_lon_eval(const double* prof, int& k, double t, double& s, double& sd, double& sdd, double& sddd) {
+  while (k < 4 && !(t < prof[24 + k])) ++k;
+  const double* q = prof + 4 * k;
+  const double sb = q[0], vb = q[1], ab = q[2], jb = q[3];
+  double dt = t;
+  if (k >= 1) dt = dt - prof[20];
+  if (k >= 2) dt = dt - prof[21];
+  if (k >= 3) dt = dt - prof[22];
+  if (k >= 4) dt = dt - prof[23];
+  s = st_by_jt(sb, vb, ab, jb, dt);
+  sd = vt_by_jt(vb, ab, jb, dt);
+  sdd = at_by_jt(ab, jb, dt);
+  sddd = jb;
+}
+
+// the seed-only part of frenet_point with fused multiply-adds: reference point (ix, iy) and u = y'/|r'|, v = x'/|r'|
+__device__ __forceinline__ void frenet_base_fma(const SplineView& sp, int seg, double s, double& ix, double& iy, double& u, double& v) {
+  const double dx = s - sp.knot[seg];
+  const double* c = sp.coef + seg;
+  const int kp = sp.kpad;
+  const double c1 = c[kp], c2 = c[2 * kp], c3 = c[3 * kp], c5 = c[5 * kp], c6 = c[6 * kp], c7 = c[7 * kp];
+  ix = fma(fma(fma(c3, dx, c2), dx, c1), dx, c[0]);
+  iy = fma(fma(fma(c7, dx, c6), dx, c5), dx, c[4 * kp]);
+  const double tx = fma(fma(3.0 * c3, dx, 2.0 * c2), dx, c1);
+  const double ty = fma(fma(3.0 * c7, dx, 2.0 * c6), dx, c5);
+  const double inv = rsqrt_fast(fma(tx, tx, ty * ty));
+  u = ty * inv;
+  v = tx * inv;
+}
+
+// arc length of the seed at time t (list building: the block's range per collision row)
+struct TileSAt {
+  const double* prof;
+  __device__ __forceinline__ double operator()(double t) const {
+    int k = 0;
+    double s, sd, sdd, sddd;
+    tile_lon_eval(prof, k, t, s, sd, sdd, sddd);
+    return s;
+  }
+};
+
+// The tiled walk of the candidate in lane (g, j): g = group (seed) within the warp, j = lateral target.  `gbase` = this group's
+// tile, `prof` = this group's segment table (already stored), both in the warp's scratch.  Inactive lanes (no seed) only keep
+// the warp-level barriers company.  On return `sink` holds the masks, the risk term and the longitudinal cost sums.
+__device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTables& tb, const TileGeom& tg, double* gbase, double* prof,
+                                           bool active, int j, int W, EvalSink& sink) {
+  const int P = p.P, TL = tg.TL;
+  const double* lat = tb.lat + (size_t)j * P * 4;
+  int k = 0, n_pts = P;
+  double pa = 0, pj = 0, pv = 0;                 // this lane's share of the longitudinal cost sums (its own samples, in time order)
+  double xp = 0, yp = 0;
+  bool walking = active;
+  for (int base = 0; base < P; base += TL) {
+    const int len = min(TL, P - base);
+    // phase 1: seed-only quantities of the samples this lane owns in the tile
+    if (active) {
+      for (int il = j; il < len; il += W) {
+        const int i = base + il;
+        double s, sd, sdd, sddd;
+        tile_lon_eval(prof, k, tb.time[i], s, sd, sdd, sddd);
+        const double ea = fmax(fabs(sdd) - p.thr_lon_a, 0.0);
+        const double ej = fmax(fabs(sddd) - p.thr_lon_j, 0.0);
+        const double ev = (p.vmax - sd) * p.inv_vmax;
+        pa = pa + ea * ea; pj = pj + ej * ej; pv = pv + ev * ev;
+        if (i == 0) prof[28] = s;
+        if (i == P - 1) prof[29] = s;
+        double2* e = reinterpret_cast<double2*>(gbase + il * 4);
+        if (spline_in_range(tb.sp, s)) {
+          double ix, iy, u, v;
+          frenet_base_fma(tb.sp, spline_walk(tb.sp, s, 0), s, ix, iy, u, v);
+          e[0] = make_double2(ix, iy); e[1] = make_double2(u, v);
+        } else {
+          e[0] = make_double2(nan(""), 0.0);      // off the reference line: the Cartesian path ends here (jssp.py:138-139)
+        }
+      }
+    }
+    __syncwarp();
+    // phase 2: this lane's candidate
+    if (walking) {
+      for (int il = 0; il < len; ++il) {
+        const int i = base + il;
+        const double2* e = reinterpret_cast<const double2*>(gbase + il * 4);
+        const double2 pxy = e[0];
+        if (!(pxy.x == pxy.x)) { n_pts = i; walking = false; break; }
+        const double2 uv = e[1];
+        const double d = lat[i * 4];
+        const double x = fma(-d, uv.x, pxy.x), y = fma(d, uv.y, pxy.y);
+        if (i >= 1) {
+          const double dx = x - xp, dy = y - yp;
+          const double q = fma(dx, dx, dy * dy);
+          double ds, c = 1.0, sn = 0.0;
+          if (q > 1e-200 && q < 1e200) { const double inv = rsqrt_fast(q); ds = q * inv; c = dx * inv; sn = dy * inv; }
+          else { ds = hypot(dx, dy); if (ds > 0.0) { c = dx / ds; sn = dy / ds; } }
+          sink.segment(i - 1, xp, yp, dx, dy, ds, c, sn);
+          if (sink.vetoed()) { walking = false; break; }     // select-only evaluation: this candidate can no longer be selected
+        }
+        xp = x; yp = y;
+      }
+    }
+    __syncwarp();                                  // the tile is rewritten by the next phase 1
+  }
+  if (active && !sink.vetoed()) sink.finish(n_pts, xp, yp);
+  // cost sums of the seed = the group's partial sums in lane order (the same order for every seed: deterministic)
+  if (active) { gbase[j * 4] = pa; gbase[j * 4 + 1] = pj; gbase[j * 4 + 2] = pv; }
+  __syncwarp();
+  if (active) {
+    double sa = 0, sj = 0, sv = 0;
+    for (int q = 0; q < W; ++q) { sa = sa + gbase[q * 4]; sj = sj + gbase[q * 4 + 1]; sv = sv + gbase[q * 4 + 2]; }
+    sink.sum_a = sa; sink.sum_j = sj; sink.sum_v = sv;
+    sink.s_first = prof[28]; sink.s_last = prof[29];
+  }
+  __syncwarp();
+}
+
+template <int kMode>
+__device__ __forceinline__ void evaluate_tiled_body(const EvalParams& p, unsigned char* smem, double* red_cost, int* red_idx,
+                                                    bool* is_last, int* sm_npts) {
+  const int Ns = resolve_n_seeds(p);
+  const int W = p.W;
+  const int N = Ns * W;
+  const TileGeom tg = tile_geom(W);
+  const int gpw = tg.gpw;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int g = lane / W, j = lane - g * W;
+  const int spb = (blockDim.x >> 5) * gpw;     // seeds per block
+  const int k = blk_index(p) * spb + wid * gpw + g;
+  const bool active = g < gpw && k < Ns;
+  double my_cost = INFINITY;
+  int my_idx = -1;
+  BlockTables tb;
+  const double* latcost;
+  const bool staged = blk_index(p) * spb < Ns;   // block-uniform
+  PHASE(p, 0);
+  if (staged) {
+    stage_tables<kMode>(p, smem, tb, latcost);
+    PHASE(p, 1);
+    const SmemLayout L = eval_smem_layout(p.win_rows, p.OMpad, kMode, p.K, p.kpad, p.P, p.W, p.list_cap);
+    double* wscr = reinterpret_cast<double*>(smem + ((L.total + 15) & ~(size_t)15)) + (size_t)wid * tg.warp_doubles;
+    double* gbase = wscr + (size_t)(g < gpw ? g : 0) * tg.grp_stride;
+    double* prof = wscr + (size_t)gpw * tg.grp_stride + (size_t)(g < gpw ? g : 0) * TILE_PROF;
+    if (active && j == 0) tile_profile_store(prof, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
+    __syncwarp();
+    if (kMode == 2) { TileSAt s_at{prof}; build_lists(p, smem, tb, s_at, active, j, W); }
+    PHASE(p, 2);
+    EvalSink sink(p, tb);
+    walk_tiles(p, tb, tg, gbase, prof, active, j, W, sink);
+    if (active) {
+      const int n = j * Ns + k;                // candidate index: width-major (jerk_space_sampling_planner.py:106,124-125)
+      const double cost = candidate_cost(p, sink, latcost + j * 4);
+      if (p.feasible) p.feasible[n] = sink.curv_fail ? 0 : 1;
+      if (p.collision) p.collision[n] = sink.collided ? 1 : 0;
+      if (p.cost) p.cost[n] = (float)cost;
+      if (!sink.curv_fail && !sink.collided && isfinite(cost)) { my_cost = cost; my_idx = n; }
+    }
+  }
+  __syncthreads();
+  PHASE(p, 3);
+  select_and_export<kMode>(p, smem, tb, latcost, staged, my_cost, my_idx, N, Ns, red_cost, red_idx, is_last, sm_npts);
+  PHASE(p, 4);
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(EVAL_THREADS, EVAL_MIN_BLOCKS) evaluate_tiled_kernel(const __grid_constant__ EvalParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ double red_cost[EVAL_THREADS / 32];
+  __shared__ int red_idx[EVAL_THREADS / 32];
+  __shared__ bool is_last;
+  __shared__ int sm_npts;
+  evaluate_tiled_body<kMode>(p, smem, red_cost, red_idx, &is_last, &sm_npts);
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(BATCH_EVAL_THREADS, BATCH_MIN_BLOCKS) evaluate_tiled_batch_kernel(const EvalParams* __restrict__ slots) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(16) EvalParams sp;
+  __shared__ double red_cost[EVAL_THREADS / 32];
+  __shared__ int red_idx[EVAL_THREADS / 32];
+  __shared__ bool is_last;
+  __shared__ int sm_npts;
+  pdl_launch_dependents(); pdl_wait();
+  if (!slot_live(slots, blockIdx.x)) return;
+  load_slot(&sp, slots + blockIdx.x);
+  evaluate_tiled_body<kMode>(sp, smem, red_cost, red_idx, &is_last, &sm_npts);
+}
+
+}  // namespace jssp

@@ -8,6 +8,9 @@
 //                            feasibility -> rectangle collision against every obstacle mode -> cost -> argmin -> export,
 //                            batched-replay hand-off         polyvt_sampling.py:311-385, jerk_space_sampling_planner.py:131-294,326-327
 //   jssp_eval_small.cuh  K2b evaluate_small_kernel           one warp per candidate (default sampling grid)
+//   jssp_eval_tiled.cuh  K2  evaluate_tiled_kernel (default for large cycles): two-phase tiled walk - seed-only work of a tile in
+//                            parallel into the warp's shared-memory tile, then one lane per candidate
+//   jssp_split.cuh           candidate-split exchange (NCCL all-gather record / peer mailboxes fused into the evaluation launch)
 //   jssp_fop.cuh         K6  evaluate_fop_kernel             frenet_optimal_planner.py:97-333
 //   jssp_aux.cuh         K3 dump_states_kernel, K5 project_states_kernel, K4 imm_update_kernel / predict_modes_kernel, fma_peak_kernel
 #pragma once
@@ -17,5 +20,6 @@
 #include "jssp_pack.cuh"
 #include "jssp_eval.cuh"
 #include "jssp_eval_small.cuh"
+#include "jssp_eval_tiled.cuh"
 #include "jssp_fop.cuh"
 #include "jssp_aux.cuh"

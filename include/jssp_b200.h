@@ -95,8 +95,11 @@ typedef struct jssp_cycle_in {
 #define JSSP_FLAG_ENUMERATE 8    /* run jssp_enumerate_seeds(s0, v0, a0) first: one call = one whole plan cycle */
 #define JSSP_FLAG_FORCE_WARP 16  /* use the warp-per-candidate kernel (default for <= 16384 candidates) */
 #define JSSP_FLAG_FORCE_THREAD 32 /* use the thread-per-candidate kernel; same results */
-#define JSSP_FLAG_FORCE_GROUP 64 /* use the group kernel (default for larger cycles): the lateral targets of a seed sit in
-                                    consecutive lanes and share the seed-only work by warp shuffles; same results */
+#define JSSP_FLAG_FORCE_GROUP 64 /* use the group kernel: the lateral targets of a seed sit in consecutive lanes and share the
+                                    seed-only work by warp shuffles; same results */
+#define JSSP_FLAG_FORCE_TILED 128 /* use the tiled two-phase kernel (default for larger cycles): per tile of the horizon the seed-only
+                                    work runs in parallel into shared memory, then one lane per candidate walks the tile; same masks
+                                    and selection, costs equal to rounding */
 #define JSSP_FLAG_NO_CULL 4      /* test every obstacle state instead of the per-block culled lists (same results) */
 
 /* Outputs.  Candidate n = w * n_seeds + k (width-major, jssp.py:106,124-125).  All dev pointers may be NULL.  With
