@@ -148,27 +148,35 @@ __device__ unsigned long long g_seed_ts[16];
 #else
 #define SEED_STAMP(k)
 #endif
-template <bool kBatch>
-__global__ void __launch_bounds__(SEED_THREADS) seed_enum_kernel(SeedGrids g, SeedState st1, const EvalParams* __restrict__ slots,
-                                                                 SeedWork wk) {
-  extern __shared__ __align__(16) unsigned char seed_smem_local[];
-  cg::cluster_group cluster = cg::this_cluster();
-  const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
-  const int sc = blockIdx.x / csize;
-  pdl_launch_dependents();                                      // the evaluation kernel behind may start being placed
-  if (kBatch) pdl_wait();                                       // the slot records are written by the previous cycle's hand-off
-  if (kBatch && !slot_live(slots, sc)) return;                  // cluster-uniform
-  const SeedState st = kBatch ? seed_state_of(slots, sc) : st1;
-  unsigned char* seed_smem = csize > 1 ? cluster.map_shared_rank(seed_smem_local, 0) : seed_smem_local;
+// Synchronisation policies of the enumeration: a thread-block cluster (lists in CTA 0's shared memory, reached through
+// distributed shared memory) or a single CTA (the persistent replay kernel).
+struct SeedClusterSync {
+  cg::cluster_group c;
+  __device__ __forceinline__ void sync() { c.sync(); }
+  __device__ __forceinline__ int rank() const { return (int)c.block_rank(); }
+  __device__ __forceinline__ int size() const { return (int)c.num_blocks(); }
+};
+struct SeedBlockSync {
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+  __device__ __forceinline__ int rank() const { return 0; }
+  __device__ __forceinline__ int size() const { return 1; }
+};
+
+// The enumeration of one scenario by the threads of `sy` (every thread of the cluster / CTA calls it).  `seed_smem` = the list
+// memory (CTA 0's for a cluster), `seeds` / `counts` = this scenario's outputs.  After the call the sorted loop positions are
+// still in the key list: key_out / n_out hand them to a caller that wants to decode seeds itself.
+template <class Sync>
+__device__ __forceinline__ void seed_enum_body(const SeedGrids& g, const SeedState& st, const SeedWork& wk, Sync& sy, unsigned char* seed_smem,
+                                               double* __restrict__ seeds, int* __restrict__ counts) {
   int* cnt = reinterpret_cast<int*>(seed_smem);                 // 0 A main, 1 A stop, 2 B, 3 keys, 4 main keys, 5 overflow
   SeedPrefixA* la_main = reinterpret_cast<SeedPrefixA*>(seed_smem + 32);
   SeedPrefixA* la_stop = la_main + wk.cap_a_main;
   SeedPrefixB* lb = reinterpret_cast<SeedPrefixB*>(la_stop + wk.cap_a_stop);
   uint32_t* key = reinterpret_cast<uint32_t*>(lb + wk.cap_b);
-  const int tid = crank * blockDim.x + threadIdx.x, nt = csize * blockDim.x;     // position in the cluster
+  const int tid = sy.rank() * blockDim.x + threadIdx.x, nt = sy.size() * blockDim.x;     // position in the cluster
   SEED_STAMP(0);
   if (tid < 8) cnt[tid] = 0;
-  cluster.sync();
+  sy.sync();
   SEED_STAMP(1);
   const double T = g.total_time;
   // level 1: (j1, t1) of the main grid and (j1 <= 0, t1) of the stop grid
@@ -192,7 +200,7 @@ __global__ void __launch_bounds__(SEED_THREADS) seed_enum_kernel(SeedGrids g, Se
       if (pos < wk.cap_a_stop) la_stop[pos] = SeedPrefixA{s1, v1, a1, ij1, i1}; else cnt[5] = 1;
     }
   }
-  cluster.sync();
+  sy.sync();
   SEED_STAMP(2);
   // level 2: main prefixes x t2 -> list B; stop prefixes x (j2 >= 0) -> stop seeds.  A warp takes whole prefixes (the
   // entry is one broadcast read, also when it lives in another CTA's shared memory) and spreads t2 / j2 over its lanes.
@@ -264,7 +272,7 @@ __global__ void __launch_bounds__(SEED_THREADS) seed_enum_kernel(SeedGrids g, Se
       }
     }
   }
-  cluster.sync();
+  sy.sync();
   SEED_STAMP(3);
   // level 3: list B x j3 x t3, then the t4 loop and the closing segment
   const int nb = min(cnt[2], wk.cap_b);
@@ -301,11 +309,11 @@ __global__ void __launch_bounds__(SEED_THREADS) seed_enum_kernel(SeedGrids g, Se
       if (pos < wk.cap_keys) key[pos] = flat; else cnt[5] = 1;
     }
   }
-  cluster.sync();
+  sy.sync();
   SEED_STAMP(4);
   // reference order: one sort of the loop positions (stop seeds carry the top bit) by CTA 0, then every CTA decodes
   const int n_all = min(cnt[3], wk.cap_keys), n_main = cnt[4];
-  if (crank == 0) {
+  if (sy.rank() == 0) {
     int np2 = 1;
     while (np2 < n_all) np2 <<= 1;
     for (int i = n_all + (int)threadIdx.x; i < np2; i += blockDim.x) key[i] = 0xffffffffu;
@@ -313,9 +321,8 @@ __global__ void __launch_bounds__(SEED_THREADS) seed_enum_kernel(SeedGrids g, Se
     if (np2 <= (int)blockDim.x) bitonic_sort_regs(key, np2); else bitonic_sort_smem(key, np2);
   }
   SEED_STAMP(5);
-  cluster.sync();
+  sy.sync();
   SEED_STAMP(6);
-  double* seeds = wk.seeds + (size_t)sc * wk.cap_seeds * 10;
   for (int i = tid; i < min(n_all, wk.cap_seeds); i += nt) {
     double* o = seeds + (size_t)i * 10;
     const uint32_t k = key[i];
@@ -332,14 +339,28 @@ __global__ void __launch_bounds__(SEED_THREADS) seed_enum_kernel(SeedGrids g, Se
     }
   }
   if (tid == 0) {
-    int* counts = wk.counts + (size_t)sc * 4;
     int overflow = cnt[5];
     int emitted = n_all;
     if (cnt[3] > wk.cap_keys || emitted > wk.cap_seeds) { overflow = 1; emitted = min(emitted, wk.cap_seeds); }
     counts[0] = n_main; counts[1] = cnt[3] - n_main; counts[2] = emitted; counts[3] = overflow;
   }
   SEED_STAMP(7);
-  cluster.sync();                                               // CTA 0's shared memory stays alive until every CTA has read it
+}
+
+template <bool kBatch>
+__global__ void __launch_bounds__(SEED_THREADS) seed_enum_kernel(SeedGrids g, SeedState st1, const EvalParams* __restrict__ slots,
+                                                                 SeedWork wk) {
+  extern __shared__ __align__(16) unsigned char seed_smem_local[];
+  SeedClusterSync sy{cg::this_cluster()};
+  const int csize = sy.size();
+  const int sc = blockIdx.x / csize;
+  pdl_launch_dependents();                                      // the evaluation kernel behind may start being placed
+  if (kBatch) pdl_wait();                                       // the slot records are written by the previous cycle's hand-off
+  if (kBatch && !slot_live(slots, sc)) return;                  // cluster-uniform
+  const SeedState st = kBatch ? seed_state_of(slots, sc) : st1;
+  unsigned char* seed_smem = csize > 1 ? sy.c.map_shared_rank(seed_smem_local, 0) : seed_smem_local;
+  seed_enum_body(g, st, wk, sy, seed_smem, wk.seeds + (size_t)sc * wk.cap_seeds * 10, wk.counts + (size_t)sc * 4);
+  sy.sync();                                                    // CTA 0's shared memory stays alive until every CTA has read it
 }
 
 }  // namespace jssp
