@@ -412,6 +412,37 @@ __host__ __device__ inline SmemLayout eval_smem_layout(int win_rows, int OMpad, 
   return L;
 }
 
+// Lateral quintic samples [W][P][4] = d, d_d, d_dd, d_ddd (jerk_space_sampling_planner.py:118-122) and the per-width lateral
+// cost sums: one warp per width, lane l adds samples l, l + 32, ... in time order, then a fixed shuffle tree (deterministic;
+// every kernel stages its tables through this function, so all of them see the same sums).  Ends with a block barrier.
+__device__ __forceinline__ void stage_lateral(const EvalParams& p, const double* sm_time, double* sm_lat, double* sm_latcost) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int e = tid; e < p.W * p.P; e += nt) {
+    const int w = e / p.P, i = e - w * p.P;
+    double d, d1, d2, d3;
+    quintic_eval(p.quintic[w], sm_time[i], d, d1, d2, d3);
+    double* o = sm_lat + (size_t)e * 4;
+    o[0] = d; o[1] = d1; o[2] = d2; o[3] = d3;
+  }
+  __syncthreads();
+  for (int w = tid >> 5; w < p.W; w += nt >> 5) {
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int i = tid & 31; i < p.P; i += 32) {
+      const double* o = sm_lat + ((size_t)w * p.P + i) * 4;
+      const double e1 = fmax(fabs(o[2]) - p.thr_lat_a, 0.0), e2 = fmax(fabs(o[3]) - p.thr_lat_j, 0.0);
+      s0 = s0 + o[0] * o[0]; s1 = s1 + e1 * e1; s2 = s2 + e2 * e2;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s0 = s0 + __shfl_down_sync(0xffffffffu, s0, off);
+      s1 = s1 + __shfl_down_sync(0xffffffffu, s1, off);
+      s2 = s2 + __shfl_down_sync(0xffffffffu, s2, off);
+    }
+    if ((tid & 31) == 0) { sm_latcost[w * 4] = s0; sm_latcost[w * 4 + 1] = s1; sm_latcost[w * 4 + 2] = s2; }
+  }
+  __syncthreads();
+}
+
 // Stage the per-block tables: obstacle window by bulk copy (TMA engine; one row per issued copy, all completing on one
 // mbarrier), spline, time grid and the lateral quintic samples (jerk_space_sampling_planner.py:118-122) by ordinary loads.
 template <int kMode>
@@ -447,32 +478,7 @@ __device__ __forceinline__ void stage_tables(const EvalParams& p, unsigned char*
   }
   if (kSmem) for (int e = rows_avail * p.OMpad + tid; e < p.win_rows * p.OMpad; e += nt) sm_broad[e] = make_float4(0.f, 0.f, FAR_AWAY, 0.f);
   mbar_wait(bar, 0);
-  for (int e = tid; e < p.W * p.P; e += nt) {
-    const int w = e / p.P, i = e - w * p.P;
-    double d, d1, d2, d3;
-    quintic_eval(p.quintic[w], sm_time[i], d, d1, d2, d3);
-    double* o = sm_lat + (size_t)e * 4;
-    o[0] = d; o[1] = d1; o[2] = d2; o[3] = d3;
-  }
-  __syncthreads();
-  // per-width lateral cost sums: one warp per width, lane l adds samples l, l + 32, ... in time order, then a fixed
-  // shuffle tree (deterministic; every kernel stages its tables through this function, so all of them see the same sums)
-  for (int w = tid >> 5; w < p.W; w += nt >> 5) {
-    double s0 = 0, s1 = 0, s2 = 0;
-    for (int i = tid & 31; i < p.P; i += 32) {
-      const double* o = sm_lat + ((size_t)w * p.P + i) * 4;
-      const double e1 = fmax(fabs(o[2]) - p.thr_lat_a, 0.0), e2 = fmax(fabs(o[3]) - p.thr_lat_j, 0.0);
-      s0 = s0 + o[0] * o[0]; s1 = s1 + e1 * e1; s2 = s2 + e2 * e2;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      s0 = s0 + __shfl_down_sync(0xffffffffu, s0, off);
-      s1 = s1 + __shfl_down_sync(0xffffffffu, s1, off);
-      s2 = s2 + __shfl_down_sync(0xffffffffu, s2, off);
-    }
-    if ((tid & 31) == 0) { sm_latcost[w * 4] = s0; sm_latcost[w * 4 + 1] = s1; sm_latcost[w * 4 + 2] = s2; }
-  }
-  __syncthreads();
+  stage_lateral(p, sm_time, sm_lat, sm_latcost);
   if (kSmem) {
     tb.broad = sm_broad; tb.broad_row0 = 0; tb.broad_stride = 1;
   } else {
@@ -623,6 +629,14 @@ __device__ __forceinline__ int resolve_n_seeds(const EvalParams& p) {
   return p.n_seeds_ptr ? min(p.n_seeds_ptr[2], p.seed_cap) : p.n_seeds_fixed;
 }
 
+// one seed row (j1, t1, ..., j5, t5) through L2-coherent loads: inside the persistent replay kernel the seeds are rewritten
+// every plan cycle of the same launch, so they must not come through the read-only (non-coherent) path
+__device__ __forceinline__ void load_seed_row(double (&r)[10], const double* src) {
+  const double2* q = reinterpret_cast<const double2*>(src);       // rows are 80 B: 16-byte aligned
+#pragma unroll
+  for (int c = 0; c < 5; ++c) { const double2 v = __ldcg(q + c); r[2 * c] = v.x; r[2 * c + 1] = v.y; }
+}
+
 __device__ __forceinline__ bool lex_less(double ca, int ia, double cb, int ib) {
   // (cost, index) lexicographic; index -1 = empty
   if (ib < 0) return ia >= 0;
@@ -690,7 +704,9 @@ __device__ __forceinline__ void export_block(const EvalParams& p, const BlockTab
   double row[JSSP_TRAJ_COLS];
   if (i < P) {
     LonProfile lp;
-    lon_profile_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
+    double seed[10];
+    load_seed_row(seed, p.seeds + (size_t)k * 10);
+    lon_profile_init(lp, seed, p.s0, p.v0, p.a0);
     lon_eval(lp, p.s0, p.v0, p.a0, tb.time[i], row[1], row[2], row[3], row[4]);
     row[0] = tb.time[i];
     row[5] = lat[i * 4]; row[6] = lat[i * 4 + 1]; row[7] = lat[i * 4 + 2]; row[8] = lat[i * 4 + 3];
@@ -713,7 +729,9 @@ __device__ __forceinline__ void export_block_global(const EvalParams& p, const B
   bool inr = false;
   for (int j = i; j < P; j += blockDim.x) {      // blockDim >= P in practice; the loop keeps small blocks correct
     LonProfile lp;
-    lon_profile_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
+    double seed[10];
+    load_seed_row(seed, p.seeds + (size_t)k * 10);
+    lon_profile_init(lp, seed, p.s0, p.v0, p.a0);
     double sd, sdd, sddd;
     lon_eval(lp, p.s0, p.v0, p.a0, tb.time[j], s, sd, sdd, sddd);
     double* r = out + (size_t)j * JSSP_TRAJ_COLS;

@@ -45,8 +45,10 @@ __host__ __device__ inline size_t tile_scratch_bytes(int W, int threads) { retur
 // segment table of one seed: the start state and jerk of each of the five segments (the same expressions as lon_profile_init:
 // bit-identical to the reference's segment end states), the durations and the asymmetric-epsilon boundaries of
 // get_one_frenet_trajectory's branch chain (polyvt_sampling.py:334-374)
-__device__ __forceinline__ void tile_profile_store(double* prof, const double* __restrict__ seed, double s0, double v0, double a0) {
+__device__ __forceinline__ void tile_profile_store(double* prof, const double* seed_row, double s0, double v0, double a0) {
   LonProfile lp;
+  double seed[10];
+  load_seed_row(seed, seed_row);
   lon_profile_init(lp, seed, s0, v0, a0);
   prof[0] = s0; prof[1] = v0; prof[2] = a0; prof[3] = lp.j1;
   prof[4] = lp.s1; prof[5] = lp.v1; prof[6] = lp.a1; prof[7] = lp.j2;
