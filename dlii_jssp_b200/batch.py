@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import JsspError, JsspCycleRecord, JsspFopIn, JsspScenarioIn, JsspScenarioResult, FLAG_FORCE_THREAD, FLAG_FORCE_WARP, FLAG_FORCE_GROUP, FLAG_FORCE_TILED
+from ._lib import JsspError, JsspCycleRecord, JsspFopIn, JsspScenarioIn, JsspScenarioResult, FLAG_FORCE_THREAD, FLAG_FORCE_WARP, FLAG_FORCE_GROUP, FLAG_FORCE_TILED, FLAG_LOCKSTEP
 from .engine import JsspConfig
 from .frenet import FrenetState, State
 from .geometry import CubicSpline2D
@@ -265,10 +265,13 @@ class BatchReplay:
         self._check(self.lib.jssp_batch_reset(self._h, self._n, self.stream), "jssp_batch_reset")
 
     def run(self, n_cycles: Optional[int] = None, kernel: Optional[str] = None):
-        """Enqueue ``n_cycles`` lock-step plan cycles (default: enough for every loaded scenario to finish).  Asynchronous."""
+        """Enqueue up to ``n_cycles`` plan cycles per scenario (default: enough for every loaded scenario to finish).  ``kernel``
+        None = the persistent replay kernel (one CTA per scenario loops over its cycles in one launch); "lockstep" = the lock-step
+        pipeline with its default evaluation kernel, "warp" / "thread" / "group" / "tiled" = lock-step with that kernel.
+        Asynchronous."""
         if n_cycles is None:
             n_cycles = max(min(p.n_cycles, self.C) for p in self._packed)
-        flags = {None: 0, "warp": FLAG_FORCE_WARP, "thread": FLAG_FORCE_THREAD, "group": FLAG_FORCE_GROUP, "tiled": FLAG_FORCE_TILED}[kernel]
+        flags = {None: 0, "warp": FLAG_FORCE_WARP, "thread": FLAG_FORCE_THREAD, "group": FLAG_FORCE_GROUP, "tiled": FLAG_FORCE_TILED, "lockstep": FLAG_LOCKSTEP}[kernel]
         self._check(self.lib.jssp_batch_run(self._h, self._n, int(n_cycles), flags, self.stream), "jssp_batch_run")
         return n_cycles
 

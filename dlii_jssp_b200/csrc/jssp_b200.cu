@@ -1176,6 +1176,7 @@ struct jssp_batch {
   std::vector<double*> d_poly;      // kinematics mode: the scenario's re-discretised reference line [n][6] (allocated on first use)
   std::vector<int> poly_cap;
   int max_smem_optin = 0;
+  int sm_count = 148;
   int64_t launches = 0;
   char cuda_err[256] = {0};
 };
@@ -1315,6 +1316,8 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   CKC(allow_max_dynamic_smem(evaluate_small_batch_kernel, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_group_batch_kernel<0>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_group_batch_kernel<1>, optin, &b->max_smem_optin));
+  CKC(allow_max_dynamic_smem(replay_persistent_kernel, optin, &b->max_smem_optin));
+  CKC(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device));
   CKC(allow_max_dynamic_smem(evaluate_tiled_batch_kernel<0>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_tiled_batch_kernel<1>, optin, &b->max_smem_optin));
   CKC(cudaDeviceSynchronize());
@@ -1597,6 +1600,23 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
     return JSSP_OK;
   }
   const int max_rows = (b->P + b->cfg.check_res - 1) / b->cfg.check_res;
+  // default: the persistent replay kernel - one CTA per scenario, every cycle of the call in ONE launch.  Few scenarios (at most
+  // one per SM) get 512 threads each, more get 256 so that two CTAs share an SM.
+  if (!(flags & (JSSP_FLAG_LOCKSTEP | JSSP_FLAG_FORCE_WARP | JSSP_FLAG_FORCE_THREAD | JSSP_FLAG_FORCE_GROUP | JSSP_FLAG_FORCE_TILED)) && !b->tune.lockstep) {
+    int threads = n_scenarios <= b->sm_count ? REPLAY_MAX_THREADS : 256;
+    if (b->tune.seed_threads == 256 || b->tune.seed_threads == 512) threads = b->tune.seed_threads;      // tools/ only
+    const int rows = b->max_OMpad > 0 ? max_rows : 0;
+    ReplaySmem RL = replay_smem_layout(b->max_kpad, b->P, b->W, rows, b->max_OMpad, b->seed_smem, threads);
+    if (RL.total > (size_t)b->max_smem_optin && threads > 256) { threads = 256; RL = replay_smem_layout(b->max_kpad, b->P, b->W, rows, b->max_OMpad, b->seed_smem, threads); }
+    if (RL.total <= (size_t)b->max_smem_optin) {
+      if (n_cycles > 0) {
+        replay_persistent_kernel<<<dim3((unsigned)n_scenarios, 1, 1), threads, RL.total, st>>>(b->grids, b->d_slots, b->seed_work, n_cycles, rows, b->max_OMpad, b->max_kpad);
+        b->launches += 1;
+        CKB(cudaGetLastError());
+      }
+      return JSSP_OK;
+    }
+  }
   // the evaluation kernel: one warp per candidate while the whole batch is small (latency), one thread per candidate otherwise
   const SmemLayout Ls = eval_smem_layout(0, b->max_OMpad, 0, b->max_K, b->max_kpad, b->P, b->W);
   const size_t small_bytes = Ls.total + small_scratch_bytes(b->P);
