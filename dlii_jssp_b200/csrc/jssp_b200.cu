@@ -1316,7 +1316,8 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   CKC(allow_max_dynamic_smem(evaluate_small_batch_kernel, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_group_batch_kernel<0>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_group_batch_kernel<1>, optin, &b->max_smem_optin));
-  CKC(allow_max_dynamic_smem(replay_persistent_kernel, optin, &b->max_smem_optin));
+  CKC(allow_max_dynamic_smem(replay_persistent_kernel<512>, optin, &b->max_smem_optin));
+  CKC(allow_max_dynamic_smem(replay_persistent_kernel<1024>, optin, &b->max_smem_optin));
   CKC(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device));
   CKC(allow_max_dynamic_smem(evaluate_tiled_batch_kernel<0>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_tiled_batch_kernel<1>, optin, &b->max_smem_optin));
@@ -1604,13 +1605,23 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   // one per SM) get 512 threads each, more get 256 so that two CTAs share an SM.
   if (!(flags & (JSSP_FLAG_LOCKSTEP | JSSP_FLAG_FORCE_WARP | JSSP_FLAG_FORCE_THREAD | JSSP_FLAG_FORCE_GROUP | JSSP_FLAG_FORCE_TILED)) && !b->tune.lockstep) {
     int threads = n_scenarios <= b->sm_count ? REPLAY_MAX_THREADS : 256;
-    if (b->tune.seed_threads == 256 || b->tune.seed_threads == 512) threads = b->tune.seed_threads;      // tools/ only
+    if (b->tune.seed_threads == 256 || b->tune.seed_threads == 512 || b->tune.seed_threads == 1024) threads = b->tune.seed_threads;      // tools/ only
     const int rows = b->max_OMpad > 0 ? max_rows : 0;
-    ReplaySmem RL = replay_smem_layout(b->max_kpad, b->P, b->W, rows, b->max_OMpad, b->seed_smem, threads);
-    if (RL.total > (size_t)b->max_smem_optin && threads > 256) { threads = 256; RL = replay_smem_layout(b->max_kpad, b->P, b->W, rows, b->max_OMpad, b->seed_smem, threads); }
+    // tile length: the default (~16 samples), shortened until the warps' tiles fit next to the tables
+    int tile_rounds = 0;
+    ReplaySmem RL = replay_smem_layout(b->max_kpad, b->P, b->W, rows, b->max_OMpad, b->seed_smem, threads, tile_rounds);
+    for (int r = tile_geom(b->W).R - 1; RL.total > (size_t)b->max_smem_optin && r >= 1; --r) {
+      tile_rounds = r;
+      RL = replay_smem_layout(b->max_kpad, b->P, b->W, rows, b->max_OMpad, b->seed_smem, threads, tile_rounds);
+    }
+    if (RL.total > (size_t)b->max_smem_optin && threads > 256) {
+      threads = 256; tile_rounds = 0;
+      RL = replay_smem_layout(b->max_kpad, b->P, b->W, rows, b->max_OMpad, b->seed_smem, threads, tile_rounds);
+    }
     if (RL.total <= (size_t)b->max_smem_optin) {
       if (n_cycles > 0) {
-        replay_persistent_kernel<<<dim3((unsigned)n_scenarios, 1, 1), threads, RL.total, st>>>(b->grids, b->d_slots, b->seed_work, n_cycles, rows, b->max_OMpad, b->max_kpad);
+        if (threads > 512) replay_persistent_kernel<1024><<<dim3((unsigned)n_scenarios, 1, 1), threads, RL.total, st>>>(b->grids, b->d_slots, b->seed_work, n_cycles, rows, b->max_OMpad, b->max_kpad, tile_rounds);
+        else replay_persistent_kernel<512><<<dim3((unsigned)n_scenarios, 1, 1), threads, RL.total, st>>>(b->grids, b->d_slots, b->seed_work, n_cycles, rows, b->max_OMpad, b->max_kpad, tile_rounds);
         b->launches += 1;
         CKB(cudaGetLastError());
       }
@@ -1689,6 +1700,8 @@ int32_t jssp_batch_best_traj(jssp_batch* b, int32_t slot, double* out, void* str
 }
 
 #ifdef JSSP_PROFILE_PHASES
+/* persistent replay kernel: per-stage nanoseconds of scenario 0 (see jssp_replay.cuh) */
+int32_t jssp_debug_replay_phases(unsigned long long* host8) { return cudaMemcpyFromSymbol(host8, g_replay_ns, sizeof(g_replay_ns)) == cudaSuccess ? JSSP_OK : JSSP_ERR_CUDA; }
 /* same for the batched replay (tools/batch_phase_probe.py): [scenarios * blocks][8]; call before jssp_batch_set_scenario */
 int32_t jssp_batch_debug_phase_buffer(jssp_batch* b, unsigned long long* dev) { if (!b) return JSSP_ERR_INVALID_ARG; b->phase_ts = dev; return JSSP_OK; }
 #endif

@@ -28,11 +28,12 @@ struct TileGeom {
   int grp_stride;   // doubles between the tiles of two groups (TL * 4 + 2: neighbouring groups land 16 B apart in the banks)
   int warp_doubles; // doubles of scratch per warp
 };
-__host__ __device__ inline TileGeom tile_geom(int W) {
+__host__ __device__ inline TileGeom tile_geom(int W, int rounds = 0) {
   TileGeom g;
   g.gpw = 32 / W;
   const int r_want = (16 + W - 1) / W, r_cap = 160 / (g.gpw * W);     // ~16 samples per tile, at most ~160 entries per warp
   g.R = r_want < r_cap ? r_want : r_cap;
+  if (rounds > 0) g.R = rounds;                                        // caller's choice (shared-memory budget of many warps)
   if (g.R < 1) g.R = 1;
   g.TL = g.R * W;
   g.grp_stride = g.TL * 4 + 2;
@@ -40,7 +41,7 @@ __host__ __device__ inline TileGeom tile_geom(int W) {
   g.warp_doubles = (g.warp_doubles + 1) & ~1;
   return g;
 }
-__host__ __device__ inline size_t tile_scratch_bytes(int W, int threads) { return (size_t)(threads / 32) * tile_geom(W).warp_doubles * 8; }
+__host__ __device__ inline size_t tile_scratch_bytes(int W, int threads, int rounds = 0) { return (size_t)(threads / 32) * tile_geom(W, rounds).warp_doubles * 8; }
 
 // segment table of one seed: the start state and jerk of each of the five segments (the same expressions as lon_profile_init:
 // bit-identical to the reference's segment end states), the durations and the asymmetric-epsilon boundaries of
@@ -102,11 +103,147 @@ struct TileSAt {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Phase-2 arithmetic: float64 only where cancellation needs it, float32 for the rest, float64 re-decision inside guard bands.
+//   float64: the candidate's position (2 FMA), the forward difference (2 ADD), and cross / dot of two consecutive difference
+//            vectors (2 MUL + 2 FMA) - these carry the angle between the segments exactly, at any speed;
+//   float32: segment lengths (MUFU.RSQ + one Newton step), sin(kmax * ds) by its series, the comparison
+//            |cross| > sin(phi) * |p| * |d|  (<=> |angle| > phi for |angle| < pi/2), the unit heading for the collision rows;
+//   float64 re-decision (the oracle's own expression, atan2 of both differences): inside a 4e-6 relative band around the
+//            threshold, for segments shorter than 1e-8 m, for phi >= 0.49 and when the un-unwrapped heading difference jumps
+//            by 2*pi (exact signs).  Masks therefore equal the float64 evaluation except on measure-zero inputs.
+// ---------------------------------------------------------------------------------------------------------------------
+struct TileSink {
+  const EvalParams& p;
+  const BlockTables& tb;
+  double sum_a = 0, sum_j = 0, sum_v = 0, s_first = 0, s_last = 0, risk = 0;
+  double pdx = 0, pdy = 0;                              // previous segment: float64 difference vector
+  float pqf = 0.f, pdsf = 0.f;                          // its squared length and length (float32)
+  int next_check = 0, row = 0;                          // next sample index to collision-check and its window row
+  bool curv_fail = false, collided = false;
+  __device__ __forceinline__ TileSink(const EvalParams& p_, const BlockTables& tb_) : p(p_), tb(tb_) {}
+  __device__ __forceinline__ bool vetoed() const { return p.select_only && (curv_fail || collided); }
+
+  // the float64 decision, exactly as the other kernels' guard-band path: c = (yaw_i - yaw_{i-1}) / ds_{i-1} without unwrapping
+  __device__ __noinline__ static bool curvature_exact(double kmax, double pdx, double pdy, double dx, double dy) {
+    const double q = pdx * pdx + pdy * pdy;
+    const double pds = (q > 1e-200 && q < 1e200) ? q * rsqrt_fast(q) : hypot(pdx, pdy);
+    const double dyaw = heading_of(dx, dy) - heading_of(pdx, pdy);
+    return fabs(dyaw) > kmax * pds;                    // pds == 0: inf fails (dyaw != 0), nan passes (dyaw == 0)
+  }
+
+  // segment (dx, dy) [float64] with squared length qf / length dsf [float32] follows the stored previous segment
+  __device__ __forceinline__ bool curvature_fails_fast(double dx, double dy, float qf, float dsf) const {
+    const float phif = (float)p.kmax * pdsf;
+    bool exact = !(pqf > 1e-16f && pqf < 1e30f) || !(qf > 1e-16f && qf < 1e30f) || !(phif < 0.49f);
+    if (!exact) {
+      const double cross = fma(pdx, dy, -(pdy * dx)), dot = fma(pdx, dx, pdy * dy);
+      const bool nb = signbit(dy);
+      if ((signbit(pdy) != nb) && (nb ? (cross > 0.0) : (cross < 0.0))) exact = true;      // the difference jumps by 2*pi: rare
+      else if (!(dot > 0.0)) return true;                                                     // |angle| >= pi/2 > phi
+      else {
+        const float p2 = phif * phif;
+        const float spf = phif * fmaf(p2, fmaf(p2, fmaf(p2, -1.0f / 5040.0f, 1.0f / 120.0f), -1.0f / 6.0f), 1.0f);
+        const float lhs = (float)fabs(cross), rhs = spf * pdsf * dsf;
+        if (fabsf(lhs - rhs) > 4e-6f * fmaxf(lhs, rhs)) return lhs > rhs;
+        exact = true;
+      }
+    } else if (dx == 0.0 && dy == 0.0 && pdx == 0.0 && pdy == 0.0) {
+      return false;                                     // standstill: both headings are atan2(0, 0) = 0, 0 / 0 = nan passes
+    }
+    return curvature_exact(p.kmax, pdx, pdy, dx, dy);
+  }
+
+  // separating-axis test with the float32 heading (cf, snf); inside the guard band the float64 heading is derived from the
+  // float64 difference vector (hdx, hdy) of the heading segment and the pair is re-decided in float64
+  __device__ __forceinline__ bool narrow_hit_lazy(int abs_step, int om, float dxo, float dyo, double x, double y, float cf, float snf,
+                                                  double hdx, double hdy) const {
+    const size_t gi = (size_t)abs_step * p.OM + om;
+    const float4 nb = __ldg(p.narrow + gi);
+    const int cls = sat_classify_f32(dxo, dyo, cf, snf, (float)p.ea, (float)p.eb, nb.x, nb.y, nb.z, nb.w, SAT_EPS);
+    if (cls != 0) return cls < 0;
+    const double q = hdx * hdx + hdy * hdy;
+    double c = 1.0, sn = 0.0;
+    if (q > 1e-200 && q < 1e200) { const double inv = rsqrt_fast(q); c = hdx * inv; sn = hdy * inv; }
+    else { const double ds = hypot(hdx, hdy); if (ds > 0.0) { c = hdx / ds; sn = hdy / ds; } }
+    const double* o = p.obs64 + gi * 4;
+    return sat_intersects_f64(o[0] - x, o[1] - y, c, sn, p.ea, p.eb, o[2], o[3], p.ext64[2 * om], p.ext64[2 * om + 1]);
+  }
+
+  // collision row of sample i (pose (x, y), heading of the segment (hdx, hdy)) - same semantics as collide_row
+  __device__ __forceinline__ void collide(int i, double x, double y, double hdx, double hdy, float hqf) {
+    if (i != next_check) return;                        // i % check_res == 0 without the division
+    next_check += p.check_res;
+    const int r = row++;
+    if (collided || p.n_dict <= 0 || i >= p.tcap) return;
+    const int abs_step = p.now + i;
+    if (abs_step >= p.Tt) return;
+    float cf = 1.0f, snf = 0.0f;
+    if (hqf > 1e-16f && hqf < 1e30f) { const float inv = rsqrtf(hqf); cf = (float)hdx * inv; snf = (float)hdy * inv; }
+    else { const double ds = hypot(hdx, hdy); if (ds > 0.0) { cf = (float)(hdx / ds); snf = (float)(hdy / ds); } }
+    const float fx = (float)(x - p.ox), fy = (float)(y - p.oy);
+    const float m2x = -2.0f * fx, m2y = -2.0f * fy, ne2 = -fmaf(fx, fx, fy * fy);
+    if (tb.use_lists) {      // block-level culled rows: a handful of entries instead of OMpad
+      const int cnt = tb.row_cnt[r];
+      const float4* e = tb.list + tb.row_off[r];
+      for (int k = 0; k < cnt; ++k) {
+        const float4 b = e[k];
+        if (fmaf(b.x, m2x, fmaf(b.y, m2y, b.z)) <= ne2) {
+          const int om = __float_as_int(b.w);
+          if (narrow_hit_lazy(abs_step, om, b.x - fx, b.y - fy, x, y, cf, snf, hdx, hdy)) {
+            const float pr = __ldg(p.probf + om);
+            if ((double)pr >= p.p_min) { collided = true; return; }
+            risk = risk + (double)pr;
+          }
+        }
+      }
+      return;
+    }
+    const float4* rowp = tb.broad + (size_t)(tb.broad_row0 + r * tb.broad_stride) * p.OMpad;
+    for (int base = 0; base < p.OM; base += 32) {
+      unsigned int mask = 0u;
+      const int nj = min(32, p.OM - base);
+#pragma unroll 4
+      for (int q = 0; q < nj; ++q) {
+        const float4 b = rowp[base + q];
+        mask |= (fmaf(b.x, m2x, fmaf(b.y, m2y, b.z)) <= ne2) ? (1u << q) : 0u;
+      }
+      while (mask) {      // rare: bounding circles overlap -> separating-axis test
+        const int om = base + __ffs(mask) - 1;
+        mask &= mask - 1u;
+        const float4 b = rowp[om];
+        if (narrow_hit_lazy(abs_step, om, b.x - fx, b.y - fy, x, y, cf, snf, hdx, hdy)) {
+          if ((double)b.w >= p.p_min) { collided = true; return; }
+          risk = risk + (double)b.w;
+        }
+      }
+    }
+  }
+
+  // segment i = p_{i+1} - p_i arrives: curvature against segment i - 1, collision row of sample i, shift
+  __device__ __forceinline__ void segment(int i, double x, double y, double dx, double dy) {
+    const float dxf = (float)dx, dyf = (float)dy;
+    const float qf = fmaf(dxf, dxf, dyf * dyf);
+    float dsf = 0.f;
+    if (qf > 1e-16f && qf < 1e30f) { float inv = rsqrtf(qf); inv = inv * fmaf(-0.5f * qf, inv * inv, 1.5f); dsf = qf * inv; }
+    if (i >= 1 && curvature_fails_fast(dx, dy, qf, dsf)) curv_fail = true;
+    collide(i, x, y, dx, dy, qf);
+    pdx = dx; pdy = dy; pqf = qf; pdsf = dsf;
+  }
+  __device__ __forceinline__ void finish(int n_pts, double x, double y) {
+    if (n_pts >= 2) collide(n_pts - 1, x, y, pdx, pdy, pqf);                // last point reuses the previous heading (:158-160)
+    else if (n_pts == 1 && p.n_dict > 0 && p.tcap >= 1) collided = true;    // bare except -> collision (:250-254)
+  }
+};
+__device__ __forceinline__ double candidate_cost(const EvalParams& p, const TileSink& k, const double* latcost) {
+  return candidate_cost(p, k.sum_a, k.sum_j, k.sum_v, k.s_first, k.s_last, k.risk, latcost);
+}
+
 // The tiled walk of the candidate in lane (g, j): g = group (seed) within the warp, j = lateral target.  `gbase` = this group's
 // tile, `prof` = this group's segment table (already stored), both in the warp's scratch.  Inactive lanes (no seed) only keep
 // the warp-level barriers company.  On return `sink` holds the masks, the risk term and the longitudinal cost sums.
 __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTables& tb, const TileGeom& tg, double* gbase, double* prof,
-                                           bool active, int j, int W, EvalSink& sink) {
+                                           bool active, int j, int W, TileSink& sink) {
   const int P = p.P, TL = tg.TL;
   const double* lat = tb.lat + (size_t)j * P * 4;
   int k = 0, n_pts = P;
@@ -149,12 +286,7 @@ __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTable
         const double d = lat[i * 4];
         const double x = fma(-d, uv.x, pxy.x), y = fma(d, uv.y, pxy.y);
         if (i >= 1) {
-          const double dx = x - xp, dy = y - yp;
-          const double q = fma(dx, dx, dy * dy);
-          double ds, c = 1.0, sn = 0.0;
-          if (q > 1e-200 && q < 1e200) { const double inv = rsqrt_fast(q); ds = q * inv; c = dx * inv; sn = dy * inv; }
-          else { ds = hypot(dx, dy); if (ds > 0.0) { c = dx / ds; sn = dy / ds; } }
-          sink.segment(i - 1, xp, yp, dx, dy, ds, c, sn);
+          sink.segment(i - 1, xp, yp, x - xp, y - yp);
           if (sink.vetoed()) { walking = false; break; }     // select-only evaluation: this candidate can no longer be selected
         }
         xp = x; yp = y;
@@ -205,7 +337,7 @@ __device__ __forceinline__ void evaluate_tiled_body(const EvalParams& p, unsigne
     __syncwarp();
     if (kMode == 2) { TileSAt s_at{prof}; build_lists(p, smem, tb, s_at, active, j, W); }
     PHASE(p, 2);
-    EvalSink sink(p, tb);
+    TileSink sink(p, tb);
     walk_tiles(p, tb, tg, gbase, prof, active, j, W, sink);
     if (active) {
       const int n = j * Ns + k;                // candidate index: width-major (jerk_space_sampling_planner.py:106,124-125)

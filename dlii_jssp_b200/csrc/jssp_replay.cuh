@@ -23,6 +23,16 @@ namespace jssp {
 
 constexpr int REPLAY_MAX_THREADS = 512;
 
+#ifdef JSSP_PROFILE_PHASES
+// profiling builds only (tools/replay_phase_probe.py): nanoseconds scenario 0 spent in each stage, summed over its cycles:
+// 0 slot load, 1 seed enumeration, 2 staging, 3 tiled evaluation, 4 selection + export + hand-off, 5 cycles, 6 passes
+__device__ unsigned long long g_replay_ns[8];
+#define RSTAMP(k) do { __syncthreads(); if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+                        g_replay_ns[k] += t_ - t_prev; t_prev = t_; } } while (0)
+#else
+#define RSTAMP(k)
+#endif
+
 struct ReplaySmem {
   size_t off_knot, off_coef, off_time, off_union;       // resident part
   size_t off_lat, off_latcost, off_window, off_tile;    // evaluation view of the union
@@ -30,7 +40,8 @@ struct ReplaySmem {
 };
 // sized by the host for the LARGEST scenario of the batch (K, kpad, OMpad, rows) and evaluated by a CTA for its own scenario:
 // a scenario's view never exceeds the launch's
-__host__ __device__ inline ReplaySmem replay_smem_layout(int kpad, int P, int W, int win_rows, int OMpad, size_t seed_bytes, int threads) {
+__host__ __device__ inline ReplaySmem replay_smem_layout(int kpad, int P, int W, int win_rows, int OMpad, size_t seed_bytes, int threads,
+                                                         int tile_rounds = 0) {
   ReplaySmem L;
   size_t o = 16;                                         // mbarrier
   L.off_knot = o; o += (size_t)kpad * 8;
@@ -43,18 +54,19 @@ __host__ __device__ inline ReplaySmem replay_smem_layout(int kpad, int P, int W,
   L.off_latcost = e; e += (size_t)W * 4 * 8;
   L.off_window = e; e += (size_t)win_rows * OMpad * 16;
   e = (e + 15) & ~(size_t)15;
-  L.off_tile = e; e += tile_scratch_bytes(W, threads);
+  L.off_tile = e; e += tile_scratch_bytes(W, threads, tile_rounds);
   const size_t s = o + ((seed_bytes + 15) & ~(size_t)15);
   L.total = e > s ? e : s;
   return L;
 }
 
-__global__ void __launch_bounds__(REPLAY_MAX_THREADS, 1) replay_persistent_kernel(SeedGrids g, const EvalParams* __restrict__ slots, SeedWork wk,
-                                                                                   int n_cycles, int max_rows, int max_OMpad, int max_kpad) {
+template <int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedGrids g, const EvalParams* __restrict__ slots, SeedWork wk,
+                                                                                   int n_cycles, int max_rows, int max_OMpad, int max_kpad, int tile_rounds) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(16) EvalParams sp;
-  __shared__ double red_cost[REPLAY_MAX_THREADS / 32];
-  __shared__ int red_idx[REPLAY_MAX_THREADS / 32];
+  __shared__ double red_cost[kMaxThreads / 32];
+  __shared__ int red_idx[kMaxThreads / 32];
   __shared__ bool is_last;
   __shared__ int sm_npts;
   const int sc = blockIdx.x;
@@ -63,7 +75,7 @@ __global__ void __launch_bounds__(REPLAY_MAX_THREADS, 1) replay_persistent_kerne
   const int lane = tid & 31, wid = tid >> 5, nwarps = nt >> 5;
   load_slot(&sp, slots + sc);
   // the launch's layout (the union must start where the largest scenario's resident part ends)
-  const ReplaySmem L = replay_smem_layout(max_kpad, sp.P, sp.W, max_rows, max_OMpad, seed_smem_bytes(wk), nt);
+  const ReplaySmem L = replay_smem_layout(max_kpad, sp.P, sp.W, max_rows, max_OMpad, seed_smem_bytes(wk), nt, tile_rounds);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   double* sm_knot = reinterpret_cast<double*>(smem + L.off_knot);
   double* sm_coef = reinterpret_cast<double*>(smem + L.off_coef);
@@ -86,7 +98,7 @@ __global__ void __launch_bounds__(REPLAY_MAX_THREADS, 1) replay_persistent_kerne
     mbar_wait(bar, 0);
   }
   const int W = sp.W;
-  const TileGeom tg = tile_geom(W);
+  const TileGeom tg = tile_geom(W, tile_rounds);
   const int g_ = lane / W, j = lane - g_ * W;
   const int spb = nwarps * tg.gpw;                        // seeds per pass of the block
   double* wscr = sm_tile + (size_t)wid * tg.warp_doubles;
@@ -95,9 +107,14 @@ __global__ void __launch_bounds__(REPLAY_MAX_THREADS, 1) replay_persistent_kerne
   double* seeds = wk.seeds + (size_t)sc * wk.cap_seeds * 10;
   int* counts = wk.counts + (size_t)sc * 4;
 
+#ifdef JSSP_PROFILE_PHASES
+  unsigned long long t_prev = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { for (int q = 0; q < 8; ++q) g_replay_ns[q] = 0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_prev)); }
+#endif
   for (int c = 0; c < n_cycles; ++c) {
     if (c > 0) load_slot(&sp, slots + sc);                // the hand-off wrote the next cycle's inputs into the slot record
     if (!sp.batch->live) break;                           // block-uniform
+    RSTAMP(0);
     // -- K1: seed enumeration by the whole CTA (survivor lists in the union region) --------------------------------------
     {
       SeedBlockSync sy;
@@ -105,6 +122,7 @@ __global__ void __launch_bounds__(REPLAY_MAX_THREADS, 1) replay_persistent_kerne
       seed_enum_body(g, st, wk, sy, smem + L.off_union, seeds, counts);
     }
     __syncthreads();                                      // seeds + counts (global) are visible to the block; the lists are dead
+    RSTAMP(1);
     // -- K2: evaluation ---------------------------------------------------------------------------------------------------
     const int Ns = min(__ldcg(counts + 2), sp.seed_cap);
     const int N = Ns * W;
@@ -128,12 +146,13 @@ __global__ void __launch_bounds__(REPLAY_MAX_THREADS, 1) replay_persistent_kerne
     const double* latcost = sm_latcost;
     double my_cost = INFINITY;
     int my_idx = -1;
+    RSTAMP(2);
     for (int base = 0; base < Ns; base += spb) {           // block-uniform trip count
       const int k = base + wid * tg.gpw + g_;
       const bool active = g_ < tg.gpw && k < Ns;
       if (active && j == 0) tile_profile_store(prof, seeds + (size_t)k * 10, sp.s0, sp.v0, sp.a0);
       __syncwarp();
-      EvalSink sink(sp, tb);
+      TileSink sink(sp, tb);
       walk_tiles(sp, tb, tg, gbase, prof, active, j, W, sink);
       if (active) {
         const int n = j * Ns + k;                          // width-major candidate index (jerk_space_sampling_planner.py:106,124-125)
@@ -145,9 +164,14 @@ __global__ void __launch_bounds__(REPLAY_MAX_THREADS, 1) replay_persistent_kerne
       }
     }
     __syncthreads();
+    RSTAMP(3);
+#ifdef JSSP_PROFILE_PHASES
+    if (blockIdx.x == 0 && threadIdx.x == 0) { g_replay_ns[5] += 1; g_replay_ns[6] += (Ns + spb - 1) / spb; g_replay_ns[7] += Ns; }
+#endif
     // -- selection, export, hand-off (one block per scenario: the ticket logic of select_and_export sees a 1-block grid) ----
     select_and_export<1>(sp, smem, tb, latcost, true, my_cost, my_idx, N, Ns, red_cost, red_idx, &is_last, &sm_npts);
     __syncthreads();                                      // the hand-off's writes (slot record, replay state) are visible
+    RSTAMP(4);
   }
 }
 

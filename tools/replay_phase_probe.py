@@ -1,0 +1,31 @@
+"""Per-stage time of the persistent replay kernel (tools/, GPU, profiling build):
+    JSSP_NVCC_EXTRA=-DJSSP_PROFILE_PHASES python -m dlii_jssp_b200.build && JSSP_NVCC_EXTRA=-DJSSP_PROFILE_PHASES python tools/replay_phase_probe.py [n] [threads]
+Scenario 0's CTA stamps %globaltimer between the stages of every plan cycle."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import dlii_jssp_b200 as J
+from dlii_jssp_b200 import batch as B
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+packed = [B.pack_scenario(J.scenario.synthetic_intersection(i), max_cycles=100) for i in range(n)]
+packed = [p for p in packed if p.initial_end == -1]
+e = packed[0].ego
+cfg = J.JsspConfig(ego_length=float(e[5]), ego_width=float(e[6]), max_seeds=1024, max_knots=max(64, max(len(p.knot_s) for p in packed)),
+                   max_obstacle_modes=max(1, max(p.state.shape[0] * p.state.shape[1] for p in packed)), max_total_steps=max(p.state.shape[2] for p in packed))
+bt = B.BatchReplay(cfg, max_scenarios=len(packed), max_cycles=100)
+bt.load(packed)
+for _ in range(2):
+    bt.reset(); bt.run(100)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); bt.reset(); bt.run(100); e1.record(); torch.cuda.synchronize()
+ns = (C.c_ulonglong * 8)()
+bt.lib.jssp_debug_replay_phases.argtypes = [C.c_void_p]
+assert bt.lib.jssp_debug_replay_phases(ns) == 0
+cyc = max(int(ns[5]), 1)
+names = ["slot load", "seed enumeration", "staging", "tiled evaluation", "select + export + hand-off"]
+print(f"{len(packed)} scenarios, sweep {e0.elapsed_time(e1):.3f} ms; scenario 0: {cyc} cycles, {ns[6] / cyc:.2f} passes and {ns[7] / cyc:.0f} seeds per cycle")
+for k, nm in enumerate(names):
+    print(f"  {nm:28s} {ns[k] / cyc / 1e3:8.2f} us per cycle")
+print(f"  {'total':28s} {sum(ns[:5]) / cyc / 1e3:8.2f} us per cycle")
