@@ -774,8 +774,25 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   if (in->flags & (JSSP_FLAG_FORCE_GROUP | JSSP_FLAG_FORCE_TILED)) small = false;
   const bool group = !small && !(in->flags & JSSP_FLAG_FORCE_THREAD);
   // large cycles: the tiled two-phase kernel unless the shuffle form is asked for (or its scratch does not fit)
-  const size_t tile_bytes = tile_scratch_bytes(W, EVAL_THREADS);
-  const size_t tiled_total = ((L.total + 15) & ~(size_t)15) + tile_bytes;
+  // tile length of the tiled kernel: the longest (<= ~16 samples) with which two blocks still share an SM, else the longest that fits
+  int tile_rounds = 0;
+  size_t tiled_total = 0;
+  {
+    cudaFuncAttributes fa{};
+    cudaFuncGetAttributes(&fa, evaluate_tiled_kernel<2>);
+    const size_t per_sm = 228u * 1024u, two = per_sm / 2 - fa.sharedSizeBytes - 1024;
+    const size_t lbase = (L.total + 15) & ~(size_t)15;
+    for (int r = tile_rounds_wanted(W); r >= 1; --r) {
+      tile_rounds = r; tiled_total = lbase + tile_scratch_bytes(W, EVAL_THREADS, r);
+      if (tiled_total <= two) break;
+    }
+    if (tiled_total > two)                                  // not even the shortest tile leaves room for two blocks: one block, long tiles
+      for (int r = tile_rounds_wanted(W); r >= 1; --r) {
+        tile_rounds = r; tiled_total = lbase + tile_scratch_bytes(W, EVAL_THREADS, r);
+        if (tiled_total <= (size_t)h->max_smem_optin) break;
+      }
+  }
+  p.tile_rounds = tile_rounds;
   const bool tiled = group && !(in->flags & JSSP_FLAG_FORCE_GROUP) && tiled_total <= (size_t)h->max_smem_optin;
   const long long seeds_max = ext ? in->n_seeds : c.max_seeds;
   const int spb = group_seeds_per_block(W);
@@ -1610,7 +1627,14 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
     // tile length: the default (~16 samples), shortened until the warps' tiles fit next to the tables
     int tile_rounds = 0;
     ReplaySmem RL = replay_smem_layout(b->max_kpad, b->P, b->W, rows, b->max_OMpad, b->seed_smem, threads, tile_rounds);
-    for (int r = tile_geom(b->W).R - 1; RL.total > (size_t)b->max_smem_optin && r >= 1; --r) {
+    // persistent kernel: as long a tile as fits (<= ~16 samples); with 256-thread CTAs two of them share an SM
+    const size_t budget = threads <= 256 ? std::min((size_t)b->max_smem_optin, (size_t)(228 * 1024 / 2 - 10 * 1024)) : (size_t)b->max_smem_optin;
+    for (int r = tile_rounds_wanted(b->W); r >= 1; --r) {
+      tile_rounds = r;
+      RL = replay_smem_layout(b->max_kpad, b->P, b->W, rows, b->max_OMpad, b->seed_smem, threads, tile_rounds);
+      if (RL.total <= budget) break;
+    }
+    for (int r = tile_rounds - 1; RL.total > (size_t)b->max_smem_optin && r >= 1; --r) {
       tile_rounds = r;
       RL = replay_smem_layout(b->max_kpad, b->P, b->W, rows, b->max_OMpad, b->seed_smem, threads, tile_rounds);
     }
@@ -1647,7 +1671,7 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   SmemLayout L = eval_smem_layout(max_rows, b->max_OMpad, mode, b->max_K, b->max_kpad, b->P, b->W);
   if (mode == 1 && L.total > (size_t)b->max_smem_optin) { mode = 0; L = eval_smem_layout(0, b->max_OMpad, 0, b->max_K, b->max_kpad, b->P, b->W); }
   if (!small && L.total > (size_t)b->max_smem_optin) return JSSP_ERR_CAPACITY;
-  const size_t tiled_total = ((L.total + 15) & ~(size_t)15) + tile_scratch_bytes(b->W, bthreads);
+  const size_t tiled_total = ((L.total + 15) & ~(size_t)15) + tile_scratch_bytes(b->W, bthreads);     // default tile length (slot records carry tile_rounds = 0)
   const bool tiled = !small && (flags & JSSP_FLAG_FORCE_TILED) && tiled_total <= (size_t)b->max_smem_optin;
   // few scenarios: clusters of up to 8 CTAs x 1024 threads answer with the lowest latency; many: one 512-thread CTA each
   int seed_cluster = 1;

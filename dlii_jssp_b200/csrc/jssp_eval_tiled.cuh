@@ -11,9 +11,10 @@
 //            vector, tests the curvature (:155-180) and, on every check_res-th sample, the collision row (:233-286).
 // Only __syncwarp() separates the phases: warps are decoupled, one warp's phase 1 (throughput) overlaps another's phase 2
 // (latency).  Compared with the shuffle form (walk_group) nothing seed-only sits on the candidate's serial chain any more and
-// the 15 SHFL per sample are gone.  Seed-only arithmetic keeps the reference's unfused operand order (s, s_d, s_dd, s_ddd and
-// the cost terms are bit-identical to the other kernels' values); the geometry of phase 2 and the spline evaluation use
-// explicit fused multiply-adds (positions agree to an ulp; masks are decided by the same guard-banded tests).
+// the 15 SHFL per sample are gone.  Seed-only arithmetic keeps the reference's unfused operand order and the cost terms are
+// added strictly in time order (one lane per seed, from the tile), so s, s_d, s_dd, s_ddd and the COSTS are bit-identical to the
+// other kernels' and to the oracle's sequential sums - near-ties select the same candidate.  The spline evaluation and phase 2
+// use explicit fused multiply-adds and float32 with float64 guard-band re-decisions (see TileSink): masks unchanged.
 #pragma once
 #include "jssp_eval.cuh"
 
@@ -26,19 +27,24 @@ struct TileGeom {
   int R;            // phase-1 rounds per tile
   int TL;           // samples per tile = R * W
   int grp_stride;   // doubles between the tiles of two groups (TL * 4 + 2: neighbouring groups land 16 B apart in the banks)
+  int off_terms;    // doubles from the warp's scratch to its cost-term table [gpw][TL][3]
+  int off_prof;     // ... to its segment tables [gpw][TILE_PROF]
   int warp_doubles; // doubles of scratch per warp
 };
+__host__ __device__ inline int tile_rounds_wanted(int W) { return (16 + W - 1) / W; }     // ~16 samples per tile
 __host__ __device__ inline TileGeom tile_geom(int W, int rounds = 0) {
   TileGeom g;
   g.gpw = 32 / W;
-  const int r_want = (16 + W - 1) / W, r_cap = 160 / (g.gpw * W);     // ~16 samples per tile, at most ~160 entries per warp
+  const int r_want = tile_rounds_wanted(W), r_cap = 80 / (g.gpw * W);   // default: at most ~80 entries (~6 KB) per warp
   g.R = r_want < r_cap ? r_want : r_cap;
-  if (rounds > 0) g.R = rounds;                                        // caller's choice (shared-memory budget of many warps)
+  if (rounds > 0) g.R = rounds;                                        // caller's choice (shared-memory budget of the launch)
   if (g.R < 1) g.R = 1;
   g.TL = g.R * W;
   g.grp_stride = g.TL * 4 + 2;
-  g.warp_doubles = g.gpw * g.grp_stride + g.gpw * TILE_PROF;
-  g.warp_doubles = (g.warp_doubles + 1) & ~1;
+  g.off_terms = g.gpw * g.grp_stride;
+  g.off_prof = g.off_terms + g.gpw * g.TL * 3;
+  g.off_prof = (g.off_prof + 1) & ~1;
+  g.warp_doubles = g.off_prof + g.gpw * TILE_PROF;
   return g;
 }
 __host__ __device__ inline size_t tile_scratch_bytes(int W, int threads, int rounds = 0) { return (size_t)(threads / 32) * tile_geom(W, rounds).warp_doubles * 8; }
@@ -242,12 +248,12 @@ __device__ __forceinline__ double candidate_cost(const EvalParams& p, const Tile
 // The tiled walk of the candidate in lane (g, j): g = group (seed) within the warp, j = lateral target.  `gbase` = this group's
 // tile, `prof` = this group's segment table (already stored), both in the warp's scratch.  Inactive lanes (no seed) only keep
 // the warp-level barriers company.  On return `sink` holds the masks, the risk term and the longitudinal cost sums.
-__device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTables& tb, const TileGeom& tg, double* gbase, double* prof,
-                                           bool active, int j, int W, TileSink& sink) {
+__device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTables& tb, const TileGeom& tg, double* gbase, double* gterms,
+                                           double* prof, bool active, int j, int W, TileSink& sink) {
   const int P = p.P, TL = tg.TL;
   const double* lat = tb.lat + (size_t)j * P * 4;
   int k = 0, n_pts = P;
-  double pa = 0, pj = 0, pv = 0;                 // this lane's share of the longitudinal cost sums (its own samples, in time order)
+  double sa = 0, sj = 0, sv = 0;                 // lane 0 of the group: the longitudinal cost sums, added strictly in time order
   double xp = 0, yp = 0;
   bool walking = active;
   for (int base = 0; base < P; base += TL) {
@@ -261,7 +267,8 @@ __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTable
         const double ea = fmax(fabs(sdd) - p.thr_lon_a, 0.0);
         const double ej = fmax(fabs(sddd) - p.thr_lon_j, 0.0);
         const double ev = (p.vmax - sd) * p.inv_vmax;
-        pa = pa + ea * ea; pj = pj + ej * ej; pv = pv + ev * ev;
+        double* tm = gterms + il * 3;
+        tm[0] = ea * ea; tm[1] = ej * ej; tm[2] = ev * ev;
         if (i == 0) prof[28] = s;
         if (i == P - 1) prof[29] = s;
         double2* e = reinterpret_cast<double2*>(gbase + il * 4);
@@ -275,6 +282,11 @@ __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTable
       }
     }
     __syncwarp();
+    // the cost sums are sequential float64 sums over the samples (the oracle's order: costs bit-identical to the other kernels):
+    // one lane per seed adds the tile's terms - three short independent chains
+    if (active && j == 0) {
+      for (int il = 0; il < len; ++il) { sa = sa + gterms[il * 3]; sj = sj + gterms[il * 3 + 1]; sv = sv + gterms[il * 3 + 2]; }
+    }
     // phase 2: this lane's candidate
     if (walking) {
       for (int il = 0; il < len; ++il) {
@@ -295,13 +307,10 @@ __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTable
     __syncwarp();                                  // the tile is rewritten by the next phase 1
   }
   if (active && !sink.vetoed()) sink.finish(n_pts, xp, yp);
-  // cost sums of the seed = the group's partial sums in lane order (the same order for every seed: deterministic)
-  if (active) { gbase[j * 4] = pa; gbase[j * 4 + 1] = pj; gbase[j * 4 + 2] = pv; }
+  if (active && j == 0) { gbase[0] = sa; gbase[1] = sj; gbase[2] = sv; }
   __syncwarp();
   if (active) {
-    double sa = 0, sj = 0, sv = 0;
-    for (int q = 0; q < W; ++q) { sa = sa + gbase[q * 4]; sj = sj + gbase[q * 4 + 1]; sv = sv + gbase[q * 4 + 2]; }
-    sink.sum_a = sa; sink.sum_j = sj; sink.sum_v = sv;
+    sink.sum_a = gbase[0]; sink.sum_j = gbase[1]; sink.sum_v = gbase[2];
     sink.s_first = prof[28]; sink.s_last = prof[29];
   }
   __syncwarp();
@@ -313,7 +322,7 @@ __device__ __forceinline__ void evaluate_tiled_body(const EvalParams& p, unsigne
   const int Ns = resolve_n_seeds(p);
   const int W = p.W;
   const int N = Ns * W;
-  const TileGeom tg = tile_geom(W);
+  const TileGeom tg = tile_geom(W, p.tile_rounds);
   const int gpw = tg.gpw;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int g = lane / W, j = lane - g * W;
@@ -331,14 +340,16 @@ __device__ __forceinline__ void evaluate_tiled_body(const EvalParams& p, unsigne
     PHASE(p, 1);
     const SmemLayout L = eval_smem_layout(p.win_rows, p.OMpad, kMode, p.K, p.kpad, p.P, p.W, p.list_cap);
     double* wscr = reinterpret_cast<double*>(smem + ((L.total + 15) & ~(size_t)15)) + (size_t)wid * tg.warp_doubles;
-    double* gbase = wscr + (size_t)(g < gpw ? g : 0) * tg.grp_stride;
-    double* prof = wscr + (size_t)gpw * tg.grp_stride + (size_t)(g < gpw ? g : 0) * TILE_PROF;
+    const int gg = g < gpw ? g : 0;
+    double* gbase = wscr + (size_t)gg * tg.grp_stride;
+    double* gterms = wscr + tg.off_terms + (size_t)gg * tg.TL * 3;
+    double* prof = wscr + tg.off_prof + (size_t)gg * TILE_PROF;
     if (active && j == 0) tile_profile_store(prof, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
     __syncwarp();
     if (kMode == 2) { TileSAt s_at{prof}; build_lists(p, smem, tb, s_at, active, j, W); }
     PHASE(p, 2);
     TileSink sink(p, tb);
-    walk_tiles(p, tb, tg, gbase, prof, active, j, W, sink);
+    walk_tiles(p, tb, tg, gbase, gterms, prof, active, j, W, sink);
     if (active) {
       const int n = j * Ns + k;                // candidate index: width-major (jerk_space_sampling_planner.py:106,124-125)
       const double cost = candidate_cost(p, sink, latcost + j * 4);

@@ -102,8 +102,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
   const int g_ = lane / W, j = lane - g_ * W;
   const int spb = nwarps * tg.gpw;                        // seeds per pass of the block
   double* wscr = sm_tile + (size_t)wid * tg.warp_doubles;
-  double* gbase = wscr + (size_t)(g_ < tg.gpw ? g_ : 0) * tg.grp_stride;
-  double* prof = wscr + (size_t)tg.gpw * tg.grp_stride + (size_t)(g_ < tg.gpw ? g_ : 0) * TILE_PROF;
+  const int gg = g_ < tg.gpw ? g_ : 0;
+  double* gbase = wscr + (size_t)gg * tg.grp_stride;
+  double* gterms = wscr + tg.off_terms + (size_t)gg * tg.TL * 3;
+  double* prof = wscr + tg.off_prof + (size_t)gg * TILE_PROF;
   double* seeds = wk.seeds + (size_t)sc * wk.cap_seeds * 10;
   int* counts = wk.counts + (size_t)sc * 4;
 
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
       if (active && j == 0) tile_profile_store(prof, seeds + (size_t)k * 10, sp.s0, sp.v0, sp.a0);
       __syncwarp();
       TileSink sink(sp, tb);
-      walk_tiles(sp, tb, tg, gbase, prof, active, j, W, sink);
+      walk_tiles(sp, tb, tg, gbase, gterms, prof, active, j, W, sink);
       if (active) {
         const int n = j * Ns + k;                          // width-major candidate index (jerk_space_sampling_planner.py:106,124-125)
         const double cost = candidate_cost(sp, sink, latcost + j * 4);

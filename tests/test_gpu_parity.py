@@ -270,21 +270,12 @@ def test_warp_and_thread_kernels_agree(n_seeds, n_widths, O_, M, horizon, seed):
             out[kern] = (r.feasible.cpu().numpy().copy(), r.collision.cpu().numpy().copy(), r.cost.cpu().numpy().copy(), r.best_idx, r.best_cost,
                          r.best_n_pts, None if r.best_traj is None else r.best_traj.copy())
         b = out["thread"]
-        for a in (out["warp"], out["group"]):
+        for a in (out["warp"], out["group"], out["tiled"]):      # the tiled kernel adds its cost terms in time order too: bit-identical costs
             ok = a[1] == 0
             assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2][ok], b[2][ok])
             assert a[3:6] == b[3:6]
             if a[6] is not None:
                 assert np.array_equal(a[6], b[6], equal_nan=True)
-        # the tiled kernel: same masks, selection and exported trajectory; its cost sums add the per-lane partial sums of a seed
-        # (other order) and its positions use fused multiply-adds -> costs equal to rounding, not bit for bit
-        a = out["tiled"]
-        ok = a[1] == 0
-        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
-        np.testing.assert_allclose(a[2][ok], b[2][ok], rtol=2e-7, atol=0)
-        assert a[3] == b[3] and a[5] == b[5] and abs(a[4] - b[4]) <= 1e-12 * max(1.0, abs(b[4]))
-        if a[6] is not None:
-            assert np.array_equal(a[6], b[6], equal_nan=True)
         ref = O.plan_cycle(cfg, spline, fr, H.oracle_obstacles(cyc.obstacles), now, final, seeds=cyc.seeds, targets=cyc.targets)
         H.compare_cycle(eng.evaluate(fr, now, final, seeds=seeds, targets=cyc.targets, kernel="warp"), ref)
     eng.close()
