@@ -43,7 +43,10 @@ def _rank_main(rank, world, port, q):
         bits, gidx, winner = D.allgather_argmin(rec)
         c32, gidx32 = D.min_reduce_packed(cost, D.global_candidate_index(loc["best"], lo, hi - lo, len(cyc.seeds)))
         rows = D.gather_results([(rank, s) for s in D.shard_scenarios(range(7), world, rank)])
-        q.put((rank, D.orderable_bits_to_float(bits), gidx, winner, c32, gidx32, rows))
+        # the plumbing of the device-side exchange: per-rank byte strings (CUDA IPC handles) and the NCCL unique id
+        handles = D.gather_bytes(bytes([rank]) * 64)
+        uid = D.broadcast_bytes(bytes(range(128)) if rank == 0 else None, 128, 0)
+        q.put((rank, D.orderable_bits_to_float(bits), gidx, winner, c32, gidx32, rows, handles, uid))
     finally:
         dist.destroy_process_group()
 
@@ -65,7 +68,8 @@ def test_candidate_split_and_scenario_shards_world2():
     o = cyc.obstacles
     full = O.plan_cycle(cfg, spline, cyc.frenet0, (o.state, o.valid.astype(bool), o.size, o.prob), 0, cyc.final_time_step, seeds=cyc.seeds, targets=cyc.targets)
     assert full["best"] >= 0
-    for rank, cost, gidx, winner, c32, gidx32, rows in out:
+    for rank, cost, gidx, winner, c32, gidx32, rows, handles, uid in out:
+        assert handles == [bytes([r]) * 64 for r in range(world)] and uid == bytes(range(128))
         assert gidx == full["best"], (gidx, full["best"])                  # candidate-split argmin == single-GPU argmin
         assert cost == full["cost"][full["best"]]                            # float64 cost survives the record exactly
         lo, hi = D.shard_range(len(cyc.seeds), world, winner)
@@ -89,3 +93,8 @@ def test_shard_helpers_single_process():
     assert D.pack_key32(1.0, 3) < D.pack_key32(1.0, 4) < D.pack_key32(1.0000002, 0) < D.pack_key32(2.0, 0) < D.pack_key32(0.0, -1)
     assert D.min_reduce_packed(4.25, 12) == (4.25, 12) and D.min_reduce_packed(0.0, -1) == (None, -1)
     assert D.allgather_argmin(torch.tensor([D.float_to_orderable_bits(2.5), 41], dtype=torch.int64)) == (D.float_to_orderable_bits(2.5), 41, 0)
+    # sweep digest: independent of the order / sharding of the rows, sensitive to any selected index
+    rows = [("a", 1.5, 3, [1, 2, 3]), ("b", -1.0, 2, [0, 1]), ("c", 2.0, 0, [])]
+    assert D.sweep_digest(rows) == D.sweep_digest(rows[::-1]) == D.sweep_digest(rows[1:] + rows[:1])
+    assert D.sweep_digest(rows) != D.sweep_digest([("a", 1.5, 3, [1, 2, 4])] + rows[1:])
+    assert D.gather_bytes(b"xy") == [b"xy"] and D.broadcast_bytes(b"id", 2) == b"id"
