@@ -28,6 +28,7 @@ struct TileGeom {
   int TL;           // samples per tile = R * W
   int grp_stride;   // doubles between the tiles of two groups (TL * 4 + 2: neighbouring groups land 16 B apart in the banks)
   int off_terms;    // doubles from the warp's scratch to its cost-term table [gpw][TL][3]
+  int off_mask;     // ... to its collision masks [gpw][TL] (64-bit)
   int off_prof;     // ... to its segment tables [gpw][TILE_PROF]
   int warp_doubles; // doubles of scratch per warp
 };
@@ -42,7 +43,8 @@ __host__ __device__ inline TileGeom tile_geom(int W, int rounds = 0) {
   g.TL = g.R * W;
   g.grp_stride = g.TL * 4 + 2;
   g.off_terms = g.gpw * g.grp_stride;
-  g.off_prof = g.off_terms + g.gpw * g.TL * 3;
+  g.off_mask = g.off_terms + g.gpw * g.TL * 3;
+  g.off_prof = g.off_mask + g.gpw * g.TL;
   g.off_prof = (g.off_prof + 1) & ~1;
   g.warp_doubles = g.off_prof + g.gpw * TILE_PROF;
   return g;
@@ -115,55 +117,62 @@ struct TileSAt {
 //            vectors (2 MUL + 2 FMA) - these carry the angle between the segments exactly, at any speed;
 //   float32: segment lengths (MUFU.RSQ + one Newton step), sin(kmax * ds) by its series, the comparison
 //            |cross| > sin(phi) * |p| * |d|  (<=> |angle| > phi for |angle| < pi/2), the unit heading for the collision rows;
-//   float64 re-decision (the oracle's own expression, atan2 of both differences): inside a 4e-6 relative band around the
-//            threshold, for segments shorter than 1e-8 m, for phi >= 0.49 and when the un-unwrapped heading difference jumps
-//            by 2*pi (exact signs).  Masks therefore equal the float64 evaluation except on measure-zero inputs.
+//   float64 re-decision (the oracle's own expression, atan2 of both differences; out of line): inside a 4e-6 relative band
+//            around the threshold, for segments shorter than 1e-8 m, for phi >= 0.49 and when the un-unwrapped heading
+//            difference jumps by 2*pi (exact signs).  Masks therefore equal the float64 evaluation except on measure-zero inputs.
+// Collision rows: the bounding-circle test runs ONCE PER SEED in phase 1.5 (the W candidates of a seed lie within dmax of the
+// seed's reference point, so the circles are enlarged by dmax): the W lanes of a group share a row's entries and OR their hits
+// into a 64-bit mask per (seed, row).  Phase 2 only visits the set bits - usually none - with the candidate's own circle test
+// and, on a hit, the separating-axis test.
 // ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float circle_enlarge(const EvalParams& p, int om, float dmax) {
+  // pack_obstacles_kernel: R = r_ego + r_obs + BROAD_PAD, z = |o'|^2 - (R^2 * 1.0001 + BROAD_CANCEL);  (R + dmax)^2 = R^2 + 2 R dmax + dmax^2
+  const double a2 = p.ext64[2 * om], b2 = p.ext64[2 * om + 1];
+  const float r = (float)(sqrt(p.ea * p.ea + p.eb * p.eb) + sqrt(a2 * a2 + b2 * b2)) + 0.05f;
+  return (2.0f * r * dmax + dmax * dmax) * 1.0002f + 1e-4f;
+}
+
 struct TileSink {
   const EvalParams& p;
   const BlockTables& tb;
   double sum_a = 0, sum_j = 0, sum_v = 0, s_first = 0, s_last = 0, risk = 0;
   double pdx = 0, pdy = 0;                              // previous segment: float64 difference vector
   float pqf = 0.f, pdsf = 0.f;                          // its squared length and length (float32)
-  int next_check = 0, row = 0;                          // next sample index to collision-check and its window row
+  float kmaxf;
   bool curv_fail = false, collided = false;
-  __device__ __forceinline__ TileSink(const EvalParams& p_, const BlockTables& tb_) : p(p_), tb(tb_) {}
+  __device__ __forceinline__ TileSink(const EvalParams& p_, const BlockTables& tb_) : p(p_), tb(tb_), kmaxf((float)p_.kmax) {}
   __device__ __forceinline__ bool vetoed() const { return p.select_only && (curv_fail || collided); }
 
   // the float64 decision, exactly as the other kernels' guard-band path: c = (yaw_i - yaw_{i-1}) / ds_{i-1} without unwrapping
   __device__ __noinline__ static bool curvature_exact(double kmax, double pdx, double pdy, double dx, double dy) {
+    if (dx == 0.0 && dy == 0.0 && pdx == 0.0 && pdy == 0.0) return false;      // standstill: both headings atan2(0, 0) = 0; 0 / 0 = nan passes
     const double q = pdx * pdx + pdy * pdy;
     const double pds = (q > 1e-200 && q < 1e200) ? q * rsqrt_fast(q) : hypot(pdx, pdy);
     const double dyaw = heading_of(dx, dy) - heading_of(pdx, pdy);
     return fabs(dyaw) > kmax * pds;                    // pds == 0: inf fails (dyaw != 0), nan passes (dyaw == 0)
   }
 
-  // segment (dx, dy) [float64] with squared length qf / length dsf [float32] follows the stored previous segment
+  // segment (dx, dy) [float64] with squared length qf / length dsf [float32] follows the stored previous segment.
+  // Straight-line fast path (everything is computed, one decision at the end); the rare cases leave through curvature_exact.
   __device__ __forceinline__ bool curvature_fails_fast(double dx, double dy, float qf, float dsf) const {
-    const float phif = (float)p.kmax * pdsf;
-    bool exact = !(pqf > 1e-16f && pqf < 1e30f) || !(qf > 1e-16f && qf < 1e30f) || !(phif < 0.49f);
-    if (!exact) {
-      const double cross = fma(pdx, dy, -(pdy * dx)), dot = fma(pdx, dx, pdy * dy);
-      const bool nb = signbit(dy);
-      if ((signbit(pdy) != nb) && (nb ? (cross > 0.0) : (cross < 0.0))) exact = true;      // the difference jumps by 2*pi: rare
-      else if (!(dot > 0.0)) return true;                                                     // |angle| >= pi/2 > phi
-      else {
-        const float p2 = phif * phif;
-        const float spf = phif * fmaf(p2, fmaf(p2, fmaf(p2, -1.0f / 5040.0f, 1.0f / 120.0f), -1.0f / 6.0f), 1.0f);
-        const float lhs = (float)fabs(cross), rhs = spf * pdsf * dsf;
-        if (fabsf(lhs - rhs) > 4e-6f * fmaxf(lhs, rhs)) return lhs > rhs;
-        exact = true;
-      }
-    } else if (dx == 0.0 && dy == 0.0 && pdx == 0.0 && pdy == 0.0) {
-      return false;                                     // standstill: both headings are atan2(0, 0) = 0, 0 / 0 = nan passes
-    }
+    const float phif = kmaxf * pdsf;
+    const double cross = fma(pdx, dy, -(pdy * dx)), dot = fma(pdx, dx, pdy * dy);
+    const float p2 = phif * phif;
+    const float spf = phif * fmaf(p2, fmaf(p2, fmaf(p2, -1.0f / 5040.0f, 1.0f / 120.0f), -1.0f / 6.0f), 1.0f);
+    const float lhs = (float)fabs(cross), rhs = spf * pdsf * dsf;
+    const bool ranges = (pqf > 1e-16f) & (pqf < 1e30f) & (qf > 1e-16f) & (qf < 1e30f) & (phif < 0.49f);
+    const bool nb = signbit(dy);
+    const bool jump = (signbit(pdy) != nb) & (nb ? (cross > 0.0) : (cross < 0.0));       // the un-unwrapped difference jumps by 2*pi
+    const bool obtuse = !(dot > 0.0);                                                    // |angle| >= pi/2 > phi
+    const bool clear = fabsf(lhs - rhs) > 4e-6f * fmaxf(lhs, rhs);
+    if (ranges & !jump & (obtuse | clear)) return obtuse | (lhs > rhs);
     return curvature_exact(p.kmax, pdx, pdy, dx, dy);
   }
 
   // separating-axis test with the float32 heading (cf, snf); inside the guard band the float64 heading is derived from the
   // float64 difference vector (hdx, hdy) of the heading segment and the pair is re-decided in float64
-  __device__ __forceinline__ bool narrow_hit_lazy(int abs_step, int om, float dxo, float dyo, double x, double y, float cf, float snf,
-                                                  double hdx, double hdy) const {
+  __device__ __noinline__ static bool narrow_hit_lazy(const EvalParams& p, int abs_step, int om, float dxo, float dyo, double x, double y,
+                                                      float cf, float snf, double hdx, double hdy) {
     const size_t gi = (size_t)abs_step * p.OM + om;
     const float4 nb = __ldg(p.narrow + gi);
     const int cls = sat_classify_f32(dxo, dyo, cf, snf, (float)p.ea, (float)p.eb, nb.x, nb.y, nb.z, nb.w, SAT_EPS);
@@ -176,86 +185,107 @@ struct TileSink {
     return sat_intersects_f64(o[0] - x, o[1] - y, c, sn, p.ea, p.eb, o[2], o[3], p.ext64[2 * om], p.ext64[2 * om + 1]);
   }
 
-  // collision row of sample i (pose (x, y), heading of the segment (hdx, hdy)) - same semantics as collide_row
-  __device__ __forceinline__ void collide(int i, double x, double y, double hdx, double hdy, float hqf) {
-    if (i != next_check) return;                        // i % check_res == 0 without the division
-    next_check += p.check_res;
-    const int r = row++;
+  // one obstacle state whose (enlarged) circle the seed's reference point touched: the candidate's own circle test against the
+  // TRUE table entry, then the separating-axis test.  Returns true when the candidate is vetoed.
+  __device__ __forceinline__ bool visit(int abs_step, int om, float fx, float fy, float ne2, double x, double y, float cf, float snf,
+                                        double hdx, double hdy) {
+    const float4 b = __ldg(p.broad + (size_t)abs_step * p.OMpad + om);
+    if (!(fmaf(b.x, -2.0f * fx, fmaf(b.y, -2.0f * fy, b.z)) <= ne2)) return false;
+    if (!narrow_hit_lazy(p, abs_step, om, b.x - fx, b.y - fy, x, y, cf, snf, hdx, hdy)) return false;
+    if ((double)b.w >= p.p_min) { collided = true; return true; }
+    risk = risk + (double)b.w;
+    return false;
+  }
+
+  // collision row r of sample i (pose (x, y), heading of the segment (hdx, hdy)); `mask` = the seed's hits of this row
+  // (bit k = entry k of the row's list / table row; only used when tb.masks)
+  __device__ __forceinline__ void collide(int i, int r, double x, double y, double hdx, double hdy, float hqf, unsigned long long mask) {
     if (collided || p.n_dict <= 0 || i >= p.tcap) return;
     const int abs_step = p.now + i;
     if (abs_step >= p.Tt) return;
+    const int cnt = tb.use_lists ? tb.row_cnt[r] : p.OM;
+    const float4* e = tb.use_lists ? tb.list + tb.row_off[r] : tb.broad + (size_t)(tb.broad_row0 + r * tb.broad_stride) * p.OMpad;
+    const bool by_mask = tb.masks && cnt <= 64;
+    if (by_mask && mask == 0ull) return;                // the usual case: nothing near any candidate of this seed
     float cf = 1.0f, snf = 0.0f;
     if (hqf > 1e-16f && hqf < 1e30f) { const float inv = rsqrtf(hqf); cf = (float)hdx * inv; snf = (float)hdy * inv; }
     else { const double ds = hypot(hdx, hdy); if (ds > 0.0) { cf = (float)(hdx / ds); snf = (float)(hdy / ds); } }
     const float fx = (float)(x - p.ox), fy = (float)(y - p.oy);
-    const float m2x = -2.0f * fx, m2y = -2.0f * fy, ne2 = -fmaf(fx, fx, fy * fy);
-    if (tb.use_lists) {      // block-level culled rows: a handful of entries instead of OMpad
-      const int cnt = tb.row_cnt[r];
-      const float4* e = tb.list + tb.row_off[r];
-      for (int k = 0; k < cnt; ++k) {
-        const float4 b = e[k];
-        if (fmaf(b.x, m2x, fmaf(b.y, m2y, b.z)) <= ne2) {
-          const int om = __float_as_int(b.w);
-          if (narrow_hit_lazy(abs_step, om, b.x - fx, b.y - fy, x, y, cf, snf, hdx, hdy)) {
-            const float pr = __ldg(p.probf + om);
-            if ((double)pr >= p.p_min) { collided = true; return; }
-            risk = risk + (double)pr;
-          }
-        }
+    const float ne2 = -fmaf(fx, fx, fy * fy);
+    if (by_mask) {
+      while (mask) {
+        const int k = __ffsll((long long)mask) - 1;
+        mask &= mask - 1ull;
+        const int om = tb.use_lists ? __float_as_int(e[k].w) : k;
+        if (visit(abs_step, om, fx, fy, ne2, x, y, cf, snf, hdx, hdy)) return;
       }
       return;
     }
-    const float4* rowp = tb.broad + (size_t)(tb.broad_row0 + r * tb.broad_stride) * p.OMpad;
-    for (int base = 0; base < p.OM; base += 32) {
-      unsigned int mask = 0u;
-      const int nj = min(32, p.OM - base);
-#pragma unroll 4
-      for (int q = 0; q < nj; ++q) {
-        const float4 b = rowp[base + q];
-        mask |= (fmaf(b.x, m2x, fmaf(b.y, m2y, b.z)) <= ne2) ? (1u << q) : 0u;
-      }
-      while (mask) {      // rare: bounding circles overlap -> separating-axis test
-        const int om = base + __ffs(mask) - 1;
-        mask &= mask - 1u;
-        const float4 b = rowp[om];
-        if (narrow_hit_lazy(abs_step, om, b.x - fx, b.y - fy, x, y, cf, snf, hdx, hdy)) {
-          if ((double)b.w >= p.p_min) { collided = true; return; }
-          risk = risk + (double)b.w;
-        }
-      }
+    // no seed-level masks (table read from global memory, or more than 64 entries in the row): every entry of the row; the
+    // entries may carry enlarged circles - visit() decides on the true table entry
+    const float m2x = -2.0f * fx, m2y = -2.0f * fy;
+    for (int k = 0; k < cnt; ++k) {
+      const float4 b = e[k];
+      if (fmaf(b.x, m2x, fmaf(b.y, m2y, b.z)) <= ne2 &&
+          visit(abs_step, tb.use_lists ? __float_as_int(b.w) : k, fx, fy, ne2, x, y, cf, snf, hdx, hdy)) return;
     }
   }
 
   // segment i = p_{i+1} - p_i arrives: curvature against segment i - 1, collision row of sample i, shift
-  __device__ __forceinline__ void segment(int i, double x, double y, double dx, double dy) {
+  __device__ __forceinline__ void segment(int i, bool is_row, int r, unsigned long long mask, double x, double y, double dx, double dy) {
     const float dxf = (float)dx, dyf = (float)dy;
     const float qf = fmaf(dxf, dxf, dyf * dyf);
-    float dsf = 0.f;
-    if (qf > 1e-16f && qf < 1e30f) { float inv = rsqrtf(qf); inv = inv * fmaf(-0.5f * qf, inv * inv, 1.5f); dsf = qf * inv; }
+    float inv = rsqrtf(fmaxf(qf, 1e-30f));
+    inv = inv * fmaf(-0.5f * qf, inv * inv, 1.5f);
+    const float dsf = (qf > 1e-16f && qf < 1e30f) ? qf * inv : 0.f;
     if (i >= 1 && curvature_fails_fast(dx, dy, qf, dsf)) curv_fail = true;
-    collide(i, x, y, dx, dy, qf);
+    if (is_row) collide(i, r, x, y, dx, dy, qf, mask);
     pdx = dx; pdy = dy; pqf = qf; pdsf = dsf;
   }
-  __device__ __forceinline__ void finish(int n_pts, double x, double y) {
-    if (n_pts >= 2) collide(n_pts - 1, x, y, pdx, pdy, pqf);                // last point reuses the previous heading (:158-160)
-    else if (n_pts == 1 && p.n_dict > 0 && p.tcap >= 1) collided = true;    // bare except -> collision (:250-254)
+  __device__ __forceinline__ void finish(int n_pts, double x, double y, unsigned long long mask) {
+    const int cr = p.check_res;
+    if (n_pts >= 2) {                                   // last point reuses the previous heading (:158-160)
+      const int i = n_pts - 1;
+      if (i % cr == 0) collide(i, i / cr, x, y, pdx, pdy, pqf, mask);
+    } else if (n_pts == 1 && p.n_dict > 0 && p.tcap >= 1) collided = true;   // bare except -> collision (:250-254)
   }
 };
 __device__ __forceinline__ double candidate_cost(const EvalParams& p, const TileSink& k, const double* latcost) {
   return candidate_cost(p, k.sum_a, k.sum_j, k.sum_v, k.s_first, k.s_last, k.risk, latcost);
 }
 
-// The tiled walk of the candidate in lane (g, j): g = group (seed) within the warp, j = lateral target.  `gbase` = this group's
-// tile, `prof` = this group's segment table (already stored), both in the warp's scratch.  Inactive lanes (no seed) only keep
-// the warp-level barriers company.  On return `sink` holds the masks, the risk term and the longitudinal cost sums.
+// max |d| over the cycle's lateral samples (block-wide; ends with a block barrier): the radius by which the seed-level circles grow
+__device__ __forceinline__ float block_lateral_reach(const double* sm_lat, int W, int P) {
+  __shared__ unsigned int sm_bits_[1];
+  unsigned int* sm_bits = sm_bits_;
+  if (threadIdx.x == 0) *sm_bits = 0u;
+  __syncthreads();
+  float m = 0.f;
+  for (int e = threadIdx.x; e < W * P; e += blockDim.x) m = fmaxf(m, __double2float_ru(fabs(sm_lat[(size_t)e * 4])));
+  m = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m)));      // non-negative floats order like their bits
+  if ((threadIdx.x & 31) == 0) atomicMax(sm_bits, __float_as_uint(m));
+  __syncthreads();
+  return __uint_as_float(*sm_bits) * 1.0001f + 1e-4f;
+}
+
+// The tiled walk of the candidate in lane (g, j): g = group (seed) within the warp, j = lateral target.  `gbase` / `gterms` /
+// `gmask` = this group's tile (reference points, cost terms, collision masks), `prof` = its segment table (already stored), all
+// in the warp's scratch.  Inactive lanes (no seed) only keep the warp-level barriers company.  On return `sink` holds the
+// masks, the risk term and the longitudinal cost sums.
 __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTables& tb, const TileGeom& tg, double* gbase, double* gterms,
-                                           double* prof, bool active, int j, int W, TileSink& sink) {
-  const int P = p.P, TL = tg.TL;
+                                           unsigned long long* gmask, double* prof, bool active, int j, int W, TileSink& sink) {
+  const int P = p.P, TL = tg.TL, cr = p.check_res;
   const double* lat = tb.lat + (size_t)j * P * 4;
-  int k = 0, n_pts = P;
+  int* np_s = reinterpret_cast<int*>(prof + 30);       // first sample off the reference line (P if none), filled by phase 1
+  int k = 0;
   double sa = 0, sj = 0, sv = 0;                 // lane 0 of the group: the longitudinal cost sums, added strictly in time order
   double xp = 0, yp = 0;
   bool walking = active;
+  const bool rows_on = p.n_dict > 0 && tb.masks;
+  unsigned long long pmask = 0ull;               // collision mask of the point (xp, yp)
+  int n_pts = P;
+  if (active && j == 0) *np_s = P;
+  __syncwarp();
   for (int base = 0; base < P; base += TL) {
     const int len = min(TL, P - base);
     // phase 1: seed-only quantities of the samples this lane owns in the tile
@@ -271,42 +301,70 @@ __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTable
         tm[0] = ea * ea; tm[1] = ej * ej; tm[2] = ev * ev;
         if (i == 0) prof[28] = s;
         if (i == P - 1) prof[29] = s;
+        gmask[il] = 0ull;
         double2* e = reinterpret_cast<double2*>(gbase + il * 4);
         if (spline_in_range(tb.sp, s)) {
           double ix, iy, u, v;
           frenet_base_fma(tb.sp, spline_walk(tb.sp, s, 0), s, ix, iy, u, v);
           e[0] = make_double2(ix, iy); e[1] = make_double2(u, v);
         } else {
-          e[0] = make_double2(nan(""), 0.0);      // off the reference line: the Cartesian path ends here (jssp.py:138-139)
+          atomicMin(np_s, i);                       // off the reference line: the Cartesian path ends here (jssp.py:138-139)
         }
       }
     }
     __syncwarp();
+    n_pts = active ? *np_s : 0;
+    const int live = min(len, n_pts - base);          // samples of the tile that are on the Cartesian path (<= 0: none)
+    // phase 1.5: bounding circles once per seed - lane j of the group takes entries j, j + W, ... of every collision row of the tile
+    if (rows_on && active) {
+      for (int il = (cr - base % cr) % cr; il < live; il += cr) {
+        const int i = base + il, abs_step = p.now + i;
+        if (i >= p.tcap || abs_step >= p.Tt) break;
+        const int r = i / cr;
+        const double2 pxy = *reinterpret_cast<const double2*>(gbase + il * 4);
+        const float fx = (float)(pxy.x - p.ox), fy = (float)(pxy.y - p.oy);
+        const float m2x = -2.0f * fx, m2y = -2.0f * fy, ne2 = -fmaf(fx, fx, fy * fy);
+        const int cnt = tb.use_lists ? tb.row_cnt[r] : p.OM;
+        const float4* e = tb.use_lists ? tb.list + tb.row_off[r] : tb.broad + (size_t)(tb.broad_row0 + r * tb.broad_stride) * p.OMpad;
+        unsigned long long lm = 0ull;
+        if (cnt <= 64) {
+          for (int q = j; q < cnt; q += W) {
+            const float4 b = e[q];
+            lm |= (fmaf(b.x, m2x, fmaf(b.y, m2y, b.z)) <= ne2) ? (1ull << q) : 0ull;
+          }
+        } else {
+          lm = ~0ull;                                 // longer rows: phase 2 falls back to the full loop over the row (see collide)
+        }
+        if (lm) atomicOr(gmask + il, lm);
+      }
+    }
     // the cost sums are sequential float64 sums over the samples (the oracle's order: costs bit-identical to the other kernels):
     // one lane per seed adds the tile's terms - three short independent chains
     if (active && j == 0) {
       for (int il = 0; il < len; ++il) { sa = sa + gterms[il * 3]; sj = sj + gterms[il * 3 + 1]; sv = sv + gterms[il * 3 + 2]; }
     }
+    __syncwarp();
     // phase 2: this lane's candidate
     if (walking) {
-      for (int il = 0; il < len; ++il) {
+      for (int il = 0; il < live; ++il) {
         const int i = base + il;
         const double2* e = reinterpret_cast<const double2*>(gbase + il * 4);
-        const double2 pxy = e[0];
-        if (!(pxy.x == pxy.x)) { n_pts = i; walking = false; break; }
-        const double2 uv = e[1];
+        const double2 pxy = e[0], uv = e[1];
         const double d = lat[i * 4];
         const double x = fma(-d, uv.x, pxy.x), y = fma(d, uv.y, pxy.y);
         if (i >= 1) {
-          sink.segment(i - 1, xp, yp, x - xp, y - yp);
+          const int ip = i - 1;                     // the segment that ends here starts at sample i - 1: its collision row, its mask
+          const bool is_row = ip % cr == 0;
+          sink.segment(ip, is_row, ip / cr, pmask, xp, yp, x - xp, y - yp);
           if (sink.vetoed()) { walking = false; break; }     // select-only evaluation: this candidate can no longer be selected
         }
-        xp = x; yp = y;
+        xp = x; yp = y; pmask = gmask[il];
       }
+      if (live < len) walking = false;             // the path ended inside this tile (or before it)
     }
     __syncwarp();                                  // the tile is rewritten by the next phase 1
   }
-  if (active && !sink.vetoed()) sink.finish(n_pts, xp, yp);
+  if (active && !sink.vetoed()) sink.finish(n_pts, xp, yp, pmask);
   if (active && j == 0) { gbase[0] = sa; gbase[1] = sj; gbase[2] = sv; }
   __syncwarp();
   if (active) {
@@ -344,12 +402,27 @@ __device__ __forceinline__ void evaluate_tiled_body(const EvalParams& p, unsigne
     double* gbase = wscr + (size_t)gg * tg.grp_stride;
     double* gterms = wscr + tg.off_terms + (size_t)gg * tg.TL * 3;
     double* prof = wscr + tg.off_prof + (size_t)gg * TILE_PROF;
+    unsigned long long* gmask = reinterpret_cast<unsigned long long*>(wscr + tg.off_mask) + (size_t)gg * tg.TL;
     if (active && j == 0) tile_profile_store(prof, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
     __syncwarp();
-    if (kMode == 2) { TileSAt s_at{prof}; build_lists(p, smem, tb, s_at, active, j, W); }
+    // seed-level bounding circles: the shared-memory entries (culled lists / staged window) are enlarged by the lateral reach
+    const float dmax = block_lateral_reach(tb.lat, W, p.P);
+    if (kMode == 2) {
+      TileSAt s_at{prof};
+      build_lists(p, smem, tb, s_at, active, j, W, dmax);
+      tb.masks = tb.use_lists;
+    } else if (kMode == 1) {
+      float4* win = const_cast<float4*>(tb.broad);
+      for (int e = threadIdx.x; e < p.win_rows * p.OMpad; e += blockDim.x) {
+        const int om = e % p.OMpad;
+        if (om < p.OM) win[e].z -= circle_enlarge(p, om, dmax);
+      }
+      __syncthreads();
+      tb.masks = true;
+    }
     PHASE(p, 2);
     TileSink sink(p, tb);
-    walk_tiles(p, tb, tg, gbase, gterms, prof, active, j, W, sink);
+    walk_tiles(p, tb, tg, gbase, gterms, gmask, prof, active, j, W, sink);
     if (active) {
       const int n = j * Ns + k;                // candidate index: width-major (jerk_space_sampling_planner.py:106,124-125)
       const double cost = candidate_cost(p, sink, latcost + j * 4);

@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
   double* gbase = wscr + (size_t)gg * tg.grp_stride;
   double* gterms = wscr + tg.off_terms + (size_t)gg * tg.TL * 3;
   double* prof = wscr + tg.off_prof + (size_t)gg * TILE_PROF;
+  unsigned long long* gmask = reinterpret_cast<unsigned long long*>(wscr + tg.off_mask) + (size_t)gg * tg.TL;
   double* seeds = wk.seeds + (size_t)sc * wk.cap_seeds * 10;
   int* counts = wk.counts + (size_t)sc * 4;
 
@@ -128,23 +129,28 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
     // -- K2: evaluation ---------------------------------------------------------------------------------------------------
     const int Ns = min(__ldcg(counts + 2), sp.seed_cap);
     const int N = Ns * W;
-    // obstacle window of the cycle: rows now, now + check_res, ... of the broad-phase table (absent rows = far away)
+    stage_lateral(sp, sm_time, sm_lat, sm_latcost);       // ends with a block barrier
+    const float dmax = block_lateral_reach(sm_lat, W, sp.P);
+    // obstacle window of the cycle: rows now, now + check_res, ... of the broad-phase table (absent rows = far away), circles
+    // enlarged by the lateral reach for the seed-level test (jssp_eval_tiled.cuh)
     {
       const int n_el = sp.win_rows * sp.OMpad;
       for (int e = tid; e < n_el; e += nt) {
         const int r = e / sp.OMpad, o = e - r * sp.OMpad;
         const int step = sp.now + r * sp.check_res;
-        sm_win[e] = step < sp.Tt ? sp.broad[(size_t)step * sp.OMpad + o] : make_float4(0.f, 0.f, FAR_AWAY, 0.f);
+        float4 b = step < sp.Tt ? sp.broad[(size_t)step * sp.OMpad + o] : make_float4(0.f, 0.f, FAR_AWAY, 0.f);
+        if (o < sp.OM) b.z -= circle_enlarge(sp, o, dmax);
+        sm_win[e] = b;
       }
     }
-    stage_lateral(sp, sm_time, sm_lat, sm_latcost);       // ends with a block barrier
+    __syncthreads();
     BlockTables tb;
     tb.broad = sp.win_rows > 0 ? sm_win : sp.broad;
     tb.broad_row0 = sp.win_rows > 0 ? 0 : sp.now; tb.broad_stride = sp.win_rows > 0 ? 1 : sp.check_res;
     tb.sp.knot = sm_knot; tb.sp.coef = sm_coef; tb.sp.K = sp.K; tb.sp.kpad = sp.kpad;
     tb.sp.inv_h = (double)(sp.K - 1) / sm_knot[sp.K - 1];
     tb.time = sm_time; tb.lat = sm_lat;
-    tb.list = nullptr; tb.row_off = nullptr; tb.row_cnt = nullptr; tb.use_lists = false;
+    tb.list = nullptr; tb.row_off = nullptr; tb.row_cnt = nullptr; tb.use_lists = false; tb.masks = sp.win_rows > 0;
     const double* latcost = sm_latcost;
     double my_cost = INFINITY;
     int my_idx = -1;
@@ -155,7 +161,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
       if (active && j == 0) tile_profile_store(prof, seeds + (size_t)k * 10, sp.s0, sp.v0, sp.a0);
       __syncwarp();
       TileSink sink(sp, tb);
-      walk_tiles(sp, tb, tg, gbase, gterms, prof, active, j, W, sink);
+      walk_tiles(sp, tb, tg, gbase, gterms, gmask, prof, active, j, W, sink);
       if (active) {
         const int n = j * Ns + k;                          // width-major candidate index (jerk_space_sampling_planner.py:106,124-125)
         const double cost = candidate_cost(sp, sink, latcost + j * 4);

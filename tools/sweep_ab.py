@@ -16,7 +16,8 @@ cfg = J.JsspConfig(ego_length=float(e[5]), ego_width=float(e[6]), max_seeds=1024
 bt = B.BatchReplay(cfg, max_scenarios=len(packed), max_cycles=C)
 bt.load(packed)
 out = {}
-for kern in (None, "lockstep"):
+kerns = (None, "lockstep") + tuple(sys.argv[3:])
+for kern in kerns:
     for _ in range(2):
         bt.reset(); bt.run(C, kernel=kern)
     torch.cuda.synchronize()
