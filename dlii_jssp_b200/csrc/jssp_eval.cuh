@@ -112,8 +112,8 @@ struct BlockTables {
   const int* row_off;
   const int* row_cnt;
   bool use_lists;
-  bool masks;            // tiled kernel: the shared-memory entries (lists / window rows) carry circles enlarged by the lateral reach and
-                         // the bounding-circle test runs once per seed into 64-bit masks (jssp_eval_tiled.cuh)
+  bool masks;            // tiled kernel: the bounding-circle test runs once per seed into 64-bit masks (jssp_eval_tiled.cuh) ...
+  const float* adj;      // ... against circles enlarged by the lateral reach: z' = z - adj[om]  (shared memory, [OMpad])
 };
 
 // Walks one candidate through the horizon and hands every derived quantity to `sink`, in the order the reference
@@ -491,7 +491,7 @@ __device__ __forceinline__ void stage_tables(const EvalParams& p, unsigned char*
   tb.sp.inv_h = (double)(p.K - 1) / sm_knot[p.K - 1];
   tb.time = sm_time; tb.lat = sm_lat;
   tb.list = sm_broad; tb.row_off = reinterpret_cast<const int*>(smem + L.off_rows); tb.row_cnt = tb.row_off + p.win_rows;
-  tb.use_lists = false; tb.masks = false;
+  tb.use_lists = false; tb.masks = false; tb.adj = nullptr;
   latcost = sm_latcost;
 }
 
@@ -509,10 +509,9 @@ struct WalkSAt {
   LonWalk lp;
   __device__ __forceinline__ double operator()(double t) { double s, sd, sdd, sddd; lon_walk_eval(lp, t, s, sd, sdd, sddd); return s; }
 };
-__device__ __forceinline__ float circle_enlarge(const EvalParams& p, int om, float dmax);    // jssp_eval_tiled.cuh
 template <class SAt>
 __device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* smem, BlockTables& tb, SAt& s_at, bool active,
-                                            int row_first = 0, int row_stride = 1, float dmax = 0.f) {
+                                            int row_first = 0, int row_stride = 1) {
   const SmemLayout L = eval_smem_layout(p.win_rows, p.OMpad, 2, p.K, p.kpad, p.P, p.W, p.list_cap);
   float4* list = reinterpret_cast<float4*>(smem + L.off_broad);
   int* row_off = reinterpret_cast<int*>(smem + L.off_rows);
@@ -589,7 +588,6 @@ __device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* 
       for (int c = 0; c < CH; ++c) {
         if ((m[c] >> lane) & 1u) {
           float4 b = bb[c];
-          if (dmax > 0.f) b.z -= circle_enlarge(p, c * 32 + lane, dmax);
           b.w = __int_as_float(c * 32 + lane);
           list[off + __popc(m[c] & ((1u << lane) - 1u))] = b;
         }
@@ -613,7 +611,6 @@ __device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* 
       const unsigned int m = __ballot_sync(0xffffffffu, keep);
       if (keep) {
         float4 b = src[base + lane];
-        if (dmax > 0.f) b.z -= circle_enlarge(p, base + lane, dmax);
         b.w = __int_as_float(base + lane);
         list[off + __popc(m & ((1u << lane) - 1u))] = b;
       }

@@ -49,7 +49,10 @@ __host__ __device__ inline TileGeom tile_geom(int W, int rounds = 0) {
   g.warp_doubles = g.off_prof + g.gpw * TILE_PROF;
   return g;
 }
-__host__ __device__ inline size_t tile_scratch_bytes(int W, int threads, int rounds = 0) { return (size_t)(threads / 32) * tile_geom(W, rounds).warp_doubles * 8; }
+// scratch of a block: the warps' tiles + the circle-enlargement table adj[OMpad] (floats) behind them
+__host__ __device__ inline size_t tile_scratch_bytes(int W, int threads, int rounds = 0, int OMpad = 0) {
+  return (size_t)(threads / 32) * tile_geom(W, rounds).warp_doubles * 8 + (((size_t)OMpad * 4 + 15) & ~(size_t)15);
+}
 
 // segment table of one seed: the start state and jerk of each of the five segments (the same expressions as lon_profile_init:
 // bit-identical to the reference's segment end states), the durations and the asymmetric-epsilon boundaries of
@@ -132,6 +135,11 @@ __device__ __forceinline__ float circle_enlarge(const EvalParams& p, int om, flo
   return (2.0f * r * dmax + dmax * dmax) * 1.0002f + 1e-4f;
 }
 
+// adj[om] for every obstacle mode of the cycle (block-wide; the caller synchronises)
+__device__ __forceinline__ void fill_circle_adj(const EvalParams& p, float dmax, float* adj) {
+  for (int om = threadIdx.x; om < p.OMpad; om += blockDim.x) adj[om] = om < p.OM ? circle_enlarge(p, om, dmax) : 0.f;
+}
+
 struct TileSink {
   const EvalParams& p;
   const BlockTables& tb;
@@ -185,15 +193,15 @@ struct TileSink {
     return sat_intersects_f64(o[0] - x, o[1] - y, c, sn, p.ea, p.eb, o[2], o[3], p.ext64[2 * om], p.ext64[2 * om + 1]);
   }
 
-  // one obstacle state whose (enlarged) circle the seed's reference point touched: the candidate's own circle test against the
-  // TRUE table entry, then the separating-axis test.  Returns true when the candidate is vetoed.
-  __device__ __forceinline__ bool visit(int abs_step, int om, float fx, float fy, float ne2, double x, double y, float cf, float snf,
+  // one obstacle state whose enlarged circle the seed's reference point touched (b = its table entry): the candidate's own
+  // circle test, then the separating-axis test.  Returns true when the candidate is vetoed.
+  __device__ __forceinline__ bool visit(int abs_step, int om, float4 b, float fx, float fy, float ne2, double x, double y, float cf, float snf,
                                         double hdx, double hdy) {
-    const float4 b = __ldg(p.broad + (size_t)abs_step * p.OMpad + om);
     if (!(fmaf(b.x, -2.0f * fx, fmaf(b.y, -2.0f * fy, b.z)) <= ne2)) return false;
     if (!narrow_hit_lazy(p, abs_step, om, b.x - fx, b.y - fy, x, y, cf, snf, hdx, hdy)) return false;
-    if ((double)b.w >= p.p_min) { collided = true; return true; }
-    risk = risk + (double)b.w;
+    const float pr = tb.use_lists ? __ldg(p.probf + om) : b.w;
+    if ((double)pr >= p.p_min) { collided = true; return true; }
+    risk = risk + (double)pr;
     return false;
   }
 
@@ -216,18 +224,15 @@ struct TileSink {
       while (mask) {
         const int k = __ffsll((long long)mask) - 1;
         mask &= mask - 1ull;
-        const int om = tb.use_lists ? __float_as_int(e[k].w) : k;
-        if (visit(abs_step, om, fx, fy, ne2, x, y, cf, snf, hdx, hdy)) return;
+        const float4 b = e[k];
+        if (visit(abs_step, tb.use_lists ? __float_as_int(b.w) : k, b, fx, fy, ne2, x, y, cf, snf, hdx, hdy)) return;
       }
       return;
     }
-    // no seed-level masks (table read from global memory, or more than 64 entries in the row): every entry of the row; the
-    // entries may carry enlarged circles - visit() decides on the true table entry
-    const float m2x = -2.0f * fx, m2y = -2.0f * fy;
+    // no seed-level masks (table read from global memory, or more than 64 entries in the row): every entry of the row
     for (int k = 0; k < cnt; ++k) {
       const float4 b = e[k];
-      if (fmaf(b.x, m2x, fmaf(b.y, m2y, b.z)) <= ne2 &&
-          visit(abs_step, tb.use_lists ? __float_as_int(b.w) : k, fx, fy, ne2, x, y, cf, snf, hdx, hdy)) return;
+      if (visit(abs_step, tb.use_lists ? __float_as_int(b.w) : k, b, fx, fy, ne2, x, y, cf, snf, hdx, hdy)) return;
     }
   }
 
@@ -242,11 +247,9 @@ struct TileSink {
     if (is_row) collide(i, r, x, y, dx, dy, qf, mask);
     pdx = dx; pdy = dy; pqf = qf; pdsf = dsf;
   }
-  __device__ __forceinline__ void finish(int n_pts, double x, double y, unsigned long long mask) {
-    const int cr = p.check_res;
+  __device__ __forceinline__ void finish(int n_pts, double x, double y, unsigned long long mask, int next_check, int row) {
     if (n_pts >= 2) {                                   // last point reuses the previous heading (:158-160)
-      const int i = n_pts - 1;
-      if (i % cr == 0) collide(i, i / cr, x, y, pdx, pdy, pqf, mask);
+      if (n_pts - 1 == next_check) collide(n_pts - 1, row, x, y, pdx, pdy, pqf, mask);
     } else if (n_pts == 1 && p.n_dict > 0 && p.tcap >= 1) collided = true;   // bare except -> collision (:250-254)
   }
 };
@@ -284,6 +287,9 @@ __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTable
   const bool rows_on = p.n_dict > 0 && tb.masks;
   unsigned long long pmask = 0ull;               // collision mask of the point (xp, yp)
   int n_pts = P;
+  int next_check = 0, row = 0;                   // next sample index with a collision row and that row (i % check_res == 0 without dividing)
+  const int lane = threadIdx.x & 31;
+  const unsigned int grp_lanes = (W >= 32 ? 0xffffffffu : ((1u << W) - 1u)) << (lane - j);
   if (active && j == 0) *np_s = P;
   __syncwarp();
   for (int base = 0; base < P; base += TL) {
@@ -315,27 +321,33 @@ __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTable
     __syncwarp();
     n_pts = active ? *np_s : 0;
     const int live = min(len, n_pts - base);          // samples of the tile that are on the Cartesian path (<= 0: none)
-    // phase 1.5: bounding circles once per seed - lane j of the group takes entries j, j + W, ... of every collision row of the tile
-    if (rows_on && active) {
-      for (int il = (cr - base % cr) % cr; il < live; il += cr) {
+    // phase 1.5: bounding circles once per seed - lane j of the group takes entries j, j + W, ... of every collision row of the tile.
+    // Skipped once no candidate of the seed can use the rows any more (all collided / vetoed / off the path).
+    const bool wants = walking && !sink.collided;
+    const bool grp_wants = (__ballot_sync(0xffffffffu, wants) & grp_lanes) != 0u;
+    if (rows_on && active && grp_wants) {
+      const int il0 = (cr - base % cr) % cr;
+      int r = (base + il0) / cr;
+      for (int il = il0; il < live; il += cr, ++r) {
         const int i = base + il, abs_step = p.now + i;
         if (i >= p.tcap || abs_step >= p.Tt) break;
-        const int r = i / cr;
         const double2 pxy = *reinterpret_cast<const double2*>(gbase + il * 4);
         const float fx = (float)(pxy.x - p.ox), fy = (float)(pxy.y - p.oy);
         const float m2x = -2.0f * fx, m2y = -2.0f * fy, ne2 = -fmaf(fx, fx, fy * fy);
         const int cnt = tb.use_lists ? tb.row_cnt[r] : p.OM;
         const float4* e = tb.use_lists ? tb.list + tb.row_off[r] : tb.broad + (size_t)(tb.broad_row0 + r * tb.broad_stride) * p.OMpad;
-        unsigned long long lm = 0ull;
+        unsigned int lo = 0u, hi = 0u;
         if (cnt <= 64) {
           for (int q = j; q < cnt; q += W) {
             const float4 b = e[q];
-            lm |= (fmaf(b.x, m2x, fmaf(b.y, m2y, b.z)) <= ne2) ? (1ull << q) : 0ull;
+            const float z = b.z - tb.adj[tb.use_lists ? __float_as_int(b.w) : q];
+            const bool hit = fmaf(b.x, m2x, fmaf(b.y, m2y, z)) <= ne2;
+            if (q < 32) lo |= hit ? (1u << q) : 0u; else hi |= hit ? (1u << (q - 32)) : 0u;
           }
         } else {
-          lm = ~0ull;                                 // longer rows: phase 2 falls back to the full loop over the row (see collide)
+          lo = hi = 0xffffffffu;                      // longer rows: phase 2 runs the full loop over the row (see collide)
         }
-        if (lm) atomicOr(gmask + il, lm);
+        if (lo | hi) atomicOr(gmask + il, ((unsigned long long)hi << 32) | lo);
       }
     }
     // the cost sums are sequential float64 sums over the samples (the oracle's order: costs bit-identical to the other kernels):
@@ -354,8 +366,9 @@ __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTable
         const double x = fma(-d, uv.x, pxy.x), y = fma(d, uv.y, pxy.y);
         if (i >= 1) {
           const int ip = i - 1;                     // the segment that ends here starts at sample i - 1: its collision row, its mask
-          const bool is_row = ip % cr == 0;
-          sink.segment(ip, is_row, ip / cr, pmask, xp, yp, x - xp, y - yp);
+          const bool is_row = ip == next_check;
+          sink.segment(ip, is_row, row, pmask, xp, yp, x - xp, y - yp);
+          if (is_row) { next_check += cr; ++row; }
           if (sink.vetoed()) { walking = false; break; }     // select-only evaluation: this candidate can no longer be selected
         }
         xp = x; yp = y; pmask = gmask[il];
@@ -364,7 +377,7 @@ __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTable
     }
     __syncwarp();                                  // the tile is rewritten by the next phase 1
   }
-  if (active && !sink.vetoed()) sink.finish(n_pts, xp, yp, pmask);
+  if (active && !sink.vetoed()) sink.finish(n_pts, xp, yp, pmask, next_check, row);
   if (active && j == 0) { gbase[0] = sa; gbase[1] = sj; gbase[2] = sv; }
   __syncwarp();
   if (active) {
@@ -405,20 +418,18 @@ __device__ __forceinline__ void evaluate_tiled_body(const EvalParams& p, unsigne
     unsigned long long* gmask = reinterpret_cast<unsigned long long*>(wscr + tg.off_mask) + (size_t)gg * tg.TL;
     if (active && j == 0) tile_profile_store(prof, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
     __syncwarp();
-    // seed-level bounding circles: the shared-memory entries (culled lists / staged window) are enlarged by the lateral reach
+    // seed-level bounding circles: circles enlarged by the lateral reach of the cycle, z' = z - adj[om]
     const float dmax = block_lateral_reach(tb.lat, W, p.P);
+    float* sm_adj = reinterpret_cast<float*>(reinterpret_cast<double*>(smem + ((L.total + 15) & ~(size_t)15)) + (size_t)(blockDim.x >> 5) * tg.warp_doubles);
+    fill_circle_adj(p, dmax, sm_adj);
+    tb.adj = sm_adj;
     if (kMode == 2) {
       TileSAt s_at{prof};
-      build_lists(p, smem, tb, s_at, active, j, W, dmax);
+      build_lists(p, smem, tb, s_at, active, j, W);      // ends with a block barrier
       tb.masks = tb.use_lists;
-    } else if (kMode == 1) {
-      float4* win = const_cast<float4*>(tb.broad);
-      for (int e = threadIdx.x; e < p.win_rows * p.OMpad; e += blockDim.x) {
-        const int om = e % p.OMpad;
-        if (om < p.OM) win[e].z -= circle_enlarge(p, om, dmax);
-      }
+    } else {
       __syncthreads();
-      tb.masks = true;
+      tb.masks = kMode == 1;
     }
     PHASE(p, 2);
     TileSink sink(p, tb);

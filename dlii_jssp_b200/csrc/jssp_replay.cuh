@@ -54,7 +54,7 @@ __host__ __device__ inline ReplaySmem replay_smem_layout(int kpad, int P, int W,
   L.off_latcost = e; e += (size_t)W * 4 * 8;
   L.off_window = e; e += (size_t)win_rows * OMpad * 16;
   e = (e + 15) & ~(size_t)15;
-  L.off_tile = e; e += tile_scratch_bytes(W, threads, tile_rounds);
+  L.off_tile = e; e += tile_scratch_bytes(W, threads, tile_rounds, OMpad);
   const size_t s = o + ((seed_bytes + 15) & ~(size_t)15);
   L.total = e > s ? e : s;
   return L;
@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
   double* sm_latcost = reinterpret_cast<double*>(smem + L.off_latcost);
   float4* sm_win = reinterpret_cast<float4*>(smem + L.off_window);
   double* sm_tile = reinterpret_cast<double*>(smem + L.off_tile);
+  float* sm_adj = reinterpret_cast<float*>(sm_tile + (size_t)nwarps * tile_geom(sp.W, tile_rounds).warp_doubles);
   // reference line + time grid: once per scenario, through the TMA engine
   {
     const uint32_t knot_bytes = (uint32_t)sp.kpad * 8u, coef_bytes = (uint32_t)sp.kpad * 64u, time_bytes = (uint32_t)((sp.P + 1) & ~1) * 8u;
@@ -131,16 +132,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
     const int N = Ns * W;
     stage_lateral(sp, sm_time, sm_lat, sm_latcost);       // ends with a block barrier
     const float dmax = block_lateral_reach(sm_lat, W, sp.P);
-    // obstacle window of the cycle: rows now, now + check_res, ... of the broad-phase table (absent rows = far away), circles
-    // enlarged by the lateral reach for the seed-level test (jssp_eval_tiled.cuh)
+    fill_circle_adj(sp, dmax, sm_adj);                    // seed-level circles: z' = z - adj[om] (jssp_eval_tiled.cuh)
+    // obstacle window of the cycle: rows now, now + check_res, ... of the broad-phase table (absent rows = far away)
     {
       const int n_el = sp.win_rows * sp.OMpad;
       for (int e = tid; e < n_el; e += nt) {
         const int r = e / sp.OMpad, o = e - r * sp.OMpad;
         const int step = sp.now + r * sp.check_res;
-        float4 b = step < sp.Tt ? sp.broad[(size_t)step * sp.OMpad + o] : make_float4(0.f, 0.f, FAR_AWAY, 0.f);
-        if (o < sp.OM) b.z -= circle_enlarge(sp, o, dmax);
-        sm_win[e] = b;
+        sm_win[e] = step < sp.Tt ? sp.broad[(size_t)step * sp.OMpad + o] : make_float4(0.f, 0.f, FAR_AWAY, 0.f);
       }
     }
     __syncthreads();
@@ -150,7 +149,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
     tb.sp.knot = sm_knot; tb.sp.coef = sm_coef; tb.sp.K = sp.K; tb.sp.kpad = sp.kpad;
     tb.sp.inv_h = (double)(sp.K - 1) / sm_knot[sp.K - 1];
     tb.time = sm_time; tb.lat = sm_lat;
-    tb.list = nullptr; tb.row_off = nullptr; tb.row_cnt = nullptr; tb.use_lists = false; tb.masks = sp.win_rows > 0;
+    tb.list = nullptr; tb.row_off = nullptr; tb.row_cnt = nullptr; tb.use_lists = false; tb.masks = sp.win_rows > 0; tb.adj = sm_adj;
     const double* latcost = sm_latcost;
     double my_cost = INFINITY;
     int my_idx = -1;
