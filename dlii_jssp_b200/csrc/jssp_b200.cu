@@ -783,12 +783,12 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
     const size_t per_sm = 228u * 1024u, two = per_sm / 2 - fa.sharedSizeBytes - 1024;
     const size_t lbase = (L.total + 15) & ~(size_t)15;
     for (int r = tile_rounds_wanted(W); r >= 1; --r) {
-      tile_rounds = r; tiled_total = lbase + tile_scratch_bytes(W, EVAL_THREADS, r, p.OMpad);
+      tile_rounds = r; tiled_total = lbase + tile_scratch_bytes(W, EVAL_THREADS, r, p.OMpad, p.P);
       if (tiled_total <= two) break;
     }
     if (tiled_total > two)                                  // not even the shortest tile leaves room for two blocks: one block, long tiles
       for (int r = tile_rounds_wanted(W); r >= 1; --r) {
-        tile_rounds = r; tiled_total = lbase + tile_scratch_bytes(W, EVAL_THREADS, r, p.OMpad);
+        tile_rounds = r; tiled_total = lbase + tile_scratch_bytes(W, EVAL_THREADS, r, p.OMpad, p.P);
         if (tiled_total <= (size_t)h->max_smem_optin) break;
       }
   }
@@ -1671,7 +1671,7 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   SmemLayout L = eval_smem_layout(max_rows, b->max_OMpad, mode, b->max_K, b->max_kpad, b->P, b->W);
   if (mode == 1 && L.total > (size_t)b->max_smem_optin) { mode = 0; L = eval_smem_layout(0, b->max_OMpad, 0, b->max_K, b->max_kpad, b->P, b->W); }
   if (!small && L.total > (size_t)b->max_smem_optin) return JSSP_ERR_CAPACITY;
-  const size_t tiled_total = ((L.total + 15) & ~(size_t)15) + tile_scratch_bytes(b->W, bthreads, 0, b->max_OMpad);     // default tile length (slot records carry tile_rounds = 0)
+  const size_t tiled_total = ((L.total + 15) & ~(size_t)15) + tile_scratch_bytes(b->W, bthreads, 0, b->max_OMpad, b->P);     // default tile length (slot records carry tile_rounds = 0)
   const bool tiled = !small && (flags & JSSP_FLAG_FORCE_TILED) && tiled_total <= (size_t)b->max_smem_optin;
   // few scenarios: clusters of up to 8 CTAs x 1024 threads answer with the lowest latency; many: one 512-thread CTA each
   int seed_cluster = 1;

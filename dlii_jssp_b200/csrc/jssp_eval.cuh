@@ -974,6 +974,7 @@ __device__ __forceinline__ void select_and_export(const EvalParams& p, unsigned 
   }
   __syncthreads();
   if (!*is_last_p) return;
+  PHASE(p, 7);
   // the last block to finish reduces the per-block winners: deterministic, no floating-point atomics
   __threadfence();
   my_cost = INFINITY; my_idx = -1;

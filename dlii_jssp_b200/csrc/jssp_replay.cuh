@@ -54,7 +54,7 @@ __host__ __device__ inline ReplaySmem replay_smem_layout(int kpad, int P, int W,
   L.off_latcost = e; e += (size_t)W * 4 * 8;
   L.off_window = e; e += (size_t)win_rows * OMpad * 16;
   e = (e + 15) & ~(size_t)15;
-  L.off_tile = e; e += tile_scratch_bytes(W, threads, tile_rounds, OMpad);
+  L.off_tile = e; e += tile_scratch_bytes(W, threads, tile_rounds, OMpad, P);
   const size_t s = o + ((seed_bytes + 15) & ~(size_t)15);
   L.total = e > s ? e : s;
   return L;
@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
   float4* sm_win = reinterpret_cast<float4*>(smem + L.off_window);
   double* sm_tile = reinterpret_cast<double*>(smem + L.off_tile);
   float* sm_adj = reinterpret_cast<float*>(sm_tile + (size_t)nwarps * tile_geom(sp.W, tile_rounds).warp_doubles);
+  float2* sm_latf = reinterpret_cast<float2*>(sm_adj + ((max_OMpad + 3) & ~3));
   // reference line + time grid: once per scenario, through the TMA engine
   {
     const uint32_t knot_bytes = (uint32_t)sp.kpad * 8u, coef_bytes = (uint32_t)sp.kpad * 64u, time_bytes = (uint32_t)((sp.P + 1) & ~1) * 8u;
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
     stage_lateral(sp, sm_time, sm_lat, sm_latcost);       // ends with a block barrier
     const float dmax = block_lateral_reach(sm_lat, W, sp.P);
     fill_circle_adj(sp, dmax, sm_adj);                    // seed-level circles: z' = z - adj[om] (jssp_eval_tiled.cuh)
+    fill_lateral_f32(sm_lat, W, sp.P, sm_latf);
     // obstacle window of the cycle: rows now, now + check_res, ... of the broad-phase table (absent rows = far away)
     {
       const int n_el = sp.win_rows * sp.OMpad;
@@ -159,8 +161,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
       const bool active = g_ < tg.gpw && k < Ns;
       if (active && j == 0) tile_profile_store(prof, seeds + (size_t)k * 10, sp.s0, sp.v0, sp.a0);
       __syncwarp();
-      TileSink sink(sp, tb);
-      walk_tiles(sp, tb, tg, gbase, gterms, gmask, prof, active, j, W, sink);
+      TileSink sink(sp, tb, prof, sm_lat + (size_t)j * sp.P * 4);
+      walk_tiles(sp, tb, tg, gbase, gterms, gmask, prof, sm_latf, active, j, W, sink);
       if (active) {
         const int n = j * Ns + k;                          // width-major candidate index (jerk_space_sampling_planner.py:106,124-125)
         const double cost = candidate_cost(sp, sink, latcost + j * 4);

@@ -33,7 +33,7 @@ print(f"{which}: {used.sum()} blocks; kernel span {(t[:, 4].max() - t0) / 1e3:.1
 names = ["entry", "staged", "lists", "walk", "select"]
 last = t[t[:, 5] > 0]
 if len(last):
-    print(f"  last block: reduce done +{(last[0, 5] - last[0, 3]) / 1e3:.1f} us after its walk, export {(last[0, 6] - last[0, 5]) / 1e3:.1f} us, "
+    print(f"  last block: ticket taken +{(last[0, 7] - last[0, 3]) / 1e3:.1f} us after its walk, reduce done +{(last[0, 5] - last[0, 3]) / 1e3:.1f} us, export {(last[0, 6] - last[0, 5]) / 1e3:.1f} us, "
           f"tail {(last[0, 4] - last[0, 6]) / 1e3:.1f} us")
 for k in range(5):
     col = (t[:, k] - t0) / 1e3
