@@ -23,6 +23,8 @@ struct Tuning {
   int seed_cluster = 0;       // CTAs per seed-enumeration cluster (0 = by batch size)
   int seed_threads = 0;       // threads per seed-enumeration CTA (0 = by batch size)
   int lockstep = 0;           // batched replay: 1 = force the lock-step kernels instead of the persistent scenario kernel
+  int no_masks = 0;           // tiled kernel: no seed-level collision masks (every candidate tests every entry of its rows)
+  int tile_rounds = 0;        // tiled kernel: phase-1 rounds per tile (0 = by shared-memory budget)
   static Tuning from_env() {
     Tuning t;
     t.no_pdl = getenv("JSSP_B200_TUNE_NO_PDL") != nullptr;
@@ -30,6 +32,8 @@ struct Tuning {
     if (const char* e = getenv("JSSP_B200_TUNE_SEED_CLUSTER")) t.seed_cluster = atoi(e);
     if (const char* e = getenv("JSSP_B200_TUNE_SEED_THREADS")) t.seed_threads = atoi(e);
     if (const char* e = getenv("JSSP_B200_TUNE_LOCKSTEP")) t.lockstep = atoi(e);
+    if (const char* e = getenv("JSSP_B200_TUNE_NO_MASKS")) t.no_masks = atoi(e);
+    if (const char* e = getenv("JSSP_B200_TUNE_TILE_ROUNDS")) t.tile_rounds = atoi(e);
     return t;
   }
 };
@@ -792,7 +796,9 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
         if (tiled_total <= (size_t)h->max_smem_optin) break;
       }
   }
+  if (h->tune.tile_rounds > 0) { tile_rounds = std::min(h->tune.tile_rounds, TILE_MAX_ROUNDS); tiled_total = ((L.total + 15) & ~(size_t)15) + tile_scratch_bytes(W, EVAL_THREADS, tile_rounds, p.OMpad, p.P); }
   p.tile_rounds = tile_rounds;
+  p.tile_flags = h->tune.no_masks ? 1 : 0;
   const bool tiled = group && !(in->flags & JSSP_FLAG_FORCE_GROUP) && tiled_total <= (size_t)h->max_smem_optin;
   const long long seeds_max = ext ? in->n_seeds : c.max_seeds;
   const int spb = group_seeds_per_block(W);

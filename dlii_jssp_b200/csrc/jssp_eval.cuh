@@ -36,6 +36,7 @@ struct EvalParams {
   const float2* sint;             // [Tt][OMpad] reachable arc-length interval of every obstacle state (block-level culling)
   const float* probf;             // [OM]
   int list_cap;                   // entries of the per-block compacted obstacle lists (mode 2)
+  int tile_flags;                 // tiled kernel: bit 0 = no seed-level collision masks (tools/ A/B)
   int tile_rounds;                // tiled kernel: phase-1 rounds per tile (0 = default), chosen by the host for its shared-memory budget
   int select_only;                // no per-candidate outputs are wanted: a candidate's walk may stop at its first veto (the
                                   // reference filters the same way: check_constraints_curvature -> check_collisions -> cost on

@@ -500,10 +500,10 @@ __device__ __forceinline__ void evaluate_tiled_body(const EvalParams& p, unsigne
     if (kMode == 2) {
       TileSAt s_at{prof};
       build_lists(p, smem, tb, s_at, active, j, W);      // ends with a block barrier
-      tb.masks = tb.use_lists;
+      tb.masks = tb.use_lists && !(p.tile_flags & 1);
     } else {
       __syncthreads();
-      tb.masks = kMode == 1;
+      tb.masks = kMode == 1 && !(p.tile_flags & 1);
     }
     PHASE(p, 2);
     TileSink sink(p, tb, prof, tb.lat + (size_t)j * p.P * 4);

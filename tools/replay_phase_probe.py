@@ -29,3 +29,11 @@ print(f"{len(packed)} scenarios, sweep {e0.elapsed_time(e1):.3f} ms; scenario 0:
 for k, nm in enumerate(names):
     print(f"  {nm:28s} {ns[k] / cyc / 1e3:8.2f} us per cycle")
 print(f"  {'total':28s} {sum(ns[:5]) / cyc / 1e3:8.2f} us per cycle")
+
+# stage stamps of the LAST seed enumeration scenario 0 ran (SEED_STAMP in jssp_seed.cuh: 0 entry, 1 lists cleared, 2 level 1, 3 level 2, 4 level 3, 5 sorted, 6 barrier, 7 decoded)
+st = (C.c_ulonglong * 16)()
+bt.lib.jssp_debug_seed_stamps.argtypes = [C.c_void_p]
+if bt.lib.jssp_debug_seed_stamps(st) == 0:
+    t = [int(v) for v in st[:8]]
+    names = ["clear", "level 1", "level 2", "level 3", "sort", "barrier", "decode"]
+    print("  last seed enumeration of scenario 0: " + ", ".join(f"{nm} {(t[k + 1] - t[k]) / 1e3:.2f} us" for k, nm in enumerate(names)))
