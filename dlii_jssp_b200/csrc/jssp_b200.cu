@@ -23,8 +23,6 @@ struct Tuning {
   int seed_cluster = 0;       // CTAs per seed-enumeration cluster (0 = by batch size)
   int seed_threads = 0;       // threads per seed-enumeration CTA (0 = by batch size)
   int lockstep = 0;           // batched replay: 1 = force the lock-step kernels instead of the persistent scenario kernel
-  int no_masks = 0;           // tiled kernel: no seed-level collision masks (every candidate tests every entry of its rows)
-  int tile_rounds = 0;        // tiled kernel: phase-1 rounds per tile (0 = by shared-memory budget)
   static Tuning from_env() {
     Tuning t;
     t.no_pdl = getenv("JSSP_B200_TUNE_NO_PDL") != nullptr;
@@ -32,8 +30,6 @@ struct Tuning {
     if (const char* e = getenv("JSSP_B200_TUNE_SEED_CLUSTER")) t.seed_cluster = atoi(e);
     if (const char* e = getenv("JSSP_B200_TUNE_SEED_THREADS")) t.seed_threads = atoi(e);
     if (const char* e = getenv("JSSP_B200_TUNE_LOCKSTEP")) t.lockstep = atoi(e);
-    if (const char* e = getenv("JSSP_B200_TUNE_NO_MASKS")) t.no_masks = atoi(e);
-    if (const char* e = getenv("JSSP_B200_TUNE_TILE_ROUNDS")) t.tile_rounds = atoi(e);
     return t;
   }
 };
@@ -787,18 +783,16 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
     const size_t per_sm = 228u * 1024u, two = per_sm / 2 - fa.sharedSizeBytes - 1024;
     const size_t lbase = (L.total + 15) & ~(size_t)15;
     for (int r = tile_rounds_wanted(W); r >= 1; --r) {
-      tile_rounds = r; tiled_total = lbase + tile_scratch_bytes(W, EVAL_THREADS, r, p.OMpad, p.P);
+      tile_rounds = r; tiled_total = lbase + tile_scratch_bytes(W, EVAL_THREADS, r);
       if (tiled_total <= two) break;
     }
     if (tiled_total > two)                                  // not even the shortest tile leaves room for two blocks: one block, long tiles
       for (int r = tile_rounds_wanted(W); r >= 1; --r) {
-        tile_rounds = r; tiled_total = lbase + tile_scratch_bytes(W, EVAL_THREADS, r, p.OMpad, p.P);
+        tile_rounds = r; tiled_total = lbase + tile_scratch_bytes(W, EVAL_THREADS, r);
         if (tiled_total <= (size_t)h->max_smem_optin) break;
       }
   }
-  if (h->tune.tile_rounds > 0) { tile_rounds = std::min(h->tune.tile_rounds, TILE_MAX_ROUNDS); tiled_total = ((L.total + 15) & ~(size_t)15) + tile_scratch_bytes(W, EVAL_THREADS, tile_rounds, p.OMpad, p.P); }
   p.tile_rounds = tile_rounds;
-  p.tile_flags = h->tune.no_masks ? 1 : 0;
   const bool tiled = group && !(in->flags & JSSP_FLAG_FORCE_GROUP) && tiled_total <= (size_t)h->max_smem_optin;
   const long long seeds_max = ext ? in->n_seeds : c.max_seeds;
   const int spb = group_seeds_per_block(W);
@@ -813,6 +807,17 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   int blocks = small ? (int)small_need
                      : (group ? (int)((seeds_max + spb - 1) / spb) : (int)((n_max + EVAL_THREADS - 1) / EVAL_THREADS));
   if (blocks < 1) blocks = 1;
+  // tiled kernel, single wave (at most two blocks per SM): fewer warps per block so that EVERY SM holds the same number of warps -
+  // 256 blocks of 8 warps leave 108 SMs with 16 warps and 40 with 8, and the kernel ends with the slow ones; 293 blocks of 7 warps
+  // give every SM 14 (BASELINE configs[2]: 16,384 seeds x 4 lateral targets)
+  int tiled_threads = EVAL_THREADS;
+  if (tiled && blocks <= 2 * h->sm_count && blocks > h->sm_count / 2 && !h->tune.lockstep) {
+    const int gpw_t = 32 / W;
+    const long long per_block = (seeds_max + 2 * h->sm_count - 1) / (2 * h->sm_count);
+    const int warps = (int)std::min<long long>(EVAL_THREADS / 32, std::max<long long>(2, (per_block + gpw_t - 1) / gpw_t));
+    tiled_threads = warps * 32;
+    blocks = (int)((seeds_max + (long long)warps * gpw_t - 1) / ((long long)warps * gpw_t));
+  }
   if (blocks > h->max_blocks) return JSSP_ERR_CAPACITY;
   if (small) {
     p.smem_obs = 0; p.win_rows = 0; p.list_cap = 0;
@@ -820,9 +825,9 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
     const bool chained = !ext && (in->flags & JSSP_FLAG_ENUMERATE) && !h->tune.no_pdl;
     CK(launch_chained(evaluate_small_kernel, dim3(blocks), SMALL_WARPS * 32, small_bytes, st, chained, p));
   }
-  else if (tiled && mode == 2) evaluate_tiled_kernel<2><<<blocks, EVAL_THREADS, tiled_total, st>>>(p);
-  else if (tiled && mode == 1) evaluate_tiled_kernel<1><<<blocks, EVAL_THREADS, tiled_total, st>>>(p);
-  else if (tiled) evaluate_tiled_kernel<0><<<blocks, EVAL_THREADS, tiled_total, st>>>(p);
+  else if (tiled && mode == 2) evaluate_tiled_kernel<2><<<blocks, tiled_threads, tiled_total, st>>>(p);
+  else if (tiled && mode == 1) evaluate_tiled_kernel<1><<<blocks, tiled_threads, tiled_total, st>>>(p);
+  else if (tiled) evaluate_tiled_kernel<0><<<blocks, tiled_threads, tiled_total, st>>>(p);
   else if (group && mode == 2) evaluate_group_kernel<2><<<blocks, EVAL_THREADS, L.total, st>>>(p);
   else if (group && mode == 1) evaluate_group_kernel<1><<<blocks, EVAL_THREADS, L.total, st>>>(p);
   else if (group) evaluate_group_kernel<0><<<blocks, EVAL_THREADS, L.total, st>>>(p);
@@ -1677,7 +1682,7 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   SmemLayout L = eval_smem_layout(max_rows, b->max_OMpad, mode, b->max_K, b->max_kpad, b->P, b->W);
   if (mode == 1 && L.total > (size_t)b->max_smem_optin) { mode = 0; L = eval_smem_layout(0, b->max_OMpad, 0, b->max_K, b->max_kpad, b->P, b->W); }
   if (!small && L.total > (size_t)b->max_smem_optin) return JSSP_ERR_CAPACITY;
-  const size_t tiled_total = ((L.total + 15) & ~(size_t)15) + tile_scratch_bytes(b->W, bthreads, 0, b->max_OMpad, b->P);     // default tile length (slot records carry tile_rounds = 0)
+  const size_t tiled_total = ((L.total + 15) & ~(size_t)15) + tile_scratch_bytes(b->W, bthreads);     // default tile length (slot records carry tile_rounds = 0)
   const bool tiled = !small && (flags & JSSP_FLAG_FORCE_TILED) && tiled_total <= (size_t)b->max_smem_optin;
   // few scenarios: clusters of up to 8 CTAs x 1024 threads answer with the lowest latency; many: one 512-thread CTA each
   int seed_cluster = 1;

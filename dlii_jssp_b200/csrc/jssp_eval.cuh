@@ -36,7 +36,6 @@ struct EvalParams {
   const float2* sint;             // [Tt][OMpad] reachable arc-length interval of every obstacle state (block-level culling)
   const float* probf;             // [OM]
   int list_cap;                   // entries of the per-block compacted obstacle lists (mode 2)
-  int tile_flags;                 // tiled kernel: bit 0 = no seed-level collision masks (tools/ A/B)
   int tile_rounds;                // tiled kernel: phase-1 rounds per tile (0 = default), chosen by the host for its shared-memory budget
   int select_only;                // no per-candidate outputs are wanted: a candidate's walk may stop at its first veto (the
                                   // reference filters the same way: check_constraints_curvature -> check_collisions -> cost on
@@ -113,8 +112,6 @@ struct BlockTables {
   const int* row_off;
   const int* row_cnt;
   bool use_lists;
-  bool masks;            // tiled kernel: the bounding-circle test runs once per seed into 64-bit masks (jssp_eval_tiled.cuh) ...
-  const float* adj;      // ... against circles enlarged by the lateral reach: z' = z - adj[om]  (shared memory, [OMpad])
 };
 
 // Walks one candidate through the horizon and hands every derived quantity to `sink`, in the order the reference
@@ -492,7 +489,7 @@ __device__ __forceinline__ void stage_tables(const EvalParams& p, unsigned char*
   tb.sp.inv_h = (double)(p.K - 1) / sm_knot[p.K - 1];
   tb.time = sm_time; tb.lat = sm_lat;
   tb.list = sm_broad; tb.row_off = reinterpret_cast<const int*>(smem + L.off_rows); tb.row_cnt = tb.row_off + p.win_rows;
-  tb.use_lists = false; tb.masks = false; tb.adj = nullptr;
+  tb.use_lists = false;
   latcost = sm_latcost;
 }
 
@@ -969,13 +966,13 @@ __device__ __forceinline__ void select_and_export(const EvalParams& p, unsigned 
       if (lex_less(red_cost[q], red_idx[q], my_cost, my_idx)) { my_cost = red_cost[q]; my_idx = red_idx[q]; }
     p.blk_cost[blk_index(p)] = my_cost;
     p.blk_idx[blk_index(p)] = my_idx;
+    PHASE(p, 7);
     __threadfence();
     const unsigned int t = atomicAdd(p.ticket, 1u);
     *is_last_p = (t == (unsigned int)blk_count(p) - 1u);
   }
   __syncthreads();
   if (!*is_last_p) return;
-  PHASE(p, 7);
   // the last block to finish reduces the per-block winners: deterministic, no floating-point atomics
   __threadfence();
   my_cost = INFINITY; my_idx = -1;

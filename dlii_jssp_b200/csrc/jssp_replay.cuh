@@ -54,10 +54,44 @@ __host__ __device__ inline ReplaySmem replay_smem_layout(int kpad, int P, int W,
   L.off_latcost = e; e += (size_t)W * 4 * 8;
   L.off_window = e; e += (size_t)win_rows * OMpad * 16;
   e = (e + 15) & ~(size_t)15;
-  L.off_tile = e; e += tile_scratch_bytes(W, threads, tile_rounds, OMpad, P);
+  L.off_tile = e; e += tile_scratch_bytes(W, threads, tile_rounds);
   const size_t s = o + ((seed_bytes + 15) & ~(size_t)15);
   L.total = e > s ? e : s;
   return L;
+}
+
+// Selection, export and hand-off of a cycle whose candidates were all evaluated by THIS block: block argmin of (cost, index) by
+// warp shuffles and one value per warp through shared memory - no per-block records in global memory, no ticket, no fence (the
+// multi-block form is select_and_export) - then the same export_block / batch_handoff as everywhere else.
+__device__ __forceinline__ void replay_select_export(const EvalParams& p, BlockTables& tb, double my_cost, int my_idx, int N, int Ns,
+                                                     double* red_cost, int* red_idx, int* sm_npts) {
+  const int nwarps = blockDim.x >> 5, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oc = __shfl_down_sync(0xffffffffu, my_cost, o);
+    const int oi = __shfl_down_sync(0xffffffffu, my_idx, o);
+    if (lex_less(oc, oi, my_cost, my_idx)) { my_cost = oc; my_idx = oi; }
+  }
+  if (lane == 0) { red_cost[wid] = my_cost; red_idx[wid] = my_idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < nwarps; ++q)
+      if (lex_less(red_cost[q], red_idx[q], my_cost, my_idx)) { my_cost = red_cost[q]; my_idx = red_idx[q]; }
+    BestRecord r;
+    r.key = orderable_bits(my_idx >= 0 ? my_cost : INFINITY);
+    r.idx = my_idx;
+    r.cost = my_cost;
+    r.n_pts = 0;
+    r.n_candidates = N;
+    r.n_seeds = Ns;
+    r.pad = p.n_seeds_ptr ? p.n_seeds_ptr[3] : 0;   // seed-enumeration overflow flag, reported with the selection
+    *p.best = r;
+    red_idx[0] = my_idx;
+  }
+  __syncthreads();
+  const int best = red_idx[0];
+  if (best >= 0) export_block(p, tb, best, p.best_traj, sm_npts);
+  batch_handoff(p, best, N, sm_npts);
 }
 
 template <int kMaxThreads>
@@ -67,7 +101,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
   __shared__ __align__(16) EvalParams sp;
   __shared__ double red_cost[kMaxThreads / 32];
   __shared__ int red_idx[kMaxThreads / 32];
-  __shared__ bool is_last;
   __shared__ int sm_npts;
   const int sc = blockIdx.x;
   if (!slot_live(slots, sc)) return;                     // block-uniform
@@ -84,8 +117,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
   double* sm_latcost = reinterpret_cast<double*>(smem + L.off_latcost);
   float4* sm_win = reinterpret_cast<float4*>(smem + L.off_window);
   double* sm_tile = reinterpret_cast<double*>(smem + L.off_tile);
-  float* sm_adj = reinterpret_cast<float*>(sm_tile + (size_t)nwarps * tile_geom(sp.W, tile_rounds).warp_doubles);
-  float2* sm_latf = reinterpret_cast<float2*>(sm_adj + ((max_OMpad + 3) & ~3));
   // reference line + time grid: once per scenario, through the TMA engine
   {
     const uint32_t knot_bytes = (uint32_t)sp.kpad * 8u, coef_bytes = (uint32_t)sp.kpad * 64u, time_bytes = (uint32_t)((sp.P + 1) & ~1) * 8u;
@@ -108,7 +139,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
   double* gbase = wscr + (size_t)gg * tg.grp_stride;
   double* gterms = wscr + tg.off_terms + (size_t)gg * tg.TL * 3;
   double* prof = wscr + tg.off_prof + (size_t)gg * TILE_PROF;
-  unsigned long long* gmask = reinterpret_cast<unsigned long long*>(wscr + tg.off_mask) + (size_t)gg * tg.TL;
   double* seeds = wk.seeds + (size_t)sc * wk.cap_seeds * 10;
   int* counts = wk.counts + (size_t)sc * 4;
 
@@ -131,10 +161,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
     // -- K2: evaluation ---------------------------------------------------------------------------------------------------
     const int Ns = min(__ldcg(counts + 2), sp.seed_cap);
     const int N = Ns * W;
-    stage_lateral(sp, sm_time, sm_lat, sm_latcost);       // ends with a block barrier
-    const float dmax = block_lateral_reach(sm_lat, W, sp.P);
-    fill_circle_adj(sp, dmax, sm_adj);                    // seed-level circles: z' = z - adj[om] (jssp_eval_tiled.cuh)
-    fill_lateral_f32(sm_lat, W, sp.P, sm_latf);
     // obstacle window of the cycle: rows now, now + check_res, ... of the broad-phase table (absent rows = far away)
     {
       const int n_el = sp.win_rows * sp.OMpad;
@@ -144,14 +170,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
         sm_win[e] = step < sp.Tt ? sp.broad[(size_t)step * sp.OMpad + o] : make_float4(0.f, 0.f, FAR_AWAY, 0.f);
       }
     }
-    __syncthreads();
+    stage_lateral(sp, sm_time, sm_lat, sm_latcost);       // ends with a block barrier
     BlockTables tb;
     tb.broad = sp.win_rows > 0 ? sm_win : sp.broad;
     tb.broad_row0 = sp.win_rows > 0 ? 0 : sp.now; tb.broad_stride = sp.win_rows > 0 ? 1 : sp.check_res;
     tb.sp.knot = sm_knot; tb.sp.coef = sm_coef; tb.sp.K = sp.K; tb.sp.kpad = sp.kpad;
     tb.sp.inv_h = (double)(sp.K - 1) / sm_knot[sp.K - 1];
     tb.time = sm_time; tb.lat = sm_lat;
-    tb.list = nullptr; tb.row_off = nullptr; tb.row_cnt = nullptr; tb.use_lists = false; tb.masks = sp.win_rows > 0; tb.adj = sm_adj;
+    tb.list = nullptr; tb.row_off = nullptr; tb.row_cnt = nullptr; tb.use_lists = false;
     const double* latcost = sm_latcost;
     double my_cost = INFINITY;
     int my_idx = -1;
@@ -161,8 +187,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
       const bool active = g_ < tg.gpw && k < Ns;
       if (active && j == 0) tile_profile_store(prof, seeds + (size_t)k * 10, sp.s0, sp.v0, sp.a0);
       __syncwarp();
-      TileSink sink(sp, tb, prof, sm_lat + (size_t)j * sp.P * 4);
-      walk_tiles(sp, tb, tg, gbase, gterms, gmask, prof, sm_latf, active, j, W, sink);
+      TileSink sink(sp, tb);
+      walk_tiles(sp, tb, tg, gbase, gterms, prof, active, j, W, sink);
       if (active) {
         const int n = j * Ns + k;                          // width-major candidate index (jerk_space_sampling_planner.py:106,124-125)
         const double cost = candidate_cost(sp, sink, latcost + j * 4);
@@ -177,8 +203,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
 #ifdef JSSP_PROFILE_PHASES
     if (blockIdx.x == 0 && threadIdx.x == 0) { g_replay_ns[5] += 1; g_replay_ns[6] += (Ns + spb - 1) / spb; g_replay_ns[7] += Ns; }
 #endif
-    // -- selection, export, hand-off (one block per scenario: the ticket logic of select_and_export sees a 1-block grid) ----
-    select_and_export<1>(sp, smem, tb, latcost, true, my_cost, my_idx, N, Ns, red_cost, red_idx, &is_last, &sm_npts);
+    // -- selection, export, hand-off ------------------------------------------------------------------------------------------
+    replay_select_export(sp, tb, my_cost, my_idx, N, Ns, red_cost, red_idx, &sm_npts);
     __syncthreads();                                      // the hand-off's writes (slot record, replay state) are visible
     RSTAMP(4);
   }

@@ -33,11 +33,15 @@ print(f"{which}: {used.sum()} blocks; kernel span {(t[:, 4].max() - t0) / 1e3:.1
 names = ["entry", "staged", "lists", "walk", "select"]
 last = t[t[:, 5] > 0]
 if len(last):
-    print(f"  last block: ticket taken +{(last[0, 7] - last[0, 3]) / 1e3:.1f} us after its walk, reduce done +{(last[0, 5] - last[0, 3]) / 1e3:.1f} us, export {(last[0, 6] - last[0, 5]) / 1e3:.1f} us, "
+    print(f"  last block: argmin +{(last[0, 7] - last[0, 3]) / 1e3:.1f} us after its walk, reduce done +{(last[0, 5] - last[0, 3]) / 1e3:.1f} us, export {(last[0, 6] - last[0, 5]) / 1e3:.1f} us, "
           f"tail {(last[0, 4] - last[0, 6]) / 1e3:.1f} us")
 for k in range(5):
     col = (t[:, k] - t0) / 1e3
     print(f"  {names[k]:7s} stamp: min {col.min():7.1f}  median {np.median(col):7.1f}  max {col.max():7.1f} us")
+d = (t[:, 7] - t[:, 3]) / 1e3
+print(f"  walk->block argmin done (before the fence): median {np.median(d):6.2f}  p90 {np.quantile(d, 0.9):6.2f}  max {d.max():6.2f} us")
+d = (t[:, 4] - t[:, 7]) / 1e3
+print(f"  fence + ticket + barrier:                   median {np.median(d):6.2f}  p90 {np.quantile(d, 0.9):6.2f}  max {d.max():6.2f} us")
 for a, b in ((0, 1), (1, 2), (2, 3), (3, 4)):
     d = (t[:, b] - t[:, a]) / 1e3
     print(f"  {names[a]}->{names[b]}: median {np.median(d):6.1f}  p90 {np.quantile(d, 0.9):6.1f}  max {d.max():6.1f} us")
