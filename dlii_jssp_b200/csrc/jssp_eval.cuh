@@ -960,13 +960,13 @@ __device__ __forceinline__ void select_and_export(const EvalParams& p, unsigned 
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 0) { red_cost[wid] = my_cost; red_idx[wid] = my_idx; }
+  PHASE(p, 7);
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int q = 1; q < nwarps; ++q)
       if (lex_less(red_cost[q], red_idx[q], my_cost, my_idx)) { my_cost = red_cost[q]; my_idx = red_idx[q]; }
     p.blk_cost[blk_index(p)] = my_cost;
     p.blk_idx[blk_index(p)] = my_idx;
-    PHASE(p, 7);
     __threadfence();
     const unsigned int t = atomicAdd(p.ticket, 1u);
     *is_last_p = (t == (unsigned int)blk_count(p) - 1u);
