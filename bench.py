@@ -574,6 +574,15 @@ def bench_sweep(ctx: Ctx, args, workload_name="C4") -> dict:
     launches = (bt.launch_count - l0) // (steps + warmup)
     total_ms = sum(ms)
     results = bt.results()
+    # the same sweep through the persistent replay kernel (one CTA per scenario, one launch per sub-batch): reported beside the default
+    persistent_ms = None
+    if fop is None:
+        def pstep():
+            bt.reset(); bt.run(args.cycles, kernel="persistent")
+        pms = ctx.timed(pstep, 3, 2)
+        persistent_ms, = ctx.allmax(sum(pms) / len(pms))
+        pres = bt.results()
+        persistent_same = all((a.end, a.cycles, list(a.best_idx)) == (b.end, b.cycles, list(b.best_idx)) for a, b in zip(results, pres))
     units = sum(sum(r.n_candidates) for r in results) * pts
     flops = sum(sum(r.n_candidates) * pts * (F_BASE + F_SAT * p.state.shape[0] * p.state.shape[1] / 2.0) for r, p in zip(results, packed))
     cycles = sum(r.cycles for r in results)
@@ -611,8 +620,11 @@ def bench_sweep(ctx: Ctx, args, workload_name="C4") -> dict:
                        "sweep_ms": 1e3 * e2e_max},
                "digest": D.sweep_digest(allrows), "end_status_counts": ends, "gpu_launches_per_step": int(launches),
                "scenarios_per_s": n_all / sweep_s, "cycles_per_s": cycles_all / sweep_s, "amortised_cycle_us": 1e6 * sweep_s * world / max(cycles_all, 1),
-               "parallelism": f"scenario shards over {world} ranks ({bt.describe() if hasattr(bt, 'describe') else 'batched device-resident replay'}), no collective",
+               "parallelism": f"scenario shards over {world} ranks (lock-step device-resident replay, {k_sub} sub-batch(es) on separate streams per rank), no collective",
                "algorithmic_tflops_per_gpu": flops_all / sweep_s / 1e12 / world, "fp32_fma_peak_tflops": peak32.value,
+               "persistent_kernel": None if persistent_ms is None else {"ms_per_step": persistent_ms, "same_rows_on_rank0": bool(persistent_same),
+                                     "note": "JSSP_FLAG_PERSISTENT: one CTA per scenario loops over its plan cycles in ONE launch; identical rows, slower "
+                                             "than the lock-step default on B200 (DESIGN.md 3.5)"},
                "clocks": clocks}
     bt.close()
     return out

@@ -1629,9 +1629,9 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
     return JSSP_OK;
   }
   const int max_rows = (b->P + b->cfg.check_res - 1) / b->cfg.check_res;
-  // default: the persistent replay kernel - one CTA per scenario, every cycle of the call in ONE launch.  Few scenarios (at most
-  // one per SM) get 512 threads each, more get 256 so that two CTAs share an SM.
-  if (!(flags & (JSSP_FLAG_LOCKSTEP | JSSP_FLAG_FORCE_WARP | JSSP_FLAG_FORCE_THREAD | JSSP_FLAG_FORCE_GROUP | JSSP_FLAG_FORCE_TILED)) && !b->tune.lockstep) {
+  // JSSP_FLAG_PERSISTENT: the persistent replay kernel - one CTA per scenario, every cycle of the call in ONE launch.  Few scenarios
+  // (at most one per SM) get 512 threads each, more get 256 so that two CTAs share an SM.
+  if ((flags & JSSP_FLAG_PERSISTENT) && !(flags & JSSP_FLAG_LOCKSTEP)) {
     int threads = n_scenarios <= b->sm_count ? REPLAY_MAX_THREADS : 256;
     if (b->tune.seed_threads == 256 || b->tune.seed_threads == 512 || b->tune.seed_threads == 1024) threads = b->tune.seed_threads;      // tools/ only
     const int rows = b->max_OMpad > 0 ? max_rows : 0;

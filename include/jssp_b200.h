@@ -100,8 +100,10 @@ typedef struct jssp_cycle_in {
 #define JSSP_FLAG_FORCE_TILED 128 /* use the tiled two-phase kernel (default for larger cycles): per tile of the horizon the seed-only
                                     work runs in parallel into shared memory, then one lane per candidate walks the tile; same masks
                                     and selection, costs equal to rounding */
-#define JSSP_FLAG_LOCKSTEP 256    /* jssp_batch_run only: the lock-step pipeline (two launches per plan cycle for the whole batch) instead of
-                                    the persistent kernel (one CTA per scenario loops over its cycles, one launch per call); same results */
+#define JSSP_FLAG_LOCKSTEP 256    /* jssp_batch_run only: the lock-step pipeline (two launches per plan cycle for the whole batch; the default) */
+#define JSSP_FLAG_PERSISTENT 512  /* jssp_batch_run only: the persistent replay kernel - one CTA per scenario loops seed enumeration -> evaluation ->
+                                    selection -> export -> hand-off over the scenario's own plan cycles, ONE launch per call, no lock-step between
+                                    scenarios; same results (measured slower than the lock-step pipeline on B200) */
 #define JSSP_FLAG_NO_CULL 4      /* test every obstacle state instead of the per-block culled lists (same results) */
 
 /* Outputs.  Candidate n = w * n_seeds + k (width-major, jssp.py:106,124-125).  All dev pointers may be NULL.  With
@@ -348,10 +350,10 @@ int32_t jssp_batch_set_scenario(jssp_batch* b, int32_t slot, const jssp_scenario
 /* put slots [0, n_scenarios) back to the state jssp_batch_set_scenario left them in (device-to-device; asynchronous):
  * a sweep can be repeated without uploading the scenarios again */
 int32_t jssp_batch_reset(jssp_batch* b, int32_t n_scenarios, void* stream);
-/* enqueue up to `n_cycles` plan cycles of every slot in [0, n_scenarios) (finished scenarios idle).  Default: ONE launch of the
- * persistent replay kernel - one CTA per scenario loops seed enumeration -> evaluation -> selection -> export -> hand-off over
- * its own cycles, no lock-step between scenarios.  JSSP_FLAG_LOCKSTEP (or any JSSP_FLAG_FORCE_* kernel choice, or the FOP
- * planner): the lock-step pipeline, two launches per cycle for the whole batch.  Same results.  Asynchronous. */
+/* enqueue up to `n_cycles` plan cycles of every slot in [0, n_scenarios) (finished scenarios idle).  Default: the lock-step
+ * pipeline - every step runs one plan cycle of all running scenarios with two launches (seed enumeration, evaluation +
+ * selection + export + hand-off); JSSP_FLAG_FORCE_* choose its evaluation kernel.  JSSP_FLAG_PERSISTENT: ONE launch of the
+ * persistent replay kernel, in which every scenario's CTA loops over its own plan cycles.  Same results.  Asynchronous. */
 int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int32_t flags, void* stream);
 /* copy results back (synchronises): results_host[n_scenarios], records_host[n_scenarios][max_cycles] (may be NULL) */
 int32_t jssp_batch_fetch(jssp_batch* b, int32_t n_scenarios, jssp_scenario_result* results_host,

@@ -30,7 +30,7 @@ def test_batch_matches_single_scenario_replays(scenario_fixture):
     assert any(g.end in (1, 1.5, 2) for g in got)           # at least one scenario ran to a real end status
 
 
-@pytest.mark.parametrize("kernel", [None, "lockstep", "warp", "thread", "group", "tiled"])
+@pytest.mark.parametrize("kernel", [None, "persistent", "warp", "thread", "group", "tiled"])
 def test_batch_kernels_agree_with_oracle_replay(kernel):
     scs = [S.synthetic_intersection(i) for i in (3, 4)]
     got = B.run_batch(scs, max_cycles=20, kernel=kernel)
@@ -50,7 +50,7 @@ def test_batch_larger_than_capacity_is_chunked_and_perturbed_scenes(scenario_fix
     got = B.run_batch(scs, max_cycles=16, batch=bt)
     for sc, g in zip(scs, got):
         _same(g, R.run_replay(sc, max_cycles=16))
-    assert bt.launch_count >= 2              # persistent replay kernel: ONE launch per chunk (+ table packing), not two per cycle
+    assert bt.launch_count >= 2 * 16 * 2
     tr = bt.best_traj(0)
     assert tr.shape == (51, 16) and np.isfinite(tr[:, :9]).all()
     bt.close()
@@ -153,17 +153,17 @@ def test_sub_batches_on_separate_streams_replay_identically(scenario_fixture):
 
 
 def test_persistent_and_lockstep_replays_are_identical(scenario_fixture):
-    """The persistent replay kernel (one CTA per scenario loops over its plan cycles in one launch; the default) and the lock-step
-    pipeline (two launches per cycle for the whole batch) produce the same records, cycle by cycle, for a mixed batch: bundled
+    """The persistent replay kernel (one CTA per scenario loops over its plan cycles in one launch) and the lock-step pipeline
+    (two launches per cycle for the whole batch; the default) produce the same records, cycle by cycle, for a mixed batch: bundled
     scene, synthetic intersections with 3..12 vehicles, an obstacle-free scenario - with 256 and (few scenarios) 512 threads."""
     scs = [scenario_fixture] + [S.synthetic_intersection(i) for i in range(20, 31)]
     empty = S.synthetic_intersection(9)
     empty.vehicle_traj = {}
     scs.append(empty)
-    a = B.run_batch(scs, max_cycles=60)
-    b = B.run_batch(scs, max_cycles=60, kernel="lockstep")
+    a = B.run_batch(scs, max_cycles=60, kernel="persistent")
+    b = B.run_batch(scs, max_cycles=60)
     for x, y in zip(a, b):
         _same(x, y)
     many = [S.synthetic_intersection(i) for i in range(100, 260)]         # > 148 scenarios: 256-thread CTAs, several per SM
-    for x, y in zip(B.run_batch(many, max_cycles=25), B.run_batch(many, max_cycles=25, kernel="lockstep")):
+    for x, y in zip(B.run_batch(many, max_cycles=25, kernel="persistent"), B.run_batch(many, max_cycles=25)):
         _same(x, y)

@@ -99,8 +99,11 @@ def test_sweep_sample_matches_oracle_replay_golden():
     from dlii_jssp_b200 import batch as B
     g = _sweep_golden()
     ids, C = g["ids"].tolist(), int(g["max_cycles"][0])
-    got = B.run_batch([S.synthetic_intersection(i) for i in ids], max_cycles=C)
+    scs = [S.synthetic_intersection(i) for i in ids]
+    got = B.run_batch(scs, max_cycles=C)
     assert len(got) >= 32
+    for a, b in zip(got, B.run_batch(scs, max_cycles=C, kernel="persistent")):     # the persistent replay kernel: the same rows
+        assert (a.end, a.cycles, list(a.best_idx), list(a.n_candidates), a.ego_rows) == (b.end, b.cycles, list(b.best_idx), list(b.n_candidates), b.ego_rows)
     for k, r in enumerate(got):
         c = int(g["cycles"][k])
         assert (r.end, r.cycles) == (float(g["end"][k]), c), (ids[k], r.end, r.cycles, g["end"][k], c)
