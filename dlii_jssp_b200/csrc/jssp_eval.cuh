@@ -943,19 +943,6 @@ __device__ __forceinline__ void batch_handoff(const EvalParams& p, int best, int
   if (c + 1 >= b->n_cycles_cap) b->live = 0;         // table end: stays "running" (end = -1) like a max_cycles stop
 }
 
-// Warp argmin of (cost, index) by shuffles, one value per warp into shared memory.  Out of line on purpose: a block runs this
-// code once, at the very end of its walk, and a cold instruction fetch then sits on the critical path of the whole launch - the
-// tiled kernel calls it once more at its start (results discarded) so that the lines are in the SM's instruction cache.
-__device__ __noinline__ void warp_argmin_to_smem(double& my_cost, int& my_idx, double* red_cost, int* red_idx) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double oc = __shfl_down_sync(0xffffffffu, my_cost, o);
-    const int oi = __shfl_down_sync(0xffffffffu, my_idx, o);
-    if (lex_less(oc, oi, my_cost, my_idx)) { my_cost = oc; my_idx = oi; }
-  }
-  if ((threadIdx.x & 31) == 0) { red_cost[threadIdx.x >> 5] = my_cost; red_idx[threadIdx.x >> 5] = my_idx; }
-}
-
 // Selection shared by both evaluation kernels: block argmin of (cost, index) by warp shuffles, one record per block,
 // and the last block to finish (ticket counter) reduces the per-block winners - deterministic, lexicographic, no
 // floating-point atomics - and exports the winning trajectory in the same launch.
@@ -965,8 +952,14 @@ __device__ __forceinline__ void select_and_export(const EvalParams& p, unsigned 
                                                   int* red_idx, bool* is_last_p, int* sm_npts_p) {
   const int nwarps = blockDim.x >> 5;
   // block argmin (cost, index) - warp shuffles, then one value per warp through shared memory
-  warp_argmin_to_smem(my_cost, my_idx, red_cost, red_idx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oc = __shfl_down_sync(0xffffffffu, my_cost, o);
+    const int oi = __shfl_down_sync(0xffffffffu, my_idx, o);
+    if (lex_less(oc, oi, my_cost, my_idx)) { my_cost = oc; my_idx = oi; }
+  }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { red_cost[wid] = my_cost; red_idx[wid] = my_idx; }
   PHASE(p, 7);
   __syncthreads();
   if (threadIdx.x == 0) {

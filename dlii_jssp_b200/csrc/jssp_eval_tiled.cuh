@@ -335,7 +335,6 @@ __device__ __forceinline__ void evaluate_tiled_body(const EvalParams& p, unsigne
   const double* latcost;
   const bool staged = blk_index(p) * spb < Ns;   // block-uniform
   PHASE(p, 0);
-  { double c0 = my_cost; int i0 = my_idx; warp_argmin_to_smem(c0, i0, red_cost, red_idx); }     // instruction-cache warm-up of the tail, see there
   if (staged) {
     stage_tables<kMode>(p, smem, tb, latcost);
     PHASE(p, 1);
