@@ -7,50 +7,101 @@ namespace jssp {
 // ------------------------------------------------------------------------------------------------------------------
 // K3: export of the selected trajectory (float64 rows) and optional fp32 state dump of every candidate
 // ------------------------------------------------------------------------------------------------------------------
-struct DumpSink {
-  __device__ __forceinline__ bool vetoed() const { return false; }
-  float* out;   // [P][8] of this candidate: s, s_d, s_dd, d, x, y, yaw, c
-  const double* lat;
-  double pyaw, pds;
-  __device__ __forceinline__ void sample(int i, double, double s, double sd, double sdd, double) {
-    float4* r = reinterpret_cast<float4*>(out + (size_t)i * JSSP_STATE_COLS);
-    const float nanv = __int_as_float(0x7fc00000);
-    r[0] = make_float4((float)s, (float)sd, (float)sdd, (float)lat[i * 4]);
-    r[1] = make_float4(nanv, nanv, nanv, nanv);
-  }
-  __device__ __forceinline__ void point(int i, double x, double y) {
-    out[(size_t)i * JSSP_STATE_COLS + 4] = (float)x; out[(size_t)i * JSSP_STATE_COLS + 5] = (float)y;
-  }
-  __device__ __forceinline__ void segment(int i, double, double, double dx, double dy, double ds, double, double) {
-    const double yaw = heading_of(dx, dy);
-    out[(size_t)i * JSSP_STATE_COLS + 6] = (float)yaw;
-    if (i >= 1) out[(size_t)(i - 1) * JSSP_STATE_COLS + 7] = (float)((yaw - pyaw) / pds);
-    pyaw = yaw; pds = ds;
-  }
-  __device__ __forceinline__ void finish(int n_pts, double, double) {
-    if (n_pts >= 2) {
-      out[(size_t)(n_pts - 1) * JSSP_STATE_COLS + 6] = (float)pyaw;
-      out[(size_t)(n_pts - 2) * JSSP_STATE_COLS + 7] = (float)((pyaw - pyaw) / pds);
-    }
-  }
-};
+// One warp per seed, lanes = samples: nothing here is a serial walk.  Per seed the unrolled s, s_d, s_dd and the reference point
+// with its unit normal go to the warp's shared-memory scratch once; per lateral target every lane forms its own point and its two
+// neighbours, the forward-difference headings (jerk_space_sampling_planner.py:155-160, last one repeated) and the un-unwrapped
+// curvature (:161-163) - the heading difference as atan2(cross, dot) of the float64 chord vectors plus the +-2*pi jump the
+// reference's plain subtraction has when the heading crosses +-pi - and writes its row [s, s_d, s_dd, d, x, y, yaw, c]: a warp
+// stores 32 consecutive rows = 1 KB contiguous, so the dump is written at HBM speed (1,632 B per candidate, the HBM-bound variant
+// of SURVEY.md section 8d).
+constexpr int DUMP_WARPS = 8;
+__host__ __device__ inline size_t dump_scratch_bytes(int P) { return (size_t)DUMP_WARPS * (TILE_PROF + (size_t)P * 4 + (size_t)((P * 3 + 1) / 2) + 2) * 8; }
 
-__global__ void __launch_bounds__(EVAL_THREADS) dump_states_kernel(const __grid_constant__ EvalParams p, float* __restrict__ states) {
+__device__ __forceinline__ void dump_point(const double* base, const double* lat, int i, double& x, double& y) {
+  const double2 a = *reinterpret_cast<const double2*>(base + (size_t)i * 4), b = *reinterpret_cast<const double2*>(base + (size_t)i * 4 + 2);
+  const double d = lat[i * 4];
+  x = fma(-d, b.x, a.x); y = fma(d, b.y, a.y);
+}
+
+__global__ void __launch_bounds__(DUMP_WARPS * 32) dump_states_kernel(const __grid_constant__ EvalParams p, float* __restrict__ states) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int Ns = resolve_n_seeds(p);
-  const int N = Ns * p.W;
-  if (blockIdx.x * blockDim.x >= N) return;
+  const int P = p.P, W = p.W;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if ((int)blockIdx.x * DUMP_WARPS >= Ns) return;
   BlockTables tb;
   const double* latcost;
   stage_tables<0>(p, smem, tb, latcost);
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  const int w = n / Ns, k = n - w * Ns;
-  LonWalk lp;
-  lon_walk_init(lp, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
-  DumpSink sink{states + (size_t)n * p.P * JSSP_STATE_COLS, tb.lat + (size_t)w * p.P * 4, 0.0, 0.0};
-  const int seg0 = spline_bisect(tb.sp, fmin(fmax(p.s0, tb.sp.knot[0]), tb.sp.knot[p.K - 1]));
-  walk_candidate(p, tb, lp, w, seg0, sink);
+  const SmemLayout L = eval_smem_layout(0, p.OMpad, 0, p.K, p.kpad, p.P, p.W);
+  const size_t per_warp = TILE_PROF + (size_t)P * 4 + (size_t)((P * 3 + 1) / 2) + 2;
+  double* prof = reinterpret_cast<double*>(smem + ((L.total + 15) & ~(size_t)15)) + (size_t)wid * per_warp;
+  double* base = prof + TILE_PROF;                       // [P][4] ix, iy, u, v
+  float* lon = reinterpret_cast<float*>(base + (size_t)P * 4);   // [P][3] s, s_d, s_dd
+  const float nanv = __int_as_float(0x7fc00000);
+  for (int k = blockIdx.x * DUMP_WARPS + wid; k < Ns; k += gridDim.x * DUMP_WARPS) {       // warp-uniform
+    if (lane == 0) tile_profile_store(prof, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
+    __syncwarp();
+    int n_pts = P, kseg = 0;
+    for (int b0 = 0; b0 < P; b0 += 32) {
+      const int i = b0 + lane;
+      bool off = false;
+      if (i < P) {
+        double s, sd, sdd, sddd;
+        tile_lon_eval(prof, kseg, tb.time[i], s, sd, sdd, sddd);
+        lon[i * 3] = (float)s; lon[i * 3 + 1] = (float)sd; lon[i * 3 + 2] = (float)sdd;
+        off = !spline_in_range(tb.sp, s);
+        if (!off) {
+          double ix, iy, u, v;
+          frenet_base(tb.sp, spline_walk(tb.sp, s, 0), s, ix, iy, u, v);
+          double2* e = reinterpret_cast<double2*>(base + (size_t)i * 4);
+          e[0] = make_double2(ix, iy); e[1] = make_double2(u, v);
+        }
+      }
+      const unsigned int m = __ballot_sync(0xffffffffu, off);
+      if (m != 0u && n_pts == P) n_pts = b0 + __ffs(m) - 1;      // first sample off the reference line (jssp.py:138-139)
+    }
+    __syncwarp();
+    for (int w = 0; w < W; ++w) {
+      const double* lat = tb.lat + (size_t)w * P * 4;
+      float* out = states + ((size_t)w * Ns + k) * P * JSSP_STATE_COLS;
+      for (int i = lane; i < P; i += 32) {
+        float4 r0 = make_float4(lon[i * 3], lon[i * 3 + 1], lon[i * 3 + 2], (float)lat[i * 4]);
+        float4 r1 = make_float4(nanv, nanv, nanv, nanv);
+        if (i < n_pts) {
+          double x, y;
+          dump_point(base, lat, i, x, y);
+          r1.x = (float)x; r1.y = (float)y;
+          if (n_pts >= 2) {
+            // heading of sample i = chord hs -> hs + 1 with hs = min(i, n_pts - 2) (the last heading repeats the previous one)
+            const int hs = min(i, n_pts - 2);
+            double ax, ay, bx, by;
+            dump_point(base, lat, hs, ax, ay);
+            dump_point(base, lat, hs + 1, bx, by);
+            const double dx0 = bx - ax, dy0 = by - ay;
+            r1.z = atan2f((float)dy0, (float)dx0);
+            if (i < n_pts - 1) {                      // c_i = (yaw_{i+1} - yaw_i) / ds_i, no unwrapping
+              double raw = 0.0;
+              if (i + 1 <= n_pts - 2) {
+                double cx, cy;
+                dump_point(base, lat, i + 2, cx, cy);
+                const double dx1 = cx - bx, dy1 = cy - by;
+                const double cross = fma(dx0, dy1, -(dy0 * dx1)), dot = fma(dx0, dx1, dy0 * dy1);
+                raw = (double)atan2f((float)cross, (float)dot);
+                const bool nb = signbit(dy1);
+                if ((signbit(dy0) != nb) && (nb ? (cross > 0.0) : (cross < 0.0))) raw += nb ? -6.283185307179586 : 6.283185307179586;
+                if (dx1 == 0.0 && dy1 == 0.0) raw = 0.0 - (double)r1.z;      // atan2(0, 0) = 0
+                else if (dx0 == 0.0 && dy0 == 0.0) raw = (double)atan2f((float)dy1, (float)dx1);
+              }
+              r1.w = (float)(raw / sqrt(dx0 * dx0 + dy0 * dy0));
+            }
+          }
+        }
+        float4* o = reinterpret_cast<float4*>(out + (size_t)i * JSSP_STATE_COLS);
+        o[0] = r0; o[1] = r1;
+      }
+    }
+    __syncwarp();                                      // the scratch is reused by the warp's next seed
+  }
 }
 
 __global__ void best_record_kernel(const BestRecord* __restrict__ best, long long offset, unsigned long long* __restrict__ rec) {

@@ -842,8 +842,11 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   q.smem_obs = 0; q.win_rows = 0; q.list_cap = 0;
   const SmemLayout L2 = eval_smem_layout(0, q.OMpad, 0, q.K, q.kpad, q.P, q.W);
   if (out->states_dev) {
-    const int dump_blocks = std::max(1, (int)((n_max + EVAL_THREADS - 1) / EVAL_THREADS));
-    dump_states_kernel<<<dump_blocks, EVAL_THREADS, L2.total, st>>>(q, out->states_dev);
+    const size_t dump_bytes = ((L2.total + 15) & ~(size_t)15) + dump_scratch_bytes(q.P);
+    if (dump_bytes > (size_t)h->max_smem_optin) return JSSP_ERR_CAPACITY;
+    const long long want = (seeds_max + DUMP_WARPS - 1) / DUMP_WARPS;
+    const int dump_blocks = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * 4));
+    dump_states_kernel<<<dump_blocks, DUMP_WARPS * 32, dump_bytes, st>>>(q, out->states_dev);
     h->launches++;
     CK(cudaGetLastError());
   }
