@@ -15,7 +15,8 @@ namespace jssp {
 // stores 32 consecutive rows = 1 KB contiguous, so the dump is written at HBM speed (1,632 B per candidate, the HBM-bound variant
 // of SURVEY.md section 8d).
 constexpr int DUMP_WARPS = 8;
-__host__ __device__ inline size_t dump_scratch_bytes(int P) { return (size_t)DUMP_WARPS * (TILE_PROF + (size_t)P * 4 + (size_t)((P * 3 + 1) / 2) + 2) * 8; }
+__host__ __device__ inline size_t dump_warp_doubles(int P) { return (TILE_PROF + (size_t)P * 4 + (size_t)((P * 3 + 1) / 2) + 3) & ~(size_t)1; }   // even: 16-byte rows
+__host__ __device__ inline size_t dump_scratch_bytes(int P) { return (size_t)DUMP_WARPS * dump_warp_doubles(P) * 8; }
 
 __device__ __forceinline__ void dump_point(const double* base, const double* lat, int i, double& x, double& y) {
   const double2 a = *reinterpret_cast<const double2*>(base + (size_t)i * 4), b = *reinterpret_cast<const double2*>(base + (size_t)i * 4 + 2);
@@ -33,7 +34,7 @@ __global__ void __launch_bounds__(DUMP_WARPS * 32) dump_states_kernel(const __gr
   const double* latcost;
   stage_tables<0>(p, smem, tb, latcost);
   const SmemLayout L = eval_smem_layout(0, p.OMpad, 0, p.K, p.kpad, p.P, p.W);
-  const size_t per_warp = TILE_PROF + (size_t)P * 4 + (size_t)((P * 3 + 1) / 2) + 2;
+  const size_t per_warp = dump_warp_doubles(P);
   double* prof = reinterpret_cast<double*>(smem + ((L.total + 15) & ~(size_t)15)) + (size_t)wid * per_warp;
   double* base = prof + TILE_PROF;                       // [P][4] ix, iy, u, v
   float* lon = reinterpret_cast<float*>(base + (size_t)P * 4);   // [P][3] s, s_d, s_dd
