@@ -490,6 +490,9 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(allow_max_dynamic_smem(evaluate_group_kernel<0>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_group_kernel<1>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_group_kernel<2>, optin, &h->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_lanes_kernel<0>, optin, &h->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_lanes_kernel<1>, optin, &h->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_lanes_kernel<2>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_tiled_kernel<0>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_tiled_kernel<1>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_tiled_kernel<2>, optin, &h->max_smem_optin));
@@ -771,7 +774,7 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   bool small = n_max <= 16384 && small_bytes <= (size_t)h->max_smem_optin;
   if (in->flags & JSSP_FLAG_FORCE_THREAD) small = false;
   if ((in->flags & JSSP_FLAG_FORCE_WARP) && small_bytes <= (size_t)h->max_smem_optin) small = true;
-  if (in->flags & (JSSP_FLAG_FORCE_GROUP | JSSP_FLAG_FORCE_TILED)) small = false;
+  if (in->flags & (JSSP_FLAG_FORCE_GROUP | JSSP_FLAG_FORCE_TILED | JSSP_FLAG_FORCE_LANES)) small = false;
   const bool group = !small && !(in->flags & JSSP_FLAG_FORCE_THREAD);
   // large cycles: the tiled two-phase kernel unless the shuffle form is asked for (or its scratch does not fit)
   // tile length of the tiled kernel: the longest (<= ~16 samples) with which two blocks still share an SM, else the longest that fits
@@ -824,6 +827,23 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
     // one-call plan cycle: the evaluation is chained to the seed enumeration just enqueued (programmatic dependent launch)
     const bool chained = !ext && (in->flags & JSSP_FLAG_ENUMERATE) && !h->tune.no_pdl;
     CK(launch_chained(evaluate_small_kernel, dim3(blocks), SMALL_WARPS * 32, small_bytes, st, chained, p));
+  }
+  else if (in->flags & JSSP_FLAG_FORCE_LANES) {
+    // one warp per seed: blocks of as many warps as fit twice on an SM next to the tables, two blocks per SM, contiguous seed ranges
+    const int rows_max = (h->P + c.check_res - 1) / c.check_res;
+    const size_t lbase = (L.total + 15) & ~(size_t)15;
+    cudaFuncAttributes fa{};
+    cudaFuncGetAttributes(&fa, evaluate_lanes_kernel<2>);
+    const size_t two = (size_t)228 * 1024 / 2 - fa.sharedSizeBytes - 1024;
+    int warps = LANES_THREADS / 32;
+    while (warps > 2 && lbase + lanes_scratch_bytes(h->P, rows_max, warps * 32) > two) --warps;
+    const size_t lanes_total = lbase + lanes_scratch_bytes(h->P, rows_max, warps * 32);
+    if (lanes_total > (size_t)h->max_smem_optin) return JSSP_ERR_CAPACITY;
+    const int lblocks = (int)std::max<long long>(1, std::min<long long>((seeds_max + warps - 1) / warps, (long long)h->sm_count * 2));
+    if (lblocks > h->max_blocks) return JSSP_ERR_CAPACITY;
+    if (mode == 2) evaluate_lanes_kernel<2><<<lblocks, warps * 32, lanes_total, st>>>(p);
+    else if (mode == 1) evaluate_lanes_kernel<1><<<lblocks, warps * 32, lanes_total, st>>>(p);
+    else evaluate_lanes_kernel<0><<<lblocks, warps * 32, lanes_total, st>>>(p);
   }
   else if (tiled && mode == 2) evaluate_tiled_kernel<2><<<blocks, tiled_threads, tiled_total, st>>>(p);
   else if (tiled && mode == 1) evaluate_tiled_kernel<1><<<blocks, tiled_threads, tiled_total, st>>>(p);

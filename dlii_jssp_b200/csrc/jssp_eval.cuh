@@ -507,54 +507,34 @@ struct WalkSAt {
   LonWalk lp;
   __device__ __forceinline__ double operator()(double t) { double s, sd, sdd, sddd; lon_walk_eval(lp, t, s, sd, sdd, sddd); return s; }
 };
-template <class SAt>
-__device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* smem, BlockTables& tb, SAt& s_at, bool active,
-                                            int row_first = 0, int row_stride = 1) {
+// The list builder in three steps (build_lists runs them for the kernels whose threads each own one seed):
+//   lists_begin    clear the per-row ranges / counters (ends with a block barrier)
+//   phase A        every seed of the block widens [row_min, row_max] of every collision row with its arc length there
+//   lists_compact  one warp per row: ballot-compaction of the states whose reachable interval overlaps the row's range
+struct ListsView {
+  float4* list; int* row_off; int* row_cnt; unsigned int* row_min; unsigned int* row_max; int* cursor;
+};
+__device__ __forceinline__ ListsView lists_view(const EvalParams& p, unsigned char* smem) {
   const SmemLayout L = eval_smem_layout(p.win_rows, p.OMpad, 2, p.K, p.kpad, p.P, p.W, p.list_cap);
-  float4* list = reinterpret_cast<float4*>(smem + L.off_broad);
-  int* row_off = reinterpret_cast<int*>(smem + L.off_rows);
-  int* row_cnt = row_off + p.win_rows;
-  unsigned int* row_min = reinterpret_cast<unsigned int*>(row_cnt + p.win_rows);
-  unsigned int* row_max = row_min + p.win_rows;
-  int* cursor = reinterpret_cast<int*>(smem);        // [0] next free list entry, [1] overflow flag
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-  for (int r = tid; r < p.win_rows; r += blockDim.x) { row_min[r] = 0x7f800000u; row_max[r] = 0u; row_cnt[r] = 0; row_off[r] = 0; }
-  if (tid == 0) { cursor[0] = 0; cursor[1] = 0; }
+  ListsView v;
+  v.list = reinterpret_cast<float4*>(smem + L.off_broad);
+  v.row_off = reinterpret_cast<int*>(smem + L.off_rows);
+  v.row_cnt = v.row_off + p.win_rows;
+  v.row_min = reinterpret_cast<unsigned int*>(v.row_cnt + p.win_rows);
+  v.row_max = v.row_min + p.win_rows;
+  v.cursor = reinterpret_cast<int*>(smem);        // [0] next free list entry, [1] overflow flag
+  return v;
+}
+__device__ __forceinline__ void lists_begin(const EvalParams& p, const ListsView& v) {
+  for (int r = threadIdx.x; r < p.win_rows; r += blockDim.x) { v.row_min[r] = 0x7f800000u; v.row_max[r] = 0u; v.row_cnt[r] = 0; v.row_off[r] = 0; }
+  if (threadIdx.x == 0) { v.cursor[0] = 0; v.cursor[1] = 0; }
   __syncthreads();
-  const double s_end = tb.sp.knot[p.K - 1];
-  if (row_stride == 1) {
-    for (int r = 0; r < p.win_rows; ++r) {
-      unsigned int lo = 0x7f800000u, hi = 0u;
-      if (active) {
-        double s = s_at(tb.time[r * p.check_res]);
-        s = fmin(fmax(s, 0.0), s_end);                  // off-line samples are never collision-checked
-        lo = __float_as_uint(__double2float_rd(s));     // s >= 0: the bit patterns order like the values
-        hi = __float_as_uint(__double2float_ru(s));
-      }
-      lo = __reduce_min_sync(0xffffffffu, lo);
-      hi = __reduce_max_sync(0xffffffffu, hi);
-      if (lane == 0) { atomicMin(&row_min[r], lo); atomicMax(&row_max[r], hi); }
-    }
-  } else {
-    // the lanes of a group share the seed: lane j of the group evaluates the rows r = j (mod W); in one round every lane
-    // with the same j holds the same row, so a stride-W shuffle tree leaves the warp's range in the lanes of group 0
-    const int W = row_stride;
-    for (int r0 = 0; r0 < p.win_rows; r0 += W) {
-      const int r = r0 + row_first;
-      unsigned int lo = 0x7f800000u, hi = 0u;
-      if (active && r < p.win_rows) {
-        double s = s_at(tb.time[r * p.check_res]);
-        s = fmin(fmax(s, 0.0), s_end);
-        lo = __float_as_uint(__double2float_rd(s));
-        hi = __float_as_uint(__double2float_ru(s));
-      }
-      for (int off = W; off < 32; off <<= 1) {
-        const unsigned int lo2 = __shfl_down_sync(0xffffffffu, lo, off), hi2 = __shfl_down_sync(0xffffffffu, hi, off);
-        if (lane + off < 32) { lo = min(lo, lo2); hi = max(hi, hi2); }
-      }
-      if (lane < W && r < p.win_rows) { atomicMin(&row_min[r], lo); atomicMax(&row_max[r], hi); }
-    }
-  }
+}
+__device__ __forceinline__ void lists_compact(const EvalParams& p, const ListsView& v, BlockTables& tb) {
+  float4* list = v.list;
+  int* row_off = v.row_off; int* row_cnt = v.row_cnt; unsigned int* row_min = v.row_min; unsigned int* row_max = v.row_max; int* cursor = v.cursor;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  (void)tid;
   __syncthreads();
   constexpr int CH = 8;                               // chunks of 32 obstacle states held in registers per pass
   for (int r = wid; r < p.win_rows; r += nw) {
@@ -618,6 +598,51 @@ __device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* 
   __syncthreads();
   tb.use_lists = cursor[1] == 0;
   tb.broad = p.broad; tb.broad_row0 = p.now; tb.broad_stride = p.check_res;   // fallback path
+}
+
+
+template <class SAt>
+__device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* smem, BlockTables& tb, SAt& s_at, bool active,
+                                            int row_first = 0, int row_stride = 1) {
+  const ListsView v = lists_view(p, smem);
+  unsigned int* row_min = v.row_min; unsigned int* row_max = v.row_max;
+  const int lane = threadIdx.x & 31;
+  lists_begin(p, v);
+  const double s_end = tb.sp.knot[p.K - 1];
+  if (row_stride == 1) {
+    for (int r = 0; r < p.win_rows; ++r) {
+      unsigned int lo = 0x7f800000u, hi = 0u;
+      if (active) {
+        double s = s_at(tb.time[r * p.check_res]);
+        s = fmin(fmax(s, 0.0), s_end);                  // off-line samples are never collision-checked
+        lo = __float_as_uint(__double2float_rd(s));     // s >= 0: the bit patterns order like the values
+        hi = __float_as_uint(__double2float_ru(s));
+      }
+      lo = __reduce_min_sync(0xffffffffu, lo);
+      hi = __reduce_max_sync(0xffffffffu, hi);
+      if (lane == 0) { atomicMin(&row_min[r], lo); atomicMax(&row_max[r], hi); }
+    }
+  } else {
+    // the lanes of a group share the seed: lane j of the group evaluates the rows r = j (mod W); in one round every lane
+    // with the same j holds the same row, so a stride-W shuffle tree leaves the warp's range in the lanes of group 0
+    const int W = row_stride;
+    for (int r0 = 0; r0 < p.win_rows; r0 += W) {
+      const int r = r0 + row_first;
+      unsigned int lo = 0x7f800000u, hi = 0u;
+      if (active && r < p.win_rows) {
+        double s = s_at(tb.time[r * p.check_res]);
+        s = fmin(fmax(s, 0.0), s_end);
+        lo = __float_as_uint(__double2float_rd(s));
+        hi = __float_as_uint(__double2float_ru(s));
+      }
+      for (int off = W; off < 32; off <<= 1) {
+        const unsigned int lo2 = __shfl_down_sync(0xffffffffu, lo, off), hi2 = __shfl_down_sync(0xffffffffu, hi, off);
+        if (lane + off < 32) { lo = min(lo, lo2); hi = max(hi, hi2); }
+      }
+      if (lane < W && r < p.win_rows) { atomicMin(&row_min[r], lo); atomicMax(&row_max[r], hi); }
+    }
+  }
+  lists_compact(p, v, tb);
 }
 
 // Block index within the plan cycle and blocks per cycle.  The batch kernels run a TRANSPOSED grid (x = scenario, y = block):
