@@ -1370,6 +1370,8 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   CKC(allow_max_dynamic_smem(replay_persistent_kernel<512>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(replay_persistent_kernel<1024>, optin, &b->max_smem_optin));
   CKC(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device));
+  CKC(allow_max_dynamic_smem(evaluate_lanes_batch_kernel<0>, optin, &b->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_lanes_batch_kernel<1>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_tiled_batch_kernel<0>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_tiled_batch_kernel<1>, optin, &b->max_smem_optin));
   CKC(cudaDeviceSynchronize());
@@ -1690,7 +1692,7 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   const SmemLayout Ls = eval_smem_layout(0, b->max_OMpad, 0, b->max_K, b->max_kpad, b->P, b->W);
   const size_t small_bytes = Ls.total + small_scratch_bytes(b->P);
   bool small = (long long)n_scenarios * b->cfg.max_seeds * b->W <= 65536 && small_bytes <= (size_t)b->max_smem_optin;
-  if (flags & (JSSP_FLAG_FORCE_THREAD | JSSP_FLAG_FORCE_GROUP | JSSP_FLAG_FORCE_TILED)) small = false;
+  if (flags & (JSSP_FLAG_FORCE_THREAD | JSSP_FLAG_FORCE_GROUP | JSSP_FLAG_FORCE_TILED | JSSP_FLAG_FORCE_LANES)) small = false;
   if ((flags & JSSP_FLAG_FORCE_WARP) && small_bytes <= (size_t)b->max_smem_optin) small = true;
   // thread per candidate for the default 3 lateral targets (a scenario's ~150 seeds fill the group kernel's 40-seed blocks and
   // 30-of-32 lanes poorly: measured 49.0 vs 53.9 ms on the 800-scenario sweep), the group kernel from 4 targets on
@@ -1707,6 +1709,10 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   if (!small && L.total > (size_t)b->max_smem_optin) return JSSP_ERR_CAPACITY;
   const size_t tiled_total = ((L.total + 15) & ~(size_t)15) + tile_scratch_bytes(b->W, bthreads);     // default tile length (slot records carry tile_rounds = 0)
   const bool tiled = !small && (flags & JSSP_FLAG_FORCE_TILED) && tiled_total <= (size_t)b->max_smem_optin;
+  // lanes kernel (one warp per seed): a scenario's seeds spread over lanes_blocks blocks of 8 warps
+  const size_t lanes_total = ((L.total + 15) & ~(size_t)15) + lanes_scratch_bytes(b->P, max_rows, LANES_BATCH_THREADS);
+  const bool lanes = !small && (flags & JSSP_FLAG_FORCE_LANES) && lanes_total <= (size_t)b->max_smem_optin;
+  const int lanes_blocks = b->tune.seed_cluster > 0 ? b->tune.seed_cluster : (n_scenarios >= 400 ? 2 : 4);
   // few scenarios: clusters of up to 8 CTAs x 1024 threads answer with the lowest latency; many: one 512-thread CTA each
   int seed_cluster = 1;
   while (seed_cluster < SEED_MAX_CLUSTER && n_scenarios * seed_cluster * 2 <= 148) seed_cluster *= 2;
@@ -1717,6 +1723,8 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
     CKB(launch_seed_enum<true>(b->grids, SeedState{0, 0, 0}, b->d_slots, b->seed_work, n_scenarios, seed_cluster, seed_threads, b->seed_smem, st, pdl));
     const EvalParams* slots = b->d_slots;
     if (small) CKB(launch_chained(evaluate_small_batch_kernel, dim3(n_scenarios, std::min(b->blocks_warp, 128)), SMALL_WARPS * 32, small_bytes, st, pdl, slots));
+    else if (lanes && mode == 1) CKB(launch_chained(evaluate_lanes_batch_kernel<1>, dim3(n_scenarios, lanes_blocks), LANES_BATCH_THREADS, lanes_total, st, pdl, slots));
+    else if (lanes) CKB(launch_chained(evaluate_lanes_batch_kernel<0>, dim3(n_scenarios, lanes_blocks), LANES_BATCH_THREADS, lanes_total, st, pdl, slots));
     else if (tiled && mode == 1) CKB(launch_chained(evaluate_tiled_batch_kernel<1>, dim3(n_scenarios, blocks_group), bthreads, tiled_total, st, pdl, slots));
     else if (tiled) CKB(launch_chained(evaluate_tiled_batch_kernel<0>, dim3(n_scenarios, blocks_group), bthreads, tiled_total, st, pdl, slots));
     else if (group && mode == 1) CKB(launch_chained(evaluate_group_batch_kernel<1>, dim3(n_scenarios, blocks_group), bthreads, L.total, st, pdl, slots));
