@@ -490,9 +490,6 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(allow_max_dynamic_smem(evaluate_group_kernel<0>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_group_kernel<1>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_group_kernel<2>, optin, &h->max_smem_optin));
-  CKC(allow_max_dynamic_smem(evaluate_lanes_kernel<0>, optin, &h->max_smem_optin));
-  CKC(allow_max_dynamic_smem(evaluate_lanes_kernel<1>, optin, &h->max_smem_optin));
-  CKC(allow_max_dynamic_smem(evaluate_lanes_kernel<2>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_tiled_kernel<0>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_tiled_kernel<1>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_tiled_kernel<2>, optin, &h->max_smem_optin));
@@ -774,7 +771,7 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
   bool small = n_max <= 16384 && small_bytes <= (size_t)h->max_smem_optin;
   if (in->flags & JSSP_FLAG_FORCE_THREAD) small = false;
   if ((in->flags & JSSP_FLAG_FORCE_WARP) && small_bytes <= (size_t)h->max_smem_optin) small = true;
-  if (in->flags & (JSSP_FLAG_FORCE_GROUP | JSSP_FLAG_FORCE_TILED | JSSP_FLAG_FORCE_LANES)) small = false;
+  if (in->flags & (JSSP_FLAG_FORCE_GROUP | JSSP_FLAG_FORCE_TILED)) small = false;
   const bool group = !small && !(in->flags & JSSP_FLAG_FORCE_THREAD);
   // large cycles: the tiled two-phase kernel unless the shuffle form is asked for (or its scratch does not fit)
   // tile length of the tiled kernel: the longest (<= ~16 samples) with which two blocks still share an SM, else the longest that fits
@@ -827,23 +824,6 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
     // one-call plan cycle: the evaluation is chained to the seed enumeration just enqueued (programmatic dependent launch)
     const bool chained = !ext && (in->flags & JSSP_FLAG_ENUMERATE) && !h->tune.no_pdl;
     CK(launch_chained(evaluate_small_kernel, dim3(blocks), SMALL_WARPS * 32, small_bytes, st, chained, p));
-  }
-  else if (in->flags & JSSP_FLAG_FORCE_LANES) {
-    // one warp per seed: blocks of as many warps as fit twice on an SM next to the tables, two blocks per SM, contiguous seed ranges
-    const int rows_max = (h->P + c.check_res - 1) / c.check_res;
-    const size_t lbase = (L.total + 15) & ~(size_t)15;
-    cudaFuncAttributes fa{};
-    cudaFuncGetAttributes(&fa, evaluate_lanes_kernel<2>);
-    const size_t two = (size_t)228 * 1024 / 2 - fa.sharedSizeBytes - 1024;
-    int warps = LANES_THREADS / 32;
-    while (warps > 2 && lbase + lanes_scratch_bytes(h->P, rows_max, warps * 32) > two) --warps;
-    const size_t lanes_total = lbase + lanes_scratch_bytes(h->P, rows_max, warps * 32);
-    if (lanes_total > (size_t)h->max_smem_optin) return JSSP_ERR_CAPACITY;
-    const int lblocks = (int)std::max<long long>(1, std::min<long long>((seeds_max + warps - 1) / warps, (long long)h->sm_count * 2));
-    if (lblocks > h->max_blocks) return JSSP_ERR_CAPACITY;
-    if (mode == 2) evaluate_lanes_kernel<2><<<lblocks, warps * 32, lanes_total, st>>>(p);
-    else if (mode == 1) evaluate_lanes_kernel<1><<<lblocks, warps * 32, lanes_total, st>>>(p);
-    else evaluate_lanes_kernel<0><<<lblocks, warps * 32, lanes_total, st>>>(p);
   }
   else if (tiled && mode == 2) evaluate_tiled_kernel<2><<<blocks, tiled_threads, tiled_total, st>>>(p);
   else if (tiled && mode == 1) evaluate_tiled_kernel<1><<<blocks, tiled_threads, tiled_total, st>>>(p);
@@ -1370,8 +1350,6 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   CKC(allow_max_dynamic_smem(replay_persistent_kernel<512>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(replay_persistent_kernel<1024>, optin, &b->max_smem_optin));
   CKC(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device));
-  CKC(allow_max_dynamic_smem(evaluate_lanes_batch_kernel<0>, optin, &b->max_smem_optin));
-  CKC(allow_max_dynamic_smem(evaluate_lanes_batch_kernel<1>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_tiled_batch_kernel<0>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_tiled_batch_kernel<1>, optin, &b->max_smem_optin));
   CKC(cudaDeviceSynchronize());
@@ -1692,7 +1670,7 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   const SmemLayout Ls = eval_smem_layout(0, b->max_OMpad, 0, b->max_K, b->max_kpad, b->P, b->W);
   const size_t small_bytes = Ls.total + small_scratch_bytes(b->P);
   bool small = (long long)n_scenarios * b->cfg.max_seeds * b->W <= 65536 && small_bytes <= (size_t)b->max_smem_optin;
-  if (flags & (JSSP_FLAG_FORCE_THREAD | JSSP_FLAG_FORCE_GROUP | JSSP_FLAG_FORCE_TILED | JSSP_FLAG_FORCE_LANES)) small = false;
+  if (flags & (JSSP_FLAG_FORCE_THREAD | JSSP_FLAG_FORCE_GROUP | JSSP_FLAG_FORCE_TILED)) small = false;
   if ((flags & JSSP_FLAG_FORCE_WARP) && small_bytes <= (size_t)b->max_smem_optin) small = true;
   // thread per candidate for the default 3 lateral targets (a scenario's ~150 seeds fill the group kernel's 40-seed blocks and
   // 30-of-32 lanes poorly: measured 49.0 vs 53.9 ms on the 800-scenario sweep), the group kernel from 4 targets on
@@ -1708,11 +1686,10 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   if (mode == 1 && L.total > (size_t)b->max_smem_optin) { mode = 0; L = eval_smem_layout(0, b->max_OMpad, 0, b->max_K, b->max_kpad, b->P, b->W); }
   if (!small && L.total > (size_t)b->max_smem_optin) return JSSP_ERR_CAPACITY;
   const size_t tiled_total = ((L.total + 15) & ~(size_t)15) + tile_scratch_bytes(b->W, bthreads);     // default tile length (slot records carry tile_rounds = 0)
-  const bool tiled = !small && (flags & JSSP_FLAG_FORCE_TILED) && tiled_total <= (size_t)b->max_smem_optin;
-  // lanes kernel (one warp per seed): a scenario's seeds spread over lanes_blocks blocks of 8 warps
-  const size_t lanes_total = ((L.total + 15) & ~(size_t)15) + lanes_scratch_bytes(b->P, max_rows, LANES_BATCH_THREADS);
-  const bool lanes = !small && (flags & JSSP_FLAG_FORCE_LANES) && lanes_total <= (size_t)b->max_smem_optin;
-  const int lanes_blocks = b->tune.seed_cluster > 0 ? b->tune.seed_cluster : (n_scenarios >= 400 ? 2 : 4);
+  // the tiled walk when a rank holds few scenarios (latency of a plan cycle matters: measured 11.8 vs 13.1 ms for 100 scenarios x <= 100
+  // cycles), the thread-per-candidate walk for large batches (throughput: 42.2 vs 48.4 ms for 800 scenarios)
+  const bool tiled_auto = !(flags & (JSSP_FLAG_FORCE_THREAD | JSSP_FLAG_FORCE_GROUP | JSSP_FLAG_FORCE_WARP)) && n_scenarios <= 256;
+  const bool tiled = !small && ((flags & JSSP_FLAG_FORCE_TILED) || tiled_auto) && tiled_total <= (size_t)b->max_smem_optin;
   // few scenarios: clusters of up to 8 CTAs x 1024 threads answer with the lowest latency; many: one 512-thread CTA each
   int seed_cluster = 1;
   while (seed_cluster < SEED_MAX_CLUSTER && n_scenarios * seed_cluster * 2 <= 148) seed_cluster *= 2;
@@ -1723,8 +1700,6 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
     CKB(launch_seed_enum<true>(b->grids, SeedState{0, 0, 0}, b->d_slots, b->seed_work, n_scenarios, seed_cluster, seed_threads, b->seed_smem, st, pdl));
     const EvalParams* slots = b->d_slots;
     if (small) CKB(launch_chained(evaluate_small_batch_kernel, dim3(n_scenarios, std::min(b->blocks_warp, 128)), SMALL_WARPS * 32, small_bytes, st, pdl, slots));
-    else if (lanes && mode == 1) CKB(launch_chained(evaluate_lanes_batch_kernel<1>, dim3(n_scenarios, lanes_blocks), LANES_BATCH_THREADS, lanes_total, st, pdl, slots));
-    else if (lanes) CKB(launch_chained(evaluate_lanes_batch_kernel<0>, dim3(n_scenarios, lanes_blocks), LANES_BATCH_THREADS, lanes_total, st, pdl, slots));
     else if (tiled && mode == 1) CKB(launch_chained(evaluate_tiled_batch_kernel<1>, dim3(n_scenarios, blocks_group), bthreads, tiled_total, st, pdl, slots));
     else if (tiled) CKB(launch_chained(evaluate_tiled_batch_kernel<0>, dim3(n_scenarios, blocks_group), bthreads, tiled_total, st, pdl, slots));
     else if (group && mode == 1) CKB(launch_chained(evaluate_group_batch_kernel<1>, dim3(n_scenarios, blocks_group), bthreads, L.total, st, pdl, slots));

@@ -100,7 +100,6 @@ typedef struct jssp_cycle_in {
 #define JSSP_FLAG_FORCE_TILED 128 /* use the tiled two-phase kernel (default for larger cycles): per tile of the horizon the seed-only
                                     work runs in parallel into shared memory, then one lane per candidate walks the tile; same masks
                                     and selection, costs equal to rounding */
-#define JSSP_FLAG_FORCE_LANES 1024 /* use the lanes kernel: one warp per seed, lanes over the samples (no serial walk); same results */
 #define JSSP_FLAG_LOCKSTEP 256    /* jssp_batch_run only: the lock-step pipeline (two launches per plan cycle for the whole batch; the default) */
 #define JSSP_FLAG_PERSISTENT 512  /* jssp_batch_run only: the persistent replay kernel - one CTA per scenario loops seed enumeration -> evaluation ->
                                     selection -> export -> hand-off over the scenario's own plan cycles, ONE launch per call, no lock-step between

@@ -6,7 +6,7 @@ import bench
 import dlii_jssp_b200 as J
 
 name = sys.argv[1] if len(sys.argv) > 1 else "C3"
-kerns = sys.argv[2:] or ["tiled", "lanes", "group"]
+kerns = sys.argv[2:] or ["tiled", "group", "thread"]
 cyc = bench.workload(name)
 eng = bench.make_engine(J, cyc, len(cyc.seeds), 0)
 seeds = torch.from_numpy(cyc.seeds).cuda()
