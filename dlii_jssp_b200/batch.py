@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import JsspError, JsspCycleRecord, JsspFopIn, JsspScenarioIn, JsspScenarioResult, FLAG_FORCE_THREAD, FLAG_FORCE_WARP, FLAG_FORCE_GROUP, FLAG_FORCE_TILED, FLAG_LOCKSTEP, FLAG_PERSISTENT
+from ._lib import JsspError, JsspCycleRecord, JsspFopIn, JsspScenarioIn, JsspScenarioResult, FLAG_FORCE_THREAD, FLAG_FORCE_WARP, FLAG_FORCE_GROUP, FLAG_FORCE_TILED, FLAG_LOCKSTEP, FLAG_PERSISTENT, FLAG_CHUNKED
 from .engine import JsspConfig
 from .frenet import FrenetState, State
 from .geometry import CubicSpline2D
@@ -271,7 +271,7 @@ class BatchReplay:
         (one CTA per scenario loops over its own cycles in ONE launch).  Same results.  Asynchronous."""
         if n_cycles is None:
             n_cycles = max(min(p.n_cycles, self.C) for p in self._packed)
-        flags = {None: 0, "warp": FLAG_FORCE_WARP, "thread": FLAG_FORCE_THREAD, "group": FLAG_FORCE_GROUP, "tiled": FLAG_FORCE_TILED, "lockstep": FLAG_LOCKSTEP, "persistent": FLAG_PERSISTENT}[kernel]
+        flags = {None: 0, "warp": FLAG_FORCE_WARP, "thread": FLAG_FORCE_THREAD, "group": FLAG_FORCE_GROUP, "tiled": FLAG_FORCE_TILED, "lockstep": FLAG_LOCKSTEP, "persistent": FLAG_PERSISTENT, "chunked": FLAG_CHUNKED}[kernel]
         self._check(self.lib.jssp_batch_run(self._h, self._n, int(n_cycles), flags, self.stream), "jssp_batch_run")
         return n_cycles
 

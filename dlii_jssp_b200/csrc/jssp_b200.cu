@@ -22,6 +22,7 @@ struct Tuning {
   bool full_walk = false;     // batched replay: walk every candidate to the end instead of stopping at its first veto
   int seed_cluster = 0;       // CTAs per seed-enumeration cluster (0 = by batch size)
   int seed_threads = 0;       // threads per seed-enumeration CTA (0 = by batch size)
+  int chunks = 0;             // lane groups per seed of the chunked tiled kernel (0 = 2)
   int lockstep = 0;           // batched replay: 1 = force the lock-step kernels instead of the persistent scenario kernel
   static Tuning from_env() {
     Tuning t;
@@ -29,6 +30,7 @@ struct Tuning {
     t.full_walk = getenv("JSSP_B200_TUNE_FULL_WALK") != nullptr;
     if (const char* e = getenv("JSSP_B200_TUNE_SEED_CLUSTER")) t.seed_cluster = atoi(e);
     if (const char* e = getenv("JSSP_B200_TUNE_SEED_THREADS")) t.seed_threads = atoi(e);
+    if (const char* e = getenv("JSSP_B200_TUNE_CHUNKS")) t.chunks = atoi(e);
     if (const char* e = getenv("JSSP_B200_TUNE_LOCKSTEP")) t.lockstep = atoi(e);
     return t;
   }
@@ -1352,6 +1354,8 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   CKC(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device));
   CKC(allow_max_dynamic_smem(evaluate_tiled_batch_kernel<0>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_tiled_batch_kernel<1>, optin, &b->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_tiled_chunked_batch_kernel<0>, optin, &b->max_smem_optin));
+  CKC(allow_max_dynamic_smem(evaluate_tiled_chunked_batch_kernel<1>, optin, &b->max_smem_optin));
   CKC(cudaDeviceSynchronize());
 #undef CKC
   *out = b;
@@ -1690,6 +1694,15 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   // cycles), the thread-per-candidate walk for large batches (throughput: 42.2 vs 48.4 ms for 800 scenarios)
   const bool tiled_auto = !(flags & (JSSP_FLAG_FORCE_THREAD | JSSP_FLAG_FORCE_GROUP | JSSP_FLAG_FORCE_WARP)) && n_scenarios <= 256;
   const bool tiled = !small && ((flags & JSSP_FLAG_FORCE_TILED) || tiled_auto) && tiled_total <= (size_t)b->max_smem_optin;
+  // the chunked tiled walk: two lane groups per seed split the horizon (half the serial chain, twice the lanes) - while the lanes of the
+  // whole batch still fit the SMs in one wave
+  int chunks = b->tune.chunks > 0 ? b->tune.chunks : 2;
+  chunks = std::max(1, std::min(chunks, 32 / b->W));
+  const size_t chunked_total = ((L.total + 15) & ~(size_t)15) + tile_scratch_bytes(b->W, bthreads, 0, chunks, b->P);
+  const bool chunk_fits = chunks > 1 && mode != 2 && chunked_total <= (size_t)b->max_smem_optin;
+  const int spb_chunked = (bthreads / 32) * ((32 / b->W) / chunks);
+  const int blocks_chunked = (b->cfg.max_seeds + spb_chunked - 1) / spb_chunked;
+  const bool chunked = !small && chunk_fits && blocks_chunked <= b->max_blocks && (flags & JSSP_FLAG_CHUNKED);
   // few scenarios: clusters of up to 8 CTAs x 1024 threads answer with the lowest latency; many: one 512-thread CTA each
   int seed_cluster = 1;
   while (seed_cluster < SEED_MAX_CLUSTER && n_scenarios * seed_cluster * 2 <= 148) seed_cluster *= 2;
@@ -1700,6 +1713,8 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
     CKB(launch_seed_enum<true>(b->grids, SeedState{0, 0, 0}, b->d_slots, b->seed_work, n_scenarios, seed_cluster, seed_threads, b->seed_smem, st, pdl));
     const EvalParams* slots = b->d_slots;
     if (small) CKB(launch_chained(evaluate_small_batch_kernel, dim3(n_scenarios, std::min(b->blocks_warp, 128)), SMALL_WARPS * 32, small_bytes, st, pdl, slots));
+    else if (chunked && mode == 1) CKB(launch_chained(evaluate_tiled_chunked_batch_kernel<1>, dim3(n_scenarios, blocks_chunked), bthreads, chunked_total, st, pdl, slots, chunks));
+    else if (chunked) CKB(launch_chained(evaluate_tiled_chunked_batch_kernel<0>, dim3(n_scenarios, blocks_chunked), bthreads, chunked_total, st, pdl, slots, chunks));
     else if (tiled && mode == 1) CKB(launch_chained(evaluate_tiled_batch_kernel<1>, dim3(n_scenarios, blocks_group), bthreads, tiled_total, st, pdl, slots));
     else if (tiled) CKB(launch_chained(evaluate_tiled_batch_kernel<0>, dim3(n_scenarios, blocks_group), bthreads, tiled_total, st, pdl, slots));
     else if (group && mode == 1) CKB(launch_chained(evaluate_group_batch_kernel<1>, dim3(n_scenarios, blocks_group), bthreads, L.total, st, pdl, slots));

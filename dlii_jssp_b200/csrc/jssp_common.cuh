@@ -19,12 +19,17 @@ namespace cg = cooperative_groups;
 #ifndef JSSP_BATCH_MIN_BLOCKS
 #define JSSP_BATCH_MIN_BLOCKS 4
 #endif
+#ifndef JSSP_CHUNK_MIN_BLOCKS
+#define JSSP_CHUNK_MIN_BLOCKS 5
+#endif
 constexpr int EVAL_THREADS = JSSP_EVAL_THREADS;
 constexpr int EVAL_MIN_BLOCKS = JSSP_EVAL_MIN_BLOCKS;
 // block size / residency of the thread and group evaluation kernels in the batched replay (a scenario has a few hundred
 // candidates: small blocks leave fewer idle lanes in its last block and spread its work over more SMs)
 constexpr int BATCH_EVAL_THREADS = JSSP_BATCH_THREADS;
 constexpr int BATCH_MIN_BLOCKS = JSSP_BATCH_MIN_BLOCKS;
+// the chunked tiled kernel doubles (or triples) the lanes of a plan cycle: 96 registers keep 5 of its blocks on an SM
+constexpr int CHUNK_MIN_BLOCKS = JSSP_CHUNK_MIN_BLOCKS;
 constexpr float SAT_EPS = 2e-3f;        // fp32 guard band [m]; inside it the pair is re-decided in float64
 constexpr float FAR_AWAY = 1e30f;       // x of an absent obstacle state: squared distance overflows to +inf -> culled
 
@@ -33,7 +38,7 @@ __device__ __forceinline__ void phase_stamp(unsigned long long* ts, int slot) {
   if (ts && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    ts[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+    ts[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + slot] = t;
   }
 }
 #define PHASE(p, k) phase_stamp((p).phase_ts, k)

@@ -37,6 +37,7 @@ struct EvalParams {
   const float* probf;             // [OM]
   int list_cap;                   // entries of the per-block compacted obstacle lists (mode 2)
   int tile_rounds;                // tiled kernel: phase-1 rounds per tile (0 = default), chosen by the host for its shared-memory budget
+  int tile_chunks;                // chunked tiled kernel: lane groups per seed that split the horizon (0 / 1 = none)
   int select_only;                // no per-candidate outputs are wanted: a candidate's walk may stop at its first veto (the
                                   // reference filters the same way: check_constraints_curvature -> check_collisions -> cost on
                                   // the survivors only, has_collision returns at the first hit; jerk_space_sampling_planner.py:311-319)

@@ -23,18 +23,24 @@ namespace jssp {
 constexpr int TILE_PROF = 32;      // doubles per seed in the segment table: 5 x (s, v, a, j) | t1..t4 | 4 bounds | s(0), s(P-1) | pad
 
 struct TileGeom {
-  int gpw;          // seeds (groups) per warp
+  int gpw;          // lane groups per warp (W lanes each)
+  int H;            // chunks of the horizon per candidate (1: a group walks the whole horizon; see TileChunk)
+  int spw;          // seeds per warp = gpw / H
   int R;            // phase-1 rounds per tile
   int TL;           // samples per tile = R * W
   int grp_stride;   // doubles between the tiles of two groups (TL * 4 + 2: neighbouring groups land 16 B apart in the banks)
   int off_terms;    // doubles from the warp's scratch to its cost-term table [gpw][TL][3]
   int off_prof;     // ... to its segment tables [gpw][TILE_PROF]
+  int own_max;      // chunked: most samples whose cost terms one chunk owns
+  int off_lterms;   // chunked: ... to the cost terms of the chunks after the first [spw * (H - 1)][own_max][3]
   int warp_doubles; // doubles of scratch per warp
 };
 __host__ __device__ inline int tile_rounds_wanted(int W) { return (16 + W - 1) / W; }     // ~16 samples per tile
-__host__ __device__ inline TileGeom tile_geom(int W, int rounds = 0) {
+__host__ __device__ inline TileGeom tile_geom(int W, int rounds = 0, int H = 1, int P = 0) {
   TileGeom g;
   g.gpw = 32 / W;
+  g.H = H < 1 ? 1 : (H > g.gpw ? g.gpw : H);
+  g.spw = g.gpw / g.H;
   const int r_want = tile_rounds_wanted(W), r_cap = 80 / (g.gpw * W);   // default: at most ~80 entries (~6 KB) per warp
   g.R = r_want < r_cap ? r_want : r_cap;
   if (rounds > 0) g.R = rounds;                                        // caller's choice (shared-memory budget of the launch)
@@ -44,10 +50,39 @@ __host__ __device__ inline TileGeom tile_geom(int W, int rounds = 0) {
   g.off_terms = g.gpw * g.grp_stride;
   g.off_prof = g.off_terms + g.gpw * g.TL * 3;
   g.off_prof = (g.off_prof + 1) & ~1;
-  g.warp_doubles = g.off_prof + g.gpw * TILE_PROF;
+  g.off_lterms = g.off_prof + g.gpw * TILE_PROF;
+  g.own_max = g.H > 1 ? (P - 1 + g.H - 1) / g.H + 1 : 0;
+  g.warp_doubles = g.off_lterms + g.spw * (g.H - 1) * g.own_max * 3;
+  g.warp_doubles = (g.warp_doubles + 1) & ~1;
   return g;
 }
-__host__ __device__ inline size_t tile_scratch_bytes(int W, int threads, int rounds = 0) { return (size_t)(threads / 32) * tile_geom(W, rounds).warp_doubles * 8; }
+__host__ __device__ inline size_t tile_scratch_bytes(int W, int threads, int rounds = 0, int H = 1, int P = 0) {
+  return (size_t)(threads / 32) * tile_geom(W, rounds, H, P).warp_doubles * 8;
+}
+
+// CHUNKED walk (batched replay with few scenarios per GPU: the plan cycle is a latency chain, the SMs are half empty): the H lane
+// groups of a seed split the horizon.  Chunk h tests the segments [a_h, a_{h+1}) with a_h = h * (P - 1) / H, i.e. it walks the
+// points [a_h - 1, a_{h+1}]: the segment before the chunk only PRIMES the curvature test (it is tested by the chunk before).
+// The cost terms of the samples [a_h, a_{h+1}) (+ the last sample for the last chunk) belong to chunk h.  After the walk the
+// chunks are combined IN TIME ORDER, with the serial walk's semantics: masks are OR-ed up to the chunk in which the path left
+// the reference line, risk stops at the first hard collision, and the cost sums continue the previous chunk's sums term by
+// term - so masks, sums and therefore the selection are those of the serial walk (the risk partial sums of the chunks are
+// added chunk by chunk: exact for probabilities that are float32 values of comparable magnitude, as the tables hold them).
+struct TileChunk {
+  int lo, hi;             // first / last point walked
+  int own_lo, own_hi;     // cost terms of the samples [own_lo, own_hi)
+  bool first, last;
+  double* lterms;         // chunks after the first: their cost terms [own_hi - own_lo][3]
+};
+__device__ __forceinline__ TileChunk tile_chunk(int h, int H, int P, double* lterms) {
+  TileChunk c;
+  const int a = h * (P - 1) / H, b = (h + 1) * (P - 1) / H;
+  c.first = h == 0; c.last = h == H - 1;
+  c.lo = a > 0 ? a - 1 : 0; c.hi = b;
+  c.own_lo = a; c.own_hi = c.last ? P : b;
+  c.lterms = lterms;
+  return c;
+}
 
 // segment table of one seed: the start state and jerk of each of the five segments (the same expressions as lon_profile_init:
 // bit-identical to the reference's segment end states), the durations and the asymmetric-epsilon boundaries of
@@ -236,6 +271,15 @@ struct TileSink {
     collide(i, x, y, dx, dy, qf);
     pdx = dx; pdy = dy; pqf = qf; pdsf = dsf;
   }
+  // chunked walk: the chunk's first tested segment is `a`; (dx, dy) = segment a - 1, tested by the chunk before
+  __device__ __forceinline__ void start_at(int a) { next_check = (a + p.check_res - 1) / p.check_res * p.check_res; row = next_check / p.check_res; }
+  __device__ __forceinline__ void prime(double dx, double dy) {
+    const float dxf = (float)dx, dyf = (float)dy;
+    const float qf = fmaf(dxf, dxf, dyf * dyf);
+    float dsf = 0.f;
+    if (qf > 1e-16f && qf < 1e30f) { float inv = rsqrtf(qf); inv = inv * fmaf(-0.5f * qf, inv * inv, 1.5f); dsf = qf * inv; }
+    pdx = dx; pdy = dy; pqf = qf; pdsf = dsf;
+  }
   __device__ __forceinline__ void finish(int n_pts, double x, double y) {
     if (n_pts >= 2) collide(n_pts - 1, x, y, pdx, pdy, pqf);                // last point reuses the previous heading (:158-160)
     else if (n_pts == 1 && p.n_dict > 0 && p.tcap >= 1) collided = true;    // bare except -> collision (:250-254)
@@ -248,16 +292,24 @@ __device__ __forceinline__ double candidate_cost(const EvalParams& p, const Tile
 // The tiled walk of the candidate in lane (g, j): g = group (seed) within the warp, j = lateral target.  `gbase` = this group's
 // tile, `prof` = this group's segment table (already stored), both in the warp's scratch.  Inactive lanes (no seed) only keep
 // the warp-level barriers company.  On return `sink` holds the masks, the risk term and the longitudinal cost sums.
+// kChunked: the group walks the chunk `ck` of the horizon only and the chunks of a candidate are combined at the end (see
+// TileChunk); the combined result is valid in the lanes of the candidate's FIRST chunk.
+template <bool kChunked>
 __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTables& tb, const TileGeom& tg, double* gbase, double* gterms,
-                                           double* prof, bool active, int j, int W, TileSink& sink) {
+                                           double* prof, bool active, int j, int W, TileSink& sink, const TileChunk& ck) {
   const int P = p.P, TL = tg.TL;
   const double* lat = tb.lat + (size_t)j * P * 4;
+  const int lo = kChunked ? ck.lo : 0, hi = kChunked ? ck.hi : P - 1;
+  // every lane of the warp runs the same number of tiles (the chunks differ by a point or two): the barriers stay warp-wide
+  const int n_tiles = ((kChunked ? tg.own_max + 1 : P) + TL - 1) / TL;
   int k = 0, n_pts = P;
+  bool ended = false;                            // the path left the reference line at point n_pts
   double sa = 0, sj = 0, sv = 0;                 // lane 0 of the group: the longitudinal cost sums, added strictly in time order
   double xp = 0, yp = 0;
   bool walking = active;
-  for (int base = 0; base < P; base += TL) {
-    const int len = min(TL, P - base);
+  for (int t = 0; t < n_tiles; ++t) {
+    const int base = lo + t * TL;
+    const int len = min(TL, hi + 1 - base);      // <= 0: the chunk is done
     // phase 1: seed-only quantities of the samples this lane owns in the tile
     if (active) {
       for (int il = j; il < len; il += W) {
@@ -267,8 +319,12 @@ __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTable
         const double ea = fmax(fabs(sdd) - p.thr_lon_a, 0.0);
         const double ej = fmax(fabs(sddd) - p.thr_lon_j, 0.0);
         const double ev = (p.vmax - sd) * p.inv_vmax;
-        double* tm = gterms + il * 3;
-        tm[0] = ea * ea; tm[1] = ej * ej; tm[2] = ev * ev;
+        if (kChunked && !ck.first) {               // later chunks keep their terms until the earlier sums are final
+          if (i >= ck.own_lo && i < ck.own_hi) { double* tm = ck.lterms + (i - ck.own_lo) * 3; tm[0] = ea * ea; tm[1] = ej * ej; tm[2] = ev * ev; }
+        } else {
+          double* tm = gterms + il * 3;
+          tm[0] = ea * ea; tm[1] = ej * ej; tm[2] = ev * ev;
+        }
         if (i == 0) prof[28] = s;
         if (i == P - 1) prof[29] = s;
         double2* e = reinterpret_cast<double2*>(gbase + il * 4);
@@ -282,53 +338,107 @@ __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTable
       }
     }
     __syncwarp();
+    if (t == 1) PHASE(p, 14);
     // the cost sums are sequential float64 sums over the samples (the oracle's order: costs bit-identical to the other kernels):
     // one lane per seed adds the tile's terms - three short independent chains
-    if (active && j == 0) {
-      for (int il = 0; il < len; ++il) { sa = sa + gterms[il * 3]; sj = sj + gterms[il * 3 + 1]; sv = sv + gterms[il * 3 + 2]; }
+    if (active && j == 0 && (!kChunked || ck.first)) {
+      const int own = kChunked ? min(len, ck.own_hi - base) : len;
+      for (int il = 0; il < own; ++il) { sa = sa + gterms[il * 3]; sj = sj + gterms[il * 3 + 1]; sv = sv + gterms[il * 3 + 2]; }
     }
+    if (t == 1) PHASE(p, 15);
     // phase 2: this lane's candidate
     if (walking) {
       for (int il = 0; il < len; ++il) {
         const int i = base + il;
         const double2* e = reinterpret_cast<const double2*>(gbase + il * 4);
         const double2 pxy = e[0];
-        if (!(pxy.x == pxy.x)) { n_pts = i; walking = false; break; }
+        if (!(pxy.x == pxy.x)) { n_pts = i; ended = true; walking = false; break; }
         const double2 uv = e[1];
         const double d = lat[i * 4];
         const double x = fma(-d, uv.x, pxy.x), y = fma(d, uv.y, pxy.y);
-        if (i >= 1) {
-          sink.segment(i - 1, xp, yp, x - xp, y - yp);
-          if (sink.vetoed()) { walking = false; break; }     // select-only evaluation: this candidate can no longer be selected
+        if (i > lo) {
+          if (kChunked && !ck.first && i == lo + 1) {
+            sink.prime(x - xp, y - yp);            // the segment before the chunk: tested by the chunk before
+          } else {
+            sink.segment(i - 1, xp, yp, x - xp, y - yp);
+            if (sink.vetoed()) { walking = false; break; }     // select-only evaluation: this candidate can no longer be selected
+          }
         }
         xp = x; yp = y;
       }
     }
     __syncwarp();                                  // the tile is rewritten by the next phase 1
+    if (t == 0) PHASE(p, 8);                       // profiling builds: progress of the block's first warp through the tiles
+    if (t == 1) PHASE(p, 9);
+    if (t == n_tiles / 2) PHASE(p, 10);
+    if (t == n_tiles - 1) PHASE(p, 11);
   }
-  if (active && !sink.vetoed()) sink.finish(n_pts, xp, yp);
-  if (active && j == 0) { gbase[0] = sa; gbase[1] = sj; gbase[2] = sv; }
-  __syncwarp();
+  if (!kChunked) {
+    if (active && !sink.vetoed()) sink.finish(n_pts, xp, yp);
+    if (active && j == 0) { gbase[0] = sa; gbase[1] = sj; gbase[2] = sv; }
+    __syncwarp();
+    if (active) {
+      sink.sum_a = gbase[0]; sink.sum_j = gbase[1]; sink.sum_v = gbase[2];
+      sink.s_first = prof[28]; sink.s_last = prof[29];
+    }
+    __syncwarp();
+    return;
+  }
+  // ---- chunked: the last point's collision row belongs to the chunk that saw the path end (an end within the chunk's first two
+  // points was also seen - and is owned - by the chunk before) or, on a complete path, to the last chunk
+  const bool owns_end = ended ? (ck.first || n_pts >= lo + 2) : ck.last;
+  if (active && owns_end && !sink.vetoed()) sink.finish(n_pts, xp, yp);
+  const unsigned int full = 0xffffffffu;
+  const int H = tg.H, lane = threadIdx.x & 31;
+  const int q = lane / W, g = q / H, h = q - g * H;
+  const int fl = (sink.curv_fail ? 1 : 0) | (sink.collided ? 2 : 0) | (ended ? 4 : 0);
+  const double rk = sink.risk;
+  bool curv = false, coll = false, over = false;
+  double risk = 0.0;
+  for (int h2 = 0; h2 < H; ++h2) {                 // in time order, with the serial walk's semantics
+    const int src = ((g * H + h2) * W + j) & 31;
+    const int f2 = __shfl_sync(full, fl, src);
+    const double r2 = __shfl_sync(full, rk, src);
+    if (!over) {
+      curv = curv || (f2 & 1);
+      if (!coll) { risk = risk + r2; coll = (f2 & 2) != 0; }   // no risk is collected after a hard collision
+      over = (f2 & 4) != 0;                         // the path ended in this chunk: the later chunks walked points that do not exist
+    }
+  }
+  for (int h2 = 1; h2 < H; ++h2) {                 // cost sums: chunk h2 continues the sums of chunk h2 - 1 term by term
+    const int src = ((g * H + h2 - 1) * W) & 31;
+    const double a2 = __shfl_sync(full, sa, src), j2 = __shfl_sync(full, sj, src), v2 = __shfl_sync(full, sv, src);
+    if (active && j == 0 && h == h2) {
+      sa = a2; sj = j2; sv = v2;
+      const int own = ck.own_hi - ck.own_lo;
+      for (int m = 0; m < own; ++m) { sa = sa + ck.lterms[m * 3]; sj = sj + ck.lterms[m * 3 + 1]; sv = sv + ck.lterms[m * 3 + 2]; }
+    }
+  }
+  const int srcl = ((g * H + H - 1) * W) & 31;
+  const double ta = __shfl_sync(full, sa, srcl), tj = __shfl_sync(full, sj, srcl), tv = __shfl_sync(full, sv, srcl);
   if (active) {
-    sink.sum_a = gbase[0]; sink.sum_j = gbase[1]; sink.sum_v = gbase[2];
-    sink.s_first = prof[28]; sink.s_last = prof[29];
+    sink.curv_fail = curv; sink.collided = coll; sink.risk = risk;
+    sink.sum_a = ta; sink.sum_j = tj; sink.sum_v = tv;
+    sink.s_first = (prof - h * TILE_PROF)[28]; sink.s_last = (prof + (H - 1 - h) * TILE_PROF)[29];
   }
   __syncwarp();
 }
 
-template <int kMode>
+template <int kMode, bool kChunked = false>
 __device__ __forceinline__ void evaluate_tiled_body(const EvalParams& p, unsigned char* smem, double* red_cost, int* red_idx,
                                                     bool* is_last, int* sm_npts) {
+  static_assert(!(kChunked && kMode == 2), "the chunked walk has no block-level lists");
   const int Ns = resolve_n_seeds(p);
   const int W = p.W;
   const int N = Ns * W;
-  const TileGeom tg = tile_geom(W, p.tile_rounds);
-  const int gpw = tg.gpw;
+  const TileGeom tg = tile_geom(W, p.tile_rounds, kChunked ? p.tile_chunks : 1, p.P);
+  const int gpw = tg.gpw, H = tg.H, spw = tg.spw;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int g = lane / W, j = lane - g * W;
-  const int spb = (blockDim.x >> 5) * gpw;     // seeds per block
-  const int k = blk_index(p) * spb + wid * gpw + g;
-  const bool active = g < gpw && k < Ns;
+  const int q = lane / W, j = lane - q * W;    // lane group and lateral target
+  const int g = q / H, h = q - g * H;          // seed within the warp and chunk of the horizon (H = 1: g = q, h = 0)
+  const int spb = (blockDim.x >> 5) * spw;     // seeds per block
+  const int k = blk_index(p) * spb + wid * spw + g;
+  const bool active = q < gpw && g < spw && k < Ns;
   double my_cost = INFINITY;
   int my_idx = -1;
   BlockTables tb;
@@ -340,17 +450,23 @@ __device__ __forceinline__ void evaluate_tiled_body(const EvalParams& p, unsigne
     PHASE(p, 1);
     const SmemLayout L = eval_smem_layout(p.win_rows, p.OMpad, kMode, p.K, p.kpad, p.P, p.W, p.list_cap);
     double* wscr = reinterpret_cast<double*>(smem + ((L.total + 15) & ~(size_t)15)) + (size_t)wid * tg.warp_doubles;
-    const int gg = g < gpw ? g : 0;
-    double* gbase = wscr + (size_t)gg * tg.grp_stride;
-    double* gterms = wscr + tg.off_terms + (size_t)gg * tg.TL * 3;
-    double* prof = wscr + tg.off_prof + (size_t)gg * TILE_PROF;
+    const int gq = active ? q : 0;
+    double* gbase = wscr + (size_t)gq * tg.grp_stride;
+    double* gterms = wscr + tg.off_terms + (size_t)gq * tg.TL * 3;
+    double* prof = wscr + tg.off_prof + (size_t)gq * TILE_PROF;
     if (active && j == 0) tile_profile_store(prof, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
     __syncwarp();
     if (kMode == 2) { TileSAt s_at{prof}; build_lists(p, smem, tb, s_at, active, j, W); }
     PHASE(p, 2);
     TileSink sink(p, tb);
-    walk_tiles(p, tb, tg, gbase, gterms, prof, active, j, W, sink);
-    if (active) {
+    TileChunk ck{};
+    if (kChunked) {
+      ck = tile_chunk(active ? h : 0, H, p.P, (active && h > 0) ? wscr + tg.off_lterms + (size_t)(g * (H - 1) + h - 1) * tg.own_max * 3 : nullptr);
+      sink.start_at(ck.own_lo);
+    }
+    walk_tiles<kChunked>(p, tb, tg, gbase, gterms, prof, active, j, W, sink, ck);
+    PHASE(p, 12);
+    if (active && h == 0) {
       const int n = j * Ns + k;                // candidate index: width-major (jerk_space_sampling_planner.py:106,124-125)
       const double cost = candidate_cost(p, sink, latcost + j * 4);
       if (p.feasible) p.feasible[n] = sink.curv_fail ? 0 : 1;
@@ -359,6 +475,7 @@ __device__ __forceinline__ void evaluate_tiled_body(const EvalParams& p, unsigne
       if (!sink.curv_fail && !sink.collided && isfinite(cost)) { my_cost = cost; my_idx = n; }
     }
   }
+  PHASE(p, 13);
   __syncthreads();
   PHASE(p, 3);
   select_and_export<kMode>(p, smem, tb, latcost, staged, my_cost, my_idx, N, Ns, red_cost, red_idx, is_last, sm_npts);
@@ -387,6 +504,23 @@ __global__ void __launch_bounds__(BATCH_EVAL_THREADS, BATCH_MIN_BLOCKS) evaluate
   if (!slot_live(slots, blockIdx.x)) return;
   load_slot(&sp, slots + blockIdx.x);
   evaluate_tiled_body<kMode>(sp, smem, red_cost, red_idx, &is_last, &sm_npts);
+}
+
+// The chunked form for few scenarios per GPU (latency of the plan cycle): `chunks` lane groups per seed split the horizon.
+template <int kMode>
+__global__ void __launch_bounds__(BATCH_EVAL_THREADS, CHUNK_MIN_BLOCKS) evaluate_tiled_chunked_batch_kernel(const EvalParams* __restrict__ slots, int chunks) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(16) EvalParams sp;
+  __shared__ double red_cost[EVAL_THREADS / 32];
+  __shared__ int red_idx[EVAL_THREADS / 32];
+  __shared__ bool is_last;
+  __shared__ int sm_npts;
+  pdl_launch_dependents(); pdl_wait();
+  if (!slot_live(slots, blockIdx.x)) return;
+  load_slot(&sp, slots + blockIdx.x);
+  if (threadIdx.x == 0) sp.tile_chunks = chunks;
+  __syncthreads();
+  evaluate_tiled_body<kMode, true>(sp, smem, red_cost, red_idx, &is_last, &sm_npts);
 }
 
 }  // namespace jssp

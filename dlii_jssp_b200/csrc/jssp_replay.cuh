@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
       if (active && j == 0) tile_profile_store(prof, seeds + (size_t)k * 10, sp.s0, sp.v0, sp.a0);
       __syncwarp();
       TileSink sink(sp, tb);
-      walk_tiles(sp, tb, tg, gbase, gterms, prof, active, j, W, sink);
+      walk_tiles<false>(sp, tb, tg, gbase, gterms, prof, active, j, W, sink, TileChunk{});
       if (active) {
         const int n = j * Ns + k;                          // width-major candidate index (jerk_space_sampling_planner.py:106,124-125)
         const double cost = candidate_cost(sp, sink, latcost + j * 4);

@@ -104,6 +104,9 @@ typedef struct jssp_cycle_in {
 #define JSSP_FLAG_PERSISTENT 512  /* jssp_batch_run only: the persistent replay kernel - one CTA per scenario loops seed enumeration -> evaluation ->
                                     selection -> export -> hand-off over the scenario's own plan cycles, ONE launch per call, no lock-step between
                                     scenarios; same results (measured slower than the lock-step pipeline on B200) */
+#define JSSP_FLAG_CHUNKED 1024    /* jssp_batch_run only: the chunked tiled kernel - two lane groups per seed split the horizon, the halves are
+                                    combined in time order with the serial walk's semantics (same selection and rows); chosen automatically
+                                    when the batch leaves the GPU half empty (JSSP_FLAG_FORCE_TILED keeps the whole-horizon walk) */
 #define JSSP_FLAG_NO_CULL 4      /* test every obstacle state instead of the per-block culled lists (same results) */
 
 /* Outputs.  Candidate n = w * n_seeds + k (width-major, jssp.py:106,124-125).  All dev pointers may be NULL.  With

@@ -30,7 +30,7 @@ def test_batch_matches_single_scenario_replays(scenario_fixture):
     assert any(g.end in (1, 1.5, 2) for g in got)           # at least one scenario ran to a real end status
 
 
-@pytest.mark.parametrize("kernel", [None, "persistent", "warp", "thread", "group", "tiled"])
+@pytest.mark.parametrize("kernel", [None, "persistent", "warp", "thread", "group", "tiled", "chunked"])
 def test_batch_kernels_agree_with_oracle_replay(kernel):
     scs = [S.synthetic_intersection(i) for i in (3, 4)]
     got = B.run_batch(scs, max_cycles=20, kernel=kernel)

@@ -16,7 +16,7 @@ packed = [p for p in packed if p.initial_end == -1]
 cfg = J.JsspConfig(max_seeds=1024, max_knots=max(len(p.knot_s) for p in packed), max_obstacle_modes=max(1, max(p.state.shape[0] for p in packed)),
                    max_total_steps=max(p.state.shape[2] for p in packed))
 bt = B.BatchReplay(cfg, max_scenarios=len(packed), max_cycles=warm + 2)
-ts = torch.zeros((len(packed) * 4096, 8), dtype=torch.int64, device="cuda")
+ts = torch.zeros((len(packed) * 4096, 16), dtype=torch.int64, device="cuda")
 fn = bt.lib.jssp_batch_debug_phase_buffer; fn.restype = C.c_int32; fn.argtypes = [C.c_void_p, C.c_void_p]
 assert fn(bt._h, ts.data_ptr()) == 0
 bt.load(packed)
@@ -41,3 +41,9 @@ if len(last):
     for nm, d in (("walk->winner known", last[:, 5] - last[:, 3]), ("export", last[:, 6] - last[:, 5]), ("hand-off", last[:, 4] - last[:, 6])):
         print(f"  reducing blocks ({len(last)}): {nm}: median {np.median(d) / 1e3:5.1f}  max {d.max() / 1e3:5.1f} us")
     print(f"  reducing blocks: winner known at median {np.median(last[:, 5] - t0) / 1e3:.1f}, max {(last[:, 5].max() - t0) / 1e3:.1f} us")
+if t.shape[1] >= 16 and (work[:, 8] > 0).any():      # tiled kernels: progress of the block's first warp (thread 0)
+    w = work[work[:, 8] > 0]
+    for nm, a, b in (("lists -> tile 0 done", 2, 8), ("tile 0 -> tile 1", 8, 9), ("  tile 1: phase 1", 8, 14), ("  tile 1: cost sums", 14, 15), ("  tile 1: phase 2", 15, 9), ("tile 1 -> middle tile", 9, 10), ("middle -> last tile", 10, 11),
+                     ("last tile -> walk returned", 11, 12), ("walk returned -> cost done", 12, 13), ("cost done -> block barrier passed", 13, 3)):
+        d = (w[:, b] - w[:, a]) / 1e3
+        print(f"  first warp: {nm}: median {np.median(d):6.1f}  p90 {np.quantile(d, 0.9):6.1f}  max {d.max():6.1f} us")

@@ -18,7 +18,7 @@ sp = J.CubicSpline2D(cyc.route_xy[:, 0], cyc.route_xy[:, 1]); eng.set_refline(sp
 o = cyc.obstacles; eng.set_obstacles(o.state, o.valid, o.size, o.prob, o.n_dict)
 seeds = torch.from_numpy(cyc.seeds).cuda()
 nb = 1 << 16
-ts = torch.zeros((nb, 8), dtype=torch.int64, device="cuda")
+ts = torch.zeros((nb, 16), dtype=torch.int64, device="cuda")
 fn = eng.lib.jssp_debug_phase_buffer; fn.restype = C.c_int32; fn.argtypes = [C.c_void_p, C.c_void_p]
 assert fn(eng._h, ts.data_ptr()) == 0
 for _ in range(3):

@@ -16,7 +16,7 @@ cfg = J.JsspConfig(ego_length=float(e[5]), ego_width=float(e[6]), max_seeds=1024
 bt = B.BatchReplay(cfg, max_scenarios=len(packed), max_cycles=C)
 bt.load(packed)
 out = {}
-kerns = ("persistent", "lockstep") + tuple(sys.argv[3:])
+kerns = (("lockstep",) if os.environ.get("SWEEP_AB_NO_PERSISTENT") else ("persistent", "lockstep")) + tuple(sys.argv[3:])
 for kern in kerns:
     for _ in range(2):
         bt.reset(); bt.run(C, kernel=kern)
@@ -29,11 +29,15 @@ for kern in kerns:
     res = bt.results()
     out[kern] = res
     print(f"{str(kern):>9}: {min(ts):8.3f} ms per sweep of {len(packed)} scenarios, {sum(r.cycles for r in res)} plan cycles, max cycles {max(r.cycles for r in res)}")
-bad = [(a.name, a.cycles, b.cycles, a.end, b.end) for a, b in zip(out["persistent"], out["lockstep"])
-       if (a.end, a.cycles, list(a.best_idx), list(a.n_candidates)) != (b.end, b.cycles, list(b.best_idx), list(b.n_candidates))]
-print("scenarios that differ:", len(bad), bad[:8])
-for a, b in zip(out["persistent"], out["lockstep"]):
-    if list(a.best_idx) != list(b.best_idx):
-        k = next(i for i, (x, y) in enumerate(zip(a.best_idx, b.best_idx)) if x != y)
-        print(" first difference", a.name, "cycle", k, a.best_idx[k], b.best_idx[k], a.n_candidates[k], b.n_candidates[k], "overflow", a.seed_overflow, b.seed_overflow)
-        break
+def rows(r):
+    return (r.end, r.cycles, list(r.best_idx), list(r.n_candidates))
+for kern in kerns:
+    if kern == "lockstep":
+        continue
+    bad = [(a.name, a.cycles, b.cycles, a.end, b.end) for a, b in zip(out[kern], out["lockstep"]) if rows(a) != rows(b)]
+    print(f"{kern} vs lockstep: scenarios that differ: {len(bad)}", bad[:8])
+    for a, b in zip(out[kern], out["lockstep"]):
+        if list(a.best_idx) != list(b.best_idx):
+            k = next(i for i, (x, y) in enumerate(zip(a.best_idx, b.best_idx)) if x != y)
+            print(" first difference", a.name, "cycle", k, a.best_idx[k], b.best_idx[k], a.n_candidates[k], b.n_candidates[k], "overflow", a.seed_overflow, b.seed_overflow)
+            break
