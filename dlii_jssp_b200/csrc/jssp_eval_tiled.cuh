@@ -261,6 +261,52 @@ struct TileSink {
     }
   }
 
+  // The same decision as curvature_fails_fast in straight-line form (no branch on the common path, so that the tests of two
+  // consecutive segments overlap in the pipeline): 0 passes, 1 fails, 2 = re-decide with curvature_redecide.
+  __device__ __forceinline__ int curvature_classify(double adx, double ady, float aqf, float adsf, double dx, double dy, float qf, float dsf) const {
+    const float phif = (float)p.kmax * adsf;
+    const bool rng = (aqf > 1e-16f && aqf < 1e30f) && (qf > 1e-16f && qf < 1e30f) && (phif < 0.49f);
+    const double cross = fma(adx, dy, -(ady * dx)), dot = fma(adx, dx, ady * dy);
+    const bool nb = signbit(dy);
+    const bool jump = (signbit(ady) != nb) && (nb ? (cross > 0.0) : (cross < 0.0));     // the difference jumps by 2*pi: rare
+    const float p2 = phif * phif;
+    const float spf = phif * fmaf(p2, fmaf(p2, fmaf(p2, -1.0f / 5040.0f, 1.0f / 120.0f), -1.0f / 6.0f), 1.0f);
+    const float lhs = (float)fabs(cross), rhs = spf * adsf * dsf;
+    const bool clear = fabsf(lhs - rhs) > 4e-6f * fmaxf(lhs, rhs);
+    const bool obtuse = !(dot > 0.0);                                                   // |angle| >= pi/2 > phi
+    return (!rng || jump) ? 2 : (obtuse ? 1 : (clear ? (lhs > rhs ? 1 : 0) : 2));
+  }
+  __device__ __noinline__ static bool curvature_redecide(double kmax, double adx, double ady, double dx, double dy) {
+    if (dx == 0.0 && dy == 0.0 && adx == 0.0 && ady == 0.0) return false;   // standstill: both headings are atan2(0, 0) = 0, 0 / 0 = nan passes
+    return curvature_exact(kmax, adx, ady, dx, dy);
+  }
+  static __device__ __forceinline__ void seg_lengths(double dx, double dy, float& qf, float& dsf) {
+    const float dxf = (float)dx, dyf = (float)dy;
+    qf = fmaf(dxf, dxf, dyf * dyf);
+    float inv = rsqrtf(qf);
+    inv = inv * fmaf(-0.5f * qf, inv * inv, 1.5f);
+    dsf = (qf > 1e-16f && qf < 1e30f) ? qf * inv : 0.f;
+  }
+
+  // two consecutive segments at once: i (pose (x0, y0), difference A) and i + 1 (pose (x1, y1), difference B) - the same
+  // decisions, flags and risk terms, in the same order, as segment(i, ...) followed by segment(i + 1, ...)
+  __device__ __forceinline__ void segment2(int i, double x0, double y0, double ax, double ay, double x1, double y1, double bx, double by) {
+    float aq, ads, bq, bds;
+    seg_lengths(ax, ay, aq, ads);
+    seg_lengths(bx, by, bq, bds);
+    int ra = curvature_classify(pdx, pdy, pqf, pdsf, ax, ay, aq, ads);
+    int rb = curvature_classify(ax, ay, aq, ads, bx, by, bq, bds);
+    if (i < 1) ra = 0;
+    if ((ra | rb) & 2) {                                                    // rare: guard band, tiny segments, heading wrap
+      if (ra == 2) ra = curvature_redecide(p.kmax, pdx, pdy, ax, ay) ? 1 : 0;
+      if (rb == 2) rb = curvature_redecide(p.kmax, ax, ay, bx, by) ? 1 : 0;
+    }
+    if (ra | rb) curv_fail = true;
+    collide(i, x0, y0, ax, ay, aq);
+    collide(i + 1, x1, y1, bx, by, bq);
+    pdx = bx; pdy = by; pqf = bq; pdsf = bds;
+  }
+
   // segment i = p_{i+1} - p_i arrives: curvature against segment i - 1, collision row of sample i, shift
   __device__ __forceinline__ void segment(int i, double x, double y, double dx, double dy) {
     const float dxf = (float)dx, dyf = (float)dy;
@@ -346,9 +392,10 @@ __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTable
       for (int il = 0; il < own; ++il) { sa = sa + gterms[il * 3]; sj = sj + gterms[il * 3 + 1]; sv = sv + gterms[il * 3 + 2]; }
     }
     if (t == 1) PHASE(p, 15);
-    // phase 2: this lane's candidate
+    // phase 2: this lane's candidate - two samples per step where the tile has them (two independent dependency chains)
     if (walking) {
-      for (int il = 0; il < len; ++il) {
+      int il = 0;
+      while (il < len) {
         const int i = base + il;
         const double2* e = reinterpret_cast<const double2*>(gbase + il * 4);
         const double2 pxy = e[0];
@@ -356,15 +403,28 @@ __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTable
         const double2 uv = e[1];
         const double d = lat[i * 4];
         const double x = fma(-d, uv.x, pxy.x), y = fma(d, uv.y, pxy.y);
-        if (i > lo) {
-          if (kChunked && !ck.first && i == lo + 1) {
-            sink.prime(x - xp, y - yp);            // the segment before the chunk: tested by the chunk before
-          } else {
-            sink.segment(i - 1, xp, yp, x - xp, y - yp);
-            if (sink.vetoed()) { walking = false; break; }     // select-only evaluation: this candidate can no longer be selected
-          }
+        if (i == lo) { xp = x; yp = y; ++il; continue; }
+        if (kChunked && !ck.first && i == lo + 1) {
+          sink.prime(x - xp, y - yp);            // the segment before the chunk: tested by the chunk before
+          xp = x; yp = y; ++il; continue;
         }
-        xp = x; yp = y;
+        bool two = il + 1 < len;
+        double x1 = 0, y1 = 0;
+        if (two) {
+          const double2 qxy = e[2];
+          const double2 uv1 = e[3];
+          const double d1 = lat[(i + 1) * 4];
+          x1 = fma(-d1, uv1.x, qxy.x); y1 = fma(d1, uv1.y, qxy.y);
+          two = qxy.x == qxy.x;                  // the path ends at the next point: it is met again, alone, in the next step
+        }
+        if (two) {
+          sink.segment2(i - 1, xp, yp, x - xp, y - yp, x, y, x1 - x, y1 - y);
+          xp = x1; yp = y1; il += 2;
+        } else {
+          sink.segment(i - 1, xp, yp, x - xp, y - yp);
+          xp = x; yp = y; ++il;
+        }
+        if (sink.vetoed()) { walking = false; break; }     // select-only evaluation: this candidate can no longer be selected
       }
     }
     __syncwarp();                                  // the tile is rewritten by the next phase 1
