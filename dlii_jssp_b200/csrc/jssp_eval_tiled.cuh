@@ -392,6 +392,7 @@ __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTable
       for (int il = 0; il < own; ++il) { sa = sa + gterms[il * 3]; sj = sj + gterms[il * 3 + 1]; sv = sv + gterms[il * 3 + 2]; }
     }
     if (t == 1) PHASE(p, 15);
+    if (t == 1) PHASE(p, 15);
     // phase 2: this lane's candidate - two samples per step where the tile has them (two independent dependency chains)
     if (walking) {
       int il = 0;
