@@ -20,7 +20,6 @@ FLAG_FORCE_TILED = 128
 FLAG_LOCKSTEP = 256
 FLAG_PERSISTENT = 512
 FLAG_CHUNKED = 1024
-FLAG_FORCE_PAIR = 2048
 
 TRAJ_COLUMNS = ("t", "s", "s_d", "s_dd", "s_ddd", "d", "d_d", "d_dd", "d_ddd", "x", "y", "yaw", "ds", "c", "c_d", "c_dd")
 STATE_COLUMNS = ("s", "s_d", "s_dd", "d", "x", "y", "yaw", "c")

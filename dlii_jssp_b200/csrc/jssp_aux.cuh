@@ -15,13 +15,24 @@ namespace jssp {
 // stores 32 consecutive rows = 1 KB contiguous, so the dump is written at HBM speed (1,632 B per candidate, the HBM-bound variant
 // of SURVEY.md section 8d).
 constexpr int DUMP_WARPS = 8;
-__host__ __device__ inline size_t dump_warp_doubles(int P) { return (TILE_PROF + (size_t)P * 4 + (size_t)((P * 3 + 1) / 2) + 3) & ~(size_t)1; }   // even: 16-byte rows
+// per warp: segment table | [P][4] ix, iy, u, v | [P][3] float s, s_d, s_dd | [2][P] double2 points of the current lateral target
+__host__ __device__ inline size_t dump_warp_doubles(int P) { return (TILE_PROF + (size_t)P * 4 + (size_t)((P * 3 + 1) / 2) + 3 + (size_t)P * 4) & ~(size_t)1; }   // even: 16-byte rows
 __host__ __device__ inline size_t dump_scratch_bytes(int P) { return (size_t)DUMP_WARPS * dump_warp_doubles(P) * 8; }
 
-__device__ __forceinline__ void dump_point(const double* base, const double* lat, int i, double& x, double& y) {
-  const double2 a = *reinterpret_cast<const double2*>(base + (size_t)i * 4), b = *reinterpret_cast<const double2*>(base + (size_t)i * 4 + 2);
-  const double d = lat[i * 4];
-  x = fma(-d, b.x, a.x); y = fma(d, b.y, a.y);
+// atan2 for the float32 dump rows: octant reduction + the Cephes atanf polynomial on |t| <= tan(pi/8) (relative error ~1e-7 with
+// the approximate division), about a third of the instructions of the library atan2f; atan2(0, 0) = 0 like NumPy
+__device__ __forceinline__ float dump_atan2(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const bool big = mn > 0.41421356f * mx;
+  const float t = __fdividef(big ? mn - mx : mn, big ? mn + mx : mx);
+  const float z = t * t;
+  float r = fmaf(fmaf(fmaf(fmaf(8.05374449538e-2f, z, -1.38776856032e-1f), z, 1.99777106478e-1f), z, -3.33329491539e-1f) * z, t, t);
+  if (big) r += 0.78539816f;
+  if (!(mx > 0.f)) r = 0.f;
+  if (ay > ax) r = 1.57079637f - r;
+  if (signbit(x)) r = 3.14159274f - r;
+  return copysignf(r, y);
 }
 
 __global__ void __launch_bounds__(DUMP_WARPS * 32) dump_states_kernel(const __grid_constant__ EvalParams p, float* __restrict__ states) {
@@ -38,6 +49,7 @@ __global__ void __launch_bounds__(DUMP_WARPS * 32) dump_states_kernel(const __gr
   double* prof = reinterpret_cast<double*>(smem + ((L.total + 15) & ~(size_t)15)) + (size_t)wid * per_warp;
   double* base = prof + TILE_PROF;                       // [P][4] ix, iy, u, v
   float* lon = reinterpret_cast<float*>(base + (size_t)P * 4);   // [P][3] s, s_d, s_dd
+  double2* pts = reinterpret_cast<double2*>(prof + ((per_warp - (size_t)P * 4) & ~(size_t)1));   // [2][P] (x, y), one buffer per parity of the lateral target
   const float nanv = __int_as_float(0x7fc00000);
   for (int k = blockIdx.x * DUMP_WARPS + wid; k < Ns; k += gridDim.x * DUMP_WARPS) {       // warp-uniform
     if (lane == 0) tile_profile_store(prof, p.seeds + (size_t)k * 10, p.s0, p.v0, p.a0);
@@ -65,40 +77,55 @@ __global__ void __launch_bounds__(DUMP_WARPS * 32) dump_states_kernel(const __gr
     for (int w = 0; w < W; ++w) {
       const double* lat = tb.lat + (size_t)w * P * 4;
       float* out = states + ((size_t)w * Ns + k) * P * JSSP_STATE_COLS;
+      // every point of this candidate once (float64), into the buffer of this target's parity; the rows then read their two
+      // neighbours.  One warp barrier per target: a buffer is rewritten two targets later, after every lane passed the next barrier.
+      double2* pw = pts + (size_t)(w & 1) * P;
+      for (int i = lane; i < n_pts; i += 32) {
+        const double2 a = *reinterpret_cast<const double2*>(base + (size_t)i * 4), b = *reinterpret_cast<const double2*>(base + (size_t)i * 4 + 2);
+        const double d = lat[i * 4];
+        pw[i] = make_double2(fma(-d, b.x, a.x), fma(d, b.y, a.y));
+      }
+      __syncwarp();
       for (int i = lane; i < P; i += 32) {
         float4 r0 = make_float4(lon[i * 3], lon[i * 3 + 1], lon[i * 3 + 2], (float)lat[i * 4]);
         float4 r1 = make_float4(nanv, nanv, nanv, nanv);
         if (i < n_pts) {
-          double x, y;
-          dump_point(base, lat, i, x, y);
-          r1.x = (float)x; r1.y = (float)y;
+          // heading of sample i = chord hs -> hs + 1 with hs = min(i, n_pts - 2) (the last heading repeats the previous one)
+          const int hs = n_pts >= 2 ? min(i, n_pts - 2) : i;
+          const double2 pa = pw[hs];
+          const double2 me = (hs == i) ? pa : pw[i];
+          r1.x = (float)me.x; r1.y = (float)me.y;
           if (n_pts >= 2) {
-            // heading of sample i = chord hs -> hs + 1 with hs = min(i, n_pts - 2) (the last heading repeats the previous one)
-            const int hs = min(i, n_pts - 2);
-            double ax, ay, bx, by;
-            dump_point(base, lat, hs, ax, ay);
-            dump_point(base, lat, hs + 1, bx, by);
-            const double dx0 = bx - ax, dy0 = by - ay;
-            r1.z = atan2f((float)dy0, (float)dx0);
+            const double2 pb = pw[hs + 1];
+            const double dx0 = pb.x - pa.x, dy0 = pb.y - pa.y;
+            r1.z = dump_atan2((float)dy0, (float)dx0);
             if (i < n_pts - 1) {                      // c_i = (yaw_{i+1} - yaw_i) / ds_i, no unwrapping
-              double raw = 0.0;
+              float raw = 0.0f;
               if (i + 1 <= n_pts - 2) {
-                double cx, cy;
-                dump_point(base, lat, i + 2, cx, cy);
-                const double dx1 = cx - bx, dy1 = cy - by;
+                const double2 pc = pw[i + 2];
+                const double dx1 = pc.x - pb.x, dy1 = pc.y - pb.y;
                 const double cross = fma(dx0, dy1, -(dy0 * dx1)), dot = fma(dx0, dx1, dy0 * dy1);
-                raw = (double)atan2f((float)cross, (float)dot);
+                // the angle between two consecutive chords is small almost everywhere: atan(z) by its series for |z| < 0.1 (truncation
+                // error z^7 / 7 < 2e-8 relative), the library atan2f otherwise
+                const float crf = (float)cross, dtf = (float)dot;
+                if (dtf > 0.f && fabsf(crf) < 0.1f * dtf) {
+                  const float z = __fdividef(crf, dtf), z2 = z * z;
+                  raw = z * fmaf(z2, fmaf(z2, 0.2f, -0.33333334f), 1.0f);
+                } else raw = dump_atan2(crf, dtf);
                 const bool nb = signbit(dy1);
-                if ((signbit(dy0) != nb) && (nb ? (cross > 0.0) : (cross < 0.0))) raw += nb ? -6.283185307179586 : 6.283185307179586;
-                if (dx1 == 0.0 && dy1 == 0.0) raw = 0.0 - (double)r1.z;      // atan2(0, 0) = 0
-                else if (dx0 == 0.0 && dy0 == 0.0) raw = (double)atan2f((float)dy1, (float)dx1);
+                if ((signbit(dy0) != nb) && (nb ? (cross > 0.0) : (cross < 0.0))) raw += nb ? -6.2831853f : 6.2831853f;
+                if (dx1 == 0.0 && dy1 == 0.0) raw = 0.0f - r1.z;      // atan2(0, 0) = 0
+                else if (dx0 == 0.0 && dy0 == 0.0) raw = dump_atan2((float)dy1, (float)dx1);
               }
-              r1.w = (float)(raw / sqrt(dx0 * dx0 + dy0 * dy0));
+              // raw / ds in float32 (the row is float32): one MUFU.RSQ instead of a float64 square root and division; ds == 0 gives
+              // +-inf or nan exactly as the division does
+              const float q0 = (float)fma(dx0, dx0, dy0 * dy0);
+              r1.w = (q0 > 1e-30f) ? raw * rsqrtf(q0) : (float)((double)raw / sqrt(dx0 * dx0 + dy0 * dy0));
             }
           }
         }
         float4* o = reinterpret_cast<float4*>(out + (size_t)i * JSSP_STATE_COLS);
-        o[0] = r0; o[1] = r1;
+        __stcs(o, r0); __stcs(o + 1, r1);               // streaming stores: the dump is written once and read by nobody on the device
       }
     }
     __syncwarp();                                      // the scratch is reused by the warp's next seed

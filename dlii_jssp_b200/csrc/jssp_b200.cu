@@ -495,9 +495,6 @@ int32_t jssp_create(const jssp_config* cfg, int32_t device, jssp_handle** out) {
   CKC(allow_max_dynamic_smem(evaluate_tiled_kernel<0>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_tiled_kernel<1>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_tiled_kernel<2>, optin, &h->max_smem_optin));
-  CKC(allow_max_dynamic_smem(evaluate_pair_kernel<0>, optin, &h->max_smem_optin));
-  CKC(allow_max_dynamic_smem(evaluate_pair_kernel<1>, optin, &h->max_smem_optin));
-  CKC(allow_max_dynamic_smem(evaluate_pair_kernel<2>, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(dump_states_kernel, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_fop_kernel, optin, &h->max_smem_optin));
   CKC(allow_max_dynamic_smem(fop_select_export_kernel, optin, &h->max_smem_optin));
@@ -823,37 +820,6 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
     tiled_threads = warps * 32;
     blocks = (int)((seeds_max + (long long)warps * gpw_t - 1) / ((long long)warps * gpw_t));
   }
-  // paired walk (jssp_eval_pair.cuh): the candidate's curvature chain and collision rows on two warps.  Same tile geometry as the
-  // tiled walk per PAIR of warps; single-wave launches are balanced over the SMs (two blocks per SM) like the tiled ones.
-  bool paired = tiled && (in->flags & JSSP_FLAG_FORCE_PAIR);
-  int pair_threads = PAIR_THREADS, pair_rounds = 0;
-  size_t pair_total = 0;
-  if (paired) {
-    const int gpw_t = 32 / W, max_pairs = PAIR_THREADS / 64;
-    int pairs = max_pairs;
-    long long pblocks = (seeds_max + (long long)pairs * gpw_t - 1) / ((long long)pairs * gpw_t);
-    if (pblocks <= 2 * h->sm_count && pblocks > h->sm_count / 2) {
-      const long long per_block = (seeds_max + 2 * h->sm_count - 1) / (2 * h->sm_count);
-      pairs = (int)std::min<long long>(max_pairs, std::max<long long>(1, (per_block + gpw_t - 1) / gpw_t));
-      pblocks = (seeds_max + (long long)pairs * gpw_t - 1) / ((long long)pairs * gpw_t);
-    }
-    pair_threads = pairs * 64;
-    cudaFuncAttributes fa{};
-    cudaFuncGetAttributes(&fa, evaluate_pair_kernel<2>);
-    const size_t per_sm = 228u * 1024u, two = per_sm / 2 - fa.sharedSizeBytes - 1024;
-    const size_t lbase = (L.total + 15) & ~(size_t)15;
-    for (int r = tile_rounds_wanted(W); r >= 1; --r) {
-      pair_rounds = r; pair_total = lbase + pair_scratch_bytes(W, pair_threads, r);
-      if (pair_total <= two) break;
-    }
-    if (pair_total > two)
-      for (int r = tile_rounds_wanted(W); r >= 1; --r) {
-        pair_rounds = r; pair_total = lbase + pair_scratch_bytes(W, pair_threads, r);
-        if (pair_total <= (size_t)h->max_smem_optin) break;
-      }
-    if (pair_total > (size_t)h->max_smem_optin || pblocks > h->max_blocks) paired = false;
-    else { blocks = (int)pblocks; p.tile_rounds = pair_rounds; }
-  }
   if (blocks > h->max_blocks) return JSSP_ERR_CAPACITY;
   if (small) {
     p.smem_obs = 0; p.win_rows = 0; p.list_cap = 0;
@@ -861,9 +827,6 @@ int32_t jssp_evaluate(jssp_handle* h, const jssp_cycle_in* in, void* stream, jss
     const bool chained = !ext && (in->flags & JSSP_FLAG_ENUMERATE) && !h->tune.no_pdl;
     CK(launch_chained(evaluate_small_kernel, dim3(blocks), SMALL_WARPS * 32, small_bytes, st, chained, p));
   }
-  else if (paired && mode == 2) evaluate_pair_kernel<2><<<blocks, pair_threads, pair_total, st>>>(p);
-  else if (paired && mode == 1) evaluate_pair_kernel<1><<<blocks, pair_threads, pair_total, st>>>(p);
-  else if (paired) evaluate_pair_kernel<0><<<blocks, pair_threads, pair_total, st>>>(p);
   else if (tiled && mode == 2) evaluate_tiled_kernel<2><<<blocks, tiled_threads, tiled_total, st>>>(p);
   else if (tiled && mode == 1) evaluate_tiled_kernel<1><<<blocks, tiled_threads, tiled_total, st>>>(p);
   else if (tiled) evaluate_tiled_kernel<0><<<blocks, tiled_threads, tiled_total, st>>>(p);

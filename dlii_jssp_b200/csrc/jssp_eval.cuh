@@ -512,7 +512,6 @@ struct WalkSAt {
 //   lists_begin    clear the per-row ranges / counters (ends with a block barrier)
 //   phase A        every seed of the block widens [row_min, row_max] of every collision row with its arc length there
 //   lists_compact  one warp per row: ballot-compaction of the states whose reachable interval overlaps the row's range
-constexpr int LIST_PAD = 4;      // list rows hold a multiple of LIST_PAD entries: the tiled walk tests them LIST_PAD at a time without a branch
 struct ListsView {
   float4* list; int* row_off; int* row_cnt; unsigned int* row_min; unsigned int* row_max; int* cursor;
 };
@@ -559,13 +558,11 @@ __device__ __forceinline__ void lists_compact(const EvalParams& p, const ListsVi
       int cnt = 0;
 #pragma unroll
       for (int c = 0; c < CH; ++c) { m[c] = __ballot_sync(0xffffffffu, v[c].y >= smin && v[c].x <= smax); cnt += __popc(m[c]); }
-      const int cntp = (cnt + LIST_PAD - 1) & ~(LIST_PAD - 1);      // rows are padded with entries that never pass the circle test
       int off = 0;
-      if (lane == 0) off = atomicAdd(&cursor[0], cntp);
+      if (lane == 0) off = atomicAdd(&cursor[0], cnt);
       off = __shfl_sync(0xffffffffu, off, 0);
-      if (off + cntp > p.list_cap) { if (lane == 0) cursor[1] = 1; continue; }
-      if (lane == 0) { row_off[r] = off; row_cnt[r] = cntp; }
-      if (lane < cntp - cnt) list[off + cnt + lane] = make_float4(0.f, 0.f, FAR_AWAY, 0.f);
+      if (off + cnt > p.list_cap) { if (lane == 0) cursor[1] = 1; continue; }
+      if (lane == 0) { row_off[r] = off; row_cnt[r] = cnt; }
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         if ((m[c] >> lane) & 1u) {
@@ -582,13 +579,11 @@ __device__ __forceinline__ void lists_compact(const EvalParams& p, const ListsVi
       const float2 v = iv[base + lane];
       cnt += __popc(__ballot_sync(0xffffffffu, v.y >= smin && v.x <= smax));
     }
-    const int cntp = (cnt + LIST_PAD - 1) & ~(LIST_PAD - 1);
     int off = 0;
-    if (lane == 0) off = atomicAdd(&cursor[0], cntp);
+    if (lane == 0) off = atomicAdd(&cursor[0], cnt);
     off = __shfl_sync(0xffffffffu, off, 0);
-    if (off + cntp > p.list_cap) { if (lane == 0) cursor[1] = 1; continue; }
-    if (lane == 0) { row_off[r] = off; row_cnt[r] = cntp; }
-    if (lane < cntp - cnt) list[off + cnt + lane] = make_float4(0.f, 0.f, FAR_AWAY, 0.f);
+    if (off + cnt > p.list_cap) { if (lane == 0) cursor[1] = 1; continue; }
+    if (lane == 0) { row_off[r] = off; row_cnt[r] = cnt; }
     for (int base = 0; base < p.OMpad; base += 32) {
       const float2 v = iv[base + lane];
       const bool keep = v.y >= smin && v.x <= smax;
@@ -609,7 +604,7 @@ __device__ __forceinline__ void lists_compact(const EvalParams& p, const ListsVi
 
 template <class SAt>
 __device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* smem, BlockTables& tb, SAt& s_at, bool active,
-                                            int row_first = 0, int row_stride = 1, int round_first = 0, int round_step = 1) {
+                                            int row_first = 0, int row_stride = 1) {
   const ListsView v = lists_view(p, smem);
   unsigned int* row_min = v.row_min; unsigned int* row_max = v.row_max;
   const int lane = threadIdx.x & 31;
@@ -632,8 +627,7 @@ __device__ __forceinline__ void build_lists(const EvalParams& p, unsigned char* 
     // the lanes of a group share the seed: lane j of the group evaluates the rows r = j (mod W); in one round every lane
     // with the same j holds the same row, so a stride-W shuffle tree leaves the warp's range in the lanes of group 0
     const int W = row_stride;
-    // (round_first, round_step): the rounds this warp takes - warps that hold the same seeds share the rows (paired walk)
-    for (int r0 = round_first * W; r0 < p.win_rows; r0 += W * round_step) {
+    for (int r0 = 0; r0 < p.win_rows; r0 += W) {
       const int r = r0 + row_first;
       unsigned int lo = 0x7f800000u, hi = 0u;
       if (active && r < p.win_rows) {

@@ -227,18 +227,9 @@ struct TileSink {
     if (tb.use_lists) {      // block-level culled rows: a handful of entries instead of OMpad
       const int cnt = tb.row_cnt[r];
       const float4* e = tb.list + tb.row_off[r];
-      // LIST_PAD circle tests at a time, straight-line (the loads of a group are in flight together, no branch per entry); the rare
-      // hits are then taken in list order, so a veto and the risk sum see the entries in the same order as an entry-by-entry loop
-      for (int k0 = 0; k0 < cnt; k0 += LIST_PAD) {
-        unsigned int hits = 0u;
-#pragma unroll
-        for (int q = 0; q < LIST_PAD; ++q) {
-          const float4 b = e[k0 + q];
-          hits |= (fmaf(b.x, m2x, fmaf(b.y, m2y, b.z)) <= ne2) ? (1u << q) : 0u;
-        }
-        while (hits) {
-          const float4 b = e[k0 + __ffs(hits) - 1];
-          hits &= hits - 1u;
+      for (int k = 0; k < cnt; ++k) {
+        const float4 b = e[k];
+        if (fmaf(b.x, m2x, fmaf(b.y, m2y, b.z)) <= ne2) {
           const int om = __float_as_int(b.w);
           if (narrow_hit_lazy(abs_step, om, b.x - fx, b.y - fy, x, y, cf, snf, hdx, hdy)) {
             const float pr = __ldg(p.probf + om);
@@ -314,30 +305,6 @@ struct TileSink {
     collide(i, x0, y0, ax, ay, aq);
     collide(i + 1, x1, y1, bx, by, bq);
     pdx = bx; pdy = by; pqf = bq; pdsf = bds;
-  }
-
-  // curvature only (paired walk, jssp_eval_pair.cuh): the decisions of segment2 / segment without the collision rows
-  __device__ __forceinline__ void curv2(int i, double ax, double ay, double bx, double by) {
-    float aq, ads, bq, bds;
-    seg_lengths(ax, ay, aq, ads);
-    seg_lengths(bx, by, bq, bds);
-    int ra = curvature_classify(pdx, pdy, pqf, pdsf, ax, ay, aq, ads);
-    int rb = curvature_classify(ax, ay, aq, ads, bx, by, bq, bds);
-    if (i < 1) ra = 0;
-    if ((ra | rb) & 2) {
-      if (ra == 2) ra = curvature_redecide(p.kmax, pdx, pdy, ax, ay) ? 1 : 0;
-      if (rb == 2) rb = curvature_redecide(p.kmax, ax, ay, bx, by) ? 1 : 0;
-    }
-    if (ra | rb) curv_fail = true;
-    pdx = bx; pdy = by; pqf = bq; pdsf = bds;
-  }
-  __device__ __forceinline__ void curv1(int i, double dx, double dy) {
-    float q, ds;
-    seg_lengths(dx, dy, q, ds);
-    int r = i >= 1 ? curvature_classify(pdx, pdy, pqf, pdsf, dx, dy, q, ds) : 0;
-    if (r == 2) r = curvature_redecide(p.kmax, pdx, pdy, dx, dy) ? 1 : 0;
-    if (r) curv_fail = true;
-    pdx = dx; pdy = dy; pqf = q; pdsf = ds;
   }
 
   // segment i = p_{i+1} - p_i arrives: curvature against segment i - 1, collision row of sample i, shift

@@ -10,7 +10,6 @@
 //   jssp_eval_small.cuh  K2b evaluate_small_kernel           one warp per candidate (default sampling grid)
 //   jssp_eval_tiled.cuh  K2  evaluate_tiled_kernel (default for large cycles): two-phase tiled walk - seed-only work of a tile in
 //                            parallel into the warp's shared-memory tile, then one lane per candidate
-//   jssp_eval_pair.cuh   K2  evaluate_pair_kernel: the tiled walk split by function over warp pairs (curvature warp / collision warp)
 //   jssp_replay.cuh      K7  replay_persistent_kernel: one CTA per scenario loops seed enumeration -> evaluation -> selection -> export ->
 //                            hand-off over the scenario's plan cycles in ONE launch        code/__main__.py:124-167, env.py:24-30
 //   jssp_split.cuh           candidate-split exchange (NCCL all-gather record / peer mailboxes fused into the evaluation launch)
@@ -24,7 +23,6 @@
 #include "jssp_eval.cuh"
 #include "jssp_eval_small.cuh"
 #include "jssp_eval_tiled.cuh"
-#include "jssp_eval_pair.cuh"
 #include "jssp_replay.cuh"
 #include "jssp_fop.cuh"
 #include "jssp_aux.cuh"

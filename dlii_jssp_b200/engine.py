@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import JsspError, JsspConfigC, JsspCycleIn, JsspCycleOut, JsspFopIn, JsspImmParams, FLAG_NO_SYNC, FLAG_NO_EXPORT, FLAG_NO_CULL, FLAG_ENUMERATE, FLAG_FORCE_WARP, FLAG_FORCE_THREAD, FLAG_FORCE_GROUP, FLAG_FORCE_TILED, FLAG_FORCE_PAIR, TRAJ_COLUMNS
+from ._lib import JsspError, JsspConfigC, JsspCycleIn, JsspCycleOut, JsspFopIn, JsspImmParams, FLAG_NO_SYNC, FLAG_NO_EXPORT, FLAG_NO_CULL, FLAG_ENUMERATE, FLAG_FORCE_WARP, FLAG_FORCE_THREAD, FLAG_FORCE_GROUP, FLAG_FORCE_TILED, TRAJ_COLUMNS
 
 
 @dataclass
@@ -227,7 +227,7 @@ class JsspEngine:
         candidate's walk then stops at its first veto, as the reference's filter chain does; the masks of the returned result
         are stale."""
         flags = (0 if sync else FLAG_NO_SYNC) | (0 if export else FLAG_NO_EXPORT) | (0 if cull else FLAG_NO_CULL)
-        flags |= {None: 0, "warp": FLAG_FORCE_WARP, "thread": FLAG_FORCE_THREAD, "group": FLAG_FORCE_GROUP, "tiled": FLAG_FORCE_TILED, "pair": FLAG_FORCE_TILED | FLAG_FORCE_PAIR}[kernel]
+        flags |= {None: 0, "warp": FLAG_FORCE_WARP, "thread": FLAG_FORCE_THREAD, "group": FLAG_FORCE_GROUP, "tiled": FLAG_FORCE_TILED}[kernel]
         cin, cout = self._cycle_structs(frenet0, time_step_now, final_time_step, seeds, targets, flags, want_states, None)
         if select_only:
             cout.feasible_dev = cout.collision_dev = cout.cost_dev = None

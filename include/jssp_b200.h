@@ -107,8 +107,6 @@ typedef struct jssp_cycle_in {
 #define JSSP_FLAG_CHUNKED 1024    /* jssp_batch_run only: the chunked tiled kernel - two lane groups per seed split the horizon, the halves are
                                     combined in time order with the serial walk's semantics (same selection and rows); chosen automatically
                                     when the batch leaves the GPU half empty (JSSP_FLAG_FORCE_TILED keeps the whole-horizon walk) */
-#define JSSP_FLAG_FORCE_PAIR 2048  /* use the paired walk: the tiled kernel with a candidate's curvature chain and collision rows on two
-                                    warps of a pair (half the serial chain, twice the warps per SM); same results */
 #define JSSP_FLAG_NO_CULL 4      /* test every obstacle state instead of the per-block culled lists (same results) */
 
 /* Outputs.  Candidate n = w * n_seeds + k (width-major, jssp.py:106,124-125).  All dev pointers may be NULL.  With

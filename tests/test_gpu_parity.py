@@ -87,7 +87,7 @@ def test_synthetic_cycle_matches_oracle(n_seeds, n_widths, O_, M, horizon, seed)
     ref = O.plan_cycle(cfg, spline, cyc.frenet0, H.oracle_obstacles(cyc.obstacles), cyc.time_step_now, cyc.final_time_step,
                        seeds=cyc.seeds, targets=cyc.targets)
     seeds = torch.from_numpy(cyc.seeds).cuda()
-    for kern in (None, "group", "thread", "warp", "tiled", "pair"):
+    for kern in (None, "group", "thread", "warp", "tiled"):
         res = eng.evaluate(cyc.frenet0, cyc.time_step_now, cyc.final_time_step, seeds=seeds, targets=cyc.targets, kernel=kern)
         H.compare_cycle(res, ref)
     assert ref["collision"].any() or O_ == 0
@@ -128,7 +128,7 @@ def test_truncated_trajectories_and_end_of_scenario():
                            ((s_end + 1.0, 3.0, 0.0, 0.0, 0.0, 0.0), 0, 100), ((5.0, 6.0, 0.0, 0.0, 0.0, 0.0), 40, 47),
                            ((5.0, 6.0, 0.0, 0.0, 0.0, 0.0), 49, 50), ((5.0, 6.0, 0.0, 0.0, 0.0, 0.0), 50, 50)]:
         ref = O.plan_cycle(cfg, spline, fr, H.oracle_obstacles(cyc.obstacles), now, final, seeds=cyc.seeds, targets=cyc.targets)
-        for kern in (None, "group", "tiled", "pair"):
+        for kern in (None, "group", "tiled"):
             H.compare_cycle(eng.evaluate(fr, now, final, seeds=seeds, targets=cyc.targets, kernel=kern), ref)
     eng.close()
 
@@ -191,7 +191,7 @@ def test_select_only_evaluation_selects_the_same_trajectory(n_seeds, n_widths, O
     trajectory as the full evaluation, for every kernel."""
     cyc, cfg, spline, eng = _dense(n_seeds, n_widths, O_, M, horizon, seed, p_min=0.2, w_risk=0.5)
     seeds = torch.from_numpy(cyc.seeds).cuda()
-    for kern in ("group", "thread", "warp", "tiled", "pair"):
+    for kern in ("group", "thread", "warp", "tiled"):
         full = eng.evaluate(cyc.frenet0, 0, cyc.final_time_step, seeds=seeds, targets=cyc.targets, kernel=kern)
         assert full.best_idx >= 0 and bool(full.collision.any())
         sel = eng.evaluate(cyc.frenet0, 0, cyc.final_time_step, seeds=seeds, targets=cyc.targets, kernel=kern, select_only=True)
@@ -236,7 +236,7 @@ def test_block_level_culling_changes_nothing(n_seeds, n_widths, O_, M, horizon, 
     cyc, cfg, spline, eng = _dense(n_seeds, n_widths, O_, M, horizon, seed, p_min=0.15, w_risk=0.7)
     seeds = torch.from_numpy(cyc.seeds).cuda()
     out = []
-    for kern in ("group", "thread", "tiled", "pair"):  # the kernels that build the per-block lists (small cycles default to the warp kernel)
+    for kern in ("group", "thread", "tiled"):  # the kernels that build the per-block lists (small cycles default to the warp kernel)
         for cull in (True, False):
             r = eng.evaluate(cyc.frenet0, 0, cyc.final_time_step, seeds=seeds, targets=cyc.targets, cull=cull, kernel=kern)
             out.append((r.feasible.cpu().numpy().copy(), r.collision.cpu().numpy().copy(), r.cost.cpu().numpy().copy(), r.best_idx, r.best_cost))
@@ -250,7 +250,7 @@ def test_block_level_culling_changes_nothing(n_seeds, n_widths, O_, M, horizon, 
     # a start offset beyond the lateral cap switches culling off instead of risking a miss
     wide = (cyc.frenet0[0], cyc.frenet0[1], 0.0, 4.2, 0.0, 0.0)
     ref = O.plan_cycle(cfg, spline, wide, H.oracle_obstacles(cyc.obstacles), 0, cyc.final_time_step, seeds=cyc.seeds, targets=cyc.targets)
-    for kern in ("group", "thread", "tiled", "pair"):
+    for kern in ("group", "thread", "tiled"):
         H.compare_cycle(eng.evaluate(wide, 0, cyc.final_time_step, seeds=seeds, targets=cyc.targets, kernel=kern), ref)
     eng.close()
 
@@ -265,12 +265,12 @@ def test_warp_and_thread_kernels_agree(n_seeds, n_widths, O_, M, horizon, seed):
     for fr, now, final in [(cyc.frenet0, 0, cyc.final_time_step), ((s_end - 9.0, 8.0, 0.5, -0.3, 0.1, 0.0), 0, 100),
                            ((s_end - 0.04, 3.0, 0.0, 0.1, 0.0, 0.0), 0, 100), ((4.0, 5.0, 0.0, 0.0, 0.0, 0.0), 43, 50)]:
         out = {}
-        for kern in ("warp", "thread", "group", "tiled", "pair"):
+        for kern in ("warp", "thread", "group", "tiled"):
             r = eng.evaluate(fr, now, final, seeds=seeds, targets=cyc.targets, kernel=kern)
             out[kern] = (r.feasible.cpu().numpy().copy(), r.collision.cpu().numpy().copy(), r.cost.cpu().numpy().copy(), r.best_idx, r.best_cost,
                          r.best_n_pts, None if r.best_traj is None else r.best_traj.copy())
         b = out["thread"]
-        for a in (out["warp"], out["group"], out["tiled"], out["pair"]):      # the tiled kernel adds its cost terms in time order too: bit-identical costs
+        for a in (out["warp"], out["group"], out["tiled"]):      # the tiled kernel adds its cost terms in time order too: bit-identical costs
             ok = a[1] == 0
             assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2][ok], b[2][ok])
             assert a[3:6] == b[3:6]
@@ -298,7 +298,7 @@ def test_cuda_path_matches_the_reference_plan_cycle(golden_dir, scenario_fixture
     for k, label in enumerate(g["labels"]):
         label, fr, now = str(label), tuple(g["frenet0"][k]), int(float(g["t"][k]) / sc.dt)
         eng.enumerate_seeds(*fr[:3])
-        for kern in (None, "thread", "group", "tiled", "pair"):
+        for kern in (None, "thread", "group", "tiled"):
             res = eng.evaluate(fr, now, final, kernel=kern)
             feas_ref = g[f"{label}_feasible"]
             assert res.n_candidates == int(g[f"{label}_n"])
@@ -344,7 +344,7 @@ def test_guard_band_decisions_near_touching_rectangles(yaw_o):
         valid = np.ones((1, 1, 60), dtype=np.uint8); size = np.array([[L, Wd]]); prob = np.ones((1, 1))
         eng.set_obstacles(state, valid, size, prob, 1)
         ref = O.plan_cycle(cfg, spline, fr, (state, valid.astype(bool), size, prob), 0, 55, seeds=seeds, targets=[0.0])
-        for kern in ("warp", "thread", "group", "tiled", "pair"):
+        for kern in ("warp", "thread", "group", "tiled"):
             res = eng.evaluate(fr, 0, 55, seeds=seeds_d, targets=[0.0], kernel=kern)
             assert np.array_equal(res.collision.cpu().numpy().astype(bool), ref["collision"]), (delta, kern)
             assert res.best_idx == ref["best"]
@@ -375,7 +375,7 @@ def test_guard_band_decisions_near_the_curvature_limit():
         eng.set_refline(spline.s_list, spline.coefficient_table())
         o = cyc.obstacles
         eng.set_obstacles(o.state, o.valid, o.size, o.prob, o.n_dict)
-        for kern in ("warp", "thread", "group", "tiled", "pair"):
+        for kern in ("warp", "thread", "group", "tiled"):
             res = eng.evaluate(fr, 0, 100, seeds=seeds_d, targets=[0.0], kernel=kern)
             assert np.array_equal(res.feasible.cpu().numpy().astype(bool), ref["feasible"]), (eps, kern)
         flips.add(int(ref["feasible"].sum()))
