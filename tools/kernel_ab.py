@@ -8,8 +8,9 @@ import dlii_jssp_b200 as J
 name = sys.argv[1] if len(sys.argv) > 1 else "C3"
 kerns = sys.argv[2:] or ["tiled", "group", "thread"]
 cyc = bench.workload(name)
+div = int(os.environ.get("AB_SEEDS_DIV", "1"))          # a rank's share of the seeds (candidate split over `div` ranks)
 eng = bench.make_engine(J, cyc, len(cyc.seeds), 0)
-seeds = torch.from_numpy(cyc.seeds).cuda()
+seeds = torch.from_numpy(cyc.seeds[: len(cyc.seeds) // div].copy()).cuda()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for kern in kerns:
     for so in (False, True):
