@@ -597,6 +597,11 @@ __device__ __forceinline__ void lists_compact(const EvalParams& p, const ListsVi
     }
   }
   __syncthreads();
+#ifdef JSSP_PROFILE_PHASES
+  // profiling builds: slot 15 of the block's stamps = entries of the block's lists (bit 32 = overflow: the block falls back to full rows)
+  if (p.phase_ts && threadIdx.x == 0)
+    p.phase_ts[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + 15] = (unsigned long long)cursor[0] | ((unsigned long long)cursor[1] << 32);
+#endif
   tb.use_lists = cursor[1] == 0;
   tb.broad = p.broad; tb.broad_row0 = p.now; tb.broad_stride = p.check_res;   // fallback path
 }

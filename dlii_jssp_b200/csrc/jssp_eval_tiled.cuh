@@ -213,6 +213,9 @@ struct TileSink {
 
   // collision row of sample i (pose (x, y), heading of the segment (hdx, hdy)) - same semantics as collide_row
   __device__ __forceinline__ void collide(int i, double x, double y, double hdx, double hdy, float hqf) {
+#ifdef JSSP_KO_COLL
+    return;
+#endif
     if (i != next_check) return;                        // i % check_res == 0 without the division
     next_check += p.check_res;
     const int r = row++;
@@ -264,6 +267,9 @@ struct TileSink {
   // The same decision as curvature_fails_fast in straight-line form (no branch on the common path, so that the tests of two
   // consecutive segments overlap in the pipeline): 0 passes, 1 fails, 2 = re-decide with curvature_redecide.
   __device__ __forceinline__ int curvature_classify(double adx, double ady, float aqf, float adsf, double dx, double dy, float qf, float dsf) const {
+#ifdef JSSP_KO_CURV
+    return 0;
+#endif
     const float phif = (float)p.kmax * adsf;
     const bool rng = (aqf > 1e-16f && aqf < 1e30f) && (qf > 1e-16f && qf < 1e30f) && (phif < 0.49f);
     const double cross = fma(adx, dy, -(ady * dx)), dot = fma(adx, dx, ady * dy);
@@ -391,8 +397,6 @@ __device__ __forceinline__ void walk_tiles(const EvalParams& p, const BlockTable
       const int own = kChunked ? min(len, ck.own_hi - base) : len;
       for (int il = 0; il < own; ++il) { sa = sa + gterms[il * 3]; sj = sj + gterms[il * 3 + 1]; sv = sv + gterms[il * 3 + 2]; }
     }
-    if (t == 1) PHASE(p, 15);
-    if (t == 1) PHASE(p, 15);
     // phase 2: this lane's candidate - two samples per step where the tile has them (two independent dependency chains)
     if (walking) {
       int il = 0;
