@@ -526,6 +526,12 @@ def bench_split(ctx: Ctx, args, transport="auto") -> dict:
 # ------------------------------------------------------------------------------------------------------------------
 # sweep: C4 (800-scenario replay sweep) / C2 (8-scene demo) over the ranks
 # ------------------------------------------------------------------------------------------------------------------
+PIPELINES = {None: "lock-step device-resident replay: seed enumeration + exhaustive evaluation, two launches per plan cycle for the whole batch",
+             "persistent": "persistent replay kernel: one CTA per scenario loops over its plan cycles in one launch, exhaustive evaluation",
+             "bestfirst": "persistent replay kernel with best-first selection: one CTA per scenario loops over its plan cycles in one launch; "
+                          "candidates checked in the order of a lower bound of their cost until none left can win"}
+
+
 def bench_sweep(ctx: Ctx, args, workload_name="C4") -> dict:
     """BASELINE configs[3] ("C4": replay sweep over seeded synthetic intersections - the reference's scenes_all(800) archive is
     absent) and configs[1] ("C2": the bundled scene + 7 seeded variants with M = 3 predicted intention modes per vehicle - the
@@ -564,7 +570,15 @@ def bench_sweep(ctx: Ctx, args, workload_name="C4") -> dict:
         cfg = B.fop_batch_config(fop, float(e[5]), float(e[6]), max_seeds=1024, max_knots=cfg.max_knots, max_obstacle_modes=cfg.max_obstacle_modes,
                                  max_total_steps=cfg.max_total_steps)
         pts = float(np.mean([len(np.arange(0.0, T, fop.delta_t)) for T in np.linspace(fop.min_t, fop.max_t, fop.num_t)]))   # samples per candidate
-    k_sub = args.sub_batches if len(packed) >= 16 else 1
+    # default: ONE launch of the persistent replay kernel with best-first selection; the FOP baseline and
+    # --sweep-kernel lockstep run the lock-step pipeline (two launches per plan cycle, sub-batches on separate streams)
+    # --sweep-kernel auto (default): best-first when the rank holds more scenarios than the GPU has SMs (measured 32 vs 39 ms for 800
+    # scenarios on one B200), the lock-step pipeline otherwise (100 scenarios per GPU: 10.3 vs 10.5 ms; 8 multi-modal scenes: 8.3 vs 13 ms)
+    sweep_kernel = args.sweep_kernel
+    if sweep_kernel == "auto":
+        sweep_kernel = "bestfirst" if len(packed) > torch.cuda.get_device_properties(local).multi_processor_count else "lockstep"
+    kern = None if (fop is not None or sweep_kernel == "lockstep") else sweep_kernel
+    k_sub = (args.sub_batches if len(packed) >= 16 else 1) if kern is None else 1
     bt = B.MultiStreamReplay(cfg, device=local, max_scenarios=len(packed), max_cycles=args.cycles, k=k_sub, fop=fop)
     bt.load(packed)
     steps, warmup = max(3, min(args.steps, 10)), 3
@@ -572,21 +586,31 @@ def bench_sweep(ctx: Ctx, args, workload_name="C4") -> dict:
     sampler.start()
 
     def step():
-        bt.reset(); bt.run(args.cycles)
+        bt.reset(); bt.run(args.cycles, kernel=kern)
     l0 = bt.launch_count
     ms = ctx.timed(step, steps, warmup)
     launches = (bt.launch_count - l0) // (steps + warmup)
     total_ms = sum(ms)
     results = bt.results()
-    # the same sweep through the persistent replay kernel (one CTA per scenario, one launch per sub-batch): reported beside the default
-    persistent_ms = None
+    # the same sweep through the other replay pipelines, reported beside the default: the exhaustive lock-step pipeline (every candidate
+    # of every cycle walked; sub-batches on separate streams) and the persistent kernel without best-first selection
+    alternatives = {}
     if fop is None:
-        def pstep():
-            bt.reset(); bt.run(args.cycles, kernel="persistent")
-        pms = ctx.timed(pstep, 3, 2)
-        persistent_ms, = ctx.allmax(sum(pms) / len(pms))
-        pres = bt.results()
-        persistent_same = all((a.end, a.cycles, list(a.best_idx)) == (b.end, b.cycles, list(b.best_idx)) for a, b in zip(results, pres))
+        same = lambda a, b: all((x.end, x.cycles, list(x.best_idx)) == (y.end, y.cycles, list(y.best_idx)) for x, y in zip(a, b))
+        k_alt = args.sub_batches if len(packed) >= 16 else 1
+        bt2 = bt if k_alt == k_sub else B.MultiStreamReplay(cfg, device=local, max_scenarios=len(packed), max_cycles=args.cycles, k=k_alt)
+        if bt2 is not bt:
+            bt2.load(packed)
+        for name, (b_, k_) in {"lockstep": (bt2, None), "persistent": (bt, "persistent"), "bestfirst": (bt, "bestfirst")}.items():
+            if k_ == kern and b_ is bt:
+                continue
+            def astep(b_=b_, k_=k_):
+                b_.reset(); b_.run(args.cycles, kernel=k_)
+            ams = ctx.timed(astep, 3, 2)
+            a_ms, = ctx.allmax(sum(ams) / len(ams))
+            alternatives[name] = {"ms_per_step": a_ms, "same_rows_on_rank0": bool(same(results, b_.results())), "sub_batches": k_alt if b_ is bt2 else k_sub}
+        if bt2 is not bt:
+            bt2.close()
     units = sum(sum(r.n_candidates) for r in results) * pts
     flops = sum(sum(r.n_candidates) * pts * (F_BASE + F_SAT * p.state.shape[0] * p.state.shape[1] / 2.0) for r, p in zip(results, packed))
     cycles = sum(r.cycles for r in results)
@@ -597,7 +621,7 @@ def bench_sweep(ctx: Ctx, args, workload_name="C4") -> dict:
     for _ in range(max(2, min(steps, 5))):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        bt.load(packed); bt.run(args.cycles); bt.results(lists=False)      # records on the host as NumPy views
+        bt.load(packed); bt.run(args.cycles, kernel=kern); bt.results(lists=False)      # records on the host as NumPy views
         lat.append(time.perf_counter() - t0)
     e2e_s = statistics.median(lat)
     clocks = sampler.finish()
@@ -624,11 +648,13 @@ def bench_sweep(ctx: Ctx, args, workload_name="C4") -> dict:
                        "sweep_ms": 1e3 * e2e_max},
                "digest": D.sweep_digest(allrows), "end_status_counts": ends, "gpu_launches_per_step": int(launches),
                "scenarios_per_s": n_all / sweep_s, "cycles_per_s": cycles_all / sweep_s, "amortised_cycle_us": 1e6 * sweep_s * world / max(cycles_all, 1),
-               "parallelism": f"scenario shards over {world} ranks (lock-step device-resident replay, {k_sub} sub-batch(es) on separate streams per rank), no collective",
+               "parallelism": f"scenario shards over {world} ranks ({PIPELINES[kern]}, {k_sub} sub-batch(es) per rank), no collective",
+               "pipeline": kern or "lockstep",
                "algorithmic_tflops_per_gpu": flops_all / sweep_s / 1e12 / world, "fp32_fma_peak_tflops": peak32.value,
-               "persistent_kernel": None if persistent_ms is None else {"ms_per_step": persistent_ms, "same_rows_on_rank0": bool(persistent_same),
-                                     "note": "JSSP_FLAG_PERSISTENT: one CTA per scenario loops over its plan cycles in ONE launch; identical rows, slower "
-                                             "than the lock-step default on B200 (DESIGN.md 3.5)"},
+               "alternatives": alternatives,
+               "note": "value counts every candidate of every plan cycle (all of them are decided); the best-first pipeline walks only the candidates "
+                       "whose cost bound does not exceed the selected cost - same selection, rows and end status as the exhaustive lock-step "
+                       "pipeline (alternatives.lockstep; digest equal)" if kern == "bestfirst" else None,
                "clocks": clocks}
     bt.close()
     return out
@@ -729,6 +755,7 @@ def main():
     ap.add_argument("--scenarios", type=int, default=800, help="C4: number of synthetic scenarios in the sweep")
     ap.add_argument("--cycles", type=int, default=100, help="C4: plan cycles per scenario (upper bound)")
     ap.add_argument("--sub-batches", type=int, default=2, help="C4/C2 lock-step replay: sub-batches per rank, each on its own CUDA stream")
+    ap.add_argument("--sweep-kernel", default="auto", choices=["auto", "bestfirst", "lockstep", "persistent"], help="C4/C2: replay pipeline (same results)")
     ap.add_argument("--planner", default="JSSP", choices=["JSSP", "frenet"], help="C4: planner of the replay (frenet = the FOP baseline)")
     ap.add_argument("--transport", default="auto", choices=["auto", "peer", "nccl"], help="C5: argmin exchange transport")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")

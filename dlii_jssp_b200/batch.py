@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import JsspError, JsspCycleRecord, JsspFopIn, JsspScenarioIn, JsspScenarioResult, FLAG_FORCE_THREAD, FLAG_FORCE_WARP, FLAG_FORCE_GROUP, FLAG_FORCE_TILED, FLAG_LOCKSTEP, FLAG_PERSISTENT, FLAG_CHUNKED
+from ._lib import JsspError, JsspCycleRecord, JsspFopIn, JsspScenarioIn, JsspScenarioResult, FLAG_FORCE_THREAD, FLAG_FORCE_WARP, FLAG_FORCE_GROUP, FLAG_FORCE_TILED, FLAG_LOCKSTEP, FLAG_PERSISTENT, FLAG_CHUNKED, FLAG_BEST_FIRST
 from .engine import JsspConfig
 from .frenet import FrenetState, State
 from .geometry import CubicSpline2D
@@ -268,10 +268,11 @@ class BatchReplay:
         """Enqueue up to ``n_cycles`` plan cycles per scenario (default: enough for every loaded scenario to finish).  ``kernel``
         None / "lockstep" = the lock-step pipeline (two launches per cycle for the whole batch) with its default evaluation
         kernel, "warp" / "thread" / "group" / "tiled" = lock-step with that kernel, "persistent" = the persistent replay kernel
-        (one CTA per scenario loops over its own cycles in ONE launch).  Same results.  Asynchronous."""
+        (one CTA per scenario loops over its own cycles in ONE launch), "bestfirst" = the persistent kernel with best-first selection
+        (candidates checked in the order of a lower bound of their cost until none left can win).  Same results.  Asynchronous."""
         if n_cycles is None:
             n_cycles = max(min(p.n_cycles, self.C) for p in self._packed)
-        flags = {None: 0, "warp": FLAG_FORCE_WARP, "thread": FLAG_FORCE_THREAD, "group": FLAG_FORCE_GROUP, "tiled": FLAG_FORCE_TILED, "lockstep": FLAG_LOCKSTEP, "persistent": FLAG_PERSISTENT, "chunked": FLAG_CHUNKED}[kernel]
+        flags = {None: 0, "warp": FLAG_FORCE_WARP, "thread": FLAG_FORCE_THREAD, "group": FLAG_FORCE_GROUP, "tiled": FLAG_FORCE_TILED, "lockstep": FLAG_LOCKSTEP, "persistent": FLAG_PERSISTENT, "chunked": FLAG_CHUNKED, "bestfirst": FLAG_BEST_FIRST}[kernel]
         self._check(self.lib.jssp_batch_run(self._h, self._n, int(n_cycles), flags, self.stream), "jssp_batch_run")
         return n_cycles
 

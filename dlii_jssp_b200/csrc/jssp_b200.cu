@@ -1351,6 +1351,7 @@ int32_t jssp_batch_create(const jssp_config* cfg, int32_t device, int32_t max_sc
   CKC(allow_max_dynamic_smem(evaluate_group_batch_kernel<1>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(replay_persistent_kernel<512>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(replay_persistent_kernel<1024>, optin, &b->max_smem_optin));
+  CKC(allow_max_dynamic_smem(replay_persistent_kernel<512, true>, optin, &b->max_smem_optin));
   CKC(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device));
   CKC(allow_max_dynamic_smem(evaluate_tiled_batch_kernel<0>, optin, &b->max_smem_optin));
   CKC(allow_max_dynamic_smem(evaluate_tiled_batch_kernel<1>, optin, &b->max_smem_optin));
@@ -1638,32 +1639,57 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   const int max_rows = (b->P + b->cfg.check_res - 1) / b->cfg.check_res;
   // JSSP_FLAG_PERSISTENT: the persistent replay kernel - one CTA per scenario, every cycle of the call in ONE launch.  Few scenarios
   // (at most one per SM) get 512 threads each, more get 256 so that two CTAs share an SM.
-  if ((flags & JSSP_FLAG_PERSISTENT) && !(flags & JSSP_FLAG_LOCKSTEP)) {
+  // JSSP_FLAG_BEST_FIRST on a batch whose every cycle qualifies (select-only slots, w_risk >= 0): the kernel variant without the
+  // exhaustive passes - 512 threads per CTA when every scenario has an SM of its own, else 256-thread CTAs, two per SM
+  if ((flags & JSSP_FLAG_BEST_FIRST) && !(flags & JSSP_FLAG_LOCKSTEP) && !b->tune.full_walk && b->cfg.w_risk >= 0.0) {
+    int threads = n_scenarios <= b->sm_count ? REPLAY_MAX_THREADS : 256;
+    if (b->tune.seed_threads == 256 || b->tune.seed_threads == 512) threads = b->tune.seed_threads;      // tools/ only
+    const int rows = b->max_OMpad > 0 ? max_rows : 0;
+    const int bf_keys = b->cfg.max_seeds * b->W;
+    ReplaySmem RL = replay_smem_layout(b->max_kpad, b->P, b->W, rows, b->max_OMpad, b->seed_smem, threads, -1, bf_keys);
+    if (RL.total > (size_t)b->max_smem_optin && threads > 256) {
+      threads = 256;
+      RL = replay_smem_layout(b->max_kpad, b->P, b->W, rows, b->max_OMpad, b->seed_smem, threads, -1, bf_keys);
+    }
+    if (RL.total <= (size_t)b->max_smem_optin) {
+      if (n_cycles > 0) {
+        replay_persistent_kernel<512, true><<<dim3((unsigned)n_scenarios, 1, 1), threads, RL.total, st>>>(b->grids, b->d_slots, b->seed_work, n_cycles, rows, b->max_OMpad, b->max_kpad, -1, bf_keys);
+        b->launches += 1;
+        CKB(cudaGetLastError());
+      }
+      return JSSP_OK;
+    }
+  }
+  if ((flags & (JSSP_FLAG_PERSISTENT | JSSP_FLAG_BEST_FIRST)) && !(flags & JSSP_FLAG_LOCKSTEP)) {
     int threads = n_scenarios <= b->sm_count ? REPLAY_MAX_THREADS : 256;
     if (b->tune.seed_threads == 256 || b->tune.seed_threads == 512 || b->tune.seed_threads == 1024) threads = b->tune.seed_threads;      // tools/ only
     const int rows = b->max_OMpad > 0 ? max_rows : 0;
     // tile length: the default (~16 samples), shortened until the warps' tiles fit next to the tables
     int tile_rounds = 0;
-    ReplaySmem RL = replay_smem_layout(b->max_kpad, b->P, b->W, rows, b->max_OMpad, b->seed_smem, threads, tile_rounds);
+    // JSSP_FLAG_BEST_FIRST: best-first selection inside the persistent kernel (jssp_bestfirst.cuh); its keys and per-warp scratch share
+    // the region of the tiles, which then only serve cycles the best-first rule does not cover and may be as short as needed
+    const int bf_keys = (flags & JSSP_FLAG_BEST_FIRST) ? b->cfg.max_seeds * b->W : 0;
+    auto layout = [&](int thr, int tr) { return replay_smem_layout(b->max_kpad, b->P, b->W, rows, b->max_OMpad, b->seed_smem, thr, tr, bf_keys); };
+    ReplaySmem RL = layout(threads, tile_rounds);
     // persistent kernel: as long a tile as fits (<= ~16 samples); with 256-thread CTAs two of them share an SM
     const size_t budget = threads <= 256 ? std::min((size_t)b->max_smem_optin, (size_t)(228 * 1024 / 2 - 10 * 1024)) : (size_t)b->max_smem_optin;
-    for (int r = tile_rounds_wanted(b->W); r >= 1; --r) {
+    for (int r = bf_keys > 0 ? 1 : tile_rounds_wanted(b->W); r >= 1; --r) {
       tile_rounds = r;
-      RL = replay_smem_layout(b->max_kpad, b->P, b->W, rows, b->max_OMpad, b->seed_smem, threads, tile_rounds);
+      RL = layout(threads, tile_rounds);
       if (RL.total <= budget) break;
     }
     for (int r = tile_rounds - 1; RL.total > (size_t)b->max_smem_optin && r >= 1; --r) {
       tile_rounds = r;
-      RL = replay_smem_layout(b->max_kpad, b->P, b->W, rows, b->max_OMpad, b->seed_smem, threads, tile_rounds);
+      RL = layout(threads, tile_rounds);
     }
     if (RL.total > (size_t)b->max_smem_optin && threads > 256) {
-      threads = 256; tile_rounds = 0;
-      RL = replay_smem_layout(b->max_kpad, b->P, b->W, rows, b->max_OMpad, b->seed_smem, threads, tile_rounds);
+      threads = 256; tile_rounds = bf_keys > 0 ? 1 : 0;
+      RL = layout(threads, tile_rounds);
     }
     if (RL.total <= (size_t)b->max_smem_optin) {
       if (n_cycles > 0) {
-        if (threads > 512) replay_persistent_kernel<1024><<<dim3((unsigned)n_scenarios, 1, 1), threads, RL.total, st>>>(b->grids, b->d_slots, b->seed_work, n_cycles, rows, b->max_OMpad, b->max_kpad, tile_rounds);
-        else replay_persistent_kernel<512><<<dim3((unsigned)n_scenarios, 1, 1), threads, RL.total, st>>>(b->grids, b->d_slots, b->seed_work, n_cycles, rows, b->max_OMpad, b->max_kpad, tile_rounds);
+        if (threads > 512) replay_persistent_kernel<1024><<<dim3((unsigned)n_scenarios, 1, 1), threads, RL.total, st>>>(b->grids, b->d_slots, b->seed_work, n_cycles, rows, b->max_OMpad, b->max_kpad, tile_rounds, bf_keys);
+        else replay_persistent_kernel<512><<<dim3((unsigned)n_scenarios, 1, 1), threads, RL.total, st>>>(b->grids, b->d_slots, b->seed_work, n_cycles, rows, b->max_OMpad, b->max_kpad, tile_rounds, bf_keys);
         b->launches += 1;
         CKB(cudaGetLastError());
       }
@@ -1758,6 +1784,7 @@ int32_t jssp_batch_best_traj(jssp_batch* b, int32_t slot, double* out, void* str
 #ifdef JSSP_PROFILE_PHASES
 /* persistent replay kernel: per-stage nanoseconds of scenario 0 (see jssp_replay.cuh) */
 int32_t jssp_debug_replay_phases(unsigned long long* host8) { return cudaMemcpyFromSymbol(host8, g_replay_ns, sizeof(g_replay_ns)) == cudaSuccess ? JSSP_OK : JSSP_ERR_CUDA; }
+int32_t jssp_debug_bestfirst(unsigned long long* host8) { return cudaMemcpyFromSymbol(host8, g_bestfirst_ns, sizeof(g_bestfirst_ns)) == cudaSuccess ? JSSP_OK : JSSP_ERR_CUDA; }
 /* same for the batched replay (tools/batch_phase_probe.py): [scenarios * blocks][8]; call before jssp_batch_set_scenario */
 int32_t jssp_batch_debug_phase_buffer(jssp_batch* b, unsigned long long* dev) { if (!b) return JSSP_ERR_INVALID_ARG; b->phase_ts = dev; return JSSP_OK; }
 #endif

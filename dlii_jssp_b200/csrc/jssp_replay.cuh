@@ -18,6 +18,7 @@
 // warps' tiles) share one region.
 #pragma once
 #include "jssp_eval_tiled.cuh"
+#include "jssp_bestfirst.cuh"
 
 namespace jssp {
 
@@ -27,6 +28,7 @@ constexpr int REPLAY_MAX_THREADS = 512;
 // profiling builds only (tools/replay_phase_probe.py): nanoseconds scenario 0 spent in each stage, summed over its cycles:
 // 0 slot load, 1 seed enumeration, 2 staging, 3 tiled evaluation, 4 selection + export + hand-off, 5 cycles, 6 passes
 __device__ unsigned long long g_replay_ns[8];
+__device__ unsigned long long g_bestfirst_ns[8];      // best-first cycles of scenario 0: ns in the keys stage, rounds, checks of warp 0
 #define RSTAMP(k) do { __syncthreads(); if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
                         g_replay_ns[k] += t_ - t_prev; t_prev = t_; } } while (0)
 #else
@@ -36,12 +38,13 @@ __device__ unsigned long long g_replay_ns[8];
 struct ReplaySmem {
   size_t off_knot, off_coef, off_time, off_union;       // resident part
   size_t off_lat, off_latcost, off_window, off_tile;    // evaluation view of the union
+  BestFirstSmem bf;                                     // best-first evaluation: replaces the tiles (offsets from the start of the block's shared memory)
   size_t total;
 };
 // sized by the host for the LARGEST scenario of the batch (K, kpad, OMpad, rows) and evaluated by a CTA for its own scenario:
 // a scenario's view never exceeds the launch's
 __host__ __device__ inline ReplaySmem replay_smem_layout(int kpad, int P, int W, int win_rows, int OMpad, size_t seed_bytes, int threads,
-                                                         int tile_rounds = 0) {
+                                                         int tile_rounds = 0, int bf_keys = 0) {
   ReplaySmem L;
   size_t o = 16;                                         // mbarrier
   L.off_knot = o; o += (size_t)kpad * 8;
@@ -54,7 +57,11 @@ __host__ __device__ inline ReplaySmem replay_smem_layout(int kpad, int P, int W,
   L.off_latcost = e; e += (size_t)W * 4 * 8;
   L.off_window = e; e += (size_t)win_rows * OMpad * 16;
   e = (e + 15) & ~(size_t)15;
-  L.off_tile = e; e += tile_scratch_bytes(W, threads, tile_rounds);
+  L.off_tile = e;
+  L.bf = BestFirstSmem{0, 0, 0, 0};
+  if (bf_keys > 0) L.bf = bestfirst_layout(e, P, bf_keys, threads);          // shares the region with the tiles (a cycle uses one of them)
+  if (tile_rounds >= 0) e += tile_scratch_bytes(W, threads, tile_rounds);      // tile_rounds < 0: best-first only, no tiles
+  if (L.bf.total > e) e = L.bf.total;
   const size_t s = o + ((seed_bytes + 15) & ~(size_t)15);
   L.total = e > s ? e : s;
   return L;
@@ -94,9 +101,11 @@ __device__ __forceinline__ void replay_select_export(const EvalParams& p, BlockT
   batch_handoff(p, best, N, sm_npts);
 }
 
-template <int kMaxThreads>
+// kBestFirstOnly: every cycle of the launch is selected best-first (the host has checked the conditions) and the exhaustive tiled
+// passes are not compiled in - the kernel then fits more threads per CTA (768) or more CTAs per SM.
+template <int kMaxThreads, bool kBestFirstOnly = false>
 __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedGrids g, const EvalParams* __restrict__ slots, SeedWork wk,
-                                                                                   int n_cycles, int max_rows, int max_OMpad, int max_kpad, int tile_rounds) {
+                                                                                   int n_cycles, int max_rows, int max_OMpad, int max_kpad, int tile_rounds, int bf_keys) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(16) EvalParams sp;
   __shared__ double red_cost[kMaxThreads / 32];
@@ -108,7 +117,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
   const int lane = tid & 31, wid = tid >> 5, nwarps = nt >> 5;
   load_slot(&sp, slots + sc);
   // the launch's layout (the union must start where the largest scenario's resident part ends)
-  const ReplaySmem L = replay_smem_layout(max_kpad, sp.P, sp.W, max_rows, max_OMpad, seed_smem_bytes(wk), nt, tile_rounds);
+  const ReplaySmem L = replay_smem_layout(max_kpad, sp.P, sp.W, max_rows, max_OMpad, seed_smem_bytes(wk), nt, tile_rounds, bf_keys);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   double* sm_knot = reinterpret_cast<double*>(smem + L.off_knot);
   double* sm_coef = reinterpret_cast<double*>(smem + L.off_coef);
@@ -144,7 +153,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
 
 #ifdef JSSP_PROFILE_PHASES
   unsigned long long t_prev = 0;
-  if (blockIdx.x == 0 && threadIdx.x == 0) { for (int q = 0; q < 8; ++q) g_replay_ns[q] = 0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_prev)); }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { for (int q = 0; q < 8; ++q) g_replay_ns[q] = 0; for (int q = 0; q < 8; ++q) g_bestfirst_ns[q] = 0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_prev)); }
 #endif
   for (int c = 0; c < n_cycles; ++c) {
     if (c > 0) load_slot(&sp, slots + sc);                // the hand-off wrote the next cycle's inputs into the slot record
@@ -161,13 +170,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
     // -- K2: evaluation ---------------------------------------------------------------------------------------------------
     const int Ns = min(__ldcg(counts + 2), sp.seed_cap);
     const int N = Ns * W;
-    // obstacle window of the cycle: rows now, now + check_res, ... of the broad-phase table (absent rows = far away)
+    // best-first selection (JSSP_FLAG_BEST_FIRST): nobody reads per-candidate results and the risk term can only add to a cost
+    const bool best_first = kBestFirstOnly || (bf_keys > 0 && N <= bf_keys && sp.select_only && !sp.feasible && !sp.collision && !sp.cost && sp.w_risk >= 0.0);
+    // obstacle window of the cycle: rows now, now + check_res, ... of the broad-phase table (absent rows = far away); transposed
+    // ([OMpad][win_rows]) for the best-first checks, whose lanes own consecutive rows
     {
       const int n_el = sp.win_rows * sp.OMpad;
       for (int e = tid; e < n_el; e += nt) {
         const int r = e / sp.OMpad, o = e - r * sp.OMpad;
         const int step = sp.now + r * sp.check_res;
-        sm_win[e] = step < sp.Tt ? sp.broad[(size_t)step * sp.OMpad + o] : make_float4(0.f, 0.f, FAR_AWAY, 0.f);
+        sm_win[best_first ? o * sp.win_rows + r : e] = step < sp.Tt ? sp.broad[(size_t)step * sp.OMpad + o] : make_float4(0.f, 0.f, FAR_AWAY, 0.f);
       }
     }
     stage_lateral(sp, sm_time, sm_lat, sm_latcost);       // ends with a block barrier
@@ -182,7 +194,17 @@ __global__ void __launch_bounds__(kMaxThreads, 1) replay_persistent_kernel(SeedG
     double my_cost = INFINITY;
     int my_idx = -1;
     RSTAMP(2);
-    for (int base = 0; base < Ns; base += spb) {           // block-uniform trip count
+    if (best_first) {
+      double bc; int bi;
+#ifdef JSSP_PROFILE_PHASES
+      bestfirst_select(sp, tb, latcost, seeds, Ns, sm_win, sp.win_rows, smem, L.bf, bc, bi, blockIdx.x == 0 ? g_bestfirst_ns : nullptr);
+#else
+      bestfirst_select(sp, tb, latcost, seeds, Ns, sm_win, sp.win_rows, smem, L.bf, bc, bi);
+#endif
+      if (tid == 0) { my_cost = bc; my_idx = bi; }
+    }
+    if (!kBestFirstOnly)
+    for (int base = best_first ? Ns : 0; base < Ns; base += spb) {           // block-uniform trip count
       const int k = base + wid * tg.gpw + g_;
       const bool active = g_ < tg.gpw && k < Ns;
       if (active && j == 0) tile_profile_store(prof, seeds + (size_t)k * 10, sp.s0, sp.v0, sp.a0);

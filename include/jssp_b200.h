@@ -107,6 +107,10 @@ typedef struct jssp_cycle_in {
 #define JSSP_FLAG_CHUNKED 1024    /* jssp_batch_run only: the chunked tiled kernel - two lane groups per seed split the horizon, the halves are
                                     combined in time order with the serial walk's semantics (same selection and rows); chosen automatically
                                     when the batch leaves the GPU half empty (JSSP_FLAG_FORCE_TILED keeps the whole-horizon walk) */
+#define JSSP_FLAG_BEST_FIRST 2048 /* jssp_batch_run only: the persistent replay kernel with BEST-FIRST selection - a cycle's candidates are ordered by a
+                                    lower bound of their cost (everything but the risk term, which needs no walk) and checked in that order, one
+                                    warp per candidate with the lanes over the samples, until no unchecked candidate can cost less than the best
+                                    survivor: the selection, its cost and the exported trajectory are those of the exhaustive evaluation */
 #define JSSP_FLAG_NO_CULL 4      /* test every obstacle state instead of the per-block culled lists (same results) */
 
 /* Outputs.  Candidate n = w * n_seeds + k (width-major, jssp.py:106,124-125).  All dev pointers may be NULL.  With

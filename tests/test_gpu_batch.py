@@ -30,7 +30,7 @@ def test_batch_matches_single_scenario_replays(scenario_fixture):
     assert any(g.end in (1, 1.5, 2) for g in got)           # at least one scenario ran to a real end status
 
 
-@pytest.mark.parametrize("kernel", [None, "persistent", "warp", "thread", "group", "tiled", "chunked"])
+@pytest.mark.parametrize("kernel", [None, "persistent", "bestfirst", "warp", "thread", "group", "tiled", "chunked"])
 def test_batch_kernels_agree_with_oracle_replay(kernel):
     scs = [S.synthetic_intersection(i) for i in (3, 4)]
     got = B.run_batch(scs, max_cycles=20, kernel=kernel)
@@ -102,6 +102,10 @@ def test_c2_multimodal_predictions_batch_matches_oracle(scenario_fixture):
         np.testing.assert_allclose(np.array(g.ego_rows), np.array(cpu["rows"]), rtol=1e-9, atol=1e-9)
         differs |= g.best_idx != R.run_replay(sc, max_cycles=18).best_idx
     assert differs                   # the predicted modes change at least one selection w.r.t. the ground-truth-only replay
+    # best-first selection with soft hits in play (modes below p_min add w_risk * prob to a survivor's cost: the bound leaves the
+    # risk term out, the exact cost adds it in the serial walk's order): the same replay
+    for a, b in zip(got, B.run_batch(packed, max_cycles=18, batch=bt, kernel="bestfirst")):
+        _same(a, b)
     bt.close()
 
 
@@ -152,18 +156,20 @@ def test_sub_batches_on_separate_streams_replay_identically(scenario_fixture):
     one.close()
 
 
-def test_persistent_and_lockstep_replays_are_identical(scenario_fixture):
-    """The persistent replay kernel (one CTA per scenario loops over its plan cycles in one launch) and the lock-step pipeline
+@pytest.mark.parametrize("kernel", ["persistent", "bestfirst"])
+def test_persistent_and_lockstep_replays_are_identical(scenario_fixture, kernel):
+    """("bestfirst" = the persistent kernel with best-first selection: candidates checked in the order of a lower bound of their cost.)
+    The persistent replay kernel (one CTA per scenario loops over its plan cycles in one launch) and the lock-step pipeline
     (two launches per cycle for the whole batch; the default) produce the same records, cycle by cycle, for a mixed batch: bundled
     scene, synthetic intersections with 3..12 vehicles, an obstacle-free scenario - with 256 and (few scenarios) 512 threads."""
     scs = [scenario_fixture] + [S.synthetic_intersection(i) for i in range(20, 31)]
     empty = S.synthetic_intersection(9)
     empty.vehicle_traj = {}
     scs.append(empty)
-    a = B.run_batch(scs, max_cycles=60, kernel="persistent")
+    a = B.run_batch(scs, max_cycles=60, kernel=kernel)
     b = B.run_batch(scs, max_cycles=60)
     for x, y in zip(a, b):
         _same(x, y)
     many = [S.synthetic_intersection(i) for i in range(100, 260)]         # > 148 scenarios: 256-thread CTAs, several per SM
-    for x, y in zip(B.run_batch(many, max_cycles=25, kernel="persistent"), B.run_batch(many, max_cycles=25)):
+    for x, y in zip(B.run_batch(many, max_cycles=25, kernel=kernel), B.run_batch(many, max_cycles=25)):
         _same(x, y)

@@ -102,8 +102,9 @@ def test_sweep_sample_matches_oracle_replay_golden():
     scs = [S.synthetic_intersection(i) for i in ids]
     got = B.run_batch(scs, max_cycles=C)
     assert len(got) >= 32
-    for a, b in zip(got, B.run_batch(scs, max_cycles=C, kernel="persistent")):     # the persistent replay kernel: the same rows
-        assert (a.end, a.cycles, list(a.best_idx), list(a.n_candidates), a.ego_rows) == (b.end, b.cycles, list(b.best_idx), list(b.n_candidates), b.ego_rows)
+    for kernel in ("persistent", "bestfirst"):       # the persistent replay kernel, exhaustive and with best-first selection: the same rows
+        for a, b in zip(got, B.run_batch(scs, max_cycles=C, kernel=kernel)):
+            assert (a.end, a.cycles, list(a.best_idx), list(a.n_candidates), a.ego_rows) == (b.end, b.cycles, list(b.best_idx), list(b.n_candidates), b.ego_rows), kernel
     for k, r in enumerate(got):
         c = int(g["cycles"][k])
         assert (r.end, r.cycles) == (float(g["end"][k]), c), (ids[k], r.end, r.cycles, g["end"][k], c)
