@@ -242,10 +242,18 @@ __device__ __forceinline__ void seed_enum_body(const SeedGrids& g, const SeedSta
       const double t1 = g.ts[A.i1];
       const double s1 = A.s, v1 = A.v, a1 = A.a;
       const float a1f = (float)a1, v1f = (float)v1;
+      // The j2 > 0 that pass the band test below form an INTERVAL: v* = v1 - h / j2 (h = a1^2 / 2) lies in [-0.32 - 0.045 / j2, 0.02]
+      // <=>  (h - 0.045) / (v1 + 0.32) <= j2 <= h / (v1 - 0.02)  (the right bound only for v1 > 0.02, the left only for h > 0.045;
+      // v1 >= -1e-9 after check_state).  Two compares (with fp32 slack) skip the other j2 before any arithmetic.
+      const float hq = 0.5f * a1f * a1f;
+      float j2_lo = 0.f, j2_hi = 3.0e38f;
+      if (v1f > 0.02f) j2_hi = hq / (v1f - 0.02f) * 1.001f + 1e-3f;
+      if (hq > 0.045f && v1f > -0.3f) j2_lo = (hq - 0.045f) / (v1f + 0.32f) * 0.999f - 1e-3f;
       for (int ij2 = j_first; ij2 < g.n_jpos; ij2 += j_step) {
         const double j2 = g.jpos[ij2];
         int lo = 0, hi = g.n_ts - 1;
         if (j2 > 1e-6 && dt_s > 0.f) {
+          if ((float)j2 > j2_hi || (float)j2 < j2_lo) continue;
           // inside the bracket v2 lies in [v*, v* + 0.045 / j2] with v* = v1 - a1^2 / (2 j2), the minimum of v2 (reached
           // where a2 = 0): unless that band meets -0.3 <= v2 <= 0 (2 cm/s of slack for fp32) no t2 can pass - most pairs
           const float rj = __fdividef(1.0f, (float)j2);

@@ -15,4 +15,9 @@ timeout 300 python bench.py $ARGS > gpurun_out/${tag}_c3_plain.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_c3.csv python bench.py $ARGS > gpurun_out/${tag}_ncu1.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:evaluate_tiled_kernel -s 6 -c 1 -f -o gpurun_out/${tag}_tiled python bench.py $ARGS > gpurun_out/${tag}_ncu2.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:dump_states_kernel -s 2 -c 1 -f -o gpurun_out/${tag}_dump python bench.py $ARGS > gpurun_out/${tag}_ncu3.log 2>&1
+# the sweep's replay kernel (best-first persistent kernel, one launch per sweep): launch list + one full capture
+SW="--workload C4 --steps 3 --warmup 3 --no-cpu"
+timeout 600 python bench.py $SW > gpurun_out/${tag}_c4_plain.log 2>&1 &&
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${tag}_launches_c4.csv python bench.py $SW > gpurun_out/${tag}_ncu4.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:replay_persistent_kernel -s 3 -c 1 -f -o gpurun_out/${tag}_replay python bench.py $SW > gpurun_out/${tag}_ncu5.log 2>&1
 ls -la gpurun_out | tail -14
