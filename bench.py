@@ -528,7 +528,7 @@ def bench_split(ctx: Ctx, args, transport="auto") -> dict:
 # ------------------------------------------------------------------------------------------------------------------
 PIPELINES = {None: "lock-step device-resident replay: seed enumeration + exhaustive evaluation, two launches per plan cycle for the whole batch",
              "persistent": "persistent replay kernel: one CTA per scenario loops over its plan cycles in one launch, exhaustive evaluation",
-             "bestfirst": "persistent replay kernel with best-first selection: one CTA per scenario loops over its plan cycles in one launch; "
+             "bestfirst": "persistent replay kernel with best-first selection: one CTA per scenario loops over its plan cycles, one launch per sub-batch; "
                           "candidates checked in the order of a lower bound of their cost until none left can win"}
 
 
@@ -570,15 +570,19 @@ def bench_sweep(ctx: Ctx, args, workload_name="C4") -> dict:
         cfg = B.fop_batch_config(fop, float(e[5]), float(e[6]), max_seeds=1024, max_knots=cfg.max_knots, max_obstacle_modes=cfg.max_obstacle_modes,
                                  max_total_steps=cfg.max_total_steps)
         pts = float(np.mean([len(np.arange(0.0, T, fop.delta_t)) for T in np.linspace(fop.min_t, fop.max_t, fop.num_t)]))   # samples per candidate
-    # default: ONE launch of the persistent replay kernel with best-first selection; the FOP baseline and
-    # --sweep-kernel lockstep run the lock-step pipeline (two launches per plan cycle, sub-batches on separate streams)
-    # --sweep-kernel auto (default): best-first when the rank holds more scenarios than the GPU has SMs (measured 32 vs 39 ms for 800
-    # scenarios on one B200), the lock-step pipeline otherwise (100 scenarios per GPU: 10.3 vs 10.5 ms; 8 multi-modal scenes: 8.3 vs 13 ms)
+    # the FOP baseline and --sweep-kernel lockstep run the lock-step pipeline (two launches per plan cycle, sub-batches on separate streams);
+    # --sweep-kernel auto (default): the persistent kernel with best-first selection for shards of 64 scenarios and more (measured on
+    # one B200: 800 scenarios 25 - 28 vs 39 ms, 100 scenarios 10.0 vs 10.3 ms), the lock-step pipeline for small batches (8 multi-modal
+    # scenes: 8.3 vs 13 ms).  Best-first sub-batches hold ~200 scenarios each (one launch per sub-batch, each on its own stream):
+    # their CTAs interleave on the SMs and, end to end, the replay of one sub-batch overlaps the upload of the next.
     sweep_kernel = args.sweep_kernel
     if sweep_kernel == "auto":
-        sweep_kernel = "bestfirst" if len(packed) > torch.cuda.get_device_properties(local).multi_processor_count else "lockstep"
+        sweep_kernel = "bestfirst" if len(packed) >= 64 else "lockstep"
     kern = None if (fop is not None or sweep_kernel == "lockstep") else sweep_kernel
-    k_sub = (args.sub_batches if len(packed) >= 16 else 1) if kern is None else 1
+    if kern is None:
+        k_sub = args.sub_batches if len(packed) >= 16 else 1
+    else:
+        k_sub = max(1, min(8, int(round(len(packed) / 200.0))))
     bt = B.MultiStreamReplay(cfg, device=local, max_scenarios=len(packed), max_cycles=args.cycles, k=k_sub, fop=fop)
     bt.load(packed)
     steps, warmup = max(3, min(args.steps, 10)), 3
@@ -621,7 +625,7 @@ def bench_sweep(ctx: Ctx, args, workload_name="C4") -> dict:
     for _ in range(max(2, min(steps, 5))):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        bt.load(packed); bt.run(args.cycles, kernel=kern); bt.results(lists=False)      # records on the host as NumPy views
+        bt.load_and_run(packed, args.cycles, kernel=kern); bt.results(lists=False)      # records on the host as NumPy views
         lat.append(time.perf_counter() - t0)
     e2e_s = statistics.median(lat)
     clocks = sampler.finish()

@@ -357,6 +357,23 @@ class MultiStreamReplay:
     def run(self, n_cycles: Optional[int] = None, kernel: Optional[str] = None):
         return max(self._each(lambda bt: bt.run(n_cycles, kernel=kernel)))
 
+    def load_and_run(self, packed: Sequence[PackedScenario], n_cycles: Optional[int] = None, kernel: Optional[str] = None):
+        """``load`` + ``run`` sub-batch by sub-batch: the replay of one sub-batch (device) overlaps the upload of the next (host staging +
+        H2D copies), so an end-to-end sweep costs about max(upload, replay) instead of their sum."""
+        self._n = len(packed)
+        groups = [list(packed[i::self.k]) for i in range(self.k)]
+        cur = torch.cuda.current_stream(self.device)
+        out = [0]
+        for bt, st, g in zip(self.parts, self.streams, groups):
+            if g:
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    bt.load(g)
+                    out.append(bt.run(n_cycles, kernel=kernel))
+        for st in self.streams:
+            cur.wait_stream(st)
+        return max(out)
+
     def results(self, lists: bool = True) -> List[ReplayResult]:
         parts = self._each(lambda bt: bt.results(lists=lists))
         out: List[Optional[ReplayResult]] = [None] * self._n

@@ -193,6 +193,15 @@ cudaError_t upload_grids(const jssp_config* cfg, double** dst[10], SeedGrids* sg
   sg.n_t3 = (int)g.t3.size(); sg.n_t4 = (int)g.t4.size();
   sg.jneg = *dst[7]; sg.jpos = *dst[8]; sg.ts = *dst[9];
   sg.n_jneg = (int)jneg.size(); sg.n_jpos = (int)jpos.size(); sg.n_ts = (int)g.ts.size();
+  sg.jpos_uniform = jpos.size() >= 2 ? 1 : 0;
+  sg.jpos0 = jpos.empty() ? 0.f : (float)jpos[0];
+  sg.jpos_inv_step = 0.f;
+  if (sg.jpos_uniform) {
+    const double step = jpos[1] - jpos[0];
+    for (size_t k = 1; k + 1 < jpos.size(); ++k)
+      if (!(step > 0) || std::fabs((jpos[k + 1] - jpos[k]) - step) > 1e-9 * std::fabs(step)) sg.jpos_uniform = 0;
+    if (sg.jpos_uniform) sg.jpos_inv_step = (float)(1.0 / step);
+  }
   sg.total_time = cfg->plan_horizon;
   sg.acc_max = cfg->lon_accel_max - 1e-9; sg.vel_max = cfg->speed_max - 1e-9; sg.v_max = cfg->speed_max;
   sg.jmin5 = -cfg->highest_jerk * 0.3; sg.jmax5 = cfg->highest_jerk * 0.3;

@@ -15,6 +15,8 @@ struct SeedGrids {
   int n_jneg, n_jpos, n_ts;
   double total_time, acc_max, vel_max, v_max, jmin5, jmax5;
   double lim2, lim3, lim4;                    // total - 0.8*3, total - 1.0*2, total - 1.5 (host-computed, same ops)
+  int jpos_uniform;                           // jpos is an arithmetic progression (np.linspace): an interval of j2 values is an index range
+  float jpos0, jpos_inv_step;
 };
 
 struct SeedState { double s0, v0, a0; };
@@ -249,7 +251,15 @@ __device__ __forceinline__ void seed_enum_body(const SeedGrids& g, const SeedSta
       float j2_lo = 0.f, j2_hi = 3.0e38f;
       if (v1f > 0.02f) j2_hi = hq / (v1f - 0.02f) * 1.001f + 1e-3f;
       if (hq > 0.045f && v1f > -0.3f) j2_lo = (hq - 0.045f) / (v1f + 0.32f) * 0.999f - 1e-3f;
-      for (int ij2 = j_first; ij2 < g.n_jpos; ij2 += j_step) {
+      // on the uniform grid the interval is an index range (one index of slack either side; j2 <= 1e-6 - no band test - stays in)
+      int ij_lo = 0, ij_hi = g.n_jpos - 1;
+      if (g.jpos_uniform && dt_s > 0.f) {
+        const float flo = (j2_lo - g.jpos0) * g.jpos_inv_step, fhi = (fminf(j2_hi, 1.0e30f) - g.jpos0) * g.jpos_inv_step;
+        ij_lo = (int)fminf(fmaxf(floorf(flo) - 1.f, 0.f), (float)g.n_jpos);
+        ij_hi = (int)fmaxf(fminf(ceilf(fhi) + 1.f, (float)(g.n_jpos - 1)), -1.f);
+        if (g.jpos0 <= 1e-6f) ij_lo = 0;
+      }
+      for (int ij2 = ij_lo + j_first; ij2 <= ij_hi; ij2 += j_step) {
         const double j2 = g.jpos[ij2];
         int lo = 0, hi = g.n_ts - 1;
         if (j2 > 1e-6 && dt_s > 0.f) {

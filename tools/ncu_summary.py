@@ -39,7 +39,7 @@ KEYS = {
     "sm__cycles_elapsed.avg": "sm_cycles_elapsed",
     "sm__cycles_elapsed.avg.per_second": "sm_ghz",
 }
-UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "usecond": 1.0, "msecond": 1e3, "nsecond": 1e-3}
+UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "usecond": 1.0, "msecond": 1e3, "nsecond": 1e-3, "ms": 1e3, "s": 1e6, "second": 1e6}
 
 
 def main():
