@@ -571,18 +571,19 @@ def bench_sweep(ctx: Ctx, args, workload_name="C4") -> dict:
                                  max_total_steps=cfg.max_total_steps)
         pts = float(np.mean([len(np.arange(0.0, T, fop.delta_t)) for T in np.linspace(fop.min_t, fop.max_t, fop.num_t)]))   # samples per candidate
     # the FOP baseline and --sweep-kernel lockstep run the lock-step pipeline (two launches per plan cycle, sub-batches on separate streams);
-    # --sweep-kernel auto (default): the persistent kernel with best-first selection for shards of 64 scenarios and more (measured on
-    # one B200: 800 scenarios 25 - 28 vs 39 ms, 100 scenarios 10.0 vs 10.3 ms), the lock-step pipeline for small batches (8 multi-modal
-    # scenes: 8.3 vs 13 ms).  Best-first sub-batches hold ~200 scenarios each (one launch per sub-batch, each on its own stream):
-    # their CTAs interleave on the SMs and, end to end, the replay of one sub-batch overlaps the upload of the next.
+    # --sweep-kernel auto (default): the persistent kernel with best-first selection for shards of 150 scenarios and more (measured on
+    # one B200: 800 scenarios 28.8 vs 37.4 ms, 400: 18.9 vs 23.8, 200: 12.8 vs 14.7), the lock-step pipeline below (100 scenarios: 10.7
+    # vs 11.5 ms - the sweep ends with its heaviest scenario, whose candidates lock-step spreads over many SMs; 8 multi-modal scenes:
+    # 8.3 vs 13 ms).  Best-first sub-batches hold ~200 scenarios each (one launch per sub-batch, each on its own stream): their CTAs
+    # interleave on the SMs and, end to end, the replay of one sub-batch overlaps the upload of the next.
     sweep_kernel = args.sweep_kernel
     if sweep_kernel == "auto":
-        sweep_kernel = "bestfirst" if len(packed) >= 64 else "lockstep"
+        sweep_kernel = "bestfirst" if len(packed) >= 150 else "lockstep"
     kern = None if (fop is not None or sweep_kernel == "lockstep") else sweep_kernel
     if kern is None:
         k_sub = args.sub_batches if len(packed) >= 16 else 1
     else:
-        k_sub = max(1, min(8, int(round(len(packed) / 200.0))))
+        k_sub = max(1, min(8, int(round(len(packed) / 200.0)))) if len(packed) > 444 else 1
     bt = B.MultiStreamReplay(cfg, device=local, max_scenarios=len(packed), max_cycles=args.cycles, k=k_sub, fop=fop)
     bt.load(packed)
     steps, warmup = max(3, min(args.steps, 10)), 3

@@ -20,6 +20,7 @@ FLAG_FORCE_TILED = 128
 FLAG_LOCKSTEP = 256
 FLAG_PERSISTENT = 512
 FLAG_BEST_FIRST = 2048
+FLAG_SMALL_CTAS = 4096
 FLAG_CHUNKED = 1024
 
 TRAJ_COLUMNS = ("t", "s", "s_d", "s_dd", "s_ddd", "d", "d_d", "d_dd", "d_ddd", "x", "y", "yaw", "ds", "c", "c_d", "c_dd")

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import JsspError, JsspCycleRecord, JsspFopIn, JsspScenarioIn, JsspScenarioResult, FLAG_FORCE_THREAD, FLAG_FORCE_WARP, FLAG_FORCE_GROUP, FLAG_FORCE_TILED, FLAG_LOCKSTEP, FLAG_PERSISTENT, FLAG_CHUNKED, FLAG_BEST_FIRST
+from ._lib import JsspError, JsspCycleRecord, JsspFopIn, JsspScenarioIn, JsspScenarioResult, FLAG_FORCE_THREAD, FLAG_FORCE_WARP, FLAG_FORCE_GROUP, FLAG_FORCE_TILED, FLAG_LOCKSTEP, FLAG_PERSISTENT, FLAG_CHUNKED, FLAG_BEST_FIRST, FLAG_SMALL_CTAS
 from .engine import JsspConfig
 from .frenet import FrenetState, State
 from .geometry import CubicSpline2D
@@ -264,8 +264,9 @@ class BatchReplay:
         """Back to the freshly loaded state without uploading anything (device-to-device)."""
         self._check(self.lib.jssp_batch_reset(self._h, self._n, self.stream), "jssp_batch_reset")
 
-    def run(self, n_cycles: Optional[int] = None, kernel: Optional[str] = None):
-        """Enqueue up to ``n_cycles`` plan cycles per scenario (default: enough for every loaded scenario to finish).  ``kernel``
+    def run(self, n_cycles: Optional[int] = None, kernel: Optional[str] = None, small_ctas: bool = False):
+        """(``small_ctas``: "bestfirst" only - 256-thread CTAs also for few scenarios, for callers running several sub-batches at once.)
+        Enqueue up to ``n_cycles`` plan cycles per scenario (default: enough for every loaded scenario to finish).  ``kernel``
         None / "lockstep" = the lock-step pipeline (two launches per cycle for the whole batch) with its default evaluation
         kernel, "warp" / "thread" / "group" / "tiled" = lock-step with that kernel, "persistent" = the persistent replay kernel
         (one CTA per scenario loops over its own cycles in ONE launch), "bestfirst" = the persistent kernel with best-first selection
@@ -273,6 +274,8 @@ class BatchReplay:
         if n_cycles is None:
             n_cycles = max(min(p.n_cycles, self.C) for p in self._packed)
         flags = {None: 0, "warp": FLAG_FORCE_WARP, "thread": FLAG_FORCE_THREAD, "group": FLAG_FORCE_GROUP, "tiled": FLAG_FORCE_TILED, "lockstep": FLAG_LOCKSTEP, "persistent": FLAG_PERSISTENT, "chunked": FLAG_CHUNKED, "bestfirst": FLAG_BEST_FIRST}[kernel]
+        if small_ctas and kernel == "bestfirst":
+            flags |= FLAG_SMALL_CTAS
         self._check(self.lib.jssp_batch_run(self._h, self._n, int(n_cycles), flags, self.stream), "jssp_batch_run")
         return n_cycles
 
@@ -328,6 +331,11 @@ class MultiStreamReplay:
         self.parts = [BatchReplay(config, device=device, max_scenarios=max(per, 1), max_cycles=max_cycles, **kw) for _ in range(self.k)]
         self.cfg, self.C, self.lib = self.parts[0].cfg, self.parts[0].C, self.parts[0].lib
         self._n = 0
+        self._sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+
+    def _small(self) -> bool:
+        """Best-first sub-batches that together put more than three scenarios on an SM run 256-thread CTAs (see JSSP_FLAG_SMALL_CTAS)."""
+        return self.k > 1 and self._n > 3 * self._sms
 
     def _each(self, fn):
         cur = torch.cuda.current_stream(self.device)
@@ -355,7 +363,7 @@ class MultiStreamReplay:
         self._each(lambda bt: bt.reset())
 
     def run(self, n_cycles: Optional[int] = None, kernel: Optional[str] = None):
-        return max(self._each(lambda bt: bt.run(n_cycles, kernel=kernel)))
+        return max(self._each(lambda bt: bt.run(n_cycles, kernel=kernel, small_ctas=self._small())))
 
     def load_and_run(self, packed: Sequence[PackedScenario], n_cycles: Optional[int] = None, kernel: Optional[str] = None):
         """``load`` + ``run`` sub-batch by sub-batch: the replay of one sub-batch (device) overlaps the upload of the next (host staging +
@@ -369,7 +377,7 @@ class MultiStreamReplay:
                 st.wait_stream(cur)
                 with torch.cuda.stream(st):
                     bt.load(g)
-                    out.append(bt.run(n_cycles, kernel=kernel))
+                    out.append(bt.run(n_cycles, kernel=kernel, small_ctas=self._small()))
         for st in self.streams:
             cur.wait_stream(st)
         return max(out)

@@ -1649,9 +1649,10 @@ int32_t jssp_batch_run(jssp_batch* b, int32_t n_scenarios, int32_t n_cycles, int
   // JSSP_FLAG_PERSISTENT: the persistent replay kernel - one CTA per scenario, every cycle of the call in ONE launch.  Few scenarios
   // (at most one per SM) get 512 threads each, more get 256 so that two CTAs share an SM.
   // JSSP_FLAG_BEST_FIRST on a batch whose every cycle qualifies (select-only slots, w_risk >= 0): the kernel variant without the
-  // exhaustive passes - 512 threads per CTA when every scenario has an SM of its own, else 256-thread CTAs, two per SM
+  // exhaustive passes - 512 threads per CTA (16 warps checking candidates: the sweep ends with its heaviest scenario) up to three
+  // scenarios per SM, 256-thread CTAs, two per SM, above that or when the caller runs several sub-batches at once (JSSP_FLAG_SMALL_CTAS)
   if ((flags & JSSP_FLAG_BEST_FIRST) && !(flags & JSSP_FLAG_LOCKSTEP) && !b->tune.full_walk && b->cfg.w_risk >= 0.0) {
-    int threads = n_scenarios <= b->sm_count ? REPLAY_MAX_THREADS : 256;
+    int threads = (n_scenarios <= 3 * b->sm_count && !(flags & JSSP_FLAG_SMALL_CTAS)) ? REPLAY_MAX_THREADS : 256;
     if (b->tune.seed_threads == 256 || b->tune.seed_threads == 512) threads = b->tune.seed_threads;      // tools/ only
     const int rows = b->max_OMpad > 0 ? max_rows : 0;
     const int bf_keys = b->cfg.max_seeds * b->W;

@@ -111,6 +111,10 @@ typedef struct jssp_cycle_in {
                                     lower bound of their cost (everything but the risk term, which needs no walk) and checked in that order, one
                                     warp per candidate with the lanes over the samples, until no unchecked candidate can cost less than the best
                                     survivor: the selection, its cost and the exported trajectory are those of the exhaustive evaluation */
+#define JSSP_FLAG_SMALL_CTAS 4096 /* with JSSP_FLAG_BEST_FIRST: 256-thread CTAs (two per SM) also for a launch of few scenarios - for callers that run
+                                    several sub-batches concurrently on separate streams.  Default: 512-thread CTAs (one per SM, 16 warps checking
+                                    candidates) up to 3 scenarios per SM, 256-thread CTAs above (measured: 200 scenarios 12.8 vs 18.1 ms, 400
+                                    18.9 vs 20.5 ms, 800 29.7 vs 28.4 ms) */
 #define JSSP_FLAG_NO_CULL 4      /* test every obstacle state instead of the per-block culled lists (same results) */
 
 /* Outputs.  Candidate n = w * n_seeds + k (width-major, jssp.py:106,124-125).  All dev pointers may be NULL.  With

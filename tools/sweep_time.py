@@ -9,7 +9,8 @@ from dlii_jssp_b200 import batch as B, scenario as S
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 800
 cyc = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 kernels = sys.argv[3:] or ["default"]
-packed = [B.pack_scenario(S.synthetic_intersection(i), max_cycles=cyc) for i in range(n)]
+stride = int(os.environ.get("SWEEP_STRIDE", "1"))      # scenario ids 0, stride, 2 * stride, ... (a rank's shard of the 800-scenario sweep)
+packed = [B.pack_scenario(S.synthetic_intersection(i * stride), max_cycles=cyc) for i in range(n)]
 packed = [p for p in packed if p.initial_end == -1]
 cfg = J.JsspConfig(max_seeds=int(os.environ.get("SWEEP_MAX_SEEDS", "1024")), max_knots=max(len(p.knot_s) for p in packed), max_obstacle_modes=max(1, max(p.state.shape[0] for p in packed)),
                    max_total_steps=max(p.state.shape[2] for p in packed))
