@@ -578,7 +578,7 @@ def bench_sweep(ctx: Ctx, args, workload_name="C4") -> dict:
     # interleave on the SMs and, end to end, the replay of one sub-batch overlaps the upload of the next.
     sweep_kernel = args.sweep_kernel
     if sweep_kernel == "auto":
-        sweep_kernel = "bestfirst" if len(packed) >= 150 else "lockstep"
+        sweep_kernel = B.auto_pipeline(len(packed)) or "lockstep"
     kern = None if (fop is not None or sweep_kernel == "lockstep") else sweep_kernel
     if kern is None:
         k_sub = args.sub_batches if len(packed) >= 16 else 1

@@ -270,9 +270,12 @@ class BatchReplay:
         None / "lockstep" = the lock-step pipeline (two launches per cycle for the whole batch) with its default evaluation
         kernel, "warp" / "thread" / "group" / "tiled" = lock-step with that kernel, "persistent" = the persistent replay kernel
         (one CTA per scenario loops over its own cycles in ONE launch), "bestfirst" = the persistent kernel with best-first selection
-        (candidates checked in the order of a lower bound of their cost until none left can win).  Same results.  Asynchronous."""
+        (candidates checked in the order of a lower bound of their cost until none left can win), "auto" = the pipeline measured
+        fastest for this many scenarios (``auto_pipeline``).  Same results.  Asynchronous."""
         if n_cycles is None:
             n_cycles = max(min(p.n_cycles, self.C) for p in self._packed)
+        if kernel == "auto":
+            kernel = auto_pipeline(self._n, fop=self.fop is not None)
         flags = {None: 0, "warp": FLAG_FORCE_WARP, "thread": FLAG_FORCE_THREAD, "group": FLAG_FORCE_GROUP, "tiled": FLAG_FORCE_TILED, "lockstep": FLAG_LOCKSTEP, "persistent": FLAG_PERSISTENT, "chunked": FLAG_CHUNKED, "bestfirst": FLAG_BEST_FIRST}[kernel]
         if small_ctas and kernel == "bestfirst":
             flags |= FLAG_SMALL_CTAS
@@ -314,6 +317,14 @@ class BatchReplay:
                 rr.best_idx, rr.n_candidates, rr.ego_rows = bi_all[s, :n], nc_all[s, :n], rows
             out.append(rr)
         return out
+
+
+def auto_pipeline(n_scenarios: int, fop: bool = False) -> Optional[str]:
+    """The replay pipeline measured fastest on a B200 for ``n_scenarios`` on one GPU: "bestfirst" (persistent kernel with best-first
+    selection) from 150 scenarios on - 800: 28.9 vs 37.4 ms, 400: 19.1 vs 23.8 ms, 200: 14.1 vs 14.7 ms - and None (the lock-step
+    pipeline) below, where a sweep ends with its heaviest scenario and lock-step spreads that scenario's candidates over many SMs
+    (100: 10.6 vs 12.6 ms).  The FOP baseline always replays in lock-step."""
+    return "bestfirst" if (not fop and n_scenarios >= 150) else None
 
 
 class MultiStreamReplay:

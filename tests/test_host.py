@@ -26,6 +26,24 @@ def test_library_exports_every_declared_symbol():
     assert b"no CPU fallback" in lib.jssp_strerror(-6)
 
 
+def test_flag_constants_match_header():
+    """Every JSSP_FLAG_* of include/jssp_b200.h has the same value in the ctypes binding, the flags are distinct bits, and the replay
+    pipelines a caller can name map onto them."""
+    header = open(os.path.join(ROOT, "include", "jssp_b200.h")).read()
+    flags = {m[0]: int(m[1]) for m in re.findall(r"#define\s+JSSP_FLAG_([A-Z_]+)\s+(\d+)", header)}
+    assert len(flags) >= 13
+    for name, value in flags.items():
+        assert getattr(_lib, "FLAG_" + name) == value, name
+        assert value & (value - 1) == 0, name                    # one bit each
+    assert len(set(flags.values())) == len(flags)
+    import inspect
+    from dlii_jssp_b200 import batch
+    src = inspect.getsource(batch.BatchReplay.run)
+    for kernel in ("lockstep", "persistent", "bestfirst", "tiled", "chunked", "auto"):
+        assert f'"{kernel}"' in src
+    assert batch.auto_pipeline(800) == "bestfirst" and batch.auto_pipeline(100) is None and batch.auto_pipeline(800, fop=True) is None
+
+
 def test_struct_layouts_match_header():
     lib = _lib.load()
     cfg = _lib.JsspConfigC()
