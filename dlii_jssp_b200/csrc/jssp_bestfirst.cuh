@@ -73,31 +73,48 @@ __device__ __forceinline__ void bestfirst_keys(const EvalParams& p, const BlockT
     if (k < Ns) {
       double seed[10];
       load_seed_row(seed, seeds + (size_t)k * 10);
-      // speed and acceleration at the segment ends (the expressions of lon_profile_init); the arc length enters the bound at both
-      // ends of the horizon only: s(0) = s0, s(T) by the lane that owns the last sample
+      // speed and acceleration at the segment ends (the expressions of lon_profile_init); the arc length enters the bound only as the
+      // displacement s(T) - s(0)
       const double j1 = seed[0], t1 = seed[1], j2 = seed[2], t2 = seed[3], j3 = seed[4], t3 = seed[5], j4 = seed[6], t4 = seed[7], j5 = seed[8];
       const double v1 = vt_by_jt(p.v0, p.a0, j1, t1), a1 = at_by_jt(p.a0, j1, t1);
       const double v2 = vt_by_jt(v1, a1, j2, t2), a2 = at_by_jt(a1, j2, t2);
       const double v3 = vt_by_jt(v2, a2, j3, t3), a3 = at_by_jt(a2, j3, t3);
       const double v4 = vt_by_jt(v3, a3, j4, t4), a4 = at_by_jt(a3, j4, t4);
       const double b1 = t1 - 1e-9, b2 = t1 + t2 + 1e-9, b3 = t1 + t2 + t3 + 1e-9, b4 = t1 + t2 + t3 + t4 + 1e-9;
-      for (int i = q; i < p.P; i += L) {
-        const double t = tb.time[i];
-        double vb, ab, jb, dt;                       // lon_eval's branch chain
-        if (t < b1) { vb = p.v0; ab = p.a0; jb = j1; dt = t; }
-        else if (t < b2) { vb = v1; ab = a1; jb = j2; dt = t - t1; }
-        else if (t < b3) { vb = v2; ab = a2; jb = j3; dt = t - t1 - t2; }
-        else if (t < b4) { vb = v3; ab = a3; jb = j4; dt = t - t1 - t2 - t3; }
-        else { vb = v4; ab = a4; jb = j5; dt = t - t1 - t2 - t3 - t4; }
-        const double sd = vt_by_jt(vb, ab, jb, dt), sdd = at_by_jt(ab, jb, dt);
-        const double ea = fmax(fabs(sdd) - p.thr_lon_a, 0.0), ej = fmax(fabs(jb) - p.thr_lon_j, 0.0), ev = (p.vmax - sd) * p.inv_vmax;
-        sa = sa + ea * ea; sj = sj + ej * ej; sv = sv + ev * ev;
-        if (i == 0) sf = p.s0;
-        if (i == p.P - 1) {
+      // this lane's samples q, q + L, ... segment by segment (lon_eval's branch chain as five loops: speed, acceleration and jerk of a
+      // segment stay in registers, the jerk term is a constant of the segment)
+      int i = q;
+#define BF_SEGMENT(VB, AB, JB, OFF, COND)                                                                                  \
+      {                                                                                                                  \
+        const double ejs_ = fmax(fabs(JB) - p.thr_lon_j, 0.0), ej2_ = ejs_ * ejs_;                                       \
+        while (i < p.P && (COND)) {                                                                                     \
+          const double dt_ = tb.time[i] - (OFF);                                                                        \
+          const double sd_ = vt_by_jt(VB, AB, JB, dt_), sdd_ = at_by_jt(AB, JB, dt_);                                   \
+          const double ea_ = fmax(fabs(sdd_) - p.thr_lon_a, 0.0), ev_ = (p.vmax - sd_) * p.inv_vmax;                    \
+          sa = sa + ea_ * ea_; sj = sj + ej2_; sv = sv + ev_ * ev_;                                                      \
+          i += L;                                                                                                       \
+        }                                                                                                               \
+      }
+      BF_SEGMENT(p.v0, p.a0, j1, 0.0, tb.time[i] < b1)
+      BF_SEGMENT(v1, a1, j2, t1, tb.time[i] < b2)
+      BF_SEGMENT(v2, a2, j3, t1 + t2, tb.time[i] < b3)
+      BF_SEGMENT(v3, a3, j4, t1 + t2 + t3, tb.time[i] < b4)
+      BF_SEGMENT(v4, a4, j5, t1 + t2 + t3 + t4, true)
+#undef BF_SEGMENT
+      // s(T) - s(0): the sum of the five segments' displacements (the arc length is continuous across the segment boundaries, so the
+      // branch the reference takes at a boundary does not matter to the bound); one lane per seed
+      if (q == 0) {
+        const double t5 = tb.time[p.P - 1] - t1 - t2 - t3 - t4;
+        if (t5 >= 0.0) {
+          sl = (p.v0 * t1 + 0.5 * p.a0 * t1 * t1 + (1 / 6.0) * j1 * t1 * t1 * t1) + (v1 * t2 + 0.5 * a1 * t2 * t2 + (1 / 6.0) * j2 * t2 * t2 * t2) +
+               (v2 * t3 + 0.5 * a2 * t3 * t3 + (1 / 6.0) * j3 * t3 * t3 * t3) + (v3 * t4 + 0.5 * a3 * t4 * t4 + (1 / 6.0) * j4 * t4 * t4 * t4) +
+               (v4 * t5 + 0.5 * a4 * t5 * t5 + (1 / 6.0) * j5 * t5 * t5 * t5);
+        } else {                                       // segments longer than the horizon: the reference's own expression
           LonProfile lp;
           lon_profile_init(lp, seed, p.s0, p.v0, p.a0);
           double d1, d2, d3;
-          lon_eval(lp, p.s0, p.v0, p.a0, t, sl, d1, d2, d3);
+          lon_eval(lp, p.s0, p.v0, p.a0, tb.time[p.P - 1], sl, d1, d2, d3);
+          sl = sl - p.s0;
         }
       }
     }
