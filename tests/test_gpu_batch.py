@@ -152,6 +152,12 @@ def test_sub_batches_on_separate_streams_replay_identically(scenario_fixture):
             assert b.best_idx.tolist() == a.best_idx
         ms.load(packed[:1]); ms.run(20)                      # fewer scenarios than sub-batches
         _same(ms.results()[0], want[0])
+        # upload and replay sub-batch by sub-batch (the replay of one overlaps the upload of the next), every pipeline
+        for kernel in (None, "bestfirst", "auto"):
+            ms.load_and_run(packed, 20, kernel=kernel)
+            for a, b in zip(want, ms.results()):
+                assert a.name == b.name
+                _same(b, a)
         ms.close()
     one.close()
 
