@@ -85,6 +85,34 @@ def test_loop_form_agrees_with_vectorised_oracle():
     assert a["best"] == b["best"]
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(p_min=0.25, w_risk=1.5), dict(O_=24, M=3, seed=9, p_min=0.4, w_risk=0.7)])
+def test_best_first_order_selects_the_exhaustive_argmin(kw):
+    """The rule behind the replay kernel's best-first selection (csrc/jssp_bestfirst.cuh), stated on the oracle: the cost without the
+    risk term needs no Frenet->Cartesian walk and never exceeds the cost (w_risk >= 0, risk >= 0); checking candidates in the order
+    of that bound and stopping when the next bound exceeds the best surviving (cost, index) returns exactly the argmin over the
+    survivors of the filter chain (jerk_space_sampling_planner.py:311-327) - without looking at the other candidates."""
+    cfg_kw = {k: v for k, v in kw.items() if k in ("p_min", "w_risk")}
+    cyc, cfg, spline, obs = _cycle(**{k: v for k, v in kw.items() if k not in cfg_kw}, **cfg_kw)
+    with np.errstate(all="ignore"):
+        r = O.plan_cycle(cfg, spline, cyc.frenet0, obs, 0, cyc.final_time_step, seeds=cyc.seeds, targets=cyc.targets)
+        bound = O.cost_total(r["s"], r["s_d"], r["s_dd"], r["s_ddd"], r["d"], r["d_d"], r["d_dd"], r["d_ddd"], cfg, risk=None)
+    fin = np.isfinite(r["cost"])
+    assert (bound[fin] <= r["cost"][fin]).all()
+    if kw.get("O_", 0) >= 24:
+        assert (r["risk"] > 0).any()                       # soft hits are in play: some bounds are strictly below their costs
+    ok = r["feasible"] & ~r["collision"] & fin
+    order = np.lexsort((np.arange(r["n"]), bound))         # (bound, index)
+    best, best_cost, checked = -1, np.inf, 0
+    for n in order:
+        if best >= 0 and bound[n] > best_cost:
+            break                                          # no unchecked candidate can cost less
+        checked += 1
+        if ok[n] and (r["cost"][n] < best_cost or (r["cost"][n] == best_cost and n < best)):
+            best, best_cost = int(n), float(r["cost"][n])
+    assert best == r["best"]
+    assert r["best"] < 0 or checked < r["n"]               # and it got there without checking everything
+
+
 def test_reference_edge_semantics():
     """Truncation, 1-point / 0-point trajectories, stopped car (ds == 0 -> nan passes), reversing car (|c| = pi/ds fails)."""
     cyc, cfg, spline, obs = _cycle()
